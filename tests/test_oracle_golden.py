@@ -1,0 +1,86 @@
+"""The oracle against the committed golden vectors (generated from the reference
+itself by oracle/make_goldens.py) and the hand-checkable TD known-answer test
+of SURVEY.md 8c.  CPU only."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import qstep
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _sample(t, n=64):
+    f = t.detach().reshape(-1)
+    step = max(1, f.numel() // n)
+    return f[::step][:n].double().numpy()
+
+
+@pytest.mark.parametrize("rbn", [1, 0])
+def test_oracle_reproduces_reference_goldens(rbn):
+    torch.set_num_threads(os.cpu_count() or 1)
+    g = np.load(os.path.join(GOLD, f"step_b8_bn{rbn}.npz"))
+    B = int(g["meta/B"])
+    tr = qstep.OracleTrainer(qstep.init_state(seed=4, randomize_bn=bool(rbn)))
+    for it in range(int(g["meta/steps"]) if rbn else 1):
+        loss, grads, aux = tr.step(qstep.synthetic_batch(B, seed=1 + it))
+        p = f"step{it}/"
+        assert abs(loss.item() - float(g[p + "loss"])) <= 2e-6 * abs(float(g[p + "loss"]))
+        np.testing.assert_allclose(aux["q_s"].numpy(), g[p + "q_s"], atol=5e-6)
+        np.testing.assert_allclose(aux["q_next_target"].numpy(), g[p + "q_next_target"], atol=5e-6)
+        assert (aux["best"].numpy() == g[p + "best"]).all()      # integer: bit-exact
+        np.testing.assert_allclose(aux["y"].numpy(), g[p + "y"], atol=5e-6)
+        for n in tr.names:
+            ref_l2 = float(g[p + f"grad/{n}/l2"])
+            assert abs(grads[n].double().norm().item() - ref_l2) <= 1e-4 * ref_l2 + 1e-12, n
+            np.testing.assert_allclose(_sample(grads[n]), g[p + f"grad/{n}/sample"],
+                                       rtol=1e-3, atol=1e-5 * ref_l2 + 1e-12, err_msg=n)
+            np.testing.assert_allclose(_sample(tr.sd[n]), g[p + f"param/{n}/sample"],
+                                       rtol=1e-5, atol=1e-7, err_msg=n)
+        if it == 0:
+            np.testing.assert_allclose(grads["top.4.weight"].numpy(),
+                                       g[p + "gradfull/top.4.weight"], rtol=1e-4, atol=1e-8)
+
+
+def test_td_known_answer():
+    cfg = qstep.StepConfig()
+    act = torch.tensor([2, 0])
+    rew = torch.tensor([[0, 1, 0, 0, 0], [0, 0, 0, 0, 1]])
+    qs = torch.tensor([[[.1, .2, .3], [.5, .4, .3], [0, 0, 0], [1.5, -1, .2], [.9, .8, .7]],
+                       [[-.2, .1, 0], [.3, .3, .1], [.6, .2, .9], [.05, .15, .25], [.4, .4, .4]]],
+                      requires_grad=True)
+    qo = torch.tensor([[[.1, .9, .2], [.7, .7, .1], [0, .1, .2], [.3, .2, .1], [.5, .6, .4]],
+                       [[.2, .1, .3], [.9, .1, .1], [.1, .8, .8], [0, 0, 0], [-1., -2, -3]]])
+    qt = torch.tensor([[[.4, .5, .6], [.2, .9, .3], [1.5, 1.6, 1.7], [-.5, .1, .2], [.3, .2, .1]],
+                       [[.7, .8, .9], [.25, .5, .75], [.1, .3, .2], [.6, .1, .1], [.9, .1, .1]]])
+    loss, aux = qstep.td_loss(qs, qo, qt, act, rew, rew, torch.ones_like(rew), cfg)
+    assert aux["best"].tolist() == [[1, 0, 2, 0, 1], [2, 0, 1, 0, 0]]
+    np.testing.assert_allclose(aux["y"].numpy(),
+                               [[.495, 1, 1, 0, .198], [.891, .2475, .297, .594, 1]], atol=1e-6)
+    assert abs(loss.item() - 0.188040555) < 1e-7
+    loss.backward()
+    exp = torch.zeros(2, 5, 3)
+    exp[0, :, 2] = torch.tensor([-.0195, -.07, -.1, .02, .0502])
+    exp[1, :, 0] = torch.tensor([-.1091, .00525, .0303, -.0544, -.06])
+    np.testing.assert_allclose(qs.grad.numpy(), exp.numpy(), atol=1e-6)
+    np.testing.assert_allclose(
+        qstep.td_grad_closed_form(qs.detach(), act, aux["y"], torch.ones_like(rew), cfg).numpy(),
+        exp.numpy(), atol=1e-6)
+
+
+def test_batched_2b_forward_is_identical():
+    """eval-mode BN => one 2B forward over cat(s, s') equals two B forwards."""
+    sd = qstep.init_state(seed=4, randomize_bn=True)
+    b = qstep.synthetic_batch(2, seed=3)
+    with torch.no_grad():
+        both = qstep.q_forward(sd, torch.cat([b[0], b[1]]))
+        sep = torch.cat([qstep.q_forward(sd, b[0]), qstep.q_forward(sd, b[1])])
+    assert torch.allclose(both, sep, atol=1e-6)
+
+
+def test_bad_shape_raises():
+    sd = qstep.init_state(seed=4)
+    with pytest.raises(Exception, match="bad shape"):
+        qstep.q_forward(sd, torch.zeros(1, 4, 3, 224, 224))
