@@ -1,0 +1,198 @@
+/* vdqn.h -- C ABI of the B200-native Q-learning hot path (libvdqn.so).
+ *
+ * The reference (uiuc-robovision/video-dqn) has NO native code and no FFI: every FLOP of
+ * its training step is dispatched by PyTorch to cuDNN/cuBLAS/ATen.  The entry points below
+ * are therefore the boundary a maintainer would bind in place of those ATen calls; each one
+ * names the reference call site (file:line, relative to the reference root) whose work it
+ * replaces.  All functions:
+ *   - take plain pointers / sizes only (device pointers unless stated), no torch types;
+ *   - enqueue work on the caller's stream (`stream` is a cudaStream_t passed as void*),
+ *     never synchronise, never allocate device memory;
+ *   - return VDQN_OK (0) or a negative error code; `vdqn_last_error()` returns a
+ *     thread-local message.  There is no CPU fallback.
+ * Activations are NHWC bf16; accumulation is fp32.
+ */
+#ifndef VDQN_H_
+#define VDQN_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VDQN_OK 0
+#define VDQN_ERR_ARG (-1)
+#define VDQN_ERR_SHAPE (-2)
+#define VDQN_ERR_CUDA (-3)
+#define VDQN_ERR_DRIVER (-4)
+
+#define VDQN_ABI_VERSION 1
+
+/* conv epilogue flags */
+#define VDQN_EPI_RELU 1     /* out = max(v, 0) */
+#define VDQN_EPI_OUT_F32 2  /* store fp32 instead of bf16 */
+
+const char* vdqn_last_error(void);
+int vdqn_abi_version(void);
+/* Resolve driver entry points (tensor-map encoders), query the device.  Idempotent. */
+int vdqn_init(int device);
+int vdqn_num_sms(void);
+
+/* ---------------------------------------------------------------------------------------
+ * Implicit-GEMM convolution, forward and data-gradient (tcgen05 + TMA im2col).
+ * Replaces: F.conv2d + eval-mode batch_norm (+ residual add) (+ relu) of
+ *   archs/HabitatDQNMultiAction.py:49-51 (self.features(...) = torchvision ResNet-18
+ *   BasicBlock.forward, torchvision/models/resnet.py:89-105) and features[8] (:30),
+ *   and, for the backward pass, the cudnn_convolution_backward_input + threshold_backward +
+ *   native_batch_norm_backward(d beta) launched by loss.backward() (train_q_network.py:226).
+ *
+ *   v[m, co] = sum_{r,s,ci} x[n, p*stride + r*dil - pad_lo, q*stride + s*dil - pad_lo, ci]
+ *                           * w[co, r, s, ci]          (m = (n,p,q) row-major)
+ *   v += shift[co]; v += residual[m, co]; if RELU v = max(v,0); if mask_src: v = mask_src[m,co] > 0 ? v : 0
+ *   out[opix(m), co] = v;  colsum[co] += sum_m v (rounded to the stored precision)
+ * BN is folded: w = gamma*rstd*W, shift = beta - mean*gamma*rstd (see vdqn_weight_prep).
+ * A data-gradient is the same computation on dY with the spatially flipped, channel-
+ * transposed filter and pad_lo = R-1-pad.
+ */
+typedef struct vdqn_conv_desc {
+  const void* x;       /* bf16 [N][H][W][Cin] */
+  const void* w;       /* bf16 [Cout][R][S][Cin] */
+  void* out;           /* bf16 (or fp32) [opix][ldc] */
+  void* out2;          /* optional bf16 second copy, written zero-dilated (stride-2 scatter) */
+  const float* shift;  /* [Cout] or NULL */
+  const void* residual; /* bf16 [M][ldr] or NULL */
+  const void* mask_src; /* bf16 [M][ldm] or NULL */
+  float* colsum;       /* [Cout], accumulated with atomics, or NULL */
+  int32_t N, H, W, Cin, Cout, R, S;
+  int32_t stride, dil, pad_lo, pad_hi;
+  int32_t ldc, ldr, ldm, out2_ld;
+  int32_t out_scatter; /* 1: opix = m; 2: opix = (n*2Ho + 2p)*2Wo + 2q */
+  int32_t flags;       /* VDQN_EPI_* */
+  int32_t tile_n;      /* 0 = auto (64/128/256) */
+  int32_t max_ctas;    /* 0 = one per SM */
+} vdqn_conv_desc;
+int vdqn_conv_gemm(const vdqn_conv_desc* d, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Convolution weight gradient (tcgen05, both operands MN-major, split over pixels).
+ * Replaces: cudnn_convolution_backward_weight launched by loss.backward()
+ *   (train_q_network.py:226) for every Conv2d of the Q-network.
+ *   part[split][co][(r,s,ci)] = sum_{m in split} dy[m, co] * x[n, p*stride + r*dil - pad_lo, ..., ci]
+ */
+typedef struct vdqn_wgrad_desc {
+  const void* x;   /* bf16 [N][H][W][Cin] */
+  const void* dy;  /* bf16 [M][ldy], M = N*Ho*Wo */
+  float* part;     /* fp32 [splits][Cout][R*S*Cin] */
+  int32_t N, H, W, Cin, Cout, R, S;
+  int32_t stride, dil, pad_lo, pad_hi;
+  int32_t ldy;
+  int32_t splits;  /* number of pixel-range partitions (>=1) */
+  int32_t max_ctas;
+} vdqn_wgrad_desc;
+int vdqn_conv_wgrad(const vdqn_wgrad_desc* d, void* stream);
+
+/* Reduce the split partials and turn them into the reference's parameter gradients:
+ *   g = sum_split part;  dW[co,ci,r,s] = scale[co] * g[co,(r,s,ci)]   (torch OIHW layout, fp32)
+ *   dgamma[co] = rstd[co] * (sum_k W[co,k] * g[co,k] - mean[co] * dbeta[co])
+ * (native_batch_norm_backward in eval mode)  `kmap` selects how the
+ * GEMM-K index maps to (ci,r,s): 0 = (r,s,ci) with ci < Cin; 1 = space-to-depth stem
+ * (4x4 taps x 16 packed channels -> 7x7 x 3). */
+typedef struct vdqn_wgrad_fin_desc {
+  const float* part;   /* [splits][Cout][K] */
+  const float* w;      /* fp32 master weights, OIHW */
+  const float* gamma;  /* BN weight or NULL (no BN: scale = 1) */
+  const float* var;    /* running_var */
+  const float* mean;   /* running_mean */
+  const float* dbeta;  /* [Cout] column sums of dy, or NULL */
+  float* dw;           /* fp32 OIHW */
+  float* dgamma;       /* [Cout] or NULL */
+  int32_t splits, Cout, Cin, R, S, K, kmap;
+  float eps;
+} vdqn_wgrad_fin_desc;
+int vdqn_wgrad_finalize(const vdqn_wgrad_fin_desc* d, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * fp32 master weights -> bf16 GEMM operands with BN folded in.
+ * Replaces nothing in the reference (it keeps fp32 weights and runs BN as a separate op,
+ * torch native_batch_norm(training=False)); it is the precision/layout boundary of this build.
+ *   w_fwd[co][r][s][ci]   = bf16(scale[co] * W[co][ci][r][s])
+ *   w_dgrad[ci][R-1-r][S-1-s][co] = same value (flipped + transposed, for the data gradient)
+ *   shift[co] = beta[co] - mean[co]*scale[co]   (or the conv bias when gamma == NULL)
+ * kmap as in vdqn_wgrad_finalize (1 = stem space-to-depth packing; w_dgrad unused).
+ */
+typedef struct vdqn_wprep_desc {
+  const float* w;     /* OIHW fp32 */
+  const float* gamma; const float* beta; const float* mean; const float* var; /* NULL if no BN */
+  const float* bias;  /* conv bias or NULL */
+  void* w_fwd;        /* bf16 [Cout][K] */
+  void* w_dgrad;      /* bf16 [Cin][R*S*Cout] or NULL */
+  float* shift;       /* [Cout] */
+  int32_t Cout, Cin, R, S, K, kmap;
+  float eps;
+} vdqn_wprep_desc;
+int vdqn_weight_prep(const vdqn_wprep_desc* d, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Input staging: NCHW fp32 (dataloaders/q_learning_real.py:75-76 output) or uint8 HWC
+ * (util/torch.py:26-36 `to_imgnet` fused) -> space-to-depth NHWC bf16 [N][H/2][W/2][16]
+ * with channel (ph*2+pw)*3 + c, channels 12..15 zero.  */
+int vdqn_stem_pack_f32(const float* x_nchw, void* out, int32_t N, int32_t H, int32_t W, void* stream);
+int vdqn_stem_pack_u8(const uint8_t* x_nhwc, void* out, int32_t N, int32_t H, int32_t W, void* stream);
+
+/* max_pool2d(3, 2, 1) on NHWC bf16 (torchvision resnet.maxpool); idx (uint8 window slot 0..8)
+ * may be NULL for inference.  Backward scatters dy to the arg-max and applies the stem ReLU mask. */
+int vdqn_maxpool_fwd(const void* x, void* y, uint8_t* idx, int32_t N, int32_t H, int32_t W, int32_t C, void* stream);
+int vdqn_maxpool_bwd(const void* dy, const uint8_t* idx, const void* x, void* dx, float* colsum,
+                     int32_t N, int32_t H, int32_t W, int32_t C, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Q-head MLP in fp32 (archs/HabitatDQNMultiAction.py:31,53: Linear 1600-512-256-15 + ReLU).
+ *   y[b,o] = act(sum_k x[b,k] * w[o,k] + bias[o])
+ *   bwd:  dx[b,k] = sum_o dy[b,o] w[o,k];  dw[o,k] = sum_b dy[b,o] x[b,k];  db[o] = sum_b dy[b,o]
+ *   (dy is pre-masked by the caller's activation: vdqn_linear_bwd applies `y > 0` when relu != 0) */
+int vdqn_linear_fwd(const float* x, const float* w, const float* bias, float* y,
+                    int32_t B, int32_t K, int32_t O, int32_t relu, void* stream);
+int vdqn_linear_bwd(const float* x, const float* w, const float* y, float* dy /* overwritten: masked */,
+                    float* dx, float* dw, float* db,
+                    int32_t B, int32_t K, int32_t O, int32_t relu, void* stream);
+/* head conv output bf16 [B][P][C] (NHWC) <-> fp32 [B][C*P] (torch Flatten order); the backward
+ * also applies the head ReLU mask and accumulates the conv-bias gradient. */
+int vdqn_head_flatten_fwd(const void* h_nhwc, float* flat, int32_t B, int32_t P, int32_t C, void* stream);
+int vdqn_head_flatten_bwd(const float* dflat, const void* h_nhwc, void* dh_nhwc, float* dbias,
+                          int32_t B, int32_t P, int32_t C, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Fused TD epilogue: replaces the ~24 ATen launches of process_batch
+ * (train_q_network.py:134-180): repeat/gather/argmax/gather/detach/mul/add/clamp/sub/pow/mean
+ * and their backward.  q_* are fp32 [B][C][A]; act int64 [B]; rew/term/valid int64 [B][C].
+ *   a* = argmax_a q_sel[b,c,:] (first max), q_sel = q_next_online if double_dqn else q_next_target
+ *   y  = rew + gamma * q_next_target[b,c,a*] * (1 - term)   (linear: rew + (q - 0.1))
+ *   y  = clamp(y, 0, 1) if clip_rect;  l = 0.5 (q_s[b,c,act[b]] - y)^2 * (valid if use_valid)
+ *   loss_sum += sum l   (caller divides by B*C*world or passes inv_count);  dq[b,c,a] = (q_b - y)*mask*inv_count on a == act[b]
+ * loss_out[0] accumulates sum(l)*inv_count with atomics: zero it first. best/y_out optional. */
+typedef struct vdqn_td_desc {
+  const float* q_s; const float* q_next_online; const float* q_next_target;
+  const int64_t* act; const int64_t* rew; const int64_t* term; const int64_t* valid;
+  float* dq; float* loss_out; int64_t* best_out; float* y_out;
+  int32_t B, C, A;
+  float gamma; float inv_count;
+  int32_t double_dqn, clip_rect, linear, use_valid;
+} vdqn_td_desc;
+int vdqn_td_epilogue(const vdqn_td_desc* d, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Fused multi-tensor Adam (+ optional hard target-network sync in the same pass).
+ * Replaces optim.Adam.step (train_q_network.py:124,227; ~550 launches under torch 1.3.1)
+ * and target_net.load_state_dict(model.state_dict()) (:215-216).
+ * p, g, m, v are flat fp32 arenas of n elements; grad_scale multiplies g (1/world for DDP).
+ *   m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;  p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
+ * if target != NULL: target[i] = p_new[i]. */
+int vdqn_adam_fused(float* p, const float* g, float* m, float* v, float* target, int64_t n,
+                    float lr, float beta1, float beta2, float eps, int32_t step, float grad_scale,
+                    void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VDQN_H_ */

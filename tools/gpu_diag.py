@@ -1,0 +1,498 @@
+"""Kernel-by-kernel diagnostics on a real B200 (run under gpurun).  Every case runs in its own
+subprocess with a timeout so a trapped / wedged kernel cannot take the other cases with it.
+The checker is torch on the same GPU in fp32 over the same bf16-rounded operands.
+
+    python tools/gpu_diag.py [--only substr] [--out gpurun_out/diag.json]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+CASES = {}
+
+
+def case(fn):
+    CASES[fn.__name__] = fn
+    return fn
+
+
+def _imports():
+    import torch
+    import torch.nn.functional as F
+    from video_dqn_b200 import ops
+    return torch, F, ops
+
+
+def _report(name, out, ref, tol, extra=""):
+    import torch
+    out = out.float(); ref = ref.float()
+    err = (out - ref).abs()
+    denom = ref.abs().max().item() + 1e-12
+    rel = err.max().item() / denom
+    bad = (err > tol * denom).float().mean().item()
+    ok = bool(rel <= tol) and bool(torch.isfinite(out).all())
+    print(json.dumps({"case": name, "ok": ok, "max_rel": rel, "frac_bad": bad,
+                      "ref_max": denom, "extra": extra}))
+    if not ok:
+        o2 = out.reshape(-1, out.shape[-1]); r2 = ref.reshape(-1, ref.shape[-1])
+        e2 = (o2 - r2).abs() > tol * denom
+        print("  rows with errors:", e2.any(1).nonzero().flatten()[:40].tolist())
+        print("  cols with errors:", e2.any(0).nonzero().flatten()[:40].tolist())
+        print("  out[0:4,0:8]", o2[:4, :8].tolist())
+        print("  ref[0:4,0:8]", r2[:4, :8].tolist())
+    return ok
+
+
+def _conv_case(name, N, H, W, Cin, Cout, R, stride, pad, seed=0, tile_n=0, **epi):
+    torch, F, ops = _imports()
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    x = torch.randn(N, H, W, Cin, device="cuda", generator=g).to(torch.bfloat16)
+    w = (torch.randn(Cout, R, R, Cin, device="cuda", generator=g) / (R * R * Cin) ** 0.5).to(torch.bfloat16)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), None, stride, pad)
+    ref = ref.permute(0, 2, 3, 1).contiguous()
+    kw = {}
+    if epi.get("shift"):
+        kw["shift"] = torch.randn(Cout, device="cuda", generator=g)
+        ref = ref + kw["shift"]
+    if epi.get("residual"):
+        kw["residual"] = torch.randn(ref.shape, device="cuda", generator=g).to(torch.bfloat16)
+        ref = ref + kw["residual"].float()
+    if epi.get("relu"):
+        kw["relu"] = True
+        ref = ref.relu()
+    if epi.get("mask"):
+        kw["mask_src"] = torch.randn(ref.shape, device="cuda", generator=g).to(torch.bfloat16)
+        ref = ref * (kw["mask_src"].float() > 0)
+    if epi.get("colsum"):
+        kw["colsum"] = torch.zeros(Cout, device="cuda")
+    if epi.get("f32"):
+        kw["out_f32"] = True
+    if epi.get("scatter"):
+        kw["out_scatter"] = 2
+    if epi.get("out2"):
+        kw["out2"] = torch.zeros(N, 2 * ref.shape[1], 2 * ref.shape[2], Cout, device="cuda", dtype=torch.bfloat16)
+    out = ops.conv_gemm(x, w, stride, pad, tile_n=tile_n, **kw)
+    torch.cuda.synchronize()
+    ok = True
+    if epi.get("scatter"):
+        full = out
+        out = full[:, ::2, ::2, :]
+        rest = full.float().abs().sum() - out.float().abs().sum()
+        ok &= abs(rest.item()) < 1e-3
+    ok &= _report(name, out, ref, 2e-2)
+    if epi.get("out2"):
+        ok &= _report(name + ":out2", kw["out2"][:, ::2, ::2, :], ref, 2e-2)
+    if epi.get("colsum"):
+        cs_ref = out.float().reshape(-1, Cout).sum(0)
+        ok &= _report(name + ":colsum", kw["colsum"][None], cs_ref[None], 2e-3)
+    return ok
+
+
+@case
+def gemm_1x1_min():       # one tile, one k-block: UMMA descriptors + TMEM epilogue only
+    return _conv_case("gemm_1x1_min", 2, 8, 8, 64, 64, 1, 1, 0)
+
+
+@case
+def gemm_1x1_k256_n128():
+    return _conv_case("gemm_1x1_k256_n128", 4, 8, 8, 256, 128, 1, 1, 0)
+
+
+@case
+def gemm_1x1_n256_tail():
+    return _conv_case("gemm_1x1_n256_tail", 3, 7, 7, 128, 512, 1, 1, 0)
+
+
+@case
+def im2col_tap_probe():
+    """w = delta at tap (r0,s0): out must be the shifted input -> isolates im2col addressing."""
+    torch, F, ops = _imports()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    N, H, W, Cc = 2, 10, 12, 64
+    x = torch.randn(N, H, W, Cc, device="cuda", generator=g).to(torch.bfloat16)
+    ok = True
+    for r0 in range(3):
+        for s0 in range(3):
+            w = torch.zeros(Cc, 3, 3, Cc, device="cuda")
+            w[torch.arange(Cc), r0, s0, torch.arange(Cc)] = 1
+            w = w.to(torch.bfloat16)
+            out = ops.conv_gemm(x, w, 1, 1)
+            torch.cuda.synchronize()
+            ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), None, 1, 1)
+            ok &= _report(f"im2col_tap_probe[{r0},{s0}]", out, ref.permute(0, 2, 3, 1), 1e-3)
+    return ok
+
+
+@case
+def conv3x3_s1_small():
+    return _conv_case("conv3x3_s1_small", 2, 12, 12, 64, 64, 3, 1, 1)
+
+
+@case
+def conv3x3_s1_layer1():
+    return _conv_case("conv3x3_s1_layer1", 8, 56, 56, 64, 64, 3, 1, 1)
+
+
+@case
+def conv3x3_s2():
+    return _conv_case("conv3x3_s2", 3, 28, 28, 64, 128, 3, 2, 1)
+
+
+@case
+def conv1x1_s2():
+    return _conv_case("conv1x1_s2", 3, 28, 28, 128, 256, 1, 2, 0)
+
+
+@case
+def conv3x3_l4():
+    return _conv_case("conv3x3_l4", 5, 7, 7, 512, 512, 3, 1, 1)
+
+
+@case
+def conv_head_p0():
+    return _conv_case("conv_head_p0", 6, 7, 7, 512, 64, 3, 1, 0, shift=True, relu=True)
+
+
+@case
+def conv_epi_fwd():
+    return _conv_case("conv_epi_fwd", 4, 14, 14, 256, 256, 3, 1, 1, shift=True, residual=True, relu=True)
+
+
+@case
+def conv_epi_bwd():
+    return _conv_case("conv_epi_bwd", 4, 14, 14, 128, 128, 3, 1, 1, residual=True, mask=True, colsum=True)
+
+
+@case
+def conv_epi_scatter():
+    return _conv_case("conv_epi_scatter", 3, 14, 14, 128, 64, 3, 1, 1, mask=True, scatter=True)
+
+
+@case
+def conv_epi_out2_f32():
+    a = _conv_case("conv_epi_out2", 3, 14, 14, 128, 64, 3, 1, 1, mask=True, out2=True)
+    b = _conv_case("conv_epi_f32", 3, 7, 7, 64, 64, 3, 1, 0, shift=True, f32=True)
+    return a and b
+
+
+@case
+def conv_tile_n_variants():
+    ok = True
+    for tn in (64, 128, 256):
+        ok &= _conv_case(f"conv_tile_n{tn}", 2, 14, 14, 128, 256, 3, 1, 1, tile_n=tn)
+    return ok
+
+
+@case
+def stem_s2d():
+    torch, F, ops = _imports()
+    g = torch.Generator(device="cuda").manual_seed(2)
+    N = 3
+    x = torch.randn(N, 3, 224, 224, device="cuda", generator=g)
+    w = torch.randn(64, 3, 7, 7, device="cuda", generator=g) * 0.1
+    gamma = torch.rand(64, device="cuda", generator=g) + 0.5
+    beta = torch.randn(64, device="cuda", generator=g) * 0.1
+    mean = torch.randn(64, device="cuda", generator=g) * 0.1
+    var = torch.rand(64, device="cuda", generator=g) + 0.5
+    wf = torch.empty(64, 256, device="cuda", dtype=torch.bfloat16)
+    shift = torch.empty(64, device="cuda")
+    ops.weight_prep(w, wf, shift, gamma=gamma, beta=beta, mean=mean, var=var, kmap=1)
+    xp = ops.stem_pack(x)
+    out = ops.conv_gemm(xp, wf.view(64, 4, 4, 16), 1, 2, 1, shift=shift, relu=True)
+    torch.cuda.synchronize()
+    xb = x.to(torch.bfloat16).float()
+    scale = gamma / torch.sqrt(var + 1e-5)
+    wb = (w * scale.view(-1, 1, 1, 1)).to(torch.bfloat16).float()
+    ref = F.relu(F.conv2d(xb, wb, None, 2, 3) + (beta - mean * scale).view(1, -1, 1, 1))
+    ok = _report("stem_s2d", out, ref.permute(0, 2, 3, 1), 2e-2)
+    # uint8 path
+    xu = torch.randint(0, 256, (N, 224, 224, 3), device="cuda", dtype=torch.uint8, generator=g)
+    xpu = ops.stem_pack(xu)
+    xf = ((xu.float() / 255).permute(0, 3, 1, 2) - torch.tensor([0.485, 0.456, 0.406], device="cuda").view(1, 3, 1, 1)) \
+        / torch.tensor([0.229, 0.224, 0.225], device="cuda").view(1, 3, 1, 1)
+    ok &= _report("stem_pack_u8_vs_f32", xpu, ops.stem_pack(xf.contiguous()), 1e-2)
+    return ok
+
+
+def _wgrad_case(name, N, H, W, Cin, Cout, R, stride, pad, splits, seed=0):
+    torch, F, ops = _imports()
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    x = torch.randn(N, H, W, Cin, device="cuda", generator=g).to(torch.bfloat16)
+    Ho, Wo = ops.conv_out_hw(H, W, R, R, stride, pad, pad)
+    dy = torch.randn(N, Ho, Wo, Cout, device="cuda", generator=g).to(torch.bfloat16)
+    part = ops.conv_wgrad(x, dy, R, R, stride, pad, splits=splits)
+    torch.cuda.synchronize()
+    got = part.sum(0).view(Cout, R, R, Cin)
+    xr = x.float().permute(0, 3, 1, 2).requires_grad_(False)
+    wz = torch.zeros(Cout, Cin, R, R, device="cuda", requires_grad=True)
+    y = F.conv2d(xr, wz, None, stride, pad)
+    (y * dy.float().permute(0, 3, 1, 2)).sum().backward()
+    ref = wz.grad.permute(0, 2, 3, 1)
+    return _report(name, got.reshape(Cout, -1), ref.reshape(Cout, -1), 2e-2, extra=f"splits={splits}")
+
+
+@case
+def wgrad_1x1_min():
+    return _wgrad_case("wgrad_1x1_min", 1, 8, 8, 64, 128, 1, 1, 0, 1)
+
+
+@case
+def wgrad_1x1_cout64():
+    return _wgrad_case("wgrad_1x1_cout64", 2, 8, 8, 64, 64, 1, 1, 0, 1)
+
+
+@case
+def wgrad_3x3_s1():
+    return _wgrad_case("wgrad_3x3_s1", 3, 14, 14, 128, 128, 3, 1, 1, 3)
+
+
+@case
+def wgrad_3x3_layer1():
+    return _wgrad_case("wgrad_3x3_layer1", 4, 56, 56, 64, 64, 3, 1, 1, 7)
+
+
+@case
+def wgrad_3x3_s2():
+    return _wgrad_case("wgrad_3x3_s2", 3, 28, 28, 64, 128, 3, 2, 1, 2)
+
+
+@case
+def wgrad_l4():
+    return _wgrad_case("wgrad_l4", 5, 7, 7, 512, 512, 3, 1, 1, 2)
+
+
+@case
+def wgrad_head():
+    return _wgrad_case("wgrad_head", 6, 7, 7, 512, 64, 3, 1, 0, 1)
+
+
+@case
+def wgrad_stem():
+    torch, F, ops = _imports()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    N = 2
+    x = torch.randn(N, 3, 224, 224, device="cuda", generator=g)
+    dy = torch.randn(N, 112, 112, 64, device="cuda", generator=g).to(torch.bfloat16)
+    xp = ops.stem_pack(x)
+    part = ops.conv_wgrad(xp, dy, 4, 4, 1, 2, 1, splits=5)
+    w = torch.randn(64, 3, 7, 7, device="cuda", generator=g)
+    dw = torch.zeros_like(w)
+    ops.wgrad_finalize(part, w, dw, splits=5, Cout=64, Cin=16, R=4, S=4, K=256, kmap=1)
+    torch.cuda.synchronize()
+    wz = torch.zeros(64, 3, 7, 7, device="cuda", requires_grad=True)
+    y = F.conv2d(x.to(torch.bfloat16).float(), wz, None, 2, 3)
+    (y * dy.float().permute(0, 3, 1, 2)).sum().backward()
+    return _report("wgrad_stem", dw.reshape(64, -1), wz.grad.reshape(64, -1), 2e-2)
+
+
+@case
+def prep_and_finalize():
+    torch, F, ops = _imports()
+    g = torch.Generator(device="cuda").manual_seed(4)
+    Cout, Cin, R = 128, 64, 3
+    w = torch.randn(Cout, Cin, R, R, device="cuda", generator=g)
+    gamma = torch.rand(Cout, device="cuda", generator=g) + 0.5
+    beta = torch.randn(Cout, device="cuda", generator=g)
+    mean = torch.randn(Cout, device="cuda", generator=g)
+    var = torch.rand(Cout, device="cuda", generator=g) + 0.5
+    K = R * R * Cin
+    wf = torch.empty(Cout, K, device="cuda", dtype=torch.bfloat16)
+    wd = torch.empty(Cin, R * R * Cout, device="cuda", dtype=torch.bfloat16)
+    shift = torch.empty(Cout, device="cuda")
+    ops.weight_prep(w, wf, shift, w_dgrad=wd, gamma=gamma, beta=beta, mean=mean, var=var)
+    scale = gamma / torch.sqrt(var + 1e-5)
+    ws = w * scale.view(-1, 1, 1, 1)
+    ok = _report("prep:w_fwd", wf.view(Cout, R, R, Cin), ws.permute(0, 2, 3, 1), 5e-3)
+    ok &= _report("prep:w_dgrad", wd.view(Cin, R, R, Cout), ws.flip(2, 3).permute(1, 2, 3, 0), 5e-3)
+    ok &= _report("prep:shift", shift[None], (beta - mean * scale)[None], 1e-5)
+    part = torch.randn(3, Cout, K, device="cuda", generator=g)
+    dbeta = torch.randn(Cout, device="cuda", generator=g)
+    dw = torch.empty_like(w); dgamma = torch.empty(Cout, device="cuda")
+    ops.wgrad_finalize(part, w, dw, splits=3, Cout=Cout, Cin=Cin, R=R, S=R, K=K, gamma=gamma, var=var,
+                       mean=mean, dbeta=dbeta, dgamma=dgamma)
+    gsum = part.sum(0).view(Cout, R, R, Cin).permute(0, 3, 1, 2)
+    ok &= _report("fin:dw", dw.reshape(Cout, -1), (gsum * scale.view(-1, 1, 1, 1)).reshape(Cout, -1), 1e-4)
+    rstd = 1 / torch.sqrt(var + 1e-5)
+    dg_ref = rstd * ((w * gsum).sum((1, 2, 3)) - mean * dbeta)
+    ok &= _report("fin:dgamma", dgamma[None], dg_ref[None], 1e-3)
+    return ok
+
+
+@case
+def maxpool():
+    torch, F, ops = _imports()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    N, H, W, Cc = 3, 112, 112, 64
+    x = torch.randn(N, H, W, Cc, device="cuda", generator=g).relu().to(torch.bfloat16)
+    y, idx = ops.maxpool_fwd(x, save_idx=True)
+    xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    yr = F.max_pool2d(xr, 3, 2, 1)
+    ok = _report("maxpool_fwd", y, yr.permute(0, 2, 3, 1), 1e-6)
+    dy = torch.randn(N, 56, 56, Cc, device="cuda", generator=g).to(torch.bfloat16)
+    cs = torch.zeros(Cc, device="cuda")
+    dx = ops.maxpool_bwd(dy, idx, x, colsum=cs)
+    torch.cuda.synchronize()
+    yr.backward(dy.float().permute(0, 3, 1, 2))
+    ref = (xr.grad * (xr > 0)).permute(0, 2, 3, 1)
+    # ties between equal bf16 maxima may route a gradient differently: compare through sums
+    ok &= _report("maxpool_bwd", dx, ref, 5e-2)
+    ok &= _report("maxpool_bwd:colsum", cs[None], dx.float().reshape(-1, Cc).sum(0)[None], 1e-3)
+    return ok
+
+
+@case
+def mlp_linear():
+    torch, F, ops = _imports()
+    g = torch.Generator(device="cuda").manual_seed(6)
+    ok = True
+    for (B, K, O, relu) in ((37, 1600, 512, True), (256, 512, 256, True), (256, 256, 15, False)):
+        x = torch.randn(B, K, device="cuda", generator=g)
+        w = torch.randn(O, K, device="cuda", generator=g) / K ** 0.5
+        b = torch.randn(O, device="cuda", generator=g)
+        y = ops.linear_fwd(x, w, b, relu)
+        xr = x.clone().requires_grad_(True); wr = w.clone().requires_grad_(True); br = b.clone().requires_grad_(True)
+        torch.backends.cuda.matmul.allow_tf32 = False
+        yr = F.linear(xr, wr, br)
+        yr = yr.relu() if relu else yr
+        ok &= _report(f"linear_fwd[{B},{K},{O}]", y, yr, 1e-4)
+        dy = torch.randn(B, O, device="cuda", generator=g)
+        yr.backward(dy)
+        dw = torch.empty_like(w); db = torch.empty_like(b)
+        dx = ops.linear_bwd(x, w, y, dy.clone(), dw, db, relu)
+        torch.cuda.synchronize()
+        ok &= _report(f"linear_bwd:dx[{B},{K},{O}]", dx, xr.grad, 1e-4)
+        ok &= _report(f"linear_bwd:dw[{B},{K},{O}]", dw, wr.grad, 1e-4)
+        ok &= _report(f"linear_bwd:db[{B},{K},{O}]", db[None], br.grad[None], 1e-4)
+    return ok
+
+
+@case
+def head_flatten():
+    torch, F, ops = _imports()
+    g = torch.Generator(device="cuda").manual_seed(7)
+    B = 9
+    h = torch.randn(B, 5, 5, 64, device="cuda", generator=g).relu().to(torch.bfloat16)
+    flat = ops.head_flatten_fwd(h)
+    ok = _report("head_flatten_fwd", flat, h.float().permute(0, 3, 1, 2).reshape(B, -1), 1e-6)
+    df = torch.randn(B, 1600, device="cuda", generator=g)
+    db = torch.zeros(64, device="cuda")
+    dh = ops.head_flatten_bwd(df, h, dbias=db)
+    torch.cuda.synchronize()
+    ref = df.view(B, 64, 5, 5).permute(0, 2, 3, 1) * (h.float() > 0)
+    ok &= _report("head_flatten_bwd", dh, ref, 1e-2)
+    ok &= _report("head_flatten_bwd:db", db[None], dh.float().reshape(-1, 64).sum(0)[None], 1e-3)
+    return ok
+
+
+@case
+def td_and_adam():
+    torch, F, ops = _imports()
+    from oracle import qstep
+    g = torch.Generator(device="cuda").manual_seed(8)
+    ok = True
+    cfg = qstep.StepConfig()
+    for B in (2, 256, 4099):
+        qs = torch.randn(B, 5, 3, device="cuda", generator=g)
+        qo = torch.randn(B, 5, 3, device="cuda", generator=g)
+        qt = torch.randn(B, 5, 3, device="cuda", generator=g)
+        qo[0, 0, :] = 0.25                     # tie -> first index
+        act = torch.randint(0, 3, (B,), device="cuda", generator=g)
+        rew = (torch.rand(B, 5, device="cuda", generator=g) < 0.1).long()
+        loss, dq, best, y = ops.td_epilogue(qs, qo, qt, act, rew, rew, want_aux=True)
+        torch.cuda.synchronize()
+        qsr = qs.cpu().requires_grad_(True)
+        l_ref, aux = qstep.td_loss(qsr, qo.cpu(), qt.cpu(), act.cpu(), rew.cpu(), rew.cpu(),
+                                   torch.ones(B, 5, dtype=torch.long), cfg)
+        l_ref.backward()
+        ok &= bool((best.cpu() == aux["best"]).all())
+        ok &= _report(f"td:loss[{B}]", loss.cpu()[None], l_ref.detach()[None][None], 1e-5)
+        ok &= _report(f"td:y[{B}]", y.cpu(), aux["y"], 1e-6)
+        ok &= _report(f"td:dq[{B}]", dq.cpu().reshape(B, -1), qsr.grad.reshape(B, -1), 1e-5)
+    n = 4 * 100003
+    p = torch.randn(n, device="cuda", generator=g); gr = torch.randn(n, device="cuda", generator=g) * 1e-3
+    m = torch.zeros(n, device="cuda"); v = torch.zeros(n, device="cuda"); tgt = torch.empty(n, device="cuda")
+    pr = p.clone().requires_grad_(True)
+    opt = torch.optim.Adam([pr], lr=1e-4)
+    for step in (1, 2, 3):
+        pr.grad = gr.clone() * step
+        opt.step()
+        ops.adam_fused(p, gr * step, m, v, lr=1e-4, step=step, target=tgt if step == 3 else None)
+    torch.cuda.synchronize()
+    ok &= _report("adam:p", p[None], pr.detach()[None], 1e-6)
+    ok &= _report("adam:target", tgt[None], p[None], 0.0)
+    return ok
+
+
+def _run_batch(names):
+    """child: run cases in-process, one marker line per finished case"""
+    for n in names:
+        print(f"@@BEGIN {n}", flush=True)
+        try:
+            ok = CASES[n]()
+        except Exception as e:  # noqa
+            import traceback
+            traceback.print_exc()
+            ok = False
+            # a CUDA error is sticky: let the parent restart the rest in a fresh process
+            print(f"@@END {n} EXC", flush=True)
+            if "CUDA" in repr(e) or "cuda" in repr(e) or "vdqn" in repr(e):
+                sys.exit(3)
+            continue
+        print(f"@@END {n} {'PASS' if ok else 'FAIL'}", flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch")
+    ap.add_argument("--only", default="")
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "diag.json"))
+    a = ap.parse_args()
+    if a.batch:
+        _run_batch(a.batch.split(","))
+        return
+    todo = [n for n in CASES if a.only in n]
+    results = {}
+    os.makedirs(os.path.dirname(a.out), exist_ok=True)
+    while todo:
+        try:
+            r = subprocess.run([sys.executable, __file__, "--batch", ",".join(todo)],
+                               capture_output=True, text=True, timeout=600)
+            out = r.stdout + "\n--- stderr ---\n" + r.stderr[-4000:]
+        except subprocess.TimeoutExpired as e:
+            out = (e.stdout.decode() if isinstance(e.stdout, bytes) else (e.stdout or "")) + "\n@@TIMEOUT"
+        cur, buf, finished = None, [], set()
+        for line in out.splitlines():
+            if line.startswith("@@BEGIN "):
+                cur, buf = line.split()[1], []
+            elif line.startswith("@@END ") and cur:
+                results[cur] = {"status": line.split()[2], "log": "\n".join(buf)[-3000:]}
+                finished.add(cur); cur = None
+            else:
+                buf.append(line)
+        if cur is not None:                       # died inside `cur`
+            results[cur] = {"status": "CRASH", "log": ("\n".join(buf) + out[-2500:])[-5000:]}
+            finished.add(cur)
+        if not finished:
+            print("batch made no progress:\n" + out[-3000:])
+            break
+        todo = [n for n in todo if n not in finished]
+    for n, r in results.items():
+        print(f"[{r['status']}] {n}")
+        if r["status"] != "PASS":
+            print(r["log"])
+    with open(a.out, "w") as f:
+        json.dump(results, f, indent=1)
+    npass = sum(r["status"] == "PASS" for r in results.values())
+    print(f"SUMMARY {npass}/{len(results)} passed")
+
+
+if __name__ == "__main__":
+    main()

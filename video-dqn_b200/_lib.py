@@ -1,0 +1,112 @@
+"""ctypes binding of libvdqn.so (include/vdqn.h).  The product path has no fallback: if the
+library is missing or a call fails, an exception is raised."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvdqn.so")
+
+EPI_RELU = 1
+EPI_OUT_F32 = 2
+
+c_void_p, c_int, c_float, c_int64 = C.c_void_p, C.c_int32, C.c_float, C.c_int64
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [("x", c_void_p), ("w", c_void_p), ("out", c_void_p), ("out2", c_void_p),
+                ("shift", c_void_p), ("residual", c_void_p), ("mask_src", c_void_p),
+                ("colsum", c_void_p)] + \
+               [(n, c_int) for n in ("N", "H", "W", "Cin", "Cout", "R", "S", "stride", "dil",
+                                     "pad_lo", "pad_hi", "ldc", "ldr", "ldm", "out2_ld",
+                                     "out_scatter", "flags", "tile_n", "max_ctas")]
+
+
+class WgradDesc(C.Structure):
+    _fields_ = [("x", c_void_p), ("dy", c_void_p), ("part", c_void_p)] + \
+               [(n, c_int) for n in ("N", "H", "W", "Cin", "Cout", "R", "S", "stride", "dil",
+                                     "pad_lo", "pad_hi", "ldy", "splits", "max_ctas")]
+
+
+class WgradFinDesc(C.Structure):
+    _fields_ = [(n, c_void_p) for n in ("part", "w", "gamma", "var", "mean", "dbeta", "dw", "dgamma")] + \
+               [(n, c_int) for n in ("splits", "Cout", "Cin", "R", "S", "K", "kmap")] + [("eps", c_float)]
+
+
+class WprepDesc(C.Structure):
+    _fields_ = [(n, c_void_p) for n in ("w", "gamma", "beta", "mean", "var", "bias", "w_fwd",
+                                        "w_dgrad", "shift")] + \
+               [(n, c_int) for n in ("Cout", "Cin", "R", "S", "K", "kmap")] + [("eps", c_float)]
+
+
+class TdDesc(C.Structure):
+    _fields_ = [(n, c_void_p) for n in ("q_s", "q_next_online", "q_next_target", "act", "rew", "term",
+                                        "valid", "dq", "loss_out", "best_out", "y_out")] + \
+               [(n, c_int) for n in ("B", "C", "A")] + [("gamma", c_float), ("inv_count", c_float)] + \
+               [(n, c_int) for n in ("double_dqn", "clip_rect", "linear", "use_valid")]
+
+
+EXPORTS = {
+    "vdqn_last_error": (C.c_char_p, []),
+    "vdqn_abi_version": (c_int, []),
+    "vdqn_init": (c_int, [c_int]),
+    "vdqn_num_sms": (c_int, []),
+    "vdqn_conv_gemm": (c_int, [C.POINTER(ConvDesc), c_void_p]),
+    "vdqn_conv_wgrad": (c_int, [C.POINTER(WgradDesc), c_void_p]),
+    "vdqn_wgrad_finalize": (c_int, [C.POINTER(WgradFinDesc), c_void_p]),
+    "vdqn_weight_prep": (c_int, [C.POINTER(WprepDesc), c_void_p]),
+    "vdqn_stem_pack_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "vdqn_stem_pack_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "vdqn_maxpool_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "vdqn_maxpool_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                 c_int, c_int, c_int, c_int, c_void_p]),
+    "vdqn_linear_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "vdqn_linear_bwd": (c_int, [c_void_p] * 7 + [c_int, c_int, c_int, c_int, c_void_p]),
+    "vdqn_head_flatten_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "vdqn_head_flatten_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "vdqn_td_epilogue": (c_int, [C.POINTER(TdDesc), c_void_p]),
+    "vdqn_adam_fused": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+                                c_float, c_float, c_float, c_float, c_int, c_float, c_void_p]),
+}
+
+_lib = None
+
+
+class VdqnError(RuntimeError):
+    pass
+
+
+def load():
+    """dlopen libvdqn.so and type its entry points.  Raises if the library is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise VdqnError(f"{LIB_PATH} not found: build it with `python video-dqn_b200/build.py` "
+                        "(there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in EXPORTS.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = load().vdqn_last_error().decode(errors="replace")
+        if rc == -2 or rc == -1:
+            raise ValueError(f"vdqn {what}: {msg} (code {rc})")
+        raise VdqnError(f"vdqn {what}: {msg} (code {rc})")
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr():
+    import torch
+    return torch.cuda.current_stream().cuda_stream

@@ -1,0 +1,395 @@
+// Implicit-GEMM convolution on the 5th-gen tensor cores (sm_100a), used for the forward and
+// data-gradient passes of every convolution of the Q-network trunk + head
+// (reference call sites: archs/HabitatDQNMultiAction.py:49-51 -> torchvision BasicBlock,
+//  SURVEY.md 2c rows K1-K5, K7).
+//
+//   D[m, co] = sum_{r,s,ci} X[n, p*stride + r*dil - pad, q*stride + s*dil - pad, ci] * W[co, r, s, ci]
+//   m = (n, p, q) linearised; X is NHWC bf16; W is [Cout][R][S][Cin] bf16; fp32 accumulation.
+//
+// One persistent CTA per SM, warp-specialised:
+//   warp 0    : TMA producer.  A tile = 128 output pixels x CK channels of one filter tap, gathered
+//               by the TMA unit in IM2COL mode (padding halo zero-filled, stride handled by the
+//               traversal stride); B tile = BN x CK slab of the weight matrix (tiled TMA).
+//   warp 1    : allocates TMEM, issues tcgen05.mma (M=128, N=BN, K=16) from one elected lane,
+//               releases smem stages / publishes accumulators with tcgen05.commit.
+//   warps 2-5 : epilogue.  tcgen05.ld the fp32 accumulator (double-buffered in TMEM so the next
+//               tile's MMAs overlap), then + per-channel shift (folded BN / bias), + residual,
+//               ReLU or ReLU-mask (backward), optional per-channel column sums (d beta), bf16/fp32
+//               store, optional stride-2 scatter (zero-dilated gradient for strided dgrad).
+#include "ptx.cuh"
+#include "vdqn_internal.h"
+
+#include <cuda_bf16.h>
+
+namespace vdqn {
+
+struct IgemmArgs {
+  int M_total, Ho, Wo, Cout;
+  int R, S, Cin, stride, dil, lower_h, lower_w;
+  int num_m_tiles, num_n_tiles;
+  void* out;          // [opix][ldc] bf16 or fp32
+  void* out2;         // optional second bf16 destination, stride-2 scatter (dilated copy)
+  const float* shift;       // [Cout] or null
+  const __nv_bfloat16* residual;  // [M_total][ldr] or null
+  const __nv_bfloat16* mask_src;  // [M_total][ldm] or null: out = (mask_src > 0) ? v : 0
+  float* colsum;            // [Cout] fp32 atomics or null
+  int ldc, ldr, ldm;
+  int out_scatter;    // 1: opix = m;  2: opix = (n*2Ho + 2p)*2Wo + 2q
+  int out2_ld;
+  int flags;          // VDQN_EPI_*
+};
+
+template <int BN, int CK>
+struct IgemmCfg {
+  static constexpr int BM = 128;
+  static constexpr int KSUB = (CK == 64) ? 1 : 4;  // TMA sub-blocks per pipeline stage
+  static constexpr int A_SUB_BYTES = BM * CK * 2;
+  static constexpr int B_SUB_BYTES = BN * CK * 2;
+  static constexpr int STAGE_BYTES = KSUB * (A_SUB_BYTES + B_SUB_BYTES);
+  static constexpr int STAGES = (190 * 1024) / STAGE_BYTES > 8 ? 8 : (190 * 1024) / STAGE_BYTES;
+  static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
+                                   : (2 * BN <= 256) ? 256 : 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr uint64_t SWZ = (CK == 64) ? kSwz128 : kSwz32;
+  static constexpr int ROW_BYTES = CK * 2;          // bytes per smem row (= swizzle span)
+  static constexpr int SBO = 8 * ROW_BYTES;         // 8-row group pitch
+};
+
+template <int BN, int CK>
+__global__ void __launch_bounds__(192, 1)
+igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+             const IgemmArgs a) {
+  using Cfg = IgemmCfg<BN, CK>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
+  // barriers: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then tmem ptr slot
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
+  auto tfull_bar = [&](int i) { return bar_base + 8u * (2 * Cfg::STAGES + i); };
+  auto tempty_bar = [&](int i) { return bar_base + 8u * (2 * Cfg::STAGES + 2 + i); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 4);
+  uint32_t* tmem_slot_ptr =
+      reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(tfull_bar(i), 1);
+      mbar_init(tempty_bar(i), 4);   // one arrive per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int num_tiles = a.num_m_tiles * a.num_n_tiles;
+  const int cblks = a.Cin / CK;
+  const int num_sub = a.R * a.S * cblks;
+  const int num_kb = num_sub / Cfg::KSUB;
+  const int HoWo = a.Ho * a.Wo;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int n_t = t % a.num_n_tiles, m_t = t / a.num_n_tiles;
+        const int m0 = m_t * Cfg::BM;
+        const int img = m0 / HoWo;
+        const int rem = m0 - img * HoWo;
+        const int p0 = rem / a.Wo, q0 = rem - p0 * a.Wo;
+        const int cw = q0 * a.stride + a.lower_w, ch = p0 * a.stride + a.lower_h;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+          const uint32_t sA = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint32_t sB = sA + Cfg::KSUB * Cfg::A_SUB_BYTES;
+#pragma unroll
+          for (int sub = 0; sub < Cfg::KSUB; ++sub) {
+            const int j = kb * Cfg::KSUB + sub;
+            const int tap = j / cblks;
+            const int c0 = (j - tap * cblks) * CK;
+            const int r = tap / a.S, s = tap - r * a.S;
+            tma_load_im2col_4d(sA + sub * Cfg::A_SUB_BYTES, &tmA, full_bar(stage), c0, cw, ch, img,
+                               (uint16_t)(s * a.dil), (uint16_t)(r * a.dil));
+            tma_load_2d(sB + sub * Cfg::B_SUB_BYTES, &tmB, full_bar(stage), j * CK, n_t * BN);
+          }
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sA = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint32_t sB = sA + Cfg::KSUB * Cfg::A_SUB_BYTES;
+#pragma unroll
+          for (int sub = 0; sub < Cfg::KSUB; ++sub) {
+#pragma unroll
+            for (int k = 0; k < CK / 16; ++k) {
+              const uint64_t ad =
+                  make_smem_desc(sA + sub * Cfg::A_SUB_BYTES + k * 32, 16, Cfg::SBO, Cfg::SWZ);
+              const uint64_t bd =
+                  make_smem_desc(sB + sub * Cfg::B_SUB_BYTES + k * 32, 16, Cfg::SBO, Cfg::SWZ);
+              umma_f16(d_tmem, ad, bd, idesc, (kb | sub | k) != 0);
+            }
+          }
+          umma_commit(empty_bar(stage));
+          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(tfull_bar(acc));
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (warps 2..5)
+    const int quad = warp & 3;                 // TMEM lane quadrant this warp may touch
+    const int row = quad * 32 + lane;
+    const bool out_f32 = a.flags & VDQN_EPI_OUT_F32;
+    const bool relu = a.flags & VDQN_EPI_RELU;
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int n_t = t % a.num_n_tiles, m_t = t / a.num_n_tiles;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int m = m_t * Cfg::BM + row;
+      const bool valid = m < a.M_total;
+      long opix = m;
+      long opix2 = 0;
+      if (a.out_scatter == 2 || a.out2 != nullptr) {
+        const int img = m / HoWo;
+        const int rem = m - img * HoWo;
+        const int p = rem / a.Wo, q = rem - p * a.Wo;
+        const long dil_pix = ((long)img * (2 * a.Ho) + 2 * p) * (2 * a.Wo) + 2 * q;
+        if (a.out_scatter == 2) opix = dil_pix;
+        opix2 = dil_pix;
+      }
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int chunk = 0; chunk < BN / 32; ++chunk) {
+        uint32_t raw[32];
+        tmem_ld_32x32(tmem_base + acc * BN + chunk * 32 + ((uint32_t)(quad * 32) << 16), raw);
+        tmem_ld_wait();
+        const int c0 = n_t * BN + chunk * 32;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+        if (a.shift != nullptr) {
+          const float4* sp = reinterpret_cast<const float4*>(a.shift + c0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 s4 = __ldg(sp + j);
+            v[4 * j + 0] += s4.x; v[4 * j + 1] += s4.y; v[4 * j + 2] += s4.z; v[4 * j + 3] += s4.w;
+          }
+        }
+        if (a.residual != nullptr && valid) {
+          const uint4* rp = reinterpret_cast<const uint4*>(a.residual + (long)m * a.ldr + c0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 r4 = __ldg(rp + j);
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r4);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = __bfloat1622float2(h[e]);
+              v[8 * j + 2 * e] += f.x;
+              v[8 * j + 2 * e + 1] += f.y;
+            }
+          }
+        }
+        if (relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        if (a.mask_src != nullptr && valid) {
+          const uint4* mp = reinterpret_cast<const uint4*>(a.mask_src + (long)m * a.ldm + c0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 r4 = __ldg(mp + j);
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r4);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = __bfloat1622float2(h[e]);
+              if (!(f.x > 0.f)) v[8 * j + 2 * e] = 0.f;
+              if (!(f.y > 0.f)) v[8 * j + 2 * e + 1] = 0.f;
+            }
+          }
+        }
+        if (!valid) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        }
+        if (valid) {
+          if (out_f32) {
+            float4* op = reinterpret_cast<float4*>(static_cast<float*>(a.out) + opix * a.ldc + c0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {
+            uint4 pk[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk[j]);
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                h[e] = __floats2bfloat162_rn(v[8 * j + 2 * e], v[8 * j + 2 * e + 1]);
+            }
+            uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(a.out) +
+                                                 opix * a.ldc + c0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) op[j] = pk[j];
+            if (a.out2 != nullptr) {
+              uint4* op2 = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(a.out2) +
+                                                    opix2 * a.out2_ld + c0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) op2[j] = pk[j];
+            }
+          }
+        }
+        if (a.colsum != nullptr) {
+          // round to the stored precision first so d beta matches what wgrad consumes
+          if (!out_f32) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __bfloat162float(__float2bfloat16_rn(v[j]));
+          }
+          // warp transpose-reduce: afterwards lane L holds the column-(c0+L) sum over 32 rows
+#pragma unroll
+          for (int off = 16; off >= 1; off >>= 1) {
+            const bool upper = (lane & off) != 0;
+#pragma unroll
+            for (int i = 0; i < off; ++i) {
+              const float send = upper ? v[i] : v[i + off];
+              const float keep = upper ? v[i + off] : v[i];
+              v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+            }
+          }
+          atomicAdd(a.colsum + c0 + lane, v[0]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------- host side
+
+template <int BN, int CK>
+static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmArgs& a,
+                        int num_sms, cudaStream_t stream) {
+  using Cfg = IgemmCfg<BN, CK>;
+  static bool attr_set = false;
+  auto kfn = igemm_kernel<BN, CK>;
+  if (!attr_set) {
+    cudaError_t e =
+        cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return set_error(VDQN_ERR_CUDA, "cudaFuncSetAttribute(igemm): %s",
+                                           cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int tiles = a.num_m_tiles * a.num_n_tiles;
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  kfn<<<grid, 192, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return set_error(VDQN_ERR_CUDA, "igemm launch: %s", cudaGetErrorString(e));
+  return VDQN_OK;
+}
+
+}  // namespace vdqn
+
+using namespace vdqn;
+
+extern "C" int vdqn_conv_gemm(const vdqn_conv_desc* d, void* stream_v) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  if (d == nullptr) return set_error(VDQN_ERR_ARG, "conv_gemm: null descriptor");
+  const int CK = (d->Cin % 64 == 0) ? 64 : 16;
+  if (d->Cin % CK != 0) return set_error(VDQN_ERR_SHAPE, "conv_gemm: Cin=%d not a multiple of 16", d->Cin);
+  if (CK == 16 && (d->R * d->S * (d->Cin / 16)) % 4 != 0)
+    return set_error(VDQN_ERR_SHAPE, "conv_gemm: 16-channel path needs R*S*Cin/16 %% 4 == 0");
+  const int Ho = (d->H + d->pad_lo + d->pad_hi - (d->R - 1) * d->dil - 1) / d->stride + 1;
+  const int Wo = (d->W + d->pad_lo + d->pad_hi - (d->S - 1) * d->dil - 1) / d->stride + 1;
+  if (Ho <= 0 || Wo <= 0) return set_error(VDQN_ERR_SHAPE, "conv_gemm: empty output");
+  int BN = d->Cout >= 256 ? 256 : d->Cout;
+  if (d->tile_n > 0) BN = d->tile_n;
+  if (!(BN == 64 || BN == 128 || BN == 256) || d->Cout % BN != 0)
+    return set_error(VDQN_ERR_SHAPE, "conv_gemm: Cout=%d unsupported (tile %d)", d->Cout, BN);
+  if (CK == 16 && BN != 64) return set_error(VDQN_ERR_SHAPE, "conv_gemm: 16-channel path is Cout=64 only");
+  if (d->ldc % 8 != 0 || (d->residual && d->ldr % 8 != 0) || (d->mask_src && d->ldm % 8 != 0))
+    return set_error(VDQN_ERR_SHAPE, "conv_gemm: leading dimensions must be multiples of 8");
+  if ((reinterpret_cast<uintptr_t>(d->x) | reinterpret_cast<uintptr_t>(d->w) |
+       reinterpret_cast<uintptr_t>(d->out)) & 15)
+    return set_error(VDQN_ERR_ARG, "conv_gemm: pointers must be 16-byte aligned");
+
+  DeviceInfo* dev = device_info();
+  if (dev == nullptr) return VDQN_ERR_CUDA;
+
+  CUtensorMap tmA, tmB;
+  int rc = make_im2col_map(&tmA, d->x, d->N, d->H, d->W, d->Cin, CK, 128, d->stride,
+                           -d->pad_lo, -d->pad_lo,
+                           d->pad_hi - (d->R - 1) * d->dil, d->pad_hi - (d->S - 1) * d->dil,
+                           CK == 64 ? 128 : 32);
+  if (rc != VDQN_OK) return rc;
+  rc = make_tiled_map_2d(&tmB, d->w, (uint64_t)d->R * d->S * d->Cin, d->Cout, CK, BN,
+                         CK == 64 ? 128 : 32);
+  if (rc != VDQN_OK) return rc;
+
+  IgemmArgs a{};
+  a.M_total = d->N * Ho * Wo;
+  a.Ho = Ho; a.Wo = Wo; a.Cout = d->Cout;
+  a.R = d->R; a.S = d->S; a.Cin = d->Cin; a.stride = d->stride; a.dil = d->dil;
+  a.lower_h = -d->pad_lo; a.lower_w = -d->pad_lo;
+  a.num_m_tiles = (a.M_total + 127) / 128;
+  a.num_n_tiles = d->Cout / BN;
+  a.out = d->out; a.out2 = d->out2; a.shift = d->shift;
+  a.residual = static_cast<const __nv_bfloat16*>(d->residual);
+  a.mask_src = static_cast<const __nv_bfloat16*>(d->mask_src);
+  a.colsum = d->colsum;
+  a.ldc = d->ldc; a.ldr = d->ldr; a.ldm = d->ldm;
+  a.out_scatter = d->out_scatter == 2 ? 2 : 1;
+  a.out2_ld = d->out2_ld;
+  a.flags = d->flags;
+
+  const int sms = d->max_ctas > 0 && d->max_ctas < dev->num_sms ? d->max_ctas : dev->num_sms;
+  if (CK == 16) return launch_igemm<64, 16>(tmA, tmB, a, sms, stream);
+  switch (BN) {
+    case 64: return launch_igemm<64, 64>(tmA, tmB, a, sms, stream);
+    case 128: return launch_igemm<128, 64>(tmA, tmB, a, sms, stream);
+    default: return launch_igemm<256, 64>(tmA, tmB, a, sms, stream);
+  }
+}

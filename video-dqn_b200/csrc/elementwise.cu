@@ -1,0 +1,640 @@
+// HBM-bound kernels of the Q-learning step: weight preparation (BN fold + bf16 cast + layout),
+// weight-gradient finalisation, input packing, max-pool, the fp32 Q-head MLP, the fused TD
+// epilogue and the fused Adam + target-sync update.  All are plain coalesced / vectorised
+// grid-stride kernels; none is GEMM-shaped except the tiny fp32 MLP (0.95 MMAC per frame).
+#include "vdqn_internal.h"
+
+#include <cuda_bf16.h>
+
+namespace vdqn {
+
+// ------------------------------------------------------------------------------------------
+// GEMM-K index -> OIHW source index.  kmap 0: k = (r*S + s)*Cin + ci.
+// kmap 1 (stem, space-to-depth): k = (a*4 + b)*16 + c16, c16 = (ph*2 + pw)*3 + c (12..15 pad),
+// original tap r = 2a + ph - 1, s = 2b + pw - 1 on the 7x7 filter (r or s == -1 -> zero).
+// Returns -1 for a structural zero.
+__device__ __forceinline__ int oihw_index(int co, int k, int Cin, int R, int S, int kmap, int* r_out,
+                                          int* s_out, int* ci_out) {
+  if (kmap == 0) {
+    const int tap = k / Cin, ci = k - tap * Cin;
+    const int r = tap / S, s = tap - r * S;
+    *r_out = r; *s_out = s; *ci_out = ci;
+    return ((co * Cin + ci) * R + r) * S + s;
+  }
+  const int tap = k >> 4, c16 = k & 15;
+  if (c16 >= 12) return -1;
+  const int a = tap >> 2, b = tap & 3;
+  const int par = c16 / 3, c = c16 - par * 3;
+  const int r = 2 * a + (par >> 1) - 1, s = 2 * b + (par & 1) - 1;
+  if (r < 0 || s < 0) return -1;
+  *r_out = r; *s_out = s; *ci_out = c;
+  return ((co * 3 + c) * 7 + r) * 7 + s;
+}
+
+__global__ void weight_prep_kernel(const vdqn_wprep_desc d) {
+  const long total = (long)d.Cout * d.K;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total;
+       i += (long)gridDim.x * blockDim.x) {
+    const int co = (int)(i / d.K), k = (int)(i - (long)co * d.K);
+    float scale = 1.f;
+    if (d.gamma != nullptr) scale = d.gamma[co] * (1.0f / sqrtf(d.var[co] + d.eps));
+    int r = 0, s = 0, ci = 0;
+    const int src = oihw_index(co, k, d.Cin, d.R, d.S, d.kmap, &r, &s, &ci);
+    const float v = src >= 0 ? d.w[src] * scale : 0.f;
+    const __nv_bfloat16 b = __float2bfloat16_rn(v);
+    static_cast<__nv_bfloat16*>(d.w_fwd)[i] = b;
+    if (d.w_dgrad != nullptr && d.kmap == 0) {
+      const long di = (long)ci * (d.R * d.S * d.Cout) +
+                      (long)((d.R - 1 - r) * d.S + (d.S - 1 - s)) * d.Cout + co;
+      static_cast<__nv_bfloat16*>(d.w_dgrad)[di] = b;
+    }
+    if (k == 0) {
+      float sh = 0.f;
+      if (d.gamma != nullptr) sh = d.beta[co] - d.mean[co] * scale;
+      if (d.bias != nullptr) sh += d.bias[co];
+      d.shift[co] = sh;
+    }
+  }
+}
+
+// one block per output channel
+__global__ void wgrad_finalize_kernel(const vdqn_wgrad_fin_desc d) {
+  const int co = blockIdx.x;
+  float rstd = 1.f, scale = 1.f;
+  if (d.gamma != nullptr) {
+    rstd = 1.0f / sqrtf(d.var[co] + d.eps);
+    scale = d.gamma[co] * rstd;
+  }
+  float dot = 0.f;
+  const long plane = (long)d.Cout * d.K;
+  for (int k = threadIdx.x; k < d.K; k += blockDim.x) {
+    float g = 0.f;
+    const float* p = d.part + (long)co * d.K + k;
+    for (int s = 0; s < d.splits; ++s) g += p[s * plane];
+    int r, ss, ci;
+    const int src = oihw_index(co, k, d.Cin, d.R, d.S, d.kmap, &r, &ss, &ci);
+    if (src >= 0) {
+      dot += d.w[src] * g;
+      d.dw[src] = scale * g;
+    }
+  }
+  if (d.dgamma != nullptr) {
+    __shared__ float red[32];
+    for (int off = 16; off; off >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, off);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dot;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+      for (int off = 16; off; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+      if (threadIdx.x == 0) {
+        const float db = d.dbeta != nullptr ? d.dbeta[co] : 0.f;
+        d.dgamma[co] = rstd * (v - d.mean[co] * db);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// input packing: one thread per packed pixel (n, h2, w2) -> 16 bf16 (32 bytes)
+template <bool U8>
+__global__ void stem_pack_kernel(const void* __restrict__ xin, __nv_bfloat16* __restrict__ out,
+                                 int N, int H, int W) {
+  const int H2 = H / 2, W2 = W / 2;
+  const long total = (long)N * H2 * W2;
+  const float mean[3] = {0.485f, 0.456f, 0.406f};
+  const float stdv[3] = {0.229f, 0.224f, 0.225f};
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total;
+       i += (long)gridDim.x * blockDim.x) {
+    const int w2 = (int)(i % W2);
+    const long t = i / W2;
+    const int h2 = (int)(t % H2), n = (int)(t / H2);
+    float v[16];
+#pragma unroll
+    for (int j = 12; j < 16; ++j) v[j] = 0.f;
+    if (U8) {
+      const uint8_t* x = static_cast<const uint8_t*>(xin);
+#pragma unroll
+      for (int ph = 0; ph < 2; ++ph) {
+        const uint8_t* row = x + (((long)n * H + 2 * h2 + ph) * W + 2 * w2) * 3;
+#pragma unroll
+        for (int pw = 0; pw < 2; ++pw)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            float f = (float)row[pw * 3 + c] / 255.f;
+            f = f - mean[c];
+            v[(ph * 2 + pw) * 3 + c] = f / stdv[c];
+          }
+      }
+    } else {
+      const float* x = static_cast<const float*>(xin);
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int ph = 0; ph < 2; ++ph) {
+          const float2 f = *reinterpret_cast<const float2*>(
+              x + (((long)n * 3 + c) * H + 2 * h2 + ph) * W + 2 * w2);
+          v[(ph * 2 + 0) * 3 + c] = f.x;
+          v[(ph * 2 + 1) * 3 + c] = f.y;
+        }
+    }
+    uint4 pk[2];
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(pk);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) h[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+    uint4* o = reinterpret_cast<uint4*>(out + i * 16);
+    o[0] = pk[0];
+    o[1] = pk[1];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// max_pool2d(3,2,1), NHWC bf16; one thread = 8 channels of one output pixel
+__global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                   uint8_t* __restrict__ idx, int N, int H, int W, int C) {
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1, CG = C / 8;
+  const long total = (long)N * Ho * Wo * CG;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total;
+       i += (long)gridDim.x * blockDim.x) {
+    const int cg = (int)(i % CG);
+    long t = i / CG;
+    const int q = (int)(t % Wo); t /= Wo;
+    const int p = (int)(t % Ho);
+    const int n = (int)(t / Ho);
+    float best[8];
+    int slot[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { best[e] = -INFINITY; slot[e] = 0; }
+    bool first = true;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int h = 2 * p - 1 + r;
+      if (h < 0 || h >= H) continue;
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int w = 2 * q - 1 + s;
+        if (w < 0 || w >= W) continue;
+        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(x + (((long)n * H + h) * W + w) * C + cg * 8));
+        const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __bfloat1622float2(hh[e]);
+          if (first || f.x > best[2 * e]) { best[2 * e] = f.x; slot[2 * e] = r * 3 + s; }
+          if (first || f.y > best[2 * e + 1]) { best[2 * e + 1] = f.y; slot[2 * e + 1] = r * 3 + s; }
+        }
+        first = false;
+      }
+    }
+    uint4 pk;
+    __nv_bfloat162* ho = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) ho[e] = __floats2bfloat162_rn(best[2 * e], best[2 * e + 1]);
+    *reinterpret_cast<uint4*>(y + i * 8) = pk;
+    if (idx != nullptr) {
+      uint2 ip;
+      ip.x = slot[0] | (slot[1] << 8) | (slot[2] << 16) | (slot[3] << 24);
+      ip.y = slot[4] | (slot[5] << 8) | (slot[6] << 16) | (slot[7] << 24);
+      *reinterpret_cast<uint2*>(idx + i * 8) = ip;
+    }
+  }
+}
+
+// backward: one thread = 8 channels of one INPUT pixel; gathers from the <=4 windows covering it,
+// applies the ReLU mask of the saved stem output x, accumulates per-channel sums (d beta of bn1).
+__global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ idx,
+                                   const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ dx,
+                                   float* __restrict__ colsum, int N, int H, int W, int C) {
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1, CG = C / 8;
+  const long total = (long)N * H * W * CG;
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  // blockDim.x is a multiple of CG, and the grid stride too, so a thread keeps its channel group
+  const int cg = threadIdx.x % CG;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total;
+       i += (long)gridDim.x * blockDim.x) {
+    long t = i / CG;
+    const int w = (int)(t % W); t /= W;
+    const int h = (int)(t % H);
+    const int n = (int)(t / H);
+    float g[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) g[e] = 0.f;
+    const int p_lo = h >> 1, p_hi = (h + 1) >> 1;     // windows p with 2p-1 <= h <= 2p+1
+    const int q_lo = w >> 1, q_hi = (w + 1) >> 1;
+    for (int p = p_lo; p <= p_hi; ++p) {
+      if (p >= Ho) continue;
+      const int r = h - 2 * p + 1;
+      for (int q = q_lo; q <= q_hi; ++q) {
+        if (q >= Wo) continue;
+        const int s = w - 2 * q + 1;
+        const int want = r * 3 + s;
+        const long o = (((long)n * Ho + p) * Wo + q) * C + cg * 8;
+        const uint2 ip = __ldg(reinterpret_cast<const uint2*>(idx + o));
+        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(dy + o));
+        const __nv_bfloat16* hv = reinterpret_cast<const __nv_bfloat16*>(&raw);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int sl = ((e < 4 ? ip.x : ip.y) >> (8 * (e & 3))) & 0xff;
+          if (sl == want) g[e] += __bfloat162float(hv[e]);
+        }
+      }
+    }
+    const uint4 xr = __ldg(reinterpret_cast<const uint4*>(x + i * 8));
+    const __nv_bfloat16* xv = reinterpret_cast<const __nv_bfloat16*>(&xr);
+    uint4 pk;
+    __nv_bfloat16* ov = reinterpret_cast<__nv_bfloat16*>(&pk);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float v = __bfloat162float(xv[e]) > 0.f ? g[e] : 0.f;
+      ov[e] = __float2bfloat16_rn(v);
+      acc[e] += __bfloat162float(ov[e]);
+    }
+    *reinterpret_cast<uint4*>(dx + i * 8) = pk;
+  }
+  if (colsum != nullptr) {
+    extern __shared__ float sm[];      // [blockDim.x][8]
+#pragma unroll
+    for (int e = 0; e < 8; ++e) sm[threadIdx.x * 8 + e] = acc[e];
+    __syncthreads();
+    if (threadIdx.x < C) {
+      const int g0 = threadIdx.x / 8, e = threadIdx.x % 8;
+      float s = 0.f;
+      for (int t = g0; t < blockDim.x; t += CG) s += sm[t * 8 + e];
+      atomicAdd(colsum + threadIdx.x, s);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// fp32 strided GEMM for the Q-head MLP:  C[m,n] = act(sum_k A(m,k) * B(k,n) + bias[n])
+// A(m,k) = A[m*a_rs + k*a_cs], B(k,n) = B[k*b_rs + n*b_cs].  64x64 tile, 16-deep, 256 threads.
+__global__ void __launch_bounds__(256)
+sgemm_strided_kernel(const float* __restrict__ A, const float* __restrict__ Bm, float* __restrict__ Cm,
+                     const float* __restrict__ bias, int M, int N, int K, long a_rs, long a_cs,
+                     long b_rs, long b_cs, int ldc, int relu) {
+  __shared__ float As[16][64 + 4];
+  __shared__ float Bs[16][64 + 4];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < K; k0 += 16) {
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+      const int e = threadIdx.x + l * 256;       // 0..1023
+      // pick the traversal order that is contiguous in memory for each operand
+      int am, ak, bk, bn;
+      if (a_cs == 1) { ak = e & 15; am = e >> 4; } else { am = e & 63; ak = e >> 6; }
+      if (b_cs == 1) { bn = e & 63; bk = e >> 6; } else { bk = e & 15; bn = e >> 4; }
+      const int gm = m0 + am, gk = k0 + ak;
+      As[ak][am] = (gm < M && gk < K) ? A[gm * a_rs + gk * a_cs] : 0.f;
+      const int gn = n0 + bn, gk2 = k0 + bk;
+      Bs[bk][bn] = (gn < N && gk2 < K) ? Bm[gk2 * b_rs + gn * b_cs] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      float av[4], bv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) av[i] = As[k][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bv[j] = Bs[k][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int gm = m0 + ty * 4 + i;
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gn = n0 + tx * 4 + j;
+      if (gn >= N) continue;
+      float v = acc[i][j];
+      if (bias != nullptr) v += bias[gn];
+      if (relu) v = fmaxf(v, 0.f);
+      Cm[(long)gm * ldc + gn] = v;
+    }
+  }
+}
+
+// dyp = dy * (y > 0 if relu); db[o] = sum_b dyp[b,o]   (one block per 32 columns)
+__global__ void mask_colsum_kernel(const float* __restrict__ dy, const float* __restrict__ y,
+                                   float* __restrict__ dyp, float* __restrict__ db, int B, int O,
+                                   int relu) {
+  const int o = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int r0 = threadIdx.x >> 5, nr = blockDim.x >> 5;
+  float s = 0.f;
+  if (o < O) {
+    for (int b = r0; b < B; b += nr) {
+      float v = dy[(long)b * O + o];
+      if (relu && !(y[(long)b * O + o] > 0.f)) v = 0.f;
+      dyp[(long)b * O + o] = v;
+      s += v;
+    }
+  }
+  __shared__ float sm[32][33];
+  sm[r0][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (r0 == 0 && o < O) {
+    float t = 0.f;
+    for (int i = 0; i < nr; ++i) t += sm[i][threadIdx.x & 31];
+    db[o] = t;
+  }
+}
+
+__global__ void head_flatten_fwd_kernel(const __nv_bfloat16* __restrict__ h, float* __restrict__ flat,
+                                        int B, int P, int C) {
+  const long total = (long)B * P * C;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total;
+       i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long t = i / C;
+    const int p = (int)(t % P);
+    const long b = t / P;
+    flat[(b * C + c) * P + p] = __bfloat162float(h[i]);
+  }
+}
+
+// one block per image: dh[b,p,c] = h > 0 ? dflat[b, c*P + p] : 0 ; dbias[c] += sum
+__global__ void head_flatten_bwd_kernel(const float* __restrict__ dflat, const __nv_bfloat16* __restrict__ h,
+                                        __nv_bfloat16* __restrict__ dh, float* __restrict__ dbias,
+                                        int B, int P, int C) {
+  const int b = blockIdx.x;
+  const int c = threadIdx.x;       // blockDim.x == C
+  float s = 0.f;
+  for (int p = 0; p < P; ++p) {
+    const long i = ((long)b * P + p) * C + c;
+    float v = dflat[((long)b * C + c) * P + p];
+    if (!(__bfloat162float(h[i]) > 0.f)) v = 0.f;
+    const __nv_bfloat16 o = __float2bfloat16_rn(v);
+    dh[i] = o;
+    s += __bfloat162float(o);
+  }
+  if (dbias != nullptr) atomicAdd(dbias + c, s);
+}
+
+// ------------------------------------------------------------------------------------------
+// fused TD epilogue: one thread per (sample, class)
+__global__ void td_epilogue_kernel(const vdqn_td_desc d) {
+  const long total = (long)d.B * d.C;
+  float local = 0.f;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total;
+       i += (long)gridDim.x * blockDim.x) {
+    const long b = i / d.C;
+    const float* qs = d.q_s + i * d.A;
+    const float* qt = d.q_next_target + i * d.A;
+    const float* qsel = d.double_dqn ? d.q_next_online + i * d.A : qt;
+    int best = 0;
+    float bv = qsel[0];
+    for (int a = 1; a < d.A; ++a) {
+      const float v = qsel[a];
+      if (v > bv) { bv = v; best = a; }            // strict > : first maximum wins (torch.argmax)
+    }
+    const float term = (float)d.term[i];
+    const float q_a = qt[best] * (1.f - term);
+    const float rew = (float)d.rew[i];
+    float y = d.linear ? rew + (q_a - 0.1f) : rew + d.gamma * q_a;
+    if (d.clip_rect) y = fminf(fmaxf(y, 0.f), 1.f);
+    const int act = (int)d.act[b];
+    const float diff = qs[act] - y;
+    float l = 0.5f * diff * diff;
+    float mask = 1.f;
+    if (d.use_valid) { mask = (float)d.valid[i]; l *= mask; }
+    local += l;
+    if (d.dq != nullptr) {
+      float* dq = d.dq + i * d.A;
+      for (int a = 0; a < d.A; ++a) dq[a] = (a == act) ? diff * mask * d.inv_count : 0.f;
+    }
+    if (d.best_out != nullptr) d.best_out[i] = best;
+    if (d.y_out != nullptr) d.y_out[i] = y;
+  }
+  __shared__ float red[32];
+  for (int off = 16; off; off >>= 1) local += __shfl_xor_sync(0xffffffffu, local, off);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    for (int off = 16; off; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if (threadIdx.x == 0 && d.loss_out != nullptr) atomicAdd(d.loss_out, v * d.inv_count);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// fused Adam (+ target sync), flat fp32 arenas, 16-byte vectors
+__global__ void __launch_bounds__(256)
+adam_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m,
+            float4* __restrict__ v, float4* __restrict__ target, long n4, float step_size,
+            float beta1, float beta2, float eps, float sqrt_bc2, float grad_scale) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n4;
+       i += (long)gridDim.x * blockDim.x) {
+    float4 pp = p[i], gg = g[i], mm = m[i], vv = v[i];
+    float* P = &pp.x; float* G = &gg.x; float* M = &mm.x; float* V = &vv.x;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float gr = G[e] * grad_scale;
+      M[e] = beta1 * M[e] + (1.f - beta1) * gr;
+      V[e] = beta2 * V[e] + (1.f - beta2) * gr * gr;
+      const float denom = sqrtf(V[e]) / sqrt_bc2 + eps;
+      P[e] = P[e] - step_size * (M[e] / denom);
+    }
+    p[i] = pp; m[i] = mm; v[i] = vv;
+    if (target != nullptr) target[i] = pp;
+  }
+}
+
+static inline int grid_for(long total, int block, int num_sms, int per_sm = 8) {
+  long g = (total + block - 1) / block;
+  const long cap = (long)num_sms * per_sm;
+  if (g > cap) g = cap;
+  return g < 1 ? 1 : (int)g;
+}
+
+}  // namespace vdqn
+
+using namespace vdqn;
+
+#define GET_DEV()                         \
+  DeviceInfo* dev = device_info();        \
+  if (dev == nullptr) return VDQN_ERR_CUDA; \
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v)
+
+extern "C" int vdqn_weight_prep(const vdqn_wprep_desc* d, void* stream_v) {
+  if (d == nullptr || d->w == nullptr || d->w_fwd == nullptr || d->shift == nullptr)
+    return set_error(VDQN_ERR_ARG, "weight_prep: null pointer");
+  GET_DEV();
+  const long total = (long)d->Cout * d->K;
+  weight_prep_kernel<<<grid_for(total, 256, dev->num_sms), 256, 0, stream>>>(*d);
+  VDQN_CHECK_LAUNCH("weight_prep");
+  return VDQN_OK;
+}
+
+extern "C" int vdqn_wgrad_finalize(const vdqn_wgrad_fin_desc* d, void* stream_v) {
+  if (d == nullptr || d->part == nullptr || d->w == nullptr || d->dw == nullptr)
+    return set_error(VDQN_ERR_ARG, "wgrad_finalize: null pointer");
+  GET_DEV();
+  (void)dev;
+  wgrad_finalize_kernel<<<d->Cout, 256, 0, stream>>>(*d);
+  VDQN_CHECK_LAUNCH("wgrad_finalize");
+  return VDQN_OK;
+}
+
+extern "C" int vdqn_stem_pack_f32(const float* x, void* out, int32_t N, int32_t H, int32_t W, void* stream_v) {
+  if (x == nullptr || out == nullptr) return set_error(VDQN_ERR_ARG, "stem_pack: null pointer");
+  if ((H | W) & 1) return set_error(VDQN_ERR_SHAPE, "stem_pack: H and W must be even");
+  GET_DEV();
+  const long total = (long)N * (H / 2) * (W / 2);
+  if (total == 0) return VDQN_OK;
+  stem_pack_kernel<false><<<grid_for(total, 256, dev->num_sms, 16), 256, 0, stream>>>(
+      x, static_cast<__nv_bfloat16*>(out), N, H, W);
+  VDQN_CHECK_LAUNCH("stem_pack_f32");
+  return VDQN_OK;
+}
+
+extern "C" int vdqn_stem_pack_u8(const uint8_t* x, void* out, int32_t N, int32_t H, int32_t W, void* stream_v) {
+  if (x == nullptr || out == nullptr) return set_error(VDQN_ERR_ARG, "stem_pack: null pointer");
+  if ((H | W) & 1) return set_error(VDQN_ERR_SHAPE, "stem_pack: H and W must be even");
+  GET_DEV();
+  const long total = (long)N * (H / 2) * (W / 2);
+  if (total == 0) return VDQN_OK;
+  stem_pack_kernel<true><<<grid_for(total, 256, dev->num_sms, 16), 256, 0, stream>>>(
+      x, static_cast<__nv_bfloat16*>(out), N, H, W);
+  VDQN_CHECK_LAUNCH("stem_pack_u8");
+  return VDQN_OK;
+}
+
+extern "C" int vdqn_maxpool_fwd(const void* x, void* y, uint8_t* idx, int32_t N, int32_t H, int32_t W,
+                                int32_t C, void* stream_v) {
+  if (x == nullptr || y == nullptr) return set_error(VDQN_ERR_ARG, "maxpool_fwd: null pointer");
+  if (C % 8) return set_error(VDQN_ERR_SHAPE, "maxpool: C must be a multiple of 8");
+  GET_DEV();
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  const long total = (long)N * Ho * Wo * (C / 8);
+  if (total == 0) return VDQN_OK;
+  maxpool_fwd_kernel<<<grid_for(total, 256, dev->num_sms, 16), 256, 0, stream>>>(
+      static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), idx, N, H, W, C);
+  VDQN_CHECK_LAUNCH("maxpool_fwd");
+  return VDQN_OK;
+}
+
+extern "C" int vdqn_maxpool_bwd(const void* dy, const uint8_t* idx, const void* x, void* dx, float* colsum,
+                                int32_t N, int32_t H, int32_t W, int32_t C, void* stream_v) {
+  if (dy == nullptr || idx == nullptr || x == nullptr || dx == nullptr)
+    return set_error(VDQN_ERR_ARG, "maxpool_bwd: null pointer");
+  if (C % 8 || 256 % (C / 8) || C > 256) return set_error(VDQN_ERR_SHAPE, "maxpool_bwd: unsupported C=%d", C);
+  GET_DEV();
+  const long total = (long)N * H * W * (C / 8);
+  if (total == 0) return VDQN_OK;
+  maxpool_bwd_kernel<<<grid_for(total, 256, dev->num_sms, 8), 256, 256 * 8 * sizeof(float), stream>>>(
+      static_cast<const __nv_bfloat16*>(dy), idx, static_cast<const __nv_bfloat16*>(x),
+      static_cast<__nv_bfloat16*>(dx), colsum, N, H, W, C);
+  VDQN_CHECK_LAUNCH("maxpool_bwd");
+  return VDQN_OK;
+}
+
+static int launch_sgemm(const float* A, const float* B, float* C, const float* bias, int M, int N, int K,
+                        long a_rs, long a_cs, long b_rs, long b_cs, int ldc, int relu, cudaStream_t stream) {
+  if (M == 0 || N == 0) return VDQN_OK;
+  dim3 grid((N + 63) / 64, (M + 63) / 64);
+  sgemm_strided_kernel<<<grid, 256, 0, stream>>>(A, B, C, bias, M, N, K, a_rs, a_cs, b_rs, b_cs, ldc, relu);
+  VDQN_CHECK_LAUNCH("sgemm");
+  return VDQN_OK;
+}
+
+extern "C" int vdqn_linear_fwd(const float* x, const float* w, const float* bias, float* y, int32_t B,
+                               int32_t K, int32_t O, int32_t relu, void* stream_v) {
+  if (x == nullptr || w == nullptr || y == nullptr) return set_error(VDQN_ERR_ARG, "linear_fwd: null pointer");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  // y[b,o] = sum_k x[b,k] * w[o,k]
+  return launch_sgemm(x, w, y, bias, B, O, K, K, 1, 1, K, O, relu, stream);
+}
+
+extern "C" int vdqn_linear_bwd(const float* x, const float* w, const float* y, float* dy, float* dx,
+                               float* dw, float* db, int32_t B, int32_t K, int32_t O, int32_t relu,
+                               void* stream_v) {
+  if (x == nullptr || w == nullptr || dy == nullptr || dw == nullptr || db == nullptr)
+    return set_error(VDQN_ERR_ARG, "linear_bwd: null pointer");
+  if (relu && y == nullptr) return set_error(VDQN_ERR_ARG, "linear_bwd: relu needs y");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  if (B == 0) return VDQN_OK;
+  // dy is overwritten in place with the masked gradient (the caller owns it as scratch)
+  float* dyp = dy;
+  mask_colsum_kernel<<<(O + 31) / 32, 1024, 0, stream>>>(dy, y, dyp, db, B, O, relu);
+  VDQN_CHECK_LAUNCH("mask_colsum");
+  // dw[o,k] = sum_b dyp[b,o] * x[b,k]
+  int rc = launch_sgemm(dyp, x, dw, nullptr, O, K, B, 1, O, K, 1, K, 0, stream);
+  if (rc != VDQN_OK) return rc;
+  // dx[b,k] = sum_o dyp[b,o] * w[o,k]
+  if (dx != nullptr) rc = launch_sgemm(dyp, w, dx, nullptr, B, K, O, O, 1, K, 1, K, 0, stream);
+  return rc;
+}
+
+extern "C" int vdqn_head_flatten_fwd(const void* h, float* flat, int32_t B, int32_t P, int32_t C, void* stream_v) {
+  if (h == nullptr || flat == nullptr) return set_error(VDQN_ERR_ARG, "head_flatten_fwd: null pointer");
+  GET_DEV();
+  const long total = (long)B * P * C;
+  if (total == 0) return VDQN_OK;
+  head_flatten_fwd_kernel<<<grid_for(total, 256, dev->num_sms), 256, 0, stream>>>(
+      static_cast<const __nv_bfloat16*>(h), flat, B, P, C);
+  VDQN_CHECK_LAUNCH("head_flatten_fwd");
+  return VDQN_OK;
+}
+
+extern "C" int vdqn_head_flatten_bwd(const float* dflat, const void* h, void* dh, float* dbias, int32_t B,
+                                     int32_t P, int32_t C, void* stream_v) {
+  if (dflat == nullptr || h == nullptr || dh == nullptr) return set_error(VDQN_ERR_ARG, "head_flatten_bwd: null pointer");
+  if (C > 1024) return set_error(VDQN_ERR_SHAPE, "head_flatten_bwd: C too large");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  if (B == 0) return VDQN_OK;
+  head_flatten_bwd_kernel<<<B, C, 0, stream>>>(dflat, static_cast<const __nv_bfloat16*>(h),
+                                               static_cast<__nv_bfloat16*>(dh), dbias, B, P, C);
+  VDQN_CHECK_LAUNCH("head_flatten_bwd");
+  return VDQN_OK;
+}
+
+extern "C" int vdqn_td_epilogue(const vdqn_td_desc* d, void* stream_v) {
+  if (d == nullptr || d->q_s == nullptr || d->q_next_target == nullptr || d->act == nullptr ||
+      d->rew == nullptr || d->term == nullptr)
+    return set_error(VDQN_ERR_ARG, "td_epilogue: null pointer");
+  if (d->double_dqn && d->q_next_online == nullptr)
+    return set_error(VDQN_ERR_ARG, "td_epilogue: double DQN needs q_next_online");
+  if (d->use_valid && d->valid == nullptr) return set_error(VDQN_ERR_ARG, "td_epilogue: valid mask missing");
+  if (d->A < 1 || d->C < 1 || d->B < 0) return set_error(VDQN_ERR_SHAPE, "td_epilogue: bad shape");
+  GET_DEV();
+  const long total = (long)d->B * d->C;
+  if (total == 0) return VDQN_OK;
+  td_epilogue_kernel<<<grid_for(total, 256, dev->num_sms, 8), 256, 0, stream>>>(*d);
+  VDQN_CHECK_LAUNCH("td_epilogue");
+  return VDQN_OK;
+}
+
+extern "C" int vdqn_adam_fused(float* p, const float* g, float* m, float* v, float* target, int64_t n,
+                               float lr, float beta1, float beta2, float eps, int32_t step,
+                               float grad_scale, void* stream_v) {
+  if (p == nullptr || g == nullptr || m == nullptr || v == nullptr)
+    return set_error(VDQN_ERR_ARG, "adam: null pointer");
+  if (n % 4 != 0) return set_error(VDQN_ERR_SHAPE, "adam: arena length must be a multiple of 4");
+  if (step < 1) return set_error(VDQN_ERR_ARG, "adam: step must be >= 1");
+  if ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+       reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(target)) & 15)
+    return set_error(VDQN_ERR_ARG, "adam: arenas must be 16-byte aligned");
+  GET_DEV();
+  if (n == 0) return VDQN_OK;
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  const float step_size = (float)((double)lr / bc1);
+  const float sqrt_bc2 = (float)sqrt(bc2);
+  adam_kernel<<<grid_for(n / 4, 256, dev->num_sms, 8), 256, 0, stream>>>(
+      reinterpret_cast<float4*>(p), reinterpret_cast<const float4*>(g), reinterpret_cast<float4*>(m),
+      reinterpret_cast<float4*>(v), reinterpret_cast<float4*>(target), n / 4, step_size, beta1, beta2,
+      eps, sqrt_bc2, grad_scale);
+  VDQN_CHECK_LAUNCH("adam");
+  return VDQN_OK;
+}

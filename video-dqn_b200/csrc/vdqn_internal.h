@@ -1,0 +1,40 @@
+// Internal helpers shared by the translation units of libvdqn.so.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/vdqn.h"
+
+namespace vdqn {
+
+struct DeviceInfo {
+  int device;
+  int num_sms;
+};
+
+// printf-style; stores a thread-local message and returns `code`.
+int set_error(int code, const char* fmt, ...);
+// Lazily initialised (vdqn_init on the current device); nullptr + error on failure.
+DeviceInfo* device_info();
+
+// NHWC bf16 activation tensor, TMA im2col mode.  lower/upper corners are the bounding box of
+// the filter window's base pixel (lower = -pad, upper = pad_hi - (R-1)*dil).
+int make_im2col_map(CUtensorMap* map, const void* base, int N, int H, int W, int C,
+                    int channels_per_pixel, int pixels_per_column, int stride,
+                    int lower_h, int lower_w, int upper_h, int upper_w, int swizzle_bytes);
+// Row-major bf16 matrix [rows][cols] (cols contiguous), box [box_rows][box_cols].
+int make_tiled_map_2d(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows,
+                      uint32_t box_cols, uint32_t box_rows, int swizzle_bytes,
+                      uint64_t row_stride_elems = 0);
+
+inline int ceil_div(long a, long b) { return (int)((a + b - 1) / b); }
+
+#define VDQN_CHECK_LAUNCH(what)                                                         \
+  do {                                                                                  \
+    cudaError_t e__ = cudaGetLastError();                                               \
+    if (e__ != cudaSuccess)                                                             \
+      return ::vdqn::set_error(VDQN_ERR_CUDA, what ": %s", cudaGetErrorString(e__));    \
+  } while (0)
+
+}  // namespace vdqn

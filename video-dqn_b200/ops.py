@@ -1,0 +1,268 @@
+"""Tensor-level wrappers over the C ABI (include/vdqn.h).  Each takes CUDA torch tensors, checks
+shapes/dtypes (ValueError before launch, mirroring the reference's `Exception("bad shape")`
+style of failing early) and enqueues on torch's current stream.  No fallback paths."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+bf16 = torch.bfloat16
+
+
+def _req(cond, msg):
+    if not cond:
+        raise ValueError(msg)
+
+
+def _cuda(t, dtype, name):
+    _req(t.is_cuda, f"{name} must be a CUDA tensor")
+    _req(t.dtype == dtype, f"{name} must be {dtype}, got {t.dtype}")
+    _req(t.is_contiguous(), f"{name} must be contiguous")
+    return t
+
+
+def conv_out_hw(H, W, R, S, stride, pad_lo, pad_hi, dil=1):
+    return ((H + pad_lo + pad_hi - (R - 1) * dil - 1) // stride + 1,
+            (W + pad_lo + pad_hi - (S - 1) * dil - 1) // stride + 1)
+
+
+def conv_gemm(x, w, stride=1, pad_lo=0, pad_hi=None, *, shift=None, residual=None, mask_src=None,
+              relu=False, out_f32=False, colsum=None, out=None, out2=None, out_scatter=1,
+              tile_n=0, max_ctas=0, dil=1):
+    """x [N,H,W,Cin] bf16, w [Cout,R,S,Cin] bf16 -> out [N,Ho,Wo,Cout] (or zero-dilated
+    [N,2Ho,2Wo,Cout] when out_scatter == 2; `out` must then be pre-zeroed)."""
+    lib = L.load()
+    _cuda(x, bf16, "x"); _cuda(w, bf16, "w")
+    _req(x.dim() == 4 and w.dim() == 4 and x.shape[3] == w.shape[3], "bad shape")
+    N, H, W_, Cin = x.shape
+    Cout, R, S, _ = w.shape
+    pad_hi = pad_lo if pad_hi is None else pad_hi
+    Ho, Wo = conv_out_hw(H, W_, R, S, stride, pad_lo, pad_hi, dil)
+    odt = torch.float32 if out_f32 else bf16
+    if out is None:
+        if out_scatter == 2:
+            out = torch.zeros(N, 2 * Ho, 2 * Wo, Cout, device=x.device, dtype=odt)
+        else:
+            out = torch.empty(N, Ho, Wo, Cout, device=x.device, dtype=odt)
+    _cuda(out, odt, "out")
+    d = L.ConvDesc()
+    d.x, d.w, d.out = x.data_ptr(), w.data_ptr(), out.data_ptr()
+    d.out2 = L.ptr(out2)
+    d.shift = L.ptr(shift); d.residual = L.ptr(residual); d.mask_src = L.ptr(mask_src)
+    d.colsum = L.ptr(colsum)
+    if shift is not None:
+        _cuda(shift, torch.float32, "shift"); _req(shift.numel() == Cout, "bad shape")
+    if residual is not None:
+        _cuda(residual, bf16, "residual"); _req(residual.numel() == N * Ho * Wo * Cout, "bad shape")
+    if mask_src is not None:
+        _cuda(mask_src, bf16, "mask_src"); _req(mask_src.numel() == N * Ho * Wo * Cout, "bad shape")
+    if colsum is not None:
+        _cuda(colsum, torch.float32, "colsum"); _req(colsum.numel() == Cout, "bad shape")
+    if out2 is not None:
+        _cuda(out2, bf16, "out2"); _req(out2.numel() == N * 4 * Ho * Wo * Cout, "bad shape")
+    d.N, d.H, d.W, d.Cin, d.Cout, d.R, d.S = N, H, W_, Cin, Cout, R, S
+    d.stride, d.dil, d.pad_lo, d.pad_hi = stride, dil, pad_lo, pad_hi
+    d.ldc = d.ldr = d.ldm = d.out2_ld = Cout
+    d.out_scatter = out_scatter
+    d.flags = (L.EPI_RELU if relu else 0) | (L.EPI_OUT_F32 if out_f32 else 0)
+    d.tile_n, d.max_ctas = tile_n, max_ctas
+    L.check(lib.vdqn_conv_gemm(C.byref(d), L.stream_ptr()), "conv_gemm")
+    return out
+
+
+def conv_wgrad(x, dy, R, S, stride=1, pad_lo=0, pad_hi=None, *, splits=1, part=None, max_ctas=0, dil=1):
+    """x [N,H,W,Cin] bf16, dy [N,Ho,Wo,Cout] bf16 -> part [splits,Cout,R*S*Cin] fp32."""
+    lib = L.load()
+    _cuda(x, bf16, "x"); _cuda(dy, bf16, "dy")
+    N, H, W_, Cin = x.shape
+    pad_hi = pad_lo if pad_hi is None else pad_hi
+    Ho, Wo = conv_out_hw(H, W_, R, S, stride, pad_lo, pad_hi, dil)
+    Cout = dy.shape[-1]
+    _req(dy.numel() == N * Ho * Wo * Cout, "bad shape")
+    K = R * S * Cin
+    if part is None:
+        part = torch.empty(splits, Cout, K, device=x.device, dtype=torch.float32)
+    _cuda(part, torch.float32, "part"); _req(part.numel() >= splits * Cout * K, "bad shape")
+    d = L.WgradDesc()
+    d.x, d.dy, d.part = x.data_ptr(), dy.data_ptr(), part.data_ptr()
+    d.N, d.H, d.W, d.Cin, d.Cout, d.R, d.S = N, H, W_, Cin, Cout, R, S
+    d.stride, d.dil, d.pad_lo, d.pad_hi = stride, dil, pad_lo, pad_hi
+    d.ldy, d.splits, d.max_ctas = Cout, splits, max_ctas
+    L.check(lib.vdqn_conv_wgrad(C.byref(d), L.stream_ptr()), "conv_wgrad")
+    return part
+
+
+def wgrad_finalize(part, w, dw, *, splits, Cout, Cin, R, S, K, kmap=0, gamma=None, var=None,
+                   mean=None, dbeta=None, dgamma=None, eps=1e-5):
+    lib = L.load()
+    d = L.WgradFinDesc()
+    d.part, d.w, d.dw = part.data_ptr(), w.data_ptr(), dw.data_ptr()
+    d.gamma, d.var, d.mean = L.ptr(gamma), L.ptr(var), L.ptr(mean)
+    d.dbeta, d.dgamma = L.ptr(dbeta), L.ptr(dgamma)
+    d.splits, d.Cout, d.Cin, d.R, d.S, d.K, d.kmap = splits, Cout, Cin, R, S, K, kmap
+    d.eps = eps
+    L.check(lib.vdqn_wgrad_finalize(C.byref(d), L.stream_ptr()), "wgrad_finalize")
+    return dw
+
+
+def weight_prep(w, w_fwd, shift, *, w_dgrad=None, gamma=None, beta=None, mean=None, var=None,
+                bias=None, kmap=0, eps=1e-5):
+    """w OIHW fp32 -> w_fwd bf16 [Cout, K] (+ w_dgrad bf16 [Cin, R*S*Cout]) and shift [Cout]."""
+    lib = L.load()
+    _cuda(w, torch.float32, "w")
+    Cout, Cin, R, S = w.shape
+    K = w_fwd.numel() // Cout
+    d = L.WprepDesc()
+    d.w, d.w_fwd, d.shift, d.w_dgrad = w.data_ptr(), w_fwd.data_ptr(), shift.data_ptr(), L.ptr(w_dgrad)
+    d.gamma, d.beta, d.mean, d.var, d.bias = (L.ptr(gamma), L.ptr(beta), L.ptr(mean), L.ptr(var),
+                                              L.ptr(bias))
+    d.Cout, d.Cin, d.R, d.S, d.K, d.kmap = Cout, Cin, R, S, K, kmap
+    d.eps = eps
+    L.check(lib.vdqn_weight_prep(C.byref(d), L.stream_ptr()), "weight_prep")
+
+
+def stem_pack(x, out=None):
+    """NCHW fp32 [N,3,H,W] or uint8 HWC [N,H,W,3] -> space-to-depth [N,H/2,W/2,16] bf16."""
+    lib = L.load()
+    _req(x.is_cuda and x.is_contiguous() and x.dim() == 4, "bad shape")
+    if x.dtype == torch.uint8:
+        N, H, W_, c = x.shape
+        fn = lib.vdqn_stem_pack_u8
+    else:
+        _req(x.dtype == torch.float32, "frames must be fp32 NCHW or uint8 NHWC")
+        N, c, H, W_ = x.shape
+        fn = lib.vdqn_stem_pack_f32
+    _req(c == 3, "bad shape")
+    if out is None:
+        out = torch.empty(N, H // 2, W_ // 2, 16, device=x.device, dtype=bf16)
+    L.check(fn(x.data_ptr(), out.data_ptr(), N, H, W_, L.stream_ptr()), "stem_pack")
+    return out
+
+
+def maxpool_fwd(x, y=None, idx=None, save_idx=False):
+    lib = L.load()
+    _cuda(x, bf16, "x")
+    N, H, W_, Cc = x.shape
+    Ho, Wo = (H - 1) // 2 + 1, (W_ - 1) // 2 + 1
+    if y is None:
+        y = torch.empty(N, Ho, Wo, Cc, device=x.device, dtype=bf16)
+    if save_idx and idx is None:
+        idx = torch.empty(N, Ho, Wo, Cc, device=x.device, dtype=torch.uint8)
+    L.check(lib.vdqn_maxpool_fwd(x.data_ptr(), y.data_ptr(), L.ptr(idx), N, H, W_, Cc, L.stream_ptr()),
+            "maxpool_fwd")
+    return y, idx
+
+
+def maxpool_bwd(dy, idx, x, dx=None, colsum=None):
+    lib = L.load()
+    _cuda(dy, bf16, "dy"); _cuda(x, bf16, "x"); _cuda(idx, torch.uint8, "idx")
+    N, H, W_, Cc = x.shape
+    if dx is None:
+        dx = torch.empty_like(x)
+    L.check(lib.vdqn_maxpool_bwd(dy.data_ptr(), idx.data_ptr(), x.data_ptr(), dx.data_ptr(),
+                                 L.ptr(colsum), N, H, W_, Cc, L.stream_ptr()), "maxpool_bwd")
+    return dx
+
+
+def linear_fwd(x, w, bias, relu, y=None):
+    lib = L.load()
+    _cuda(x, torch.float32, "x"); _cuda(w, torch.float32, "w")
+    B, K = x.shape
+    O = w.shape[0]
+    _req(w.shape[1] == K, "bad shape")
+    if y is None:
+        y = torch.empty(B, O, device=x.device, dtype=torch.float32)
+    L.check(lib.vdqn_linear_fwd(x.data_ptr(), w.data_ptr(), L.ptr(bias), y.data_ptr(), B, K, O,
+                                int(relu), L.stream_ptr()), "linear_fwd")
+    return y
+
+
+def linear_bwd(x, w, y, dy, dw, db, relu, dx=None, need_dx=True):
+    """dy is overwritten with the ReLU-masked gradient."""
+    lib = L.load()
+    B, K = x.shape
+    O = w.shape[0]
+    if need_dx and dx is None:
+        dx = torch.empty(B, K, device=x.device, dtype=torch.float32)
+    L.check(lib.vdqn_linear_bwd(x.data_ptr(), w.data_ptr(), L.ptr(y), dy.data_ptr(),
+                                L.ptr(dx) if need_dx else None, dw.data_ptr(), db.data_ptr(),
+                                B, K, O, int(relu), L.stream_ptr()), "linear_bwd")
+    return dx
+
+
+def head_flatten_fwd(h, flat=None):
+    lib = L.load()
+    _cuda(h, bf16, "h")
+    B = h.shape[0]
+    Cc = h.shape[-1]
+    P = h.numel() // (B * Cc)
+    if flat is None:
+        flat = torch.empty(B, Cc * P, device=h.device, dtype=torch.float32)
+    L.check(lib.vdqn_head_flatten_fwd(h.data_ptr(), flat.data_ptr(), B, P, Cc, L.stream_ptr()),
+            "head_flatten_fwd")
+    return flat
+
+
+def head_flatten_bwd(dflat, h, dh=None, dbias=None):
+    lib = L.load()
+    B = h.shape[0]
+    Cc = h.shape[-1]
+    P = h.numel() // (B * Cc)
+    if dh is None:
+        dh = torch.empty_like(h)
+    L.check(lib.vdqn_head_flatten_bwd(dflat.data_ptr(), h.data_ptr(), dh.data_ptr(), L.ptr(dbias),
+                                      B, P, Cc, L.stream_ptr()), "head_flatten_bwd")
+    return dh
+
+
+def td_epilogue(q_s, q_next_online, q_next_target, act, rew, term, valid=None, *, gamma=0.99,
+                double_dqn=True, clip_rect=True, linear=False, use_valid=False, inv_count=None,
+                dq=None, loss=None, best=None, y=None, want_aux=False):
+    """Fused Double-DQN TD loss + gradient.  Returns (loss[1] fp32, dq [B,C,A] fp32, best, y)."""
+    lib = L.load()
+    for t, n in ((q_s, "q_s"), (q_next_target, "q_next_target")):
+        _cuda(t, torch.float32, n)
+    _req(q_s.dim() == 3 and q_s.shape == q_next_target.shape, "bad shape")
+    B, Cc, A = q_s.shape
+    for t, n in ((act, "act"), (rew, "rew"), (term, "term")):
+        _cuda(t, torch.int64, n)
+    _req(act.numel() == B and rew.numel() == B * Cc and term.numel() == B * Cc, "bad shape")
+    if q_next_online is not None:
+        _cuda(q_next_online, torch.float32, "q_next_online")
+        _req(q_next_online.shape == q_s.shape, "bad shape")
+    if use_valid:
+        _cuda(valid, torch.int64, "valid_mask")
+    dev = q_s.device
+    if dq is None:
+        dq = torch.empty_like(q_s)
+    if loss is None:
+        loss = torch.zeros(1, device=dev, dtype=torch.float32)
+    if want_aux:
+        best = torch.empty(B, Cc, device=dev, dtype=torch.int64) if best is None else best
+        y = torch.empty(B, Cc, device=dev, dtype=torch.float32) if y is None else y
+    d = L.TdDesc()
+    d.q_s, d.q_next_online, d.q_next_target = q_s.data_ptr(), L.ptr(q_next_online), q_next_target.data_ptr()
+    d.act, d.rew, d.term, d.valid = act.data_ptr(), rew.data_ptr(), term.data_ptr(), L.ptr(valid)
+    d.dq, d.loss_out, d.best_out, d.y_out = dq.data_ptr(), loss.data_ptr(), L.ptr(best), L.ptr(y)
+    d.B, d.C, d.A = B, Cc, A
+    d.gamma = gamma
+    d.inv_count = (1.0 / (B * Cc)) if inv_count is None else inv_count
+    d.double_dqn, d.clip_rect, d.linear, d.use_valid = int(double_dqn), int(clip_rect), int(linear), int(use_valid)
+    L.check(lib.vdqn_td_epilogue(C.byref(d), L.stream_ptr()), "td_epilogue")
+    return loss, dq, best, y
+
+
+def adam_fused(p, g, m, v, *, lr, step, betas=(0.9, 0.999), eps=1e-8, target=None, grad_scale=1.0):
+    lib = L.load()
+    for t, n in ((p, "p"), (g, "g"), (m, "m"), (v, "v")):
+        _cuda(t, torch.float32, n)
+    n = p.numel()
+    _req(g.numel() == n and m.numel() == n and v.numel() == n, "bad shape")
+    if target is not None:
+        _cuda(target, torch.float32, "target"); _req(target.numel() == n, "bad shape")
+    L.check(lib.vdqn_adam_fused(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), L.ptr(target),
+                                n, lr, betas[0], betas[1], eps, step, grad_scale, L.stream_ptr()),
+            "adam_fused")
