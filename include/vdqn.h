@@ -189,8 +189,13 @@ int vdqn_td_epilogue(const vdqn_td_desc* d, void* stream);
  *   m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;  p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
  * if target != NULL: target[i] = p_new[i]. */
 int vdqn_adam_fused(float* p, const float* g, float* m, float* v, float* target, int64_t n,
-                    float lr, float beta1, float beta2, float eps, int32_t step, float grad_scale,
+                    double lr, double beta1, double beta2, double eps, int32_t step, float grad_scale,
                     void* stream);
+/* Same update for CUDA-graph replay: the step counter lives in HBM (`step_dev`, incremented by the
+ * call) and the bias-correction scalars are recomputed on the device into `scalars_dev[2]`. */
+int vdqn_adam_fused_graph(float* p, const float* g, float* m, float* v, float* target, int64_t n,
+                          double lr, double beta1, double beta2, double eps, float grad_scale,
+                          int32_t* step_dev, float* scalars_dev, void* stream);
 
 #ifdef __cplusplus
 }

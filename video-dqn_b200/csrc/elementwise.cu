@@ -432,7 +432,12 @@ __global__ void td_epilogue_kernel(const vdqn_td_desc d) {
 __global__ void __launch_bounds__(256)
 adam_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m,
             float4* __restrict__ v, float4* __restrict__ target, long n4, float step_size,
-            float beta1, float beta2, float eps, float sqrt_bc2, float grad_scale) {
+            float beta1, float beta2, float eps, float sqrt_bc2, float grad_scale,
+            const float* __restrict__ dev_scalars) {
+  if (dev_scalars != nullptr) {          // graph-replay mode: step-dependent scalars live in HBM
+    step_size = dev_scalars[0];
+    sqrt_bc2 = dev_scalars[1];
+  }
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n4;
        i += (long)gridDim.x * blockDim.x) {
     float4 pp = p[i], gg = g[i], mm = m[i], vv = v[i];
@@ -448,6 +453,16 @@ adam_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __rest
     p[i] = pp; m[i] = mm; v[i] = vv;
     if (target != nullptr) target[i] = pp;
   }
+}
+
+// step counter and bias corrections kept on the device so a captured CUDA graph can be replayed
+__global__ void adam_scalars_kernel(int* step, float* out, double lr, double b1, double b2) {
+  const int t = *step + 1;
+  *step = t;
+  const double bc1 = 1.0 - pow(b1, (double)t);
+  const double bc2 = 1.0 - pow(b2, (double)t);
+  out[0] = (float)(lr / bc1);
+  out[1] = (float)sqrt(bc2);
 }
 
 static inline int grid_for(long total, int block, int num_sms, int per_sm = 8) {
@@ -615,26 +630,51 @@ extern "C" int vdqn_td_epilogue(const vdqn_td_desc* d, void* stream_v) {
   return VDQN_OK;
 }
 
-extern "C" int vdqn_adam_fused(float* p, const float* g, float* m, float* v, float* target, int64_t n,
-                               float lr, float beta1, float beta2, float eps, int32_t step,
-                               float grad_scale, void* stream_v) {
+static int adam_check(const float* p, const float* g, const float* m, const float* v, const float* target,
+                      int64_t n) {
   if (p == nullptr || g == nullptr || m == nullptr || v == nullptr)
     return set_error(VDQN_ERR_ARG, "adam: null pointer");
   if (n % 4 != 0) return set_error(VDQN_ERR_SHAPE, "adam: arena length must be a multiple of 4");
-  if (step < 1) return set_error(VDQN_ERR_ARG, "adam: step must be >= 1");
   if ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
        reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(target)) & 15)
     return set_error(VDQN_ERR_ARG, "adam: arenas must be 16-byte aligned");
+  return VDQN_OK;
+}
+
+extern "C" int vdqn_adam_fused(float* p, const float* g, float* m, float* v, float* target, int64_t n,
+                               double lr, double beta1, double beta2, double eps, int32_t step,
+                               float grad_scale, void* stream_v) {
+  int rc = adam_check(p, g, m, v, target, n);
+  if (rc != VDQN_OK) return rc;
+  if (step < 1) return set_error(VDQN_ERR_ARG, "adam: step must be >= 1");
   GET_DEV();
   if (n == 0) return VDQN_OK;
-  const double bc1 = 1.0 - pow((double)beta1, (double)step);
-  const double bc2 = 1.0 - pow((double)beta2, (double)step);
-  const float step_size = (float)((double)lr / bc1);
-  const float sqrt_bc2 = (float)sqrt(bc2);
+  const double bc1 = 1.0 - pow(beta1, (double)step);
+  const double bc2 = 1.0 - pow(beta2, (double)step);
   adam_kernel<<<grid_for(n / 4, 256, dev->num_sms, 8), 256, 0, stream>>>(
       reinterpret_cast<float4*>(p), reinterpret_cast<const float4*>(g), reinterpret_cast<float4*>(m),
-      reinterpret_cast<float4*>(v), reinterpret_cast<float4*>(target), n / 4, step_size, beta1, beta2,
-      eps, sqrt_bc2, grad_scale);
+      reinterpret_cast<float4*>(v), reinterpret_cast<float4*>(target), n / 4, (float)(lr / bc1),
+      (float)beta1, (float)beta2, (float)eps, (float)sqrt(bc2), grad_scale, nullptr);
+  VDQN_CHECK_LAUNCH("adam");
+  return VDQN_OK;
+}
+
+extern "C" int vdqn_adam_fused_graph(float* p, const float* g, float* m, float* v, float* target,
+                                     int64_t n, double lr, double beta1, double beta2, double eps,
+                                     float grad_scale, int32_t* step_dev, float* scalars_dev,
+                                     void* stream_v) {
+  int rc = adam_check(p, g, m, v, target, n);
+  if (rc != VDQN_OK) return rc;
+  if (step_dev == nullptr || scalars_dev == nullptr)
+    return set_error(VDQN_ERR_ARG, "adam_graph: device step counter / scalar buffer missing");
+  GET_DEV();
+  adam_scalars_kernel<<<1, 1, 0, stream>>>(step_dev, scalars_dev, lr, beta1, beta2);
+  VDQN_CHECK_LAUNCH("adam_scalars");
+  if (n == 0) return VDQN_OK;
+  adam_kernel<<<grid_for(n / 4, 256, dev->num_sms, 8), 256, 0, stream>>>(
+      reinterpret_cast<float4*>(p), reinterpret_cast<const float4*>(g), reinterpret_cast<float4*>(m),
+      reinterpret_cast<float4*>(v), reinterpret_cast<float4*>(target), n / 4, 0.f, (float)beta1,
+      (float)beta2, (float)eps, 1.f, grad_scale, scalars_dev);
   VDQN_CHECK_LAUNCH("adam");
   return VDQN_OK;
 }

@@ -1,0 +1,280 @@
+"""Forward / backward schedule of the Q-network over the C-ABI kernels.
+
+The network is the reference's `extra_capacity` HabitatDQNMultiAction
+(archs/HabitatDQNMultiAction.py:27-31,44-54): ResNet-18 trunk (torchvision BasicBlocks,
+BatchNorm in eval mode during training, :37-40) -> Conv2d(512,64,3)+ReLU -> Flatten ->
+Linear 1600F-512-256-5A.  Layout in HBM: activations NHWC bf16, trunk/head conv weights bf16
+with the BN scale folded in (both the forward [Cout][R][S][Cin] and the data-gradient
+[Cin][R][S][Cout] flipped form), fp32 master parameters / gradients / Adam state in flat arenas,
+the Q-head MLP entirely in fp32.
+
+Everything here only *enqueues* kernels on the current stream (no host sync, no allocation when
+a preallocated Workspace is passed), so a whole step can be captured in a CUDA graph.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional
+
+import torch
+
+from . import ops
+
+bf16 = torch.bfloat16
+BN_EPS = 1e-5
+NUM_SMS_TARGET_UNITS = 296          # ~2 waves of 148 SMs for the split-K weight gradient
+
+
+@dataclass
+class ConvSpec:
+    name: str            # short id
+    wkey: str            # state-dict key of the OIHW fp32 weight (under resnet.* / features.8)
+    bn: Optional[str]    # BN prefix or None
+    bias: Optional[str]  # conv bias key or None
+    cin: int
+    cout: int
+    k: int               # filter size of the GEMM form (4 for the packed stem)
+    stride: int          # stride of the GEMM form
+    pad_lo: int
+    pad_hi: int
+    in_hw: int           # input spatial size of the GEMM form
+    out_hw: int
+    kmap: int = 0
+    gemm_cin: int = 0    # channels of the GEMM form (16 for the packed stem)
+
+    @property
+    def K(self):
+        return self.k * self.k * self.gemm_cin
+
+
+@dataclass
+class BlockSpec:
+    conv1: ConvSpec
+    conv2: ConvSpec
+    ds: Optional[ConvSpec]
+    in_hw: int
+    out_hw: int
+    cin: int
+    cout: int
+    stride: int
+
+
+@dataclass
+class NetPlan:
+    stem: ConvSpec
+    blocks: List[BlockSpec]
+    head: ConvSpec
+    action_dim: int
+    num_classes: int
+    num_frames: int
+    convs: List[ConvSpec] = field(default_factory=list)
+
+
+def make_plan(action_dim: int, num_classes: int = 5, num_frames: int = 1) -> NetPlan:
+    stem = ConvSpec("stem", "resnet.conv1.weight", "resnet.bn1", None, 3, 64, 4, 1, 2, 1, 112, 112,
+                    kmap=1, gemm_cin=16)
+    blocks = []
+    hw, cin = 56, 64
+    for li, (cout, stride) in enumerate(((64, 1), (128, 2), (256, 2), (512, 2)), start=1):
+        for b in range(2):
+            s = stride if b == 0 else 1
+            ohw = hw // s
+            p = f"resnet.layer{li}.{b}."
+            c1 = ConvSpec(f"l{li}.{b}.c1", p + "conv1.weight", p + "bn1", None, cin, cout, 3, s, 1, 1,
+                          hw, ohw, gemm_cin=cin)
+            c2 = ConvSpec(f"l{li}.{b}.c2", p + "conv2.weight", p + "bn2", None, cout, cout, 3, 1, 1, 1,
+                          ohw, ohw, gemm_cin=cout)
+            ds = None
+            if b == 0 and s != 1:
+                ds = ConvSpec(f"l{li}.{b}.ds", p + "downsample.0.weight", p + "downsample.1", None,
+                              cin, cout, 1, s, 0, 0, hw, ohw, gemm_cin=cin)
+            blocks.append(BlockSpec(c1, c2, ds, hw, ohw, cin, cout, s))
+            hw, cin = ohw, cout
+    head = ConvSpec("head", "features.8.weight", None, "features.8.bias", 512, 64, 3, 1, 0, 0, 7, 5,
+                    gemm_cin=512)
+    plan = NetPlan(stem, blocks, head, action_dim, num_classes, num_frames)
+    plan.convs = [stem] + [c for b in blocks for c in (b.conv1, b.conv2, b.ds) if c is not None] + [head]
+    return plan
+
+
+def wgrad_splits(spec: ConvSpec, n_img: int) -> int:
+    M = n_img * spec.out_hw * spec.out_hw
+    co_tiles = (spec.cout + 127) // 128
+    per = 4 if spec.gemm_cin % 64 == 0 else 16
+    slab = 64 if spec.gemm_cin % 64 == 0 else 16
+    groups = -(-(spec.K // slab) // per)
+    s = max(1, round(NUM_SMS_TARGET_UNITS / (co_tiles * groups)))
+    return int(max(1, min(s, M // 512 if M >= 512 else 1)))
+
+
+class PreparedWeights:
+    """bf16 GEMM operands + fp32 shifts for every conv, regenerated from the fp32 masters."""
+
+    def __init__(self, plan: NetPlan, device):
+        self.plan = plan
+        self.w_fwd: Dict[str, torch.Tensor] = {}
+        self.w_dgrad: Dict[str, torch.Tensor] = {}
+        self.shift: Dict[str, torch.Tensor] = {}
+        for c in plan.convs:
+            self.w_fwd[c.name] = torch.empty(c.cout, c.k, c.k, c.gemm_cin, device=device, dtype=bf16)
+            if c.kmap == 0:
+                self.w_dgrad[c.name] = torch.empty(c.cin, c.k, c.k, c.cout, device=device, dtype=bf16)
+            self.shift[c.name] = torch.empty(c.cout, device=device, dtype=torch.float32)
+
+    def prepare(self, P: Dict[str, torch.Tensor]):
+        for c in self.plan.convs:
+            kw = {}
+            if c.bn is not None:
+                kw = dict(gamma=P[c.bn + ".weight"], beta=P[c.bn + ".bias"],
+                          mean=P[c.bn + ".running_mean"], var=P[c.bn + ".running_var"])
+            if c.bias is not None:
+                kw["bias"] = P[c.bias]
+            ops.weight_prep(P[c.wkey], self.w_fwd[c.name], self.shift[c.name],
+                            w_dgrad=self.w_dgrad.get(c.name), kmap=c.kmap, eps=BN_EPS, **kw)
+
+
+class Workspace:
+    """All activation / gradient buffers for one forward (and optionally its backward) at a
+    fixed number of frames `n` (= B * num_frames)."""
+
+    def __init__(self, plan: NetPlan, n: int, device, train: bool):
+        self.n, self.train = n, train
+        e = lambda *s, dt=bf16: torch.empty(*s, device=device, dtype=dt)  # noqa: E731
+        z = lambda *s, dt=bf16: torch.zeros(*s, device=device, dtype=dt)  # noqa: E731
+        self.xp = e(n, 112, 112, 16)
+        self.s = e(n, 112, 112, 64)
+        self.idx = e(n, 56, 56, 64, dt=torch.uint8) if train else None
+        self.p = e(n, 56, 56, 64)
+        self.a1, self.idn, self.out = [], [], []
+        for b in plan.blocks:
+            self.a1.append(e(n, b.out_hw, b.out_hw, b.cout))
+            self.idn.append(e(n, b.out_hw, b.out_hw, b.cout) if b.ds is not None else None)
+            self.out.append(e(n, b.out_hw, b.out_hw, b.cout))
+        self.h = e(n, 5, 5, 64)
+        B = n // plan.num_frames
+        F = plan.num_frames
+        f32 = torch.float32
+        self.flat = e(B, 1600 * F, dt=f32)
+        self.z1 = e(B, 512, dt=f32)
+        self.z2 = e(B, 256, dt=f32)
+        self.q = e(B, plan.num_classes * plan.action_dim, dt=f32)
+        if train:
+            self.dz2 = e(B, 256, dt=f32)
+            self.dz1 = e(B, 512, dt=f32)
+            self.dflat = e(B, 1600 * F, dt=f32)
+            self.dh = e(n, 5, 5, 64)
+            # gradient wrt block outputs / conv1 outputs: two rotating buffers per resolution
+            self.dy_out = {b.out_hw: (e(n, b.out_hw, b.out_hw, b.cout), e(n, b.out_hw, b.out_hw, b.cout))
+                           for b in plan.blocks}
+            self.dy_a1 = {b.out_hw: e(n, b.out_hw, b.out_hw, b.cout) for b in plan.blocks}
+            # zero-dilated copies for the strided data gradients (odd positions stay zero forever)
+            self.dy_a1_dil = {b.out_hw: z(n, b.in_hw, b.in_hw, b.cout) for b in plan.blocks if b.stride == 2}
+            self.r_dil = {b.out_hw: z(n, b.in_hw, b.in_hw, b.cin) for b in plan.blocks if b.stride == 2}
+            self.dy_p = e(n, 56, 56, 64)
+            self.dy_s = e(n, 112, 112, 64)
+            max_part = max(wgrad_splits(c, n) * c.cout * c.K for c in plan.convs)
+            self.part = e(max_part, dt=f32)
+
+
+def _conv(W: PreparedWeights, c: ConvSpec, x, out, **kw):
+    return ops.conv_gemm(x, W.w_fwd[c.name], c.stride, c.pad_lo, c.pad_hi, shift=W.shift[c.name],
+                         out=out, **kw)
+
+
+def forward(plan: NetPlan, W: PreparedWeights, P: Dict[str, torch.Tensor], ws: Workspace,
+            frames: torch.Tensor) -> torch.Tensor:
+    """frames: [n,3,224,224] fp32 NCHW (or [n,224,224,3] uint8) -> Q [B, classes*actions] fp32."""
+    ops.stem_pack(frames, ws.xp)
+    _conv(W, plan.stem, ws.xp, ws.s, relu=True)
+    ops.maxpool_fwd(ws.s, ws.p, ws.idx)
+    x = ws.p
+    for i, b in enumerate(plan.blocks):
+        _conv(W, b.conv1, x, ws.a1[i], relu=True)
+        idn = x
+        if b.ds is not None:
+            _conv(W, b.ds, x, ws.idn[i])
+            idn = ws.idn[i]
+        _conv(W, b.conv2, ws.a1[i], ws.out[i], residual=idn, relu=True)
+        x = ws.out[i]
+    _conv(W, plan.head, x, ws.h, relu=True)
+    ops.head_flatten_fwd(ws.h, ws.flat)
+    ops.linear_fwd(ws.flat, P["top.0.weight"], P["top.0.bias"], True, ws.z1)
+    ops.linear_fwd(ws.z1, P["top.2.weight"], P["top.2.bias"], True, ws.z2)
+    ops.linear_fwd(ws.z2, P["top.4.weight"], P["top.4.bias"], False, ws.q)
+    return ws.q
+
+
+def _wgrad(plan, P, G, ws: Workspace, c: ConvSpec, x, dy, dbeta_key: Optional[str]):
+    splits = wgrad_splits(c, ws.n)
+    part = ws.part[: splits * c.cout * c.K]
+    ops.conv_wgrad(x, dy, c.k, c.k, c.stride, c.pad_lo, c.pad_hi, splits=splits, part=part)
+    kw = {}
+    if c.bn is not None:
+        kw = dict(gamma=P[c.bn + ".weight"], var=P[c.bn + ".running_var"], mean=P[c.bn + ".running_mean"],
+                  dbeta=G[c.bn + ".bias"], dgamma=G[c.bn + ".weight"])
+    ops.wgrad_finalize(part, P[c.wkey], G[c.wkey], splits=splits, Cout=c.cout, Cin=c.gemm_cin, R=c.k,
+                       S=c.k, K=c.K, kmap=c.kmap, eps=BN_EPS, **kw)
+
+
+def backward(plan: NetPlan, W: PreparedWeights, P: Dict[str, torch.Tensor], G: Dict[str, torch.Tensor],
+             ws: Workspace, dq: torch.Tensor, on_grads_ready=None):
+    """dq: [B, classes*actions] fp32 (overwritten).  Writes every parameter gradient into G
+    (views of the flat gradient arena; BN-bias slots must be zero on entry: they are accumulated
+    with atomics).  `on_grads_ready(stage)` is called after each stage's gradients are enqueued
+    (used by the data-parallel wrapper to launch bucketed all-reduces)."""
+    notify = on_grads_ready or (lambda stage: None)
+    # ---- MLP (fp32)
+    ops.linear_bwd(ws.z2, P["top.4.weight"], None, dq, G["top.4.weight"], G["top.4.bias"], False, dx=ws.dz2)
+    ops.linear_bwd(ws.z1, P["top.2.weight"], ws.z2, ws.dz2, G["top.2.weight"], G["top.2.bias"], True, dx=ws.dz1)
+    ops.linear_bwd(ws.flat, P["top.0.weight"], ws.z1, ws.dz1, G["top.0.weight"], G["top.0.bias"], True,
+                   dx=ws.dflat)
+    # ---- head conv
+    ops.head_flatten_bwd(ws.dflat, ws.h, ws.dh, dbias=G["features.8.bias"])
+    last = plan.blocks[-1]
+    x_head = ws.out[-1]
+    _wgrad(plan, P, G, ws, plan.head, x_head, ws.dh, None)
+    ci = 0
+    cur = ws.dy_out[last.out_hw][ci]
+    ops.conv_gemm(ws.dh, W.w_dgrad["head"], 1, 2, 2, mask_src=x_head, colsum=G[last.conv2.bn + ".bias"],
+                  out=cur)
+    notify("head")
+    # ---- residual blocks, last to first.  `cur` = d loss / d (block output), already masked by
+    # the block's final ReLU; its column sums are already accumulated in G[bn2.bias].
+    for i in range(len(plan.blocks) - 1, -1, -1):
+        b = plan.blocks[i]
+        x_in = ws.out[i - 1] if i > 0 else ws.p
+        prev = plan.blocks[i - 1] if i > 0 else None
+        if b.ds is not None:
+            # the downsample BN sees the same upstream gradient as bn2
+            G[b.ds.bn + ".bias"].copy_(G[b.conv2.bn + ".bias"])
+        # conv2: weight gradient, then data gradient masked by relu(bn1(conv1))
+        _wgrad(plan, P, G, ws, b.conv2, ws.a1[i], cur, None)
+        dy_a1 = ws.dy_a1[b.out_hw]
+        ops.conv_gemm(cur, W.w_dgrad[b.conv2.name], 1, 1, 1, mask_src=ws.a1[i],
+                      colsum=G[b.conv1.bn + ".bias"], out=dy_a1,
+                      out2=ws.dy_a1_dil[b.out_hw] if b.stride == 2 else None)
+        # identity / downsample branch
+        if b.ds is not None:
+            _wgrad(plan, P, G, ws, b.ds, x_in, cur, None)
+            res = ws.r_dil[b.out_hw]
+            ops.conv_gemm(cur, W.w_dgrad[b.ds.name], 1, 0, 0, out=res, out_scatter=2)
+        else:
+            res = cur
+        # conv1: weight gradient, then the gradient wrt the block input (+ identity branch),
+        # masked by the previous block's final ReLU
+        _wgrad(plan, P, G, ws, b.conv1, x_in, dy_a1, None)
+        if prev is not None:
+            ni = (1 - ci) if prev.out_hw == b.out_hw else 0
+            dst = ws.dy_out[prev.out_hw][ni]
+            colsum, mask = G[prev.conv2.bn + ".bias"], x_in
+        else:
+            ni, dst, colsum, mask = 0, ws.dy_p, None, None
+        src = ws.dy_a1_dil[b.out_hw] if b.stride == 2 else dy_a1
+        ops.conv_gemm(src, W.w_dgrad[b.conv1.name], 1, 1, 1, residual=res, mask_src=mask, colsum=colsum,
+                      out=dst)
+        notify(b.conv1.name)
+        cur, ci = dst, ni
+    # ---- max-pool + stem
+    ops.maxpool_bwd(ws.dy_p, ws.idx, ws.s, ws.dy_s, colsum=G[plan.stem.bn + ".bias"])
+    _wgrad(plan, P, G, ws, plan.stem, ws.xp, ws.dy_s, None)
+    notify("stem")

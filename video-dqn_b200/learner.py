@@ -1,0 +1,205 @@
+"""The fused Q-learning step: one call = one iteration of the reference loop body
+(train_q_network.py:211-229), all on the device, replayed as a CUDA graph.
+
+    model.set_train(); optimizer.zero_grad()
+    loss = process_batch(batch)            # 3 forwards + Double-DQN TD loss   (:126-181)
+    loss.backward(); optimizer.step()      # (:226-227)
+    [target_net.load_state_dict(model.state_dict()) every TARGET_UPDATE_INTERVAL]   (:215-216)
+
+Differences from the reference that do not change results: the `target_net(after)` and
+`model(after)` forwards run without saving activations (the reference records and discards their
+autograd graphs), the ~24 ATen launches of the TD loss are one kernel, Adam is one kernel, and the
+hard target sync is folded into the Adam pass of the step *before* the one the reference performs
+it at the top of (same values reach the same forward).  `loss` is returned as a device tensor;
+`.item()` stays the caller's choice (the reference syncs every step, :229).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, Optional
+
+import torch
+
+from . import engine as E
+from . import ops
+from .optim import FlatArena, FusedAdam, bump_arena_epoch
+from .qnet import HabitatDQNMultiAction
+
+
+@dataclass
+class StepConfig:
+    """Hot-path hyper-parameters (defaults.py:4-37 overlaid with
+    configs/experiments/real_data/config.yml)."""
+    GAMMA: float = 0.99
+    LOSS_CLIP: str = "rect"
+    LINEAR: bool = False
+    REMOVE_BEFORE_REWARD: bool = False
+    LEARNING_RATE: float = 1e-4
+    TARGET_UPDATE_INTERVAL: int = 8000
+    double_dqn: bool = True
+
+    @classmethod
+    def from_config(cls, config):
+        """Build from the reference's flattened ExperimentConfig attribute bag."""
+        kw = {f: getattr(config, f) for f in ("GAMMA", "LOSS_CLIP", "LINEAR", "REMOVE_BEFORE_REWARD",
+                                              "LEARNING_RATE", "TARGET_UPDATE_INTERVAL") if hasattr(config, f)}
+        return cls(**kw)
+
+
+class QLearner:
+    def __init__(self, model: HabitatDQNMultiAction, target_net: HabitatDQNMultiAction,
+                 cfg: Optional[StepConfig] = None, batch_size: int = 16, *,
+                 optimizer: Optional[FusedAdam] = None, frames_uint8: bool = False,
+                 use_graph: bool = True, grad_sync=None, world_size: int = 1):
+        self.cfg = cfg or StepConfig()
+        self.model, self.target_net = model, target_net
+        self.B = batch_size
+        self.world_size = world_size
+        self.grad_sync = grad_sync
+        self.use_graph = use_graph
+        dev = next(model.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("QLearner needs the model on a CUDA device (no CPU path)")
+        self.device = dev
+        model.set_train()
+        target_net.eval()
+        self.plan = model._state().plan
+        F = self.plan.num_frames
+        names = model._grad_names
+        # ---- parameters / gradients / Adam state / target copy in flat arenas
+        self.opt = optimizer or FusedAdam(model.parameters(), lr=self.cfg.LEARNING_RATE)
+        mp = dict(model.named_parameters())
+        self.opt.adopt([mp[n] for n in names])
+        self.G: Dict[str, torch.Tensor] = dict(zip(names, self.opt.grad_views()))
+        tp = dict(target_net.named_parameters())
+        self.t_arena = FlatArena([mp[n].shape for n in names], dev)
+        for i, n in enumerate(names):
+            v = self.t_arena.view(i)
+            v.copy_(tp[n].data)
+            tp[n].data = v
+        self.step_dev = torch.zeros(1, device=dev, dtype=torch.int32)
+        if self.opt._step:
+            self.step_dev.fill_(self.opt._step)
+        self.scalars_dev = torch.zeros(2, device=dev, dtype=torch.float32)
+        # ---- static inputs
+        n = batch_size * F
+        if frames_uint8:
+            shp = (batch_size, F, 224, 224, 3) if F > 1 else (batch_size, 224, 224, 3)
+            self.before = torch.zeros(shp, device=dev, dtype=torch.uint8)
+        else:
+            shp = (batch_size, F, 3, 224, 224) if F > 1 else (batch_size, 3, 224, 224)
+            self.before = torch.zeros(shp, device=dev, dtype=torch.float32)
+        self.after = torch.zeros_like(self.before)
+        C = self.plan.num_classes
+        self.act = torch.zeros(batch_size, device=dev, dtype=torch.int64)
+        self.rew = torch.zeros(batch_size, C, device=dev, dtype=torch.int64)
+        self.term = torch.zeros(batch_size, C, device=dev, dtype=torch.int64)
+        self.valid = torch.ones(batch_size, C, device=dev, dtype=torch.int64)
+        # ---- workspaces and step outputs
+        self.ws_train = E.Workspace(self.plan, n, dev, train=True)
+        self.ws_eval = E.Workspace(self.plan, n, dev, train=False)
+        A = self.plan.action_dim
+        self.q_next_online = torch.empty(batch_size, C * A, device=dev, dtype=torch.float32)
+        self.dq = torch.empty(batch_size, C * A, device=dev, dtype=torch.float32)
+        self.loss = torch.zeros(1, device=dev, dtype=torch.float32)
+        self.best = torch.empty(batch_size, C, device=dev, dtype=torch.int64)
+        self.y = torch.empty(batch_size, C, device=dev, dtype=torch.float32)
+        self.sample_number = 0
+        self._graphs: Dict[bool, torch.cuda.CUDAGraph] = {}
+        self._eager_steps = 0
+        self.kernels_per_step = 0
+
+    # ------------------------------------------------------------------ the step body
+    def _frames(self, t):
+        F = self.plan.num_frames
+        return t.view(self.B * F, *t.shape[-3:])
+
+    def _enqueue(self, sync_target: bool):
+        cfg, plan = self.cfg, self.plan
+        st, tt = self.model._eng, self.target_net._eng
+        C, A = plan.num_classes, plan.action_dim
+        self.opt.grad_arena.zero_()
+        self.loss.zero_()
+        # online net on s' and target net on s' (no activations kept), online net on s (kept)
+        E.forward(plan, st.W, st.P, self.ws_eval, self._frames(self.after))
+        self.q_next_online.copy_(self.ws_eval.q)
+        E.forward(plan, tt.W, tt.P, self.ws_eval, self._frames(self.after))
+        E.forward(plan, st.W, st.P, self.ws_train, self._frames(self.before))
+        B = self.B
+        ops.td_epilogue(self.ws_train.q.view(B, C, A), self.q_next_online.view(B, C, A),
+                        self.ws_eval.q.view(B, C, A), self.act, self.rew, self.term, self.valid,
+                        gamma=cfg.GAMMA, double_dqn=cfg.double_dqn, clip_rect=(cfg.LOSS_CLIP == "rect"),
+                        linear=cfg.LINEAR, use_valid=cfg.REMOVE_BEFORE_REWARD,
+                        inv_count=1.0 / (B * C), dq=self.dq.view(B, C, A), loss=self.loss,
+                        best=self.best, y=self.y)
+        sync = self.grad_sync
+        E.backward(plan, st.W, st.P, self.G, self.ws_train, self.dq,
+                   on_grads_ready=(sync.on_stage if sync is not None else None))
+        if sync is not None:
+            sync.finish()
+        self.opt.step(grads_in_arena=True, step_dev=self.step_dev, scalars_dev=self.scalars_dev,
+                      grad_scale=1.0 / self.world_size,
+                      target_arena=self.t_arena.flat if sync_target else None)
+        st.W.prepare(st.P)
+        if sync_target:
+            tb, mb = dict(self.target_net.named_buffers()), dict(self.model.named_buffers())
+            for k, v in tb.items():
+                v.copy_(mb[k])
+            tt.W.prepare(tt.P)
+
+    # ------------------------------------------------------------------ public API
+    def load_batch(self, batch, non_blocking: bool = True):
+        """Copy a reference-format batch (before, after, act, rew, term, gt, valid_mask)
+        (dataloaders/q_learning_real.py:98) into the static device buffers."""
+        before, after, act, rew, term, _gt, valid = batch
+        if before.shape[0] != self.B:
+            raise ValueError("bad shape")
+        self.before.copy_(before.view(self.before.shape), non_blocking=non_blocking)
+        self.after.copy_(after.view(self.after.shape), non_blocking=non_blocking)
+        self.act.copy_(act.view(-1), non_blocking=non_blocking)
+        self.rew.copy_(rew, non_blocking=non_blocking)
+        self.term.copy_(term, non_blocking=non_blocking)
+        self.valid.copy_(valid, non_blocking=non_blocking)
+
+    def step(self, batch=None) -> torch.Tensor:
+        """One training iteration; returns the loss as a 1-element device tensor."""
+        if batch is not None:
+            self.load_batch(batch)
+        self.model._state(); self.target_net._state()        # refresh bf16 operands if stale
+        self.sample_number += 1
+        sync_target = (self.sample_number + 1) % self.cfg.TARGET_UPDATE_INTERVAL == 0
+        if self.use_graph and self._eager_steps >= 1:
+            g = self._graphs.get(sync_target)
+            if g is None:
+                g = torch.cuda.CUDAGraph()
+                torch.cuda.synchronize()
+                with torch.cuda.graph(g):
+                    self._enqueue(sync_target)
+                self._graphs[sync_target] = g
+                # capture does not execute: undo the bookkeeping _enqueue did on the host
+                self.opt._step -= 1
+            g.replay()
+            self.opt.note_graph_replay(sync_target, self.t_arena.flat)
+        else:
+            self._enqueue(sync_target)
+            self._eager_steps += 1
+        # the bf16 operands were just re-derived inside the step: mark the modules in sync
+        self.model._eng.sig = None
+        self.target_net._eng.sig = None
+        self._mark_clean()
+        return self.loss
+
+    def _mark_clean(self):
+        from .optim import arena_epoch
+        for m in (self.model, self.target_net):
+            nt = m._named_tensors()
+            m._eng.P = nt
+            m._eng.sig = tuple((t.data_ptr(), t._version, arena_epoch(t)) for t in nt.values())
+
+    def sync_target_now(self):
+        """target_net.load_state_dict(model.state_dict()) (train_q_network.py:121,208)."""
+        self.t_arena.flat.copy_(self.opt.param_arena)
+        bump_arena_epoch(self.t_arena.flat)
+        tb, mb = dict(self.target_net.named_buffers()), dict(self.model.named_buffers())
+        for k, v in tb.items():
+            v.copy_(mb[k])

@@ -255,7 +255,10 @@ def td_epilogue(q_s, q_next_online, q_next_target, act, rew, term, valid=None, *
     return loss, dq, best, y
 
 
-def adam_fused(p, g, m, v, *, lr, step, betas=(0.9, 0.999), eps=1e-8, target=None, grad_scale=1.0):
+def adam_fused(p, g, m, v, *, lr, step=None, betas=(0.9, 0.999), eps=1e-8, target=None, grad_scale=1.0,
+               step_dev=None, scalars_dev=None):
+    """Fused Adam over flat fp32 arenas.  Either `step` (host int) or `step_dev` + `scalars_dev`
+    (int32[1] / float32[2] device tensors; graph-replay mode, the call increments the counter)."""
     lib = L.load()
     for t, n in ((p, "p"), (g, "g"), (m, "m"), (v, "v")):
         _cuda(t, torch.float32, n)
@@ -263,6 +266,13 @@ def adam_fused(p, g, m, v, *, lr, step, betas=(0.9, 0.999), eps=1e-8, target=Non
     _req(g.numel() == n and m.numel() == n and v.numel() == n, "bad shape")
     if target is not None:
         _cuda(target, torch.float32, "target"); _req(target.numel() == n, "bad shape")
-    L.check(lib.vdqn_adam_fused(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), L.ptr(target),
-                                n, lr, betas[0], betas[1], eps, step, grad_scale, L.stream_ptr()),
-            "adam_fused")
+    if step_dev is not None:
+        _cuda(step_dev, torch.int32, "step_dev"); _cuda(scalars_dev, torch.float32, "scalars_dev")
+        L.check(lib.vdqn_adam_fused_graph(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(),
+                                          L.ptr(target), n, lr, betas[0], betas[1], eps, grad_scale,
+                                          step_dev.data_ptr(), scalars_dev.data_ptr(), L.stream_ptr()),
+                "adam_fused_graph")
+    else:
+        L.check(lib.vdqn_adam_fused(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), L.ptr(target),
+                                    n, lr, betas[0], betas[1], eps, int(step), grad_scale, L.stream_ptr()),
+                "adam_fused")
