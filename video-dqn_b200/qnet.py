@@ -65,7 +65,7 @@ class _QNetFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, frames, module, *params):
         st = module._state()
-        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        need_grad = any(ctx.needs_input_grad[2:])
         n = frames.shape[0]
         ws = E.Workspace(st.plan, n, frames.device, train=need_grad)
         q = E.forward(st.plan, st.W, st.P, ws, frames)
