@@ -38,6 +38,8 @@ int vdqn_abi_version(void);
 /* Resolve driver entry points (tensor-map encoders), query the device.  Idempotent. */
 int vdqn_init(int device);
 int vdqn_num_sms(void);
+/* Number of kernels this library has launched (or captured into a graph) so far in this process. */
+long long vdqn_launch_count(void);
 
 /* ---------------------------------------------------------------------------------------
  * Implicit-GEMM convolution, forward and data-gradient (tcgen05 + TMA im2col).

@@ -6,11 +6,14 @@
 #include <stdarg.h>
 #include <stdio.h>
 
+#include <atomic>
 #include <mutex>
 
 namespace vdqn {
 
 static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 int set_error(int code, const char* fmt, ...) {
   va_list ap;
@@ -134,3 +137,4 @@ extern "C" int vdqn_num_sms(void) {
   vdqn::DeviceInfo* d = vdqn::device_info();
   return d ? d->num_sms : -1;
 }
+extern "C" long long vdqn_launch_count(void) { return vdqn::g_launches.load(); }

@@ -326,8 +326,7 @@ static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Ig
   const int tiles = a.num_m_tiles * a.num_n_tiles;
   const int grid = tiles < num_sms ? tiles : num_sms;
   kfn<<<grid, 192, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, a);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return set_error(VDQN_ERR_CUDA, "igemm launch: %s", cudaGetErrorString(e));
+  VDQN_CHECK_LAUNCH("igemm launch");
   return VDQN_OK;
 }
 

@@ -30,8 +30,12 @@ int make_tiled_map_2d(CUtensorMap* map, const void* base, uint64_t cols, uint64_
 
 inline int ceil_div(long a, long b) { return (int)((a + b - 1) / b); }
 
+// every kernel launch of the library is counted (bench.py reports it as `gpu_launches`)
+void count_launch();
+
 #define VDQN_CHECK_LAUNCH(what)                                                         \
   do {                                                                                  \
+    ::vdqn::count_launch();                                                             \
     cudaError_t e__ = cudaGetLastError();                                               \
     if (e__ != cudaSuccess)                                                             \
       return ::vdqn::set_error(VDQN_ERR_CUDA, what ": %s", cudaGetErrorString(e__));    \

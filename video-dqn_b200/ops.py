@@ -11,6 +11,29 @@ from . import _lib as L
 
 bf16 = torch.bfloat16
 
+# When set to a list, conv_gemm / conv_wgrad / adam_fused / td_epilogue bracket their launch with
+# CUDA events on the launching stream and append (kind, tag, start_event, end_event).  bench.py uses
+# this for the per-kernel roofline; it is None (zero overhead) otherwise.
+PROFILE = None
+
+
+class _Prof:
+    def __init__(self, kind, tag):
+        self.kind, self.tag = kind, tag
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.s = torch.cuda.Event(enable_timing=True)
+            self.e = torch.cuda.Event(enable_timing=True)
+            self.s.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            self.e.record()
+            PROFILE.append((self.kind, self.tag, self.s, self.e))
+        return False
+
 
 def _req(cond, msg):
     if not cond:
@@ -69,7 +92,8 @@ def conv_gemm(x, w, stride=1, pad_lo=0, pad_hi=None, *, shift=None, residual=Non
     d.out_scatter = out_scatter
     d.flags = (L.EPI_RELU if relu else 0) | (L.EPI_OUT_F32 if out_f32 else 0)
     d.tile_n, d.max_ctas = tile_n, max_ctas
-    L.check(lib.vdqn_conv_gemm(C.byref(d), L.stream_ptr()), "conv_gemm")
+    with _Prof("igemm", (N, H, W_, Cin, Cout, R, stride)):
+        L.check(lib.vdqn_conv_gemm(C.byref(d), L.stream_ptr()), "conv_gemm")
     return out
 
 
@@ -91,7 +115,8 @@ def conv_wgrad(x, dy, R, S, stride=1, pad_lo=0, pad_hi=None, *, splits=1, part=N
     d.N, d.H, d.W, d.Cin, d.Cout, d.R, d.S = N, H, W_, Cin, Cout, R, S
     d.stride, d.dil, d.pad_lo, d.pad_hi = stride, dil, pad_lo, pad_hi
     d.ldy, d.splits, d.max_ctas = Cout, splits, max_ctas
-    L.check(lib.vdqn_conv_wgrad(C.byref(d), L.stream_ptr()), "conv_wgrad")
+    with _Prof("wgrad", (N, H, W_, Cin, Cout, R, stride)):
+        L.check(lib.vdqn_conv_wgrad(C.byref(d), L.stream_ptr()), "conv_wgrad")
     return part
 
 
@@ -251,7 +276,8 @@ def td_epilogue(q_s, q_next_online, q_next_target, act, rew, term, valid=None, *
     d.gamma = gamma
     d.inv_count = (1.0 / (B * Cc)) if inv_count is None else inv_count
     d.double_dqn, d.clip_rect, d.linear, d.use_valid = int(double_dqn), int(clip_rect), int(linear), int(use_valid)
-    L.check(lib.vdqn_td_epilogue(C.byref(d), L.stream_ptr()), "td_epilogue")
+    with _Prof("td", (B, Cc, A)):
+        L.check(lib.vdqn_td_epilogue(C.byref(d), L.stream_ptr()), "td_epilogue")
     return loss, dq, best, y
 
 
@@ -268,7 +294,8 @@ def adam_fused(p, g, m, v, *, lr, step=None, betas=(0.9, 0.999), eps=1e-8, targe
         _cuda(target, torch.float32, "target"); _req(target.numel() == n, "bad shape")
     if step_dev is not None:
         _cuda(step_dev, torch.int32, "step_dev"); _cuda(scalars_dev, torch.float32, "scalars_dev")
-        L.check(lib.vdqn_adam_fused_graph(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(),
+        with _Prof("adam", (n, target is not None)):
+          L.check(lib.vdqn_adam_fused_graph(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(),
                                           L.ptr(target), n, lr, betas[0], betas[1], eps, grad_scale,
                                           step_dev.data_ptr(), scalars_dev.data_ptr(), L.stream_ptr()),
                 "adam_fused_graph")
