@@ -146,7 +146,7 @@ def run_reference(a):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU)
@@ -202,6 +202,8 @@ def main():
         return t.item()
 
     # ---------------- device-resident timing ("value")
+    sampler = ClockSampler(local)
+    sampler.start()                            # nvidia-smi needs ~0.5 s to start streaming samples
     learner.model._state(); learner.target_net._state()
     torch.cuda.synchronize()
     lc0 = lib.vdqn_launch_count()
@@ -212,9 +214,7 @@ def main():
         learner.load_batch(pool[i % len(pool)])
         learner.step()
     torch.cuda.synchronize()
-    sampler = ClockSampler(local)
     barrier()
-    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(a.steps):
