@@ -73,6 +73,7 @@ typedef struct vdqn_conv_desc {
   int32_t flags;       /* VDQN_EPI_* */
   int32_t tile_n;      /* 0 = auto (64/128/256) */
   int32_t max_ctas;    /* 0 = one per SM */
+  int32_t algo;        /* 0 = auto, 1 = im2col-TMA kernel, 2 = halo-tile kernel (Cout = 64 layers) */
 } vdqn_conv_desc;
 int vdqn_conv_gemm(const vdqn_conv_desc* d, void* stream);
 

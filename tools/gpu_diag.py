@@ -192,6 +192,42 @@ def conv_tile_n_variants():
 
 
 @case
+def halo_conv_cases():
+    ok = True
+    ok &= _conv_case("halo_20x28", 3, 20, 28, 64, 64, 3, 1, 1, shift=True, residual=True, relu=True)
+    ok &= _conv_case("halo_56_bwd", 2, 56, 56, 64, 64, 3, 1, 1, residual=True, mask=True, colsum=True)
+    ok &= _conv_case("halo_13x9_f32", 2, 13, 9, 64, 64, 3, 1, 1, shift=True, f32=True)
+    return ok
+
+
+@case
+def halo_speed():
+    """halo-tile vs im2col kernel on the layer1 / stem shapes at the bench batch"""
+    torch, F, ops = _imports()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    res = {}
+    for name, shp, wshp, pads in (("layer1", (256, 56, 56, 64), (64, 3, 3, 64), (1, 1)),
+                                   ("stem", (256, 112, 112, 16), (64, 4, 4, 16), (2, 1))):
+        x = torch.randn(*shp, device="cuda", generator=g).to(torch.bfloat16)
+        w = (torch.randn(*wshp, device="cuda", generator=g) * 0.05).to(torch.bfloat16)
+        outs = {}
+        for algo in (1, 2):
+            out = torch.empty(shp[0], shp[1], shp[2], 64, device="cuda", dtype=torch.bfloat16)
+            for _ in range(3):
+                ops.conv_gemm(x, w, 1, pads[0], pads[1], out=out, algo=algo, relu=True)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            for _ in range(10):
+                ops.conv_gemm(x, w, 1, pads[0], pads[1], out=out, algo=algo, relu=True)
+            e.record(); torch.cuda.synchronize()
+            res[f"{name}_algo{algo}_us"] = s.elapsed_time(e) * 100
+            outs[algo] = out
+        res[f"{name}_maxdiff"] = (outs[1].float() - outs[2].float()).abs().max().item()
+    print(json.dumps(res))
+    return res["layer1_maxdiff"] < 0.05 and res["stem_maxdiff"] < 0.05
+
+
+@case
 def stem_s2d():
     torch, F, ops = _imports()
     g = torch.Generator(device="cuda").manual_seed(2)
@@ -486,7 +522,7 @@ def main():
         todo = [n for n in todo if n not in finished]
     for n, r in results.items():
         print(f"[{r['status']}] {n}")
-        if r["status"] != "PASS":
+        if r["status"] != "PASS" or "speed" in n:
             print(r["log"])
     with open(a.out, "w") as f:
         json.dump(results, f, indent=1)

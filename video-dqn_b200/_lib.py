@@ -20,7 +20,7 @@ class ConvDesc(C.Structure):
                 ("colsum", c_void_p)] + \
                [(n, c_int) for n in ("N", "H", "W", "Cin", "Cout", "R", "S", "stride", "dil",
                                      "pad_lo", "pad_hi", "ldc", "ldr", "ldm", "out2_ld",
-                                     "out_scatter", "flags", "tile_n", "max_ctas")]
+                                     "out_scatter", "flags", "tile_n", "max_ctas", "algo")]
 
 
 class WgradDesc(C.Structure):

@@ -110,6 +110,22 @@ int make_im2col_map(CUtensorMap* map, const void* base, int N, int H, int W, int
   return VDQN_OK;
 }
 
+int make_tiled_map_nhwc(CUtensorMap* map, const void* base, int N, int H, int W, int C, int box_c,
+                        int box_w, int box_h, int swizzle_bytes) {
+  if (device_info() == nullptr) return VDQN_ERR_CUDA;
+  const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  const cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = g_encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims,
+                              strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz_enum(swizzle_bytes),
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(VDQN_ERR_DRIVER, "cuTensorMapEncodeTiled(4d) failed (%d): N=%d H=%d W=%d C=%d box=(%d,%d,%d)",
+                     (int)r, N, H, W, C, box_c, box_w, box_h);
+  return VDQN_OK;
+}
+
 int make_tiled_map_2d(CUtensorMap* map, const void* base, uint64_t cols, uint64_t rows,
                       uint32_t box_cols, uint32_t box_rows, int swizzle_bytes,
                       uint64_t row_stride_elems) {

@@ -16,10 +16,9 @@
 //               tile's MMAs overlap), then + per-channel shift (folded BN / bias), + residual,
 //               ReLU or ReLU-mask (backward), optional per-channel column sums (d beta), bf16/fp32
 //               store, optional stride-2 scatter (zero-dilated gradient for strided dgrad).
+#include "epilogue.cuh"
 #include "ptx.cuh"
 #include "vdqn_internal.h"
-
-#include <cuda_bf16.h>
 
 namespace vdqn {
 
@@ -27,16 +26,8 @@ struct IgemmArgs {
   int M_total, Ho, Wo, Cout;
   int R, S, Cin, stride, dil, lower_h, lower_w;
   int num_m_tiles, num_n_tiles;
-  void* out;          // [opix][ldc] bf16 or fp32
-  void* out2;         // optional second bf16 destination, stride-2 scatter (dilated copy)
-  const float* shift;       // [Cout] or null
-  const __nv_bfloat16* residual;  // [M_total][ldr] or null
-  const __nv_bfloat16* mask_src;  // [M_total][ldm] or null: out = (mask_src > 0) ? v : 0
-  float* colsum;            // [Cout] fp32 atomics or null
-  int ldc, ldr, ldm;
+  EpiArgs epi;
   int out_scatter;    // 1: opix = m;  2: opix = (n*2Ho + 2p)*2Wo + 2q
-  int out2_ld;
-  int flags;          // VDQN_EPI_*
 };
 
 template <int BN, int CK>
@@ -173,8 +164,6 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     // ------------------------------------------------------------ epilogue (warps 2..5)
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may touch
     const int row = quad * 32 + lane;
-    const bool out_f32 = a.flags & VDQN_EPI_OUT_F32;
-    const bool relu = a.flags & VDQN_EPI_RELU;
     int it = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       const int n_t = t % a.num_n_tiles, m_t = t / a.num_n_tiles;
@@ -184,7 +173,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const bool valid = m < a.M_total;
       long opix = m;
       long opix2 = 0;
-      if (a.out_scatter == 2 || a.out2 != nullptr) {
+      if (a.out_scatter == 2 || a.epi.out2 != nullptr) {
         const int img = m / HoWo;
         const int rem = m - img * HoWo;
         const int p = rem / a.Wo, q = rem - p * a.Wo;
@@ -199,100 +188,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         uint32_t raw[32];
         tmem_ld_32x32(tmem_base + acc * BN + chunk * 32 + ((uint32_t)(quad * 32) << 16), raw);
         tmem_ld_wait();
-        const int c0 = n_t * BN + chunk * 32;
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-        if (a.shift != nullptr) {
-          const float4* sp = reinterpret_cast<const float4*>(a.shift + c0);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 s4 = __ldg(sp + j);
-            v[4 * j + 0] += s4.x; v[4 * j + 1] += s4.y; v[4 * j + 2] += s4.z; v[4 * j + 3] += s4.w;
-          }
-        }
-        if (a.residual != nullptr && valid) {
-          const uint4* rp = reinterpret_cast<const uint4*>(a.residual + (long)m * a.ldr + c0);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint4 r4 = __ldg(rp + j);
-            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r4);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 f = __bfloat1622float2(h[e]);
-              v[8 * j + 2 * e] += f.x;
-              v[8 * j + 2 * e + 1] += f.y;
-            }
-          }
-        }
-        if (relu) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-        }
-        if (a.mask_src != nullptr && valid) {
-          const uint4* mp = reinterpret_cast<const uint4*>(a.mask_src + (long)m * a.ldm + c0);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint4 r4 = __ldg(mp + j);
-            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r4);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 f = __bfloat1622float2(h[e]);
-              if (!(f.x > 0.f)) v[8 * j + 2 * e] = 0.f;
-              if (!(f.y > 0.f)) v[8 * j + 2 * e + 1] = 0.f;
-            }
-          }
-        }
-        if (!valid) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = 0.f;
-        }
-        if (valid) {
-          if (out_f32) {
-            float4* op = reinterpret_cast<float4*>(static_cast<float*>(a.out) + opix * a.ldc + c0);
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          } else {
-            uint4 pk[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk[j]);
-#pragma unroll
-              for (int e = 0; e < 4; ++e)
-                h[e] = __floats2bfloat162_rn(v[8 * j + 2 * e], v[8 * j + 2 * e + 1]);
-            }
-            uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(a.out) +
-                                                 opix * a.ldc + c0);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) op[j] = pk[j];
-            if (a.out2 != nullptr) {
-              uint4* op2 = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(a.out2) +
-                                                    opix2 * a.out2_ld + c0);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) op2[j] = pk[j];
-            }
-          }
-        }
-        if (a.colsum != nullptr) {
-          // round to the stored precision first so d beta matches what wgrad consumes
-          if (!out_f32) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __bfloat162float(__float2bfloat16_rn(v[j]));
-          }
-          // warp transpose-reduce: afterwards lane L holds the column-(c0+L) sum over 32 rows
-#pragma unroll
-          for (int off = 16; off >= 1; off >>= 1) {
-            const bool upper = (lane & off) != 0;
-#pragma unroll
-            for (int i = 0; i < off; ++i) {
-              const float send = upper ? v[i] : v[i + off];
-              const float keep = upper ? v[i + off] : v[i];
-              v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-            }
-          }
-          atomicAdd(a.colsum + c0 + lane, v[0]);
-        }
+        epilogue_chunk(a.epi, raw, valid, (long)m, opix, opix2, n_t * BN + chunk * 32, lane);
       }
       tc_fence_before();
       __syncwarp();
@@ -357,6 +253,9 @@ extern "C" int vdqn_conv_gemm(const vdqn_conv_desc* d, void* stream_v) {
 
   DeviceInfo* dev = device_info();
   if (dev == nullptr) return VDQN_ERR_CUDA;
+  if (d->algo == 2 && !halo_conv_supported(d))
+    return set_error(VDQN_ERR_SHAPE, "conv_gemm: halo algorithm requested for an unsupported shape");
+  if (d->algo != 1 && d->tile_n == 0 && halo_conv_supported(d)) return halo_conv_launch(d, stream);
 
   CUtensorMap tmA, tmB;
   int rc = make_im2col_map(&tmA, d->x, d->N, d->H, d->W, d->Cin, CK, 128, d->stride,
@@ -375,14 +274,8 @@ extern "C" int vdqn_conv_gemm(const vdqn_conv_desc* d, void* stream_v) {
   a.lower_h = -d->pad_lo; a.lower_w = -d->pad_lo;
   a.num_m_tiles = (a.M_total + 127) / 128;
   a.num_n_tiles = d->Cout / BN;
-  a.out = d->out; a.out2 = d->out2; a.shift = d->shift;
-  a.residual = static_cast<const __nv_bfloat16*>(d->residual);
-  a.mask_src = static_cast<const __nv_bfloat16*>(d->mask_src);
-  a.colsum = d->colsum;
-  a.ldc = d->ldc; a.ldr = d->ldr; a.ldm = d->ldm;
+  a.epi = make_epi_args(d);
   a.out_scatter = d->out_scatter == 2 ? 2 : 1;
-  a.out2_ld = d->out2_ld;
-  a.flags = d->flags;
 
   const int sms = d->max_ctas > 0 && d->max_ctas < dev->num_sms ? d->max_ctas : dev->num_sms;
   if (CK == 16) return launch_igemm<64, 16>(tmA, tmB, a, sms, stream);

@@ -1,0 +1,131 @@
+// Shared accumulator epilogue of the convolution kernels: one thread owns one output pixel (TMEM
+// lane) and 32 consecutive output channels per call.
+//   v = acc + shift[c] + residual[m,c];  ReLU;  v = mask_src[m,c] > 0 ? v : 0;  store bf16/fp32;
+//   colsum[c] += sum over the warp's 32 pixels (warp transpose-reduce, one atomic per channel).
+#pragma once
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+#include "../../include/vdqn.h"
+
+namespace vdqn {
+
+struct EpiArgs {
+  void* out;                      // [opix][ldc] bf16 or fp32
+  void* out2;                     // optional second bf16 destination (zero-dilated copy)
+  const float* shift;             // [Cout] or null
+  const __nv_bfloat16* residual;  // [M][ldr] or null
+  const __nv_bfloat16* mask_src;  // [M][ldm] or null
+  float* colsum;                  // [Cout] or null
+  int ldc, ldr, ldm, out2_ld;
+  int flags;                      // VDQN_EPI_*
+};
+
+inline EpiArgs make_epi_args(const vdqn_conv_desc* d) {
+  EpiArgs e;
+  e.out = d->out; e.out2 = d->out2; e.shift = d->shift;
+  e.residual = static_cast<const __nv_bfloat16*>(d->residual);
+  e.mask_src = static_cast<const __nv_bfloat16*>(d->mask_src);
+  e.colsum = d->colsum;
+  e.ldc = d->ldc; e.ldr = d->ldr; e.ldm = d->ldm; e.out2_ld = d->out2_ld;
+  e.flags = d->flags;
+  return e;
+}
+
+// raw: 32 fp32 accumulators of this thread's pixel, channels [c0, c0+32).  `m` indexes
+// residual / mask_src (compact pixel index), `opix` / `opix2` the destinations.
+__device__ __forceinline__ void epilogue_chunk(const EpiArgs& a, const uint32_t (&raw)[32], bool valid,
+                                               long m, long opix, long opix2, int c0, int lane) {
+  const bool out_f32 = a.flags & VDQN_EPI_OUT_F32;
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+  if (a.shift != nullptr) {
+    const float4* sp = reinterpret_cast<const float4*>(a.shift + c0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 s4 = __ldg(sp + j);
+      v[4 * j + 0] += s4.x; v[4 * j + 1] += s4.y; v[4 * j + 2] += s4.z; v[4 * j + 3] += s4.w;
+    }
+  }
+  if (a.residual != nullptr && valid) {
+    const uint4* rp = reinterpret_cast<const uint4*>(a.residual + m * a.ldr + c0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint4 r4 = __ldg(rp + j);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r4);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __bfloat1622float2(h[e]);
+        v[8 * j + 2 * e] += f.x;
+        v[8 * j + 2 * e + 1] += f.y;
+      }
+    }
+  }
+  if (a.flags & VDQN_EPI_RELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+  }
+  if (a.mask_src != nullptr && valid) {
+    const uint4* mp = reinterpret_cast<const uint4*>(a.mask_src + m * a.ldm + c0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint4 r4 = __ldg(mp + j);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r4);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __bfloat1622float2(h[e]);
+        if (!(f.x > 0.f)) v[8 * j + 2 * e] = 0.f;
+        if (!(f.y > 0.f)) v[8 * j + 2 * e + 1] = 0.f;
+      }
+    }
+  }
+  if (!valid) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = 0.f;
+  }
+  if (valid) {
+    if (out_f32) {
+      float4* op = reinterpret_cast<float4*>(static_cast<float*>(a.out) + opix * a.ldc + c0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    } else {
+      uint4 pk[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk[j]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[8 * j + 2 * e], v[8 * j + 2 * e + 1]);
+      }
+      uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(a.out) + opix * a.ldc + c0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) op[j] = pk[j];
+      if (a.out2 != nullptr) {
+        uint4* op2 = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(a.out2) + opix2 * a.out2_ld + c0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) op2[j] = pk[j];
+      }
+    }
+  }
+  if (a.colsum != nullptr) {
+    // round to the stored precision first so d beta matches what the weight gradient consumes
+    if (!out_f32) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __bfloat162float(__float2bfloat16_rn(v[j]));
+    }
+    // warp transpose-reduce: afterwards lane L holds the column-(c0+L) sum over 32 pixels
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+      const bool upper = (lane & off) != 0;
+#pragma unroll
+      for (int i = 0; i < off; ++i) {
+        const float send = upper ? v[i] : v[i + off];
+        const float keep = upper ? v[i + off] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+      }
+    }
+    atomicAdd(a.colsum + c0 + lane, v[0]);
+  }
+}
+
+}  // namespace vdqn

@@ -1,0 +1,247 @@
+// "Halo" convolution kernel for the wide, shallow layers (Cout = 64: the packed stem and the four
+// 3x3 convolutions of layer1, forward and data-gradient).
+//
+// The im2col kernel (conv_gemm.cu) re-reads every input pixel R*S times from L2; for these layers
+// (K per pixel small, N = 64) that makes them L2->SM bandwidth bound (ncu: 1.39 GB through the
+// crossbar for a 103 MB input, ~9 TB/s, tensor pipe 19 %).  Here an output tile is a spatial
+// rectangle of 8 (W) x 16 (H) pixels of one image and its input window -- (16+R-1) x (8+S-1)
+// pixels x Cin -- is brought into shared memory ONCE by a tiled 4-D TMA box (out-of-image pixels
+// zero-filled = the padding).  Every filter tap is then an A-operand descriptor that starts
+// (r*(8+S-1)+s) pixel rows further into the same buffer, with the 8-pixel group pitch (SBO) equal
+// to one halo row: tcgen05.mma applies the 128B/32B swizzle on absolute shared-memory addresses,
+// so shifted starts and a non-1024B pitch read exactly what TMA wrote (verified on hardware by
+// tools/umma_probe.cu).  The whole filter (<= 72 KB) stays resident in shared memory for the
+// lifetime of the persistent CTA.  L2->SM traffic per layer1 conv drops 1.39 GB -> ~0.15 GB.
+#include "epilogue.cuh"
+#include "ptx.cuh"
+#include "vdqn_internal.h"
+
+namespace vdqn {
+
+struct HaloArgs {
+  int N, H, W, Cout;
+  int R, S, pad_lo;
+  int tiles_w, tiles_h, num_tiles;
+  EpiArgs epi;
+};
+
+template <int CK>
+struct HaloCfg {
+  static constexpr int TH = 16, TW = 8, BN = 64;
+  static constexpr int ROW_BYTES = CK * 2;
+  static constexpr uint64_t SWZ = (CK == 64) ? kSwz128 : kSwz32;
+  static constexpr int MAX_TAPS = (CK == 64) ? 9 : 16;
+  static constexpr int HALO_H = (CK == 64) ? 18 : 19, HALO_W = (CK == 64) ? 10 : 11;
+  static constexpr int HALO_BYTES = HALO_H * HALO_W * ROW_BYTES;
+  static constexpr int STAGE_BYTES = (HALO_BYTES + 1023) / 1024 * 1024;
+  static constexpr int W_TILE_BYTES = BN * ROW_BYTES;              // one tap: 64 rows x CK
+  static constexpr int W_BYTES = MAX_TAPS * W_TILE_BYTES;          // 72 KB / 32 KB, resident
+  static constexpr int STAGES = (CK == 64) ? 6 : 12;
+  static constexpr int SMEM_BYTES = W_BYTES + STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int TMEM_COLS = 128;
+};
+
+__device__ __forceinline__ void tma_load_tiled_4d(uint32_t dst, const void* tmap, uint32_t bar, int c,
+                                                  int w, int h, int n) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n)
+      : "memory");
+}
+
+template <int CK>
+__global__ void __launch_bounds__(192, 1)
+halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+                 const HaloArgs a) {
+  using Cfg = HaloCfg<CK>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sW = smem_base;
+  const uint32_t sA0 = smem_base + Cfg::W_BYTES;
+  const uint32_t bar_base = sA0 + Cfg::STAGES * Cfg::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
+  auto tfull_bar = [&](int i) { return bar_base + 8u * (2 * Cfg::STAGES + i); };
+  auto tempty_bar = [&](int i) { return bar_base + 8u * (2 * Cfg::STAGES + 2 + i); };
+  const uint32_t w_bar = bar_base + 8u * (2 * Cfg::STAGES + 4);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 5);
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int taps = a.R * a.S;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmW);
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(tfull_bar(i), 1);
+      mbar_init(tempty_bar(i), 4);
+    }
+    mbar_init(w_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  auto decode = [&](int t, int& n, int& h0, int& w0) {
+    const int tw = t % a.tiles_w;
+    const int r = t / a.tiles_w;
+    const int th = r % a.tiles_h;
+    n = r / a.tiles_h;
+    h0 = th * Cfg::TH;
+    w0 = tw * Cfg::TW;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // the filter: one [64 x CK] tile per tap, resident for the whole kernel
+      mbar_expect_tx(w_bar, taps * Cfg::W_TILE_BYTES);
+      for (int j = 0; j < taps; ++j) tma_load_2d(sW + j * Cfg::W_TILE_BYTES, &tmW, w_bar, j * CK, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
+        int n, h0, w0;
+        decode(t, n, h0, w0);
+        mbar_wait(empty_bar(stage), phase ^ 1);
+        mbar_expect_tx(full_bar(stage), Cfg::HALO_BYTES);
+        tma_load_tiled_4d(sA0 + stage * Cfg::STAGE_BYTES, &tmX, full_bar(stage), 0, w0 - a.pad_lo,
+                          h0 - a.pad_lo, n);
+        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, Cfg::BN, 0, 0);
+      mbar_wait(w_bar, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * Cfg::BN;
+        const uint32_t sA = sA0 + stage * Cfg::STAGE_BYTES;
+        for (int r = 0; r < a.R; ++r) {
+          for (int s = 0; s < a.S; ++s) {
+            const uint32_t a_tap = sA + (r * Cfg::HALO_W + s) * Cfg::ROW_BYTES;
+            const uint32_t b_tap = sW + (r * a.S + s) * Cfg::W_TILE_BYTES;
+#pragma unroll
+            for (int k = 0; k < CK / 16; ++k) {
+              const uint64_t ad = make_smem_desc(a_tap + k * 32, 16, Cfg::HALO_W * Cfg::ROW_BYTES, Cfg::SWZ);
+              const uint64_t bd = make_smem_desc(b_tap + k * 32, 16, 8 * Cfg::ROW_BYTES, Cfg::SWZ);
+              umma_f16(d_tmem, ad, bd, idesc, (r | s | k) != 0);
+            }
+          }
+        }
+        umma_commit(empty_bar(stage));
+        umma_commit(tfull_bar(acc));
+        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const int g = row >> 3, j = row & 7;
+    int it = 0;
+    for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x, ++it) {
+      int n, h0, w0;
+      decode(t, n, h0, w0);
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int h = h0 + g, w = w0 + j;
+      const bool valid = h < a.H && w < a.W;
+      const long opix = ((long)n * a.H + h) * a.W + w;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int chunk = 0; chunk < Cfg::BN / 32; ++chunk) {
+        uint32_t raw[32];
+        tmem_ld_32x32(tmem_base + acc * Cfg::BN + chunk * 32 + ((uint32_t)(quad * 32) << 16), raw);
+        tmem_ld_wait();
+        epilogue_chunk(a.epi, raw, valid, opix, opix, 0, chunk * 32, lane);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+static int make_tiled_map_4d(CUtensorMap* map, const void* base, int N, int H, int W, int C, int box_c,
+                             int box_w, int box_h, int swizzle_bytes);
+
+template <int CK>
+static int launch_halo(const vdqn_conv_desc* d, cudaStream_t stream) {
+  using Cfg = HaloCfg<CK>;
+  DeviceInfo* dev = device_info();
+  if (dev == nullptr) return VDQN_ERR_CUDA;
+  static bool attr_set = false;
+  auto kfn = halo_conv_kernel<CK>;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess)
+      return set_error(VDQN_ERR_CUDA, "cudaFuncSetAttribute(halo_conv): %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  CUtensorMap tmX, tmW;
+  int rc = make_tiled_map_4d(&tmX, d->x, d->N, d->H, d->W, d->Cin, CK, Cfg::TW + d->S - 1,
+                             Cfg::TH + d->R - 1, CK == 64 ? 128 : 32);
+  if (rc != VDQN_OK) return rc;
+  rc = make_tiled_map_2d(&tmW, d->w, (uint64_t)d->R * d->S * d->Cin, d->Cout, CK, 64, CK == 64 ? 128 : 32);
+  if (rc != VDQN_OK) return rc;
+  HaloArgs a{};
+  a.N = d->N; a.H = d->H; a.W = d->W; a.Cout = d->Cout;
+  a.R = d->R; a.S = d->S; a.pad_lo = d->pad_lo;
+  a.tiles_w = (d->W + Cfg::TW - 1) / Cfg::TW;
+  a.tiles_h = (d->H + Cfg::TH - 1) / Cfg::TH;
+  a.num_tiles = d->N * a.tiles_w * a.tiles_h;
+  a.epi = make_epi_args(d);
+  const int sms = d->max_ctas > 0 && d->max_ctas < dev->num_sms ? d->max_ctas : dev->num_sms;
+  const int grid = a.num_tiles < sms ? a.num_tiles : sms;
+  kfn<<<grid, 192, Cfg::SMEM_BYTES, stream>>>(tmX, tmW, a);
+  VDQN_CHECK_LAUNCH("halo_conv launch");
+  return VDQN_OK;
+}
+
+static int make_tiled_map_4d(CUtensorMap* map, const void* base, int N, int H, int W, int C, int box_c,
+                             int box_w, int box_h, int swizzle_bytes) {
+  return make_tiled_map_nhwc(map, base, N, H, W, C, box_c, box_w, box_h, swizzle_bytes);
+}
+
+// Shapes this kernel takes: stride-1 "same" convolutions with Cout = 64 whose whole filter fits in
+// shared memory: 3x3 over 64 channels (layer1 fwd/dgrad) and the packed 4x4 x 16-channel stem.
+bool halo_conv_supported(const vdqn_conv_desc* d) {
+  if (d->stride != 1 || d->dil != 1 || d->Cout != 64 || d->out_scatter == 2 || d->out2 != nullptr)
+    return false;
+  if (d->Cin == 64 && d->R == 3 && d->S == 3 && d->pad_lo == 1 && d->pad_hi == 1) return true;
+  if (d->Cin == 16 && d->R == 4 && d->S == 4 && d->pad_lo == 2 && d->pad_hi == 1) return true;
+  return false;
+}
+
+int halo_conv_launch(const vdqn_conv_desc* d, cudaStream_t stream) {
+  return d->Cin == 64 ? launch_halo<64>(d, stream) : launch_halo<16>(d, stream);
+}
+
+}  // namespace vdqn

@@ -28,6 +28,15 @@ int make_tiled_map_2d(CUtensorMap* map, const void* base, uint64_t cols, uint64_
                       uint32_t box_cols, uint32_t box_rows, int swizzle_bytes,
                       uint64_t row_stride_elems = 0);
 
+// NHWC bf16 activation tensor, plain tiled mode, box = [1][box_h][box_w][box_c] (out-of-image
+// coordinates, including negative ones, are zero-filled).
+int make_tiled_map_nhwc(CUtensorMap* map, const void* base, int N, int H, int W, int C, int box_c,
+                        int box_w, int box_h, int swizzle_bytes);
+
+// halo_conv.cu
+bool halo_conv_supported(const vdqn_conv_desc* d);
+int halo_conv_launch(const vdqn_conv_desc* d, cudaStream_t stream);
+
 inline int ceil_div(long a, long b) { return (int)((a + b - 1) / b); }
 
 // every kernel launch of the library is counted (bench.py reports it as `gpu_launches`)

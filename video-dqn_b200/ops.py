@@ -54,7 +54,7 @@ def conv_out_hw(H, W, R, S, stride, pad_lo, pad_hi, dil=1):
 
 def conv_gemm(x, w, stride=1, pad_lo=0, pad_hi=None, *, shift=None, residual=None, mask_src=None,
               relu=False, out_f32=False, colsum=None, out=None, out2=None, out_scatter=1,
-              tile_n=0, max_ctas=0, dil=1):
+              tile_n=0, max_ctas=0, dil=1, algo=0):
     """x [N,H,W,Cin] bf16, w [Cout,R,S,Cin] bf16 -> out [N,Ho,Wo,Cout] (or zero-dilated
     [N,2Ho,2Wo,Cout] when out_scatter == 2; `out` must then be pre-zeroed)."""
     lib = L.load()
@@ -91,7 +91,7 @@ def conv_gemm(x, w, stride=1, pad_lo=0, pad_hi=None, *, shift=None, residual=Non
     d.ldc = d.ldr = d.ldm = d.out2_ld = Cout
     d.out_scatter = out_scatter
     d.flags = (L.EPI_RELU if relu else 0) | (L.EPI_OUT_F32 if out_f32 else 0)
-    d.tile_n, d.max_ctas = tile_n, max_ctas
+    d.tile_n, d.max_ctas, d.algo = tile_n, max_ctas, algo
     with _Prof("igemm", (N, H, W_, Cin, Cout, R, stride)):
         L.check(lib.vdqn_conv_gemm(C.byref(d), L.stream_ptr()), "conv_gemm")
     return out
