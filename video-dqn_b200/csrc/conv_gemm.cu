@@ -63,7 +63,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint32_t* tmem_slot_ptr =
       reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
-  const int warp = threadIdx.x >> 5;
+  // warp index via a shuffle broadcast so the compiler keeps role dispatch (and the TMA / MMA
+  // operands computed under it) on the uniform datapath
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
@@ -96,18 +98,18 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int n_t = t % a.num_n_tiles, m_t = t / a.num_n_tiles;
-        const int m0 = m_t * Cfg::BM;
-        const int img = m0 / HoWo;
-        const int rem = m0 - img * HoWo;
-        const int p0 = rem / a.Wo, q0 = rem - p0 * a.Wo;
-        const int cw = q0 * a.stride + a.lower_w, ch = p0 * a.stride + a.lower_h;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(empty_bar(stage), phase ^ 1);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int n_t = t % a.num_n_tiles, m_t = t / a.num_n_tiles;
+      const int m0 = m_t * Cfg::BM;
+      const int img = m0 / HoWo;
+      const int rem = m0 - img * HoWo;
+      const int p0 = rem / a.Wo, q0 = rem - p0 * a.Wo;
+      const int cw = q0 * a.stride + a.lower_w, ch = p0 * a.stride + a.lower_h;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(empty_bar(stage), phase ^ 1);
+        if (elect_one()) {
           mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
           const uint32_t sA = smem_base + stage * Cfg::STAGE_BYTES;
           const uint32_t sB = sA + Cfg::KSUB * Cfg::A_SUB_BYTES;
@@ -121,26 +123,27 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                                (uint16_t)(s * a.dil), (uint16_t)(r * a.dil));
             tma_load_2d(sB + sub * Cfg::B_SUB_BYTES, &tmB, full_bar(stage), j * CK, n_t * BN);
           }
-          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
-        const int acc = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1;
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+    constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(full_bar(stage), phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(full_bar(stage), phase);
-          tc_fence_after();
+        if (elect_one()) {
           const uint32_t sA = smem_base + stage * Cfg::STAGE_BYTES;
           const uint32_t sB = sA + Cfg::KSUB * Cfg::A_SUB_BYTES;
 #pragma unroll
@@ -155,9 +158,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             }
           }
           umma_commit(empty_bar(stage));
-          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+          if (kb == num_kb - 1) umma_commit(tfull_bar(acc));
         }
-        umma_commit(tfull_bar(acc));
+        __syncwarp();
+        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else {

@@ -30,7 +30,8 @@ struct HaloCfg {
   static constexpr int TH = 16, TW = 8, BN = 64;
   static constexpr int ROW_BYTES = CK * 2;
   static constexpr uint64_t SWZ = (CK == 64) ? kSwz128 : kSwz32;
-  static constexpr int MAX_TAPS = (CK == 64) ? 9 : 16;
+  static constexpr int R = (CK == 64) ? 3 : 4, S = R;   // filter size is fixed per variant
+  static constexpr int MAX_TAPS = R * S;
   static constexpr int HALO_H = (CK == 64) ? 18 : 19, HALO_W = (CK == 64) ? 10 : 11;
   static constexpr int HALO_BYTES = HALO_H * HALO_W * ROW_BYTES;
   static constexpr int STAGE_BYTES = (HALO_BYTES + 1023) / 1024 * 1024;
@@ -68,7 +69,7 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 5);
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
   const int taps = a.R * a.S;
 
@@ -105,53 +106,61 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   };
 
   if (warp == 0) {
-    if (lane == 0) {
-      // the filter: one [64 x CK] tile per tap, resident for the whole kernel
+    // the filter: one [64 x CK] tile per tap, resident for the whole kernel
+    if (elect_one()) {
       mbar_expect_tx(w_bar, taps * Cfg::W_TILE_BYTES);
       for (int j = 0; j < taps; ++j) tma_load_2d(sW + j * Cfg::W_TILE_BYTES, &tmW, w_bar, j * CK, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
-        int n, h0, w0;
-        decode(t, n, h0, w0);
-        mbar_wait(empty_bar(stage), phase ^ 1);
+    }
+    __syncwarp();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
+      int n, h0, w0;
+      decode(t, n, h0, w0);
+      mbar_wait(empty_bar(stage), phase ^ 1);
+      if (elect_one()) {
         mbar_expect_tx(full_bar(stage), Cfg::HALO_BYTES);
         tma_load_tiled_4d(sA0 + stage * Cfg::STAGE_BYTES, &tmX, full_bar(stage), 0, w0 - a.pad_lo,
                           h0 - a.pad_lo, n);
-        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
       }
+      __syncwarp();
+      if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(128, Cfg::BN, 0, 0);
-      mbar_wait(w_bar, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x, ++it) {
-        const int acc = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1;
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
-        mbar_wait(full_bar(stage), phase);
-        tc_fence_after();
+    constexpr uint32_t idesc = make_idesc_bf16(128, Cfg::BN, 0, 0);
+    mbar_wait(w_bar, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+      mbar_wait(full_bar(stage), phase);
+      tc_fence_after();
+      if (elect_one()) {
         const uint32_t d_tmem = tmem_base + acc * Cfg::BN;
         const uint32_t sA = sA0 + stage * Cfg::STAGE_BYTES;
-        for (int r = 0; r < a.R; ++r) {
-          for (int s = 0; s < a.S; ++s) {
-            const uint32_t a_tap = sA + (r * Cfg::HALO_W + s) * Cfg::ROW_BYTES;
-            const uint32_t b_tap = sW + (r * a.S + s) * Cfg::W_TILE_BYTES;
+        // descriptors advance by compile-time constants: (tap row, tap col, k16 step)
+        const uint64_t a0 = make_smem_desc(sA, 16, Cfg::HALO_W * Cfg::ROW_BYTES, Cfg::SWZ);
+        const uint64_t b0 = make_smem_desc(sW, 16, 8 * Cfg::ROW_BYTES, Cfg::SWZ);
+#pragma unroll
+        for (int r = 0; r < Cfg::R; ++r) {
+#pragma unroll
+          for (int s = 0; s < Cfg::S; ++s) {
 #pragma unroll
             for (int k = 0; k < CK / 16; ++k) {
-              const uint64_t ad = make_smem_desc(a_tap + k * 32, 16, Cfg::HALO_W * Cfg::ROW_BYTES, Cfg::SWZ);
-              const uint64_t bd = make_smem_desc(b_tap + k * 32, 16, 8 * Cfg::ROW_BYTES, Cfg::SWZ);
+              const uint64_t ad = a0 + (uint64_t)(((r * Cfg::HALO_W + s) * Cfg::ROW_BYTES + k * 32) >> 4);
+              const uint64_t bd = b0 + (uint64_t)(((r * Cfg::S + s) * Cfg::W_TILE_BYTES + k * 32) >> 4);
               umma_f16(d_tmem, ad, bd, idesc, (r | s | k) != 0);
             }
           }
         }
         umma_commit(empty_bar(stage));
         umma_commit(tfull_bar(acc));
-        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
       }
+      __syncwarp();
+      if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
     }
   } else {
     const int quad = warp & 3;

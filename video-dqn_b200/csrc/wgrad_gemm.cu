@@ -57,7 +57,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ C
   uint32_t* tmem_slot_ptr =
       reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
@@ -103,22 +103,22 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ C
   };
 
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int u = blockIdx.x; u < units; u += gridDim.x) {
-        int split, co_t, grp;
-        decode(u, split, co_t, grp);
-        const int nslab = min(Cfg::SLABS, total_slabs - grp * Cfg::SLABS);
-        const int ksteps = ksteps_of(split);
-        const uint32_t tx = co_slabs * Cfg::A_SLAB_BYTES + nslab * Cfg::B_SLAB_BYTES;
-        for (int i = 0; i < ksteps; ++i) {
-          const int m0 = split * a.pix_per_split + i * Cfg::PIX;
-          const int img = m0 / HoWo;
-          const int rem = m0 - img * HoWo;
-          const int p0 = rem / a.Wo, q0 = rem - p0 * a.Wo;
-          const int cw = q0 * a.stride + a.lower_w, ch = p0 * a.stride + a.lower_h;
-          mbar_wait(empty_bar(stage), phase ^ 1);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int u = blockIdx.x; u < units; u += gridDim.x) {
+      int split, co_t, grp;
+      decode(u, split, co_t, grp);
+      const int nslab = min(Cfg::SLABS, total_slabs - grp * Cfg::SLABS);
+      const int ksteps = ksteps_of(split);
+      const uint32_t tx = co_slabs * Cfg::A_SLAB_BYTES + nslab * Cfg::B_SLAB_BYTES;
+      for (int i = 0; i < ksteps; ++i) {
+        const int m0 = split * a.pix_per_split + i * Cfg::PIX;
+        const int img = m0 / HoWo;
+        const int rem = m0 - img * HoWo;
+        const int p0 = rem / a.Wo, q0 = rem - p0 * a.Wo;
+        const int cw = q0 * a.stride + a.lower_w, ch = p0 * a.stride + a.lower_h;
+        mbar_wait(empty_bar(stage), phase ^ 1);
+        if (elect_one()) {
           mbar_expect_tx(full_bar(stage), tx);
           const uint32_t sA = smem_base + stage * Cfg::STAGE_BYTES;
           const uint32_t sB = sA + Cfg::A_BYTES;
@@ -132,29 +132,30 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ C
             tma_load_im2col_4d(sB + sl * Cfg::B_SLAB_BYTES, &tmX, full_bar(stage), c0, cw, ch, img,
                                (uint16_t)(s * a.dil), (uint16_t)(r * a.dil));
           }
-          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int u = blockIdx.x; u < units; u += gridDim.x, ++it) {
-        int split, co_t, grp;
-        decode(u, split, co_t, grp);
-        const int nslab = min(Cfg::SLABS, total_slabs - grp * Cfg::SLABS);
-        const int ksteps = ksteps_of(split);
-        const uint32_t idesc = make_idesc_bf16(128, nslab * CK, 1, 1);
-        const int acc = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1;
-        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int u = blockIdx.x; u < units; u += gridDim.x, ++it) {
+      int split, co_t, grp;
+      decode(u, split, co_t, grp);
+      const int nslab = min(Cfg::SLABS, total_slabs - grp * Cfg::SLABS);
+      const int ksteps = ksteps_of(split);
+      const uint32_t idesc = make_idesc_bf16(128, nslab * CK, 1, 1);
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * Cfg::BN;
+      for (int i = 0; i < ksteps; ++i) {
+        mbar_wait(full_bar(stage), phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * Cfg::BN;
-        for (int i = 0; i < ksteps; ++i) {
-          mbar_wait(full_bar(stage), phase);
-          tc_fence_after();
+        if (elect_one()) {
           const uint32_t sA = smem_base + stage * Cfg::STAGE_BYTES;
           const uint32_t sB = sA + Cfg::A_BYTES;
 #pragma unroll
@@ -166,9 +167,14 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ C
             umma_f16(d_tmem, ad, bd, idesc, (i | k) != 0);
           }
           umma_commit(empty_bar(stage));
-          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+          if (i == ksteps - 1) umma_commit(tfull_bar(acc));
         }
-        umma_commit(tfull_bar(acc));
+        __syncwarp();
+        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (ksteps == 0) {
+        if (elect_one()) umma_commit(tfull_bar(acc));
+        __syncwarp();
       }
     }
   } else {
