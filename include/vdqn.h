@@ -97,7 +97,7 @@ int vdqn_conv_wgrad(const vdqn_wgrad_desc* d, void* stream);
 
 /* Reduce the split partials and turn them into the reference's parameter gradients:
  *   g = sum_split part;  dW[co,ci,r,s] = scale[co] * g[co,(r,s,ci)]   (torch OIHW layout, fp32)
- *   dgamma[co] = rstd[co] * (sum_k W[co,k] * g[co,k] - mean[co] * dbeta[co])
+ *   dgamma[co] += rstd[co] * (sum_k W[co,k] * g[co,k] - mean[co] * dbeta[co])   (atomics: zero it first)
  * (native_batch_norm_backward in eval mode)  `kmap` selects how the
  * GEMM-K index maps to (ci,r,s): 0 = (r,s,ci) with ci < Cin; 1 = space-to-depth stem
  * (4x4 taps x 16 packed channels -> 7x7 x 3). */

@@ -351,7 +351,7 @@ def prep_and_finalize():
     ok &= _report("prep:shift", shift[None], (beta - mean * scale)[None], 1e-5)
     part = torch.randn(3, Cout, K, device="cuda", generator=g)
     dbeta = torch.randn(Cout, device="cuda", generator=g)
-    dw = torch.empty_like(w); dgamma = torch.empty(Cout, device="cuda")
+    dw = torch.empty_like(w); dgamma = torch.zeros(Cout, device="cuda")
     ops.wgrad_finalize(part, w, dw, splits=3, Cout=Cout, Cin=Cin, R=R, S=R, K=K, gamma=gamma, var=var,
                        mean=mean, dbeta=dbeta, dgamma=dgamma)
     gsum = part.sum(0).view(Cout, R, R, Cin).permute(0, 3, 1, 2)

@@ -57,39 +57,35 @@ __global__ void weight_prep_kernel(const vdqn_wprep_desc d) {
   }
 }
 
-// one block per output channel
+// grid = (K blocks of 256, Cout): thread = one (co, k).  The split partials are summed in a fixed
+// order (deterministic); d gamma is accumulated with one atomic per warp into a zeroed slot.
 __global__ void wgrad_finalize_kernel(const vdqn_wgrad_fin_desc d) {
-  const int co = blockIdx.x;
+  const int co = blockIdx.y;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
   float rstd = 1.f, scale = 1.f;
   if (d.gamma != nullptr) {
     rstd = 1.0f / sqrtf(d.var[co] + d.eps);
     scale = d.gamma[co] * rstd;
   }
   float dot = 0.f;
-  const long plane = (long)d.Cout * d.K;
-  for (int k = threadIdx.x; k < d.K; k += blockDim.x) {
-    float g = 0.f;
+  if (k < d.K) {
+    const long plane = (long)d.Cout * d.K;
     const float* p = d.part + (long)co * d.K + k;
+    float g = 0.f;
     for (int s = 0; s < d.splits; ++s) g += p[s * plane];
     int r, ss, ci;
     const int src = oihw_index(co, k, d.Cin, d.R, d.S, d.kmap, &r, &ss, &ci);
     if (src >= 0) {
-      dot += d.w[src] * g;
+      dot = d.w[src] * g;
       d.dw[src] = scale * g;
     }
   }
   if (d.dgamma != nullptr) {
-    __shared__ float red[32];
     for (int off = 16; off; off >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, off);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dot;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-      float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
-      for (int off = 16; off; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-      if (threadIdx.x == 0) {
-        const float db = d.dbeta != nullptr ? d.dbeta[co] : 0.f;
-        d.dgamma[co] = rstd * (v - d.mean[co] * db);
-      }
+    if ((threadIdx.x & 31) == 0) {
+      float v = rstd * dot;
+      if (blockIdx.x == 0 && threadIdx.x == 0 && d.dbeta != nullptr) v -= rstd * d.mean[co] * d.dbeta[co];
+      atomicAdd(d.dgamma + co, v);
     }
   }
 }
@@ -148,7 +144,10 @@ __global__ void stem_pack_kernel(const void* __restrict__ xin, __nv_bfloat16* __
 }
 
 // ------------------------------------------------------------------------------------------
-// max_pool2d(3,2,1), NHWC bf16; one thread = 8 channels of one output pixel
+// max_pool2d(3,2,1), NHWC bf16; one thread = 8 channels of one output pixel.  Values stay packed
+// as bf16x2: one __hgt2_mask + __hmax2 + select per pair and tap.  Strict '>' against a -inf start
+// keeps the first maximum of the window scan (torch's choice of arg-max).
+template <bool IDX>
 __global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
                                    uint8_t* __restrict__ idx, int N, int H, int W, int C) {
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1, CG = C / 8;
@@ -160,11 +159,10 @@ __global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfl
     const int q = (int)(t % Wo); t /= Wo;
     const int p = (int)(t % Ho);
     const int n = (int)(t / Ho);
-    float best[8];
-    int slot[8];
+    uint32_t best[4], slot[4];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) { best[e] = -INFINITY; slot[e] = 0; }
-    bool first = true;
+    for (int e = 0; e < 4; ++e) { best[e] = 0xFF80FF80u; slot[e] = 0u; }     // -inf, -inf
+    const __nv_bfloat16* base = x + ((long)n * H * W) * C + cg * 8;
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
       const int h = 2 * p - 1 + r;
@@ -173,26 +171,27 @@ __global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfl
       for (int s = 0; s < 3; ++s) {
         const int w = 2 * q - 1 + s;
         if (w < 0 || w >= W) continue;
-        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(x + (((long)n * H + h) * W + w) * C + cg * 8));
-        const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&raw);
+        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(base + ((long)h * W + w) * C));
+        const uint32_t v[4] = {raw.x, raw.y, raw.z, raw.w};
+        const uint32_t tap2 = (uint32_t)(r * 3 + s) * 0x00010001u;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float2 f = __bfloat1622float2(hh[e]);
-          if (first || f.x > best[2 * e]) { best[2 * e] = f.x; slot[2 * e] = r * 3 + s; }
-          if (first || f.y > best[2 * e + 1]) { best[2 * e + 1] = f.y; slot[2 * e + 1] = r * 3 + s; }
+          const __nv_bfloat162 nv = *reinterpret_cast<const __nv_bfloat162*>(&v[e]);
+          const __nv_bfloat162 bv = *reinterpret_cast<const __nv_bfloat162*>(&best[e]);
+          if (IDX) {
+            const uint32_t m = __hgt2_mask(nv, bv);
+            slot[e] = (tap2 & m) | (slot[e] & ~m);
+          }
+          const __nv_bfloat162 mx = __hmax2(nv, bv);
+          best[e] = *reinterpret_cast<const uint32_t*>(&mx);
         }
-        first = false;
       }
     }
-    uint4 pk;
-    __nv_bfloat162* ho = reinterpret_cast<__nv_bfloat162*>(&pk);
-#pragma unroll
-    for (int e = 0; e < 4; ++e) ho[e] = __floats2bfloat162_rn(best[2 * e], best[2 * e + 1]);
-    *reinterpret_cast<uint4*>(y + i * 8) = pk;
-    if (idx != nullptr) {
-      uint2 ip;
-      ip.x = slot[0] | (slot[1] << 8) | (slot[2] << 16) | (slot[3] << 24);
-      ip.y = slot[4] | (slot[5] << 8) | (slot[6] << 16) | (slot[7] << 24);
+    *reinterpret_cast<uint4*>(y + i * 8) = make_uint4(best[0], best[1], best[2], best[3]);
+    if (IDX) {
+      uint2 ip;     // 16-bit slots -> bytes, channel order preserved
+      ip.x = __byte_perm(slot[0], slot[1], 0x6420);
+      ip.y = __byte_perm(slot[2], slot[3], 0x6420);
       *reinterpret_cast<uint2*>(idx + i * 8) = ip;
     }
   }
@@ -216,9 +215,7 @@ __global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const u
     const int w = (int)(t % W); t /= W;
     const int h = (int)(t % H);
     const int n = (int)(t / H);
-    float g[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) g[e] = 0.f;
+    uint32_t g2[4] = {0u, 0u, 0u, 0u};              // packed bf16x2 accumulators
     const int p_lo = h >> 1, p_hi = (h + 1) >> 1;     // windows p with 2p-1 <= h <= 2p+1
     const int q_lo = w >> 1, q_hi = (w + 1) >> 1;
     for (int p = p_lo; p <= p_hi; ++p) {
@@ -227,27 +224,34 @@ __global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const u
       for (int q = q_lo; q <= q_hi; ++q) {
         if (q >= Wo) continue;
         const int s = w - 2 * q + 1;
-        const int want = r * 3 + s;
+        const uint32_t want4 = (uint32_t)(r * 3 + s) * 0x01010101u;
         const long o = (((long)n * Ho + p) * Wo + q) * C + cg * 8;
         const uint2 ip = __ldg(reinterpret_cast<const uint2*>(idx + o));
         const uint4 raw = __ldg(reinterpret_cast<const uint4*>(dy + o));
-        const __nv_bfloat16* hv = reinterpret_cast<const __nv_bfloat16*>(&raw);
+        const uint32_t m_lo = __vcmpeq4(ip.x, want4), m_hi = __vcmpeq4(ip.y, want4);   // 0xFF per match
+        const uint32_t m[4] = {__byte_perm(m_lo, 0, 0x1100), __byte_perm(m_lo, 0, 0x3322),
+                               __byte_perm(m_hi, 0, 0x1100), __byte_perm(m_hi, 0, 0x3322)};
+        const uint32_t v[4] = {raw.x & m[0], raw.y & m[1], raw.z & m[2], raw.w & m[3]};
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int sl = ((e < 4 ? ip.x : ip.y) >> (8 * (e & 3))) & 0xff;
-          if (sl == want) g[e] += __bfloat162float(hv[e]);
+        for (int e = 0; e < 4; ++e) {
+          const __nv_bfloat162 sum = __hadd2(*reinterpret_cast<const __nv_bfloat162*>(&g2[e]),
+                                             *reinterpret_cast<const __nv_bfloat162*>(&v[e]));
+          g2[e] = *reinterpret_cast<const uint32_t*>(&sum);
         }
       }
     }
     const uint4 xr = __ldg(reinterpret_cast<const uint4*>(x + i * 8));
-    const __nv_bfloat16* xv = reinterpret_cast<const __nv_bfloat16*>(&xr);
+    const uint32_t xv[4] = {xr.x, xr.y, xr.z, xr.w};
+    const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
     uint4 pk;
-    __nv_bfloat16* ov = reinterpret_cast<__nv_bfloat16*>(&pk);
+    uint32_t* ov = reinterpret_cast<uint32_t*>(&pk);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const float v = __bfloat162float(xv[e]) > 0.f ? g[e] : 0.f;
-      ov[e] = __float2bfloat16_rn(v);
-      acc[e] += __bfloat162float(ov[e]);
+    for (int e = 0; e < 4; ++e) {
+      const uint32_t keep = __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&xv[e]), zero2);
+      ov[e] = g2[e] & keep;
+      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ov[e]));
+      acc[2 * e] += f.x;
+      acc[2 * e + 1] += f.y;
     }
     *reinterpret_cast<uint4*>(dx + i * 8) = pk;
   }
@@ -271,7 +275,7 @@ __global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const u
 __global__ void __launch_bounds__(256)
 sgemm_strided_kernel(const float* __restrict__ A, const float* __restrict__ Bm, float* __restrict__ Cm,
                      const float* __restrict__ bias, int M, int N, int K, long a_rs, long a_cs,
-                     long b_rs, long b_cs, int ldc, int relu) {
+                     long b_rs, long b_cs, int ldc, int relu, int k_len) {
   __shared__ float As[16][64 + 4];
   __shared__ float Bs[16][64 + 4];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -281,7 +285,11 @@ sgemm_strided_kernel(const float* __restrict__ A, const float* __restrict__ Bm, 
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (int k0 = 0; k0 < K; k0 += 16) {
+  // split-K: blockIdx.z owns K range [k_begin, k_end) and accumulates with atomics
+  const int k_begin = blockIdx.z * k_len;
+  const int k_end = min(K, k_begin + k_len);
+  const bool split = gridDim.z > 1;
+  for (int k0 = k_begin; k0 < k_end; k0 += 16) {
 #pragma unroll
     for (int l = 0; l < 4; ++l) {
       const int e = threadIdx.x + l * 256;       // 0..1023
@@ -290,9 +298,9 @@ sgemm_strided_kernel(const float* __restrict__ A, const float* __restrict__ Bm, 
       if (a_cs == 1) { ak = e & 15; am = e >> 4; } else { am = e & 63; ak = e >> 6; }
       if (b_cs == 1) { bn = e & 63; bk = e >> 6; } else { bk = e & 15; bn = e >> 4; }
       const int gm = m0 + am, gk = k0 + ak;
-      As[ak][am] = (gm < M && gk < K) ? A[gm * a_rs + gk * a_cs] : 0.f;
+      As[ak][am] = (gm < M && gk < k_end) ? A[gm * a_rs + gk * a_cs] : 0.f;
       const int gn = n0 + bn, gk2 = k0 + bk;
-      Bs[bk][bn] = (gn < N && gk2 < K) ? Bm[gk2 * b_rs + gn * b_cs] : 0.f;
+      Bs[bk][bn] = (gn < N && gk2 < k_end) ? Bm[gk2 * b_rs + gn * b_cs] : 0.f;
     }
     __syncthreads();
 #pragma unroll
@@ -318,10 +326,24 @@ sgemm_strided_kernel(const float* __restrict__ A, const float* __restrict__ Bm, 
       const int gn = n0 + tx * 4 + j;
       if (gn >= N) continue;
       float v = acc[i][j];
-      if (bias != nullptr) v += bias[gn];
-      if (relu) v = fmaxf(v, 0.f);
-      Cm[(long)gm * ldc + gn] = v;
+      if (split) {
+        atomicAdd(Cm + (long)gm * ldc + gn, v);
+      } else {
+        if (bias != nullptr) v += bias[gn];
+        if (relu) v = fmaxf(v, 0.f);
+        Cm[(long)gm * ldc + gn] = v;
+      }
     }
+  }
+}
+
+__global__ void bias_act_kernel(float* __restrict__ c, const float* __restrict__ bias, long total, int N,
+                                int relu) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    float v = c[i];
+    if (bias != nullptr) v += bias[i % N];
+    if (relu) v = fmaxf(v, 0.f);
+    c[i] = v;
   }
 }
 
@@ -496,7 +518,7 @@ extern "C" int vdqn_wgrad_finalize(const vdqn_wgrad_fin_desc* d, void* stream_v)
     return set_error(VDQN_ERR_ARG, "wgrad_finalize: null pointer");
   GET_DEV();
   (void)dev;
-  wgrad_finalize_kernel<<<d->Cout, 256, 0, stream>>>(*d);
+  wgrad_finalize_kernel<<<dim3((d->K + 255) / 256, d->Cout), 256, 0, stream>>>(*d);
   VDQN_CHECK_LAUNCH("wgrad_finalize");
   return VDQN_OK;
 }
@@ -533,8 +555,12 @@ extern "C" int vdqn_maxpool_fwd(const void* x, void* y, uint8_t* idx, int32_t N,
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
   const long total = (long)N * Ho * Wo * (C / 8);
   if (total == 0) return VDQN_OK;
-  maxpool_fwd_kernel<<<grid_for(total, 256, dev->num_sms, 16), 256, 0, stream>>>(
-      static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), idx, N, H, W, C);
+  if (idx != nullptr)
+    maxpool_fwd_kernel<true><<<grid_for(total, 256, dev->num_sms, 16), 256, 0, stream>>>(
+        static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), idx, N, H, W, C);
+  else
+    maxpool_fwd_kernel<false><<<grid_for(total, 256, dev->num_sms, 16), 256, 0, stream>>>(
+        static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), idx, N, H, W, C);
   VDQN_CHECK_LAUNCH("maxpool_fwd");
   return VDQN_OK;
 }
@@ -557,9 +583,33 @@ extern "C" int vdqn_maxpool_bwd(const void* dy, const uint8_t* idx, const void* 
 static int launch_sgemm(const float* A, const float* B, float* C, const float* bias, int M, int N, int K,
                         long a_rs, long a_cs, long b_rs, long b_cs, int ldc, int relu, cudaStream_t stream) {
   if (M == 0 || N == 0) return VDQN_OK;
-  dim3 grid((N + 63) / 64, (M + 63) / 64);
-  sgemm_strided_kernel<<<grid, 256, 0, stream>>>(A, B, C, bias, M, N, K, a_rs, a_cs, b_rs, b_cs, ldc, relu);
+  DeviceInfo* dev = device_info();
+  if (dev == nullptr) return VDQN_ERR_CUDA;
+  dim3 grid((N + 63) / 64, (M + 63) / 64, 1);
+  // under-filled grids (the MLP has M = batch): split K across blockIdx.z
+  const int tiles = grid.x * grid.y;
+  int splitk = 1;
+  if (tiles * 2 <= dev->num_sms && ldc == N) {
+    splitk = (dev->num_sms + tiles - 1) / tiles;
+    if (splitk > 16) splitk = 16;
+    while (splitk > 1 && K / splitk < 64) --splitk;
+  }
+  int k_len = (K + splitk - 1) / splitk;
+  k_len = (k_len + 15) / 16 * 16;
+  splitk = (K + k_len - 1) / k_len;
+  grid.z = splitk;
+  if (splitk > 1) {
+    cudaError_t e = cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, stream);
+    if (e != cudaSuccess) return set_error(VDQN_ERR_CUDA, "sgemm memset: %s", cudaGetErrorString(e));
+  }
+  sgemm_strided_kernel<<<grid, 256, 0, stream>>>(A, B, C, bias, M, N, K, a_rs, a_cs, b_rs, b_cs, ldc, relu,
+                                                 k_len);
   VDQN_CHECK_LAUNCH("sgemm");
+  if (splitk > 1 && (bias != nullptr || relu)) {
+    const long total = (long)M * N;
+    bias_act_kernel<<<grid_for(total, 256, dev->num_sms), 256, 0, stream>>>(C, bias, total, N, relu);
+    VDQN_CHECK_LAUNCH("bias_act");
+  }
   return VDQN_OK;
 }
 
