@@ -28,6 +28,7 @@ struct IgemmArgs {
   int num_m_tiles, num_n_tiles;
   EpiArgs epi;
   int out_scatter;    // 1: opix = m;  2: opix = (n*2Ho + 2p)*2Wo + 2q
+  int fast;           // staged TMA epilogue (BN <= 128, bf16 compact output)
 };
 
 template <int BN, int CK>
@@ -37,10 +38,17 @@ struct IgemmCfg {
   static constexpr int A_SUB_BYTES = BM * CK * 2;
   static constexpr int B_SUB_BYTES = BN * CK * 2;
   static constexpr int STAGE_BYTES = KSUB * (A_SUB_BYTES + B_SUB_BYTES);
-  static constexpr int STAGES = (190 * 1024) / STAGE_BYTES > 8 ? 8 : (190 * 1024) / STAGE_BYTES;
+  // staged epilogue tiles (per epilogue warp: out / residual / mask, 4 KB per 64-column group);
+  // BN = 256 keeps the direct epilogue (its long K loops hide it) and all its smem for the pipeline
+  static constexpr bool FAST_EPI = BN <= 128;
+  static constexpr int GROUPS = BN / 64;
+  static constexpr int EPI_WARP_BYTES = FAST_EPI ? GROUPS * 3 * 4096 : 0;
+  static constexpr int EPI_BYTES = 4 * EPI_WARP_BYTES;
+  static constexpr int PIPE_BUDGET = 224 * 1024 - EPI_BYTES;
+  static constexpr int STAGES = PIPE_BUDGET / STAGE_BYTES > 8 ? 8 : PIPE_BUDGET / STAGE_BYTES;
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
                                    : (2 * BN <= 256) ? 256 : 512;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   static constexpr uint64_t SWZ = (CK == 64) ? kSwz128 : kSwz32;
   static constexpr int ROW_BYTES = CK * 2;          // bytes per smem row (= swizzle span)
   static constexpr int SBO = 8 * ROW_BYTES;         // 8-row group pitch
@@ -49,17 +57,20 @@ struct IgemmCfg {
 template <int BN, int CK>
 __global__ void __launch_bounds__(192, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-             const IgemmArgs a) {
+             const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
+             const __grid_constant__ CUtensorMap tmMask, const IgemmArgs a) {
   using Cfg = IgemmCfg<BN, CK>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
+  const uint32_t epi_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
+  const uint32_t bar_base = epi_base + Cfg::EPI_BYTES;
   // barriers: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then tmem ptr slot
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
   auto tfull_bar = [&](int i) { return bar_base + 8u * (2 * Cfg::STAGES + i); };
   auto tempty_bar = [&](int i) { return bar_base + 8u * (2 * Cfg::STAGES + 2 + i); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 4);
+  const uint32_t ld_bar0 = bar_base + 8u * (2 * Cfg::STAGES + 4);     // one per epilogue warp
+  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 8);
   uint32_t* tmem_slot_ptr =
       reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -79,6 +90,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       mbar_init(tfull_bar(i), 1);
       mbar_init(tempty_bar(i), 4);   // one arrive per epilogue warp
     }
+    for (int i = 0; i < 4; ++i) mbar_init(ld_bar0 + 8u * i, 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -168,6 +180,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     // ------------------------------------------------------------ epilogue (warps 2..5)
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may touch
     const int row = quad * 32 + lane;
+    const uint32_t stg = epi_base + quad * Cfg::EPI_WARP_BYTES;     // [GROUPS] out | res | mask tiles
+    const uint32_t ld_bar = ld_bar0 + 8u * quad;
+    const bool has_res = a.epi.residual != nullptr, has_mask = a.epi.mask_src != nullptr;
+    const bool has_in = has_res || has_mask;
+    uint32_t ld_parity = 0;
     int it = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       const int n_t = t % a.num_n_tiles, m_t = t / a.num_n_tiles;
@@ -175,6 +192,49 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const uint32_t acc_phase = (it >> 1) & 1;
       const int m = m_t * Cfg::BM + row;
       const bool valid = m < a.M_total;
+      if (Cfg::FAST_EPI && a.fast) {
+        const int row0 = m_t * Cfg::BM + quad * 32;            // this warp's 32 output rows
+        if (has_in) {
+          if (elect_one()) {
+            mbar_expect_tx(ld_bar, Cfg::GROUPS * ((has_res ? 4096u : 0u) + (has_mask ? 4096u : 0u)));
+#pragma unroll
+            for (int gidx = 0; gidx < Cfg::GROUPS; ++gidx) {
+              const int col = n_t * BN + gidx * 64;
+              if (has_res) tma_load_2d(stg + (Cfg::GROUPS + gidx) * 4096, &tmRes, ld_bar, col, row0);
+              if (has_mask) tma_load_2d(stg + (2 * Cfg::GROUPS + gidx) * 4096, &tmMask, ld_bar, col, row0);
+            }
+          }
+          __syncwarp();
+        }
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
+        if (elect_one()) tma_store_wait_read<0>();     // previous tile's stores have left the out tiles
+        __syncwarp();
+#pragma unroll 1
+        for (int chunk = 0; chunk < BN / 32; ++chunk) {
+          uint32_t raw[32];
+          tmem_ld_32x32(tmem_base + acc * BN + chunk * 32 + ((uint32_t)(quad * 32) << 16), raw);
+          tmem_ld_wait();
+          if (chunk == 0 && has_in) mbar_wait(ld_bar, ld_parity);
+          const int gidx = chunk >> 1;
+          epilogue_half_staged(a.epi, raw, valid, n_t * BN + chunk * 32, chunk & 1, lane, stg + gidx * 4096,
+                               stg + (Cfg::GROUPS + gidx) * 4096, stg + (2 * Cfg::GROUPS + gidx) * 4096);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
+        fence_proxy_async();
+        __syncwarp();
+        if (elect_one()) {
+#pragma unroll
+          for (int gidx = 0; gidx < Cfg::GROUPS; ++gidx)
+            tma_store_2d(&tmOut, stg + gidx * 4096, n_t * BN + gidx * 64, row0);
+          tma_store_commit();
+        }
+        __syncwarp();
+        if (has_in) ld_parity ^= 1;
+        continue;
+      }
       long opix = m;
       long opix2 = 0;
       if (a.out_scatter == 2 || a.epi.out2 != nullptr) {
@@ -198,6 +258,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
     }
+    if (Cfg::FAST_EPI && a.fast) {
+      if (elect_one()) tma_store_wait<0>();
+      __syncwarp();
+    }
   }
 
   tc_fence_before();
@@ -211,8 +275,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 // ---------------------------------------------------------------------------- host side
 
 template <int BN, int CK>
-static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const IgemmArgs& a,
-                        int num_sms, cudaStream_t stream) {
+static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* epi_maps,
+                        const IgemmArgs& a, int num_sms, cudaStream_t stream) {
   using Cfg = IgemmCfg<BN, CK>;
   static bool attr_set = false;
   auto kfn = igemm_kernel<BN, CK>;
@@ -225,7 +289,7 @@ static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Ig
   }
   const int tiles = a.num_m_tiles * a.num_n_tiles;
   const int grid = tiles < num_sms ? tiles : num_sms;
-  kfn<<<grid, 192, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, a);
+  kfn<<<grid, 192, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, epi_maps[0], epi_maps[1], epi_maps[2], a);
   VDQN_CHECK_LAUNCH("igemm launch");
   return VDQN_OK;
 }
@@ -281,11 +345,22 @@ extern "C" int vdqn_conv_gemm(const vdqn_conv_desc* d, void* stream_v) {
   a.epi = make_epi_args(d);
   a.out_scatter = d->out_scatter == 2 ? 2 : 1;
 
+  // staged epilogue: 2-D maps over the [M][ld] output / residual / mask matrices, 64 x 32 boxes
+  CUtensorMap epi_maps[3] = {tmB, tmB, tmB};
+  a.fast = (BN <= 128 && fast_epilogue_ok(d)) ? 1 : 0;
+  if (a.fast) {
+    rc = make_tiled_map_2d(&epi_maps[0], d->out, d->Cout, a.M_total, 64, 32, 128, d->ldc);
+    if (rc == VDQN_OK && d->residual)
+      rc = make_tiled_map_2d(&epi_maps[1], d->residual, d->Cout, a.M_total, 64, 32, 128, d->ldr);
+    if (rc == VDQN_OK && d->mask_src)
+      rc = make_tiled_map_2d(&epi_maps[2], d->mask_src, d->Cout, a.M_total, 64, 32, 128, d->ldm);
+    if (rc != VDQN_OK) return rc;
+  }
   const int sms = d->max_ctas > 0 && d->max_ctas < dev->num_sms ? d->max_ctas : dev->num_sms;
-  if (CK == 16) return launch_igemm<64, 16>(tmA, tmB, a, sms, stream);
+  if (CK == 16) return launch_igemm<64, 16>(tmA, tmB, epi_maps, a, sms, stream);
   switch (BN) {
-    case 64: return launch_igemm<64, 64>(tmA, tmB, a, sms, stream);
-    case 128: return launch_igemm<128, 64>(tmA, tmB, a, sms, stream);
-    default: return launch_igemm<256, 64>(tmA, tmB, a, sms, stream);
+    case 64: return launch_igemm<64, 64>(tmA, tmB, epi_maps, a, sms, stream);
+    case 128: return launch_igemm<128, 64>(tmA, tmB, epi_maps, a, sms, stream);
+    default: return launch_igemm<256, 64>(tmA, tmB, epi_maps, a, sms, stream);
   }
 }

@@ -7,6 +7,7 @@
 #include <stdint.h>
 
 #include "../../include/vdqn.h"
+#include "ptx.cuh"
 
 namespace vdqn {
 
@@ -126,6 +127,95 @@ __device__ __forceinline__ void epilogue_chunk(const EpiArgs& a, const uint32_t 
     }
     atomicAdd(a.colsum + c0 + lane, v[0]);
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Staged ("fast") epilogue: global traffic goes through per-warp shared-memory tiles of
+// 32 pixels x 64 channels (bf16, 128-byte rows, 128B swizzle) moved by TMA -- residual / mask
+// tiles are TMA-loaded, the output tile is TMA-stored -- so the LSU only sees conflict-free
+// 16-byte shared accesses instead of 32 different cache lines per instruction.
+// One call handles 32 accumulator columns [half*32, half*32+32) of the warp's current 64-column
+// group: `stg_*` are the warp's staging tiles (1024-byte aligned), `c0` the first global channel.
+__device__ __forceinline__ void epilogue_half_staged(const EpiArgs& a, const uint32_t (&raw)[32], bool valid,
+                                                     int c0, int half, int lane, uint32_t stg_out,
+                                                     uint32_t stg_res, uint32_t stg_mask) {
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+  if (a.shift != nullptr) {
+    const float4* sp = reinterpret_cast<const float4*>(a.shift + c0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 s4 = __ldg(sp + j);
+      v[4 * j + 0] += s4.x; v[4 * j + 1] += s4.y; v[4 * j + 2] += s4.z; v[4 * j + 3] += s4.w;
+    }
+  }
+  const uint32_t row_off = (uint32_t)lane * 128u;
+  const uint32_t sw = (uint32_t)(lane & 7);
+  if (a.residual != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint4 r4 = lds128(stg_res + row_off + ((((uint32_t)(half * 4 + j)) ^ sw) << 4));
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r4);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __bfloat1622float2(h[e]);
+        v[8 * j + 2 * e] += f.x;
+        v[8 * j + 2 * e + 1] += f.y;
+      }
+    }
+  }
+  if (a.flags & VDQN_EPI_RELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+  }
+  if (a.mask_src != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint4 r4 = lds128(stg_mask + row_off + ((((uint32_t)(half * 4 + j)) ^ sw) << 4));
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r4);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __bfloat1622float2(h[e]);
+        if (!(f.x > 0.f)) v[8 * j + 2 * e] = 0.f;
+        if (!(f.y > 0.f)) v[8 * j + 2 * e + 1] = 0.f;
+      }
+    }
+  }
+  if (!valid) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = 0.f;
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint4 pk;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[8 * j + 2 * e], v[8 * j + 2 * e + 1]);
+    sts128(stg_out + row_off + ((((uint32_t)(half * 4 + j)) ^ sw) << 4), pk);
+  }
+  if (a.colsum != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __bfloat162float(__float2bfloat16_rn(v[j]));
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+      const bool upper = (lane & off) != 0;
+#pragma unroll
+      for (int i = 0; i < off; ++i) {
+        const float send = upper ? v[i] : v[i + off];
+        const float keep = upper ? v[i + off] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+      }
+    }
+    atomicAdd(a.colsum + c0 + lane, v[0]);
+  }
+}
+
+// bf16 output, compact destination: the staged epilogue applies
+inline bool fast_epilogue_ok(const vdqn_conv_desc* d) {
+  return !(d->flags & VDQN_EPI_OUT_F32) && d->out_scatter != 2 && d->out2 == nullptr &&
+         d->ldc % 8 == 0 && (d->residual == nullptr || d->ldr % 8 == 0) &&
+         (d->mask_src == nullptr || d->ldm % 8 == 0);
 }
 
 }  // namespace vdqn

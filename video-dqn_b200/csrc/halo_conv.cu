@@ -22,6 +22,7 @@ struct HaloArgs {
   int N, H, W, Cout;
   int R, S, pad_lo;
   int tiles_w, tiles_h, num_tiles;
+  int fast;            // staged TMA epilogue (bf16 compact output)
   EpiArgs epi;
 };
 
@@ -37,8 +38,10 @@ struct HaloCfg {
   static constexpr int STAGE_BYTES = (HALO_BYTES + 1023) / 1024 * 1024;
   static constexpr int W_TILE_BYTES = BN * ROW_BYTES;              // one tap: 64 rows x CK
   static constexpr int W_BYTES = MAX_TAPS * W_TILE_BYTES;          // 72 KB / 32 KB, resident
-  static constexpr int STAGES = (CK == 64) ? 6 : 12;
-  static constexpr int SMEM_BYTES = W_BYTES + STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int STAGES = (CK == 64) ? 4 : 12;
+  static constexpr int EPI_WARP_BYTES = 3 * 4096;                  // out, residual, mask tiles
+  static constexpr int EPI_BYTES = 4 * EPI_WARP_BYTES;
+  static constexpr int SMEM_BYTES = W_BYTES + STAGES * STAGE_BYTES + EPI_BYTES + 1024 + 256;
   static constexpr int TMEM_COLS = 128;
 };
 
@@ -54,19 +57,22 @@ __device__ __forceinline__ void tma_load_tiled_4d(uint32_t dst, const void* tmap
 template <int CK>
 __global__ void __launch_bounds__(192, 1)
 halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
-                 const HaloArgs a) {
+                 const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
+                 const __grid_constant__ CUtensorMap tmMask, const HaloArgs a) {
   using Cfg = HaloCfg<CK>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sW = smem_base;
   const uint32_t sA0 = smem_base + Cfg::W_BYTES;
-  const uint32_t bar_base = sA0 + Cfg::STAGES * Cfg::STAGE_BYTES;
+  const uint32_t epi_base = sA0 + Cfg::STAGES * Cfg::STAGE_BYTES;
+  const uint32_t bar_base = epi_base + Cfg::EPI_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
   auto tfull_bar = [&](int i) { return bar_base + 8u * (2 * Cfg::STAGES + i); };
   auto tempty_bar = [&](int i) { return bar_base + 8u * (2 * Cfg::STAGES + 2 + i); };
   const uint32_t w_bar = bar_base + 8u * (2 * Cfg::STAGES + 4);
-  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 5);
+  const uint32_t ld_bar0 = bar_base + 8u * (2 * Cfg::STAGES + 5);     // 4 barriers, one per epilogue warp
+  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 9);
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
@@ -85,6 +91,7 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       mbar_init(tempty_bar(i), 4);
     }
     mbar_init(w_bar, 1);
+    for (int i = 0; i < 4; ++i) mbar_init(ld_bar0 + 8u * i, 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -166,6 +173,12 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
     const int g = row >> 3, j = row & 7;
+    const uint32_t stg_out = epi_base + quad * Cfg::EPI_WARP_BYTES;
+    const uint32_t stg_res = stg_out + 4096, stg_mask = stg_out + 8192;
+    const uint32_t ld_bar = ld_bar0 + 8u * quad;
+    const bool has_res = a.epi.residual != nullptr, has_mask = a.epi.mask_src != nullptr;
+    const bool has_in = has_res || has_mask;
+    uint32_t ld_parity = 0;
     int it = 0;
     for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x, ++it) {
       int n, h0, w0;
@@ -175,6 +188,41 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       const int h = h0 + g, w = w0 + j;
       const bool valid = h < a.H && w < a.W;
       const long opix = ((long)n * a.H + h) * a.W + w;
+      if (a.fast) {
+        // this warp's 32 pixels = image rows h0+4*quad .. +3, 8 pixels each: a [1][4][8][64] TMA box
+        if (has_in) {
+          if (elect_one()) {
+            mbar_expect_tx(ld_bar, (has_res ? 4096u : 0u) + (has_mask ? 4096u : 0u));
+            if (has_res) tma_load_4d(stg_res, &tmRes, ld_bar, 0, w0, h0 + 4 * quad, n);
+            if (has_mask) tma_load_4d(stg_mask, &tmMask, ld_bar, 0, w0, h0 + 4 * quad, n);
+          }
+          __syncwarp();
+        }
+        mbar_wait(tfull_bar(acc), acc_phase);
+        tc_fence_after();
+        if (elect_one()) tma_store_wait_read<0>();      // previous tile's store has left stg_out
+        __syncwarp();
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+          uint32_t raw[32];
+          tmem_ld_32x32(tmem_base + acc * Cfg::BN + half * 32 + ((uint32_t)(quad * 32) << 16), raw);
+          tmem_ld_wait();
+          if (half == 0 && has_in) mbar_wait(ld_bar, ld_parity);
+          epilogue_half_staged(a.epi, raw, valid, half * 32, half, lane, stg_out, stg_res, stg_mask);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
+        fence_proxy_async();
+        __syncwarp();
+        if (elect_one()) {
+          tma_store_4d(&tmOut, stg_out, 0, w0, h0 + 4 * quad, n);
+          tma_store_commit();
+        }
+        __syncwarp();
+        if (has_in) ld_parity ^= 1;
+        continue;
+      }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
 #pragma unroll 1
@@ -187,6 +235,10 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
+    }
+    if (a.fast) {
+      if (elect_one()) tma_store_wait<0>();
+      __syncwarp();
     }
   }
 
@@ -220,7 +272,17 @@ static int launch_halo(const vdqn_conv_desc* d, cudaStream_t stream) {
   if (rc != VDQN_OK) return rc;
   rc = make_tiled_map_2d(&tmW, d->w, (uint64_t)d->R * d->S * d->Cin, d->Cout, CK, 64, CK == 64 ? 128 : 32);
   if (rc != VDQN_OK) return rc;
+  CUtensorMap tmOut = tmX, tmRes = tmX, tmMask = tmX;
+  const bool fast = fast_epilogue_ok(d) && d->ldc == d->Cout && (!d->residual || d->ldr == d->Cout) &&
+                    (!d->mask_src || d->ldm == d->Cout);
+  if (fast) {
+    rc = make_tiled_map_nhwc(&tmOut, d->out, d->N, d->H, d->W, d->Cout, 64, 8, 4, 128);
+    if (rc == VDQN_OK && d->residual) rc = make_tiled_map_nhwc(&tmRes, d->residual, d->N, d->H, d->W, d->Cout, 64, 8, 4, 128);
+    if (rc == VDQN_OK && d->mask_src) rc = make_tiled_map_nhwc(&tmMask, d->mask_src, d->N, d->H, d->W, d->Cout, 64, 8, 4, 128);
+    if (rc != VDQN_OK) return rc;
+  }
   HaloArgs a{};
+  a.fast = fast ? 1 : 0;
   a.N = d->N; a.H = d->H; a.W = d->W; a.Cout = d->Cout;
   a.R = d->R; a.S = d->S; a.pad_lo = d->pad_lo;
   a.tiles_w = (d->W + Cfg::TW - 1) / Cfg::TW;
@@ -229,7 +291,7 @@ static int launch_halo(const vdqn_conv_desc* d, cudaStream_t stream) {
   a.epi = make_epi_args(d);
   const int sms = d->max_ctas > 0 && d->max_ctas < dev->num_sms ? d->max_ctas : dev->num_sms;
   const int grid = a.num_tiles < sms ? a.num_tiles : sms;
-  kfn<<<grid, 192, Cfg::SMEM_BYTES, stream>>>(tmX, tmW, a);
+  kfn<<<grid, 192, Cfg::SMEM_BYTES, stream>>>(tmX, tmW, tmOut, tmRes, tmMask, a);
   VDQN_CHECK_LAUNCH("halo_conv launch");
   return VDQN_OK;
 }
