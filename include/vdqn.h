@@ -90,8 +90,9 @@ typedef struct vdqn_wgrad_desc {
   int32_t N, H, W, Cin, Cout, R, S;
   int32_t stride, dil, pad_lo, pad_hi;
   int32_t ldy;
-  int32_t splits;  /* number of pixel-range partitions (>=1) */
+  int32_t splits;  /* number of pixel-range partitions (>=1); algo 2: number of CTAs (<= SMs, <= tiles) */
   int32_t max_ctas;
+  int32_t algo;    /* 0/1 = im2col-TMA kernel; 2 = halo-tile kernel (64->64 3x3 stride 1 only) */
 } vdqn_wgrad_desc;
 int vdqn_conv_wgrad(const vdqn_wgrad_desc* d, void* stream);
 

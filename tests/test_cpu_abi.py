@@ -103,4 +103,4 @@ def test_plan_matches_survey_flop_count():
     macs += 1600 * 512 + 512 * 256 + 256 * 15
     assert macs == 1821888256
     for c in plan.convs:
-        assert 1 <= E.wgrad_splits(c, 256) <= 4096
+        assert 1 <= E.wgrad_splits(c, 256, sms=148) <= 4096

@@ -258,13 +258,13 @@ def stem_s2d():
     return ok
 
 
-def _wgrad_case(name, N, H, W, Cin, Cout, R, stride, pad, splits, seed=0):
+def _wgrad_case(name, N, H, W, Cin, Cout, R, stride, pad, splits, seed=0, algo=0):
     torch, F, ops = _imports()
     g = torch.Generator(device="cuda").manual_seed(seed)
     x = torch.randn(N, H, W, Cin, device="cuda", generator=g).to(torch.bfloat16)
     Ho, Wo = ops.conv_out_hw(H, W, R, R, stride, pad, pad)
     dy = torch.randn(N, Ho, Wo, Cout, device="cuda", generator=g).to(torch.bfloat16)
-    part = ops.conv_wgrad(x, dy, R, R, stride, pad, splits=splits)
+    part = ops.conv_wgrad(x, dy, R, R, stride, pad, splits=splits, algo=algo)
     torch.cuda.synchronize()
     got = part.sum(0).view(Cout, R, R, Cin)
     xr = x.float().permute(0, 3, 1, 2).requires_grad_(False)
@@ -298,6 +298,36 @@ def wgrad_3x3_layer1():
 @case
 def wgrad_3x3_s2():
     return _wgrad_case("wgrad_3x3_s2", 3, 28, 28, 64, 128, 3, 2, 1, 2)
+
+
+@case
+def wgrad_halo():
+    ok = _wgrad_case("wgrad_halo_56", 6, 56, 56, 64, 64, 3, 1, 1, 148, algo=2)
+    ok &= _wgrad_case("wgrad_halo_20x28", 3, 20, 28, 64, 64, 3, 1, 1, 7, algo=2)
+    ok &= _wgrad_case("wgrad_halo_1cta", 2, 13, 9, 64, 64, 3, 1, 1, 1, algo=2)
+    return ok
+
+
+@case
+def wgrad_halo_speed():
+    torch, F, ops = _imports()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.randn(256, 56, 56, 64, device="cuda", generator=g).to(torch.bfloat16)
+    dy = torch.randn(256, 56, 56, 64, device="cuda", generator=g).to(torch.bfloat16)
+    res = {}
+    for algo, splits in ((1, 98), (2, 148)):
+        part = torch.empty(splits, 64, 576, device="cuda")
+        for _ in range(3):
+            ops.conv_wgrad(x, dy, 3, 3, 1, 1, splits=splits, part=part, algo=algo)
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(10):
+            ops.conv_wgrad(x, dy, 3, 3, 1, 1, splits=splits, part=part, algo=algo)
+        e.record(); torch.cuda.synchronize()
+        res[f"algo{algo}_us"] = s.elapsed_time(e) * 100
+        res[f"sum{algo}"] = part.sum(0).abs().sum().item()
+    print(json.dumps(res))
+    return abs(res["sum1"] - res["sum2"]) < 1e-3 * res["sum1"]
 
 
 @case

@@ -26,7 +26,7 @@ class ConvDesc(C.Structure):
 class WgradDesc(C.Structure):
     _fields_ = [("x", c_void_p), ("dy", c_void_p), ("part", c_void_p)] + \
                [(n, c_int) for n in ("N", "H", "W", "Cin", "Cout", "R", "S", "stride", "dil",
-                                     "pad_lo", "pad_hi", "ldy", "splits", "max_ctas")]
+                                     "pad_lo", "pad_hi", "ldy", "splits", "max_ctas", "algo")]
 
 
 class WgradFinDesc(C.Structure):

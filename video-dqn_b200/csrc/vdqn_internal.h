@@ -37,6 +37,11 @@ int make_tiled_map_nhwc(CUtensorMap* map, const void* base, int N, int H, int W,
 bool halo_conv_supported(const vdqn_conv_desc* d);
 int halo_conv_launch(const vdqn_conv_desc* d, cudaStream_t stream);
 
+// halo_wgrad.cu: 64->64 3x3 weight gradient from one smem copy of the input window;
+// writes part[splits][64][576] with splits = number of CTAs launched
+bool halo_wgrad_supported(const vdqn_wgrad_desc* d);
+int halo_wgrad_launch(const vdqn_wgrad_desc* d, cudaStream_t stream);
+
 inline int ceil_div(long a, long b) { return (int)((a + b - 1) / b); }
 
 // every kernel launch of the library is counted (bench.py reports it as `gpu_launches`)

@@ -97,7 +97,16 @@ def make_plan(action_dim: int, num_classes: int = 5, num_frames: int = 1) -> Net
     return plan
 
 
-def wgrad_splits(spec: ConvSpec, n_img: int) -> int:
+def wgrad_uses_halo(spec: ConvSpec) -> bool:
+    """64->64 3x3 stride-1 convolutions (layer1) take the halo-tile weight-gradient kernel."""
+    return (spec.kmap == 0 and spec.cin == 64 and spec.cout == 64 and spec.k == 3 and spec.stride == 1
+            and spec.pad_lo == 1)
+
+
+def wgrad_splits(spec: ConvSpec, n_img: int, sms: int = 0) -> int:
+    if wgrad_uses_halo(spec):
+        tiles = n_img * ((spec.out_hw + 7) // 8) * ((spec.out_hw + 15) // 16)
+        return min(sms or ops.num_sms(), tiles)    # = number of persistent CTAs
     M = n_img * spec.out_hw * spec.out_hw
     co_tiles = (spec.cout + 127) // 128
     per = 4 if spec.gemm_cin % 64 == 0 else 16
@@ -207,7 +216,8 @@ def forward(plan: NetPlan, W: PreparedWeights, P: Dict[str, torch.Tensor], ws: W
 def _wgrad(plan, P, G, ws: Workspace, c: ConvSpec, x, dy, dbeta_key: Optional[str]):
     splits = wgrad_splits(c, ws.n)
     part = ws.part[: splits * c.cout * c.K]
-    ops.conv_wgrad(x, dy, c.k, c.k, c.stride, c.pad_lo, c.pad_hi, splits=splits, part=part)
+    ops.conv_wgrad(x, dy, c.k, c.k, c.stride, c.pad_lo, c.pad_hi, splits=splits, part=part,
+                   algo=2 if wgrad_uses_halo(c) else 0)
     kw = {}
     if c.bn is not None:
         kw = dict(gamma=P[c.bn + ".weight"], var=P[c.bn + ".running_var"], mean=P[c.bn + ".running_mean"],

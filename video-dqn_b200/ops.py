@@ -47,6 +47,19 @@ def _cuda(t, dtype, name):
     return t
 
 
+_NUM_SMS = None
+
+
+def num_sms() -> int:
+    global _NUM_SMS
+    if _NUM_SMS is None:
+        n = L.load().vdqn_num_sms()
+        if n <= 0:
+            L.check(-3, "num_sms")
+        _NUM_SMS = n
+    return _NUM_SMS
+
+
 def conv_out_hw(H, W, R, S, stride, pad_lo, pad_hi, dil=1):
     return ((H + pad_lo + pad_hi - (R - 1) * dil - 1) // stride + 1,
             (W + pad_lo + pad_hi - (S - 1) * dil - 1) // stride + 1)
@@ -97,7 +110,8 @@ def conv_gemm(x, w, stride=1, pad_lo=0, pad_hi=None, *, shift=None, residual=Non
     return out
 
 
-def conv_wgrad(x, dy, R, S, stride=1, pad_lo=0, pad_hi=None, *, splits=1, part=None, max_ctas=0, dil=1):
+def conv_wgrad(x, dy, R, S, stride=1, pad_lo=0, pad_hi=None, *, splits=1, part=None, max_ctas=0, dil=1,
+               algo=0):
     """x [N,H,W,Cin] bf16, dy [N,Ho,Wo,Cout] bf16 -> part [splits,Cout,R*S*Cin] fp32."""
     lib = L.load()
     _cuda(x, bf16, "x"); _cuda(dy, bf16, "dy")
@@ -114,7 +128,7 @@ def conv_wgrad(x, dy, R, S, stride=1, pad_lo=0, pad_hi=None, *, splits=1, part=N
     d.x, d.dy, d.part = x.data_ptr(), dy.data_ptr(), part.data_ptr()
     d.N, d.H, d.W, d.Cin, d.Cout, d.R, d.S = N, H, W_, Cin, Cout, R, S
     d.stride, d.dil, d.pad_lo, d.pad_hi = stride, dil, pad_lo, pad_hi
-    d.ldy, d.splits, d.max_ctas = Cout, splits, max_ctas
+    d.ldy, d.splits, d.max_ctas, d.algo = Cout, splits, max_ctas, algo
     with _Prof("wgrad", (N, H, W_, Cin, Cout, R, stride)):
         L.check(lib.vdqn_conv_wgrad(C.byref(d), L.stream_ptr()), "conv_wgrad")
     return part
