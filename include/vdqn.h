@@ -145,9 +145,10 @@ int vdqn_stem_pack_f32(const float* x_nchw, void* out, int32_t N, int32_t H, int
 int vdqn_stem_pack_u8(const uint8_t* x_nhwc, void* out, int32_t N, int32_t H, int32_t W, void* stream);
 
 /* max_pool2d(3, 2, 1) on NHWC bf16 (torchvision resnet.maxpool); idx (uint8 window slot 0..8)
- * may be NULL for inference.  Backward scatters dy to the arg-max and applies the stem ReLU mask. */
+ * may be NULL for inference.  Backward scatters dy to the arg-max and applies the stem ReLU mask,
+ * taken from the pooled output y (window max > 0); dx is [N][H][W][C]. */
 int vdqn_maxpool_fwd(const void* x, void* y, uint8_t* idx, int32_t N, int32_t H, int32_t W, int32_t C, void* stream);
-int vdqn_maxpool_bwd(const void* dy, const uint8_t* idx, const void* x, void* dx, float* colsum,
+int vdqn_maxpool_bwd(const void* dy, const uint8_t* idx, const void* y, void* dx, float* colsum,
                      int32_t N, int32_t H, int32_t W, int32_t C, void* stream);
 
 /* ---------------------------------------------------------------------------------------

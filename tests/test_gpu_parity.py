@@ -147,7 +147,7 @@ def test_fused_learner_three_steps_match_oracle():
         assert abs(lv - loss_ref.item()) <= tol * abs(loss_ref.item()), (it, lv, loss_ref.item())
         if it == 0:
             assert abs(lv - float(g["step0/loss"])) <= LOSS_RTOL * float(g["step0/loss"])
-            assert (lr.ws_train.q.view(8, 5, 3).cpu().numpy() - g["step0/q_s"]).__abs__().max() <= Q_TOL
+            assert (lr.ws_train.q[:8].view(8, 5, 3).cpu().numpy() - g["step0/q_s"]).__abs__().max() <= Q_TOL
         rel, worst = _check_grads(lr.G, grads_ref, names)
         print(f"fused step {it}: loss {lv:.6f} oracle {loss_ref.item():.6f} grad rel-L2 {rel:.4f} worst {worst}")
         # every element moved by at most lr * (1/(1-b1^t)) ... <= ~1.0001 * 1e-4 per Adam step

@@ -404,7 +404,7 @@ def maxpool():
     ok = _report("maxpool_fwd", y, yr.permute(0, 2, 3, 1), 1e-6)
     dy = torch.randn(N, 56, 56, Cc, device="cuda", generator=g).to(torch.bfloat16)
     cs = torch.zeros(Cc, device="cuda")
-    dx = ops.maxpool_bwd(dy, idx, x, colsum=cs)
+    dx = ops.maxpool_bwd(dy, idx, y, colsum=cs)
     torch.cuda.synchronize()
     yr.backward(dy.float().permute(0, 3, 1, 2))
     ref = (xr.grad * (xr > 0)).permute(0, 2, 3, 1)

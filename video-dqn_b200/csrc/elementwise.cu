@@ -197,10 +197,12 @@ __global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfl
   }
 }
 
-// backward: one thread = 8 channels of one INPUT pixel; gathers from the <=4 windows covering it,
-// applies the ReLU mask of the saved stem output x, accumulates per-channel sums (d beta of bn1).
+// backward: one thread = 8 channels of one INPUT pixel; gathers from the <=4 windows covering it.
+// The stem ReLU mask is taken from the POOLED output y (the arg-max element is > 0 exactly when the
+// window maximum is), so the 4x larger pre-pool activation is not re-read.  Accumulates per-channel
+// sums (d beta of bn1).
 __global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ idx,
-                                   const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ dx,
+                                   const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ dx,
                                    float* __restrict__ colsum, int N, int H, int W, int C) {
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1, CG = C / 8;
   const long total = (long)N * H * W * CG;
@@ -231,7 +233,12 @@ __global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const u
         const uint32_t m_lo = __vcmpeq4(ip.x, want4), m_hi = __vcmpeq4(ip.y, want4);   // 0xFF per match
         const uint32_t m[4] = {__byte_perm(m_lo, 0, 0x1100), __byte_perm(m_lo, 0, 0x3322),
                                __byte_perm(m_hi, 0, 0x1100), __byte_perm(m_hi, 0, 0x3322)};
-        const uint32_t v[4] = {raw.x & m[0], raw.y & m[1], raw.z & m[2], raw.w & m[3]};
+        const uint4 yr = __ldg(reinterpret_cast<const uint4*>(y + o));
+        const uint32_t yv[4] = {yr.x, yr.y, yr.z, yr.w};
+        const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
+        uint32_t v[4] = {raw.x & m[0], raw.y & m[1], raw.z & m[2], raw.w & m[3]};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] &= __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&yv[e]), zero2);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const __nv_bfloat162 sum = __hadd2(*reinterpret_cast<const __nv_bfloat162*>(&g2[e]),
@@ -240,15 +247,11 @@ __global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const u
         }
       }
     }
-    const uint4 xr = __ldg(reinterpret_cast<const uint4*>(x + i * 8));
-    const uint32_t xv[4] = {xr.x, xr.y, xr.z, xr.w};
-    const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
     uint4 pk;
     uint32_t* ov = reinterpret_cast<uint32_t*>(&pk);
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const uint32_t keep = __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&xv[e]), zero2);
-      ov[e] = g2[e] & keep;
+      ov[e] = g2[e];
       const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ov[e]));
       acc[2 * e] += f.x;
       acc[2 * e + 1] += f.y;
@@ -565,16 +568,16 @@ extern "C" int vdqn_maxpool_fwd(const void* x, void* y, uint8_t* idx, int32_t N,
   return VDQN_OK;
 }
 
-extern "C" int vdqn_maxpool_bwd(const void* dy, const uint8_t* idx, const void* x, void* dx, float* colsum,
+extern "C" int vdqn_maxpool_bwd(const void* dy, const uint8_t* idx, const void* y, void* dx, float* colsum,
                                 int32_t N, int32_t H, int32_t W, int32_t C, void* stream_v) {
-  if (dy == nullptr || idx == nullptr || x == nullptr || dx == nullptr)
+  if (dy == nullptr || idx == nullptr || y == nullptr || dx == nullptr)
     return set_error(VDQN_ERR_ARG, "maxpool_bwd: null pointer");
   if (C % 8 || 256 % (C / 8) || C > 256) return set_error(VDQN_ERR_SHAPE, "maxpool_bwd: unsupported C=%d", C);
   GET_DEV();
   const long total = (long)N * H * W * (C / 8);
   if (total == 0) return VDQN_OK;
   maxpool_bwd_kernel<<<grid_for(total, 256, dev->num_sms, 8), 256, 256 * 8 * sizeof(float), stream>>>(
-      static_cast<const __nv_bfloat16*>(dy), idx, static_cast<const __nv_bfloat16*>(x),
+      static_cast<const __nv_bfloat16*>(dy), idx, static_cast<const __nv_bfloat16*>(y),
       static_cast<__nv_bfloat16*>(dx), colsum, N, H, W, C);
   VDQN_CHECK_LAUNCH("maxpool_bwd");
   return VDQN_OK;

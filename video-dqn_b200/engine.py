@@ -146,27 +146,36 @@ class Workspace:
     """All activation / gradient buffers for one forward (and optionally its backward) at a
     fixed number of frames `n` (= B * num_frames)."""
 
-    def __init__(self, plan: NetPlan, n: int, device, train: bool):
+    def __init__(self, plan: NetPlan, n: int, device, train: bool, n_bwd: Optional[int] = None):
+        """`n` frames go through the forward; the backward (if `train`) covers the first `n_bwd`
+        (default all) -- the fused step runs the online net on [s ; s'] in one 2B forward and
+        back-propagates through the s half only."""
         self.n, self.train = n, train
+        self.n_bwd = n if n_bwd is None else n_bwd
+        self._view = None
+        nf, n = n, self.n_bwd
         e = lambda *s, dt=bf16: torch.empty(*s, device=device, dtype=dt)  # noqa: E731
         z = lambda *s, dt=bf16: torch.zeros(*s, device=device, dtype=dt)  # noqa: E731
-        self.xp = e(n, 112, 112, 16)
-        self.s = e(n, 112, 112, 64)
-        self.idx = e(n, 56, 56, 64, dt=torch.uint8) if train else None
-        self.p = e(n, 56, 56, 64)
+        self.xp = e(nf, 112, 112, 16)
+        self.s = e(nf, 112, 112, 64)
+        self.idx = e(nf, 56, 56, 64, dt=torch.uint8) if train else None
+        self.p = e(nf, 56, 56, 64)
         self.a1, self.idn, self.out = [], [], []
         for b in plan.blocks:
-            self.a1.append(e(n, b.out_hw, b.out_hw, b.cout))
-            self.idn.append(e(n, b.out_hw, b.out_hw, b.cout) if b.ds is not None else None)
-            self.out.append(e(n, b.out_hw, b.out_hw, b.cout))
-        self.h = e(n, 5, 5, 64)
-        B = n // plan.num_frames
+            self.a1.append(e(nf, b.out_hw, b.out_hw, b.cout))
+            self.idn.append(e(nf, b.out_hw, b.out_hw, b.cout) if b.ds is not None else None)
+            self.out.append(e(nf, b.out_hw, b.out_hw, b.cout))
+        self.h = e(nf, 5, 5, 64)
         F = plan.num_frames
+        Bf, B = nf // F, n // F
         f32 = torch.float32
-        self.flat = e(B, 1600 * F, dt=f32)
-        self.z1 = e(B, 512, dt=f32)
-        self.z2 = e(B, 256, dt=f32)
-        self.q = e(B, plan.num_classes * plan.action_dim, dt=f32)
+        self.flat = e(Bf, 1600 * F, dt=f32)
+        self.z1 = e(Bf, 512, dt=f32)
+        self.z2 = e(Bf, 256, dt=f32)
+        self.q = e(Bf, plan.num_classes * plan.action_dim, dt=f32)
+        self._fwd_names = ("xp", "s", "idx", "p", "h")
+        self._mlp_names = ("flat", "z1", "z2", "q")
+        self._F = F
         if train:
             self.dz2 = e(B, 256, dt=f32)
             self.dz1 = e(B, 512, dt=f32)
@@ -183,6 +192,26 @@ class Workspace:
             self.dy_s = e(n, 112, 112, 64)
             max_part = max(wgrad_splits(c, n) * c.cout * c.K for c in plan.convs)
             self.part = e(max_part, dt=f32)
+
+    def bwd_view(self):
+        """The workspace as the backward pass sees it: activations sliced to the first n_bwd frames."""
+        if self.n_bwd == self.n:
+            return self
+        if self._view is None:
+            import copy
+            v = copy.copy(self)
+            nb, Bb = self.n_bwd, self.n_bwd // self._F
+            for nm in self._fwd_names:
+                t = getattr(self, nm)
+                setattr(v, nm, None if t is None else t[:nb])
+            for nm in self._mlp_names:
+                setattr(v, nm, getattr(self, nm)[:Bb])
+            v.a1 = [t[:nb] for t in self.a1]
+            v.out = [t[:nb] for t in self.out]
+            v.idn = [None if t is None else t[:nb] for t in self.idn]
+            v.n = nb
+            self._view = v
+        return self._view
 
 
 def _conv(W: PreparedWeights, c: ConvSpec, x, out, **kw):
@@ -233,6 +262,7 @@ def backward(plan: NetPlan, W: PreparedWeights, P: Dict[str, torch.Tensor], G: D
     with atomics).  `on_grads_ready(stage)` is called after each stage's gradients are enqueued
     (used by the data-parallel wrapper to launch bucketed all-reduces)."""
     notify = on_grads_ready or (lambda stage: None)
+    ws = ws.bwd_view()
     # ---- MLP (fp32)
     ops.linear_bwd(ws.z2, P["top.4.weight"], None, dq, G["top.4.weight"], G["top.4.bias"], False, dx=ws.dz2)
     ops.linear_bwd(ws.z1, P["top.2.weight"], ws.z2, ws.dz2, G["top.2.weight"], G["top.2.bias"], True, dx=ws.dz1)
@@ -285,6 +315,6 @@ def backward(plan: NetPlan, W: PreparedWeights, P: Dict[str, torch.Tensor], G: D
         notify(b.conv1.name)
         cur, ci = dst, ni
     # ---- max-pool + stem
-    ops.maxpool_bwd(ws.dy_p, ws.idx, ws.s, ws.dy_s, colsum=G[plan.stem.bn + ".bias"])
+    ops.maxpool_bwd(ws.dy_p, ws.idx, ws.p, ws.dy_s, colsum=G[plan.stem.bn + ".bias"])
     _wgrad(plan, P, G, ws, plan.stem, ws.xp, ws.dy_s, None)
     notify("stem")

@@ -83,23 +83,25 @@ class QLearner:
         self.scalars_dev = torch.zeros(2, device=dev, dtype=torch.float32)
         # ---- static inputs
         n = batch_size * F
+        # `before` and `after` are the two halves of one [2B, ...] buffer: the online network runs on
+        # both in a single 2B forward (bit-identical to two B forwards: eval-mode BN has no batch
+        # statistics)
         if frames_uint8:
-            shp = (batch_size, F, 224, 224, 3) if F > 1 else (batch_size, 224, 224, 3)
-            self.before = torch.zeros(shp, device=dev, dtype=torch.uint8)
+            shp = (2 * batch_size, F, 224, 224, 3) if F > 1 else (2 * batch_size, 224, 224, 3)
+            self.frames2 = torch.zeros(shp, device=dev, dtype=torch.uint8)
         else:
-            shp = (batch_size, F, 3, 224, 224) if F > 1 else (batch_size, 3, 224, 224)
-            self.before = torch.zeros(shp, device=dev, dtype=torch.float32)
-        self.after = torch.zeros_like(self.before)
+            shp = (2 * batch_size, F, 3, 224, 224) if F > 1 else (2 * batch_size, 3, 224, 224)
+            self.frames2 = torch.zeros(shp, device=dev, dtype=torch.float32)
+        self.before, self.after = self.frames2[:batch_size], self.frames2[batch_size:]
         C = self.plan.num_classes
         self.act = torch.zeros(batch_size, device=dev, dtype=torch.int64)
         self.rew = torch.zeros(batch_size, C, device=dev, dtype=torch.int64)
         self.term = torch.zeros(batch_size, C, device=dev, dtype=torch.int64)
         self.valid = torch.ones(batch_size, C, device=dev, dtype=torch.int64)
         # ---- workspaces and step outputs
-        self.ws_train = E.Workspace(self.plan, n, dev, train=True)
+        self.ws_train = E.Workspace(self.plan, 2 * n, dev, train=True, n_bwd=n)
         self.ws_eval = E.Workspace(self.plan, n, dev, train=False)
         A = self.plan.action_dim
-        self.q_next_online = torch.empty(batch_size, C * A, device=dev, dtype=torch.float32)
         self.dq = torch.empty(batch_size, C * A, device=dev, dtype=torch.float32)
         self.loss = torch.zeros(1, device=dev, dtype=torch.float32)
         self.best = torch.empty(batch_size, C, device=dev, dtype=torch.int64)
@@ -111,8 +113,7 @@ class QLearner:
 
     # ------------------------------------------------------------------ the step body
     def _frames(self, t):
-        F = self.plan.num_frames
-        return t.view(self.B * F, *t.shape[-3:])
+        return t.view(-1, *t.shape[-3:])
 
     def _enqueue(self, sync_target: bool):
         cfg, plan = self.cfg, self.plan
@@ -120,13 +121,12 @@ class QLearner:
         C, A = plan.num_classes, plan.action_dim
         self.opt.grad_arena.zero_()
         self.loss.zero_()
-        # online net on s' and target net on s' (no activations kept), online net on s (kept)
-        E.forward(plan, st.W, st.P, self.ws_eval, self._frames(self.after))
-        self.q_next_online.copy_(self.ws_eval.q)
+        # online net on [s ; s'] in one 2B forward (activations of the s half feed the backward),
+        # target net on s' (nothing kept)
+        E.forward(plan, st.W, st.P, self.ws_train, self._frames(self.frames2))
         E.forward(plan, tt.W, tt.P, self.ws_eval, self._frames(self.after))
-        E.forward(plan, st.W, st.P, self.ws_train, self._frames(self.before))
         B = self.B
-        ops.td_epilogue(self.ws_train.q.view(B, C, A), self.q_next_online.view(B, C, A),
+        ops.td_epilogue(self.ws_train.q[:B].view(B, C, A), self.ws_train.q[B:].view(B, C, A),
                         self.ws_eval.q.view(B, C, A), self.act, self.rew, self.term, self.valid,
                         gamma=cfg.GAMMA, double_dqn=cfg.double_dqn, clip_rect=(cfg.LOSS_CLIP == "rect"),
                         linear=cfg.LINEAR, use_valid=cfg.REMOVE_BEFORE_REWARD,

@@ -195,13 +195,15 @@ def maxpool_fwd(x, y=None, idx=None, save_idx=False):
     return y, idx
 
 
-def maxpool_bwd(dy, idx, x, dx=None, colsum=None):
+def maxpool_bwd(dy, idx, y, dx=None, colsum=None):
+    """dy, idx, y: pooled-resolution [N,Ho,Wo,C]; dx: [N,2Ho,2Wo,C] (masked by the stem ReLU via y > 0)."""
     lib = L.load()
-    _cuda(dy, bf16, "dy"); _cuda(x, bf16, "x"); _cuda(idx, torch.uint8, "idx")
-    N, H, W_, Cc = x.shape
+    _cuda(dy, bf16, "dy"); _cuda(y, bf16, "y"); _cuda(idx, torch.uint8, "idx")
+    N, Ho, Wo, Cc = y.shape
+    H, W_ = 2 * Ho, 2 * Wo
     if dx is None:
-        dx = torch.empty_like(x)
-    L.check(lib.vdqn_maxpool_bwd(dy.data_ptr(), idx.data_ptr(), x.data_ptr(), dx.data_ptr(),
+        dx = torch.empty(N, H, W_, Cc, device=y.device, dtype=bf16)
+    L.check(lib.vdqn_maxpool_bwd(dy.data_ptr(), idx.data_ptr(), y.data_ptr(), dx.data_ptr(),
                                  L.ptr(colsum), N, H, W_, Cc, L.stream_ptr()), "maxpool_bwd")
     return dx
 
