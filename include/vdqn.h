@@ -136,6 +136,10 @@ typedef struct vdqn_wprep_desc {
   float eps;
 } vdqn_wprep_desc;
 int vdqn_weight_prep(const vdqn_wprep_desc* d, void* stream);
+/* Same for `n` tensors in one launch: `descs_dev` / `offsets_dev` are DEVICE arrays (offsets[t] = sum of
+ * Cout*K of tensors before t; total = sum over all). */
+int vdqn_weight_prep_multi(const vdqn_wprep_desc* descs_dev, const int64_t* offsets_dev, int32_t n,
+                           int64_t total, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Input staging: NCHW fp32 (dataloaders/q_learning_real.py:75-76 output) or uint8 HWC

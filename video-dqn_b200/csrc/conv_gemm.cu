@@ -185,9 +185,23 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const bool has_res = a.epi.residual != nullptr, has_mask = a.epi.mask_src != nullptr;
     const bool has_in = has_res || has_mask;
     uint32_t ld_parity = 0;
+    float csum[BN / 32];                 // per-lane column sums of the current column tile
+#pragma unroll
+    for (int i = 0; i < BN / 32; ++i) csum[i] = 0.f;
+    int cs_nt = -1;
+    auto flush_colsum = [&]() {
+      if (a.epi.colsum != nullptr && cs_nt >= 0) {
+#pragma unroll
+        for (int i = 0; i < BN / 32; ++i) {
+          atomicAdd(a.epi.colsum + cs_nt * BN + i * 32 + lane, csum[i]);
+          csum[i] = 0.f;
+        }
+      }
+    };
     int it = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
       const int n_t = t % a.num_n_tiles, m_t = t / a.num_n_tiles;
+      if (n_t != cs_nt) { flush_colsum(); cs_nt = n_t; }
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int m = m_t * Cfg::BM + row;
@@ -217,8 +231,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           tmem_ld_wait();
           if (chunk == 0 && has_in) mbar_wait(ld_bar, ld_parity);
           const int gidx = chunk >> 1;
-          epilogue_half_staged(a.epi, raw, valid, n_t * BN + chunk * 32, chunk & 1, lane, stg + gidx * 4096,
-                               stg + (Cfg::GROUPS + gidx) * 4096, stg + (2 * Cfg::GROUPS + gidx) * 4096);
+          const float cs = epilogue_half_staged(a.epi, raw, valid, n_t * BN + chunk * 32, chunk & 1, lane,
+                                                stg + gidx * 4096, stg + (Cfg::GROUPS + gidx) * 4096,
+                                                stg + (2 * Cfg::GROUPS + gidx) * 4096);
+#pragma unroll
+          for (int i = 0; i < BN / 32; ++i)
+            if (i == chunk) csum[i] += cs;
         }
         tc_fence_before();
         __syncwarp();
@@ -252,12 +270,16 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         uint32_t raw[32];
         tmem_ld_32x32(tmem_base + acc * BN + chunk * 32 + ((uint32_t)(quad * 32) << 16), raw);
         tmem_ld_wait();
-        epilogue_chunk(a.epi, raw, valid, (long)m, opix, opix2, n_t * BN + chunk * 32, lane);
+        const float cs = epilogue_chunk(a.epi, raw, valid, (long)m, opix, opix2, n_t * BN + chunk * 32, lane);
+#pragma unroll
+        for (int i = 0; i < BN / 32; ++i)
+          if (i == chunk) csum[i] += cs;
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
     }
+    flush_colsum();
     if (Cfg::FAST_EPI && a.fast) {
       if (elect_one()) tma_store_wait<0>();
       __syncwarp();

@@ -31,29 +31,43 @@ __device__ __forceinline__ int oihw_index(int co, int k, int Cin, int R, int S, 
   return ((co * 3 + c) * 7 + r) * 7 + s;
 }
 
+__device__ __forceinline__ void weight_prep_element(const vdqn_wprep_desc& d, long i) {
+  const int co = (int)(i / d.K), k = (int)(i - (long)co * d.K);
+  float scale = 1.f;
+  if (d.gamma != nullptr) scale = d.gamma[co] * (1.0f / sqrtf(d.var[co] + d.eps));
+  int r = 0, s = 0, ci = 0;
+  const int src = oihw_index(co, k, d.Cin, d.R, d.S, d.kmap, &r, &s, &ci);
+  const float v = src >= 0 ? d.w[src] * scale : 0.f;
+  const __nv_bfloat16 b = __float2bfloat16_rn(v);
+  static_cast<__nv_bfloat16*>(d.w_fwd)[i] = b;
+  if (d.w_dgrad != nullptr && d.kmap == 0) {
+    const long di = (long)ci * (d.R * d.S * d.Cout) + (long)((d.R - 1 - r) * d.S + (d.S - 1 - s)) * d.Cout + co;
+    static_cast<__nv_bfloat16*>(d.w_dgrad)[di] = b;
+  }
+  if (k == 0) {
+    float sh = 0.f;
+    if (d.gamma != nullptr) sh = d.beta[co] - d.mean[co] * scale;
+    if (d.bias != nullptr) sh += d.bias[co];
+    d.shift[co] = sh;
+  }
+}
+
 __global__ void weight_prep_kernel(const vdqn_wprep_desc d) {
   const long total = (long)d.Cout * d.K;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total;
-       i += (long)gridDim.x * blockDim.x) {
-    const int co = (int)(i / d.K), k = (int)(i - (long)co * d.K);
-    float scale = 1.f;
-    if (d.gamma != nullptr) scale = d.gamma[co] * (1.0f / sqrtf(d.var[co] + d.eps));
-    int r = 0, s = 0, ci = 0;
-    const int src = oihw_index(co, k, d.Cin, d.R, d.S, d.kmap, &r, &s, &ci);
-    const float v = src >= 0 ? d.w[src] * scale : 0.f;
-    const __nv_bfloat16 b = __float2bfloat16_rn(v);
-    static_cast<__nv_bfloat16*>(d.w_fwd)[i] = b;
-    if (d.w_dgrad != nullptr && d.kmap == 0) {
-      const long di = (long)ci * (d.R * d.S * d.Cout) +
-                      (long)((d.R - 1 - r) * d.S + (d.S - 1 - s)) * d.Cout + co;
-      static_cast<__nv_bfloat16*>(d.w_dgrad)[di] = b;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x)
+    weight_prep_element(d, i);
+}
+
+// all convolutions of the network in one launch: `offsets[t]` = first flat element of tensor t
+__global__ void weight_prep_multi_kernel(const vdqn_wprep_desc* __restrict__ descs,
+                                         const long long* __restrict__ offsets, int n, long total) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    int lo = 0, hi = n - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (offsets[mid] <= i) lo = mid; else hi = mid - 1;
     }
-    if (k == 0) {
-      float sh = 0.f;
-      if (d.gamma != nullptr) sh = d.beta[co] - d.mean[co] * scale;
-      if (d.bias != nullptr) sh += d.bias[co];
-      d.shift[co] = sh;
-    }
+    weight_prep_element(descs[lo], i - offsets[lo]);
   }
 }
 
@@ -513,6 +527,18 @@ extern "C" int vdqn_weight_prep(const vdqn_wprep_desc* d, void* stream_v) {
   const long total = (long)d->Cout * d->K;
   weight_prep_kernel<<<grid_for(total, 256, dev->num_sms), 256, 0, stream>>>(*d);
   VDQN_CHECK_LAUNCH("weight_prep");
+  return VDQN_OK;
+}
+
+extern "C" int vdqn_weight_prep_multi(const vdqn_wprep_desc* descs_dev, const int64_t* offsets_dev, int32_t n,
+                                      int64_t total, void* stream_v) {
+  if (descs_dev == nullptr || offsets_dev == nullptr || n < 1)
+    return set_error(VDQN_ERR_ARG, "weight_prep_multi: bad arguments");
+  GET_DEV();
+  if (total == 0) return VDQN_OK;
+  weight_prep_multi_kernel<<<grid_for(total, 256, dev->num_sms, 16), 256, 0, stream>>>(
+      descs_dev, reinterpret_cast<const long long*>(offsets_dev), n, total);
+  VDQN_CHECK_LAUNCH("weight_prep_multi");
   return VDQN_OK;
 }
 

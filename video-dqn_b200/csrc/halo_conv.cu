@@ -179,6 +179,7 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     const bool has_res = a.epi.residual != nullptr, has_mask = a.epi.mask_src != nullptr;
     const bool has_in = has_res || has_mask;
     uint32_t ld_parity = 0;
+    float csum[2] = {0.f, 0.f};          // per-lane column sums (channels lane, 32 + lane) over all tiles
     int it = 0;
     for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x, ++it) {
       int n, h0, w0;
@@ -208,7 +209,8 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           tmem_ld_32x32(tmem_base + acc * Cfg::BN + half * 32 + ((uint32_t)(quad * 32) << 16), raw);
           tmem_ld_wait();
           if (half == 0 && has_in) mbar_wait(ld_bar, ld_parity);
-          epilogue_half_staged(a.epi, raw, valid, half * 32, half, lane, stg_out, stg_res, stg_mask);
+          const float cs = epilogue_half_staged(a.epi, raw, valid, half * 32, half, lane, stg_out, stg_res, stg_mask);
+          if (half == 0) csum[0] += cs; else csum[1] += cs;
         }
         tc_fence_before();
         __syncwarp();
@@ -230,11 +232,16 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         uint32_t raw[32];
         tmem_ld_32x32(tmem_base + acc * Cfg::BN + chunk * 32 + ((uint32_t)(quad * 32) << 16), raw);
         tmem_ld_wait();
-        epilogue_chunk(a.epi, raw, valid, opix, opix, 0, chunk * 32, lane);
+        const float cs = epilogue_chunk(a.epi, raw, valid, opix, opix, 0, chunk * 32, lane);
+        if (chunk == 0) csum[0] += cs; else csum[1] += cs;
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
+    }
+    if (a.epi.colsum != nullptr) {
+      atomicAdd(a.epi.colsum + lane, csum[0]);
+      atomicAdd(a.epi.colsum + 32 + lane, csum[1]);
     }
     if (a.fast) {
       if (elect_one()) tma_store_wait<0>();

@@ -131,15 +131,36 @@ class PreparedWeights:
             self.shift[c.name] = torch.empty(c.cout, device=device, dtype=torch.float32)
 
     def prepare(self, P: Dict[str, torch.Tensor]):
-        for c in self.plan.convs:
-            kw = {}
-            if c.bn is not None:
-                kw = dict(gamma=P[c.bn + ".weight"], beta=P[c.bn + ".bias"],
-                          mean=P[c.bn + ".running_mean"], var=P[c.bn + ".running_var"])
-            if c.bias is not None:
-                kw["bias"] = P[c.bias]
-            ops.weight_prep(P[c.wkey], self.w_fwd[c.name], self.shift[c.name],
-                            w_dgrad=self.w_dgrad.get(c.name), kmap=c.kmap, eps=BN_EPS, **kw)
+        """Re-derive every bf16 operand from the fp32 masters in ONE launch.  The descriptor table
+        lives on the device and is rebuilt only when a parameter's storage moved."""
+        import ctypes as C
+        from . import _lib as L
+        sig = tuple(P[c.wkey].data_ptr() for c in self.plan.convs) + \
+            tuple(P[c.bn + ".weight"].data_ptr() for c in self.plan.convs if c.bn)
+        if getattr(self, "_table_sig", None) != sig:
+            descs = (L.WprepDesc * len(self.plan.convs))()
+            offs, total = [], 0
+            for d, c in zip(descs, self.plan.convs):
+                w = P[c.wkey]
+                d.w, d.w_fwd, d.shift = w.data_ptr(), self.w_fwd[c.name].data_ptr(), self.shift[c.name].data_ptr()
+                d.w_dgrad = L.ptr(self.w_dgrad.get(c.name))
+                if c.bn is not None:
+                    d.gamma, d.beta = P[c.bn + ".weight"].data_ptr(), P[c.bn + ".bias"].data_ptr()
+                    d.mean, d.var = P[c.bn + ".running_mean"].data_ptr(), P[c.bn + ".running_var"].data_ptr()
+                if c.bias is not None:
+                    d.bias = P[c.bias].data_ptr()
+                d.Cout, d.Cin, d.R, d.S = w.shape
+                d.K, d.kmap, d.eps = c.K, c.kmap, BN_EPS
+                offs.append(total)
+                total += c.cout * c.K
+            dev = self.shift["stem"].device
+            raw = torch.frombuffer(bytearray(bytes(descs)), dtype=torch.uint8).clone()
+            self._table = raw.to(dev)
+            self._offsets = torch.tensor(offs, dtype=torch.int64, device=dev)
+            self._total, self._table_sig = total, sig
+        L.check(L.load().vdqn_weight_prep_multi(self._table.data_ptr(), self._offsets.data_ptr(),
+                                                len(self.plan.convs), self._total, L.stream_ptr()),
+                "weight_prep_multi")
 
 
 class Workspace:
