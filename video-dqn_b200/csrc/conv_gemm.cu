@@ -42,7 +42,9 @@ struct IgemmCfg {
   // BN = 256 keeps the direct epilogue (its long K loops hide it) and all its smem for the pipeline
   static constexpr bool FAST_EPI = BN <= 128;
   static constexpr int GROUPS = BN / 64;
-  static constexpr int EPI_WARP_BYTES = FAST_EPI ? GROUPS * 3 * 4096 : 0;
+  // BN = 64: the out tile is double-buffered so a tile never waits for the previous tile's TMA store
+  static constexpr int OUT_BUFS = (GROUPS == 1) ? 2 : 1;
+  static constexpr int EPI_WARP_BYTES = FAST_EPI ? (GROUPS * (2 + OUT_BUFS)) * 4096 : 0;
   static constexpr int EPI_BYTES = 4 * EPI_WARP_BYTES;
   static constexpr int PIPE_BUDGET = 224 * 1024 - EPI_BYTES;
   static constexpr int STAGES = PIPE_BUDGET / STAGE_BYTES > 8 ? 8 : PIPE_BUDGET / STAGE_BYTES;
@@ -180,7 +182,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     // ------------------------------------------------------------ epilogue (warps 2..5)
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may touch
     const int row = quad * 32 + lane;
-    const uint32_t stg = epi_base + quad * Cfg::EPI_WARP_BYTES;     // [GROUPS] out | res | mask tiles
+    // per-warp staging: res[GROUPS] | mask[GROUPS] | out[OUT_BUFS][GROUPS]
+    const uint32_t stg_in = epi_base + quad * Cfg::EPI_WARP_BYTES;
+    const uint32_t stg_out_base = stg_in + 2 * Cfg::GROUPS * 4096;
     const uint32_t ld_bar = ld_bar0 + 8u * quad;
     const bool has_res = a.epi.residual != nullptr, has_mask = a.epi.mask_src != nullptr;
     const bool has_in = has_res || has_mask;
@@ -214,15 +218,16 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
             for (int gidx = 0; gidx < Cfg::GROUPS; ++gidx) {
               const int col = n_t * BN + gidx * 64;
-              if (has_res) tma_load_2d(stg + (Cfg::GROUPS + gidx) * 4096, &tmRes, ld_bar, col, row0);
-              if (has_mask) tma_load_2d(stg + (2 * Cfg::GROUPS + gidx) * 4096, &tmMask, ld_bar, col, row0);
+              if (has_res) tma_load_2d(stg_in + gidx * 4096, &tmRes, ld_bar, col, row0);
+              if (has_mask) tma_load_2d(stg_in + (Cfg::GROUPS + gidx) * 4096, &tmMask, ld_bar, col, row0);
             }
           }
           __syncwarp();
         }
         mbar_wait(tfull_bar(acc), acc_phase);
         tc_fence_after();
-        if (elect_one()) tma_store_wait_read<0>();     // previous tile's stores have left the out tiles
+        const uint32_t stg = stg_out_base + (uint32_t)((it % Cfg::OUT_BUFS) * Cfg::GROUPS) * 4096u;
+        if (elect_one()) tma_store_wait_read<Cfg::OUT_BUFS - 1>();   // this out buffer's last store has been read
         __syncwarp();
 #pragma unroll 1
         for (int chunk = 0; chunk < BN / 32; ++chunk) {
@@ -232,8 +237,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           if (chunk == 0 && has_in) mbar_wait(ld_bar, ld_parity);
           const int gidx = chunk >> 1;
           const float cs = epilogue_half_staged(a.epi, raw, valid, n_t * BN + chunk * 32, chunk & 1, lane,
-                                                stg + gidx * 4096, stg + (Cfg::GROUPS + gidx) * 4096,
-                                                stg + (2 * Cfg::GROUPS + gidx) * 4096);
+                                                stg + gidx * 4096, stg_in + gidx * 4096,
+                                                stg_in + (Cfg::GROUPS + gidx) * 4096);
 #pragma unroll
           for (int i = 0; i < BN / 32; ++i)
             if (i == chunk) csum[i] += cs;

@@ -23,6 +23,7 @@ struct HaloArgs {
   int R, S, pad_lo;
   int tiles_w, tiles_h, num_tiles;
   int fast;            // staged TMA epilogue (bf16 compact output)
+  const __nv_bfloat16* x;   // input tensor (the 16-channel variant gathers it with cp.async)
   EpiArgs epi;
 };
 
@@ -38,8 +39,8 @@ struct HaloCfg {
   static constexpr int STAGE_BYTES = (HALO_BYTES + 1023) / 1024 * 1024;
   static constexpr int W_TILE_BYTES = BN * ROW_BYTES;              // one tap: 64 rows x CK
   static constexpr int W_BYTES = MAX_TAPS * W_TILE_BYTES;          // 72 KB / 32 KB, resident
-  static constexpr int STAGES = (CK == 64) ? 4 : 12;
-  static constexpr int EPI_WARP_BYTES = 3 * 4096;                  // out, residual, mask tiles
+  static constexpr int STAGES = (CK == 64) ? 3 : 12;
+  static constexpr int EPI_WARP_BYTES = 4 * 4096;                  // out x2 (double-buffered), residual, mask
   static constexpr int EPI_BYTES = 4 * EPI_WARP_BYTES;
   static constexpr int SMEM_BYTES = W_BYTES + STAGES * STAGE_BYTES + EPI_BYTES + 1024 + 256;
   static constexpr int TMEM_COLS = 128;
@@ -83,7 +84,7 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmW);
     for (int s = 0; s < Cfg::STAGES; ++s) {
-      mbar_init(full_bar(s), 1);
+      mbar_init(full_bar(s), CK == 16 ? 32 : 1);     // cp.async variant: every producer lane arrives
       mbar_init(empty_bar(s), 1);
     }
     for (int i = 0; i < 2; ++i) {
@@ -119,19 +120,62 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       for (int j = 0; j < taps; ++j) tma_load_2d(sW + j * Cfg::W_TILE_BYTES, &tmW, w_bar, j * CK, 0);
     }
     __syncwarp();
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
-      int n, h0, w0;
-      decode(t, n, h0, w0);
-      mbar_wait(empty_bar(stage), phase ^ 1);
-      if (elect_one()) {
-        mbar_expect_tx(full_bar(stage), Cfg::HALO_BYTES);
-        tma_load_tiled_4d(sA0 + stage * Cfg::STAGE_BYTES, &tmX, full_bar(stage), 0, w0 - a.pad_lo,
-                          h0 - a.pad_lo, n);
+    if constexpr (CK == 16) {
+      // 32-byte pixel rows are slow through the TMA unit (one request per row); the whole warp
+      // gathers the 19 x 11 x 32 B window with 16-byte cp.async instead (zero-fill = padding),
+      // writing the 32B-swizzled layout the MMA descriptors expect.  Up to DEPTH tiles in flight.
+      constexpr int DEPTH = 4;
+      constexpr int CHUNKS = Cfg::HALO_H * Cfg::HALO_W * 2;
+      int stage = 0, done_stage = 0, issued = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
+        int n, h0, w0;
+        decode(t, n, h0, w0);
+        mbar_wait(empty_bar(stage), phase ^ 1);
+        const uint32_t base = sA0 + stage * Cfg::STAGE_BYTES;
+        const __nv_bfloat16* img = a.x + (long)n * a.H * a.W * 16;
+        for (int c = lane; c < CHUNKS; c += 32) {
+          const int p = c >> 1, hf = c & 1;
+          const int hy = p / Cfg::HALO_W, wx = p - hy * Cfg::HALO_W;
+          const int gh = h0 - a.pad_lo + hy, gw = w0 - a.pad_lo + wx;
+          const bool inb = gh >= 0 && gh < a.H && gw >= 0 && gw < a.W;
+          const __nv_bfloat16* src = inb ? img + ((long)gh * a.W + gw) * 16 + hf * 8 : a.x;
+          const uint32_t dst = base + p * 32 + ((uint32_t)(hf ^ ((p >> 2) & 1)) << 4);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(inb ? 16 : 0)
+                       : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        ++issued;
+        if (issued >= DEPTH) {          // the oldest in-flight tile has landed: publish it
+          asm volatile("cp.async.wait_group %0;" ::"n"(DEPTH - 1) : "memory");
+          fence_proxy_async();
+          mbar_arrive(full_bar(done_stage));
+          if (++done_stage == Cfg::STAGES) done_stage = 0;
+        }
+        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
       }
-      __syncwarp();
-      if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      fence_proxy_async();
+      const int pending = issued < DEPTH - 1 ? issued : DEPTH - 1;
+      for (int i = 0; i < pending; ++i) {
+        mbar_arrive(full_bar(done_stage));
+        if (++done_stage == Cfg::STAGES) done_stage = 0;
+      }
+    } else {
+        int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
+        int n, h0, w0;
+        decode(t, n, h0, w0);
+        mbar_wait(empty_bar(stage), phase ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(full_bar(stage), Cfg::HALO_BYTES);
+          tma_load_tiled_4d(sA0 + stage * Cfg::STAGE_BYTES, &tmX, full_bar(stage), 0, w0 - a.pad_lo,
+                            h0 - a.pad_lo, n);
+        }
+        __syncwarp();
+        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+      }
     }
   } else if (warp == 1) {
     constexpr uint32_t idesc = make_idesc_bf16(128, Cfg::BN, 0, 0);
@@ -173,8 +217,8 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
     const int g = row >> 3, j = row & 7;
-    const uint32_t stg_out = epi_base + quad * Cfg::EPI_WARP_BYTES;
-    const uint32_t stg_res = stg_out + 4096, stg_mask = stg_out + 8192;
+    const uint32_t stg_out0 = epi_base + quad * Cfg::EPI_WARP_BYTES;
+    const uint32_t stg_res = stg_out0 + 8192, stg_mask = stg_out0 + 12288;
     const uint32_t ld_bar = ld_bar0 + 8u * quad;
     const bool has_res = a.epi.residual != nullptr, has_mask = a.epi.mask_src != nullptr;
     const bool has_in = has_res || has_mask;
@@ -201,7 +245,8 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         }
         mbar_wait(tfull_bar(acc), acc_phase);
         tc_fence_after();
-        if (elect_one()) tma_store_wait_read<0>();      // previous tile's store has left stg_out
+        const uint32_t stg_out = stg_out0 + (uint32_t)(it & 1) * 4096u;
+        if (elect_one()) tma_store_wait_read<1>();      // the store from two tiles ago has left this buffer
         __syncwarp();
 #pragma unroll 1
         for (int half = 0; half < 2; ++half) {
@@ -290,6 +335,7 @@ static int launch_halo(const vdqn_conv_desc* d, cudaStream_t stream) {
   }
   HaloArgs a{};
   a.fast = fast ? 1 : 0;
+  a.x = static_cast<const __nv_bfloat16*>(d->x);
   a.N = d->N; a.H = d->H; a.W = d->W; a.Cout = d->Cout;
   a.R = d->R; a.S = d->S; a.pad_lo = d->pad_lo;
   a.tiles_w = (d->W + Cfg::TW - 1) / Cfg::TW;
