@@ -153,6 +153,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--detail", action="store_true", help="also print per-shape conv timings to stderr")
     a = ap.parse_args()
     if a.impl == "reference":
         return run_reference(a)
@@ -227,7 +228,7 @@ def main():
     loss_dev = float(learner.loss.item())
 
     # ---------------- per-kernel roofline (eager instrumented steps, CUDA events on the launch stream)
-    roof, roof_other = None, []
+    roof, roof_other, breakdown, conv_detail = None, [], None, None
     pk, pk_kind = peaks()
     if rank == 0:
         learner_use_graph, saved_sync = learner.use_graph, learner.grad_sync
@@ -243,9 +244,17 @@ def main():
         for kind, tag, s, e in ops.PROFILE:
             t, n = agg.get(kind, (0.0, 0))
             agg[kind] = (t + s.elapsed_time(e), n + 1)
-        ops.PROFILE = None
         learner.use_graph, learner.grad_sync = learner_use_graph, saved_sync
         step_ms_eager = sum(t for t, _ in agg.values()) / nprof
+        breakdown = {k: {"ms_per_step": round(t / nprof, 4), "launches_per_step": n / nprof}
+                     for k, (t, n) in sorted(agg.items(), key=lambda kv: -kv[1][0])}
+        conv_detail = {}
+        for kind, tag, s_, e_ in ops.PROFILE:
+            if kind in ("igemm", "wgrad"):
+                key = f"{kind}:{tag}"
+                t0, n0 = conv_detail.get(key, (0.0, 0))
+                conv_detail[key] = (t0 + s_.elapsed_time(e_), n0 + 1)
+        conv_detail = {k: [round(t / n * 1e3, 1), n // nprof] for k, (t, n) in conv_detail.items()}
 
         def entry(kind, bound, work_per_step, unit_scale, peak, unit):
             t, n = agg[kind]
@@ -282,6 +291,7 @@ def main():
             del q, act, rw
         except Exception as ex:  # noqa
             roof_other.append({"kernel": "td@B=2^20", "error": repr(ex)})
+        ops.PROFILE = None
         ncu = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(ncu):
             tr = json.load(open(ncu))
@@ -323,6 +333,9 @@ def main():
                "sample": "4 steps of 8 quadruplets (of the 256-quadruplet workload), fp32 oracle port",
                "ms_per_step_b8": dtc * 1e3}
 
+    if rank == 0 and a.detail and conv_detail:
+        for k, v in sorted(conv_detail.items(), key=lambda kv: -kv[1][0] * kv[1][1]):
+            print(f"{v[0]:9.1f} us x{v[1]:2d}  {k}", file=sys.stderr)
     if rank == 0:
         fps = world * B * 2 / (ms * 1e-3)
         out = {
@@ -343,6 +356,7 @@ def main():
             "clocks": clocks, "gpu_launches": (per_step_launches or 0) * a.steps,
             "gpu_launches_per_step": per_step_launches,
             "e2e": e2e, "roofline": roof, "roofline_kernels": roof_other, "cpu_baseline": cpu,
+            "breakdown_eager_ms": breakdown if rank == 0 else None,
         }
         print(json.dumps(out))
     if world > 1:

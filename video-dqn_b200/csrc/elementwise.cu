@@ -85,8 +85,16 @@ __global__ void wgrad_finalize_kernel(const vdqn_wgrad_fin_desc d) {
   if (k < d.K) {
     const long plane = (long)d.Cout * d.K;
     const float* p = d.part + (long)co * d.K + k;
-    float g = 0.f;
-    for (int s = 0; s < d.splits; ++s) g += p[s * plane];
+    float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;      // fixed summation order: deterministic
+    int s = 0;
+    for (; s + 4 <= d.splits; s += 4) {
+      g0 += p[(long)s * plane];
+      g1 += p[(long)(s + 1) * plane];
+      g2 += p[(long)(s + 2) * plane];
+      g3 += p[(long)(s + 3) * plane];
+    }
+    for (; s < d.splits; ++s) g0 += p[(long)s * plane];
+    const float g = (g0 + g1) + (g2 + g3);
     int r, ss, ci;
     const int src = oihw_index(co, k, d.Cin, d.R, d.S, d.kmap, &r, &ss, &ci);
     if (src >= 0) {
@@ -106,47 +114,25 @@ __global__ void wgrad_finalize_kernel(const vdqn_wgrad_fin_desc d) {
 
 // ------------------------------------------------------------------------------------------
 // input packing: one thread per packed pixel (n, h2, w2) -> 16 bf16 (32 bytes)
-template <bool U8>
-__global__ void stem_pack_kernel(const void* __restrict__ xin, __nv_bfloat16* __restrict__ out,
-                                 int N, int H, int W) {
+__global__ void stem_pack_f32_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int H,
+                                     int W) {
   const int H2 = H / 2, W2 = W / 2;
   const long total = (long)N * H2 * W2;
-  const float mean[3] = {0.485f, 0.456f, 0.406f};
-  const float stdv[3] = {0.229f, 0.224f, 0.225f};
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total;
-       i += (long)gridDim.x * blockDim.x) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const int w2 = (int)(i % W2);
     const long t = i / W2;
     const int h2 = (int)(t % H2), n = (int)(t / H2);
     float v[16];
 #pragma unroll
     for (int j = 12; j < 16; ++j) v[j] = 0.f;
-    if (U8) {
-      const uint8_t* x = static_cast<const uint8_t*>(xin);
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
 #pragma unroll
       for (int ph = 0; ph < 2; ++ph) {
-        const uint8_t* row = x + (((long)n * H + 2 * h2 + ph) * W + 2 * w2) * 3;
-#pragma unroll
-        for (int pw = 0; pw < 2; ++pw)
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            float f = (float)row[pw * 3 + c] / 255.f;
-            f = f - mean[c];
-            v[(ph * 2 + pw) * 3 + c] = f / stdv[c];
-          }
+        const float2 f = *reinterpret_cast<const float2*>(x + (((long)n * 3 + c) * H + 2 * h2 + ph) * W + 2 * w2);
+        v[(ph * 2 + 0) * 3 + c] = f.x;
+        v[(ph * 2 + 1) * 3 + c] = f.y;
       }
-    } else {
-      const float* x = static_cast<const float*>(xin);
-#pragma unroll
-      for (int c = 0; c < 3; ++c)
-#pragma unroll
-        for (int ph = 0; ph < 2; ++ph) {
-          const float2 f = *reinterpret_cast<const float2*>(
-              x + (((long)n * 3 + c) * H + 2 * h2 + ph) * W + 2 * w2);
-          v[(ph * 2 + 0) * 3 + c] = f.x;
-          v[(ph * 2 + 1) * 3 + c] = f.y;
-        }
-    }
     uint4 pk[2];
     __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(pk);
 #pragma unroll
@@ -154,6 +140,53 @@ __global__ void stem_pack_kernel(const void* __restrict__ xin, __nv_bfloat16* __
     uint4* o = reinterpret_cast<uint4*>(out + i * 16);
     o[0] = pk[0];
     o[1] = pk[1];
+  }
+}
+
+// uint8 HWC frames: one thread = TWO horizontally adjacent packed pixels = 12 source bytes per image
+// row (three aligned 32-bit loads), normalised as util/torch.py:26-36 (x/255, -mean, /std).
+__global__ void stem_pack_u8_kernel(const uint8_t* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int H,
+                                    int W) {
+  const int H2 = H / 2, W4 = W / 4;
+  const long total = (long)N * H2 * W4;
+  const float mean[3] = {0.485f, 0.456f, 0.406f};
+  const float stdv[3] = {0.229f, 0.224f, 0.225f};
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int w4 = (int)(i % W4);
+    const long t = i / W4;
+    const int h2 = (int)(t % H2), n = (int)(t / H2);
+    uint32_t raw[2][3];
+#pragma unroll
+    for (int ph = 0; ph < 2; ++ph) {
+      const uint32_t* row = reinterpret_cast<const uint32_t*>(x + (((long)n * H + 2 * h2 + ph) * W + 4 * w4) * 3);
+#pragma unroll
+      for (int j = 0; j < 3; ++j) raw[ph][j] = __ldg(row + j);
+    }
+#pragma unroll
+    for (int px = 0; px < 2; ++px) {          // packed pixel 2*w4 + px <- source pixels 4*w4 + 2*px + {0,1}
+      float v[16];
+#pragma unroll
+      for (int j = 12; j < 16; ++j) v[j] = 0.f;
+#pragma unroll
+      for (int ph = 0; ph < 2; ++ph)
+#pragma unroll
+        for (int pw = 0; pw < 2; ++pw)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const int byte = (2 * px + pw) * 3 + c;                 // 0..11 within the 12-byte row chunk
+            const uint32_t b = (raw[ph][byte >> 2] >> (8 * (byte & 3))) & 0xffu;
+            float f = (float)b / 255.f;
+            f = f - mean[c];
+            v[(ph * 2 + pw) * 3 + c] = f / stdv[c];
+          }
+      uint4 pk[2];
+      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(pk);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) h[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+      uint4* o = reinterpret_cast<uint4*>(out + ((((long)n * H2 + h2) * (W / 2)) + 2 * w4 + px) * 16);
+      o[0] = pk[0];
+      o[1] = pk[1];
+    }
   }
 }
 
@@ -211,66 +244,83 @@ __global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfl
   }
 }
 
-// backward: one thread = 8 channels of one INPUT pixel; gathers from the <=4 windows covering it.
-// The stem ReLU mask is taken from the POOLED output y (the arg-max element is > 0 exactly when the
-// window maximum is), so the 4x larger pre-pool activation is not re-read.  Accumulates per-channel
-// sums (d beta of bn1).
+// backward: one thread = 8 channels of a 2x2 block of INPUT pixels (rows 2i, 2i+1; cols 2j, 2j+1).
+// The block is covered by the four windows (i..i+1, j..j+1), each loaded once (arg-max slots,
+// dy, pooled y); a window's gradient goes to the pixel whose slot matches.  The stem ReLU mask is
+// taken from the POOLED output y (the arg-max element is > 0 exactly when the window maximum is), so
+// the 4x larger pre-pool activation is not re-read.  Accumulates per-channel sums (d beta of bn1).
 __global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ idx,
                                    const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ dx,
                                    float* __restrict__ colsum, int N, int H, int W, int C) {
-  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1, CG = C / 8;
-  const long total = (long)N * H * W * CG;
+  const int Ho = H / 2, Wo = W / 2, CG = C / 8;      // H, W even: 3x3/2/1 pooling halves them
+  const long total = (long)N * Ho * Wo * CG;
   float acc[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-  // blockDim.x is a multiple of CG, and the grid stride too, so a thread keeps its channel group
-  const int cg = threadIdx.x % CG;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total;
-       i += (long)gridDim.x * blockDim.x) {
-    long t = i / CG;
-    const int w = (int)(t % W); t /= W;
-    const int h = (int)(t % H);
-    const int n = (int)(t / H);
-    uint32_t g2[4] = {0u, 0u, 0u, 0u};              // packed bf16x2 accumulators
-    const int p_lo = h >> 1, p_hi = (h + 1) >> 1;     // windows p with 2p-1 <= h <= 2p+1
-    const int q_lo = w >> 1, q_hi = (w + 1) >> 1;
-    for (int p = p_lo; p <= p_hi; ++p) {
-      if (p >= Ho) continue;
-      const int r = h - 2 * p + 1;
-      for (int q = q_lo; q <= q_hi; ++q) {
-        if (q >= Wo) continue;
-        const int s = w - 2 * q + 1;
-        const uint32_t want4 = (uint32_t)(r * 3 + s) * 0x01010101u;
-        const long o = (((long)n * Ho + p) * Wo + q) * C + cg * 8;
-        const uint2 ip = __ldg(reinterpret_cast<const uint2*>(idx + o));
-        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(dy + o));
-        const uint32_t m_lo = __vcmpeq4(ip.x, want4), m_hi = __vcmpeq4(ip.y, want4);   // 0xFF per match
-        const uint32_t m[4] = {__byte_perm(m_lo, 0, 0x1100), __byte_perm(m_lo, 0, 0x3322),
-                               __byte_perm(m_hi, 0, 0x1100), __byte_perm(m_hi, 0, 0x3322)};
-        const uint4 yr = __ldg(reinterpret_cast<const uint4*>(y + o));
-        const uint32_t yv[4] = {yr.x, yr.y, yr.z, yr.w};
-        const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
-        uint32_t v[4] = {raw.x & m[0], raw.y & m[1], raw.z & m[2], raw.w & m[3]};
+  const int cg = threadIdx.x % CG;                  // blockDim.x and the grid stride are multiples of CG
+  const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
+  for (long t0 = blockIdx.x * (long)blockDim.x + threadIdx.x; t0 < total; t0 += (long)gridDim.x * blockDim.x) {
+    long t = t0 / CG;
+    const int j = (int)(t % Wo); t /= Wo;
+    const int i = (int)(t % Ho);
+    const int n = (int)(t / Ho);
+    // masked window gradients gw[a][b] for windows (i+a, j+b) and their arg-max slots
+    uint32_t gw[2][2][4];
+    uint2 sl[2][2];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) v[e] &= __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&yv[e]), zero2);
+    for (int a = 0; a < 2; ++a)
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const __nv_bfloat162 sum = __hadd2(*reinterpret_cast<const __nv_bfloat162*>(&g2[e]),
-                                             *reinterpret_cast<const __nv_bfloat162*>(&v[e]));
-          g2[e] = *reinterpret_cast<const uint32_t*>(&sum);
+      for (int b = 0; b < 2; ++b) {
+        const bool in = (i + a < Ho) && (j + b < Wo);
+        if (in) {
+          const long o = (((long)n * Ho + i + a) * Wo + j + b) * C + cg * 8;
+          sl[a][b] = __ldg(reinterpret_cast<const uint2*>(idx + o));
+          const uint4 g = __ldg(reinterpret_cast<const uint4*>(dy + o));
+          const uint4 yy = __ldg(reinterpret_cast<const uint4*>(y + o));
+          const uint32_t gv[4] = {g.x, g.y, g.z, g.w}, yv[4] = {yy.x, yy.y, yy.z, yy.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            gw[a][b][e] = gv[e] & __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&yv[e]), zero2);
+        } else {
+          sl[a][b] = make_uint2(0xffffffffu, 0xffffffffu);      // slot 255 never matches
+#pragma unroll
+          for (int e = 0; e < 4; ++e) gw[a][b][e] = 0u;
         }
       }
-    }
-    uint4 pk;
-    uint32_t* ov = reinterpret_cast<uint32_t*>(&pk);
+    // out[ph][pw] for input pixel (2i+ph, 2j+pw): window (i+a, j+b) reaches it through slot
+    // r*3+s with r = ph - 2a + 1, s = pw - 2b + 1 (valid when 0 <= r,s <= 2)
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      ov[e] = g2[e];
-      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ov[e]));
-      acc[2 * e] += f.x;
-      acc[2 * e + 1] += f.y;
-    }
-    *reinterpret_cast<uint4*>(dx + i * 8) = pk;
+    for (int ph = 0; ph < 2; ++ph)
+#pragma unroll
+      for (int pw = 0; pw < 2; ++pw) {
+        uint32_t o2[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+          for (int b = 0; b < 2; ++b) {
+            const int r = ph - 2 * a + 1, sx = pw - 2 * b + 1;
+            if (r < 0 || r > 2 || sx < 0 || sx > 2) continue;
+            const uint32_t want4 = (uint32_t)(r * 3 + sx) * 0x01010101u;
+            const uint32_t m_lo = __vcmpeq4(sl[a][b].x, want4), m_hi = __vcmpeq4(sl[a][b].y, want4);
+            const uint32_t m[4] = {__byte_perm(m_lo, 0, 0x1100), __byte_perm(m_lo, 0, 0x3322),
+                                   __byte_perm(m_hi, 0, 0x1100), __byte_perm(m_hi, 0, 0x3322)};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const uint32_t v = gw[a][b][e] & m[e];
+              const __nv_bfloat162 sum = __hadd2(*reinterpret_cast<const __nv_bfloat162*>(&o2[e]),
+                                                 *reinterpret_cast<const __nv_bfloat162*>(&v));
+              o2[e] = *reinterpret_cast<const uint32_t*>(&sum);
+            }
+          }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&o2[e]));
+          acc[2 * e] += f.x;
+          acc[2 * e + 1] += f.y;
+        }
+        const long op = (((long)n * H + 2 * i + ph) * W + 2 * j + pw) * C + cg * 8;
+        *reinterpret_cast<uint4*>(dx + op) = make_uint4(o2[0], o2[1], o2[2], o2[3]);
+      }
   }
   if (colsum != nullptr) {
     extern __shared__ float sm[];      // [blockDim.x][8]
@@ -558,7 +608,7 @@ extern "C" int vdqn_stem_pack_f32(const float* x, void* out, int32_t N, int32_t 
   GET_DEV();
   const long total = (long)N * (H / 2) * (W / 2);
   if (total == 0) return VDQN_OK;
-  stem_pack_kernel<false><<<grid_for(total, 256, dev->num_sms, 16), 256, 0, stream>>>(
+  stem_pack_f32_kernel<<<grid_for(total, 256, dev->num_sms, 16), 256, 0, stream>>>(
       x, static_cast<__nv_bfloat16*>(out), N, H, W);
   VDQN_CHECK_LAUNCH("stem_pack_f32");
   return VDQN_OK;
@@ -566,11 +616,12 @@ extern "C" int vdqn_stem_pack_f32(const float* x, void* out, int32_t N, int32_t 
 
 extern "C" int vdqn_stem_pack_u8(const uint8_t* x, void* out, int32_t N, int32_t H, int32_t W, void* stream_v) {
   if (x == nullptr || out == nullptr) return set_error(VDQN_ERR_ARG, "stem_pack: null pointer");
-  if ((H | W) & 1) return set_error(VDQN_ERR_SHAPE, "stem_pack: H and W must be even");
+  if ((H & 1) || (W & 3)) return set_error(VDQN_ERR_SHAPE, "stem_pack_u8: H must be even and W a multiple of 4");
+  if (reinterpret_cast<uintptr_t>(x) & 3) return set_error(VDQN_ERR_ARG, "stem_pack_u8: frames must be 4-byte aligned");
   GET_DEV();
-  const long total = (long)N * (H / 2) * (W / 2);
+  const long total = (long)N * (H / 2) * (W / 4);
   if (total == 0) return VDQN_OK;
-  stem_pack_kernel<true><<<grid_for(total, 256, dev->num_sms, 16), 256, 0, stream>>>(
+  stem_pack_u8_kernel<<<grid_for(total, 256, dev->num_sms, 16), 256, 0, stream>>>(
       x, static_cast<__nv_bfloat16*>(out), N, H, W);
   VDQN_CHECK_LAUNCH("stem_pack_u8");
   return VDQN_OK;
@@ -599,8 +650,9 @@ extern "C" int vdqn_maxpool_bwd(const void* dy, const uint8_t* idx, const void* 
   if (dy == nullptr || idx == nullptr || y == nullptr || dx == nullptr)
     return set_error(VDQN_ERR_ARG, "maxpool_bwd: null pointer");
   if (C % 8 || 256 % (C / 8) || C > 256) return set_error(VDQN_ERR_SHAPE, "maxpool_bwd: unsupported C=%d", C);
+  if ((H | W) & 1) return set_error(VDQN_ERR_SHAPE, "maxpool_bwd: H and W must be even");
   GET_DEV();
-  const long total = (long)N * H * W * (C / 8);
+  const long total = (long)N * (H / 2) * (W / 2) * (C / 8);
   if (total == 0) return VDQN_OK;
   maxpool_bwd_kernel<<<grid_for(total, 256, dev->num_sms, 8), 256, 256 * 8 * sizeof(float), stream>>>(
       static_cast<const __nv_bfloat16*>(dy), idx, static_cast<const __nv_bfloat16*>(y),

@@ -158,9 +158,10 @@ class PreparedWeights:
             self._table = raw.to(dev)
             self._offsets = torch.tensor(offs, dtype=torch.int64, device=dev)
             self._total, self._table_sig = total, sig
-        L.check(L.load().vdqn_weight_prep_multi(self._table.data_ptr(), self._offsets.data_ptr(),
-                                                len(self.plan.convs), self._total, L.stream_ptr()),
-                "weight_prep_multi")
+        with ops._Prof("weight_prep", (self._total,)):
+            L.check(L.load().vdqn_weight_prep_multi(self._table.data_ptr(), self._offsets.data_ptr(),
+                                                    len(self.plan.convs), self._total, L.stream_ptr()),
+                    "weight_prep_multi")
 
 
 class Workspace:
@@ -235,9 +236,16 @@ class Workspace:
         return self._view
 
 
+import os as _os
+
+# column-tile width for the Cout >= 256 layers (0 = kernel default 256); tuning knob
+TILE_N_WIDE = int(_os.environ.get("VDQN_TILE_N_WIDE", "0"))
+
+
 def _conv(W: PreparedWeights, c: ConvSpec, x, out, **kw):
+    tn = TILE_N_WIDE if c.cout >= 256 else 0
     return ops.conv_gemm(x, W.w_fwd[c.name], c.stride, c.pad_lo, c.pad_hi, shift=W.shift[c.name],
-                         out=out, **kw)
+                         out=out, tile_n=tn, **kw)
 
 
 def forward(plan: NetPlan, W: PreparedWeights, P: Dict[str, torch.Tensor], ws: Workspace,
@@ -313,7 +321,8 @@ def backward(plan: NetPlan, W: PreparedWeights, P: Dict[str, torch.Tensor], G: D
         dy_a1 = ws.dy_a1[b.out_hw]
         ops.conv_gemm(cur, W.w_dgrad[b.conv2.name], 1, 1, 1, mask_src=ws.a1[i],
                       colsum=G[b.conv1.bn + ".bias"], out=dy_a1,
-                      out2=ws.dy_a1_dil[b.out_hw] if b.stride == 2 else None)
+                      out2=ws.dy_a1_dil[b.out_hw] if b.stride == 2 else None,
+                      tile_n=TILE_N_WIDE if b.cout >= 256 else 0)
         # identity / downsample branch
         if b.ds is not None:
             _wgrad(plan, P, G, ws, b.ds, x_in, cur, None)
@@ -332,7 +341,7 @@ def backward(plan: NetPlan, W: PreparedWeights, P: Dict[str, torch.Tensor], G: D
             ni, dst, colsum, mask = 0, ws.dy_p, None, None
         src = ws.dy_a1_dil[b.out_hw] if b.stride == 2 else dy_a1
         ops.conv_gemm(src, W.w_dgrad[b.conv1.name], 1, 1, 1, residual=res, mask_src=mask, colsum=colsum,
-                      out=dst)
+                      out=dst, tile_n=TILE_N_WIDE if b.cin >= 256 else 0)
         notify(b.conv1.name)
         cur, ci = dst, ni
     # ---- max-pool + stem

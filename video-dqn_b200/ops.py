@@ -143,7 +143,8 @@ def wgrad_finalize(part, w, dw, *, splits, Cout, Cin, R, S, K, kmap=0, gamma=Non
     d.dbeta, d.dgamma = L.ptr(dbeta), L.ptr(dgamma)
     d.splits, d.Cout, d.Cin, d.R, d.S, d.K, d.kmap = splits, Cout, Cin, R, S, K, kmap
     d.eps = eps
-    L.check(lib.vdqn_wgrad_finalize(C.byref(d), L.stream_ptr()), "wgrad_finalize")
+    with _Prof("wgrad_finalize", (Cout, K, splits)):
+        L.check(lib.vdqn_wgrad_finalize(C.byref(d), L.stream_ptr()), "wgrad_finalize")
     return dw
 
 
@@ -177,7 +178,8 @@ def stem_pack(x, out=None):
     _req(c == 3, "bad shape")
     if out is None:
         out = torch.empty(N, H // 2, W_ // 2, 16, device=x.device, dtype=bf16)
-    L.check(fn(x.data_ptr(), out.data_ptr(), N, H, W_, L.stream_ptr()), "stem_pack")
+    with _Prof("stem_pack", (N,)):
+        L.check(fn(x.data_ptr(), out.data_ptr(), N, H, W_, L.stream_ptr()), "stem_pack")
     return out
 
 
@@ -190,8 +192,9 @@ def maxpool_fwd(x, y=None, idx=None, save_idx=False):
         y = torch.empty(N, Ho, Wo, Cc, device=x.device, dtype=bf16)
     if save_idx and idx is None:
         idx = torch.empty(N, Ho, Wo, Cc, device=x.device, dtype=torch.uint8)
-    L.check(lib.vdqn_maxpool_fwd(x.data_ptr(), y.data_ptr(), L.ptr(idx), N, H, W_, Cc, L.stream_ptr()),
-            "maxpool_fwd")
+    with _Prof("maxpool_fwd", (N,)):
+        L.check(lib.vdqn_maxpool_fwd(x.data_ptr(), y.data_ptr(), L.ptr(idx), N, H, W_, Cc, L.stream_ptr()),
+                "maxpool_fwd")
     return y, idx
 
 
@@ -203,8 +206,9 @@ def maxpool_bwd(dy, idx, y, dx=None, colsum=None):
     H, W_ = 2 * Ho, 2 * Wo
     if dx is None:
         dx = torch.empty(N, H, W_, Cc, device=y.device, dtype=bf16)
-    L.check(lib.vdqn_maxpool_bwd(dy.data_ptr(), idx.data_ptr(), y.data_ptr(), dx.data_ptr(),
-                                 L.ptr(colsum), N, H, W_, Cc, L.stream_ptr()), "maxpool_bwd")
+    with _Prof("maxpool_bwd", (N,)):
+        L.check(lib.vdqn_maxpool_bwd(dy.data_ptr(), idx.data_ptr(), y.data_ptr(), dx.data_ptr(),
+                                     L.ptr(colsum), N, H, W_, Cc, L.stream_ptr()), "maxpool_bwd")
     return dx
 
 
@@ -216,8 +220,9 @@ def linear_fwd(x, w, bias, relu, y=None):
     _req(w.shape[1] == K, "bad shape")
     if y is None:
         y = torch.empty(B, O, device=x.device, dtype=torch.float32)
-    L.check(lib.vdqn_linear_fwd(x.data_ptr(), w.data_ptr(), L.ptr(bias), y.data_ptr(), B, K, O,
-                                int(relu), L.stream_ptr()), "linear_fwd")
+    with _Prof("mlp", (B, K, O)):
+        L.check(lib.vdqn_linear_fwd(x.data_ptr(), w.data_ptr(), L.ptr(bias), y.data_ptr(), B, K, O,
+                                    int(relu), L.stream_ptr()), "linear_fwd")
     return y
 
 
@@ -228,9 +233,10 @@ def linear_bwd(x, w, y, dy, dw, db, relu, dx=None, need_dx=True):
     O = w.shape[0]
     if need_dx and dx is None:
         dx = torch.empty(B, K, device=x.device, dtype=torch.float32)
-    L.check(lib.vdqn_linear_bwd(x.data_ptr(), w.data_ptr(), L.ptr(y), dy.data_ptr(),
-                                L.ptr(dx) if need_dx else None, dw.data_ptr(), db.data_ptr(),
-                                B, K, O, int(relu), L.stream_ptr()), "linear_bwd")
+    with _Prof("mlp", (B, K, O)):
+        L.check(lib.vdqn_linear_bwd(x.data_ptr(), w.data_ptr(), L.ptr(y), dy.data_ptr(),
+                                    L.ptr(dx) if need_dx else None, dw.data_ptr(), db.data_ptr(),
+                                    B, K, O, int(relu), L.stream_ptr()), "linear_bwd")
     return dx
 
 
@@ -242,8 +248,9 @@ def head_flatten_fwd(h, flat=None):
     P = h.numel() // (B * Cc)
     if flat is None:
         flat = torch.empty(B, Cc * P, device=h.device, dtype=torch.float32)
-    L.check(lib.vdqn_head_flatten_fwd(h.data_ptr(), flat.data_ptr(), B, P, Cc, L.stream_ptr()),
-            "head_flatten_fwd")
+    with _Prof("mlp", (B,)):
+        L.check(lib.vdqn_head_flatten_fwd(h.data_ptr(), flat.data_ptr(), B, P, Cc, L.stream_ptr()),
+                "head_flatten_fwd")
     return flat
 
 
@@ -254,8 +261,9 @@ def head_flatten_bwd(dflat, h, dh=None, dbias=None):
     P = h.numel() // (B * Cc)
     if dh is None:
         dh = torch.empty_like(h)
-    L.check(lib.vdqn_head_flatten_bwd(dflat.data_ptr(), h.data_ptr(), dh.data_ptr(), L.ptr(dbias),
-                                      B, P, Cc, L.stream_ptr()), "head_flatten_bwd")
+    with _Prof("mlp", (B,)):
+        L.check(lib.vdqn_head_flatten_bwd(dflat.data_ptr(), h.data_ptr(), dh.data_ptr(), L.ptr(dbias),
+                                          B, P, Cc, L.stream_ptr()), "head_flatten_bwd")
     return dh
 
 
