@@ -32,6 +32,7 @@ extern "C" {
 /* conv epilogue flags */
 #define VDQN_EPI_RELU 1     /* out = max(v, 0) */
 #define VDQN_EPI_OUT_F32 2  /* store fp32 instead of bf16 */
+#define VDQN_EPI_SCATTER_INPUTS 4 /* with out_scatter == 2: residual / mask_src are read at the scattered pixel too */
 
 const char* vdqn_last_error(void);
 int vdqn_abi_version(void);
@@ -74,6 +75,8 @@ typedef struct vdqn_conv_desc {
   int32_t tile_n;      /* 0 = auto (64/128/256) */
   int32_t max_ctas;    /* 0 = one per SM */
   int32_t algo;        /* 0 = auto, 1 = im2col-TMA kernel, 2 = halo-tile kernel (Cout = 64 layers) */
+  int32_t pad_hi_w;    /* upper padding along W when it differs from pad_hi (H); -1 = same */
+  int32_t scatter_off_h, scatter_off_w; /* out_scatter == 2: opix = (n*2Ho + 2p + off_h)*2Wo + 2q + off_w */
 } vdqn_conv_desc;
 int vdqn_conv_gemm(const vdqn_conv_desc* d, void* stream);
 
@@ -130,10 +133,14 @@ typedef struct vdqn_wprep_desc {
   const float* gamma; const float* beta; const float* mean; const float* var; /* NULL if no BN */
   const float* bias;  /* conv bias or NULL */
   void* w_fwd;        /* bf16 [Cout][K] */
-  void* w_dgrad;      /* bf16 [Cin][R*S*Cout] or NULL */
+  void* w_dgrad;      /* bf16 [Cin][R*S*Cout] or NULL; dgrad_parity: four parity-class filters (see below) */
   float* shift;       /* [Cout] */
   int32_t Cout, Cin, R, S, K, kmap;
   float eps;
+  /* 1 (3x3 stride-2 convs): w_dgrad holds the data-gradient filters of the four output-parity
+   * classes (h%2, w%2) back to back -- class (a,b) is [Cin][na][nb][Cout] with na = 1 + a,
+   * nb = 1 + b taps (rows r = 1 | {2, 0}, same for columns), class offsets 0, 1, 3, 5 taps x Cin*Cout. */
+  int32_t dgrad_parity;
 } vdqn_wprep_desc;
 int vdqn_weight_prep(const vdqn_wprep_desc* d, void* stream);
 /* Same for `n` tensors in one launch: `descs_dev` / `offsets_dev` are DEVICE arrays (offsets[t] = sum of

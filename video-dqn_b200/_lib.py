@@ -10,6 +10,7 @@ LIB_PATH = os.path.join(_HERE, "libvdqn.so")
 
 EPI_RELU = 1
 EPI_OUT_F32 = 2
+EPI_SCATTER_INPUTS = 4
 
 c_void_p, c_int, c_float, c_int64 = C.c_void_p, C.c_int32, C.c_float, C.c_int64
 
@@ -20,7 +21,8 @@ class ConvDesc(C.Structure):
                 ("colsum", c_void_p)] + \
                [(n, c_int) for n in ("N", "H", "W", "Cin", "Cout", "R", "S", "stride", "dil",
                                      "pad_lo", "pad_hi", "ldc", "ldr", "ldm", "out2_ld",
-                                     "out_scatter", "flags", "tile_n", "max_ctas", "algo")]
+                                     "out_scatter", "flags", "tile_n", "max_ctas", "algo", "pad_hi_w",
+                                     "scatter_off_h", "scatter_off_w")]
 
 
 class WgradDesc(C.Structure):
@@ -37,7 +39,8 @@ class WgradFinDesc(C.Structure):
 class WprepDesc(C.Structure):
     _fields_ = [(n, c_void_p) for n in ("w", "gamma", "beta", "mean", "var", "bias", "w_fwd",
                                         "w_dgrad", "shift")] + \
-               [(n, c_int) for n in ("Cout", "Cin", "R", "S", "K", "kmap")] + [("eps", c_float)]
+               [(n, c_int) for n in ("Cout", "Cin", "R", "S", "K", "kmap")] + [("eps", c_float),
+                                                                                ("dgrad_parity", c_int)]
 
 
 class TdDesc(C.Structure):

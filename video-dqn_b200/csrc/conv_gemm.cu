@@ -27,7 +27,9 @@ struct IgemmArgs {
   int R, S, Cin, stride, dil, lower_h, lower_w;
   int num_m_tiles, num_n_tiles;
   EpiArgs epi;
-  int out_scatter;    // 1: opix = m;  2: opix = (n*2Ho + 2p)*2Wo + 2q
+  int out_scatter;    // 1: opix = m;  2: opix = (n*2Ho + 2p + off_h)*2Wo + 2q + off_w
+  int off_h, off_w;
+  int scatter_inputs; // residual / mask indexed by the scattered pixel
   int fast;           // staged TMA epilogue (BN <= 128, bf16 compact output)
 };
 
@@ -265,7 +267,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const int rem = m - img * HoWo;
         const int p = rem / a.Wo, q = rem - p * a.Wo;
         const long dil_pix = ((long)img * (2 * a.Ho) + 2 * p) * (2 * a.Wo) + 2 * q;
-        if (a.out_scatter == 2) opix = dil_pix;
+        if (a.out_scatter == 2) opix = ((long)img * (2 * a.Ho) + 2 * p + a.off_h) * (2 * a.Wo) + 2 * q + a.off_w;
         opix2 = dil_pix;
       }
       mbar_wait(tfull_bar(acc), acc_phase);
@@ -275,7 +277,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         uint32_t raw[32];
         tmem_ld_32x32(tmem_base + acc * BN + chunk * 32 + ((uint32_t)(quad * 32) << 16), raw);
         tmem_ld_wait();
-        const float cs = epilogue_chunk(a.epi, raw, valid, (long)m, opix, opix2, n_t * BN + chunk * 32, lane);
+        const float cs = epilogue_chunk(a.epi, raw, valid, a.scatter_inputs ? opix : (long)m, opix, opix2,
+                                        n_t * BN + chunk * 32, lane);
 #pragma unroll
         for (int i = 0; i < BN / 32; ++i)
           if (i == chunk) csum[i] += cs;
@@ -333,7 +336,8 @@ extern "C" int vdqn_conv_gemm(const vdqn_conv_desc* d, void* stream_v) {
   if (CK == 16 && (d->R * d->S * (d->Cin / 16)) % 4 != 0)
     return set_error(VDQN_ERR_SHAPE, "conv_gemm: 16-channel path needs R*S*Cin/16 %% 4 == 0");
   const int Ho = (d->H + d->pad_lo + d->pad_hi - (d->R - 1) * d->dil - 1) / d->stride + 1;
-  const int Wo = (d->W + d->pad_lo + d->pad_hi - (d->S - 1) * d->dil - 1) / d->stride + 1;
+  const int pad_hi_w = d->pad_hi_w >= 0 ? d->pad_hi_w : d->pad_hi;
+  const int Wo = (d->W + d->pad_lo + pad_hi_w - (d->S - 1) * d->dil - 1) / d->stride + 1;
   if (Ho <= 0 || Wo <= 0) return set_error(VDQN_ERR_SHAPE, "conv_gemm: empty output");
   int BN = d->Cout >= 256 ? 256 : d->Cout;
   if (d->tile_n > 0) BN = d->tile_n;
@@ -355,7 +359,7 @@ extern "C" int vdqn_conv_gemm(const vdqn_conv_desc* d, void* stream_v) {
   CUtensorMap tmA, tmB;
   int rc = make_im2col_map(&tmA, d->x, d->N, d->H, d->W, d->Cin, CK, 128, d->stride,
                            -d->pad_lo, -d->pad_lo,
-                           d->pad_hi - (d->R - 1) * d->dil, d->pad_hi - (d->S - 1) * d->dil,
+                           d->pad_hi - (d->R - 1) * d->dil, pad_hi_w - (d->S - 1) * d->dil,
                            CK == 64 ? 128 : 32);
   if (rc != VDQN_OK) return rc;
   rc = make_tiled_map_2d(&tmB, d->w, (uint64_t)d->R * d->S * d->Cin, d->Cout, CK, BN,
@@ -371,6 +375,8 @@ extern "C" int vdqn_conv_gemm(const vdqn_conv_desc* d, void* stream_v) {
   a.num_n_tiles = d->Cout / BN;
   a.epi = make_epi_args(d);
   a.out_scatter = d->out_scatter == 2 ? 2 : 1;
+  a.off_h = d->scatter_off_h; a.off_w = d->scatter_off_w;
+  a.scatter_inputs = (d->out_scatter == 2 && (d->flags & VDQN_EPI_SCATTER_INPUTS)) ? 1 : 0;
 
   // staged epilogue: 2-D maps over the [M][ld] output / residual / mask matrices, 64 x 32 boxes
   CUtensorMap epi_maps[3] = {tmB, tmB, tmB};

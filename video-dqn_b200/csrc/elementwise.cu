@@ -41,7 +41,17 @@ __device__ __forceinline__ void weight_prep_element(const vdqn_wprep_desc& d, lo
   const __nv_bfloat16 b = __float2bfloat16_rn(v);
   static_cast<__nv_bfloat16*>(d.w_fwd)[i] = b;
   if (d.w_dgrad != nullptr && d.kmap == 0) {
-    const long di = (long)ci * (d.R * d.S * d.Cout) + (long)((d.R - 1 - r) * d.S + (d.S - 1 - s)) * d.Cout + co;
+    long di;
+    if (d.dgrad_parity) {
+      // output-parity class (a, b) and tap (u, v) inside it: r = 1 -> (a=0,u=0); r = 2 -> (1,0); r = 0 -> (1,1)
+      const int pa = (r == 1) ? 0 : 1, u = (r == 0) ? 1 : 0;
+      const int pb = (s == 1) ? 0 : 1, v = (s == 0) ? 1 : 0;
+      const int nb = 1 + pb, nt = (1 + pa) * nb;
+      const int cls_off = (pa == 0) ? (pb == 0 ? 0 : 1) : (pb == 0 ? 3 : 5);
+      di = (long)cls_off * d.Cin * d.Cout + (long)ci * (nt * d.Cout) + (long)(u * nb + v) * d.Cout + co;
+    } else {
+      di = (long)ci * (d.R * d.S * d.Cout) + (long)((d.R - 1 - r) * d.S + (d.S - 1 - s)) * d.Cout + co;
+    }
     static_cast<__nv_bfloat16*>(d.w_dgrad)[di] = b;
   }
   if (k == 0) {

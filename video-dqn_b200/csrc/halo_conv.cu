@@ -359,6 +359,7 @@ static int make_tiled_map_4d(CUtensorMap* map, const void* base, int N, int H, i
 bool halo_conv_supported(const vdqn_conv_desc* d) {
   if (d->stride != 1 || d->dil != 1 || d->Cout != 64 || d->out_scatter == 2 || d->out2 != nullptr)
     return false;
+  if (d->pad_hi_w >= 0 && d->pad_hi_w != d->pad_hi) return false;
   if (d->Cin == 64 && d->R == 3 && d->S == 3 && d->pad_lo == 1 && d->pad_hi == 1) return true;
   if (d->Cin == 16 && d->R == 4 && d->S == 4 && d->pad_lo == 2 && d->pad_hi == 1) return true;
   return false;

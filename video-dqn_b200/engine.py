@@ -151,6 +151,7 @@ class PreparedWeights:
                     d.bias = P[c.bias].data_ptr()
                 d.Cout, d.Cin, d.R, d.S = w.shape
                 d.K, d.kmap, d.eps = c.K, c.kmap, BN_EPS
+                d.dgrad_parity = int(c.kmap == 0 and c.stride == 2 and c.k == 3)
                 offs.append(total)
                 total += c.cout * c.K
             dev = self.shift["stem"].device
@@ -162,6 +163,18 @@ class PreparedWeights:
             L.check(L.load().vdqn_weight_prep_multi(self._table.data_ptr(), self._offsets.data_ptr(),
                                                     len(self.plan.convs), self._total, L.stream_ptr()),
                     "weight_prep_multi")
+
+
+# output-parity classes of a 3x3 stride-2 data gradient: (a, b, taps_h, taps_w, offset in taps)
+PARITY_CLASSES = ((0, 0, 1, 1, 0), (0, 1, 1, 2, 1), (1, 0, 2, 1, 3), (1, 1, 2, 2, 5))
+
+
+def parity_filters(W: "PreparedWeights", c: ConvSpec):
+    """Views of the four parity-class data-gradient filters [Cin][na][nb][Cout] of a strided conv."""
+    flat = W.w_dgrad[c.name].view(-1)
+    unit = c.cin * c.cout
+    return [(a, b, flat[off * unit:(off + na * nb) * unit].view(c.cin, na, nb, c.cout))
+            for a, b, na, nb, off in PARITY_CLASSES]
 
 
 class Workspace:
@@ -207,8 +220,8 @@ class Workspace:
             self.dy_out = {b.out_hw: (e(n, b.out_hw, b.out_hw, b.cout), e(n, b.out_hw, b.out_hw, b.cout))
                            for b in plan.blocks}
             self.dy_a1 = {b.out_hw: e(n, b.out_hw, b.out_hw, b.cout) for b in plan.blocks}
-            # zero-dilated copies for the strided data gradients (odd positions stay zero forever)
-            self.dy_a1_dil = {b.out_hw: z(n, b.in_hw, b.in_hw, b.cout) for b in plan.blocks if b.stride == 2}
+            # zero-dilated buffer the 1x1/2 downsample data gradient scatters into (odd positions stay
+            # zero forever); it is the residual of the strided conv1 data gradient
             self.r_dil = {b.out_hw: z(n, b.in_hw, b.in_hw, b.cin) for b in plan.blocks if b.stride == 2}
             self.dy_p = e(n, 56, 56, 64)
             self.dy_s = e(n, 112, 112, 64)
@@ -321,7 +334,6 @@ def backward(plan: NetPlan, W: PreparedWeights, P: Dict[str, torch.Tensor], G: D
         dy_a1 = ws.dy_a1[b.out_hw]
         ops.conv_gemm(cur, W.w_dgrad[b.conv2.name], 1, 1, 1, mask_src=ws.a1[i],
                       colsum=G[b.conv1.bn + ".bias"], out=dy_a1,
-                      out2=ws.dy_a1_dil[b.out_hw] if b.stride == 2 else None,
                       tile_n=TILE_N_WIDE if b.cout >= 256 else 0)
         # identity / downsample branch
         if b.ds is not None:
@@ -339,9 +351,16 @@ def backward(plan: NetPlan, W: PreparedWeights, P: Dict[str, torch.Tensor], G: D
             colsum, mask = G[prev.conv2.bn + ".bias"], x_in
         else:
             ni, dst, colsum, mask = 0, ws.dy_p, None, None
-        src = ws.dy_a1_dil[b.out_hw] if b.stride == 2 else dy_a1
-        ops.conv_gemm(src, W.w_dgrad[b.conv1.name], 1, 1, 1, residual=res, mask_src=mask, colsum=colsum,
-                      out=dst, tile_n=TILE_N_WIDE if b.cin >= 256 else 0)
+        if b.stride == 2:
+            # strided data gradient, one small stride-1 conv per output-parity class (h%2, w%2): exactly
+            # the 9 taps of work, each class scattering into its own pixels of dX
+            for pa, pb, wf in parity_filters(W, b.conv1):
+                ops.conv_gemm(dy_a1, wf, 1, 0, wf.shape[1] - 1, pad_hi_w=wf.shape[2] - 1, residual=res,
+                              mask_src=mask, colsum=colsum, out=dst, out_scatter=2, scatter_off=(pa, pb),
+                              scatter_inputs=True)
+        else:
+            ops.conv_gemm(dy_a1, W.w_dgrad[b.conv1.name], 1, 1, 1, residual=res, mask_src=mask,
+                          colsum=colsum, out=dst, tile_n=TILE_N_WIDE if b.cin >= 256 else 0)
         notify(b.conv1.name)
         cur, ci = dst, ni
     # ---- max-pool + stem

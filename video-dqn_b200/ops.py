@@ -67,7 +67,7 @@ def conv_out_hw(H, W, R, S, stride, pad_lo, pad_hi, dil=1):
 
 def conv_gemm(x, w, stride=1, pad_lo=0, pad_hi=None, *, shift=None, residual=None, mask_src=None,
               relu=False, out_f32=False, colsum=None, out=None, out2=None, out_scatter=1,
-              tile_n=0, max_ctas=0, dil=1, algo=0):
+              tile_n=0, max_ctas=0, dil=1, algo=0, pad_hi_w=-1, scatter_off=(0, 0), scatter_inputs=False):
     """x [N,H,W,Cin] bf16, w [Cout,R,S,Cin] bf16 -> out [N,Ho,Wo,Cout] (or zero-dilated
     [N,2Ho,2Wo,Cout] when out_scatter == 2; `out` must then be pre-zeroed)."""
     lib = L.load()
@@ -76,7 +76,8 @@ def conv_gemm(x, w, stride=1, pad_lo=0, pad_hi=None, *, shift=None, residual=Non
     N, H, W_, Cin = x.shape
     Cout, R, S, _ = w.shape
     pad_hi = pad_lo if pad_hi is None else pad_hi
-    Ho, Wo = conv_out_hw(H, W_, R, S, stride, pad_lo, pad_hi, dil)
+    Ho = conv_out_hw(H, W_, R, S, stride, pad_lo, pad_hi, dil)[0]
+    Wo = conv_out_hw(H, W_, R, S, stride, pad_lo, pad_hi if pad_hi_w < 0 else pad_hi_w, dil)[1]
     odt = torch.float32 if out_f32 else bf16
     if out is None:
         if out_scatter == 2:
@@ -91,10 +92,11 @@ def conv_gemm(x, w, stride=1, pad_lo=0, pad_hi=None, *, shift=None, residual=Non
     d.colsum = L.ptr(colsum)
     if shift is not None:
         _cuda(shift, torch.float32, "shift"); _req(shift.numel() == Cout, "bad shape")
+    n_in = N * Ho * Wo * Cout * (4 if scatter_inputs else 1)
     if residual is not None:
-        _cuda(residual, bf16, "residual"); _req(residual.numel() == N * Ho * Wo * Cout, "bad shape")
+        _cuda(residual, bf16, "residual"); _req(residual.numel() == n_in, "bad shape")
     if mask_src is not None:
-        _cuda(mask_src, bf16, "mask_src"); _req(mask_src.numel() == N * Ho * Wo * Cout, "bad shape")
+        _cuda(mask_src, bf16, "mask_src"); _req(mask_src.numel() == n_in, "bad shape")
     if colsum is not None:
         _cuda(colsum, torch.float32, "colsum"); _req(colsum.numel() == Cout, "bad shape")
     if out2 is not None:
@@ -103,7 +105,9 @@ def conv_gemm(x, w, stride=1, pad_lo=0, pad_hi=None, *, shift=None, residual=Non
     d.stride, d.dil, d.pad_lo, d.pad_hi = stride, dil, pad_lo, pad_hi
     d.ldc = d.ldr = d.ldm = d.out2_ld = Cout
     d.out_scatter = out_scatter
-    d.flags = (L.EPI_RELU if relu else 0) | (L.EPI_OUT_F32 if out_f32 else 0)
+    d.flags = (L.EPI_RELU if relu else 0) | (L.EPI_OUT_F32 if out_f32 else 0) | \
+        (L.EPI_SCATTER_INPUTS if scatter_inputs else 0)
+    d.pad_hi_w, d.scatter_off_h, d.scatter_off_w = pad_hi_w, scatter_off[0], scatter_off[1]
     d.tile_n, d.max_ctas, d.algo = tile_n, max_ctas, algo
     with _Prof("igemm", (N, H, W_, Cin, Cout, R, stride)):
         L.check(lib.vdqn_conv_gemm(C.byref(d), L.stream_ptr()), "conv_gemm")
@@ -149,7 +153,7 @@ def wgrad_finalize(part, w, dw, *, splits, Cout, Cin, R, S, K, kmap=0, gamma=Non
 
 
 def weight_prep(w, w_fwd, shift, *, w_dgrad=None, gamma=None, beta=None, mean=None, var=None,
-                bias=None, kmap=0, eps=1e-5):
+                bias=None, kmap=0, eps=1e-5, dgrad_parity=False):
     """w OIHW fp32 -> w_fwd bf16 [Cout, K] (+ w_dgrad bf16 [Cin, R*S*Cout]) and shift [Cout]."""
     lib = L.load()
     _cuda(w, torch.float32, "w")
@@ -161,6 +165,7 @@ def weight_prep(w, w_fwd, shift, *, w_dgrad=None, gamma=None, beta=None, mean=No
                                               L.ptr(bias))
     d.Cout, d.Cin, d.R, d.S, d.K, d.kmap = Cout, Cin, R, S, K, kmap
     d.eps = eps
+    d.dgrad_parity = int(dgrad_parity)
     L.check(lib.vdqn_weight_prep(C.byref(d), L.stream_ptr()), "weight_prep")
 
 
