@@ -214,18 +214,22 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const bool valid = m < a.M_total;
       if (Cfg::FAST_EPI && a.fast) {
         const int row0 = m_t * Cfg::BM + quad * 32;            // this warp's 32 output rows
-        if (has_in) {
+        // residual / mask tiles are prefetched one tile ahead (see halo_conv.cu)
+        auto issue_inputs = [&](int tt) {
+          const int nn_t = tt % a.num_n_tiles, mm_t = tt / a.num_n_tiles;
+          const int r0 = mm_t * Cfg::BM + quad * 32;
           if (elect_one()) {
             mbar_expect_tx(ld_bar, Cfg::GROUPS * ((has_res ? 4096u : 0u) + (has_mask ? 4096u : 0u)));
 #pragma unroll
             for (int gidx = 0; gidx < Cfg::GROUPS; ++gidx) {
-              const int col = n_t * BN + gidx * 64;
-              if (has_res) tma_load_2d(stg_in + gidx * 4096, &tmRes, ld_bar, col, row0);
-              if (has_mask) tma_load_2d(stg_in + (Cfg::GROUPS + gidx) * 4096, &tmMask, ld_bar, col, row0);
+              const int col = nn_t * BN + gidx * 64;
+              if (has_res) tma_load_2d(stg_in + gidx * 4096, &tmRes, ld_bar, col, r0);
+              if (has_mask) tma_load_2d(stg_in + (Cfg::GROUPS + gidx) * 4096, &tmMask, ld_bar, col, r0);
             }
           }
           __syncwarp();
-        }
+        };
+        if (has_in && it == 0) issue_inputs(t);
         mbar_wait(tfull_bar(acc), acc_phase);
         tc_fence_after();
         const uint32_t stg = stg_out_base + (uint32_t)((it % Cfg::OUT_BUFS) * Cfg::GROUPS) * 4096u;
@@ -248,6 +252,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar(acc));
+        if (has_in) {
+          ld_parity ^= 1;
+          if (t + (int)gridDim.x < num_tiles) issue_inputs(t + gridDim.x);
+        }
         fence_proxy_async();
         __syncwarp();
         if (elect_one()) {
@@ -257,7 +265,6 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           tma_store_commit();
         }
         __syncwarp();
-        if (has_in) ld_parity ^= 1;
         continue;
       }
       long opix = m;

@@ -234,15 +234,20 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       const bool valid = h < a.H && w < a.W;
       const long opix = ((long)n * a.H + h) * a.W + w;
       if (a.fast) {
-        // this warp's 32 pixels = image rows h0+4*quad .. +3, 8 pixels each: a [1][4][8][64] TMA box
-        if (has_in) {
+        // this warp's 32 pixels = image rows h0+4*quad .. +3, 8 pixels each: a [1][4][8][64] TMA box.
+        // Residual / mask tiles are prefetched ONE TILE AHEAD (issued as soon as the previous tile has
+        // consumed the staging tiles), so their L2/HBM latency hides behind a whole tile of work.
+        auto issue_inputs = [&](int tt) {
+          int nn, hh0, ww0;
+          decode(tt, nn, hh0, ww0);
           if (elect_one()) {
             mbar_expect_tx(ld_bar, (has_res ? 4096u : 0u) + (has_mask ? 4096u : 0u));
-            if (has_res) tma_load_4d(stg_res, &tmRes, ld_bar, 0, w0, h0 + 4 * quad, n);
-            if (has_mask) tma_load_4d(stg_mask, &tmMask, ld_bar, 0, w0, h0 + 4 * quad, n);
+            if (has_res) tma_load_4d(stg_res, &tmRes, ld_bar, 0, ww0, hh0 + 4 * quad, nn);
+            if (has_mask) tma_load_4d(stg_mask, &tmMask, ld_bar, 0, ww0, hh0 + 4 * quad, nn);
           }
           __syncwarp();
-        }
+        };
+        if (has_in && it == 0) issue_inputs(t);
         mbar_wait(tfull_bar(acc), acc_phase);
         tc_fence_after();
         const uint32_t stg_out = stg_out0 + (uint32_t)(it & 1) * 4096u;
@@ -260,6 +265,10 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar(acc));
+        if (has_in) {
+          ld_parity ^= 1;
+          if (t + (int)gridDim.x < a.num_tiles) issue_inputs(t + gridDim.x);   // staging tiles are free again
+        }
         fence_proxy_async();
         __syncwarp();
         if (elect_one()) {
@@ -267,7 +276,6 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           tma_store_commit();
         }
         __syncwarp();
-        if (has_in) ld_parity ^= 1;
         continue;
       }
       mbar_wait(tfull_bar(acc), acc_phase);
