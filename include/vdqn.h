@@ -147,6 +147,11 @@ int vdqn_weight_prep(const vdqn_wprep_desc* d, void* stream);
  * Cout*K of tensors before t; total = sum over all). */
 int vdqn_weight_prep_multi(const vdqn_wprep_desc* descs_dev, const int64_t* offsets_dev, int32_t n,
                            int64_t total, void* stream);
+/* Tiled variant (coalesced reads and writes through a shared-memory transpose) for tensors with
+ * kmap == 0, Cin % 32 == 0, Cout % 32 == 0 and R*S <= 9: one block per 32x32 channel tile;
+ * tile_offsets_dev[t] = first block of tensor t (device array), total_tiles = number of blocks. */
+int vdqn_weight_prep_tiled(const vdqn_wprep_desc* descs_dev, const int32_t* tile_offsets_dev, int32_t n,
+                           int32_t total_tiles, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Input staging: NCHW fp32 (dataloaders/q_learning_real.py:75-76 output) or uint8 HWC

@@ -61,6 +61,7 @@ EXPORTS = {
     "vdqn_wgrad_finalize": (c_int, [C.POINTER(WgradFinDesc), c_void_p]),
     "vdqn_weight_prep": (c_int, [C.POINTER(WprepDesc), c_void_p]),
     "vdqn_weight_prep_multi": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_void_p]),
+    "vdqn_weight_prep_tiled": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "vdqn_stem_pack_f32": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "vdqn_stem_pack_u8": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "vdqn_maxpool_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),

@@ -81,6 +81,70 @@ __global__ void weight_prep_multi_kernel(const vdqn_wprep_desc* __restrict__ des
   }
 }
 
+// Tiled variant for the regular (r,s,ci) layout: one block = 32 output x 32 input channels x all taps
+// of one tensor.  OIHW is read as contiguous runs of 32*R*S floats per output channel, transposed in
+// shared memory, and both bf16 layouts are written with the fastest index contiguous.
+// `tile_offsets[t]` = first block of tensor t.
+__global__ void __launch_bounds__(256)
+weight_prep_tiled_kernel(const vdqn_wprep_desc* __restrict__ descs, const int* __restrict__ tile_offsets, int n) {
+  __shared__ float sw[32][32 * 9 + 1];
+  __shared__ float sscale[32];
+  int lo = 0, hi = n - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (tile_offsets[mid] <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const vdqn_wprep_desc d = descs[lo];
+  const int b = blockIdx.x - tile_offsets[lo];
+  const int ci_tiles = d.Cin / 32;
+  const int co0 = (b / ci_tiles) * 32, ci0 = (b % ci_tiles) * 32;
+  const int RS = d.R * d.S, run = 32 * RS;
+  if (threadIdx.x < 32) {
+    const int co = co0 + threadIdx.x;
+    float scale = 1.f;
+    if (d.gamma != nullptr) scale = d.gamma[co] * (1.0f / sqrtf(d.var[co] + d.eps));
+    sscale[threadIdx.x] = scale;
+    if (ci0 == 0) {
+      float sh = 0.f;
+      if (d.gamma != nullptr) sh = d.beta[co] - d.mean[co] * scale;
+      if (d.bias != nullptr) sh += d.bias[co];
+      d.shift[co] = sh;
+    }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < 32 * run; e += blockDim.x) {
+    const int col = e / run, j = e - col * run;                 // j = cil*RS + tap, contiguous in OIHW
+    sw[col][j] = d.w[((long)(co0 + col) * d.Cin + ci0) * RS + j] * sscale[col];
+  }
+  __syncthreads();
+  __nv_bfloat16* wf = static_cast<__nv_bfloat16*>(d.w_fwd);
+  for (int e = threadIdx.x; e < 32 * run; e += blockDim.x) {    // forward: [co][tap][ci], ci fastest
+    const int cil = e & 31, rest = e >> 5;
+    const int tap = rest % RS, col = rest / RS;
+    wf[(long)(co0 + col) * d.K + (long)tap * d.Cin + ci0 + cil] = __float2bfloat16_rn(sw[col][cil * RS + tap]);
+  }
+  if (d.w_dgrad != nullptr) {
+    __nv_bfloat16* wd = static_cast<__nv_bfloat16*>(d.w_dgrad);
+    for (int e = threadIdx.x; e < 32 * run; e += blockDim.x) {  // data gradient: co fastest
+      const int col = e & 31, rest = e >> 5;
+      const int tap = rest % RS, cil = rest / RS;
+      const int r = tap / d.S, sx = tap - r * d.S;
+      const int ci = ci0 + cil, co = co0 + col;
+      long di;
+      if (d.dgrad_parity) {
+        const int pa = (r == 1) ? 0 : 1, u = (r == 0) ? 1 : 0;
+        const int pb = (sx == 1) ? 0 : 1, v = (sx == 0) ? 1 : 0;
+        const int nb = 1 + pb, nt = (1 + pa) * nb;
+        const int cls_off = (pa == 0) ? (pb == 0 ? 0 : 1) : (pb == 0 ? 3 : 5);
+        di = (long)cls_off * d.Cin * d.Cout + (long)ci * (nt * d.Cout) + (long)(u * nb + v) * d.Cout + co;
+      } else {
+        di = (long)ci * (RS * d.Cout) + (long)((d.R - 1 - r) * d.S + (d.S - 1 - sx)) * d.Cout + co;
+      }
+      wd[di] = __float2bfloat16_rn(sw[col][cil * RS + tap]);
+    }
+  }
+}
+
 // grid = (K blocks of 256, Cout): thread = one (co, k).  The split partials are summed in a fixed
 // order (deterministic); d gamma is accumulated with one atomic per warp into a zeroed slot.
 __global__ void wgrad_finalize_kernel(const vdqn_wgrad_fin_desc d) {
@@ -599,6 +663,17 @@ extern "C" int vdqn_weight_prep_multi(const vdqn_wprep_desc* descs_dev, const in
   weight_prep_multi_kernel<<<grid_for(total, 256, dev->num_sms, 16), 256, 0, stream>>>(
       descs_dev, reinterpret_cast<const long long*>(offsets_dev), n, total);
   VDQN_CHECK_LAUNCH("weight_prep_multi");
+  return VDQN_OK;
+}
+
+extern "C" int vdqn_weight_prep_tiled(const vdqn_wprep_desc* descs_dev, const int32_t* tile_offsets_dev, int32_t n,
+                                      int32_t total_tiles, void* stream_v) {
+  if (descs_dev == nullptr || tile_offsets_dev == nullptr || n < 1)
+    return set_error(VDQN_ERR_ARG, "weight_prep_tiled: bad arguments");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  if (total_tiles == 0) return VDQN_OK;
+  weight_prep_tiled_kernel<<<total_tiles, 256, 0, stream>>>(descs_dev, tile_offsets_dev, n);
+  VDQN_CHECK_LAUNCH("weight_prep_tiled");
   return VDQN_OK;
 }
 

@@ -138,9 +138,11 @@ class PreparedWeights:
         sig = tuple(P[c.wkey].data_ptr() for c in self.plan.convs) + \
             tuple(P[c.bn + ".weight"].data_ptr() for c in self.plan.convs if c.bn)
         if getattr(self, "_table_sig", None) != sig:
-            descs = (L.WprepDesc * len(self.plan.convs))()
-            offs, total = [], 0
-            for d, c in zip(descs, self.plan.convs):
+            # the stem (space-to-depth packing) goes through the element-wise kernel, everything else
+            # through the tiled (coalesced) one
+            dev = self.shift["stem"].device
+
+            def fill(d, c):
                 w = P[c.wkey]
                 d.w, d.w_fwd, d.shift = w.data_ptr(), self.w_fwd[c.name].data_ptr(), self.shift[c.name].data_ptr()
                 d.w_dgrad = L.ptr(self.w_dgrad.get(c.name))
@@ -152,17 +154,35 @@ class PreparedWeights:
                 d.Cout, d.Cin, d.R, d.S = w.shape
                 d.K, d.kmap, d.eps = c.K, c.kmap, BN_EPS
                 d.dgrad_parity = int(c.kmap == 0 and c.stride == 2 and c.k == 3)
+
+            def upload(descs):
+                return torch.frombuffer(bytearray(bytes(descs)), dtype=torch.uint8).clone().to(dev)
+
+            elem = [c for c in self.plan.convs if c.kmap != 0]
+            tiled = [c for c in self.plan.convs if c.kmap == 0]
+            d_elem = (L.WprepDesc * len(elem))()
+            offs, total = [], 0
+            for d, c in zip(d_elem, elem):
+                fill(d, c)
                 offs.append(total)
                 total += c.cout * c.K
-            dev = self.shift["stem"].device
-            raw = torch.frombuffer(bytearray(bytes(descs)), dtype=torch.uint8).clone()
-            self._table = raw.to(dev)
-            self._offsets = torch.tensor(offs, dtype=torch.int64, device=dev)
-            self._total, self._table_sig = total, sig
+            d_tiled = (L.WprepDesc * len(tiled))()
+            toffs, tiles = [], 0
+            for d, c in zip(d_tiled, tiled):
+                fill(d, c)
+                toffs.append(tiles)
+                tiles += (c.cout // 32) * (c.cin // 32)
+            self._elem = (upload(d_elem), torch.tensor(offs, dtype=torch.int64, device=dev), len(elem), total)
+            self._tiled = (upload(d_tiled), torch.tensor(toffs, dtype=torch.int32, device=dev), len(tiled), tiles)
+            self._total, self._table_sig = total + sum(c.cout * c.K for c in tiled), sig
+        lib = L.load()
         with ops._Prof("weight_prep", (self._total,)):
-            L.check(L.load().vdqn_weight_prep_multi(self._table.data_ptr(), self._offsets.data_ptr(),
-                                                    len(self.plan.convs), self._total, L.stream_ptr()),
+            t, o, n, tot = self._elem
+            L.check(lib.vdqn_weight_prep_multi(t.data_ptr(), o.data_ptr(), n, tot, L.stream_ptr()),
                     "weight_prep_multi")
+            t, o, n, tot = self._tiled
+            L.check(lib.vdqn_weight_prep_tiled(t.data_ptr(), o.data_ptr(), n, tot, L.stream_ptr()),
+                    "weight_prep_tiled")
 
 
 # output-parity classes of a 3x3 stride-2 data gradient: (a, b, taps_h, taps_w, offset in taps)
