@@ -77,6 +77,12 @@ typedef struct vdqn_conv_desc {
   int32_t algo;        /* 0 = auto, 1 = im2col-TMA kernel, 2 = halo-tile kernel (Cout = 64 layers) */
   int32_t pad_hi_w;    /* upper padding along W when it differs from pad_hi (H); -1 = same */
   int32_t scatter_off_h, scatter_off_w; /* out_scatter == 2: opix = (n*2Ho + 2p + off_h)*2Wo + 2q + off_w */
+  /* Two networks in one launch (online + target forward): images [split_n, N) use w2 / shift2, the
+   * SMs are partitioned between the two image ranges in proportion to their tiles.  split_n == 0:
+   * off.  Requires split_n*Ho*Wo % 128 == 0 for the im2col kernel. */
+  const void* w2;
+  const float* shift2;
+  int32_t split_n;
 } vdqn_conv_desc;
 int vdqn_conv_gemm(const vdqn_conv_desc* d, void* stream);
 

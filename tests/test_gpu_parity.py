@@ -275,6 +275,31 @@ def test_batch_duplication_property_full_size():
     assert all(torch.isfinite(v).all() for v in g2.values())
 
 
+def test_one_pass_dual_network_forward_equals_two_passes():
+    """B % 64 == 0: online [s; s'] and target [s'] share one 3B pass (CTAs split between the two
+    weight sets).  Must give the same step as the 2B + B schedule (same kernels per tile)."""
+    from video_dqn_b200.learner import QLearner, StepConfig
+    dev = _dev()
+    sd = qstep.init_state(seed=4, randomize_bn=True)
+    sd_t = qstep.init_state(seed=5, randomize_bn=True)          # a DIFFERENT target network
+    batch = _to(qstep.synthetic_batch(64, seed=21), dev)
+    out = []
+    for one_pass in (True, False):
+        lr = QLearner(_build(sd, dev), _build(sd_t, dev), StepConfig(), batch_size=64, use_graph=False,
+                      one_pass=one_pass)
+        assert lr.one_pass == one_pass
+        loss = lr.step(batch)
+        torch.cuda.synchronize()
+        out.append((loss.item(), {n: g.clone() for n, g in lr.G.items()}, lr.y.clone(), lr.best.clone()))
+        del lr
+    (l1, g1, y1, b1), (l2, g2, y2, b2) = out
+    assert abs(l1 - l2) <= 1e-5 * abs(l2)
+    assert torch.equal(b1, b2) and (y1 - y2).abs().max().item() <= 1e-5
+    for n in g1:
+        e = (g1[n] - g2[n]).norm().item() / (g2[n].norm().item() + 1e-30)
+        assert e <= 3e-2, (n, e)
+
+
 def test_adam_and_target_sync_vs_oracle():
     from video_dqn_b200.optim import FusedAdam
     dev = _dev()

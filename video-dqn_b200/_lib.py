@@ -22,7 +22,8 @@ class ConvDesc(C.Structure):
                [(n, c_int) for n in ("N", "H", "W", "Cin", "Cout", "R", "S", "stride", "dil",
                                      "pad_lo", "pad_hi", "ldc", "ldr", "ldm", "out2_ld",
                                      "out_scatter", "flags", "tile_n", "max_ctas", "algo", "pad_hi_w",
-                                     "scatter_off_h", "scatter_off_w")]
+                                     "scatter_off_h", "scatter_off_w")] + \
+               [("w2", c_void_p), ("shift2", c_void_p), ("split_n", c_int)]
 
 
 class WgradDesc(C.Structure):

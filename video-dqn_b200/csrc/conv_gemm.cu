@@ -31,6 +31,10 @@ struct IgemmArgs {
   int off_h, off_w;
   int scatter_inputs; // residual / mask indexed by the scattered pixel
   int fast;           // staged TMA epilogue (BN <= 128, bf16 compact output)
+  // dual-network launch: m-tiles [split_m_tile, num_m_tiles) use the second weight set; CTAs
+  // [0, split_cta) work on the first range, the rest on the second (split_cta == 0: off)
+  int split_m_tile, split_cta;
+  const float* shift2;
 };
 
 template <int BN, int CK>
@@ -61,7 +65,7 @@ struct IgemmCfg {
 template <int BN, int CK>
 __global__ void __launch_bounds__(192, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-             const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
+             const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
              const __grid_constant__ CUtensorMap tmMask, const IgemmArgs a) {
   using Cfg = IgemmCfg<BN, CK>;
   extern __shared__ uint8_t smem_raw[];
@@ -106,7 +110,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  const int num_tiles = a.num_m_tiles * a.num_n_tiles;
+  // this CTA's slice of the tile space (whole launch, or one of the two networks' image ranges)
+  const bool second = a.split_cta > 0 && (int)blockIdx.x >= a.split_cta;
+  const int tile0 = (second ? a.split_m_tile * a.num_n_tiles : 0) + (int)blockIdx.x - (second ? a.split_cta : 0);
+  const int tstep = a.split_cta > 0 ? (second ? (int)gridDim.x - a.split_cta : a.split_cta) : (int)gridDim.x;
+  const int num_tiles = (a.split_cta > 0 && !second ? a.split_m_tile : a.num_m_tiles) * a.num_n_tiles;
+  const CUtensorMap* tmBp = second ? &tmB2 : &tmB;
   const int cblks = a.Cin / CK;
   const int num_sub = a.R * a.S * cblks;
   const int num_kb = num_sub / Cfg::KSUB;
@@ -116,7 +125,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     // ------------------------------------------------------------ TMA producer
     int stage = 0;
     uint32_t phase = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    for (int t = tile0; t < num_tiles; t += tstep) {
       const int n_t = t % a.num_n_tiles, m_t = t / a.num_n_tiles;
       const int m0 = m_t * Cfg::BM;
       const int img = m0 / HoWo;
@@ -137,7 +146,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             const int r = tap / a.S, s = tap - r * a.S;
             tma_load_im2col_4d(sA + sub * Cfg::A_SUB_BYTES, &tmA, full_bar(stage), c0, cw, ch, img,
                                (uint16_t)(s * a.dil), (uint16_t)(r * a.dil));
-            tma_load_2d(sB + sub * Cfg::B_SUB_BYTES, &tmB, full_bar(stage), j * CK, n_t * BN);
+            tma_load_2d(sB + sub * Cfg::B_SUB_BYTES, tmBp, full_bar(stage), j * CK, n_t * BN);
           }
         }
         __syncwarp();
@@ -150,7 +159,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+    for (int t = tile0; t < num_tiles; t += tstep, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(tempty_bar(acc), acc_phase ^ 1);
@@ -188,7 +197,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const uint32_t stg_in = epi_base + quad * Cfg::EPI_WARP_BYTES;
     const uint32_t stg_out_base = stg_in + 2 * Cfg::GROUPS * 4096;
     const uint32_t ld_bar = ld_bar0 + 8u * quad;
-    const bool has_res = a.epi.residual != nullptr, has_mask = a.epi.mask_src != nullptr;
+    EpiArgs epi = a.epi;
+    if (second) epi.shift = a.shift2;
+    const bool has_res = epi.residual != nullptr, has_mask = epi.mask_src != nullptr;
     const bool has_in = has_res || has_mask;
     uint32_t ld_parity = 0;
     float csum[BN / 32];                 // per-lane column sums of the current column tile
@@ -205,7 +216,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
     };
     int it = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+    for (int t = tile0; t < num_tiles; t += tstep, ++it) {
       const int n_t = t % a.num_n_tiles, m_t = t / a.num_n_tiles;
       if (n_t != cs_nt) { flush_colsum(); cs_nt = n_t; }
       const int acc = it & 1;
@@ -242,7 +253,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           tmem_ld_wait();
           if (chunk == 0 && has_in) mbar_wait(ld_bar, ld_parity);
           const int gidx = chunk >> 1;
-          const float cs = epilogue_half_staged(a.epi, raw, valid, n_t * BN + chunk * 32, chunk & 1, lane,
+          const float cs = epilogue_half_staged(epi, raw, valid, n_t * BN + chunk * 32, chunk & 1, lane,
                                                 stg + gidx * 4096, stg_in + gidx * 4096,
                                                 stg_in + (Cfg::GROUPS + gidx) * 4096);
 #pragma unroll
@@ -254,7 +265,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (lane == 0) mbar_arrive(tempty_bar(acc));
         if (has_in) {
           ld_parity ^= 1;
-          if (t + (int)gridDim.x < num_tiles) issue_inputs(t + gridDim.x);
+          if (t + tstep < num_tiles) issue_inputs(t + tstep);
         }
         fence_proxy_async();
         __syncwarp();
@@ -284,7 +295,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         uint32_t raw[32];
         tmem_ld_32x32(tmem_base + acc * BN + chunk * 32 + ((uint32_t)(quad * 32) << 16), raw);
         tmem_ld_wait();
-        const float cs = epilogue_chunk(a.epi, raw, valid, a.scatter_inputs ? opix : (long)m, opix, opix2,
+        const float cs = epilogue_chunk(epi, raw, valid, a.scatter_inputs ? opix : (long)m, opix, opix2,
                                         n_t * BN + chunk * 32, lane);
 #pragma unroll
         for (int i = 0; i < BN / 32; ++i)
@@ -312,8 +323,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 // ---------------------------------------------------------------------------- host side
 
 template <int BN, int CK>
-static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* epi_maps,
-                        const IgemmArgs& a, int num_sms, cudaStream_t stream) {
+static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmB2,
+                        const CUtensorMap* epi_maps, IgemmArgs& a, int num_sms, cudaStream_t stream) {
   using Cfg = IgemmCfg<BN, CK>;
   static bool attr_set = false;
   auto kfn = igemm_kernel<BN, CK>;
@@ -325,8 +336,17 @@ static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
     attr_set = true;
   }
   const int tiles = a.num_m_tiles * a.num_n_tiles;
-  const int grid = tiles < num_sms ? tiles : num_sms;
-  kfn<<<grid, 192, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, epi_maps[0], epi_maps[1], epi_maps[2], a);
+  int grid = tiles < num_sms ? tiles : num_sms;
+  if (a.split_m_tile > 0) {
+    // two image ranges (two weight sets): give each its share of the SMs
+    const int t0 = a.split_m_tile * a.num_n_tiles, t1 = tiles - t0;
+    if (t1 <= 0 || grid < 2) return set_error(VDQN_ERR_SHAPE, "conv_gemm: empty second image range");
+    int g0 = (int)((long)grid * t0 / tiles);
+    if (g0 < 1) g0 = 1;
+    if (g0 > grid - 1) g0 = grid - 1;
+    a.split_cta = g0;
+  }
+  kfn<<<grid, 192, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmB2, epi_maps[0], epi_maps[1], epi_maps[2], a);
   VDQN_CHECK_LAUNCH("igemm launch");
   return VDQN_OK;
 }
@@ -396,11 +416,21 @@ extern "C" int vdqn_conv_gemm(const vdqn_conv_desc* d, void* stream_v) {
       rc = make_tiled_map_2d(&epi_maps[2], d->mask_src, d->Cout, a.M_total, 64, 32, 128, d->ldm);
     if (rc != VDQN_OK) return rc;
   }
+  CUtensorMap tmB2 = tmB;
+  a.split_m_tile = 0; a.split_cta = 0; a.shift2 = d->shift2;
+  if (d->split_n > 0) {
+    const long split_m = (long)d->split_n * Ho * Wo;
+    if (d->w2 == nullptr || d->split_n >= d->N || split_m % 128 != 0)
+      return set_error(VDQN_ERR_SHAPE, "conv_gemm: dual-network launch needs w2 and split_n*Ho*Wo %% 128 == 0");
+    rc = make_tiled_map_2d(&tmB2, d->w2, (uint64_t)d->R * d->S * d->Cin, d->Cout, CK, BN, CK == 64 ? 128 : 32);
+    if (rc != VDQN_OK) return rc;
+    a.split_m_tile = (int)(split_m / 128);
+  }
   const int sms = d->max_ctas > 0 && d->max_ctas < dev->num_sms ? d->max_ctas : dev->num_sms;
-  if (CK == 16) return launch_igemm<64, 16>(tmA, tmB, epi_maps, a, sms, stream);
+  if (CK == 16) return launch_igemm<64, 16>(tmA, tmB, tmB2, epi_maps, a, sms, stream);
   switch (BN) {
-    case 64: return launch_igemm<64, 64>(tmA, tmB, epi_maps, a, sms, stream);
-    case 128: return launch_igemm<128, 64>(tmA, tmB, epi_maps, a, sms, stream);
-    default: return launch_igemm<256, 64>(tmA, tmB, epi_maps, a, sms, stream);
+    case 64: return launch_igemm<64, 64>(tmA, tmB, tmB2, epi_maps, a, sms, stream);
+    case 128: return launch_igemm<128, 64>(tmA, tmB, tmB2, epi_maps, a, sms, stream);
+    default: return launch_igemm<256, 64>(tmA, tmB, tmB2, epi_maps, a, sms, stream);
   }
 }

@@ -24,6 +24,10 @@ struct HaloArgs {
   int tiles_w, tiles_h, num_tiles;
   int fast;            // staged TMA epilogue (bf16 compact output)
   const __nv_bfloat16* x;   // input tensor (the 16-channel variant gathers it with cp.async)
+  // dual-network launch: tiles [split_tile, num_tiles) (images >= split_n) use the second filter;
+  // CTAs [0, split_cta) work on the first range, the rest on the second (split_cta == 0: off)
+  int split_tile, split_cta;
+  const float* shift2;
   EpiArgs epi;
 };
 
@@ -58,7 +62,7 @@ __device__ __forceinline__ void tma_load_tiled_4d(uint32_t dst, const void* tmap
 template <int CK>
 __global__ void __launch_bounds__(192, 1)
 halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
-                 const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
+                 const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
                  const __grid_constant__ CUtensorMap tmMask, const HaloArgs a) {
   using Cfg = HaloCfg<CK>;
   extern __shared__ uint8_t smem_raw[];
@@ -104,6 +108,12 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
+  const bool second = a.split_cta > 0 && (int)blockIdx.x >= a.split_cta;
+  const int tile0 = (second ? a.split_tile : 0) + (int)blockIdx.x - (second ? a.split_cta : 0);
+  const int tstep = a.split_cta > 0 ? (second ? (int)gridDim.x - a.split_cta : a.split_cta) : (int)gridDim.x;
+  const int tile_end = (a.split_cta > 0 && !second) ? a.split_tile : a.num_tiles;
+  const CUtensorMap* tmWp = second ? &tmW2 : &tmW;
+
   auto decode = [&](int t, int& n, int& h0, int& w0) {
     const int tw = t % a.tiles_w;
     const int r = t / a.tiles_w;
@@ -117,7 +127,7 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     // the filter: one [64 x CK] tile per tap, resident for the whole kernel
     if (elect_one()) {
       mbar_expect_tx(w_bar, taps * Cfg::W_TILE_BYTES);
-      for (int j = 0; j < taps; ++j) tma_load_2d(sW + j * Cfg::W_TILE_BYTES, &tmW, w_bar, j * CK, 0);
+      for (int j = 0; j < taps; ++j) tma_load_2d(sW + j * Cfg::W_TILE_BYTES, tmWp, w_bar, j * CK, 0);
     }
     __syncwarp();
     if constexpr (CK == 16) {
@@ -128,7 +138,7 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       constexpr int CHUNKS = Cfg::HALO_H * Cfg::HALO_W * 2;
       int stage = 0, done_stage = 0, issued = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
+      for (int t = tile0; t < tile_end; t += tstep) {
         int n, h0, w0;
         decode(t, n, h0, w0);
         mbar_wait(empty_bar(stage), phase ^ 1);
@@ -164,7 +174,7 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     } else {
         int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x) {
+      for (int t = tile0; t < tile_end; t += tstep) {
         int n, h0, w0;
         decode(t, n, h0, w0);
         mbar_wait(empty_bar(stage), phase ^ 1);
@@ -183,7 +193,7 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x, ++it) {
+    for (int t = tile0; t < tile_end; t += tstep, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(tempty_bar(acc), acc_phase ^ 1);
@@ -220,12 +230,14 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     const uint32_t stg_out0 = epi_base + quad * Cfg::EPI_WARP_BYTES;
     const uint32_t stg_res = stg_out0 + 8192, stg_mask = stg_out0 + 12288;
     const uint32_t ld_bar = ld_bar0 + 8u * quad;
-    const bool has_res = a.epi.residual != nullptr, has_mask = a.epi.mask_src != nullptr;
+    EpiArgs epi = a.epi;
+    if (second) epi.shift = a.shift2;
+    const bool has_res = epi.residual != nullptr, has_mask = epi.mask_src != nullptr;
     const bool has_in = has_res || has_mask;
     uint32_t ld_parity = 0;
     float csum[2] = {0.f, 0.f};          // per-lane column sums (channels lane, 32 + lane) over all tiles
     int it = 0;
-    for (int t = blockIdx.x; t < a.num_tiles; t += gridDim.x, ++it) {
+    for (int t = tile0; t < tile_end; t += tstep, ++it) {
       int n, h0, w0;
       decode(t, n, h0, w0);
       const int acc = it & 1;
@@ -259,7 +271,7 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           tmem_ld_32x32(tmem_base + acc * Cfg::BN + half * 32 + ((uint32_t)(quad * 32) << 16), raw);
           tmem_ld_wait();
           if (half == 0 && has_in) mbar_wait(ld_bar, ld_parity);
-          const float cs = epilogue_half_staged(a.epi, raw, valid, half * 32, half, lane, stg_out, stg_res, stg_mask);
+          const float cs = epilogue_half_staged(epi, raw, valid, half * 32, half, lane, stg_out, stg_res, stg_mask);
           if (half == 0) csum[0] += cs; else csum[1] += cs;
         }
         tc_fence_before();
@@ -267,7 +279,7 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         if (lane == 0) mbar_arrive(tempty_bar(acc));
         if (has_in) {
           ld_parity ^= 1;
-          if (t + (int)gridDim.x < a.num_tiles) issue_inputs(t + gridDim.x);   // staging tiles are free again
+          if (t + tstep < tile_end) issue_inputs(t + tstep);   // staging tiles are free again
         }
         fence_proxy_async();
         __syncwarp();
@@ -285,7 +297,7 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         uint32_t raw[32];
         tmem_ld_32x32(tmem_base + acc * Cfg::BN + chunk * 32 + ((uint32_t)(quad * 32) << 16), raw);
         tmem_ld_wait();
-        const float cs = epilogue_chunk(a.epi, raw, valid, opix, opix, 0, chunk * 32, lane);
+        const float cs = epilogue_chunk(epi, raw, valid, opix, opix, 0, chunk * 32, lane);
         if (chunk == 0) csum[0] += cs; else csum[1] += cs;
       }
       tc_fence_before();
@@ -352,7 +364,20 @@ static int launch_halo(const vdqn_conv_desc* d, cudaStream_t stream) {
   a.epi = make_epi_args(d);
   const int sms = d->max_ctas > 0 && d->max_ctas < dev->num_sms ? d->max_ctas : dev->num_sms;
   const int grid = a.num_tiles < sms ? a.num_tiles : sms;
-  kfn<<<grid, 192, Cfg::SMEM_BYTES, stream>>>(tmX, tmW, tmOut, tmRes, tmMask, a);
+  CUtensorMap tmW2 = tmW;
+  a.split_tile = 0; a.split_cta = 0; a.shift2 = d->shift2;
+  if (d->split_n > 0) {
+    if (d->w2 == nullptr || d->split_n >= d->N || grid < 2)
+      return set_error(VDQN_ERR_SHAPE, "halo_conv: bad dual-network launch");
+    rc = make_tiled_map_2d(&tmW2, d->w2, (uint64_t)d->R * d->S * d->Cin, d->Cout, CK, 64, CK == 64 ? 128 : 32);
+    if (rc != VDQN_OK) return rc;
+    a.split_tile = d->split_n * a.tiles_w * a.tiles_h;
+    int g0 = (int)((long)grid * a.split_tile / a.num_tiles);
+    if (g0 < 1) g0 = 1;
+    if (g0 > grid - 1) g0 = grid - 1;
+    a.split_cta = g0;
+  }
+  kfn<<<grid, 192, Cfg::SMEM_BYTES, stream>>>(tmX, tmW, tmW2, tmOut, tmRes, tmMask, a);
   VDQN_CHECK_LAUNCH("halo_conv launch");
   return VDQN_OK;
 }

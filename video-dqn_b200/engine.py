@@ -275,8 +275,10 @@ import os as _os
 TILE_N_WIDE = int(_os.environ.get("VDQN_TILE_N_WIDE", "0"))
 
 
-def _conv(W: PreparedWeights, c: ConvSpec, x, out, **kw):
+def _conv(W: PreparedWeights, c: ConvSpec, x, out, W2: Optional[PreparedWeights] = None, split: int = 0, **kw):
     tn = TILE_N_WIDE if c.cout >= 256 else 0
+    if W2 is not None:
+        kw.update(w2=W2.w_fwd[c.name], shift2=W2.shift[c.name], split_n=split)
     return ops.conv_gemm(x, W.w_fwd[c.name], c.stride, c.pad_lo, c.pad_hi, shift=W.shift[c.name],
                          out=out, tile_n=tn, **kw)
 
@@ -285,22 +287,38 @@ def forward(plan: NetPlan, W: PreparedWeights, P: Dict[str, torch.Tensor], ws: W
             frames: torch.Tensor) -> torch.Tensor:
     """frames: [n,3,224,224] fp32 NCHW (or [n,224,224,3] uint8) -> Q [B, classes*actions] fp32."""
     ops.stem_pack(frames, ws.xp)
-    _conv(W, plan.stem, ws.xp, ws.s, relu=True)
+    return forward_packed(plan, W, P, ws)
+
+
+def forward_packed(plan: NetPlan, W: PreparedWeights, P: Dict[str, torch.Tensor], ws: Workspace,
+                   W2: Optional[PreparedWeights] = None, P2: Optional[Dict[str, torch.Tensor]] = None,
+                   split: int = 0) -> torch.Tensor:
+    """Forward from the packed input ws.xp.  With (W2, P2, split) the frames [split, n) go through a
+    SECOND network (the target net) inside the same launches: every conv kernel partitions its CTAs
+    between the two image ranges, so online and target forwards share one pass (better SM filling
+    for the small late layers, a third fewer launches)."""
+    dual = dict(W2=W2, split=split) if W2 is not None else {}
+    _conv(W, plan.stem, ws.xp, ws.s, relu=True, **dual)
     ops.maxpool_fwd(ws.s, ws.p, ws.idx)
     x = ws.p
     for i, b in enumerate(plan.blocks):
-        _conv(W, b.conv1, x, ws.a1[i], relu=True)
+        _conv(W, b.conv1, x, ws.a1[i], relu=True, **dual)
         idn = x
         if b.ds is not None:
-            _conv(W, b.ds, x, ws.idn[i])
+            _conv(W, b.ds, x, ws.idn[i], **dual)
             idn = ws.idn[i]
-        _conv(W, b.conv2, ws.a1[i], ws.out[i], residual=idn, relu=True)
+        _conv(W, b.conv2, ws.a1[i], ws.out[i], residual=idn, relu=True, **dual)
         x = ws.out[i]
-    _conv(W, plan.head, x, ws.h, relu=True)
+    _conv(W, plan.head, x, ws.h, relu=True, **dual)
     ops.head_flatten_fwd(ws.h, ws.flat)
-    ops.linear_fwd(ws.flat, P["top.0.weight"], P["top.0.bias"], True, ws.z1)
-    ops.linear_fwd(ws.z1, P["top.2.weight"], P["top.2.bias"], True, ws.z2)
-    ops.linear_fwd(ws.z2, P["top.4.weight"], P["top.4.bias"], False, ws.q)
+    parts = [(P, slice(0, ws.flat.shape[0]))]
+    if W2 is not None:
+        bs = split // plan.num_frames
+        parts = [(P, slice(0, bs)), (P2, slice(bs, ws.flat.shape[0]))]
+    for Pn, rows in parts:
+        ops.linear_fwd(ws.flat[rows], Pn["top.0.weight"], Pn["top.0.bias"], True, ws.z1[rows])
+        ops.linear_fwd(ws.z1[rows], Pn["top.2.weight"], Pn["top.2.bias"], True, ws.z2[rows])
+        ops.linear_fwd(ws.z2[rows], Pn["top.4.weight"], Pn["top.4.bias"], False, ws.q[rows])
     return ws.q
 
 

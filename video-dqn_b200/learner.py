@@ -50,7 +50,7 @@ class QLearner:
     def __init__(self, model: HabitatDQNMultiAction, target_net: HabitatDQNMultiAction,
                  cfg: Optional[StepConfig] = None, batch_size: int = 16, *,
                  optimizer: Optional[FusedAdam] = None, frames_uint8: bool = False,
-                 use_graph: bool = True, grad_sync=None, world_size: int = 1):
+                 use_graph: bool = True, grad_sync=None, world_size: int = 1, one_pass: Optional[bool] = None):
         self.cfg = cfg or StepConfig()
         self.model, self.target_net = model, target_net
         self.B = batch_size
@@ -99,8 +99,11 @@ class QLearner:
         self.term = torch.zeros(batch_size, C, device=dev, dtype=torch.int64)
         self.valid = torch.ones(batch_size, C, device=dev, dtype=torch.int64)
         # ---- workspaces and step outputs
-        self.ws_train = E.Workspace(self.plan, 2 * n, dev, train=True, n_bwd=n)
-        self.ws_eval = E.Workspace(self.plan, n, dev, train=False)
+        # B*F % 64 == 0: online [s ; s'] and target [s'] share ONE 3B forward pass (every conv launch
+        # splits its CTAs between the two networks); otherwise a 2B online pass + a B target pass
+        self.one_pass = (n % 64 == 0) if one_pass is None else (bool(one_pass) and n % 64 == 0)
+        self.ws_train = E.Workspace(self.plan, (3 if self.one_pass else 2) * n, dev, train=True, n_bwd=n)
+        self.ws_eval = None if self.one_pass else E.Workspace(self.plan, n, dev, train=False)
         A = self.plan.action_dim
         self.dq = torch.empty(batch_size, C * A, device=dev, dtype=torch.float32)
         self.loss = torch.zeros(1, device=dev, dtype=torch.float32)
@@ -123,11 +126,20 @@ class QLearner:
         self.loss.zero_()
         # online net on [s ; s'] in one 2B forward (activations of the s half feed the backward),
         # target net on s' (nothing kept)
-        E.forward(plan, st.W, st.P, self.ws_train, self._frames(self.frames2))
-        E.forward(plan, tt.W, tt.P, self.ws_eval, self._frames(self.after))
         B = self.B
-        ops.td_epilogue(self.ws_train.q[:B].view(B, C, A), self.ws_train.q[B:].view(B, C, A),
-                        self.ws_eval.q.view(B, C, A), self.act, self.rew, self.term, self.valid,
+        wt = self.ws_train
+        if self.one_pass:
+            n = B * plan.num_frames
+            ops.stem_pack(self._frames(self.frames2), wt.xp[:2 * n])
+            wt.xp[2 * n:].copy_(wt.xp[n:2 * n])            # the target net sees s' too
+            E.forward_packed(plan, st.W, st.P, wt, W2=tt.W, P2=tt.P, split=2 * n)
+            q_nt = wt.q[2 * B:3 * B]
+        else:
+            E.forward(plan, st.W, st.P, wt, self._frames(self.frames2))
+            E.forward(plan, tt.W, tt.P, self.ws_eval, self._frames(self.after))
+            q_nt = self.ws_eval.q
+        ops.td_epilogue(wt.q[:B].view(B, C, A), wt.q[B:2 * B].view(B, C, A),
+                        q_nt.view(B, C, A), self.act, self.rew, self.term, self.valid,
                         gamma=cfg.GAMMA, double_dqn=cfg.double_dqn, clip_rect=(cfg.LOSS_CLIP == "rect"),
                         linear=cfg.LINEAR, use_valid=cfg.REMOVE_BEFORE_REWARD,
                         inv_count=1.0 / (B * C), dq=self.dq.view(B, C, A), loss=self.loss,

@@ -67,7 +67,8 @@ def conv_out_hw(H, W, R, S, stride, pad_lo, pad_hi, dil=1):
 
 def conv_gemm(x, w, stride=1, pad_lo=0, pad_hi=None, *, shift=None, residual=None, mask_src=None,
               relu=False, out_f32=False, colsum=None, out=None, out2=None, out_scatter=1,
-              tile_n=0, max_ctas=0, dil=1, algo=0, pad_hi_w=-1, scatter_off=(0, 0), scatter_inputs=False):
+              tile_n=0, max_ctas=0, dil=1, algo=0, pad_hi_w=-1, scatter_off=(0, 0), scatter_inputs=False,
+              w2=None, shift2=None, split_n=0):
     """x [N,H,W,Cin] bf16, w [Cout,R,S,Cin] bf16 -> out [N,Ho,Wo,Cout] (or zero-dilated
     [N,2Ho,2Wo,Cout] when out_scatter == 2; `out` must then be pre-zeroed)."""
     lib = L.load()
@@ -108,6 +109,9 @@ def conv_gemm(x, w, stride=1, pad_lo=0, pad_hi=None, *, shift=None, residual=Non
     d.flags = (L.EPI_RELU if relu else 0) | (L.EPI_OUT_F32 if out_f32 else 0) | \
         (L.EPI_SCATTER_INPUTS if scatter_inputs else 0)
     d.pad_hi_w, d.scatter_off_h, d.scatter_off_w = pad_hi_w, scatter_off[0], scatter_off[1]
+    if split_n:
+        _cuda(w2, bf16, "w2"); _req(w2.shape == w.shape and shift2 is not None, "bad shape")
+        d.w2, d.shift2, d.split_n = w2.data_ptr(), shift2.data_ptr(), split_n
     d.tile_n, d.max_ctas, d.algo = tile_n, max_ctas, algo
     with _Prof("igemm", (N, H, W_, Cin, Cout, R, stride)):
         L.check(lib.vdqn_conv_gemm(C.byref(d), L.stream_ptr()), "conv_gemm")
