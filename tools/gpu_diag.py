@@ -348,15 +348,18 @@ def wgrad_stem():
     x = torch.randn(N, 3, 224, 224, device="cuda", generator=g)
     dy = torch.randn(N, 112, 112, 64, device="cuda", generator=g).to(torch.bfloat16)
     xp = ops.stem_pack(x)
-    part = ops.conv_wgrad(xp, dy, 4, 4, 1, 2, 1, splits=5)
     w = torch.randn(64, 3, 7, 7, device="cuda", generator=g)
-    dw = torch.zeros_like(w)
-    ops.wgrad_finalize(part, w, dw, splits=5, Cout=64, Cin=16, R=4, S=4, K=256, kmap=1)
-    torch.cuda.synchronize()
     wz = torch.zeros(64, 3, 7, 7, device="cuda", requires_grad=True)
     y = F.conv2d(x.to(torch.bfloat16).float(), wz, None, 2, 3)
     (y * dy.float().permute(0, 3, 1, 2)).sum().backward()
-    return _report("wgrad_stem", dw.reshape(64, -1), wz.grad.reshape(64, -1), 2e-2)
+    ok = True
+    for algo, splits in ((1, 5), (2, 37)):
+        part = ops.conv_wgrad(xp, dy, 4, 4, 1, 2, 1, splits=splits, algo=algo)
+        dw = torch.zeros_like(w)
+        ops.wgrad_finalize(part, w, dw, splits=splits, Cout=64, Cin=16, R=4, S=4, K=256, kmap=1)
+        torch.cuda.synchronize()
+        ok &= _report(f"wgrad_stem_algo{algo}", dw.reshape(64, -1), wz.grad.reshape(64, -1), 2e-2)
+    return ok
 
 
 @case

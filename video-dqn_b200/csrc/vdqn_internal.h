@@ -42,6 +42,10 @@ int halo_conv_launch(const vdqn_conv_desc* d, cudaStream_t stream);
 bool halo_wgrad_supported(const vdqn_wgrad_desc* d);
 int halo_wgrad_launch(const vdqn_wgrad_desc* d, cudaStream_t stream);
 
+// halo_wgrad_stem.cu: packed-stem weight gradient; writes part[splits][64][256]
+bool halo_wgrad_stem_supported(const vdqn_wgrad_desc* d);
+int halo_wgrad_stem_launch(const vdqn_wgrad_desc* d, cudaStream_t stream);
+
 inline int ceil_div(long a, long b) { return (int)((a + b - 1) / b); }
 
 // every kernel launch of the library is counted (bench.py reports it as `gpu_launches`)

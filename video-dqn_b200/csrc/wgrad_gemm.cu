@@ -261,9 +261,9 @@ extern "C" int vdqn_conv_wgrad(const vdqn_wgrad_desc* d, void* stream_v) {
     return set_error(VDQN_ERR_SHAPE, "conv_wgrad: Cout=%d unsupported", d->Cout);
   if (d->splits < 1) return set_error(VDQN_ERR_ARG, "conv_wgrad: splits must be >= 1");
   if (d->algo == 2) {
-    if (!halo_wgrad_supported(d))
-      return set_error(VDQN_ERR_SHAPE, "conv_wgrad: halo algorithm requested for an unsupported shape");
-    return halo_wgrad_launch(d, stream);
+    if (halo_wgrad_supported(d)) return halo_wgrad_launch(d, stream);
+    if (halo_wgrad_stem_supported(d)) return halo_wgrad_stem_launch(d, stream);
+    return set_error(VDQN_ERR_SHAPE, "conv_wgrad: halo algorithm requested for an unsupported shape");
   }
   if (d->ldy % 8 != 0) return set_error(VDQN_ERR_SHAPE, "conv_wgrad: ldy must be a multiple of 8");
   const int Ho = (d->H + d->pad_lo + d->pad_hi - (d->R - 1) * d->dil - 1) / d->stride + 1;

@@ -98,7 +98,10 @@ def make_plan(action_dim: int, num_classes: int = 5, num_frames: int = 1) -> Net
 
 
 def wgrad_uses_halo(spec: ConvSpec) -> bool:
-    """64->64 3x3 stride-1 convolutions (layer1) take the halo-tile weight-gradient kernel."""
+    """64->64 3x3 stride-1 convolutions (layer1) and the packed stem take the halo-tile weight-gradient
+    kernels."""
+    if spec.kmap == 1:                       # packed stem
+        return True
     return (spec.kmap == 0 and spec.cin == 64 and spec.cout == 64 and spec.k == 3 and spec.stride == 1
             and spec.pad_lo == 1)
 
