@@ -120,6 +120,16 @@ def cpu_reference_arm(steps, warmup, batch, threads):
     return dt
 
 
+def make_config(world, B, graph):
+    return {"workload": "HabitatDQNMultiAction (extra_capacity, 1 frame, 3 actions) Double-DQN "
+                        "training step, synthetic quadruplets (BASELINE configs[1])",
+            "batch_per_gpu": B, "global_batch": world * B, "frame": "3x224x224",
+            "parallelism": f"dp{world}", "cuda_graph": graph,
+            "l2": "inputs rotate over 3 device-resident batches (231 MB) and the step streams "
+                  ">3 GB of activations: working set larger than the 126 MB L2",
+            "random_init_weights": True}
+
+
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -135,8 +145,8 @@ def run_reference(a):
         "steps": steps, "warmup": warmup, "ms_per_step": dt * 1e3, "steps_per_sec": 1.0 / dt,
         "quadruplets_per_sec": B / dt, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "HabitatDQNMultiAction Q-learning step, synthetic quadruplets, CPU fp32",
-                   "batch": B, "threads": threads},
+        "config": dict(make_config(a.gpus, BATCH_PER_GPU, False), cuda_graph=None, parallelism="cpu",
+                       sample=sample, threads=threads),
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -343,13 +353,7 @@ def main():
             "warmup": a.warmup, "ms_per_step": ms, "steps_per_sec": 1e3 / ms,
             "quadruplets_per_sec": world * B / (ms * 1e-3), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "HabitatDQNMultiAction (extra_capacity, 1 frame, 3 actions) Double-DQN "
-                                   "training step, synthetic quadruplets (BASELINE configs[1])",
-                       "batch_per_gpu": B, "global_batch": world * B, "frame": "3x224x224",
-                       "parallelism": f"dp{world}", "cuda_graph": not a.no_graph,
-                       "l2": "inputs rotate over 3 device-resident batches (231 MB) and the step streams "
-                             ">3 GB of activations: working set larger than the 126 MB L2",
-                       "random_init_weights": True},
+            "config": make_config(world, B, not a.no_graph),
             "tensor_pipe_frac_of_step": STEP_FLOP_PER_QUAD * B / (ms * 1e-3) / 1e12 / pk["bf16_tflops_sustained"],
             "step_tflops": STEP_FLOP_PER_QUAD * B / (ms * 1e-3) / 1e12,
             "loss": loss_dev,
