@@ -145,11 +145,35 @@ weight_prep_tiled_kernel(const vdqn_wprep_desc* __restrict__ descs, const int* _
   }
 }
 
-// grid = (K blocks of 256, Cout): thread = one (co, k).  The split partials are summed in a fixed
-// order (deterministic); d gamma is accumulated with one atomic per warp into a zeroed slot.
-__global__ void wgrad_finalize_kernel(const vdqn_wgrad_fin_desc d) {
+// grid = (K blocks of 64, Cout), block = 64 (k) x 4 (split lanes).  A thread sums the partials of the
+// splits s = ty, ty+4, ... for its (co, k) (4 independent loads in flight per iteration), the four
+// lanes are combined through shared memory in a fixed order (deterministic), lane 0 writes dW and
+// feeds d gamma (one atomic per warp into a zeroed slot).
+__global__ void __launch_bounds__(256)
+wgrad_finalize_kernel(const vdqn_wgrad_fin_desc d) {
+  __shared__ float red[4][64];
   const int co = blockIdx.y;
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int k = blockIdx.x * 64 + tx;
+  float g = 0.f;
+  if (k < d.K) {
+    const long plane = (long)d.Cout * d.K;
+    const float* p = d.part + (long)co * d.K + k;
+    float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;
+    int s = ty;
+    for (; s + 12 < d.splits; s += 16) {
+      g0 += p[(long)s * plane];
+      g1 += p[(long)(s + 4) * plane];
+      g2 += p[(long)(s + 8) * plane];
+      g3 += p[(long)(s + 12) * plane];
+    }
+    for (; s < d.splits; s += 4) g0 += p[(long)s * plane];
+    g = (g0 + g1) + (g2 + g3);
+  }
+  red[ty][tx] = g;
+  __syncthreads();
+  if (ty != 0) return;
+  g = (red[0][tx] + red[1][tx]) + (red[2][tx] + red[3][tx]);
   float rstd = 1.f, scale = 1.f;
   if (d.gamma != nullptr) {
     rstd = 1.0f / sqrtf(d.var[co] + d.eps);
@@ -157,18 +181,6 @@ __global__ void wgrad_finalize_kernel(const vdqn_wgrad_fin_desc d) {
   }
   float dot = 0.f;
   if (k < d.K) {
-    const long plane = (long)d.Cout * d.K;
-    const float* p = d.part + (long)co * d.K + k;
-    float g0 = 0.f, g1 = 0.f, g2 = 0.f, g3 = 0.f;      // fixed summation order: deterministic
-    int s = 0;
-    for (; s + 4 <= d.splits; s += 4) {
-      g0 += p[(long)s * plane];
-      g1 += p[(long)(s + 1) * plane];
-      g2 += p[(long)(s + 2) * plane];
-      g3 += p[(long)(s + 3) * plane];
-    }
-    for (; s < d.splits; ++s) g0 += p[(long)s * plane];
-    const float g = (g0 + g1) + (g2 + g3);
     int r, ss, ci;
     const int src = oihw_index(co, k, d.Cin, d.R, d.S, d.kmap, &r, &ss, &ci);
     if (src >= 0) {
@@ -178,9 +190,9 @@ __global__ void wgrad_finalize_kernel(const vdqn_wgrad_fin_desc d) {
   }
   if (d.dgamma != nullptr) {
     for (int off = 16; off; off >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, off);
-    if ((threadIdx.x & 31) == 0) {
+    if ((tx & 31) == 0) {
       float v = rstd * dot;
-      if (blockIdx.x == 0 && threadIdx.x == 0 && d.dbeta != nullptr) v -= rstd * d.mean[co] * d.dbeta[co];
+      if (blockIdx.x == 0 && tx == 0 && d.dbeta != nullptr) v -= rstd * d.mean[co] * d.dbeta[co];
       atomicAdd(d.dgamma + co, v);
     }
   }
@@ -682,7 +694,7 @@ extern "C" int vdqn_wgrad_finalize(const vdqn_wgrad_fin_desc* d, void* stream_v)
     return set_error(VDQN_ERR_ARG, "wgrad_finalize: null pointer");
   GET_DEV();
   (void)dev;
-  wgrad_finalize_kernel<<<dim3((d->K + 255) / 256, d->Cout), 256, 0, stream>>>(*d);
+  wgrad_finalize_kernel<<<dim3((d->K + 63) / 64, d->Cout), dim3(64, 4), 0, stream>>>(*d);
   VDQN_CHECK_LAUNCH("wgrad_finalize");
   return VDQN_OK;
 }

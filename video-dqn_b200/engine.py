@@ -16,13 +16,15 @@ from __future__ import annotations
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional
 
+import os as _os
+
 import torch
 
 from . import ops
 
 bf16 = torch.bfloat16
 BN_EPS = 1e-5
-NUM_SMS_TARGET_UNITS = 296          # ~2 waves of 148 SMs for the split-K weight gradient
+WGRAD_WAVES = int(_os.environ.get("VDQN_WGRAD_WAVES", "1"))   # work units per SM for the split weight gradient
 
 
 @dataclass
@@ -115,7 +117,8 @@ def wgrad_splits(spec: ConvSpec, n_img: int, sms: int = 0) -> int:
     per = 4 if spec.gemm_cin % 64 == 0 else 16
     slab = 64 if spec.gemm_cin % 64 == 0 else 16
     groups = -(-(spec.K // slab) // per)
-    s = max(1, round(NUM_SMS_TARGET_UNITS / (co_tiles * groups)))
+    # every extra split costs a Cout x K fp32 partial written and re-read: one wave of units, no more
+    s = max(1, (WGRAD_WAVES * (sms or ops.num_sms())) // (co_tiles * groups))
     return int(max(1, min(s, M // 512 if M >= 512 else 1)))
 
 
