@@ -228,6 +228,39 @@ def halo_speed():
 
 
 @case
+def halo_probe_speed():
+    """where does the stem halo kernel spend its time?  (a) normal, (b) output store skipped"""
+    torch, F, ops = _imports()
+    from video_dqn_b200 import _lib as L
+    import ctypes as C
+    g = torch.Generator(device="cuda").manual_seed(0)
+    res = {}
+    for name, shp, wshp, pads in (("stem", (256, 112, 112, 16), (64, 4, 4, 16), (2, 1)),
+                                   ("layer1", (256, 56, 56, 64), (64, 3, 3, 64), (1, 1))):
+        x = torch.randn(*shp, device="cuda", generator=g).to(torch.bfloat16)
+        w = (torch.randn(*wshp, device="cuda", generator=g) * 0.05).to(torch.bfloat16)
+        out = torch.empty(shp[0], shp[1], shp[2], 64, device="cuda", dtype=torch.bfloat16)
+        for flags in (1, 1 | 8, 1 | 16, 1 | 8 | 32, 1 | 8 | 16 | 32):
+            d = L.ConvDesc()
+            d.x, d.w, d.out = x.data_ptr(), w.data_ptr(), out.data_ptr()
+            d.N, d.H, d.W, d.Cin, d.Cout, d.R, d.S = shp[0], shp[1], shp[2], shp[3], 64, wshp[1], wshp[2]
+            d.stride, d.dil, d.pad_lo, d.pad_hi = 1, 1, pads[0], pads[1]
+            d.ldc = d.ldr = d.ldm = d.out2_ld = 64
+            d.out_scatter, d.flags, d.algo, d.pad_hi_w = 1, flags, 2, -1
+            lib = L.load()
+            for _ in range(3):
+                L.check(lib.vdqn_conv_gemm(C.byref(d), L.stream_ptr()))
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            for _ in range(10):
+                L.check(lib.vdqn_conv_gemm(C.byref(d), L.stream_ptr()))
+            e.record(); torch.cuda.synchronize()
+            res[f"{name}_flags{flags}_us"] = s.elapsed_time(e) * 100
+    print(json.dumps(res))
+    return True
+
+
+@case
 def stem_s2d():
     torch, F, ops = _imports()
     g = torch.Generator(device="cuda").manual_seed(2)

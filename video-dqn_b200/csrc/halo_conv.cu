@@ -60,7 +60,7 @@ __device__ __forceinline__ void tma_load_tiled_4d(uint32_t dst, const void* tmap
 }
 
 template <int CK>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(288, 1)
 halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                  const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
                  const __grid_constant__ CUtensorMap tmMask, const HaloArgs a) {
@@ -99,7 +99,9 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     for (int i = 0; i < 4; ++i) mbar_init(ld_bar0 + 8u * i, 1);
     fence_mbar_init();
   }
-  if (warp == 1) {
+  // warps 0-3: producers (the cp.async variant uses all four, the TMA variant only warp 0),
+  // warp 4: MMA issuer + TMEM owner, warps 5-8: epilogue (TMEM lane quadrant = warp & 3)
+  if (warp == 4) {
     tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
     tmem_relinquish();
   }
@@ -123,56 +125,71 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     w0 = tw * Cfg::TW;
   };
 
-  if (warp == 0) {
+  if (warp < 4) {
     // the filter: one [64 x CK] tile per tap, resident for the whole kernel
-    if (elect_one()) {
-      mbar_expect_tx(w_bar, taps * Cfg::W_TILE_BYTES);
-      for (int j = 0; j < taps; ++j) tma_load_2d(sW + j * Cfg::W_TILE_BYTES, tmWp, w_bar, j * CK, 0);
+    if (warp == 0) {
+      if (elect_one()) {
+        mbar_expect_tx(w_bar, taps * Cfg::W_TILE_BYTES);
+        for (int j = 0; j < taps; ++j) tma_load_2d(sW + j * Cfg::W_TILE_BYTES, tmWp, w_bar, j * CK, 0);
+      }
+      __syncwarp();
     }
-    __syncwarp();
     if constexpr (CK == 16) {
-      // 32-byte pixel rows are slow through the TMA unit (one request per row); the whole warp
-      // gathers the 19 x 11 x 32 B window with 16-byte cp.async instead (zero-fill = padding),
-      // writing the 32B-swizzled layout the MMA descriptors expect.  Up to DEPTH tiles in flight.
-      constexpr int DEPTH = 4;
+      // 32-byte pixel rows are slow through the TMA unit (one request per row) and a single warp
+      // gathering them with cp.async is issue-bound (measured: 133 us of the 190 us stem kernel with
+      // everything else switched off), so FOUR producer warps share the work: warp p gathers the
+      // 19 x 11 x 32 B windows of the CTA's tiles p, p+4, ... with 16-byte cp.async (zero-fill =
+      // padding) into the 32B-swizzled layout the MMA descriptors expect, DEPTH tiles in flight each.
+      constexpr int DEPTH = 2;
       constexpr int CHUNKS = Cfg::HALO_H * Cfg::HALO_W * 2;
-      int stage = 0, done_stage = 0, issued = 0;
-      uint32_t phase = 0;
-      for (int t = tile0; t < tile_end; t += tstep) {
+      constexpr int PER_LANE = (CHUNKS + 31) / 32;
+      // the chunk -> (window pixel, smem offset) map is the same for every tile: keep it in registers
+      uint32_t dst_off[PER_LANE], hywx[PER_LANE];
+#pragma unroll
+      for (int i = 0; i < PER_LANE; ++i) {
+        const int c = lane + 32 * i;
+        const int p = c >> 1, hf = c & 1;
+        const int hy = p / Cfg::HALO_W, wx = p - hy * Cfg::HALO_W;
+        dst_off[i] = (uint32_t)(p * 32) + ((uint32_t)(hf ^ ((p >> 2) & 1)) << 4);
+        hywx[i] = (c < CHUNKS) ? ((uint32_t)hy | ((uint32_t)wx << 8) | ((uint32_t)hf << 16)) : 0xffffffffu;
+      }
+      int issued = 0, done_k = warp;
+      int k = warp;
+      for (int t = tile0 + warp * tstep; t < tile_end; t += 4 * tstep, k += 4) {
         int n, h0, w0;
         decode(t, n, h0, w0);
-        mbar_wait(empty_bar(stage), phase ^ 1);
+        const int stage = k % Cfg::STAGES;
+        mbar_wait(empty_bar(stage), (((uint32_t)(k / Cfg::STAGES)) & 1u) ^ 1u);
         const uint32_t base = sA0 + stage * Cfg::STAGE_BYTES;
         const __nv_bfloat16* img = a.x + (long)n * a.H * a.W * 16;
-        for (int c = lane; c < CHUNKS; c += 32) {
-          const int p = c >> 1, hf = c & 1;
-          const int hy = p / Cfg::HALO_W, wx = p - hy * Cfg::HALO_W;
-          const int gh = h0 - a.pad_lo + hy, gw = w0 - a.pad_lo + wx;
-          const bool inb = gh >= 0 && gh < a.H && gw >= 0 && gw < a.W;
-          const __nv_bfloat16* src = inb ? img + ((long)gh * a.W + gw) * 16 + hf * 8 : a.x;
-          const uint32_t dst = base + p * 32 + ((uint32_t)(hf ^ ((p >> 2) & 1)) << 4);
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(inb ? 16 : 0)
+#pragma unroll
+        for (int i = 0; i < PER_LANE; ++i) {
+          if (hywx[i] == 0xffffffffu) continue;
+          const int gh = h0 - a.pad_lo + (int)(hywx[i] & 0xff), gw = w0 - a.pad_lo + (int)((hywx[i] >> 8) & 0xff);
+          const bool inb = (unsigned)gh < (unsigned)a.H && (unsigned)gw < (unsigned)a.W;
+          const __nv_bfloat16* src = inb ? img + ((long)gh * a.W + gw) * 16 + ((hywx[i] >> 16) & 1) * 8 : a.x;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(base + dst_off[i]), "l"(src),
+                       "r"(inb ? 16 : 0)
                        : "memory");
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
         ++issued;
-        if (issued >= DEPTH) {          // the oldest in-flight tile has landed: publish it
+        if (issued >= DEPTH) {          // this warp's oldest in-flight tile has landed: publish it
           asm volatile("cp.async.wait_group %0;" ::"n"(DEPTH - 1) : "memory");
           fence_proxy_async();
-          mbar_arrive(full_bar(done_stage));
-          if (++done_stage == Cfg::STAGES) done_stage = 0;
+          mbar_arrive(full_bar(done_k % Cfg::STAGES));
+          done_k += 4;
         }
-        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
       }
       asm volatile("cp.async.wait_group 0;" ::: "memory");
       fence_proxy_async();
       const int pending = issued < DEPTH - 1 ? issued : DEPTH - 1;
       for (int i = 0; i < pending; ++i) {
-        mbar_arrive(full_bar(done_stage));
-        if (++done_stage == Cfg::STAGES) done_stage = 0;
+        mbar_arrive(full_bar(done_k % Cfg::STAGES));
+        done_k += 4;
       }
-    } else {
-        int stage = 0;
+    } else if (warp == 0) {
+      int stage = 0;
       uint32_t phase = 0;
       for (int t = tile0; t < tile_end; t += tstep) {
         int n, h0, w0;
@@ -187,7 +204,7 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 4) {
     constexpr uint32_t idesc = make_idesc_bf16(128, Cfg::BN, 0, 0);
     mbar_wait(w_bar, 0);
     int stage = 0;
@@ -205,6 +222,7 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         // descriptors advance by compile-time constants: (tap row, tap col, k16 step)
         const uint64_t a0 = make_smem_desc(sA, 16, Cfg::HALO_W * Cfg::ROW_BYTES, Cfg::SWZ);
         const uint64_t b0 = make_smem_desc(sW, 16, 8 * Cfg::ROW_BYTES, Cfg::SWZ);
+        if (!(a.epi.flags & 16))        // flag 16: debug, skip the MMAs (bottleneck probing)
 #pragma unroll
         for (int r = 0; r < Cfg::R; ++r) {
 #pragma unroll
@@ -265,6 +283,7 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         const uint32_t stg_out = stg_out0 + (uint32_t)(it & 1) * 4096u;
         if (elect_one()) tma_store_wait_read<1>();      // the store from two tiles ago has left this buffer
         __syncwarp();
+        if (!(epi.flags & 32))          // flag 32: debug, skip the epilogue math (bottleneck probing)
 #pragma unroll 1
         for (int half = 0; half < 2; ++half) {
           uint32_t raw[32];
@@ -283,7 +302,7 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         }
         fence_proxy_async();
         __syncwarp();
-        if (elect_one()) {
+        if (elect_one() && !(epi.flags & 8)) {      // flag 8: debug, skip the store (bottleneck probing)
           tma_store_4d(&tmOut, stg_out, 0, w0, h0 + 4 * quad, n);
           tma_store_commit();
         }
@@ -316,7 +335,7 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 4) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
@@ -377,7 +396,7 @@ static int launch_halo(const vdqn_conv_desc* d, cudaStream_t stream) {
     if (g0 > grid - 1) g0 = grid - 1;
     a.split_cta = g0;
   }
-  kfn<<<grid, 192, Cfg::SMEM_BYTES, stream>>>(tmX, tmW, tmW2, tmOut, tmRes, tmMask, a);
+  kfn<<<grid, 288, Cfg::SMEM_BYTES, stream>>>(tmX, tmW, tmW2, tmOut, tmRes, tmMask, a);
   VDQN_CHECK_LAUNCH("halo_conv launch");
   return VDQN_OK;
 }
