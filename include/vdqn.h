@@ -33,6 +33,10 @@ extern "C" {
 #define VDQN_EPI_RELU 1     /* out = max(v, 0) */
 #define VDQN_EPI_OUT_F32 2  /* store fp32 instead of bf16 */
 #define VDQN_EPI_SCATTER_INPUTS 4 /* with out_scatter == 2: residual / mask_src are read at the scattered pixel too */
+/* debugging only (bottleneck probing of the halo kernel, tools/gpu_diag.py): results are wrong */
+#define VDQN_EPI_DEBUG_NO_STORE 8
+#define VDQN_EPI_DEBUG_NO_MMA 16
+#define VDQN_EPI_DEBUG_NO_MATH 32
 
 const char* vdqn_last_error(void);
 int vdqn_abi_version(void);
@@ -207,6 +211,11 @@ typedef struct vdqn_td_desc {
   int32_t double_dqn, clip_rect, linear, use_valid;
 } vdqn_td_desc;
 int vdqn_td_epilogue(const vdqn_td_desc* d, void* stream);
+
+/* value[r] = max_a q[r][a] and (optional) its first arg-max, r over B*C rows: the
+ * `model(images).max(2).values` of visualize_value.py:96-97 and `[0, class, :].max()` of
+ * evaluation/evaluate.py:110-114. */
+int vdqn_q_max(const float* q, float* value, int64_t* arg, int64_t rows, int32_t A, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Fused multi-tensor Adam (+ optional hard target-network sync in the same pass).

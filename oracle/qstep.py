@@ -88,7 +88,7 @@ def _feat_key(resnet_key: str) -> str:
     return f"features.{idx}.{rest}"
 
 
-def init_state(seed: int = 4, action_dim: int = 3, randomize_bn: bool = False
+def init_state(seed: int = 4, action_dim: int = 3, randomize_bn: bool = False, num_frames: int = 1
                ) -> Dict[str, torch.Tensor]:
     """Random-init weights with the distributions torchvision / torch.nn use
     (kaiming-normal fan_out convs, BN gamma=1 beta=0, default Linear/Conv2d
@@ -137,7 +137,7 @@ def init_state(seed: int = 4, action_dim: int = 3, randomize_bn: bool = False
     b8 = 1 / math.sqrt(512 * 9)
     sd["features.8.weight"] = uniform((64, 512, 3, 3), b8)
     sd["features.8.bias"] = uniform((64,), b8)
-    dims = [(1600, 512), (512, 256), (256, action_dim * NUM_CLASSES)]
+    dims = [(1600 * num_frames, 512), (512, 256), (256, action_dim * NUM_CLASSES)]
     for i, (fin, fout) in zip((0, 2, 4), dims):
         sd[f"top.{i}.weight"] = uniform((fout, fin), 1 / math.sqrt(fin))
         sd[f"top.{i}.bias"] = uniform((fout,), 1 / math.sqrt(fin))
@@ -177,14 +177,20 @@ def trunk_forward(sd: Dict[str, torch.Tensor], x: torch.Tensor) -> torch.Tensor:
 
 def q_forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, action_dim: int = 3
               ) -> torch.Tensor:
-    """Q[B, 5, A] for one frame per sample (num_frames == 1)."""
-    if x.dim() == 5:
-        if x.shape[1] != 1:
-            raise Exception("bad shape")
-        x = x[:, 0]
-    t = trunk_forward(sd, x)
-    h = F.relu(F.conv2d(t, sd["features.8.weight"], sd["features.8.bias"]))
-    h = h.flatten(1)                                   # NCHW flatten: c*25 + y*5 + x
+    """Q[B, 5, A].  `x` is [B,3,224,224] (one frame) or [B,F,3,224,224]; with F frames the per-frame
+    features are concatenated before the MLP (archs/HabitatDQNMultiAction.py:49-52) and
+    top.0 has 1600*F inputs."""
+    if x.dim() == 4:
+        x = x.unsqueeze(1)
+    nf = sd["top.0.weight"].shape[1] // 1600
+    if x.shape[1] != nf:
+        raise Exception("bad shape")
+    feats = []
+    for i in range(nf):
+        t = trunk_forward(sd, x[:, i])
+        hi = F.relu(F.conv2d(t, sd["features.8.weight"], sd["features.8.bias"]))
+        feats.append(hi.flatten(1))                    # NCHW flatten: c*25 + y*5 + x
+    h = torch.cat(feats, 1)
     h = F.relu(F.linear(h, sd["top.0.weight"], sd["top.0.bias"]))
     h = F.relu(F.linear(h, sd["top.2.weight"], sd["top.2.bias"]))
     q = F.linear(h, sd["top.4.weight"], sd["top.4.bias"])

@@ -300,6 +300,65 @@ def test_one_pass_dual_network_forward_equals_two_passes():
         assert e <= 3e-2, (n, e)
 
 
+def test_value_map_and_policy_scoring_runner():
+    """the forward-only callers.  Batch-32 value-map call (visualize_value.py:96-97) and
+    the batch-1 policy score on a uint8 HWC frame (evaluation/evaluate.py:110-114) through
+    QValueRunner (CUDA-graph replay), against the oracle on to_imgnet-normalised frames."""
+    from video_dqn_b200.inference import QValueRunner
+    dev = _dev()
+    sd = qstep.init_state(seed=4, randomize_bn=True)
+    m = _build(sd, dev)
+    m.eval()
+    u8 = qstep.synthetic_batch(32, seed=7, uint8=True)[0]
+    with torch.no_grad():
+        q_ref = qstep.q_forward(sd, qstep.to_imgnet(u8))
+    run = QValueRunner(m, 32, frames_uint8=True)
+    for _ in range(3):                                   # eager, capture, replay
+        q, value, best = run(u8.to(dev))
+    torch.cuda.synchronize()
+    assert (q.cpu() - q_ref).abs().max().item() <= Q_TOL
+    assert (value.cpu() - q_ref.max(2).values).abs().max().item() <= Q_TOL
+    top2 = q_ref.topk(2, dim=-1).values
+    clear = (top2[..., 0] - top2[..., 1]) > MARGIN
+    assert (best.cpu()[clear] == q_ref.argmax(-1)[clear]).all()
+    one = QValueRunner(m, 1, frames_uint8=True)
+    for _ in range(3):
+        s = one.score(u8[5].to(dev), class_index=2)
+    assert abs(s - q_ref[5, 2].max().item()) <= Q_TOL
+    # the module's own call text gives the same numbers
+    with torch.no_grad():
+        v_mod = m(u8.to(dev)).max(2).values
+    assert (v_mod - value).abs().max().item() <= 1e-5
+
+
+def test_panorama_four_frames_forward_and_grads():
+    """F = 4 (PANORAMA / PREVIOUS_IMAGES, archs/HabitatDQNMultiAction.py:16-19,49-52): the frames are
+    folded into the batch dimension and concatenated before the MLP."""
+    from video_dqn_b200.qnet import HabitatDQNMultiAction
+    dev = _dev()
+    sd = qstep.init_state(seed=4, randomize_bn=True, num_frames=4)
+    m = HabitatDQNMultiAction(3, 5, extra_capacity=True, panorama=True)
+    m.load_state_dict(sd, strict=True)
+    m = m.to(dev)
+    m.set_train()
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(2, 4, 3, 224, 224, generator=g)
+    leaves = {n: sd[n].clone().requires_grad_(True) for n in qstep.grad_param_names()}
+    sdl = dict(sd); sdl.update(leaves); qstep.OracleTrainer._realias(sdl)
+    q_ref = qstep.q_forward(sdl, x)
+    w = torch.randn(2, 5, 3, generator=g)
+    (q_ref * w).sum().backward()
+    q = m(x.to(dev))
+    assert q.shape == (2, 5, 3)
+    assert (q.detach().cpu() - q_ref.detach()).abs().max().item() <= Q_TOL
+    (q * w.to(dev)).sum().backward()
+    got = {n: p.grad for n, p in m.named_parameters() if p.grad is not None}
+    ref = {n: leaves[n].grad for n in leaves}
+    _check_grads(got, ref, qstep.grad_param_names())
+    with pytest.raises(Exception, match="bad shape"):
+        m(x[:, :1].to(dev))
+
+
 def test_adam_and_target_sync_vs_oracle():
     from video_dqn_b200.optim import FusedAdam
     dev = _dev()

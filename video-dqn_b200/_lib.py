@@ -73,6 +73,7 @@ EXPORTS = {
     "vdqn_head_flatten_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "vdqn_head_flatten_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "vdqn_td_epilogue": (c_int, [C.POINTER(TdDesc), c_void_p]),
+    "vdqn_q_max": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "vdqn_adam_fused": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                                 C.c_double, C.c_double, C.c_double, C.c_double, c_int, c_float, c_void_p]),
     "vdqn_adam_fused_graph": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,

@@ -602,6 +602,21 @@ __global__ void td_epilogue_kernel(const vdqn_td_desc d) {
   }
 }
 
+// value[b,c] = max_a q[b,c,a] (+ first arg-max): the `model(images).max(2)` of the value-map / policy
+// callers (visualize_value.py:96-97, evaluation/evaluate.py:110-114)
+__global__ void q_max_kernel(const float* __restrict__ q, float* __restrict__ value, int64_t* __restrict__ arg,
+                             long total, int A) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const float* p = q + i * A;
+    float bv = p[0];
+    int best = 0;
+    for (int a = 1; a < A; ++a)
+      if (p[a] > bv) { bv = p[a]; best = a; }
+    value[i] = bv;
+    if (arg != nullptr) arg[i] = best;
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // fused Adam (+ target sync), flat fp32 arenas, 16-byte vectors
 __global__ void __launch_bounds__(256)
@@ -866,6 +881,16 @@ static int adam_check(const float* p, const float* g, const float* m, const floa
   if ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
        reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(target)) & 15)
     return set_error(VDQN_ERR_ARG, "adam: arenas must be 16-byte aligned");
+  return VDQN_OK;
+}
+
+extern "C" int vdqn_q_max(const float* q, float* value, int64_t* arg, int64_t rows, int32_t A, void* stream_v) {
+  if (q == nullptr || value == nullptr) return set_error(VDQN_ERR_ARG, "q_max: null pointer");
+  if (A < 1 || rows < 0) return set_error(VDQN_ERR_SHAPE, "q_max: bad shape");
+  GET_DEV();
+  if (rows == 0) return VDQN_OK;
+  q_max_kernel<<<grid_for(rows, 256, dev->num_sms), 256, 0, stream>>>(q, value, arg, rows, A);
+  VDQN_CHECK_LAUNCH("q_max");
   return VDQN_OK;
 }
 

@@ -314,6 +314,20 @@ def td_epilogue(q_s, q_next_online, q_next_target, act, rew, term, valid=None, *
     return loss, dq, best, y
 
 
+def q_max(q, value=None, arg=None, want_arg=False):
+    """q [B,C,A] fp32 -> value [B,C] = max over actions (and the first arg-max)."""
+    lib = L.load()
+    _cuda(q, torch.float32, "q")
+    _req(q.dim() == 3, "bad shape")
+    B, Cc, A = q.shape
+    if value is None:
+        value = torch.empty(B, Cc, device=q.device, dtype=torch.float32)
+    if want_arg and arg is None:
+        arg = torch.empty(B, Cc, device=q.device, dtype=torch.int64)
+    L.check(lib.vdqn_q_max(q.data_ptr(), value.data_ptr(), L.ptr(arg), B * Cc, A, L.stream_ptr()), "q_max")
+    return value, arg
+
+
 def adam_fused(p, g, m, v, *, lr, step=None, betas=(0.9, 0.999), eps=1e-8, target=None, grad_scale=1.0,
                step_dev=None, scalars_dev=None):
     """Fused Adam over flat fp32 arenas.  Either `step` (host int) or `step_dev` + `scalars_dev`
