@@ -164,6 +164,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--detail", action="store_true", help="also print per-shape conv timings to stderr")
+    ap.add_argument("--no-inference", action="store_true")
     a = ap.parse_args()
     if a.impl == "reference":
         return run_reference(a)
@@ -334,6 +335,36 @@ def main():
                "d2h_bytes_per_step": 4, "ms_per_step": dt * 1e3, "steps_per_sec": 1.0 / dt,
                "frames": "uint8 HWC (to_imgnet fused into the stem-pack kernel)"}
 
+    # ---------------- forward-only callers (BASELINE configs[3]): value-map batches of 32 views
+    # (visualize_value.py:78-98) and batch-1 policy scoring of a uint8 frame (evaluate.py:110-114)
+    inference = None
+    if rank == 0 and world == 1 and not a.no_inference:
+        from video_dqn_b200.inference import QValueRunner
+        model.eval()
+        inference = {}
+        for nb in (32, 1):
+            run = QValueRunner(model, nb, frames_uint8=True)
+            hostf = torch.empty(nb, 224, 224, 3, dtype=torch.uint8, pin_memory=True).random_(0, 256)
+            devf = hostf.to(dev)
+            for _ in range(5):
+                run(devf)
+            torch.cuda.synchronize()
+            iters = 200
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                run()
+            e1.record(); torch.cuda.synchronize()
+            dev_ms = e0.elapsed_time(e1) / iters
+            t0 = time.perf_counter()
+            for _ in range(iters):
+                _q, v, _b = run(hostf)                 # H2D of the uint8 views + forward
+                _ = v[0, 0].item()                      # D2H of the result, every call (evaluate.py:114)
+            host_ms = (time.perf_counter() - t0) / iters * 1e3
+            inference[f"batch{nb}"] = {"device_ms": dev_ms, "views_per_sec_device": nb / dev_ms * 1e3,
+                                       "e2e_ms": host_ms, "views_per_sec_e2e": nb / host_ms * 1e3}
+        model.set_train()
+
     # ---------------- CPU baseline (rank 0, N = 1): bounded sample of the same workload
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
@@ -361,6 +392,7 @@ def main():
             "gpu_launches_per_step": per_step_launches,
             "e2e": e2e, "roofline": roof, "roofline_kernels": roof_other, "cpu_baseline": cpu,
             "breakdown_eager_ms": breakdown if rank == 0 else None,
+            "inference": inference,
         }
         print(json.dumps(out))
     if world > 1:
