@@ -24,3 +24,13 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built_library():
+    """The C-ABI library is a build artefact (git-ignored): build it once per session if absent."""
+    so = os.path.join(ROOT, "video-dqn_b200", "libvdqn.so")
+    if not os.path.exists(so):
+        import subprocess
+        subprocess.check_call([sys.executable, os.path.join(ROOT, "video-dqn_b200", "build.py")])
+    yield
