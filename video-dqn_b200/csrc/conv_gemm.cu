@@ -54,9 +54,12 @@ struct IgemmCfg {
   static constexpr int EPI_BYTES = 4 * EPI_WARP_BYTES;
   static constexpr int PIPE_BUDGET = 224 * 1024 - EPI_BYTES;
   static constexpr int STAGES = PIPE_BUDGET / STAGE_BYTES > 8 ? 8 : PIPE_BUDGET / STAGE_BYTES;
-  static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128
-                                   : (2 * BN <= 256) ? 256 : 512;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  // accumulator ring over all 512 TMEM columns (8 / 4 / 2 accumulators for BN = 64 / 128 / 256): the
+  // MMA warp may run that many tiles ahead of the epilogue, which hides the mbarrier hand-off
+  // latencies that otherwise bound launches with few k-blocks per tile (1x1, parity-class convs)
+  static constexpr int NACC = 512 / BN;
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align*/ + 512 /*barriers*/;
   static constexpr uint64_t SWZ = (CK == 64) ? kSwz128 : kSwz32;
   static constexpr int ROW_BYTES = CK * 2;          // bytes per smem row (= swizzle span)
   static constexpr int SBO = 8 * ROW_BYTES;         // 8-row group pitch
@@ -76,9 +79,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
   auto tfull_bar = [&](int i) { return bar_base + 8u * (2 * Cfg::STAGES + i); };
-  auto tempty_bar = [&](int i) { return bar_base + 8u * (2 * Cfg::STAGES + 2 + i); };
-  const uint32_t ld_bar0 = bar_base + 8u * (2 * Cfg::STAGES + 4);     // one per epilogue warp
-  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 8);
+  auto tempty_bar = [&](int i) { return bar_base + 8u * (2 * Cfg::STAGES + Cfg::NACC + i); };
+  const uint32_t ld_bar0 = bar_base + 8u * (2 * Cfg::STAGES + 2 * Cfg::NACC);     // one per epilogue warp
+  const uint32_t tmem_slot = ld_bar0 + 8u * 4;
   uint32_t* tmem_slot_ptr =
       reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -94,7 +97,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < Cfg::NACC; ++i) {
       mbar_init(tfull_bar(i), 1);
       mbar_init(tempty_bar(i), 4);   // one arrive per epilogue warp
     }
@@ -160,8 +163,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     uint32_t phase = 0;
     int it = 0;
     for (int t = tile0; t < num_tiles; t += tstep, ++it) {
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
+      const int acc = it % Cfg::NACC;
+      const uint32_t acc_phase = (it / Cfg::NACC) & 1;
       mbar_wait(tempty_bar(acc), acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BN;
@@ -219,8 +222,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     for (int t = tile0; t < num_tiles; t += tstep, ++it) {
       const int n_t = t % a.num_n_tiles, m_t = t / a.num_n_tiles;
       if (n_t != cs_nt) { flush_colsum(); cs_nt = n_t; }
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
+      const int acc = it % Cfg::NACC;
+      const uint32_t acc_phase = (it / Cfg::NACC) & 1;
       const int m = m_t * Cfg::BM + row;
       const bool valid = m < a.M_total;
       if (Cfg::FAST_EPI && a.fast) {

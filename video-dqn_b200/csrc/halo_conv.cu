@@ -43,11 +43,14 @@ struct HaloCfg {
   static constexpr int STAGE_BYTES = (HALO_BYTES + 1023) / 1024 * 1024;
   static constexpr int W_TILE_BYTES = BN * ROW_BYTES;              // one tap: 64 rows x CK
   static constexpr int W_BYTES = MAX_TAPS * W_TILE_BYTES;          // 72 KB / 32 KB, resident
-  static constexpr int STAGES = (CK == 64) ? 3 : 12;
+  static constexpr int STAGES = (CK == 64) ? 3 : 16;
   static constexpr int EPI_WARP_BYTES = 4 * 4096;                  // out x2 (double-buffered), residual, mask
   static constexpr int EPI_BYTES = 4 * EPI_WARP_BYTES;
-  static constexpr int SMEM_BYTES = W_BYTES + STAGES * STAGE_BYTES + EPI_BYTES + 1024 + 256;
-  static constexpr int TMEM_COLS = 128;
+  static constexpr int SMEM_BYTES = W_BYTES + STAGES * STAGE_BYTES + EPI_BYTES + 1024 + 512;
+  // accumulator ring: with 64-column accumulators TMEM holds 4 of them, so the MMA warp can run up to
+  // 4 tiles ahead of the epilogue and the mbarrier hand-off latencies (MMA -> epilogue -> MMA) overlap
+  static constexpr int NACC = 4;
+  static constexpr int TMEM_COLS = NACC * BN;
 };
 
 __device__ __forceinline__ void tma_load_tiled_4d(uint32_t dst, const void* tmap, uint32_t bar, int c,
@@ -74,10 +77,10 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
   auto tfull_bar = [&](int i) { return bar_base + 8u * (2 * Cfg::STAGES + i); };
-  auto tempty_bar = [&](int i) { return bar_base + 8u * (2 * Cfg::STAGES + 2 + i); };
-  const uint32_t w_bar = bar_base + 8u * (2 * Cfg::STAGES + 4);
-  const uint32_t ld_bar0 = bar_base + 8u * (2 * Cfg::STAGES + 5);     // 4 barriers, one per epilogue warp
-  const uint32_t tmem_slot = bar_base + 8u * (2 * Cfg::STAGES + 9);
+  auto tempty_bar = [&](int i) { return bar_base + 8u * (2 * Cfg::STAGES + Cfg::NACC + i); };
+  const uint32_t w_bar = bar_base + 8u * (2 * Cfg::STAGES + 2 * Cfg::NACC);
+  const uint32_t ld_bar0 = w_bar + 8u;                                  // 4 barriers, one per epilogue warp
+  const uint32_t tmem_slot = w_bar + 8u * 5;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
@@ -91,7 +94,7 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       mbar_init(full_bar(s), CK == 16 ? 32 : 1);     // cp.async variant: every producer lane arrives
       mbar_init(empty_bar(s), 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < Cfg::NACC; ++i) {
       mbar_init(tfull_bar(i), 1);
       mbar_init(tempty_bar(i), 4);
     }
@@ -140,7 +143,9 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       // everything else switched off), so FOUR producer warps share the work: warp p gathers the
       // 19 x 11 x 32 B windows of the CTA's tiles p, p+4, ... with 16-byte cp.async (zero-fill =
       // padding) into the 32B-swizzled layout the MMA descriptors expect, DEPTH tiles in flight each.
-      constexpr int DEPTH = 2;
+      // each warp waits for the tile it issued DEPTH-1 iterations ago: with too few tiles in flight the
+      // loop period is the memory latency (measured: 84 us floor at DEPTH 2); 4 warps x 4 = all 16 stages
+      constexpr int DEPTH = 4;
       constexpr int CHUNKS = Cfg::HALO_H * Cfg::HALO_W * 2;
       constexpr int PER_LANE = (CHUNKS + 31) / 32;
       // the chunk -> (window pixel, smem offset) map is the same for every tile: keep it in registers
@@ -211,8 +216,8 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     uint32_t phase = 0;
     int it = 0;
     for (int t = tile0; t < tile_end; t += tstep, ++it) {
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
+      const int acc = it % Cfg::NACC;
+      const uint32_t acc_phase = (it / Cfg::NACC) & 1;
       mbar_wait(tempty_bar(acc), acc_phase ^ 1);
       mbar_wait(full_bar(stage), phase);
       tc_fence_after();
@@ -258,8 +263,8 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     for (int t = tile0; t < tile_end; t += tstep, ++it) {
       int n, h0, w0;
       decode(t, n, h0, w0);
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
+      const int acc = it % Cfg::NACC;
+      const uint32_t acc_phase = (it / Cfg::NACC) & 1;
       const int h = h0 + g, w = w0 + j;
       const bool valid = h < a.H && w < a.W;
       const long opix = ((long)n * a.H + h) * a.W + w;
