@@ -84,3 +84,19 @@ def test_bad_shape_raises():
     sd = qstep.init_state(seed=4)
     with pytest.raises(Exception, match="bad shape"):
         qstep.q_forward(sd, torch.zeros(1, 4, 3, 224, 224))
+
+
+def test_u8_normalisation_fma_is_exact():
+    """stem_pack_u8 evaluates fma(b, 1/(255 std), -mean/std) instead of ((b/255) - mean)/std
+    (util/torch.py:26-36).  Exhaustive over the 3 x 256 possible inputs: both round to the same
+    bf16, so the packed uint8 path is bit-identical to the reference normalisation."""
+    frame = torch.arange(256, dtype=torch.uint8).view(1, 256, 1, 1).repeat(1, 1, 1, 3)
+    ref = qstep.to_imgnet(frame)[0, :, :, 0].to(torch.bfloat16)              # [3, 256]
+    for c in range(3):
+        std, mean = np.float64(np.float32(qstep.IMAGENET_STD[c])), np.float64(np.float32(qstep.IMAGENET_MEAN[c]))
+        ka = np.float64(np.float32(1.0 / (255.0 * std)))
+        kb = np.float64(np.float32(-mean / std))
+        # b*ka + kb is exact in float64 (8 + 24 significant bits), so one rounding = fmaf
+        fma = (np.arange(256, dtype=np.float64) * ka + kb).astype(np.float32)
+        got = torch.from_numpy(fma).to(torch.bfloat16)
+        assert torch.equal(got, ref[c]), c

@@ -429,6 +429,40 @@ def prep_and_finalize():
 
 
 @case
+def finalize_rows():
+    """row-form finalize over the layer shapes of the network (splits as the engine picks them)"""
+    torch, F, ops = _imports()
+    g = torch.Generator(device="cuda").manual_seed(7)
+    ok = True
+    for Cout, Cin, R, splits, bn in ((64, 64, 3, 148, True), (128, 64, 3, 33, True), (128, 128, 3, 32, True),
+                                     (128, 64, 1, 40, True), (256, 256, 3, 8, True), (512, 512, 3, 2, True),
+                                     (64, 512, 3, 18, False), (512, 256, 1, 5, True), (64, 64, 3, 1, True),
+                                     (256, 128, 3, 7, True)):
+        K = R * R * Cin
+        w = torch.randn(Cout, Cin, R, R, device="cuda", generator=g)
+        part = torch.randn(splits, Cout, K, device="cuda", generator=g)
+        dw = torch.empty_like(w)
+        kw, scale = {}, torch.ones(Cout, device="cuda")
+        if bn:
+            gamma = torch.rand(Cout, device="cuda", generator=g) + 0.5
+            mean = torch.randn(Cout, device="cuda", generator=g)
+            var = torch.rand(Cout, device="cuda", generator=g) + 0.5
+            dbeta = torch.randn(Cout, device="cuda", generator=g)
+            dgamma = torch.zeros(Cout, device="cuda")
+            kw = dict(gamma=gamma, var=var, mean=mean, dbeta=dbeta, dgamma=dgamma)
+            scale = gamma / torch.sqrt(var + 1e-5)
+        ops.wgrad_finalize(part, w, dw, splits=splits, Cout=Cout, Cin=Cin, R=R, S=R, K=K, **kw)
+        gsum = part.double().sum(0).view(Cout, R, R, Cin).permute(0, 3, 1, 2)
+        tag = f"fin_rows[{Cout},{Cin},{R},s{splits}]"
+        ok &= _report(tag + ":dw", dw.reshape(Cout, -1), (gsum * scale.view(-1, 1, 1, 1)).float().reshape(Cout, -1), 1e-4)
+        if bn:
+            rstd = 1 / torch.sqrt(var + 1e-5)
+            dg_ref = rstd * ((w.double() * gsum).sum((1, 2, 3)).float() - mean * dbeta)
+            ok &= _report(tag + ":dgamma", dgamma[None], dg_ref[None], 1e-3)
+    return ok
+
+
+@case
 def maxpool():
     torch, F, ops = _imports()
     g = torch.Generator(device="cuda").manual_seed(5)

@@ -5,6 +5,7 @@
 
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <atomic>
 #include <mutex>
@@ -14,6 +15,14 @@ namespace vdqn {
 static thread_local char g_err[512] = "";
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("VDQN_PDL");
+    return e != nullptr && e[0] == '1';
+  }();
+  return on;
+}
 
 int set_error(int code, const char* fmt, ...) {
   va_list ap;

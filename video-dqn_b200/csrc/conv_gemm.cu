@@ -89,6 +89,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   // operands computed under it) on the uniform datapath
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -112,6 +113,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();      // the previous kernel's global writes are visible from here on
 
   // this CTA's slice of the tile space (whole launch, or one of the two networks' image ranges)
   const bool second = a.split_cta > 0 && (int)blockIdx.x >= a.split_cta;
@@ -349,7 +351,7 @@ static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
     if (g0 > grid - 1) g0 = grid - 1;
     a.split_cta = g0;
   }
-  kfn<<<grid, 192, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmB2, epi_maps[0], epi_maps[1], epi_maps[2], a);
+  launch_kernel(kfn, grid, 192, Cfg::SMEM_BYTES, stream, tmA, tmB, tmB2, epi_maps[0], epi_maps[1], epi_maps[2], a);
   VDQN_CHECK_LAUNCH("igemm launch");
   return VDQN_OK;
 }

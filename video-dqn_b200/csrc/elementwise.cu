@@ -2,6 +2,7 @@
 // weight-gradient finalisation, input packing, max-pool, the fp32 Q-head MLP, the fused TD
 // epilogue and the fused Adam + target-sync update.  All are plain coalesced / vectorised
 // grid-stride kernels; none is GEMM-shaped except the tiny fp32 MLP (0.95 MMAC per frame).
+#include "ptx.cuh"
 #include "vdqn_internal.h"
 
 #include <cuda_bf16.h>
@@ -63,6 +64,8 @@ __device__ __forceinline__ void weight_prep_element(const vdqn_wprep_desc& d, lo
 }
 
 __global__ void weight_prep_kernel(const vdqn_wprep_desc d) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long total = (long)d.Cout * d.K;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x)
     weight_prep_element(d, i);
@@ -71,6 +74,8 @@ __global__ void weight_prep_kernel(const vdqn_wprep_desc d) {
 // all convolutions of the network in one launch: `offsets[t]` = first flat element of tensor t
 __global__ void weight_prep_multi_kernel(const vdqn_wprep_desc* __restrict__ descs,
                                          const long long* __restrict__ offsets, int n, long total) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     int lo = 0, hi = n - 1;
     while (lo < hi) {
@@ -82,11 +87,63 @@ __global__ void weight_prep_multi_kernel(const vdqn_wprep_desc* __restrict__ des
 }
 
 // Tiled variant for the regular (r,s,ci) layout: one block = 32 output x 32 input channels x all taps
-// of one tensor.  OIHW is read as contiguous runs of 32*R*S floats per output channel, transposed in
-// shared memory, and both bf16 layouts are written with the fastest index contiguous.
-// `tile_offsets[t]` = first block of tensor t.
+// of one tensor.  OIHW is read as contiguous runs of 32*R*S floats per output channel (four
+// independent loads in flight per thread), transposed in shared memory, and both bf16 layouts are
+// written as bf16x2 pairs with the fastest index contiguous.  `tile_offsets[t]` = first block of
+// tensor t.  RS_T = R*S as a compile-time constant (0: generic).
+template <int RS_T>
+__device__ __forceinline__ void weight_prep_tile(const vdqn_wprep_desc& d, int co0, int ci0,
+                                                 float (*sw)[32 * 9 + 1], const float* sscale) {
+  const int RS = RS_T ? RS_T : d.R * d.S, run = 32 * RS;
+  const int tid = threadIdx.x;
+  const float* wbase = d.w + ((long)co0 * d.Cin + ci0) * RS;
+  const long co_pitch = (long)d.Cin * RS;
+  for (int e0 = 0; e0 < 32 * run; e0 += 1024) {               // 32*run is a multiple of 1024
+    float v[4];
+    int col[4], j[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = e0 + u * 256 + tid;
+      col[u] = e / run; j[u] = e - col[u] * run;                // j = cil*RS + tap, contiguous in OIHW
+      v[u] = __ldg(wbase + col[u] * co_pitch + j[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) sw[col[u]][j[u]] = v[u] * sscale[col[u]];
+  }
+  __syncthreads();
+  __nv_bfloat162* wf = reinterpret_cast<__nv_bfloat162*>(d.w_fwd);
+  for (int e = tid; e < 16 * run; e += 256) {                  // forward: [co][tap][ci], ci fastest
+    const int cil = (e & 15) * 2, rest = e >> 4;
+    const int c = rest / RS, tap = rest - c * RS;
+    const long o = (long)(co0 + c) * d.K + (long)tap * d.Cin + ci0 + cil;
+    wf[o >> 1] = __floats2bfloat162_rn(sw[c][cil * RS + tap], sw[c][(cil + 1) * RS + tap]);
+  }
+  if (d.w_dgrad != nullptr) {
+    __nv_bfloat162* wd = reinterpret_cast<__nv_bfloat162*>(d.w_dgrad);
+    for (int e = tid; e < 16 * run; e += 256) {                // data gradient: co fastest
+      const int c = (e & 15) * 2, rest = e >> 4;
+      const int cil = rest / RS, tap = rest - cil * RS;
+      const int r = tap / d.S, sx = tap - r * d.S;
+      const int ci = ci0 + cil, co = co0 + c;
+      long di;
+      if (d.dgrad_parity) {
+        const int pa = (r == 1) ? 0 : 1, u = (r == 0) ? 1 : 0;
+        const int pb = (sx == 1) ? 0 : 1, v = (sx == 0) ? 1 : 0;
+        const int nb = 1 + pb, nt = (1 + pa) * nb;
+        const int cls_off = (pa == 0) ? (pb == 0 ? 0 : 1) : (pb == 0 ? 3 : 5);
+        di = (long)cls_off * d.Cin * d.Cout + (long)ci * (nt * d.Cout) + (long)(u * nb + v) * d.Cout + co;
+      } else {
+        di = (long)ci * (RS * d.Cout) + (long)((d.R - 1 - r) * d.S + (d.S - 1 - sx)) * d.Cout + co;
+      }
+      wd[di >> 1] = __floats2bfloat162_rn(sw[c][cil * RS + tap], sw[c + 1][cil * RS + tap]);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256)
 weight_prep_tiled_kernel(const vdqn_wprep_desc* __restrict__ descs, const int* __restrict__ tile_offsets, int n) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float sw[32][32 * 9 + 1];
   __shared__ float sscale[32];
   int lo = 0, hi = n - 1;
@@ -98,7 +155,6 @@ weight_prep_tiled_kernel(const vdqn_wprep_desc* __restrict__ descs, const int* _
   const int b = blockIdx.x - tile_offsets[lo];
   const int ci_tiles = d.Cin / 32;
   const int co0 = (b / ci_tiles) * 32, ci0 = (b % ci_tiles) * 32;
-  const int RS = d.R * d.S, run = 32 * RS;
   if (threadIdx.x < 32) {
     const int co = co0 + threadIdx.x;
     float scale = 1.f;
@@ -112,37 +168,10 @@ weight_prep_tiled_kernel(const vdqn_wprep_desc* __restrict__ descs, const int* _
     }
   }
   __syncthreads();
-  for (int e = threadIdx.x; e < 32 * run; e += blockDim.x) {
-    const int col = e / run, j = e - col * run;                 // j = cil*RS + tap, contiguous in OIHW
-    sw[col][j] = d.w[((long)(co0 + col) * d.Cin + ci0) * RS + j] * sscale[col];
-  }
-  __syncthreads();
-  __nv_bfloat16* wf = static_cast<__nv_bfloat16*>(d.w_fwd);
-  for (int e = threadIdx.x; e < 32 * run; e += blockDim.x) {    // forward: [co][tap][ci], ci fastest
-    const int cil = e & 31, rest = e >> 5;
-    const int tap = rest % RS, col = rest / RS;
-    wf[(long)(co0 + col) * d.K + (long)tap * d.Cin + ci0 + cil] = __float2bfloat16_rn(sw[col][cil * RS + tap]);
-  }
-  if (d.w_dgrad != nullptr) {
-    __nv_bfloat16* wd = static_cast<__nv_bfloat16*>(d.w_dgrad);
-    for (int e = threadIdx.x; e < 32 * run; e += blockDim.x) {  // data gradient: co fastest
-      const int col = e & 31, rest = e >> 5;
-      const int tap = rest % RS, cil = rest / RS;
-      const int r = tap / d.S, sx = tap - r * d.S;
-      const int ci = ci0 + cil, co = co0 + col;
-      long di;
-      if (d.dgrad_parity) {
-        const int pa = (r == 1) ? 0 : 1, u = (r == 0) ? 1 : 0;
-        const int pb = (sx == 1) ? 0 : 1, v = (sx == 0) ? 1 : 0;
-        const int nb = 1 + pb, nt = (1 + pa) * nb;
-        const int cls_off = (pa == 0) ? (pb == 0 ? 0 : 1) : (pb == 0 ? 3 : 5);
-        di = (long)cls_off * d.Cin * d.Cout + (long)ci * (nt * d.Cout) + (long)(u * nb + v) * d.Cout + co;
-      } else {
-        di = (long)ci * (RS * d.Cout) + (long)((d.R - 1 - r) * d.S + (d.S - 1 - sx)) * d.Cout + co;
-      }
-      wd[di] = __float2bfloat16_rn(sw[col][cil * RS + tap]);
-    }
-  }
+  const int RS = d.R * d.S;
+  if (RS == 9) weight_prep_tile<9>(d, co0, ci0, sw, sscale);
+  else if (RS == 1) weight_prep_tile<1>(d, co0, ci0, sw, sscale);
+  else weight_prep_tile<0>(d, co0, ci0, sw, sscale);
 }
 
 // grid = (K blocks of 64, Cout), block = 64 (k) x 4 (split lanes).  A thread sums the partials of the
@@ -151,6 +180,8 @@ weight_prep_tiled_kernel(const vdqn_wprep_desc* __restrict__ descs, const int* _
 // feeds d gamma (one atomic per warp into a zeroed slot).
 __global__ void __launch_bounds__(256)
 wgrad_finalize_kernel(const vdqn_wgrad_fin_desc d) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float red[4][64];
   const int co = blockIdx.y;
   const int tx = threadIdx.x, ty = threadIdx.y;
@@ -198,10 +229,94 @@ wgrad_finalize_kernel(const vdqn_wgrad_fin_desc d) {
   }
 }
 
+// Row form of the finalize step for the (tap, ci)-ordered GEMM-K layouts (kmap 0): one block owns
+// output channel co = blockIdx.y and input channels [ci0, ci0 + cn).  Phase 1 sums the split
+// partials with 16-byte loads -- item = (tap, 4 consecutive ci), TX items x TY split lanes, four
+// independent loads in flight per thread -- into shared memory; phase 2 walks the same elements in
+// OIHW order (contiguous for a fixed co: o = ci*RS + tap), so W is read and dW written as full
+// lines, and folds the d gamma dot product into one atomic per block.  Fixed summation order.
+struct FinRowCfg {
+  int cn, items, TX, TY;
+};
+
+__global__ void __launch_bounds__(256)
+wgrad_finalize_rows_kernel(const vdqn_wgrad_fin_desc d, const FinRowCfg c) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float red[4608 + 160];
+  __shared__ float wsum[8];
+  const int co = blockIdx.y, ci0 = blockIdx.x * c.cn;
+  const int RS = d.R * d.S;
+  const int E = c.cn * RS;
+  const int pitch = c.cn + 1;                    // per-tap pitch in shared memory (bank spread)
+  const int lane_pitch = RS * pitch;
+  const int tid = threadIdx.x;
+  const int lane = tid / c.TX, tx = tid - lane * c.TX;
+  const long plane = (long)d.Cout * d.K;
+  const int cn4 = c.cn >> 2;
+  if (lane < c.TY) {
+    for (int item = tx; item < c.items; item += c.TX) {
+      const int tap = item / cn4, c4 = item - tap * cn4;
+      const float* p = d.part + (long)co * d.K + (long)tap * d.Cin + ci0 + 4 * c4;
+      float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+      int s = lane;
+      for (; s + 3 * c.TY < d.splits; s += 4 * c.TY) {
+        const float4 v0 = *reinterpret_cast<const float4*>(p + (long)s * plane);
+        const float4 v1 = *reinterpret_cast<const float4*>(p + (long)(s + c.TY) * plane);
+        const float4 v2 = *reinterpret_cast<const float4*>(p + (long)(s + 2 * c.TY) * plane);
+        const float4 v3 = *reinterpret_cast<const float4*>(p + (long)(s + 3 * c.TY) * plane);
+        a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
+        a1.x += v1.x; a1.y += v1.y; a1.z += v1.z; a1.w += v1.w;
+        a2.x += v2.x; a2.y += v2.y; a2.z += v2.z; a2.w += v2.w;
+        a3.x += v3.x; a3.y += v3.y; a3.z += v3.z; a3.w += v3.w;
+      }
+      for (; s < d.splits; s += c.TY) {
+        const float4 v0 = *reinterpret_cast<const float4*>(p + (long)s * plane);
+        a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
+      }
+      float* r = red + lane * lane_pitch + tap * pitch + 4 * c4;
+      r[0] = (a0.x + a1.x) + (a2.x + a3.x);
+      r[1] = (a0.y + a1.y) + (a2.y + a3.y);
+      r[2] = (a0.z + a1.z) + (a2.z + a3.z);
+      r[3] = (a0.w + a1.w) + (a2.w + a3.w);
+    }
+  }
+  __syncthreads();
+  float rstd = 1.f, scale = 1.f;
+  if (d.gamma != nullptr) {
+    rstd = 1.0f / sqrtf(d.var[co] + d.eps);
+    scale = d.gamma[co] * rstd;
+  }
+  const long o0 = ((long)co * d.Cin + ci0) * RS;
+  float dot = 0.f;
+  for (int j = tid; j < E; j += 256) {
+    const int cil = j / RS, tap = j - cil * RS;
+    const float* r = red + tap * pitch + cil;
+    float g = r[0];
+    for (int l = 1; l < c.TY; ++l) g += r[l * lane_pitch];
+    dot += __ldg(d.w + o0 + j) * g;
+    d.dw[o0 + j] = scale * g;
+  }
+  if (d.dgamma != nullptr) {
+    for (int off = 16; off; off >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, off);
+    if ((tid & 31) == 0) wsum[tid >> 5] = dot;
+    __syncthreads();
+    if (tid == 0) {
+      float v = 0.f;
+      for (int w = 0; w < 8; ++w) v += wsum[w];
+      v *= rstd;
+      if (blockIdx.x == 0 && d.dbeta != nullptr) v -= rstd * d.mean[co] * d.dbeta[co];
+      atomicAdd(d.dgamma + co, v);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // input packing: one thread per packed pixel (n, h2, w2) -> 16 bf16 (32 bytes)
 __global__ void stem_pack_f32_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int H,
                                      int W) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int H2 = H / 2, W2 = W / 2;
   const long total = (long)N * H2 * W2;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -231,16 +346,25 @@ __global__ void stem_pack_f32_kernel(const float* __restrict__ x, __nv_bfloat16*
 
 // uint8 HWC frames: one thread = TWO horizontally adjacent packed pixels = 12 source bytes per image
 // row (three aligned 32-bit loads), normalised as util/torch.py:26-36 (x/255, -mean, /std).
+// The two fp32 divisions per element made this kernel instruction-bound; it evaluates
+// fma(b, 1/(255 std), -mean/std) instead, which rounds to the SAME bf16 as the reference formula
+// for every one of the 3 x 256 possible (channel, byte) inputs (exhaustive check:
+// tests/test_oracle_golden.py::test_u8_normalisation_fma_is_exact).
 __global__ void stem_pack_u8_kernel(const uint8_t* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int H,
                                     int W) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int H2 = H / 2, W4 = W / 4;
   const long total = (long)N * H2 * W4;
-  const float mean[3] = {0.485f, 0.456f, 0.406f};
-  const float stdv[3] = {0.229f, 0.224f, 0.225f};
+  const float ka[3] = {(float)(1.0 / (255.0 * (double)0.229f)), (float)(1.0 / (255.0 * (double)0.224f)),
+                       (float)(1.0 / (255.0 * (double)0.225f))};
+  const float kb[3] = {(float)(-(double)0.485f / (double)0.229f), (float)(-(double)0.456f / (double)0.224f),
+                       (float)(-(double)0.406f / (double)0.225f)};
+  const int per_img = H2 * W4;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const int w4 = (int)(i % W4);
-    const long t = i / W4;
-    const int h2 = (int)(t % H2), n = (int)(t / H2);
+    const int n = (int)(i / per_img);
+    const int t = (int)(i - (long)n * per_img);
+    const int h2 = t / W4, w4 = t - h2 * W4;
     uint32_t raw[2][3];
 #pragma unroll
     for (int ph = 0; ph < 2; ++ph) {
@@ -261,9 +385,7 @@ __global__ void stem_pack_u8_kernel(const uint8_t* __restrict__ x, __nv_bfloat16
           for (int c = 0; c < 3; ++c) {
             const int byte = (2 * px + pw) * 3 + c;                 // 0..11 within the 12-byte row chunk
             const uint32_t b = (raw[ph][byte >> 2] >> (8 * (byte & 3))) & 0xffu;
-            float f = (float)b / 255.f;
-            f = f - mean[c];
-            v[(ph * 2 + pw) * 3 + c] = f / stdv[c];
+            v[(ph * 2 + pw) * 3 + c] = fmaf((float)b, ka[c], kb[c]);
           }
       uint4 pk[2];
       __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(pk);
@@ -279,33 +401,48 @@ __global__ void stem_pack_u8_kernel(const uint8_t* __restrict__ x, __nv_bfloat16
 // ------------------------------------------------------------------------------------------
 // max_pool2d(3,2,1), NHWC bf16; one thread = 8 channels of one output pixel.  Values stay packed
 // as bf16x2: one __hgt2_mask + __hmax2 + select per pair and tap.  Strict '>' against a -inf start
-// keeps the first maximum of the window scan (torch's choice of arg-max).
+// keeps the first maximum of the window scan (torch's choice of arg-max).  All nine 16-byte loads
+// are issued up front from clamped (always valid) addresses and out-of-image taps are replaced by
+// -inf afterwards: no branch sits between the loads, so nine are in flight per thread (the branchy
+// form had one, and ran at half the HBM rate).
 template <bool IDX>
 __global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
                                    uint8_t* __restrict__ idx, int N, int H, int W, int C) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1, CG = C / 8;
   const long total = (long)N * Ho * Wo * CG;
+  const int per_img = Ho * Wo * CG;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total;
        i += (long)gridDim.x * blockDim.x) {
-    const int cg = (int)(i % CG);
-    long t = i / CG;
-    const int q = (int)(t % Wo); t /= Wo;
-    const int p = (int)(t % Ho);
-    const int n = (int)(t / Ho);
+    const int n = (int)(i / per_img);
+    int t = (int)(i - (long)n * per_img);
+    const int cg = t % CG; t /= CG;
+    const int q = t % Wo;
+    const int p = t / Wo;
+    const uint4* base = reinterpret_cast<const uint4*>(x + ((long)n * H * W) * C + cg * 8);
+    const int h0 = 2 * p - 1, w0 = 2 * q - 1;
+    uint4 raw[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int h = min(max(h0 + r, 0), H - 1);
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int w = min(max(w0 + s, 0), W - 1);
+        raw[r * 3 + s] = __ldg(base + (h * W + w) * CG);
+      }
+    }
     uint32_t best[4], slot[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) { best[e] = 0xFF80FF80u; slot[e] = 0u; }     // -inf, -inf
-    const __nv_bfloat16* base = x + ((long)n * H * W) * C + cg * 8;
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
-      const int h = 2 * p - 1 + r;
-      if (h < 0 || h >= H) continue;
 #pragma unroll
       for (int s = 0; s < 3; ++s) {
-        const int w = 2 * q - 1 + s;
-        if (w < 0 || w >= W) continue;
-        const uint4 raw = __ldg(reinterpret_cast<const uint4*>(base + ((long)h * W + w) * C));
-        const uint32_t v[4] = {raw.x, raw.y, raw.z, raw.w};
+        const bool valid = (unsigned)(h0 + r) < (unsigned)H && (unsigned)(w0 + s) < (unsigned)W;
+        const uint4 rv = raw[r * 3 + s];
+        const uint32_t v[4] = {valid ? rv.x : 0xFF80FF80u, valid ? rv.y : 0xFF80FF80u,
+                               valid ? rv.z : 0xFF80FF80u, valid ? rv.w : 0xFF80FF80u};
         const uint32_t tap2 = (uint32_t)(r * 3 + s) * 0x00010001u;
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -338,40 +475,48 @@ __global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfl
 __global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ idx,
                                    const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ dx,
                                    float* __restrict__ colsum, int N, int H, int W, int C) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int Ho = H / 2, Wo = W / 2, CG = C / 8;      // H, W even: 3x3/2/1 pooling halves them
   const long total = (long)N * Ho * Wo * CG;
   float acc[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) acc[e] = 0.f;
   const int cg = threadIdx.x % CG;                  // blockDim.x and the grid stride are multiples of CG
+  const int per_img = Ho * Wo * CG;
   const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
   for (long t0 = blockIdx.x * (long)blockDim.x + threadIdx.x; t0 < total; t0 += (long)gridDim.x * blockDim.x) {
-    long t = t0 / CG;
-    const int j = (int)(t % Wo); t /= Wo;
-    const int i = (int)(t % Ho);
-    const int n = (int)(t / Ho);
-    // masked window gradients gw[a][b] for windows (i+a, j+b) and their arg-max slots
+    const int n = (int)(t0 / per_img);
+    int t = (int)(t0 - (long)n * per_img) / CG;
+    const int j = t % Wo;
+    const int i = t / Wo;
+    // masked window gradients gw[a][b] for windows (i+a, j+b) and their arg-max slots.  All twelve
+    // loads are issued first, from clamped addresses (no branch in between); windows outside the
+    // image are neutralised afterwards.
     uint32_t gw[2][2][4];
     uint2 sl[2][2];
+    uint4 gr[2][2], yr[2][2];
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const int ii = min(i + a, Ho - 1), jj = min(j + b, Wo - 1);
+        const long o = (((long)n * Ho + ii) * Wo + jj) * C + cg * 8;
+        sl[a][b] = __ldg(reinterpret_cast<const uint2*>(idx + o));
+        gr[a][b] = __ldg(reinterpret_cast<const uint4*>(dy + o));
+        yr[a][b] = __ldg(reinterpret_cast<const uint4*>(y + o));
+      }
 #pragma unroll
     for (int a = 0; a < 2; ++a)
 #pragma unroll
       for (int b = 0; b < 2; ++b) {
         const bool in = (i + a < Ho) && (j + b < Wo);
-        if (in) {
-          const long o = (((long)n * Ho + i + a) * Wo + j + b) * C + cg * 8;
-          sl[a][b] = __ldg(reinterpret_cast<const uint2*>(idx + o));
-          const uint4 g = __ldg(reinterpret_cast<const uint4*>(dy + o));
-          const uint4 yy = __ldg(reinterpret_cast<const uint4*>(y + o));
-          const uint32_t gv[4] = {g.x, g.y, g.z, g.w}, yv[4] = {yy.x, yy.y, yy.z, yy.w};
+        const uint32_t gv[4] = {gr[a][b].x, gr[a][b].y, gr[a][b].z, gr[a][b].w};
+        const uint32_t yv[4] = {yr[a][b].x, yr[a][b].y, yr[a][b].z, yr[a][b].w};
+        if (!in) sl[a][b] = make_uint2(0xffffffffu, 0xffffffffu);      // slot 255 never matches
 #pragma unroll
-          for (int e = 0; e < 4; ++e)
-            gw[a][b][e] = gv[e] & __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&yv[e]), zero2);
-        } else {
-          sl[a][b] = make_uint2(0xffffffffu, 0xffffffffu);      // slot 255 never matches
-#pragma unroll
-          for (int e = 0; e < 4; ++e) gw[a][b][e] = 0u;
-        }
+        for (int e = 0; e < 4; ++e)
+          gw[a][b][e] = in ? (gv[e] & __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&yv[e]), zero2)) : 0u;
       }
     // out[ph][pw] for input pixel (2i+ph, 2j+pw): window (i+a, j+b) reaches it through slot
     // r*3+s with r = ph - 2a + 1, s = pw - 2b + 1 (valid when 0 <= r,s <= 2)
@@ -429,6 +574,8 @@ __global__ void __launch_bounds__(256)
 sgemm_strided_kernel(const float* __restrict__ A, const float* __restrict__ Bm, float* __restrict__ Cm,
                      const float* __restrict__ bias, int M, int N, int K, long a_rs, long a_cs,
                      long b_rs, long b_cs, int ldc, int relu, int k_len) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float As[16][64 + 4];
   __shared__ float Bs[16][64 + 4];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -492,6 +639,8 @@ sgemm_strided_kernel(const float* __restrict__ A, const float* __restrict__ Bm, 
 
 __global__ void bias_act_kernel(float* __restrict__ c, const float* __restrict__ bias, long total, int N,
                                 int relu) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     float v = c[i];
     if (bias != nullptr) v += bias[i % N];
@@ -504,6 +653,8 @@ __global__ void bias_act_kernel(float* __restrict__ c, const float* __restrict__
 __global__ void mask_colsum_kernel(const float* __restrict__ dy, const float* __restrict__ y,
                                    float* __restrict__ dyp, float* __restrict__ db, int B, int O,
                                    int relu) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int o = blockIdx.x * 32 + (threadIdx.x & 31);
   const int r0 = threadIdx.x >> 5, nr = blockDim.x >> 5;
   float s = 0.f;
@@ -527,6 +678,8 @@ __global__ void mask_colsum_kernel(const float* __restrict__ dy, const float* __
 
 __global__ void head_flatten_fwd_kernel(const __nv_bfloat16* __restrict__ h, float* __restrict__ flat,
                                         int B, int P, int C) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long total = (long)B * P * C;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total;
        i += (long)gridDim.x * blockDim.x) {
@@ -542,6 +695,8 @@ __global__ void head_flatten_fwd_kernel(const __nv_bfloat16* __restrict__ h, flo
 __global__ void head_flatten_bwd_kernel(const float* __restrict__ dflat, const __nv_bfloat16* __restrict__ h,
                                         __nv_bfloat16* __restrict__ dh, float* __restrict__ dbias,
                                         int B, int P, int C) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x;
   const int c = threadIdx.x;       // blockDim.x == C
   float s = 0.f;
@@ -559,6 +714,8 @@ __global__ void head_flatten_bwd_kernel(const float* __restrict__ dflat, const _
 // ------------------------------------------------------------------------------------------
 // fused TD epilogue: one thread per (sample, class)
 __global__ void td_epilogue_kernel(const vdqn_td_desc d) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long total = (long)d.B * d.C;
   float local = 0.f;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total;
@@ -606,6 +763,8 @@ __global__ void td_epilogue_kernel(const vdqn_td_desc d) {
 // callers (visualize_value.py:96-97, evaluation/evaluate.py:110-114)
 __global__ void q_max_kernel(const float* __restrict__ q, float* __restrict__ value, int64_t* __restrict__ arg,
                              long total, int A) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const float* p = q + i * A;
     float bv = p[0];
@@ -624,6 +783,8 @@ adam_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __rest
             float4* __restrict__ v, float4* __restrict__ target, long n4, float step_size,
             float beta1, float beta2, float eps, float sqrt_bc2, float grad_scale,
             const float* __restrict__ dev_scalars) {
+  pdl_launch_dependents();
+  pdl_wait();
   if (dev_scalars != nullptr) {          // graph-replay mode: step-dependent scalars live in HBM
     step_size = dev_scalars[0];
     sqrt_bc2 = dev_scalars[1];
@@ -647,6 +808,8 @@ adam_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __rest
 
 // step counter and bias corrections kept on the device so a captured CUDA graph can be replayed
 __global__ void adam_scalars_kernel(int* step, float* out, double lr, double b1, double b2) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int t = *step + 1;
   *step = t;
   const double bc1 = 1.0 - pow(b1, (double)t);
@@ -676,7 +839,7 @@ extern "C" int vdqn_weight_prep(const vdqn_wprep_desc* d, void* stream_v) {
     return set_error(VDQN_ERR_ARG, "weight_prep: null pointer");
   GET_DEV();
   const long total = (long)d->Cout * d->K;
-  weight_prep_kernel<<<grid_for(total, 256, dev->num_sms), 256, 0, stream>>>(*d);
+  launch_kernel(weight_prep_kernel, grid_for(total, 256, dev->num_sms), 256, 0, stream, *d);
   VDQN_CHECK_LAUNCH("weight_prep");
   return VDQN_OK;
 }
@@ -687,8 +850,7 @@ extern "C" int vdqn_weight_prep_multi(const vdqn_wprep_desc* descs_dev, const in
     return set_error(VDQN_ERR_ARG, "weight_prep_multi: bad arguments");
   GET_DEV();
   if (total == 0) return VDQN_OK;
-  weight_prep_multi_kernel<<<grid_for(total, 256, dev->num_sms, 16), 256, 0, stream>>>(
-      descs_dev, reinterpret_cast<const long long*>(offsets_dev), n, total);
+  launch_kernel(weight_prep_multi_kernel, grid_for(total, 256, dev->num_sms, 16), 256, 0, stream, descs_dev, reinterpret_cast<const long long*>(offsets_dev), n, total);
   VDQN_CHECK_LAUNCH("weight_prep_multi");
   return VDQN_OK;
 }
@@ -699,7 +861,7 @@ extern "C" int vdqn_weight_prep_tiled(const vdqn_wprep_desc* descs_dev, const in
     return set_error(VDQN_ERR_ARG, "weight_prep_tiled: bad arguments");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   if (total_tiles == 0) return VDQN_OK;
-  weight_prep_tiled_kernel<<<total_tiles, 256, 0, stream>>>(descs_dev, tile_offsets_dev, n);
+  launch_kernel(weight_prep_tiled_kernel, total_tiles, 256, 0, stream, descs_dev, tile_offsets_dev, n);
   VDQN_CHECK_LAUNCH("weight_prep_tiled");
   return VDQN_OK;
 }
@@ -709,7 +871,27 @@ extern "C" int vdqn_wgrad_finalize(const vdqn_wgrad_fin_desc* d, void* stream_v)
     return set_error(VDQN_ERR_ARG, "wgrad_finalize: null pointer");
   GET_DEV();
   (void)dev;
-  wgrad_finalize_kernel<<<dim3((d->K + 63) / 64, d->Cout), dim3(64, 4), 0, stream>>>(*d);
+  const int RS = d->R * d->S;
+  if (d->kmap == 0 && d->K == RS * d->Cin && d->Cin % 16 == 0 && d->K <= 4608 &&
+      (reinterpret_cast<uintptr_t>(d->part) & 15) == 0) {
+    // input-channel chunks: enough blocks to cover the SMs while a chunk stays >= 16 channels
+    int nchunks = 1;
+    while (d->Cout * nchunks < 2 * dev->num_sms && d->Cin / (2 * nchunks) >= 16 && d->Cin % (2 * nchunks) == 0)
+      nchunks *= 2;
+    FinRowCfg c;
+    c.cn = d->Cin / nchunks;
+    c.items = RS * (c.cn / 4);
+    c.TX = c.items < 256 ? c.items : 256;
+    c.TY = 256 / c.TX;
+    if (c.TY > d->splits) c.TY = d->splits;
+    // shared memory: TY lanes x RS x (cn + 1) floats
+    if ((long)c.TY * RS * (c.cn + 1) <= 4608 + 160) {
+      launch_kernel(wgrad_finalize_rows_kernel, dim3(nchunks, d->Cout), 256, 0, stream, *d, c);
+      VDQN_CHECK_LAUNCH("wgrad_finalize_rows");
+      return VDQN_OK;
+    }
+  }
+  launch_kernel(wgrad_finalize_kernel, dim3((d->K + 63) / 64, d->Cout), dim3(64, 4), 0, stream, *d);
   VDQN_CHECK_LAUNCH("wgrad_finalize");
   return VDQN_OK;
 }
@@ -720,8 +902,7 @@ extern "C" int vdqn_stem_pack_f32(const float* x, void* out, int32_t N, int32_t 
   GET_DEV();
   const long total = (long)N * (H / 2) * (W / 2);
   if (total == 0) return VDQN_OK;
-  stem_pack_f32_kernel<<<grid_for(total, 256, dev->num_sms, 16), 256, 0, stream>>>(
-      x, static_cast<__nv_bfloat16*>(out), N, H, W);
+  launch_kernel(stem_pack_f32_kernel, grid_for(total, 256, dev->num_sms, 16), 256, 0, stream, x, static_cast<__nv_bfloat16*>(out), N, H, W);
   VDQN_CHECK_LAUNCH("stem_pack_f32");
   return VDQN_OK;
 }
@@ -733,8 +914,7 @@ extern "C" int vdqn_stem_pack_u8(const uint8_t* x, void* out, int32_t N, int32_t
   GET_DEV();
   const long total = (long)N * (H / 2) * (W / 4);
   if (total == 0) return VDQN_OK;
-  stem_pack_u8_kernel<<<grid_for(total, 256, dev->num_sms, 16), 256, 0, stream>>>(
-      x, static_cast<__nv_bfloat16*>(out), N, H, W);
+  launch_kernel(stem_pack_u8_kernel, grid_for(total, 256, dev->num_sms, 16), 256, 0, stream, x, static_cast<__nv_bfloat16*>(out), N, H, W);
   VDQN_CHECK_LAUNCH("stem_pack_u8");
   return VDQN_OK;
 }
@@ -748,11 +928,9 @@ extern "C" int vdqn_maxpool_fwd(const void* x, void* y, uint8_t* idx, int32_t N,
   const long total = (long)N * Ho * Wo * (C / 8);
   if (total == 0) return VDQN_OK;
   if (idx != nullptr)
-    maxpool_fwd_kernel<true><<<grid_for(total, 256, dev->num_sms, 16), 256, 0, stream>>>(
-        static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), idx, N, H, W, C);
+    launch_kernel(maxpool_fwd_kernel<true>, grid_for(total, 256, dev->num_sms, 16), 256, 0, stream, static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), idx, N, H, W, C);
   else
-    maxpool_fwd_kernel<false><<<grid_for(total, 256, dev->num_sms, 16), 256, 0, stream>>>(
-        static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), idx, N, H, W, C);
+    launch_kernel(maxpool_fwd_kernel<false>, grid_for(total, 256, dev->num_sms, 16), 256, 0, stream, static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), idx, N, H, W, C);
   VDQN_CHECK_LAUNCH("maxpool_fwd");
   return VDQN_OK;
 }
@@ -766,8 +944,7 @@ extern "C" int vdqn_maxpool_bwd(const void* dy, const uint8_t* idx, const void* 
   GET_DEV();
   const long total = (long)N * (H / 2) * (W / 2) * (C / 8);
   if (total == 0) return VDQN_OK;
-  maxpool_bwd_kernel<<<grid_for(total, 256, dev->num_sms, 8), 256, 256 * 8 * sizeof(float), stream>>>(
-      static_cast<const __nv_bfloat16*>(dy), idx, static_cast<const __nv_bfloat16*>(y),
+  launch_kernel(maxpool_bwd_kernel, grid_for(total, 256, dev->num_sms, 8), 256, 256 * 8 * sizeof(float), stream, static_cast<const __nv_bfloat16*>(dy), idx, static_cast<const __nv_bfloat16*>(y),
       static_cast<__nv_bfloat16*>(dx), colsum, N, H, W, C);
   VDQN_CHECK_LAUNCH("maxpool_bwd");
   return VDQN_OK;
@@ -795,12 +972,12 @@ static int launch_sgemm(const float* A, const float* B, float* C, const float* b
     cudaError_t e = cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, stream);
     if (e != cudaSuccess) return set_error(VDQN_ERR_CUDA, "sgemm memset: %s", cudaGetErrorString(e));
   }
-  sgemm_strided_kernel<<<grid, 256, 0, stream>>>(A, B, C, bias, M, N, K, a_rs, a_cs, b_rs, b_cs, ldc, relu,
+  launch_kernel(sgemm_strided_kernel, grid, 256, 0, stream, A, B, C, bias, M, N, K, a_rs, a_cs, b_rs, b_cs, ldc, relu,
                                                  k_len);
   VDQN_CHECK_LAUNCH("sgemm");
   if (splitk > 1 && (bias != nullptr || relu)) {
     const long total = (long)M * N;
-    bias_act_kernel<<<grid_for(total, 256, dev->num_sms), 256, 0, stream>>>(C, bias, total, N, relu);
+    launch_kernel(bias_act_kernel, grid_for(total, 256, dev->num_sms), 256, 0, stream, C, bias, total, N, relu);
     VDQN_CHECK_LAUNCH("bias_act");
   }
   return VDQN_OK;
@@ -824,7 +1001,7 @@ extern "C" int vdqn_linear_bwd(const float* x, const float* w, const float* y, f
   if (B == 0) return VDQN_OK;
   // dy is overwritten in place with the masked gradient (the caller owns it as scratch)
   float* dyp = dy;
-  mask_colsum_kernel<<<(O + 31) / 32, 1024, 0, stream>>>(dy, y, dyp, db, B, O, relu);
+  launch_kernel(mask_colsum_kernel, (O + 31) / 32, 1024, 0, stream, dy, y, dyp, db, B, O, relu);
   VDQN_CHECK_LAUNCH("mask_colsum");
   // dw[o,k] = sum_b dyp[b,o] * x[b,k]
   int rc = launch_sgemm(dyp, x, dw, nullptr, O, K, B, 1, O, K, 1, K, 0, stream);
@@ -839,8 +1016,7 @@ extern "C" int vdqn_head_flatten_fwd(const void* h, float* flat, int32_t B, int3
   GET_DEV();
   const long total = (long)B * P * C;
   if (total == 0) return VDQN_OK;
-  head_flatten_fwd_kernel<<<grid_for(total, 256, dev->num_sms), 256, 0, stream>>>(
-      static_cast<const __nv_bfloat16*>(h), flat, B, P, C);
+  launch_kernel(head_flatten_fwd_kernel, grid_for(total, 256, dev->num_sms), 256, 0, stream, static_cast<const __nv_bfloat16*>(h), flat, B, P, C);
   VDQN_CHECK_LAUNCH("head_flatten_fwd");
   return VDQN_OK;
 }
@@ -851,7 +1027,7 @@ extern "C" int vdqn_head_flatten_bwd(const float* dflat, const void* h, void* dh
   if (C > 1024) return set_error(VDQN_ERR_SHAPE, "head_flatten_bwd: C too large");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
   if (B == 0) return VDQN_OK;
-  head_flatten_bwd_kernel<<<B, C, 0, stream>>>(dflat, static_cast<const __nv_bfloat16*>(h),
+  launch_kernel(head_flatten_bwd_kernel, B, C, 0, stream, dflat, static_cast<const __nv_bfloat16*>(h),
                                                static_cast<__nv_bfloat16*>(dh), dbias, B, P, C);
   VDQN_CHECK_LAUNCH("head_flatten_bwd");
   return VDQN_OK;
@@ -868,7 +1044,7 @@ extern "C" int vdqn_td_epilogue(const vdqn_td_desc* d, void* stream_v) {
   GET_DEV();
   const long total = (long)d->B * d->C;
   if (total == 0) return VDQN_OK;
-  td_epilogue_kernel<<<grid_for(total, 256, dev->num_sms, 8), 256, 0, stream>>>(*d);
+  launch_kernel(td_epilogue_kernel, grid_for(total, 256, dev->num_sms, 8), 256, 0, stream, *d);
   VDQN_CHECK_LAUNCH("td_epilogue");
   return VDQN_OK;
 }
@@ -889,7 +1065,7 @@ extern "C" int vdqn_q_max(const float* q, float* value, int64_t* arg, int64_t ro
   if (A < 1 || rows < 0) return set_error(VDQN_ERR_SHAPE, "q_max: bad shape");
   GET_DEV();
   if (rows == 0) return VDQN_OK;
-  q_max_kernel<<<grid_for(rows, 256, dev->num_sms), 256, 0, stream>>>(q, value, arg, rows, A);
+  launch_kernel(q_max_kernel, grid_for(rows, 256, dev->num_sms), 256, 0, stream, q, value, arg, rows, A);
   VDQN_CHECK_LAUNCH("q_max");
   return VDQN_OK;
 }
@@ -904,8 +1080,7 @@ extern "C" int vdqn_adam_fused(float* p, const float* g, float* m, float* v, flo
   if (n == 0) return VDQN_OK;
   const double bc1 = 1.0 - pow(beta1, (double)step);
   const double bc2 = 1.0 - pow(beta2, (double)step);
-  adam_kernel<<<grid_for(n / 4, 256, dev->num_sms, 8), 256, 0, stream>>>(
-      reinterpret_cast<float4*>(p), reinterpret_cast<const float4*>(g), reinterpret_cast<float4*>(m),
+  launch_kernel(adam_kernel, grid_for(n / 4, 256, dev->num_sms, 8), 256, 0, stream, reinterpret_cast<float4*>(p), reinterpret_cast<const float4*>(g), reinterpret_cast<float4*>(m),
       reinterpret_cast<float4*>(v), reinterpret_cast<float4*>(target), n / 4, (float)(lr / bc1),
       (float)beta1, (float)beta2, (float)eps, (float)sqrt(bc2), grad_scale, nullptr);
   VDQN_CHECK_LAUNCH("adam");
@@ -921,11 +1096,10 @@ extern "C" int vdqn_adam_fused_graph(float* p, const float* g, float* m, float* 
   if (step_dev == nullptr || scalars_dev == nullptr)
     return set_error(VDQN_ERR_ARG, "adam_graph: device step counter / scalar buffer missing");
   GET_DEV();
-  adam_scalars_kernel<<<1, 1, 0, stream>>>(step_dev, scalars_dev, lr, beta1, beta2);
+  launch_kernel(adam_scalars_kernel, 1, 1, 0, stream, step_dev, scalars_dev, lr, beta1, beta2);
   VDQN_CHECK_LAUNCH("adam_scalars");
   if (n == 0) return VDQN_OK;
-  adam_kernel<<<grid_for(n / 4, 256, dev->num_sms, 8), 256, 0, stream>>>(
-      reinterpret_cast<float4*>(p), reinterpret_cast<const float4*>(g), reinterpret_cast<float4*>(m),
+  launch_kernel(adam_kernel, grid_for(n / 4, 256, dev->num_sms, 8), 256, 0, stream, reinterpret_cast<float4*>(p), reinterpret_cast<const float4*>(g), reinterpret_cast<float4*>(m),
       reinterpret_cast<float4*>(v), reinterpret_cast<float4*>(target), n / 4, 0.f, (float)beta1,
       (float)beta2, (float)eps, 1.f, grad_scale, scalars_dev);
   VDQN_CHECK_LAUNCH("adam");

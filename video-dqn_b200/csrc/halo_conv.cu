@@ -85,6 +85,7 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();
   const int taps = a.R * a.S;
 
   if (warp == 0 && lane == 0) {
@@ -112,6 +113,7 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();
 
   const bool second = a.split_cta > 0 && (int)blockIdx.x >= a.split_cta;
   const int tile0 = (second ? a.split_tile : 0) + (int)blockIdx.x - (second ? a.split_cta : 0);
@@ -401,7 +403,7 @@ static int launch_halo(const vdqn_conv_desc* d, cudaStream_t stream) {
     if (g0 > grid - 1) g0 = grid - 1;
     a.split_cta = g0;
   }
-  kfn<<<grid, 288, Cfg::SMEM_BYTES, stream>>>(tmX, tmW, tmW2, tmOut, tmRes, tmMask, a);
+  launch_kernel(kfn, grid, 288, Cfg::SMEM_BYTES, stream, tmX, tmW, tmW2, tmOut, tmRes, tmMask, a);
   VDQN_CHECK_LAUNCH("halo_conv launch");
   return VDQN_OK;
 }

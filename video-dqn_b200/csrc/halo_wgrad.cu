@@ -53,6 +53,7 @@ halo_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmX);
@@ -72,6 +73,7 @@ halo_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();
 
   if (warp == 0) {
     int stage = 0;
@@ -188,7 +190,7 @@ int halo_wgrad_launch(const vdqn_wgrad_desc* d, cudaStream_t stream) {
   if (rc != VDQN_OK) return rc;
   rc = make_tiled_map_nhwc(&tmDy, d->dy, d->N, d->H, d->W, 64, 64, Cfg::TW, Cfg::TH, 128);
   if (rc != VDQN_OK) return rc;
-  halo_wgrad_kernel<<<d->splits, 192, Cfg::SMEM_BYTES, stream>>>(tmX, tmDy, a);
+  launch_kernel(halo_wgrad_kernel, d->splits, 192, Cfg::SMEM_BYTES, stream, tmX, tmDy, a);
   VDQN_CHECK_LAUNCH("halo_wgrad launch");
   return VDQN_OK;
 }

@@ -23,6 +23,18 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// With VDQN_PDL=1 every kernel of the library is launched with programmatic stream serialisation
+// (vdqn_internal.h, launch_kernel): it may become resident while its predecessor on the stream is still draining, run
+// its prologue (barrier init, TMEM allocation, descriptor prefetch), and must then wait here before
+// touching global memory.  No-ops when the launch did not carry the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");

@@ -59,6 +59,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ C
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmDy);
@@ -81,6 +82,7 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ C
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();
 
   const int units = a.splits * a.co_tiles * a.groups;
   const int cblks = a.Cin / CK;
@@ -243,7 +245,7 @@ static int launch_wgrad(const CUtensorMap& tmDy, const CUtensorMap& tmX, const W
   }
   const int units = a.splits * a.co_tiles * a.groups;
   const int grid = units < num_sms ? units : num_sms;
-  kfn<<<grid, 192, Cfg::SMEM_BYTES, stream>>>(tmDy, tmX, a);
+  launch_kernel(kfn, grid, 192, Cfg::SMEM_BYTES, stream, tmDy, tmX, a);
   VDQN_CHECK_LAUNCH("wgrad launch");
   return VDQN_OK;
 }
