@@ -137,21 +137,28 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const int rem = m0 - img * HoWo;
       const int p0 = rem / a.Wo, q0 = rem - p0 * a.Wo;
       const int cw = q0 * a.stride + a.lower_w, ch = p0 * a.stride + a.lower_h;
+      // (tap row, tap column, channel block) advance incrementally: the producer is one thread and
+      // an integer division per k-block would sit on its critical path
+      int c0 = 0, off_w = 0, off_h = 0, s_i = 0, jk = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(empty_bar(stage), phase ^ 1);
-        if (elect_one()) {
-          mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
-          const uint32_t sA = smem_base + stage * Cfg::STAGE_BYTES;
-          const uint32_t sB = sA + Cfg::KSUB * Cfg::A_SUB_BYTES;
+        const bool leader = elect_one();
+        if (leader) mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+        const uint32_t sA = smem_base + stage * Cfg::STAGE_BYTES;
+        const uint32_t sB = sA + Cfg::KSUB * Cfg::A_SUB_BYTES;
 #pragma unroll
-          for (int sub = 0; sub < Cfg::KSUB; ++sub) {
-            const int j = kb * Cfg::KSUB + sub;
-            const int tap = j / cblks;
-            const int c0 = (j - tap * cblks) * CK;
-            const int r = tap / a.S, s = tap - r * a.S;
+        for (int sub = 0; sub < Cfg::KSUB; ++sub) {
+          if (leader) {
             tma_load_im2col_4d(sA + sub * Cfg::A_SUB_BYTES, &tmA, full_bar(stage), c0, cw, ch, img,
-                               (uint16_t)(s * a.dil), (uint16_t)(r * a.dil));
-            tma_load_2d(sB + sub * Cfg::B_SUB_BYTES, tmBp, full_bar(stage), j * CK, n_t * BN);
+                               (uint16_t)off_w, (uint16_t)off_h);
+            tma_load_2d(sB + sub * Cfg::B_SUB_BYTES, tmBp, full_bar(stage), jk, n_t * BN);
+          }
+          jk += CK;
+          c0 += CK;
+          if (c0 == a.Cin) {
+            c0 = 0;
+            off_w += a.dil;
+            if (++s_i == a.S) { s_i = 0; off_w = 0; off_h += a.dil; }
           }
         }
         __syncwarp();

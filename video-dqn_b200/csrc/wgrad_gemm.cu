@@ -105,38 +105,54 @@ wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ C
   };
 
   if (warp == 0) {
+    // The producer is ONE thread: every integer division here is ~100 dependent cycles on the
+    // critical path of a stage whose MMAs take 512.  Slab coordinates are therefore decoded once per
+    // unit and the pixel coordinate advances incrementally (no division inside the k loop).
     int stage = 0;
     uint32_t phase = 0;
+    const int dq = Cfg::PIX % a.Wo, dp = Cfg::PIX / a.Wo;
     for (int u = blockIdx.x; u < units; u += gridDim.x) {
       int split, co_t, grp;
       decode(u, split, co_t, grp);
       const int nslab = min(Cfg::SLABS, total_slabs - grp * Cfg::SLABS);
       const int ksteps = ksteps_of(split);
       const uint32_t tx = co_slabs * Cfg::A_SLAB_BYTES + nslab * Cfg::B_SLAB_BYTES;
+      int sl_c0[Cfg::SLABS];
+      uint32_t sl_off[Cfg::SLABS];          // (offset_w, offset_h) packed 16:16
+#pragma unroll
+      for (int sl = 0; sl < Cfg::SLABS; ++sl) {
+        const int j = grp * Cfg::SLABS + (sl < nslab ? sl : 0);
+        const int tap = j / cblks;
+        sl_c0[sl] = (j - tap * cblks) * CK;
+        const int r = tap / a.S, sx = tap - r * a.S;
+        sl_off[sl] = (uint32_t)(sx * a.dil) | ((uint32_t)(r * a.dil) << 16);
+      }
+      int m0 = split * a.pix_per_split;
+      int img = m0 / HoWo;
+      const int rem = m0 - img * HoWo;
+      int p0 = rem / a.Wo, q0 = rem - p0 * a.Wo;
       for (int i = 0; i < ksteps; ++i) {
-        const int m0 = split * a.pix_per_split + i * Cfg::PIX;
-        const int img = m0 / HoWo;
-        const int rem = m0 - img * HoWo;
-        const int p0 = rem / a.Wo, q0 = rem - p0 * a.Wo;
         const int cw = q0 * a.stride + a.lower_w, ch = p0 * a.stride + a.lower_h;
         mbar_wait(empty_bar(stage), phase ^ 1);
         if (elect_one()) {
           mbar_expect_tx(full_bar(stage), tx);
           const uint32_t sA = smem_base + stage * Cfg::STAGE_BYTES;
           const uint32_t sB = sA + Cfg::A_BYTES;
-          for (int cs = 0; cs < co_slabs; ++cs)
-            tma_load_2d(sA + cs * Cfg::A_SLAB_BYTES, &tmDy, full_bar(stage), co_t * 128 + cs * 64, m0);
-          for (int sl = 0; sl < nslab; ++sl) {
-            const int j = grp * Cfg::SLABS + sl;
-            const int tap = j / cblks;
-            const int c0 = (j - tap * cblks) * CK;
-            const int r = tap / a.S, s = tap - r * a.S;
-            tma_load_im2col_4d(sB + sl * Cfg::B_SLAB_BYTES, &tmX, full_bar(stage), c0, cw, ch, img,
-                               (uint16_t)(s * a.dil), (uint16_t)(r * a.dil));
+          tma_load_2d(sA, &tmDy, full_bar(stage), co_t * 128, m0);
+          if (co_slabs == 2) tma_load_2d(sA + Cfg::A_SLAB_BYTES, &tmDy, full_bar(stage), co_t * 128 + 64, m0);
+#pragma unroll
+          for (int sl = 0; sl < Cfg::SLABS; ++sl) {
+            if (sl < nslab)
+              tma_load_im2col_4d(sB + sl * Cfg::B_SLAB_BYTES, &tmX, full_bar(stage), sl_c0[sl], cw, ch, img,
+                                 (uint16_t)(sl_off[sl] & 0xffffu), (uint16_t)(sl_off[sl] >> 16));
           }
         }
         __syncwarp();
         if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        m0 += Cfg::PIX;
+        q0 += dq; p0 += dp;
+        if (q0 >= a.Wo) { q0 -= a.Wo; ++p0; }
+        while (p0 >= a.Ho) { p0 -= a.Ho; ++img; }
       }
     }
   } else if (warp == 1) {

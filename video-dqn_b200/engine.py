@@ -279,6 +279,15 @@ import os as _os
 
 # column-tile width for the Cout >= 256 layers (0 = kernel default 256); tuning knob
 TILE_N_WIDE = int(_os.environ.get("VDQN_TILE_N_WIDE", "0"))
+# column-tile width of the layer4 data gradients (196 tiles of 128x256 on 148 SMs = two uneven waves
+# at B = 256; 128 gives 392 smaller tiles)
+TILE_N_DGRAD4 = int(_os.environ.get("VDQN_TILE_N_DGRAD4", "0"))
+
+
+def _dgrad_tile_n(ch: int) -> int:
+    if ch >= 512 and TILE_N_DGRAD4:
+        return TILE_N_DGRAD4
+    return TILE_N_WIDE if ch >= 256 else 0
 
 
 def _conv(W: PreparedWeights, c: ConvSpec, x, out, W2: Optional[PreparedWeights] = None, split: int = 0, **kw):
@@ -378,7 +387,7 @@ def backward(plan: NetPlan, W: PreparedWeights, P: Dict[str, torch.Tensor], G: D
         dy_a1 = ws.dy_a1[b.out_hw]
         ops.conv_gemm(cur, W.w_dgrad[b.conv2.name], 1, 1, 1, mask_src=ws.a1[i],
                       colsum=G[b.conv1.bn + ".bias"], out=dy_a1,
-                      tile_n=TILE_N_WIDE if b.cout >= 256 else 0)
+                      tile_n=_dgrad_tile_n(b.cout))
         # identity / downsample branch
         if b.ds is not None:
             _wgrad(plan, P, G, ws, b.ds, x_in, cur, None)
@@ -404,7 +413,7 @@ def backward(plan: NetPlan, W: PreparedWeights, P: Dict[str, torch.Tensor], G: D
                               scatter_inputs=True)
         else:
             ops.conv_gemm(dy_a1, W.w_dgrad[b.conv1.name], 1, 1, 1, residual=res, mask_src=mask,
-                          colsum=colsum, out=dst, tile_n=TILE_N_WIDE if b.cin >= 256 else 0)
+                          colsum=colsum, out=dst, tile_n=_dgrad_tile_n(b.cin))
         notify(b.conv1.name)
         cur, ci = dst, ni
     # ---- max-pool + stem
