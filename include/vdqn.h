@@ -78,7 +78,9 @@ typedef struct vdqn_conv_desc {
   int32_t flags;       /* VDQN_EPI_* */
   int32_t tile_n;      /* 0 = auto (64/128/256) */
   int32_t max_ctas;    /* 0 = one per SM */
-  int32_t algo;        /* 0 = auto, 1 = im2col-TMA kernel, 2 = halo-tile kernel (Cout = 64 layers) */
+  int32_t algo;        /* 0 = auto, 1 = im2col-TMA kernel, 2 = halo-tile kernel (Cout = 64 layers),
+                        * 3 = im2col-TMA kernel on CTA pairs (tcgen05 cta_group::2, 256 x tile_n tiles;
+                        *     needs Cout >= 128 and an even number of 128-pixel tiles), 4 = never pairs */
   int32_t pad_hi_w;    /* upper padding along W when it differs from pad_hi (H); -1 = same */
   int32_t scatter_off_h, scatter_off_w; /* out_scatter == 2: opix = (n*2Ho + 2p + off_h)*2Wo + 2q + off_w */
   /* Two networks in one launch (online + target forward): images [split_n, N) use w2 / shift2, the

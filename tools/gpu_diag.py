@@ -51,7 +51,7 @@ def _report(name, out, ref, tol, extra=""):
     return ok
 
 
-def _conv_case(name, N, H, W, Cin, Cout, R, stride, pad, seed=0, tile_n=0, **epi):
+def _conv_case(name, N, H, W, Cin, Cout, R, stride, pad, seed=0, tile_n=0, algo=0, **epi):
     torch, F, ops = _imports()
     g = torch.Generator(device="cuda").manual_seed(seed)
     x = torch.randn(N, H, W, Cin, device="cuda", generator=g).to(torch.bfloat16)
@@ -79,7 +79,7 @@ def _conv_case(name, N, H, W, Cin, Cout, R, stride, pad, seed=0, tile_n=0, **epi
         kw["out_scatter"] = 2
     if epi.get("out2"):
         kw["out2"] = torch.zeros(N, 2 * ref.shape[1], 2 * ref.shape[2], Cout, device="cuda", dtype=torch.bfloat16)
-    out = ops.conv_gemm(x, w, stride, pad, tile_n=tile_n, **kw)
+    out = ops.conv_gemm(x, w, stride, pad, tile_n=tile_n, algo=algo, **kw)
     torch.cuda.synchronize()
     ok = True
     if epi.get("scatter"):
@@ -189,6 +189,70 @@ def conv_tile_n_variants():
     for tn in (64, 128, 256):
         ok &= _conv_case(f"conv_tile_n{tn}", 2, 14, 14, 128, 256, 3, 1, 1, tile_n=tn)
     return ok
+
+
+@case
+def pair_cases():
+    """cta_group::2 kernel (algo 3 = required): 256 x BN tiles over CTA pairs"""
+    ok = True
+    ok &= _conv_case("pair_l4", 10, 7, 7, 512, 512, 3, 1, 1, algo=3)
+    ok &= _conv_case("pair_l3_partial", 14, 14, 14, 256, 256, 3, 1, 1, algo=3, shift=True, residual=True, relu=True)
+    ok &= _conv_case("pair_l2_n128", 9, 28, 28, 128, 128, 3, 1, 1, algo=3, shift=True, residual=True, relu=True)
+    ok &= _conv_case("pair_l2_bwd", 9, 28, 28, 128, 128, 3, 1, 1, algo=3, residual=True, mask=True, colsum=True)
+    ok &= _conv_case("pair_l3_s2", 14, 28, 28, 128, 256, 3, 2, 1, algo=3, shift=True, relu=True)
+    ok &= _conv_case("pair_ds_1x1", 14, 28, 28, 128, 256, 1, 2, 0, algo=3, shift=True)
+    ok &= _conv_case("pair_big", 64, 14, 14, 256, 256, 3, 1, 1, algo=3, mask=True, colsum=True)
+    return ok
+
+
+@case
+def pair_dual():
+    """dual-network launch (two weight sets over two image ranges) on the pair and single-CTA kernels"""
+    torch, F, ops = _imports()
+    g = torch.Generator(device="cuda").manual_seed(11)
+    ok = True
+    for name, N, split, hw, C in (("dual_l3", 128, 64, 14, 256), ("dual_l2", 32, 16, 28, 128)):
+        x = torch.randn(N, hw, hw, C, device="cuda", generator=g).to(torch.bfloat16)
+        w1 = (torch.randn(C, 3, 3, C, device="cuda", generator=g) / (9 * C) ** 0.5).to(torch.bfloat16)
+        w2 = (torch.randn(C, 3, 3, C, device="cuda", generator=g) / (9 * C) ** 0.5).to(torch.bfloat16)
+        s1 = torch.randn(C, device="cuda", generator=g)
+        s2 = torch.randn(C, device="cuda", generator=g)
+        xf = x.float().permute(0, 3, 1, 2)
+        r1 = F.conv2d(xf[:split], w1.float().permute(0, 3, 1, 2), s1, 1, 1)
+        r2 = F.conv2d(xf[split:], w2.float().permute(0, 3, 1, 2), s2, 1, 1)
+        ref = torch.cat([r1, r2]).relu().permute(0, 2, 3, 1)
+        for algo in (3, 4):
+            out = ops.conv_gemm(x, w1, 1, 1, shift=s1, relu=True, w2=w2, shift2=s2, split_n=split, algo=algo)
+            torch.cuda.synchronize()
+            ok &= _report(f"{name}:algo{algo}", out, ref, 2e-2)
+    return ok
+
+
+@case
+def pair_speed():
+    """single-CTA vs CTA-pair kernel on the layer2-4 shapes at the bench batch (forward 3B and dgrad B)"""
+    torch, F, ops = _imports()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for name, N, hw, C in (("l2_fwd", 768, 28, 128), ("l3_fwd", 768, 14, 256), ("l4_fwd", 768, 7, 512),
+                           ("l2_bwd", 256, 28, 128), ("l3_bwd", 256, 14, 256), ("l4_bwd", 256, 7, 512)):
+        x = torch.randn(N, hw, hw, C, device="cuda", generator=g).to(torch.bfloat16)
+        w = (torch.randn(C, 3, 3, C, device="cuda", generator=g) / (9 * C) ** 0.5).to(torch.bfloat16)
+        out = torch.empty_like(x)
+        row = {}
+        for algo in (4, 3):
+            for _ in range(3):
+                ops.conv_gemm(x, w, 1, 1, relu=True, out=out, algo=algo)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                ops.conv_gemm(x, w, 1, 1, relu=True, out=out, algo=algo)
+            e1.record(); torch.cuda.synchronize()
+            row[algo] = e0.elapsed_time(e1) * 100
+        fl = 2.0 * N * hw * hw * C * C * 9
+        print(json.dumps({"case": "pair_speed:" + name, "single_us": round(row[4], 1), "pair_us": round(row[3], 1),
+                          "single_tflops": round(fl / row[4] / 1e6, 1), "pair_tflops": round(fl / row[3] / 1e6, 1)}))
+    return True
 
 
 @case

@@ -16,6 +16,8 @@
 //               tile's MMAs overlap), then + per-channel shift (folded BN / bias), + residual,
 //               ReLU or ReLU-mask (backward), optional per-channel column sums (d beta), bf16/fp32
 //               store, optional stride-2 scatter (zero-dilated gradient for strided dgrad).
+#include <stdlib.h>
+
 #include "epilogue.cuh"
 #include "ptx.cuh"
 #include "vdqn_internal.h"
@@ -37,12 +39,15 @@ struct IgemmArgs {
   const float* shift2;
 };
 
-template <int BN, int CK>
+// PAIR: the CTA is one half of a cta_group::2 pair -- the pair computes a 256 x BN tile, this CTA
+// stages its own 128 A rows and BN/2 of the B rows (see ptx.cuh)
+template <int BN, int CK, bool PAIR = false>
 struct IgemmCfg {
   static constexpr int BM = 128;
   static constexpr int KSUB = (CK == 64) ? 1 : 4;  // TMA sub-blocks per pipeline stage
   static constexpr int A_SUB_BYTES = BM * CK * 2;
-  static constexpr int B_SUB_BYTES = BN * CK * 2;
+  static constexpr int B_ROWS = PAIR ? BN / 2 : BN;
+  static constexpr int B_SUB_BYTES = B_ROWS * CK * 2;
   static constexpr int STAGE_BYTES = KSUB * (A_SUB_BYTES + B_SUB_BYTES);
   // staged epilogue tiles (per epilogue warp: out / residual / mask, 4 KB per 64-column group);
   // BN = 256 keeps the direct epilogue (its long K loops hide it) and all its smem for the pipeline
@@ -65,12 +70,12 @@ struct IgemmCfg {
   static constexpr int SBO = 8 * ROW_BYTES;         // 8-row group pitch
 };
 
-template <int BN, int CK>
+template <int BN, int CK, bool PAIR>
 __global__ void __launch_bounds__(192, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
              const __grid_constant__ CUtensorMap tmMask, const IgemmArgs a) {
-  using Cfg = IgemmCfg<BN, CK>;
+  using Cfg = IgemmCfg<BN, CK, PAIR>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t epi_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
@@ -100,26 +105,37 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
     for (int i = 0; i < Cfg::NACC; ++i) {
       mbar_init(tfull_bar(i), 1);
-      mbar_init(tempty_bar(i), 4);   // one arrive per epilogue warp
+      mbar_init(tempty_bar(i), PAIR ? 8 : 4);   // one arrive per epilogue warp (of both CTAs of a pair)
     }
     for (int i = 0; i < 4; ++i) mbar_init(ld_bar0 + 8u * i, 1);
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-    tmem_relinquish();
+    if (PAIR) {
+      tmem_alloc_pair(tmem_slot, Cfg::TMEM_COLS);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();      // the peer's barriers must be initialised before anything signals them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   pdl_wait();      // the previous kernel's global writes are visible from here on
 
-  // this CTA's slice of the tile space (whole launch, or one of the two networks' image ranges)
-  const bool second = a.split_cta > 0 && (int)blockIdx.x >= a.split_cta;
-  const int tile0 = (second ? a.split_m_tile * a.num_n_tiles : 0) + (int)blockIdx.x - (second ? a.split_cta : 0);
-  const int tstep = a.split_cta > 0 ? (second ? (int)gridDim.x - a.split_cta : a.split_cta) : (int)gridDim.x;
-  const int num_tiles = (a.split_cta > 0 && !second ? a.split_m_tile : a.num_m_tiles) * a.num_n_tiles;
+  // this CTA's slice of the tile space (whole launch, or one of the two networks' image ranges).
+  // PAIR: the schedule runs over CTA pairs and pairs of m-tiles; rank r takes m-tile 2*m_pair + r.
+  const int rank = PAIR ? (int)cluster_ctarank() : 0;
+  constexpr int MT = PAIR ? 2 : 1;
+  const int cta = (int)blockIdx.x / MT, ncta = (int)gridDim.x / MT;
+  const int split_cta = a.split_cta / MT, split_mt = a.split_m_tile / MT, n_mt = a.num_m_tiles / MT;
+  const bool second = split_cta > 0 && cta >= split_cta;
+  const int tile0 = (second ? split_mt * a.num_n_tiles : 0) + cta - (second ? split_cta : 0);
+  const int tstep = split_cta > 0 ? (second ? ncta - split_cta : split_cta) : ncta;
+  const int num_tiles = (split_cta > 0 && !second ? split_mt : n_mt) * a.num_n_tiles;
   const CUtensorMap* tmBp = second ? &tmB2 : &tmB;
   const int cblks = a.Cin / CK;
   const int num_sub = a.R * a.S * cblks;
@@ -131,7 +147,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     int stage = 0;
     uint32_t phase = 0;
     for (int t = tile0; t < num_tiles; t += tstep) {
-      const int n_t = t % a.num_n_tiles, m_t = t / a.num_n_tiles;
+      const int n_t = t % a.num_n_tiles, m_t = (t / a.num_n_tiles) * MT + rank;
       const int m0 = m_t * Cfg::BM;
       const int img = m0 / HoWo;
       const int rem = m0 - img * HoWo;
@@ -143,15 +159,23 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(empty_bar(stage), phase ^ 1);
         const bool leader = elect_one();
-        if (leader) mbar_expect_tx(full_bar(stage), Cfg::STAGE_BYTES);
+        // PAIR: the leader CTA's barrier collects the bytes of both CTAs' loads
+        if (leader && rank == 0) mbar_expect_tx(full_bar(stage), MT * Cfg::STAGE_BYTES);
+        const uint32_t fbar = PAIR ? mapa_u32(full_bar(stage), 0) : full_bar(stage);
         const uint32_t sA = smem_base + stage * Cfg::STAGE_BYTES;
         const uint32_t sB = sA + Cfg::KSUB * Cfg::A_SUB_BYTES;
 #pragma unroll
         for (int sub = 0; sub < Cfg::KSUB; ++sub) {
           if (leader) {
-            tma_load_im2col_4d(sA + sub * Cfg::A_SUB_BYTES, &tmA, full_bar(stage), c0, cw, ch, img,
-                               (uint16_t)off_w, (uint16_t)off_h);
-            tma_load_2d(sB + sub * Cfg::B_SUB_BYTES, tmBp, full_bar(stage), jk, n_t * BN);
+            if (PAIR) {
+              tma_load_im2col_4d_pair(sA + sub * Cfg::A_SUB_BYTES, &tmA, fbar, c0, cw, ch, img,
+                                      (uint16_t)off_w, (uint16_t)off_h);
+              tma_load_2d_pair(sB + sub * Cfg::B_SUB_BYTES, tmBp, fbar, jk, n_t * BN + rank * Cfg::B_ROWS);
+            } else {
+              tma_load_im2col_4d(sA + sub * Cfg::A_SUB_BYTES, &tmA, fbar, c0, cw, ch, img,
+                                 (uint16_t)off_w, (uint16_t)off_h);
+              tma_load_2d(sB + sub * Cfg::B_SUB_BYTES, tmBp, fbar, jk, n_t * BN);
+            }
           }
           jk += CK;
           c0 += CK;
@@ -166,8 +190,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
-    constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+    // ------------------------------------------------------------ MMA issuer (PAIR: leader CTA only)
+    constexpr uint32_t idesc = make_idesc_bf16(PAIR ? 256 : 128, BN, 0, 0);
+    if (PAIR && rank != 0) goto teardown;
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
@@ -191,11 +216,17 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                   make_smem_desc(sA + sub * Cfg::A_SUB_BYTES + k * 32, 16, Cfg::SBO, Cfg::SWZ);
               const uint64_t bd =
                   make_smem_desc(sB + sub * Cfg::B_SUB_BYTES + k * 32, 16, Cfg::SBO, Cfg::SWZ);
-              umma_f16(d_tmem, ad, bd, idesc, (kb | sub | k) != 0);
+              if (PAIR) umma_f16_pair(d_tmem, ad, bd, idesc, (kb | sub | k) != 0);
+              else umma_f16(d_tmem, ad, bd, idesc, (kb | sub | k) != 0);
             }
           }
-          umma_commit(empty_bar(stage));
-          if (kb == num_kb - 1) umma_commit(tfull_bar(acc));
+          if (PAIR) {
+            umma_commit_pair(empty_bar(stage));
+            if (kb == num_kb - 1) umma_commit_pair(tfull_bar(acc));
+          } else {
+            umma_commit(empty_bar(stage));
+            if (kb == num_kb - 1) umma_commit(tfull_bar(acc));
+          }
         }
         __syncwarp();
         if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
@@ -227,9 +258,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
       }
     };
+    // accumulator drained: tell the MMA issuer (PAIR: the leader CTA's barrier, counted over both CTAs)
+    auto release_acc = [&](int acc_i) {
+      if (PAIR) mbar_arrive_cluster(mapa_u32(tempty_bar(acc_i), 0));
+      else mbar_arrive(tempty_bar(acc_i));
+    };
     int it = 0;
     for (int t = tile0; t < num_tiles; t += tstep, ++it) {
-      const int n_t = t % a.num_n_tiles, m_t = t / a.num_n_tiles;
+      const int n_t = t % a.num_n_tiles, m_t = (t / a.num_n_tiles) * MT + rank;
       if (n_t != cs_nt) { flush_colsum(); cs_nt = n_t; }
       const int acc = it % Cfg::NACC;
       const uint32_t acc_phase = (it / Cfg::NACC) & 1;
@@ -239,7 +275,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const int row0 = m_t * Cfg::BM + quad * 32;            // this warp's 32 output rows
         // residual / mask tiles are prefetched one tile ahead (see halo_conv.cu)
         auto issue_inputs = [&](int tt) {
-          const int nn_t = tt % a.num_n_tiles, mm_t = tt / a.num_n_tiles;
+          const int nn_t = tt % a.num_n_tiles, mm_t = (tt / a.num_n_tiles) * MT + rank;
           const int r0 = mm_t * Cfg::BM + quad * 32;
           if (elect_one()) {
             mbar_expect_tx(ld_bar, Cfg::GROUPS * ((has_res ? 4096u : 0u) + (has_mask ? 4096u : 0u)));
@@ -274,7 +310,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(acc));
+        if (lane == 0) release_acc(acc);
         if (has_in) {
           ld_parity ^= 1;
           if (t + tstep < num_tiles) issue_inputs(t + tstep);
@@ -315,7 +351,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) release_acc(acc);
     }
     flush_colsum();
     if (Cfg::FAST_EPI && a.fast) {
@@ -324,22 +360,25 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
   }
 
+teardown:
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();      // neither CTA may exit while the other can still signal it
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if (PAIR) tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
+    else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
 // ---------------------------------------------------------------------------- host side
 
-template <int BN, int CK>
+template <int BN, int CK, bool PAIR = false>
 static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmB2,
                         const CUtensorMap* epi_maps, IgemmArgs& a, int num_sms, cudaStream_t stream) {
-  using Cfg = IgemmCfg<BN, CK>;
+  using Cfg = IgemmCfg<BN, CK, PAIR>;
   static bool attr_set = false;
-  auto kfn = igemm_kernel<BN, CK>;
+  auto kfn = igemm_kernel<BN, CK, PAIR>;
   if (!attr_set) {
     cudaError_t e =
         cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
@@ -347,20 +386,36 @@ static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
                                            cudaGetErrorString(e));
     attr_set = true;
   }
-  const int tiles = a.num_m_tiles * a.num_n_tiles;
-  int grid = tiles < num_sms ? tiles : num_sms;
+  // schedule units: CTAs over tiles, or (PAIR) CTA pairs over pairs of m-tiles
+  constexpr int MT = PAIR ? 2 : 1;
+  const int tiles = (a.num_m_tiles / MT) * a.num_n_tiles;
+  const int slots = num_sms / MT;
+  int grid = tiles < slots ? tiles : slots;
   if (a.split_m_tile > 0) {
     // two image ranges (two weight sets): give each its share of the SMs
-    const int t0 = a.split_m_tile * a.num_n_tiles, t1 = tiles - t0;
+    const int t0 = (a.split_m_tile / MT) * a.num_n_tiles, t1 = tiles - t0;
     if (t1 <= 0 || grid < 2) return set_error(VDQN_ERR_SHAPE, "conv_gemm: empty second image range");
     int g0 = (int)((long)grid * t0 / tiles);
     if (g0 < 1) g0 = 1;
     if (g0 > grid - 1) g0 = grid - 1;
-    a.split_cta = g0;
+    a.split_cta = g0 * MT;
   }
-  launch_kernel(kfn, grid, 192, Cfg::SMEM_BYTES, stream, tmA, tmB, tmB2, epi_maps[0], epi_maps[1], epi_maps[2], a);
+  if (PAIR)
+    launch_kernel_cluster(kfn, grid * 2, 192, Cfg::SMEM_BYTES, stream, 2, tmA, tmB, tmB2, epi_maps[0], epi_maps[1],
+                          epi_maps[2], a);
+  else
+    launch_kernel(kfn, grid, 192, Cfg::SMEM_BYTES, stream, tmA, tmB, tmB2, epi_maps[0], epi_maps[1], epi_maps[2], a);
   VDQN_CHECK_LAUNCH("igemm launch");
   return VDQN_OK;
+}
+
+// VDQN_PAIR=0 in the environment keeps every launch on the single-CTA kernel
+static bool pair_default() {
+  static const bool on = [] {
+    const char* e = getenv("VDQN_PAIR");
+    return e == nullptr || e[0] != '0';
+  }();
+  return on;
 }
 
 }  // namespace vdqn
@@ -401,7 +456,16 @@ extern "C" int vdqn_conv_gemm(const vdqn_conv_desc* d, void* stream_v) {
                            d->pad_hi - (d->R - 1) * d->dil, pad_hi_w - (d->S - 1) * d->dil,
                            CK == 64 ? 128 : 32);
   if (rc != VDQN_OK) return rc;
-  rc = make_tiled_map_2d(&tmB, d->w, (uint64_t)d->R * d->S * d->Cin, d->Cout, CK, BN,
+  // CTA pairs (cta_group::2, 256 x BN tiles): wide tiles of the 64-channel-block path, an even
+  // number of m-tiles (in both image ranges of a dual-network launch).  algo 3 demands it, 4 forbids.
+  const long M_total_l = (long)d->N * Ho * Wo;
+  const int m_tiles = (int)((M_total_l + 127) / 128);
+  bool pair = CK == 64 && BN >= 128 && m_tiles % 2 == 0 && d->algo != 4 && (d->algo == 3 || pair_default());
+  if (pair && d->split_n > 0 && (((long)d->split_n * Ho * Wo) / 128) % 2 != 0) pair = false;
+  if (d->algo == 3 && !pair)
+    return set_error(VDQN_ERR_SHAPE, "conv_gemm: CTA-pair kernel requested for an unsupported shape");
+  const int b_rows = pair ? BN / 2 : BN;
+  rc = make_tiled_map_2d(&tmB, d->w, (uint64_t)d->R * d->S * d->Cin, d->Cout, CK, b_rows,
                          CK == 64 ? 128 : 32);
   if (rc != VDQN_OK) return rc;
 
@@ -434,12 +498,16 @@ extern "C" int vdqn_conv_gemm(const vdqn_conv_desc* d, void* stream_v) {
     const long split_m = (long)d->split_n * Ho * Wo;
     if (d->w2 == nullptr || d->split_n >= d->N || split_m % 128 != 0)
       return set_error(VDQN_ERR_SHAPE, "conv_gemm: dual-network launch needs w2 and split_n*Ho*Wo %% 128 == 0");
-    rc = make_tiled_map_2d(&tmB2, d->w2, (uint64_t)d->R * d->S * d->Cin, d->Cout, CK, BN, CK == 64 ? 128 : 32);
+    rc = make_tiled_map_2d(&tmB2, d->w2, (uint64_t)d->R * d->S * d->Cin, d->Cout, CK, b_rows, CK == 64 ? 128 : 32);
     if (rc != VDQN_OK) return rc;
     a.split_m_tile = (int)(split_m / 128);
   }
   const int sms = d->max_ctas > 0 && d->max_ctas < dev->num_sms ? d->max_ctas : dev->num_sms;
   if (CK == 16) return launch_igemm<64, 16>(tmA, tmB, tmB2, epi_maps, a, sms, stream);
+  if (pair) {
+    if (BN == 128) return launch_igemm<128, 64, true>(tmA, tmB, tmB2, epi_maps, a, sms, stream);
+    return launch_igemm<256, 64, true>(tmA, tmB, tmB2, epi_maps, a, sms, stream);
+  }
   switch (BN) {
     case 64: return launch_igemm<64, 64>(tmA, tmB, tmB2, epi_maps, a, sms, stream);
     case 128: return launch_igemm<128, 64>(tmA, tmB, tmB2, epi_maps, a, sms, stream);
