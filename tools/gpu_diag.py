@@ -256,6 +256,38 @@ def pair_speed():
 
 
 @case
+def scatter_staged():
+    """zero-dilated destination with residual / mask indexed by the scattered pixel (parity-class
+    data gradients): staged epilogue with LSU row copies; BN = 64 / 128, single CTA and pair"""
+    torch, F, ops = _imports()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    ok = True
+    for name, N, hw, Cin, Cout, tile_n, algo in (("sc64", 5, 14, 128, 64, 0, 0), ("sc128", 5, 14, 256, 128, 0, 4),
+                                                 ("sc128_pair", 6, 16, 256, 128, 0, 3),
+                                                 ("sc256_t128", 9, 7, 512, 256, 128, 0)):
+        x = torch.randn(N, hw, hw, Cin, device="cuda", generator=g).to(torch.bfloat16)
+        w = (torch.randn(Cout, 2, 2, Cin, device="cuda", generator=g) / (4 * Cin) ** 0.5).to(torch.bfloat16)
+        res = torch.randn(N, 2 * hw, 2 * hw, Cout, device="cuda", generator=g).to(torch.bfloat16)
+        msk = torch.randn(N, 2 * hw, 2 * hw, Cout, device="cuda", generator=g).to(torch.bfloat16)
+        out = torch.zeros(N, 2 * hw, 2 * hw, Cout, device="cuda", dtype=torch.bfloat16)
+        colsum = torch.zeros(Cout, device="cuda")
+        # 2x2 taps, pad (0 low, 1 high): same spatial size
+        ref = F.conv2d(F.pad(x.float().permute(0, 3, 1, 2), (0, 1, 0, 1)), w.float().permute(0, 3, 1, 2))
+        ref = ref.permute(0, 2, 3, 1)
+        for pa, pb in ((1, 0), (0, 1)):
+            ops.conv_gemm(x, w, 1, 0, 1, residual=res, mask_src=msk, colsum=colsum, out=out, out_scatter=2,
+                          scatter_off=(pa, pb), scatter_inputs=True, tile_n=tile_n, algo=algo)
+            torch.cuda.synchronize()
+            want = (ref + res[:, pa::2, pb::2].float()) * (msk[:, pa::2, pb::2].float() > 0)
+            ok &= _report(f"{name}:({pa},{pb})", out[:, pa::2, pb::2], want, 2e-2)
+        untouched = out[:, 0::2, 0::2].float().abs().sum() + out[:, 1::2, 1::2].float().abs().sum()
+        ok &= abs(untouched.item()) == 0.0
+        cs_ref = out.float().reshape(-1, Cout).sum(0)
+        ok &= _report(name + ":colsum", colsum[None], cs_ref[None], 2e-3)
+    return ok
+
+
+@case
 def halo_conv_cases():
     ok = True
     ok &= _conv_case("halo_20x28", 3, 20, 28, 64, 64, 3, 1, 1, shift=True, residual=True, relu=True)

@@ -288,7 +288,40 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           }
           __syncwarp();
         };
-        if (has_in && it == 0) issue_inputs(t);
+        // scatter launches (zero-dilated destination: parity-class data gradients): the same staged
+        // tiles, but rows live at per-pixel addresses a tensor map cannot describe, so the LSU moves
+        // them -- eight lanes per 128-byte row (whole sectors), cp.async for the inputs
+        const bool gather = a.out_scatter == 2;
+        auto scatter_pix = [&](int mm) -> long {
+          if (mm >= a.M_total) return -1;
+          const int img = mm / HoWo;
+          const int rem = mm - img * HoWo;
+          const int p = rem / a.Wo, q = rem - p * a.Wo;
+          return ((long)img * (2 * a.Ho) + 2 * p + a.off_h) * (2 * a.Wo) + 2 * q + a.off_w;
+        };
+        auto gather_inputs = [&](int tt) {
+          const int nn_t = tt % a.num_n_tiles, mm_t = (tt / a.num_n_tiles) * MT + rank;
+          const long pix = scatter_pix(mm_t * Cfg::BM + quad * 32 + lane);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = 4 * i + (lane >> 3);
+            const long pr = __shfl_sync(0xffffffffu, pix, r);
+            const uint32_t dst = (uint32_t)r * 128u + ((uint32_t)((lane & 7) ^ (r & 7)) << 4);
+            const uint32_t nb = pr >= 0 ? 16u : 0u;
+            const long prc = pr >= 0 ? pr : 0;
+#pragma unroll
+            for (int gidx = 0; gidx < Cfg::GROUPS; ++gidx) {
+              const int col = nn_t * BN + gidx * 64 + (lane & 7) * 8;
+              if (has_res) cp_async_16(stg_in + gidx * 4096 + dst, epi.residual + prc * epi.ldr + col, nb);
+              if (has_mask)
+                cp_async_16(stg_in + (Cfg::GROUPS + gidx) * 4096 + dst, epi.mask_src + prc * epi.ldm + col, nb);
+            }
+          }
+          cp_async_commit();
+        };
+        if (has_in && it == 0) {
+          if (gather) gather_inputs(t); else issue_inputs(t);
+        }
         mbar_wait(tfull_bar(acc), acc_phase);
         tc_fence_after();
         const uint32_t stg = stg_out_base + (uint32_t)((it % Cfg::OUT_BUFS) * Cfg::GROUPS) * 4096u;
@@ -299,7 +332,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           uint32_t raw[32];
           tmem_ld_32x32(tmem_base + acc * BN + chunk * 32 + ((uint32_t)(quad * 32) << 16), raw);
           tmem_ld_wait();
-          if (chunk == 0 && has_in) mbar_wait(ld_bar, ld_parity);
+          if (chunk == 0 && has_in) {
+            if (gather) { cp_async_wait_all(); __syncwarp(); }
+            else mbar_wait(ld_bar, ld_parity);
+          }
           const int gidx = chunk >> 1;
           const float cs = epilogue_half_staged(epi, raw, valid, n_t * BN + chunk * 32, chunk & 1, lane,
                                                 stg + gidx * 4096, stg_in + gidx * 4096,
@@ -313,7 +349,28 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (lane == 0) release_acc(acc);
         if (has_in) {
           ld_parity ^= 1;
-          if (t + tstep < num_tiles) issue_inputs(t + tstep);
+          if (t + tstep < num_tiles) {
+            if (gather) gather_inputs(t + tstep); else issue_inputs(t + tstep);
+          }
+        }
+        if (gather) {
+          __syncwarp();                       // the staged tile is complete
+          const long pix = scatter_pix(m);
+          __nv_bfloat16* obase = static_cast<__nv_bfloat16*>(epi.out);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = 4 * i + (lane >> 3);
+            const long pr = __shfl_sync(0xffffffffu, pix, r);
+            const uint32_t src = (uint32_t)r * 128u + ((uint32_t)((lane & 7) ^ (r & 7)) << 4);
+#pragma unroll
+            for (int gidx = 0; gidx < Cfg::GROUPS; ++gidx) {
+              const uint4 v4 = lds128(stg + gidx * 4096 + src);
+              if (pr >= 0)
+                *reinterpret_cast<uint4*>(obase + pr * epi.ldc + n_t * BN + gidx * 64 + (lane & 7) * 8) = v4;
+            }
+          }
+          __syncwarp();
+          continue;
         }
         fence_proxy_async();
         __syncwarp();
@@ -484,7 +541,7 @@ extern "C" int vdqn_conv_gemm(const vdqn_conv_desc* d, void* stream_v) {
   // staged epilogue: 2-D maps over the [M][ld] output / residual / mask matrices, 64 x 32 boxes
   CUtensorMap epi_maps[3] = {tmB, tmB, tmB};
   a.fast = (BN <= 128 && fast_epilogue_ok(d)) ? 1 : 0;
-  if (a.fast) {
+  if (a.fast && d->out_scatter != 2) {     // scatter launches move the staged tiles with the LSU
     rc = make_tiled_map_2d(&epi_maps[0], d->out, d->Cout, a.M_total, 64, 32, 128, d->ldc);
     if (rc == VDQN_OK && d->residual)
       rc = make_tiled_map_2d(&epi_maps[1], d->residual, d->Cout, a.M_total, 64, 32, 128, d->ldr);

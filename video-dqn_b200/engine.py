@@ -284,6 +284,11 @@ TILE_N_WIDE = int(_os.environ.get("VDQN_TILE_N_WIDE", "0"))
 TILE_N_DGRAD4 = int(_os.environ.get("VDQN_TILE_N_DGRAD4", "0"))
 
 
+def _scatter_tile_n(ch: int) -> int:
+    """zero-dilated (stride-2) data gradients: column tiles of at most 128 keep the staged epilogue"""
+    return 128 if ch >= 256 else 0
+
+
 def _dgrad_tile_n(ch: int) -> int:
     if ch >= 512 and TILE_N_DGRAD4:
         return TILE_N_DGRAD4
@@ -392,7 +397,7 @@ def backward(plan: NetPlan, W: PreparedWeights, P: Dict[str, torch.Tensor], G: D
         if b.ds is not None:
             _wgrad(plan, P, G, ws, b.ds, x_in, cur, None)
             res = ws.r_dil[b.out_hw]
-            ops.conv_gemm(cur, W.w_dgrad[b.ds.name], 1, 0, 0, out=res, out_scatter=2)
+            ops.conv_gemm(cur, W.w_dgrad[b.ds.name], 1, 0, 0, out=res, out_scatter=2, tile_n=_scatter_tile_n(b.cin))
         else:
             res = cur
         # conv1: weight gradient, then the gradient wrt the block input (+ identity branch),
@@ -410,7 +415,7 @@ def backward(plan: NetPlan, W: PreparedWeights, P: Dict[str, torch.Tensor], G: D
             for pa, pb, wf in parity_filters(W, b.conv1):
                 ops.conv_gemm(dy_a1, wf, 1, 0, wf.shape[1] - 1, pad_hi_w=wf.shape[2] - 1, residual=res,
                               mask_src=mask, colsum=colsum, out=dst, out_scatter=2, scatter_off=(pa, pb),
-                              scatter_inputs=True)
+                              scatter_inputs=True, tile_n=_scatter_tile_n(b.cin))
         else:
             ops.conv_gemm(dy_a1, W.w_dgrad[b.conv1.name], 1, 1, 1, residual=res, mask_src=mask,
                           colsum=colsum, out=dst, tile_n=_dgrad_tile_n(b.cin))
