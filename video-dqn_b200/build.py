@@ -41,6 +41,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(objdir, exist_ok=True)
     deps = _deps()
     flags = [f for f in FLAGS if not f.startswith("--use_fast_math")]
+    # extra defines for instrumented builds (tools/role_profile.py: -DVDQN_ROLE_PROFILE)
+    flags += os.environ.get("VDQN_NVCC_FLAGS", "").split()
 
     def compile_one(src):
         obj = os.path.join(objdir, src.replace(".cu", ".o"))

@@ -141,6 +141,11 @@ __device__ __forceinline__ float epilogue_chunk(const EpiArgs& a, const uint32_t
 // 16-byte shared accesses instead of 32 different cache lines per instruction.
 // One call handles 32 accumulator columns [half*32, half*32+32) of the warp's current 64-column
 // group: `stg_*` are the warp's staging tiles (1024-byte aligned), `c0` the first global channel.
+//
+// ROW_BYTES = 128: 64-column tiles (128B swizzle), `half` selects the 32 columns inside the row.
+// ROW_BYTES = 64: the tile IS 32 columns wide (64-byte rows, 64B swizzle; `half` unused) -- used
+// when every epilogue warp owns its own 32-column slice (two warps per TMEM lane quadrant).
+template <int ROW_BYTES = 128>
 __device__ __forceinline__ float epilogue_half_staged(const EpiArgs& a, const uint32_t (&raw)[32], bool valid,
                                                       int c0, int half, int lane, uint32_t stg_out,
                                                       uint32_t stg_res, uint32_t stg_mask) {
@@ -155,8 +160,9 @@ __device__ __forceinline__ float epilogue_half_staged(const EpiArgs& a, const ui
       v[4 * j + 0] += s4.x; v[4 * j + 1] += s4.y; v[4 * j + 2] += s4.z; v[4 * j + 3] += s4.w;
     }
   }
-  const uint32_t row_off = (uint32_t)lane * 128u;
-  const uint32_t sw = (uint32_t)(lane & 7);
+  const uint32_t row_off = (uint32_t)lane * (uint32_t)ROW_BYTES;
+  const uint32_t sw = ROW_BYTES == 128 ? (uint32_t)(lane & 7) : (uint32_t)((lane >> 1) & 3);
+  if (ROW_BYTES == 64) half = 0;
   if (a.residual != nullptr) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {

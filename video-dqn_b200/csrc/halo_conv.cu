@@ -18,6 +18,28 @@
 
 namespace vdqn {
 
+// Instrumented build (-DVDQN_ROLE_PROFILE, tools/role_profile.py): every role records the cycles it
+// spent blocked on its two kinds of waits and its total loop time, per CTA -- the role that never
+// waits is the bottleneck.  Compiles to nothing otherwise.
+#ifdef VDQN_ROLE_PROFILE
+__device__ unsigned long long g_role_prof[160 * 16 * 4];
+#define PROF_BEGIN long long prof_wa = 0, prof_wb = 0, prof_n = 0; const long long prof_t0 = clock64();
+#define PROF_WAIT_A(x) { const long long w0_ = clock64(); x; prof_wa += clock64() - w0_; }
+#define PROF_WAIT_B(x) { const long long w0_ = clock64(); x; prof_wb += clock64() - w0_; }
+#define PROF_TILE ++prof_n;
+#define PROF_END(role)                                                                   \
+  if (lane == 0) {                                                                       \
+    unsigned long long* p_ = g_role_prof + ((size_t)blockIdx.x * 16 + (role)) * 4;       \
+    p_[0] = prof_wa; p_[1] = prof_wb; p_[2] = clock64() - prof_t0; p_[3] = prof_n;       \
+  }
+#else
+#define PROF_BEGIN
+#define PROF_WAIT_A(x) x;
+#define PROF_WAIT_B(x) x;
+#define PROF_TILE
+#define PROF_END(role)
+#endif
+
 struct HaloArgs {
   int N, H, W, Cout;
   int R, S, pad_lo;
@@ -44,8 +66,15 @@ struct HaloCfg {
   static constexpr int W_TILE_BYTES = BN * ROW_BYTES;              // one tap: 64 rows x CK
   static constexpr int W_BYTES = MAX_TAPS * W_TILE_BYTES;          // 72 KB / 32 KB, resident
   static constexpr int STAGES = (CK == 64) ? 3 : 16;
-  static constexpr int EPI_WARP_BYTES = 4 * 4096;                  // out x2 (double-buffered), residual, mask
-  static constexpr int EPI_BYTES = 4 * EPI_WARP_BYTES;
+  // EIGHT epilogue warps, two per TMEM lane quadrant, each owning 32 of the 64 output columns with
+  // private staging tiles [32 pixels][32 ch] (64-byte rows, 64B swizzle): out x2, residual, mask.
+  // (role profile: with four warps the epilogue was the longest role of every variant of this kernel
+  //  -- 1900 cycles per tile against 950 of MMA issue for the stem -- a single warp per scheduler
+  //  cannot hide its own TMEM / shared-memory / mbarrier latencies.)
+  static constexpr int EPI_WARPS = 8;
+  static constexpr int EPI_WARP_BYTES = 4 * 2048;
+  static constexpr int EPI_BYTES = EPI_WARPS * EPI_WARP_BYTES;
+  static constexpr int THREADS = (4 + 1 + EPI_WARPS) * 32;
   static constexpr int SMEM_BYTES = W_BYTES + STAGES * STAGE_BYTES + EPI_BYTES + 1024 + 512;
   // accumulator ring: with 64-column accumulators TMEM holds 4 of them, so the MMA warp can run up to
   // 4 tiles ahead of the epilogue and the mbarrier hand-off latencies (MMA -> epilogue -> MMA) overlap
@@ -63,7 +92,7 @@ __device__ __forceinline__ void tma_load_tiled_4d(uint32_t dst, const void* tmap
 }
 
 template <int CK>
-__global__ void __launch_bounds__(288, 1)
+__global__ void __launch_bounds__(HaloCfg<CK>::THREADS, 1)
 halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                  const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
                  const __grid_constant__ CUtensorMap tmMask, const HaloArgs a) {
@@ -79,8 +108,8 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   auto tfull_bar = [&](int i) { return bar_base + 8u * (2 * Cfg::STAGES + i); };
   auto tempty_bar = [&](int i) { return bar_base + 8u * (2 * Cfg::STAGES + Cfg::NACC + i); };
   const uint32_t w_bar = bar_base + 8u * (2 * Cfg::STAGES + 2 * Cfg::NACC);
-  const uint32_t ld_bar0 = w_bar + 8u;                                  // 4 barriers, one per epilogue warp
-  const uint32_t tmem_slot = w_bar + 8u * 5;
+  const uint32_t ld_bar0 = w_bar + 8u;                                  // one barrier per epilogue warp
+  const uint32_t tmem_slot = w_bar + 8u * (1 + Cfg::EPI_WARPS);
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
@@ -97,14 +126,15 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     }
     for (int i = 0; i < Cfg::NACC; ++i) {
       mbar_init(tfull_bar(i), 1);
-      mbar_init(tempty_bar(i), 4);
+      mbar_init(tempty_bar(i), Cfg::EPI_WARPS);
     }
     mbar_init(w_bar, 1);
-    for (int i = 0; i < 4; ++i) mbar_init(ld_bar0 + 8u * i, 1);
+    for (int i = 0; i < Cfg::EPI_WARPS; ++i) mbar_init(ld_bar0 + 8u * i, 1);
     fence_mbar_init();
   }
   // warps 0-3: producers (the cp.async variant uses all four, the TMA variant only warp 0),
-  // warp 4: MMA issuer + TMEM owner, warps 5-8: epilogue (TMEM lane quadrant = warp & 3)
+  // warp 4: MMA issuer + TMEM owner, warps 5-12: epilogue (TMEM lane quadrant = warp & 3, column
+  // half = (warp - 5) / 4)
   if (warp == 4) {
     tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
     tmem_relinquish();
@@ -121,13 +151,25 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   const int tile_end = (a.split_cta > 0 && !second) ? a.split_tile : a.num_tiles;
   const CUtensorMap* tmWp = second ? &tmW2 : &tmW;
 
-  auto decode = [&](int t, int& n, int& h0, int& w0) {
-    const int tw = t % a.tiles_w;
+  // Tile coordinates advance incrementally (a role is one warp walking its tiles in order; integer
+  // divisions per tile would sit on its critical path): `step` tiles = (dn images, dth rows, dtw cols).
+  struct TileIt { int tw, th, n, dtw, dth, dn; };
+  auto tile_it = [&](int t, int step) {
+    TileIt c;
+    c.tw = t % a.tiles_w;
     const int r = t / a.tiles_w;
-    const int th = r % a.tiles_h;
-    n = r / a.tiles_h;
-    h0 = th * Cfg::TH;
-    w0 = tw * Cfg::TW;
+    c.th = r % a.tiles_h;
+    c.n = r / a.tiles_h;
+    c.dtw = step % a.tiles_w;
+    const int rs = step / a.tiles_w;
+    c.dth = rs % a.tiles_h;
+    c.dn = rs / a.tiles_h;
+    return c;
+  };
+  auto advance = [&](TileIt& c) {
+    c.tw += c.dtw; c.th += c.dth; c.n += c.dn;
+    if (c.tw >= a.tiles_w) { c.tw -= a.tiles_w; ++c.th; }
+    if (c.th >= a.tiles_h) { c.th -= a.tiles_h; ++c.n; }
   };
 
   if (warp < 4) {
@@ -162,11 +204,13 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       }
       int issued = 0, done_k = warp;
       int k = warp;
-      for (int t = tile0 + warp * tstep; t < tile_end; t += 4 * tstep, k += 4) {
-        int n, h0, w0;
-        decode(t, n, h0, w0);
+      PROF_BEGIN
+      TileIt ti = tile_it(tile0 + warp * tstep, 4 * tstep);
+      for (int t = tile0 + warp * tstep; t < tile_end; t += 4 * tstep, k += 4, advance(ti)) {
+        const int n = ti.n, h0 = ti.th * Cfg::TH, w0 = ti.tw * Cfg::TW;
+        PROF_TILE
         const int stage = k % Cfg::STAGES;
-        mbar_wait(empty_bar(stage), (((uint32_t)(k / Cfg::STAGES)) & 1u) ^ 1u);
+        PROF_WAIT_A(mbar_wait(empty_bar(stage), (((uint32_t)(k / Cfg::STAGES)) & 1u) ^ 1u))
         const uint32_t base = sA0 + stage * Cfg::STAGE_BYTES;
         const __nv_bfloat16* img = a.x + (long)n * a.H * a.W * 16;
 #pragma unroll
@@ -182,12 +226,13 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         asm volatile("cp.async.commit_group;" ::: "memory");
         ++issued;
         if (issued >= DEPTH) {          // this warp's oldest in-flight tile has landed: publish it
-          asm volatile("cp.async.wait_group %0;" ::"n"(DEPTH - 1) : "memory");
+          PROF_WAIT_B(asm volatile("cp.async.wait_group %0;" ::"n"(DEPTH - 1) : "memory"))
           fence_proxy_async();
           mbar_arrive(full_bar(done_k % Cfg::STAGES));
           done_k += 4;
         }
       }
+      PROF_END(warp)
       asm volatile("cp.async.wait_group 0;" ::: "memory");
       fence_proxy_async();
       const int pending = issued < DEPTH - 1 ? issued : DEPTH - 1;
@@ -198,10 +243,12 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     } else if (warp == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = tile0; t < tile_end; t += tstep) {
-        int n, h0, w0;
-        decode(t, n, h0, w0);
-        mbar_wait(empty_bar(stage), phase ^ 1);
+      PROF_BEGIN
+      TileIt ti = tile_it(tile0, tstep);
+      for (int t = tile0; t < tile_end; t += tstep, advance(ti)) {
+        const int n = ti.n, h0 = ti.th * Cfg::TH, w0 = ti.tw * Cfg::TW;
+        PROF_TILE
+        PROF_WAIT_A(mbar_wait(empty_bar(stage), phase ^ 1))
         if (elect_one()) {
           mbar_expect_tx(full_bar(stage), Cfg::HALO_BYTES);
           tma_load_tiled_4d(sA0 + stage * Cfg::STAGE_BYTES, &tmX, full_bar(stage), 0, w0 - a.pad_lo,
@@ -210,6 +257,7 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         __syncwarp();
         if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
       }
+      PROF_END(0)
     }
   } else if (warp == 4) {
     constexpr uint32_t idesc = make_idesc_bf16(128, Cfg::BN, 0, 0);
@@ -217,11 +265,13 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
+    PROF_BEGIN
     for (int t = tile0; t < tile_end; t += tstep, ++it) {
       const int acc = it % Cfg::NACC;
       const uint32_t acc_phase = (it / Cfg::NACC) & 1;
-      mbar_wait(tempty_bar(acc), acc_phase ^ 1);
-      mbar_wait(full_bar(stage), phase);
+      PROF_TILE
+      PROF_WAIT_A(mbar_wait(tempty_bar(acc), acc_phase ^ 1))
+      PROF_WAIT_B(mbar_wait(full_bar(stage), phase))
       tc_fence_after();
       if (elect_one()) {
         const uint32_t d_tmem = tmem_base + acc * Cfg::BN;
@@ -248,92 +298,82 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       __syncwarp();
       if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
     }
+    PROF_END(4)
   } else {
-    const int quad = warp & 3;
+    const int ew = warp - 5;                  // 0..7
+    const int quad = warp & 3;                // TMEM lane quadrant this warp may touch
+    const int half = ew >> 2;                 // its 32 output columns: [half*32, half*32 + 32)
     const int row = quad * 32 + lane;
     const int g = row >> 3, j = row & 7;
-    const uint32_t stg_out0 = epi_base + quad * Cfg::EPI_WARP_BYTES;
-    const uint32_t stg_res = stg_out0 + 8192, stg_mask = stg_out0 + 12288;
-    const uint32_t ld_bar = ld_bar0 + 8u * quad;
+    const uint32_t stg_out0 = epi_base + ew * Cfg::EPI_WARP_BYTES;
+    const uint32_t stg_res = stg_out0 + 4096, stg_mask = stg_out0 + 6144;
+    const uint32_t ld_bar = ld_bar0 + 8u * ew;
+    const int c0 = half * 32;
     EpiArgs epi = a.epi;
     if (second) epi.shift = a.shift2;
     const bool has_res = epi.residual != nullptr, has_mask = epi.mask_src != nullptr;
     const bool has_in = has_res || has_mask;
     uint32_t ld_parity = 0;
-    float csum[2] = {0.f, 0.f};          // per-lane column sums (channels lane, 32 + lane) over all tiles
+    float csum = 0.f;                    // per-lane column sum (channel c0 + lane) over all tiles
     int it = 0;
+    PROF_BEGIN
+    TileIt ti = tile_it(tile0, tstep);
+    // this warp's 32 pixels = image rows h0+4*quad .. +3, 8 pixels each: a [1][4][8][32] TMA box.
+    // Residual / mask tiles are prefetched ONE TILE AHEAD (issued as soon as the previous tile has
+    // consumed the staging tiles), so their L2/HBM latency hides behind a whole tile of work.
+    auto issue_inputs = [&](const TileIt& c) {
+      if (elect_one()) {
+        mbar_expect_tx(ld_bar, (has_res ? 2048u : 0u) + (has_mask ? 2048u : 0u));
+        if (has_res) tma_load_4d(stg_res, &tmRes, ld_bar, c0, c.tw * Cfg::TW, c.th * Cfg::TH + 4 * quad, c.n);
+        if (has_mask) tma_load_4d(stg_mask, &tmMask, ld_bar, c0, c.tw * Cfg::TW, c.th * Cfg::TH + 4 * quad, c.n);
+      }
+      __syncwarp();
+    };
+    if (a.fast && has_in && tile0 < tile_end) issue_inputs(ti);
     for (int t = tile0; t < tile_end; t += tstep, ++it) {
-      int n, h0, w0;
-      decode(t, n, h0, w0);
+      const int n = ti.n, h0 = ti.th * Cfg::TH, w0 = ti.tw * Cfg::TW;
+      advance(ti);                         // ti = the NEXT tile from here on
+      PROF_TILE
       const int acc = it % Cfg::NACC;
       const uint32_t acc_phase = (it / Cfg::NACC) & 1;
       const int h = h0 + g, w = w0 + j;
       const bool valid = h < a.H && w < a.W;
-      const long opix = ((long)n * a.H + h) * a.W + w;
+      PROF_WAIT_A(mbar_wait(tfull_bar(acc), acc_phase))
+      tc_fence_after();
+      uint32_t raw[32];
+      tmem_ld_32x32(tmem_base + acc * Cfg::BN + c0 + ((uint32_t)(quad * 32) << 16), raw);
       if (a.fast) {
-        // this warp's 32 pixels = image rows h0+4*quad .. +3, 8 pixels each: a [1][4][8][64] TMA box.
-        // Residual / mask tiles are prefetched ONE TILE AHEAD (issued as soon as the previous tile has
-        // consumed the staging tiles), so their L2/HBM latency hides behind a whole tile of work.
-        auto issue_inputs = [&](int tt) {
-          int nn, hh0, ww0;
-          decode(tt, nn, hh0, ww0);
-          if (elect_one()) {
-            mbar_expect_tx(ld_bar, (has_res ? 4096u : 0u) + (has_mask ? 4096u : 0u));
-            if (has_res) tma_load_4d(stg_res, &tmRes, ld_bar, 0, ww0, hh0 + 4 * quad, nn);
-            if (has_mask) tma_load_4d(stg_mask, &tmMask, ld_bar, 0, ww0, hh0 + 4 * quad, nn);
-          }
-          __syncwarp();
-        };
-        if (has_in && it == 0) issue_inputs(t);
-        mbar_wait(tfull_bar(acc), acc_phase);
-        tc_fence_after();
-        const uint32_t stg_out = stg_out0 + (uint32_t)(it & 1) * 4096u;
-        if (elect_one()) tma_store_wait_read<1>();      // the store from two tiles ago has left this buffer
-        __syncwarp();
+        const uint32_t stg_out = stg_out0 + (uint32_t)(it & 1) * 2048u;
+        PROF_WAIT_B(if (elect_one()) tma_store_wait_read<1>(); __syncwarp())      // the store from two tiles ago has left this buffer
+        tmem_ld_wait();
+        if (has_in) PROF_WAIT_B(mbar_wait(ld_bar, ld_parity))
         if (!(epi.flags & 32))          // flag 32: debug, skip the epilogue math (bottleneck probing)
-#pragma unroll 1
-        for (int half = 0; half < 2; ++half) {
-          uint32_t raw[32];
-          tmem_ld_32x32(tmem_base + acc * Cfg::BN + half * 32 + ((uint32_t)(quad * 32) << 16), raw);
-          tmem_ld_wait();
-          if (half == 0 && has_in) mbar_wait(ld_bar, ld_parity);
-          const float cs = epilogue_half_staged(epi, raw, valid, half * 32, half, lane, stg_out, stg_res, stg_mask);
-          if (half == 0) csum[0] += cs; else csum[1] += cs;
-        }
+          csum += epilogue_half_staged<64>(epi, raw, valid, c0, 0, lane, stg_out, stg_res, stg_mask);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar(acc));
         if (has_in) {
           ld_parity ^= 1;
-          if (t + tstep < tile_end) issue_inputs(t + tstep);   // staging tiles are free again
+          if (t + tstep < tile_end) issue_inputs(ti);   // staging tiles are free again
         }
         fence_proxy_async();
         __syncwarp();
         if (elect_one() && !(epi.flags & 8)) {      // flag 8: debug, skip the store (bottleneck probing)
-          tma_store_4d(&tmOut, stg_out, 0, w0, h0 + 4 * quad, n);
+          tma_store_4d(&tmOut, stg_out, c0, w0, h0 + 4 * quad, n);
           tma_store_commit();
         }
         __syncwarp();
         continue;
       }
-      mbar_wait(tfull_bar(acc), acc_phase);
-      tc_fence_after();
-#pragma unroll 1
-      for (int chunk = 0; chunk < Cfg::BN / 32; ++chunk) {
-        uint32_t raw[32];
-        tmem_ld_32x32(tmem_base + acc * Cfg::BN + chunk * 32 + ((uint32_t)(quad * 32) << 16), raw);
-        tmem_ld_wait();
-        const float cs = epilogue_chunk(epi, raw, valid, opix, opix, 0, chunk * 32, lane);
-        if (chunk == 0) csum[0] += cs; else csum[1] += cs;
-      }
+      tmem_ld_wait();
+      const long opix = ((long)n * a.H + h) * a.W + w;
+      csum += epilogue_chunk(epi, raw, valid, opix, opix, 0, c0, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(acc));
     }
-    if (a.epi.colsum != nullptr) {
-      atomicAdd(a.epi.colsum + lane, csum[0]);
-      atomicAdd(a.epi.colsum + 32 + lane, csum[1]);
-    }
+    PROF_END(5 + ew)
+    if (a.epi.colsum != nullptr) atomicAdd(a.epi.colsum + c0 + lane, csum);
     if (a.fast) {
       if (elect_one()) tma_store_wait<0>();
       __syncwarp();
@@ -374,9 +414,10 @@ static int launch_halo(const vdqn_conv_desc* d, cudaStream_t stream) {
   const bool fast = fast_epilogue_ok(d) && d->ldc == d->Cout && (!d->residual || d->ldr == d->Cout) &&
                     (!d->mask_src || d->ldm == d->Cout);
   if (fast) {
-    rc = make_tiled_map_nhwc(&tmOut, d->out, d->N, d->H, d->W, d->Cout, 64, 8, 4, 128);
-    if (rc == VDQN_OK && d->residual) rc = make_tiled_map_nhwc(&tmRes, d->residual, d->N, d->H, d->W, d->Cout, 64, 8, 4, 128);
-    if (rc == VDQN_OK && d->mask_src) rc = make_tiled_map_nhwc(&tmMask, d->mask_src, d->N, d->H, d->W, d->Cout, 64, 8, 4, 128);
+    // per-warp tiles: 32 channels x 8 x 4 pixels, 64-byte rows
+    rc = make_tiled_map_nhwc(&tmOut, d->out, d->N, d->H, d->W, d->Cout, 32, 8, 4, 64);
+    if (rc == VDQN_OK && d->residual) rc = make_tiled_map_nhwc(&tmRes, d->residual, d->N, d->H, d->W, d->Cout, 32, 8, 4, 64);
+    if (rc == VDQN_OK && d->mask_src) rc = make_tiled_map_nhwc(&tmMask, d->mask_src, d->N, d->H, d->W, d->Cout, 32, 8, 4, 64);
     if (rc != VDQN_OK) return rc;
   }
   HaloArgs a{};
@@ -403,7 +444,7 @@ static int launch_halo(const vdqn_conv_desc* d, cudaStream_t stream) {
     if (g0 > grid - 1) g0 = grid - 1;
     a.split_cta = g0;
   }
-  launch_kernel(kfn, grid, 288, Cfg::SMEM_BYTES, stream, tmX, tmW, tmW2, tmOut, tmRes, tmMask, a);
+  launch_kernel(kfn, grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream, tmX, tmW, tmW2, tmOut, tmRes, tmMask, a);
   VDQN_CHECK_LAUNCH("halo_conv launch");
   return VDQN_OK;
 }
@@ -429,3 +470,14 @@ int halo_conv_launch(const vdqn_conv_desc* d, cudaStream_t stream) {
 }
 
 }  // namespace vdqn
+
+// instrumented builds only (not part of include/vdqn.h): copies the per-CTA role counters
+extern "C" int vdqn_debug_role_profile(unsigned long long* out, int count) {
+#ifdef VDQN_ROLE_PROFILE
+  cudaError_t e = cudaMemcpyFromSymbol(out, vdqn::g_role_prof, sizeof(unsigned long long) * count);
+  return e == cudaSuccess ? 0 : -1;
+#else
+  (void)out; (void)count;
+  return -2;
+#endif
+}
