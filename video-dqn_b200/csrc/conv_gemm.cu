@@ -12,7 +12,8 @@
 //               traversal stride); B tile = BN x CK slab of the weight matrix (tiled TMA).
 //   warp 1    : allocates TMEM, issues tcgen05.mma (M=128, N=BN, K=16) from one elected lane,
 //               releases smem stages / publishes accumulators with tcgen05.commit.
-//   warps 2-5 : epilogue.  tcgen05.ld the fp32 accumulator (double-buffered in TMEM so the next
+//   warps 2-9 : epilogue, two warps per TMEM lane quadrant, each owning every other 32-column chunk
+//               of the tile.  tcgen05.ld the fp32 accumulator (a ring in TMEM so the next
 //               tile's MMAs overlap), then + per-channel shift (folded BN / bias), + residual,
 //               ReLU or ReLU-mask (backward), optional per-channel column sums (d beta), bf16/fp32
 //               store, optional stride-2 scatter (zero-dilated gradient for strided dgrad).
@@ -55,8 +56,12 @@ struct IgemmCfg {
   static constexpr int GROUPS = BN / 64;
   // BN = 64: the out tile is double-buffered so a tile never waits for the previous tile's TMA store
   static constexpr int OUT_BUFS = (GROUPS == 1) ? 2 : 1;
-  static constexpr int EPI_WARP_BYTES = FAST_EPI ? (GROUPS * (2 + OUT_BUFS)) * 4096 : 0;
-  static constexpr int EPI_BYTES = 4 * EPI_WARP_BYTES;
+  // eight epilogue warps; a warp's staging tiles are [32 pixels][32 channels] (64-byte rows, 64B
+  // swizzle), one set (residual, mask, OUT_BUFS x out) per 32-column chunk it owns (GROUPS of them)
+  static constexpr int EPI_WARPS = 8;
+  static constexpr int EPI_WARP_BYTES = FAST_EPI ? (GROUPS * (2 + OUT_BUFS)) * 2048 : 0;
+  static constexpr int EPI_BYTES = EPI_WARPS * EPI_WARP_BYTES;
+  static constexpr int THREADS = (2 + EPI_WARPS) * 32;
   static constexpr int PIPE_BUDGET = 224 * 1024 - EPI_BYTES;
   static constexpr int STAGES = PIPE_BUDGET / STAGE_BYTES > 8 ? 8 : PIPE_BUDGET / STAGE_BYTES;
   // accumulator ring over all 512 TMEM columns (8 / 4 / 2 accumulators for BN = 64 / 128 / 256): the
@@ -71,7 +76,7 @@ struct IgemmCfg {
 };
 
 template <int BN, int CK, bool PAIR>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
              const __grid_constant__ CUtensorMap tmMask, const IgemmArgs a) {
@@ -86,7 +91,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   auto tfull_bar = [&](int i) { return bar_base + 8u * (2 * Cfg::STAGES + i); };
   auto tempty_bar = [&](int i) { return bar_base + 8u * (2 * Cfg::STAGES + Cfg::NACC + i); };
   const uint32_t ld_bar0 = bar_base + 8u * (2 * Cfg::STAGES + 2 * Cfg::NACC);     // one per epilogue warp
-  const uint32_t tmem_slot = ld_bar0 + 8u * 4;
+  const uint32_t tmem_slot = ld_bar0 + 8u * Cfg::EPI_WARPS;
   uint32_t* tmem_slot_ptr =
       reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -105,9 +110,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
     for (int i = 0; i < Cfg::NACC; ++i) {
       mbar_init(tfull_bar(i), 1);
-      mbar_init(tempty_bar(i), PAIR ? 8 : 4);   // one arrive per epilogue warp (of both CTAs of a pair)
+      mbar_init(tempty_bar(i), (PAIR ? 2 : 1) * Cfg::EPI_WARPS);   // one arrive per epilogue warp (of both CTAs of a pair)
     }
-    for (int i = 0; i < 4; ++i) mbar_init(ld_bar0 + 8u * i, 1);
+    for (int i = 0; i < Cfg::EPI_WARPS; ++i) mbar_init(ld_bar0 + 8u * i, 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -233,27 +238,36 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
     }
   } else {
-    // ------------------------------------------------------------ epilogue (warps 2..5)
+    // ------------------------------------------------------------ epilogue (warps 2..9)
+    const int ew = warp - 2;                   // 0..7
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may touch
+    const int half = ew >> 2;                  // it owns the 32-column chunks half, half + 2, ...
     const int row = quad * 32 + lane;
-    // per-warp staging: res[GROUPS] | mask[GROUPS] | out[OUT_BUFS][GROUPS]
-    const uint32_t stg_in = epi_base + quad * Cfg::EPI_WARP_BYTES;
-    const uint32_t stg_out_base = stg_in + 2 * Cfg::GROUPS * 4096;
-    const uint32_t ld_bar = ld_bar0 + 8u * quad;
+    constexpr int NCH = BN / 64;               // chunks per warp
+    // per-warp staging: res[NCH] | mask[NCH] | out[OUT_BUFS][NCH], 2 KB tiles
+    const uint32_t stg_in = epi_base + ew * Cfg::EPI_WARP_BYTES;
+    const uint32_t stg_out_base = stg_in + 2 * NCH * 2048;
+    const uint32_t ld_bar = ld_bar0 + 8u * ew;
     EpiArgs epi = a.epi;
     if (second) epi.shift = a.shift2;
-    const bool has_res = epi.residual != nullptr, has_mask = epi.mask_src != nullptr;
+    const bool fast = Cfg::FAST_EPI && a.fast;
+    // the tile loop is instantiated once per combination of optional epilogue steps; the launch picks
+    // its specialisation (epilogue.cuh, epi_dispatch)
+    auto epi_loop = [&](auto mode_tag) {
+    constexpr int EPI = decltype(mode_tag)::value;
+    const bool has_res = (EPI & EPI_HAS_RES) && epi.residual != nullptr;
+    const bool has_mask = (EPI & EPI_HAS_MASK) && epi.mask_src != nullptr;
     const bool has_in = has_res || has_mask;
     uint32_t ld_parity = 0;
-    float csum[BN / 32];                 // per-lane column sums of the current column tile
+    float csum[NCH];                     // per-lane column sums of this warp's chunks of the current column tile
 #pragma unroll
-    for (int i = 0; i < BN / 32; ++i) csum[i] = 0.f;
+    for (int i = 0; i < NCH; ++i) csum[i] = 0.f;
     int cs_nt = -1;
     auto flush_colsum = [&]() {
       if (a.epi.colsum != nullptr && cs_nt >= 0) {
 #pragma unroll
-        for (int i = 0; i < BN / 32; ++i) {
-          atomicAdd(a.epi.colsum + cs_nt * BN + i * 32 + lane, csum[i]);
+        for (int i = 0; i < NCH; ++i) {
+          atomicAdd(a.epi.colsum + cs_nt * BN + (half + 2 * i) * 32 + lane, csum[i]);
           csum[i] = 0.f;
         }
       }
@@ -263,110 +277,110 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       if (PAIR) mbar_arrive_cluster(mapa_u32(tempty_bar(acc_i), 0));
       else mbar_arrive(tempty_bar(acc_i));
     };
+    // scatter launches (zero-dilated destination: parity-class data gradients): the same staged
+    // tiles, but rows live at per-pixel addresses a tensor map cannot describe, so the LSU moves
+    // them -- four lanes per 64-byte row (whole sectors), cp.async for the inputs
+    const bool gather = a.out_scatter == 2;
+    auto scatter_pix = [&](int mm) -> long {
+      if (mm >= a.M_total) return -1;
+      const int img = mm / HoWo;
+      const int rem = mm - img * HoWo;
+      const int p = rem / a.Wo, q = rem - p * a.Wo;
+      return ((long)img * (2 * a.Ho) + 2 * p + a.off_h) * (2 * a.Wo) + 2 * q + a.off_w;
+    };
+    auto tile_mn = [&](int tt, int& nn_t, int& mm_t) {
+      nn_t = tt % a.num_n_tiles;
+      mm_t = (tt / a.num_n_tiles) * MT + rank;
+    };
+    // residual / mask tiles are prefetched one tile ahead (see halo_conv.cu)
+    auto issue_inputs = [&](int tt) {
+      int nn_t, mm_t;
+      tile_mn(tt, nn_t, mm_t);
+      if (gather) {
+        const long pix = scatter_pix(mm_t * Cfg::BM + row);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = 8 * i + (lane >> 2);
+          const long pr = __shfl_sync(0xffffffffu, pix, r);
+          const uint32_t dst = (uint32_t)r * 64u + ((uint32_t)((lane & 3) ^ ((r >> 1) & 3)) << 4);
+          const uint32_t nb = pr >= 0 ? 16u : 0u;
+          const long prc = pr >= 0 ? pr : 0;
+#pragma unroll
+          for (int ci = 0; ci < NCH; ++ci) {
+            const int col = nn_t * BN + (half + 2 * ci) * 32 + (lane & 3) * 8;
+            if (has_res) cp_async_16(stg_in + ci * 2048 + dst, epi.residual + prc * epi.ldr + col, nb);
+            if (has_mask) cp_async_16(stg_in + (NCH + ci) * 2048 + dst, epi.mask_src + prc * epi.ldm + col, nb);
+          }
+        }
+        cp_async_commit();
+        return;
+      }
+      const int r0 = mm_t * Cfg::BM + quad * 32;
+      if (elect_one()) {
+        mbar_expect_tx(ld_bar, NCH * ((has_res ? 2048u : 0u) + (has_mask ? 2048u : 0u)));
+#pragma unroll
+        for (int ci = 0; ci < NCH; ++ci) {
+          const int col = nn_t * BN + (half + 2 * ci) * 32;
+          if (has_res) tma_load_2d(stg_in + ci * 2048, &tmRes, ld_bar, col, r0);
+          if (has_mask) tma_load_2d(stg_in + (NCH + ci) * 2048, &tmMask, ld_bar, col, r0);
+        }
+      }
+      __syncwarp();
+    };
+    if (fast && has_in && tile0 < num_tiles) issue_inputs(tile0);
     int it = 0;
     for (int t = tile0; t < num_tiles; t += tstep, ++it) {
-      const int n_t = t % a.num_n_tiles, m_t = (t / a.num_n_tiles) * MT + rank;
+      int n_t, m_t;
+      tile_mn(t, n_t, m_t);
       if (n_t != cs_nt) { flush_colsum(); cs_nt = n_t; }
       const int acc = it % Cfg::NACC;
       const uint32_t acc_phase = (it / Cfg::NACC) & 1;
       const int m = m_t * Cfg::BM + row;
       const bool valid = m < a.M_total;
-      if (Cfg::FAST_EPI && a.fast) {
+      if (fast) {
         const int row0 = m_t * Cfg::BM + quad * 32;            // this warp's 32 output rows
-        // residual / mask tiles are prefetched one tile ahead (see halo_conv.cu)
-        auto issue_inputs = [&](int tt) {
-          const int nn_t = tt % a.num_n_tiles, mm_t = (tt / a.num_n_tiles) * MT + rank;
-          const int r0 = mm_t * Cfg::BM + quad * 32;
-          if (elect_one()) {
-            mbar_expect_tx(ld_bar, Cfg::GROUPS * ((has_res ? 4096u : 0u) + (has_mask ? 4096u : 0u)));
-#pragma unroll
-            for (int gidx = 0; gidx < Cfg::GROUPS; ++gidx) {
-              const int col = nn_t * BN + gidx * 64;
-              if (has_res) tma_load_2d(stg_in + gidx * 4096, &tmRes, ld_bar, col, r0);
-              if (has_mask) tma_load_2d(stg_in + (Cfg::GROUPS + gidx) * 4096, &tmMask, ld_bar, col, r0);
-            }
-          }
-          __syncwarp();
-        };
-        // scatter launches (zero-dilated destination: parity-class data gradients): the same staged
-        // tiles, but rows live at per-pixel addresses a tensor map cannot describe, so the LSU moves
-        // them -- eight lanes per 128-byte row (whole sectors), cp.async for the inputs
-        const bool gather = a.out_scatter == 2;
-        auto scatter_pix = [&](int mm) -> long {
-          if (mm >= a.M_total) return -1;
-          const int img = mm / HoWo;
-          const int rem = mm - img * HoWo;
-          const int p = rem / a.Wo, q = rem - p * a.Wo;
-          return ((long)img * (2 * a.Ho) + 2 * p + a.off_h) * (2 * a.Wo) + 2 * q + a.off_w;
-        };
-        auto gather_inputs = [&](int tt) {
-          const int nn_t = tt % a.num_n_tiles, mm_t = (tt / a.num_n_tiles) * MT + rank;
-          const long pix = scatter_pix(mm_t * Cfg::BM + quad * 32 + lane);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = 4 * i + (lane >> 3);
-            const long pr = __shfl_sync(0xffffffffu, pix, r);
-            const uint32_t dst = (uint32_t)r * 128u + ((uint32_t)((lane & 7) ^ (r & 7)) << 4);
-            const uint32_t nb = pr >= 0 ? 16u : 0u;
-            const long prc = pr >= 0 ? pr : 0;
-#pragma unroll
-            for (int gidx = 0; gidx < Cfg::GROUPS; ++gidx) {
-              const int col = nn_t * BN + gidx * 64 + (lane & 7) * 8;
-              if (has_res) cp_async_16(stg_in + gidx * 4096 + dst, epi.residual + prc * epi.ldr + col, nb);
-              if (has_mask)
-                cp_async_16(stg_in + (Cfg::GROUPS + gidx) * 4096 + dst, epi.mask_src + prc * epi.ldm + col, nb);
-            }
-          }
-          cp_async_commit();
-        };
-        if (has_in && it == 0) {
-          if (gather) gather_inputs(t); else issue_inputs(t);
-        }
         mbar_wait(tfull_bar(acc), acc_phase);
         tc_fence_after();
-        const uint32_t stg = stg_out_base + (uint32_t)((it % Cfg::OUT_BUFS) * Cfg::GROUPS) * 4096u;
+        const uint32_t stg = stg_out_base + (uint32_t)((it % Cfg::OUT_BUFS) * NCH) * 2048u;
         if (elect_one()) tma_store_wait_read<Cfg::OUT_BUFS - 1>();   // this out buffer's last store has been read
         __syncwarp();
 #pragma unroll 1
-        for (int chunk = 0; chunk < BN / 32; ++chunk) {
+        for (int ci = 0; ci < NCH; ++ci) {
+          const int chunk = half + 2 * ci;
           uint32_t raw[32];
           tmem_ld_32x32(tmem_base + acc * BN + chunk * 32 + ((uint32_t)(quad * 32) << 16), raw);
           tmem_ld_wait();
-          if (chunk == 0 && has_in) {
+          if (ci == 0 && has_in) {
             if (gather) { cp_async_wait_all(); __syncwarp(); }
             else mbar_wait(ld_bar, ld_parity);
           }
-          const int gidx = chunk >> 1;
-          const float cs = epilogue_half_staged(epi, raw, valid, n_t * BN + chunk * 32, chunk & 1, lane,
-                                                stg + gidx * 4096, stg_in + gidx * 4096,
-                                                stg_in + (Cfg::GROUPS + gidx) * 4096);
+          const float cs = epilogue_half_staged<64, EPI>(epi, raw, valid, n_t * BN + chunk * 32, 0, lane, stg + ci * 2048,
+                                                    stg_in + ci * 2048, stg_in + (NCH + ci) * 2048);
 #pragma unroll
-          for (int i = 0; i < BN / 32; ++i)
-            if (i == chunk) csum[i] += cs;
+          for (int i = 0; i < NCH; ++i)
+            if (i == ci) csum[i] += cs;
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) release_acc(acc);
         if (has_in) {
           ld_parity ^= 1;
-          if (t + tstep < num_tiles) {
-            if (gather) gather_inputs(t + tstep); else issue_inputs(t + tstep);
-          }
+          if (t + tstep < num_tiles) issue_inputs(t + tstep);
         }
         if (gather) {
-          __syncwarp();                       // the staged tile is complete
+          __syncwarp();                       // the staged tiles are complete
           const long pix = scatter_pix(m);
           __nv_bfloat16* obase = static_cast<__nv_bfloat16*>(epi.out);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = 4 * i + (lane >> 3);
+          for (int i = 0; i < 4; ++i) {
+            const int r = 8 * i + (lane >> 2);
             const long pr = __shfl_sync(0xffffffffu, pix, r);
-            const uint32_t src = (uint32_t)r * 128u + ((uint32_t)((lane & 7) ^ (r & 7)) << 4);
+            const uint32_t src = (uint32_t)r * 64u + ((uint32_t)((lane & 3) ^ ((r >> 1) & 3)) << 4);
 #pragma unroll
-            for (int gidx = 0; gidx < Cfg::GROUPS; ++gidx) {
-              const uint4 v4 = lds128(stg + gidx * 4096 + src);
+            for (int ci = 0; ci < NCH; ++ci) {
+              const uint4 v4 = lds128(stg + ci * 2048 + src);
               if (pr >= 0)
-                *reinterpret_cast<uint4*>(obase + pr * epi.ldc + n_t * BN + gidx * 64 + (lane & 7) * 8) = v4;
+                *reinterpret_cast<uint4*>(obase + pr * epi.ldc + n_t * BN + (half + 2 * ci) * 32 + (lane & 3) * 8) = v4;
             }
           }
           __syncwarp();
@@ -376,8 +390,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         __syncwarp();
         if (elect_one()) {
 #pragma unroll
-          for (int gidx = 0; gidx < Cfg::GROUPS; ++gidx)
-            tma_store_2d(&tmOut, stg + gidx * 4096, n_t * BN + gidx * 64, row0);
+          for (int ci = 0; ci < NCH; ++ci)
+            tma_store_2d(&tmOut, stg + ci * 2048, n_t * BN + (half + 2 * ci) * 32, row0);
           tma_store_commit();
         }
         __syncwarp();
@@ -396,22 +410,26 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
 #pragma unroll 1
-      for (int chunk = 0; chunk < BN / 32; ++chunk) {
+      for (int ci = 0; ci < NCH; ++ci) {
+        const int chunk = half + 2 * ci;
         uint32_t raw[32];
         tmem_ld_32x32(tmem_base + acc * BN + chunk * 32 + ((uint32_t)(quad * 32) << 16), raw);
         tmem_ld_wait();
         const float cs = epilogue_chunk(epi, raw, valid, a.scatter_inputs ? opix : (long)m, opix, opix2,
                                         n_t * BN + chunk * 32, lane);
 #pragma unroll
-        for (int i = 0; i < BN / 32; ++i)
-          if (i == chunk) csum[i] += cs;
+        for (int i = 0; i < NCH; ++i)
+          if (i == ci) csum[i] += cs;
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) release_acc(acc);
     }
     flush_colsum();
-    if (Cfg::FAST_EPI && a.fast) {
+    };
+    if constexpr (Cfg::FAST_EPI) epi_dispatch(fast ? epi_mode(epi) : EPI_HAS_ALL, epi_loop);
+    else epi_loop(EpiMode<EPI_HAS_ALL>{});
+    if (fast) {
       if (elect_one()) tma_store_wait<0>();
       __syncwarp();
     }
@@ -458,10 +476,10 @@ static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
     a.split_cta = g0 * MT;
   }
   if (PAIR)
-    launch_kernel_cluster(kfn, grid * 2, 192, Cfg::SMEM_BYTES, stream, 2, tmA, tmB, tmB2, epi_maps[0], epi_maps[1],
+    launch_kernel_cluster(kfn, grid * 2, Cfg::THREADS, Cfg::SMEM_BYTES, stream, 2, tmA, tmB, tmB2, epi_maps[0], epi_maps[1],
                           epi_maps[2], a);
   else
-    launch_kernel(kfn, grid, 192, Cfg::SMEM_BYTES, stream, tmA, tmB, tmB2, epi_maps[0], epi_maps[1], epi_maps[2], a);
+    launch_kernel(kfn, grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream, tmA, tmB, tmB2, epi_maps[0], epi_maps[1], epi_maps[2], a);
   VDQN_CHECK_LAUNCH("igemm launch");
   return VDQN_OK;
 }
@@ -538,15 +556,16 @@ extern "C" int vdqn_conv_gemm(const vdqn_conv_desc* d, void* stream_v) {
   a.off_h = d->scatter_off_h; a.off_w = d->scatter_off_w;
   a.scatter_inputs = (d->out_scatter == 2 && (d->flags & VDQN_EPI_SCATTER_INPUTS)) ? 1 : 0;
 
-  // staged epilogue: 2-D maps over the [M][ld] output / residual / mask matrices, 64 x 32 boxes
+  // staged epilogue: 2-D maps over the [M][ld] output / residual / mask matrices, boxes of
+  // 32 channels x 32 pixels (64-byte rows)
   CUtensorMap epi_maps[3] = {tmB, tmB, tmB};
   a.fast = (BN <= 128 && fast_epilogue_ok(d)) ? 1 : 0;
   if (a.fast && d->out_scatter != 2) {     // scatter launches move the staged tiles with the LSU
-    rc = make_tiled_map_2d(&epi_maps[0], d->out, d->Cout, a.M_total, 64, 32, 128, d->ldc);
+    rc = make_tiled_map_2d(&epi_maps[0], d->out, d->Cout, a.M_total, 32, 32, 64, d->ldc);
     if (rc == VDQN_OK && d->residual)
-      rc = make_tiled_map_2d(&epi_maps[1], d->residual, d->Cout, a.M_total, 64, 32, 128, d->ldr);
+      rc = make_tiled_map_2d(&epi_maps[1], d->residual, d->Cout, a.M_total, 32, 32, 64, d->ldr);
     if (rc == VDQN_OK && d->mask_src)
-      rc = make_tiled_map_2d(&epi_maps[2], d->mask_src, d->Cout, a.M_total, 64, 32, 128, d->ldm);
+      rc = make_tiled_map_2d(&epi_maps[2], d->mask_src, d->Cout, a.M_total, 32, 32, 64, d->ldm);
     if (rc != VDQN_OK) return rc;
   }
   CUtensorMap tmB2 = tmB;

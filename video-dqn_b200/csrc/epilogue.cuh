@@ -33,6 +33,21 @@ inline EpiArgs make_epi_args(const vdqn_conv_desc* d) {
   return e;
 }
 
+// warp transpose-reduce: lane L ends up with the sum over the 32 lanes of v[L]
+__device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = upper ? v[i] : v[i + off];
+      const float keep = upper ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
 // raw: 32 fp32 accumulators of this thread's pixel, channels [c0, c0+32).  `m` indexes
 // residual / mask_src (compact pixel index), `opix` / `opix2` the destinations.
 // Returns this lane's share of the per-channel column sum (channel c0 + lane, summed over the warp's
@@ -145,14 +160,50 @@ __device__ __forceinline__ float epilogue_chunk(const EpiArgs& a, const uint32_t
 // ROW_BYTES = 128: 64-column tiles (128B swizzle), `half` selects the 32 columns inside the row.
 // ROW_BYTES = 64: the tile IS 32 columns wide (64-byte rows, 64B swizzle; `half` unused) -- used
 // when every epilogue warp owns its own 32-column slice (two warps per TMEM lane quadrant).
-template <int ROW_BYTES = 128>
+// `row_acc` (optional, 32 floats per thread): column sums are then NOT reduced per call -- the
+// thread adds its own row's (rounded) values into row_acc and the caller reduces once at the end of
+// the kernel with warp_transpose_reduce (the 31 shuffles per tile were a third of the data-gradient
+// epilogue).
+// EPI: which optional steps are COMPILED IN (EPI_HAS_* bits; each still checks its pointer / flag at
+// run time).  ptxas if-converts the optional blocks into predicated instructions, so a forward
+// launch compiled with everything present issues the whole residual + mask code with the predicate
+// off (measured: 310 instead of ~130 instructions per 32 columns, and the epilogue warps are the
+// longest role of the small-K kernels).  Callers therefore dispatch ONCE per kernel to a loop
+// specialised for the steps the launch actually has (epi_mode()).
+enum : int { EPI_HAS_RES = 1, EPI_HAS_MASK = 2, EPI_HAS_COLSUM = 4, EPI_HAS_SHIFT_RELU = 8, EPI_HAS_ALL = 15 };
+
+__device__ __forceinline__ int epi_mode(const EpiArgs& a) {
+  return (a.residual != nullptr ? EPI_HAS_RES : 0) | (a.mask_src != nullptr ? EPI_HAS_MASK : 0) |
+         (a.colsum != nullptr ? EPI_HAS_COLSUM : 0) |
+         ((a.shift != nullptr || (a.flags & VDQN_EPI_RELU)) ? EPI_HAS_SHIFT_RELU : 0);
+}
+
+template <int V>
+struct EpiMode { static constexpr int value = V; };
+
+// run `f(EpiMode<m>{})` for the specialisation matching `mode` (the common combinations of this
+// network; anything else takes the generic all-steps version)
+template <typename F>
+__device__ __forceinline__ void epi_dispatch(int mode, F&& f) {
+  switch (mode) {
+    case EPI_HAS_SHIFT_RELU: f(EpiMode<EPI_HAS_SHIFT_RELU>{}); break;                                  // conv + BN (+ ReLU)
+    case EPI_HAS_SHIFT_RELU | EPI_HAS_RES: f(EpiMode<EPI_HAS_SHIFT_RELU | EPI_HAS_RES>{}); break;      // + identity
+    case EPI_HAS_MASK | EPI_HAS_COLSUM: f(EpiMode<EPI_HAS_MASK | EPI_HAS_COLSUM>{}); break;            // data gradient
+    case EPI_HAS_RES | EPI_HAS_MASK | EPI_HAS_COLSUM: f(EpiMode<EPI_HAS_RES | EPI_HAS_MASK | EPI_HAS_COLSUM>{}); break;
+    case 0: f(EpiMode<0>{}); break;                                                                    // plain GEMM
+    default: f(EpiMode<EPI_HAS_ALL>{}); break;
+  }
+}
+
+template <int ROW_BYTES = 128, int EPI = EPI_HAS_ALL>
 __device__ __forceinline__ float epilogue_half_staged(const EpiArgs& a, const uint32_t (&raw)[32], bool valid,
                                                       int c0, int half, int lane, uint32_t stg_out,
-                                                      uint32_t stg_res, uint32_t stg_mask) {
+                                                      uint32_t stg_res, uint32_t stg_mask,
+                                                      float* row_acc = nullptr) {
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-  if (a.shift != nullptr) {
+  if ((EPI & EPI_HAS_SHIFT_RELU) && a.shift != nullptr) {
     const float4* sp = reinterpret_cast<const float4*>(a.shift + c0);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -163,7 +214,7 @@ __device__ __forceinline__ float epilogue_half_staged(const EpiArgs& a, const ui
   const uint32_t row_off = (uint32_t)lane * (uint32_t)ROW_BYTES;
   const uint32_t sw = ROW_BYTES == 128 ? (uint32_t)(lane & 7) : (uint32_t)((lane >> 1) & 3);
   if (ROW_BYTES == 64) half = 0;
-  if (a.residual != nullptr) {
+  if ((EPI & EPI_HAS_RES) && a.residual != nullptr) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const uint4 r4 = lds128(stg_res + row_off + ((((uint32_t)(half * 4 + j)) ^ sw) << 4));
@@ -176,11 +227,11 @@ __device__ __forceinline__ float epilogue_half_staged(const EpiArgs& a, const ui
       }
     }
   }
-  if (a.flags & VDQN_EPI_RELU) {
+  if ((EPI & EPI_HAS_SHIFT_RELU) && (a.flags & VDQN_EPI_RELU)) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
   }
-  if (a.mask_src != nullptr) {
+  if ((EPI & EPI_HAS_MASK) && a.mask_src != nullptr) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const uint4 r4 = lds128(stg_mask + row_off + ((((uint32_t)(half * 4 + j)) ^ sw) << 4));
@@ -204,21 +255,23 @@ __device__ __forceinline__ float epilogue_half_staged(const EpiArgs& a, const ui
 #pragma unroll
     for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[8 * j + 2 * e], v[8 * j + 2 * e + 1]);
     sts128(stg_out + row_off + ((((uint32_t)(half * 4 + j)) ^ sw) << 4), pk);
-  }
-  if (a.colsum != nullptr) {
+    if ((EPI & EPI_HAS_COLSUM) && a.colsum != nullptr) {
+      // column sums use the values as stored (rounded), so d beta matches what the weight gradient consumes
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = __bfloat162float(__float2bfloat16_rn(v[j]));
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) {
-      const bool upper = (lane & off) != 0;
-#pragma unroll
-      for (int i = 0; i < off; ++i) {
-        const float send = upper ? v[i] : v[i + off];
-        const float keep = upper ? v[i + off] : v[i];
-        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __bfloat1622float2(h[e]);
+        v[8 * j + 2 * e] = f.x;
+        v[8 * j + 2 * e + 1] = f.y;
       }
     }
-    return v[0];
+  }
+  if ((EPI & EPI_HAS_COLSUM) && a.colsum != nullptr) {
+    if (row_acc != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) row_acc[j] += v[j];
+      return 0.f;
+    }
+    return warp_transpose_reduce(v, lane);
   }
   return 0.f;
 }

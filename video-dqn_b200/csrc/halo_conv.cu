@@ -74,7 +74,11 @@ struct HaloCfg {
   static constexpr int EPI_WARPS = 8;
   static constexpr int EPI_WARP_BYTES = 4 * 2048;
   static constexpr int EPI_BYTES = EPI_WARPS * EPI_WARP_BYTES;
-  static constexpr int THREADS = (4 + 1 + EPI_WARPS) * 32;
+  // 12 warps = 384 threads: the register file then allows 168 registers per thread (416 threads were
+  // compiled against the 512-thread limit of 128 and spilled)
+  static constexpr int PROD_WARPS = 3;
+  static constexpr int MMA_WARP = PROD_WARPS;
+  static constexpr int THREADS = (PROD_WARPS + 1 + EPI_WARPS) * 32;
   static constexpr int SMEM_BYTES = W_BYTES + STAGES * STAGE_BYTES + EPI_BYTES + 1024 + 512;
   // accumulator ring: with 64-column accumulators TMEM holds 4 of them, so the MMA warp can run up to
   // 4 tiles ahead of the epilogue and the mbarrier hand-off latencies (MMA -> epilogue -> MMA) overlap
@@ -132,10 +136,10 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     for (int i = 0; i < Cfg::EPI_WARPS; ++i) mbar_init(ld_bar0 + 8u * i, 1);
     fence_mbar_init();
   }
-  // warps 0-3: producers (the cp.async variant uses all four, the TMA variant only warp 0),
-  // warp 4: MMA issuer + TMEM owner, warps 5-12: epilogue (TMEM lane quadrant = warp & 3, column
-  // half = (warp - 5) / 4)
-  if (warp == 4) {
+  // warps 0-2: producers (the cp.async variant uses all three, the TMA variant only warp 0),
+  // warp 3: MMA issuer + TMEM owner, warps 4-11: epilogue (TMEM lane quadrant = warp & 3, column
+  // half = (warp - 4) / 4)
+  if (warp == Cfg::MMA_WARP) {
     tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
     tmem_relinquish();
   }
@@ -172,7 +176,7 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     if (c.th >= a.tiles_h) { c.th -= a.tiles_h; ++c.n; }
   };
 
-  if (warp < 4) {
+  if (warp < Cfg::PROD_WARPS) {
     // the filter: one [64 x CK] tile per tap, resident for the whole kernel
     if (warp == 0) {
       if (elect_one()) {
@@ -184,11 +188,11 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     if constexpr (CK == 16) {
       // 32-byte pixel rows are slow through the TMA unit (one request per row) and a single warp
       // gathering them with cp.async is issue-bound (measured: 133 us of the 190 us stem kernel with
-      // everything else switched off), so FOUR producer warps share the work: warp p gathers the
-      // 19 x 11 x 32 B windows of the CTA's tiles p, p+4, ... with 16-byte cp.async (zero-fill =
+      // everything else switched off), so THREE producer warps share the work: warp p gathers the
+      // 19 x 11 x 32 B windows of the CTA's tiles p, p+3, ... with 16-byte cp.async (zero-fill =
       // padding) into the 32B-swizzled layout the MMA descriptors expect, DEPTH tiles in flight each.
       // each warp waits for the tile it issued DEPTH-1 iterations ago: with too few tiles in flight the
-      // loop period is the memory latency (measured: 84 us floor at DEPTH 2); 4 warps x 4 = all 16 stages
+      // loop period is the memory latency (measured: 84 us floor at DEPTH 2); 3 warps x 4 tiles in flight of the 16 stages
       constexpr int DEPTH = 4;
       constexpr int CHUNKS = Cfg::HALO_H * Cfg::HALO_W * 2;
       constexpr int PER_LANE = (CHUNKS + 31) / 32;
@@ -205,8 +209,9 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       int issued = 0, done_k = warp;
       int k = warp;
       PROF_BEGIN
-      TileIt ti = tile_it(tile0 + warp * tstep, 4 * tstep);
-      for (int t = tile0 + warp * tstep; t < tile_end; t += 4 * tstep, k += 4, advance(ti)) {
+      constexpr int NP = Cfg::PROD_WARPS;
+      TileIt ti = tile_it(tile0 + warp * tstep, NP * tstep);
+      for (int t = tile0 + warp * tstep; t < tile_end; t += NP * tstep, k += NP, advance(ti)) {
         const int n = ti.n, h0 = ti.th * Cfg::TH, w0 = ti.tw * Cfg::TW;
         PROF_TILE
         const int stage = k % Cfg::STAGES;
@@ -229,7 +234,7 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           PROF_WAIT_B(asm volatile("cp.async.wait_group %0;" ::"n"(DEPTH - 1) : "memory"))
           fence_proxy_async();
           mbar_arrive(full_bar(done_k % Cfg::STAGES));
-          done_k += 4;
+          done_k += Cfg::PROD_WARPS;
         }
       }
       PROF_END(warp)
@@ -238,7 +243,7 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       const int pending = issued < DEPTH - 1 ? issued : DEPTH - 1;
       for (int i = 0; i < pending; ++i) {
         mbar_arrive(full_bar(done_k % Cfg::STAGES));
-        done_k += 4;
+        done_k += Cfg::PROD_WARPS;
       }
     } else if (warp == 0) {
       int stage = 0;
@@ -259,7 +264,7 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       }
       PROF_END(0)
     }
-  } else if (warp == 4) {
+  } else if (warp == Cfg::MMA_WARP) {
     constexpr uint32_t idesc = make_idesc_bf16(128, Cfg::BN, 0, 0);
     mbar_wait(w_bar, 0);
     int stage = 0;
@@ -300,7 +305,7 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     }
     PROF_END(4)
   } else {
-    const int ew = warp - 5;                  // 0..7
+    const int ew = warp - (Cfg::MMA_WARP + 1);   // 0..7
     const int quad = warp & 3;                // TMEM lane quadrant this warp may touch
     const int half = ew >> 2;                 // its 32 output columns: [half*32, half*32 + 32)
     const int row = quad * 32 + lane;
@@ -311,69 +316,86 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     const int c0 = half * 32;
     EpiArgs epi = a.epi;
     if (second) epi.shift = a.shift2;
-    const bool has_res = epi.residual != nullptr, has_mask = epi.mask_src != nullptr;
-    const bool has_in = has_res || has_mask;
-    uint32_t ld_parity = 0;
-    float csum = 0.f;                    // per-lane column sum (channel c0 + lane) over all tiles
-    int it = 0;
-    PROF_BEGIN
-    TileIt ti = tile_it(tile0, tstep);
-    // this warp's 32 pixels = image rows h0+4*quad .. +3, 8 pixels each: a [1][4][8][32] TMA box.
-    // Residual / mask tiles are prefetched ONE TILE AHEAD (issued as soon as the previous tile has
-    // consumed the staging tiles), so their L2/HBM latency hides behind a whole tile of work.
-    auto issue_inputs = [&](const TileIt& c) {
-      if (elect_one()) {
-        mbar_expect_tx(ld_bar, (has_res ? 2048u : 0u) + (has_mask ? 2048u : 0u));
-        if (has_res) tma_load_4d(stg_res, &tmRes, ld_bar, c0, c.tw * Cfg::TW, c.th * Cfg::TH + 4 * quad, c.n);
-        if (has_mask) tma_load_4d(stg_mask, &tmMask, ld_bar, c0, c.tw * Cfg::TW, c.th * Cfg::TH + 4 * quad, c.n);
-      }
-      __syncwarp();
-    };
-    if (a.fast && has_in && tile0 < tile_end) issue_inputs(ti);
-    for (int t = tile0; t < tile_end; t += tstep, ++it) {
-      const int n = ti.n, h0 = ti.th * Cfg::TH, w0 = ti.tw * Cfg::TW;
-      advance(ti);                         // ti = the NEXT tile from here on
-      PROF_TILE
-      const int acc = it % Cfg::NACC;
-      const uint32_t acc_phase = (it / Cfg::NACC) & 1;
-      const int h = h0 + g, w = w0 + j;
-      const bool valid = h < a.H && w < a.W;
-      PROF_WAIT_A(mbar_wait(tfull_bar(acc), acc_phase))
-      tc_fence_after();
-      uint32_t raw[32];
-      tmem_ld_32x32(tmem_base + acc * Cfg::BN + c0 + ((uint32_t)(quad * 32) << 16), raw);
-      if (a.fast) {
-        const uint32_t stg_out = stg_out0 + (uint32_t)(it & 1) * 2048u;
-        PROF_WAIT_B(if (elect_one()) tma_store_wait_read<1>(); __syncwarp())      // the store from two tiles ago has left this buffer
+    // The tile loop is instantiated once per combination of optional epilogue steps and the launch
+    // picks its specialisation (epilogue.cuh, epi_dispatch).
+    auto epi_loop = [&](auto mode_tag) {
+      constexpr int EPI = decltype(mode_tag)::value;
+      constexpr bool COLSUM = (EPI & EPI_HAS_COLSUM) != 0;
+      const bool has_res = (EPI & EPI_HAS_RES) && epi.residual != nullptr;
+      const bool has_mask = (EPI & EPI_HAS_MASK) && epi.mask_src != nullptr;
+      const bool has_in = has_res || has_mask;
+      uint32_t ld_parity = 0;
+      float csum = 0.f;                    // per-lane column sum (channel c0 + lane) over all tiles
+      float row_acc[COLSUM ? 32 : 1];      // staged path: this pixel row's running sums, reduced once at the end
+#pragma unroll
+      for (int i = 0; i < (COLSUM ? 32 : 1); ++i) row_acc[i] = 0.f;
+      int it = 0;
+      PROF_BEGIN
+      TileIt ti = tile_it(tile0, tstep);
+      // this warp's 32 pixels = image rows h0+4*quad .. +3, 8 pixels each: a [1][4][8][32] TMA box.
+      // Residual / mask tiles are prefetched ONE TILE AHEAD (issued as soon as the previous tile has
+      // consumed the staging tiles), so their L2/HBM latency hides behind a whole tile of work.
+      auto issue_inputs = [&](const TileIt& c) {
+        if (elect_one()) {
+          mbar_expect_tx(ld_bar, (has_res ? 2048u : 0u) + (has_mask ? 2048u : 0u));
+          if (has_res) tma_load_4d(stg_res, &tmRes, ld_bar, c0, c.tw * Cfg::TW, c.th * Cfg::TH + 4 * quad, c.n);
+          if (has_mask) tma_load_4d(stg_mask, &tmMask, ld_bar, c0, c.tw * Cfg::TW, c.th * Cfg::TH + 4 * quad, c.n);
+        }
+        __syncwarp();
+      };
+      if (a.fast && has_in && tile0 < tile_end) issue_inputs(ti);
+      for (int t = tile0; t < tile_end; t += tstep, ++it) {
+        const int n = ti.n, h0 = ti.th * Cfg::TH, w0 = ti.tw * Cfg::TW;
+        advance(ti);                         // ti = the NEXT tile from here on
+        PROF_TILE
+        const int acc = it % Cfg::NACC;
+        const uint32_t acc_phase = (it / Cfg::NACC) & 1;
+        const int h = h0 + g, w = w0 + j;
+        const bool valid = h < a.H && w < a.W;
+        PROF_WAIT_A(mbar_wait(tfull_bar(acc), acc_phase))
+        tc_fence_after();
+        uint32_t raw[32];
+        tmem_ld_32x32(tmem_base + acc * Cfg::BN + c0 + ((uint32_t)(quad * 32) << 16), raw);
+        if (a.fast) {
+          const uint32_t stg_out = stg_out0 + (uint32_t)(it & 1) * 2048u;
+          PROF_WAIT_B(if (elect_one()) tma_store_wait_read<1>(); __syncwarp())      // the store from two tiles ago has left this buffer
+          tmem_ld_wait();
+          if (has_in) PROF_WAIT_B(mbar_wait(ld_bar, ld_parity))
+          if (!(epi.flags & 32))          // flag 32: debug, skip the epilogue math (bottleneck probing)
+            csum += epilogue_half_staged<64, EPI>(epi, raw, valid, c0, 0, lane, stg_out, stg_res, stg_mask,
+                                                  COLSUM ? row_acc : nullptr);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(acc));
+          if (has_in) {
+            ld_parity ^= 1;
+            if (t + tstep < tile_end) issue_inputs(ti);   // staging tiles are free again
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (elect_one() && !(epi.flags & 8)) {      // flag 8: debug, skip the store (bottleneck probing)
+            tma_store_4d(&tmOut, stg_out, c0, w0, h0 + 4 * quad, n);
+            tma_store_commit();
+          }
+          __syncwarp();
+          continue;
+        }
         tmem_ld_wait();
-        if (has_in) PROF_WAIT_B(mbar_wait(ld_bar, ld_parity))
-        if (!(epi.flags & 32))          // flag 32: debug, skip the epilogue math (bottleneck probing)
-          csum += epilogue_half_staged<64>(epi, raw, valid, c0, 0, lane, stg_out, stg_res, stg_mask);
+        const long opix = ((long)n * a.H + h) * a.W + w;
+        csum += epilogue_chunk(epi, raw, valid, opix, opix, 0, c0, lane);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar(acc));
-        if (has_in) {
-          ld_parity ^= 1;
-          if (t + tstep < tile_end) issue_inputs(ti);   // staging tiles are free again
-        }
-        fence_proxy_async();
-        __syncwarp();
-        if (elect_one() && !(epi.flags & 8)) {      // flag 8: debug, skip the store (bottleneck probing)
-          tma_store_4d(&tmOut, stg_out, c0, w0, h0 + 4 * quad, n);
-          tma_store_commit();
-        }
-        __syncwarp();
-        continue;
       }
-      tmem_ld_wait();
-      const long opix = ((long)n * a.H + h) * a.W + w;
-      csum += epilogue_chunk(epi, raw, valid, opix, opix, 0, c0, lane);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
-    }
-    PROF_END(5 + ew)
-    if (a.epi.colsum != nullptr) atomicAdd(a.epi.colsum + c0 + lane, csum);
+      PROF_END(5 + ew)
+      if (COLSUM && a.epi.colsum != nullptr) {
+        if constexpr (COLSUM) {
+          if (a.fast) csum += warp_transpose_reduce(row_acc, lane);
+        }
+        atomicAdd(a.epi.colsum + c0 + lane, csum);
+      }
+    };
+    epi_dispatch(a.fast ? epi_mode(epi) : EPI_HAS_ALL, epi_loop);
     if (a.fast) {
       if (elect_one()) tma_store_wait<0>();
       __syncwarp();
@@ -382,7 +404,7 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == Cfg::MMA_WARP) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
