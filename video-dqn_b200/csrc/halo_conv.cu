@@ -65,14 +65,14 @@ struct HaloCfg {
   static constexpr int STAGE_BYTES = (HALO_BYTES + 1023) / 1024 * 1024;
   static constexpr int W_TILE_BYTES = BN * ROW_BYTES;              // one tap: 64 rows x CK
   static constexpr int W_BYTES = MAX_TAPS * W_TILE_BYTES;          // 72 KB / 32 KB, resident
-  static constexpr int STAGES = (CK == 64) ? 3 : 16;
+  static constexpr int STAGES = (CK == 64) ? 3 : 12;
   // EIGHT epilogue warps, two per TMEM lane quadrant, each owning 32 of the 64 output columns with
-  // private staging tiles [32 pixels][32 ch] (64-byte rows, 64B swizzle): out x2, residual, mask.
+  // private staging tiles [32 pixels][32 ch] (64-byte rows, 64B swizzle): out, 2 x (residual, mask).
   // (role profile: with four warps the epilogue was the longest role of every variant of this kernel
   //  -- 1900 cycles per tile against 950 of MMA issue for the stem -- a single warp per scheduler
   //  cannot hide its own TMEM / shared-memory / mbarrier latencies.)
   static constexpr int EPI_WARPS = 8;
-  static constexpr int EPI_WARP_BYTES = 4 * 2048;
+  static constexpr int EPI_WARP_BYTES = 5 * 2048;
   static constexpr int EPI_BYTES = EPI_WARPS * EPI_WARP_BYTES;
   // 12 warps = 384 threads: the register file then allows 168 registers per thread (416 threads were
   // compiled against the 512-thread limit of 128 and spilled)
@@ -113,7 +113,7 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   auto tempty_bar = [&](int i) { return bar_base + 8u * (2 * Cfg::STAGES + Cfg::NACC + i); };
   const uint32_t w_bar = bar_base + 8u * (2 * Cfg::STAGES + 2 * Cfg::NACC);
   const uint32_t ld_bar0 = w_bar + 8u;                                  // one barrier per epilogue warp
-  const uint32_t tmem_slot = w_bar + 8u * (1 + Cfg::EPI_WARPS);
+  const uint32_t tmem_slot = w_bar + 8u * (1 + 2 * Cfg::EPI_WARPS);
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
@@ -133,7 +133,7 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       mbar_init(tempty_bar(i), Cfg::EPI_WARPS);
     }
     mbar_init(w_bar, 1);
-    for (int i = 0; i < Cfg::EPI_WARPS; ++i) mbar_init(ld_bar0 + 8u * i, 1);
+    for (int i = 0; i < 2 * Cfg::EPI_WARPS; ++i) mbar_init(ld_bar0 + 8u * i, 1);
     fence_mbar_init();
   }
   // warps 0-2: producers (the cp.async variant uses all three, the TMA variant only warp 0),
@@ -311,8 +311,8 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     const int row = quad * 32 + lane;
     const int g = row >> 3, j = row & 7;
     const uint32_t stg_out0 = epi_base + ew * Cfg::EPI_WARP_BYTES;
-    const uint32_t stg_res = stg_out0 + 4096, stg_mask = stg_out0 + 6144;
-    const uint32_t ld_bar = ld_bar0 + 8u * ew;
+    const uint32_t stg_in0 = stg_out0 + 2048;          // input set s: residual at +s*4096, mask at +s*4096 + 2048
+    const uint32_t ld_bar = ld_bar0 + 16u * ew;        // two barriers, one per input set
     const int c0 = half * 32;
     EpiArgs epi = a.epi;
     if (second) epi.shift = a.shift2;
@@ -324,7 +324,6 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       const bool has_res = (EPI & EPI_HAS_RES) && epi.residual != nullptr;
       const bool has_mask = (EPI & EPI_HAS_MASK) && epi.mask_src != nullptr;
       const bool has_in = has_res || has_mask;
-      uint32_t ld_parity = 0;
       float csum = 0.f;                    // per-lane column sum (channel c0 + lane) over all tiles
       float row_acc[COLSUM ? 32 : 1];      // staged path: this pixel row's running sums, reduced once at the end
 #pragma unroll
@@ -333,17 +332,25 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       PROF_BEGIN
       TileIt ti = tile_it(tile0, tstep);
       // this warp's 32 pixels = image rows h0+4*quad .. +3, 8 pixels each: a [1][4][8][32] TMA box.
-      // Residual / mask tiles are prefetched ONE TILE AHEAD (issued as soon as the previous tile has
-      // consumed the staging tiles), so their L2/HBM latency hides behind a whole tile of work.
-      auto issue_inputs = [&](const TileIt& c) {
+      // Residual / mask tiles are prefetched TWO TILES AHEAD into two staging sets: a set is refilled
+      // as soon as its tile's math is done, for the tile after the next one (one tile of lead was not
+      // enough -- the role profile showed 600-800 cycles per tile waiting for these loads).
+      auto issue_inputs = [&](const TileIt& c, int set) {
         if (elect_one()) {
-          mbar_expect_tx(ld_bar, (has_res ? 2048u : 0u) + (has_mask ? 2048u : 0u));
-          if (has_res) tma_load_4d(stg_res, &tmRes, ld_bar, c0, c.tw * Cfg::TW, c.th * Cfg::TH + 4 * quad, c.n);
-          if (has_mask) tma_load_4d(stg_mask, &tmMask, ld_bar, c0, c.tw * Cfg::TW, c.th * Cfg::TH + 4 * quad, c.n);
+          const uint32_t bar = ld_bar + 8u * set, dst = stg_in0 + (uint32_t)set * 4096u;
+          mbar_expect_tx(bar, (has_res ? 2048u : 0u) + (has_mask ? 2048u : 0u));
+          if (has_res) tma_load_4d(dst, &tmRes, bar, c0, c.tw * Cfg::TW, c.th * Cfg::TH + 4 * quad, c.n);
+          if (has_mask) tma_load_4d(dst + 2048, &tmMask, bar, c0, c.tw * Cfg::TW, c.th * Cfg::TH + 4 * quad, c.n);
         }
         __syncwarp();
       };
-      if (a.fast && has_in && tile0 < tile_end) issue_inputs(ti);
+      TileIt tp = ti;                      // prefetch cursor: two tiles ahead of the loop
+      if (a.fast && has_in) {
+        if (tile0 < tile_end) issue_inputs(tp, 0);
+        advance(tp);
+        if (tile0 + tstep < tile_end) issue_inputs(tp, 1);
+        advance(tp);
+      }
       for (int t = tile0; t < tile_end; t += tstep, ++it) {
         const int n = ti.n, h0 = ti.th * Cfg::TH, w0 = ti.tw * Cfg::TW;
         advance(ti);                         // ti = the NEXT tile from here on
@@ -357,10 +364,12 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         uint32_t raw[32];
         tmem_ld_32x32(tmem_base + acc * Cfg::BN + c0 + ((uint32_t)(quad * 32) << 16), raw);
         if (a.fast) {
-          const uint32_t stg_out = stg_out0 + (uint32_t)(it & 1) * 2048u;
-          PROF_WAIT_B(if (elect_one()) tma_store_wait_read<1>(); __syncwarp())      // the store from two tiles ago has left this buffer
+          const uint32_t stg_out = stg_out0;
+          const int set = it & 1;
+          const uint32_t stg_res = stg_in0 + (uint32_t)set * 4096u, stg_mask = stg_res + 2048u;
+          PROF_WAIT_B(if (elect_one()) tma_store_wait_read<0>(); __syncwarp())      // the previous tile's store has left the out tile
           tmem_ld_wait();
-          if (has_in) PROF_WAIT_B(mbar_wait(ld_bar, ld_parity))
+          if (has_in) PROF_WAIT_B(mbar_wait(ld_bar + 8u * set, (uint32_t)(it >> 1) & 1u))
           if (!(epi.flags & 32))          // flag 32: debug, skip the epilogue math (bottleneck probing)
             csum += epilogue_half_staged<64, EPI>(epi, raw, valid, c0, 0, lane, stg_out, stg_res, stg_mask,
                                                   COLSUM ? row_acc : nullptr);
@@ -368,8 +377,8 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty_bar(acc));
           if (has_in) {
-            ld_parity ^= 1;
-            if (t + tstep < tile_end) issue_inputs(ti);   // staging tiles are free again
+            if (t + 2 * tstep < tile_end) issue_inputs(tp, set);   // this set is free again
+            advance(tp);
           }
           fence_proxy_async();
           __syncwarp();
