@@ -233,7 +233,7 @@ def pair_speed():
     """single-CTA vs CTA-pair kernel on the layer2-4 shapes at the bench batch (forward 3B and dgrad B)"""
     torch, F, ops = _imports()
     g = torch.Generator(device="cuda").manual_seed(0)
-    for name, N, hw, C in (("l2_fwd", 768, 28, 128), ("l3_fwd", 768, 14, 256), ("l4_fwd", 768, 7, 512),
+    for name, N, hw, C in (("l1_fwd_halo", 768, 56, 64), ("l1_bwd_halo", 256, 56, 64), ("l2_fwd", 768, 28, 128), ("l3_fwd", 768, 14, 256), ("l4_fwd", 768, 7, 512),
                            ("l2_bwd", 256, 28, 128), ("l3_bwd", 256, 14, 256), ("l4_bwd", 256, 7, 512)):
         x = torch.randn(N, hw, hw, C, device="cuda", generator=g).to(torch.bfloat16)
         w = (torch.randn(C, 3, 3, C, device="cuda", generator=g) / (9 * C) ** 0.5).to(torch.bfloat16)

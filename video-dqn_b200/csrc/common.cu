@@ -16,6 +16,15 @@ static thread_local char g_err[512] = "";
 static std::atomic<long long> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
+// VDQN_PAIR=0 in the environment keeps every launch on the single-CTA kernels
+bool pair_default() {
+  static const bool on = [] {
+    const char* e = getenv("VDQN_PAIR");
+    return e == nullptr || e[0] != '0';
+  }();
+  return on;
+}
+
 bool pdl_enabled() {
   static const bool on = [] {
     const char* e = getenv("VDQN_PDL");

@@ -274,7 +274,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     };
     // accumulator drained: tell the MMA issuer (PAIR: the leader CTA's barrier, counted over both CTAs)
     auto release_acc = [&](int acc_i) {
-      if (PAIR) mbar_arrive_cluster(mapa_u32(tempty_bar(acc_i), 0));
+      if (PAIR && rank != 0) mbar_arrive_cluster(mapa_u32(tempty_bar(acc_i), 0));
       else mbar_arrive(tempty_bar(acc_i));
     };
     // scatter launches (zero-dilated destination: parity-class data gradients): the same staged
@@ -482,15 +482,6 @@ static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
     launch_kernel(kfn, grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream, tmA, tmB, tmB2, epi_maps[0], epi_maps[1], epi_maps[2], a);
   VDQN_CHECK_LAUNCH("igemm launch");
   return VDQN_OK;
-}
-
-// VDQN_PAIR=0 in the environment keeps every launch on the single-CTA kernel
-static bool pair_default() {
-  static const bool on = [] {
-    const char* e = getenv("VDQN_PAIR");
-    return e == nullptr || e[0] != '0';
-  }();
-  return on;
 }
 
 }  // namespace vdqn

@@ -199,11 +199,15 @@ template <int ROW_BYTES = 128, int EPI = EPI_HAS_ALL>
 __device__ __forceinline__ float epilogue_half_staged(const EpiArgs& a, const uint32_t (&raw)[32], bool valid,
                                                       int c0, int half, int lane, uint32_t stg_out,
                                                       uint32_t stg_res, uint32_t stg_mask,
-                                                      float* row_acc = nullptr) {
+                                                      float* row_acc = nullptr, const float* shift_r = nullptr) {
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-  if ((EPI & EPI_HAS_SHIFT_RELU) && a.shift != nullptr) {
+  if ((EPI & EPI_HAS_SHIFT_RELU) && shift_r != nullptr) {
+    // the caller keeps its 32 shift values in registers across tiles (zeros when there is no shift)
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] += shift_r[j];
+  } else if ((EPI & EPI_HAS_SHIFT_RELU) && a.shift != nullptr) {
     const float4* sp = reinterpret_cast<const float4*>(a.shift + c0);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -244,7 +248,9 @@ __device__ __forceinline__ float epilogue_half_staged(const EpiArgs& a, const ui
       }
     }
   }
-  if (!valid) {
+  // rows outside the image / matrix are never stored (TMA clips, the LSU copies check bounds): they
+  // only have to be zero for the column sums
+  if ((EPI & EPI_HAS_COLSUM) && !valid) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = 0.f;
   }

@@ -53,7 +53,12 @@ struct HaloArgs {
   EpiArgs epi;
 };
 
-template <int CK>
+// PAIR (CK = 64 only): the CTA is one half of a cta_group::2 pair.  The pair works on two tiles at a
+// time with ONE M = 256 MMA per (tap, k-step); each CTA stages its own halo window and only HALF of
+// the filter rows -- these kernels are bound by the shared-memory reads of the MMA operands
+// (role profile: ~1900 cycles per tile against 1152 of tensor-pipe time), and the filter is a third
+// of them.
+template <int CK, bool PAIR = false>
 struct HaloCfg {
   static constexpr int TH = 16, TW = 8, BN = 64;
   static constexpr int ROW_BYTES = CK * 2;
@@ -63,16 +68,21 @@ struct HaloCfg {
   static constexpr int HALO_H = (CK == 64) ? 18 : 19, HALO_W = (CK == 64) ? 10 : 11;
   static constexpr int HALO_BYTES = HALO_H * HALO_W * ROW_BYTES;
   static constexpr int STAGE_BYTES = (HALO_BYTES + 1023) / 1024 * 1024;
-  static constexpr int W_TILE_BYTES = BN * ROW_BYTES;              // one tap: 64 rows x CK
+  static constexpr int W_ROWS = PAIR ? BN / 2 : BN;               // filter rows staged by this CTA
+  static constexpr int W_TILE_BYTES = W_ROWS * ROW_BYTES;          // one tap: W_ROWS x CK
   static constexpr int W_BYTES = MAX_TAPS * W_TILE_BYTES;          // 72 KB / 32 KB, resident
   static constexpr int STAGES = (CK == 64) ? 3 : 12;
   // EIGHT epilogue warps, two per TMEM lane quadrant, each owning 32 of the 64 output columns with
-  // private staging tiles [32 pixels][32 ch] (64-byte rows, 64B swizzle): out, 2 x (residual, mask).
+  // private staging tiles [32 pixels][32 ch] (64-byte rows, 64B swizzle): OUT_BUFS x out,
+  // 2 x (residual, mask).  The out tile is double-buffered wherever shared memory allows (not next to
+  // the full 72 KB filter of the single-CTA 64-channel variant): with one buffer a warp waits ~700
+  // cycles per tile for the previous TMA store to have read it.
   // (role profile: with four warps the epilogue was the longest role of every variant of this kernel
   //  -- 1900 cycles per tile against 950 of MMA issue for the stem -- a single warp per scheduler
   //  cannot hide its own TMEM / shared-memory / mbarrier latencies.)
   static constexpr int EPI_WARPS = 8;
-  static constexpr int EPI_WARP_BYTES = 5 * 2048;
+  static constexpr int OUT_BUFS = (CK == 64 && !PAIR) ? 1 : 2;
+  static constexpr int EPI_WARP_BYTES = (OUT_BUFS + 4) * 2048;
   static constexpr int EPI_BYTES = EPI_WARPS * EPI_WARP_BYTES;
   // 12 warps = 384 threads: the register file then allows 168 registers per thread (416 threads were
   // compiled against the 512-thread limit of 128 and spilled)
@@ -95,12 +105,13 @@ __device__ __forceinline__ void tma_load_tiled_4d(uint32_t dst, const void* tmap
       : "memory");
 }
 
-template <int CK>
-__global__ void __launch_bounds__(HaloCfg<CK>::THREADS, 1)
+template <int CK, bool PAIR>
+__global__ void __launch_bounds__(HaloCfg<CK, PAIR>::THREADS, 1)
 halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                  const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
                  const __grid_constant__ CUtensorMap tmMask, const HaloArgs a) {
-  using Cfg = HaloCfg<CK>;
+  using Cfg = HaloCfg<CK, PAIR>;
+  static_assert(!PAIR || CK == 64, "CTA pairs: 64-channel variant only");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sW = smem_base;
@@ -130,7 +141,7 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     }
     for (int i = 0; i < Cfg::NACC; ++i) {
       mbar_init(tfull_bar(i), 1);
-      mbar_init(tempty_bar(i), Cfg::EPI_WARPS);
+      mbar_init(tempty_bar(i), (PAIR ? 2 : 1) * Cfg::EPI_WARPS);
     }
     mbar_init(w_bar, 1);
     for (int i = 0; i < 2 * Cfg::EPI_WARPS; ++i) mbar_init(ld_bar0 + 8u * i, 1);
@@ -140,19 +151,30 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   // warp 3: MMA issuer + TMEM owner, warps 4-11: epilogue (TMEM lane quadrant = warp & 3, column
   // half = (warp - 4) / 4)
   if (warp == Cfg::MMA_WARP) {
-    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-    tmem_relinquish();
+    if (PAIR) {
+      tmem_alloc_pair(tmem_slot, Cfg::TMEM_COLS);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();      // the peer's barriers must be initialised before anything signals them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   pdl_wait();
 
-  const bool second = a.split_cta > 0 && (int)blockIdx.x >= a.split_cta;
-  const int tile0 = (second ? a.split_tile : 0) + (int)blockIdx.x - (second ? a.split_cta : 0);
-  const int tstep = a.split_cta > 0 ? (second ? (int)gridDim.x - a.split_cta : a.split_cta) : (int)gridDim.x;
-  const int tile_end = (a.split_cta > 0 && !second) ? a.split_tile : a.num_tiles;
+  // PAIR: the schedule runs over CTA pairs and pairs of consecutive tiles; rank r takes tile 2*i + r
+  // (the host guarantees an even number of tiles in every range)
+  constexpr int MT = PAIR ? 2 : 1;
+  const int rank = PAIR ? (int)cluster_ctarank() : 0;
+  const int cta = (int)blockIdx.x / MT, ncta = (int)gridDim.x / MT, split_cta = a.split_cta / MT;
+  const bool second = split_cta > 0 && cta >= split_cta;
+  const int tile0 = (second ? a.split_tile : 0) + (cta - (second ? split_cta : 0)) * MT + rank;
+  const int tstep = (split_cta > 0 ? (second ? ncta - split_cta : split_cta) : ncta) * MT;
+  const int tile_end = (split_cta > 0 && !second) ? a.split_tile : a.num_tiles;
   const CUtensorMap* tmWp = second ? &tmW2 : &tmW;
 
   // Tile coordinates advance incrementally (a role is one warp walking its tiles in order; integer
@@ -180,8 +202,16 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     // the filter: one [64 x CK] tile per tap, resident for the whole kernel
     if (warp == 0) {
       if (elect_one()) {
-        mbar_expect_tx(w_bar, taps * Cfg::W_TILE_BYTES);
-        for (int j = 0; j < taps; ++j) tma_load_2d(sW + j * Cfg::W_TILE_BYTES, tmWp, w_bar, j * CK, 0);
+        if (PAIR) {
+          // both CTAs' filter halves signal the leader's barrier (its MMAs read both)
+          if (rank == 0) mbar_expect_tx(w_bar, 2 * taps * Cfg::W_TILE_BYTES);
+          const uint32_t wb = mapa_u32(w_bar, 0);
+          for (int j = 0; j < taps; ++j)
+            tma_load_2d_pair(sW + j * Cfg::W_TILE_BYTES, tmWp, wb, j * CK, rank * Cfg::W_ROWS);
+        } else {
+          mbar_expect_tx(w_bar, taps * Cfg::W_TILE_BYTES);
+          for (int j = 0; j < taps; ++j) tma_load_2d(sW + j * Cfg::W_TILE_BYTES, tmWp, w_bar, j * CK, 0);
+        }
       }
       __syncwarp();
     }
@@ -255,9 +285,15 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         PROF_TILE
         PROF_WAIT_A(mbar_wait(empty_bar(stage), phase ^ 1))
         if (elect_one()) {
-          mbar_expect_tx(full_bar(stage), Cfg::HALO_BYTES);
-          tma_load_tiled_4d(sA0 + stage * Cfg::STAGE_BYTES, &tmX, full_bar(stage), 0, w0 - a.pad_lo,
-                            h0 - a.pad_lo, n);
+          if (PAIR) {
+            if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * Cfg::HALO_BYTES);
+            tma_load_4d_pair(sA0 + stage * Cfg::STAGE_BYTES, &tmX, mapa_u32(full_bar(stage), 0), 0, w0 - a.pad_lo,
+                             h0 - a.pad_lo, n);
+          } else {
+            mbar_expect_tx(full_bar(stage), Cfg::HALO_BYTES);
+            tma_load_tiled_4d(sA0 + stage * Cfg::STAGE_BYTES, &tmX, full_bar(stage), 0, w0 - a.pad_lo,
+                              h0 - a.pad_lo, n);
+          }
         }
         __syncwarp();
         if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
@@ -265,7 +301,8 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       PROF_END(0)
     }
   } else if (warp == Cfg::MMA_WARP) {
-    constexpr uint32_t idesc = make_idesc_bf16(128, Cfg::BN, 0, 0);
+    constexpr uint32_t idesc = make_idesc_bf16(PAIR ? 256 : 128, Cfg::BN, 0, 0);
+    if (PAIR && rank != 0) goto teardown;       // only the leader CTA issues MMAs
     mbar_wait(w_bar, 0);
     int stage = 0;
     uint32_t phase = 0;
@@ -293,12 +330,18 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             for (int k = 0; k < CK / 16; ++k) {
               const uint64_t ad = a0 + (uint64_t)(((r * Cfg::HALO_W + s) * Cfg::ROW_BYTES + k * 32) >> 4);
               const uint64_t bd = b0 + (uint64_t)(((r * Cfg::S + s) * Cfg::W_TILE_BYTES + k * 32) >> 4);
-              umma_f16(d_tmem, ad, bd, idesc, (r | s | k) != 0);
+              if (PAIR) umma_f16_pair(d_tmem, ad, bd, idesc, (r | s | k) != 0);
+              else umma_f16(d_tmem, ad, bd, idesc, (r | s | k) != 0);
             }
           }
         }
-        umma_commit(empty_bar(stage));
-        umma_commit(tfull_bar(acc));
+        if (PAIR) {
+          umma_commit_pair(empty_bar(stage));
+          umma_commit_pair(tfull_bar(acc));
+        } else {
+          umma_commit(empty_bar(stage));
+          umma_commit(tfull_bar(acc));
+        }
       }
       __syncwarp();
       if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
@@ -311,11 +354,16 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     const int row = quad * 32 + lane;
     const int g = row >> 3, j = row & 7;
     const uint32_t stg_out0 = epi_base + ew * Cfg::EPI_WARP_BYTES;
-    const uint32_t stg_in0 = stg_out0 + 2048;          // input set s: residual at +s*4096, mask at +s*4096 + 2048
+    const uint32_t stg_in0 = stg_out0 + Cfg::OUT_BUFS * 2048;   // input set s: residual at +s*4096, mask at +s*4096 + 2048
     const uint32_t ld_bar = ld_bar0 + 16u * ew;        // two barriers, one per input set
     const int c0 = half * 32;
     EpiArgs epi = a.epi;
     if (second) epi.shift = a.shift2;
+    // accumulator drained: tell the MMA issuer (PAIR: the leader CTA's barrier, counted over both CTAs)
+    auto release_acc = [&](int acc_i) {
+      if (PAIR && rank != 0) mbar_arrive_cluster(mapa_u32(tempty_bar(acc_i), 0));
+      else mbar_arrive(tempty_bar(acc_i));
+    };
     // The tile loop is instantiated once per combination of optional epilogue steps and the launch
     // picks its specialisation (epilogue.cuh, epi_dispatch).
     auto epi_loop = [&](auto mode_tag) {
@@ -328,6 +376,12 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       float row_acc[COLSUM ? 32 : 1];      // staged path: this pixel row's running sums, reduced once at the end
 #pragma unroll
       for (int i = 0; i < (COLSUM ? 32 : 1); ++i) row_acc[i] = 0.f;
+      // this warp's 32 shift values stay in registers for the whole kernel
+      float shift_r[(EPI & EPI_HAS_SHIFT_RELU) ? 32 : 1];
+      if constexpr ((EPI & EPI_HAS_SHIFT_RELU) != 0) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) shift_r[i] = epi.shift != nullptr ? __ldg(epi.shift + c0 + i) : 0.f;
+      }
       int it = 0;
       PROF_BEGIN
       TileIt ti = tile_it(tile0, tstep);
@@ -364,18 +418,19 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         uint32_t raw[32];
         tmem_ld_32x32(tmem_base + acc * Cfg::BN + c0 + ((uint32_t)(quad * 32) << 16), raw);
         if (a.fast) {
-          const uint32_t stg_out = stg_out0;
+          const uint32_t stg_out = stg_out0 + (uint32_t)(it % Cfg::OUT_BUFS) * 2048u;
           const int set = it & 1;
           const uint32_t stg_res = stg_in0 + (uint32_t)set * 4096u, stg_mask = stg_res + 2048u;
-          PROF_WAIT_B(if (elect_one()) tma_store_wait_read<0>(); __syncwarp())      // the previous tile's store has left the out tile
+          PROF_WAIT_B(if (elect_one()) tma_store_wait_read<Cfg::OUT_BUFS - 1>(); __syncwarp())   // this out tile's last store has been read
           tmem_ld_wait();
           if (has_in) PROF_WAIT_B(mbar_wait(ld_bar + 8u * set, (uint32_t)(it >> 1) & 1u))
           if (!(epi.flags & 32))          // flag 32: debug, skip the epilogue math (bottleneck probing)
             csum += epilogue_half_staged<64, EPI>(epi, raw, valid, c0, 0, lane, stg_out, stg_res, stg_mask,
-                                                  COLSUM ? row_acc : nullptr);
+                                                  COLSUM ? row_acc : nullptr,
+                                                  (EPI & EPI_HAS_SHIFT_RELU) ? shift_r : nullptr);
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar(acc));
+          if (lane == 0) release_acc(acc);
           if (has_in) {
             if (t + 2 * tstep < tile_end) issue_inputs(tp, set);   // this set is free again
             advance(tp);
@@ -394,7 +449,7 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         csum += epilogue_chunk(epi, raw, valid, opix, opix, 0, c0, lane);
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty_bar(acc));
+        if (lane == 0) release_acc(acc);
       }
       PROF_END(5 + ew)
       if (COLSUM && a.epi.colsum != nullptr) {
@@ -411,24 +466,27 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     }
   }
 
+teardown:
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();      // neither CTA may exit while the other can still signal it
+  else __syncthreads();
   if (warp == Cfg::MMA_WARP) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if (PAIR) tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
+    else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
 }
 
 static int make_tiled_map_4d(CUtensorMap* map, const void* base, int N, int H, int W, int C, int box_c,
                              int box_w, int box_h, int swizzle_bytes);
 
-template <int CK>
+template <int CK, bool PAIR>
 static int launch_halo(const vdqn_conv_desc* d, cudaStream_t stream) {
-  using Cfg = HaloCfg<CK>;
+  using Cfg = HaloCfg<CK, PAIR>;
   DeviceInfo* dev = device_info();
   if (dev == nullptr) return VDQN_ERR_CUDA;
   static bool attr_set = false;
-  auto kfn = halo_conv_kernel<CK>;
+  auto kfn = halo_conv_kernel<CK, PAIR>;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess)
@@ -439,7 +497,7 @@ static int launch_halo(const vdqn_conv_desc* d, cudaStream_t stream) {
   int rc = make_tiled_map_4d(&tmX, d->x, d->N, d->H, d->W, d->Cin, CK, Cfg::TW + d->S - 1,
                              Cfg::TH + d->R - 1, CK == 64 ? 128 : 32);
   if (rc != VDQN_OK) return rc;
-  rc = make_tiled_map_2d(&tmW, d->w, (uint64_t)d->R * d->S * d->Cin, d->Cout, CK, 64, CK == 64 ? 128 : 32);
+  rc = make_tiled_map_2d(&tmW, d->w, (uint64_t)d->R * d->S * d->Cin, d->Cout, CK, Cfg::W_ROWS, CK == 64 ? 128 : 32);
   if (rc != VDQN_OK) return rc;
   CUtensorMap tmOut = tmX, tmRes = tmX, tmMask = tmX;
   const bool fast = fast_epilogue_ok(d) && d->ldc == d->Cout && (!d->residual || d->ldr == d->Cout) &&
@@ -461,21 +519,28 @@ static int launch_halo(const vdqn_conv_desc* d, cudaStream_t stream) {
   a.num_tiles = d->N * a.tiles_w * a.tiles_h;
   a.epi = make_epi_args(d);
   const int sms = d->max_ctas > 0 && d->max_ctas < dev->num_sms ? d->max_ctas : dev->num_sms;
-  const int grid = a.num_tiles < sms ? a.num_tiles : sms;
+  // schedule units: CTAs over tiles, or (PAIR) CTA pairs over pairs of tiles
+  constexpr int MT = PAIR ? 2 : 1;
+  const int units = a.num_tiles / MT, slots = sms / MT;
+  const int grid = units < slots ? units : slots;
   CUtensorMap tmW2 = tmW;
   a.split_tile = 0; a.split_cta = 0; a.shift2 = d->shift2;
   if (d->split_n > 0) {
     if (d->w2 == nullptr || d->split_n >= d->N || grid < 2)
       return set_error(VDQN_ERR_SHAPE, "halo_conv: bad dual-network launch");
-    rc = make_tiled_map_2d(&tmW2, d->w2, (uint64_t)d->R * d->S * d->Cin, d->Cout, CK, 64, CK == 64 ? 128 : 32);
+    rc = make_tiled_map_2d(&tmW2, d->w2, (uint64_t)d->R * d->S * d->Cin, d->Cout, CK, Cfg::W_ROWS, CK == 64 ? 128 : 32);
     if (rc != VDQN_OK) return rc;
     a.split_tile = d->split_n * a.tiles_w * a.tiles_h;
     int g0 = (int)((long)grid * a.split_tile / a.num_tiles);
     if (g0 < 1) g0 = 1;
     if (g0 > grid - 1) g0 = grid - 1;
-    a.split_cta = g0;
+    a.split_cta = g0 * MT;
   }
-  launch_kernel(kfn, grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream, tmX, tmW, tmW2, tmOut, tmRes, tmMask, a);
+  if (PAIR)
+    launch_kernel_cluster(kfn, grid * 2, Cfg::THREADS, Cfg::SMEM_BYTES, stream, 2, tmX, tmW, tmW2, tmOut, tmRes,
+                          tmMask, a);
+  else
+    launch_kernel(kfn, grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream, tmX, tmW, tmW2, tmOut, tmRes, tmMask, a);
   VDQN_CHECK_LAUNCH("halo_conv launch");
   return VDQN_OK;
 }
@@ -497,7 +562,14 @@ bool halo_conv_supported(const vdqn_conv_desc* d) {
 }
 
 int halo_conv_launch(const vdqn_conv_desc* d, cudaStream_t stream) {
-  return d->Cin == 64 ? launch_halo<64>(d, stream) : launch_halo<16>(d, stream);
+  if (d->Cin != 64) return launch_halo<16, false>(d, stream);
+  // CTA pairs need an even number of tiles (in both image ranges of a dual-network launch)
+  const int per_img = ((d->W + 7) / 8) * ((d->H + 15) / 16);
+  const bool even = ((long)d->N * per_img) % 2 == 0 && (d->split_n <= 0 || ((long)d->split_n * per_img) % 2 == 0);
+  const bool pair = even && d->N * per_img >= 2 && d->algo != 4 && (d->algo == 3 || pair_default());
+  if (d->algo == 3 && !pair)
+    return set_error(VDQN_ERR_SHAPE, "halo_conv: CTA-pair kernel requested for an unsupported shape");
+  return pair ? launch_halo<64, true>(d, stream) : launch_halo<64, false>(d, stream);
 }
 
 }  // namespace vdqn

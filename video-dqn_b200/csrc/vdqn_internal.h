@@ -65,6 +65,8 @@ void count_launch();
 // B = 256 step (CUDA-graph replay): 7.66 ms with, 7.55 ms without -- the persistent kernels fill
 // every SM, so an early-resident successor only takes issue slots from the tail; hence off by default.
 bool pdl_enabled();
+// CTA-pair (tcgen05 cta_group::2) kernels are used where a shape allows it unless VDQN_PAIR=0
+bool pair_default();
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
