@@ -189,6 +189,13 @@ int vdqn_linear_fwd(const float* x, const float* w, const float* bias, float* y,
 int vdqn_linear_bwd(const float* x, const float* w, const float* y, float* dy /* overwritten: masked */,
                     float* dx, float* dw, float* db,
                     int32_t B, int32_t K, int32_t O, int32_t relu, void* stream);
+/* First half of the backward of y = relu(x W^T + b) when the weight / data gradients run on the
+ * tensor-core conv kernels (top.0 seen as a 5x5 valid convolution over the head output,
+ * archs/HabitatDQNMultiAction.py:31): dy <- dy * (y > 0) in place, db[o] = sum_b dy[b,o], and an
+ * optional bf16 copy of the masked gradient (dy_bf16, [B][O]). */
+int vdqn_relu_mask_colsum(float* dy, const float* y, void* dy_bf16, float* db, int32_t B, int32_t O,
+                          int32_t relu, void* stream);
+
 /* head conv output bf16 [B][P][C] (NHWC) <-> fp32 [B][C*P] (torch Flatten order); the backward
  * also applies the head ReLU mask and accumulates the conv-bias gradient. */
 int vdqn_head_flatten_fwd(const void* h_nhwc, float* flat, int32_t B, int32_t P, int32_t C, void* stream);

@@ -288,6 +288,46 @@ def scatter_staged():
 
 
 @case
+def top0_as_conv():
+    """top.0 (Linear 1600 -> 512 over the NCHW-flattened head output) through the conv kernels:
+    forward = 5x5 valid conv (fp32 out), weight gradient = 5x5 conv wgrad, data gradient = full
+    correlation (pad 4) with ReLU mask + column sums"""
+    torch, F, ops = _imports()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    B = 256
+    h = torch.randn(B, 5, 5, 64, device="cuda", generator=g).relu().to(torch.bfloat16)
+    w = torch.randn(512, 1600, device="cuda", generator=g) / 40
+    bias = torch.randn(512, device="cuda", generator=g)
+    wf = torch.empty(512, 5, 5, 64, device="cuda", dtype=torch.bfloat16)
+    wd = torch.empty(64, 5, 5, 512, device="cuda", dtype=torch.bfloat16)
+    shift = torch.empty(512, device="cuda")
+    ops.weight_prep(w.view(512, 64, 5, 5), wf, shift, w_dgrad=wd, bias=bias)
+    flat = h.float().permute(0, 3, 1, 2).reshape(B, 1600)            # NCHW flatten (c*25 + p)
+    wq = wf.float().permute(0, 3, 1, 2).reshape(512, 1600)           # the bf16 weights, same order
+    ref = (flat @ wq.t() + bias).relu()
+    z1 = ops.conv_gemm(h, wf, 1, 0, 0, shift=shift, relu=True, out_f32=True)
+    ok = _report("top0:fwd", z1.view(B, 512), ref, 5e-3)
+    dz = torch.randn(B, 512, device="cuda", generator=g)
+    db = torch.empty(512, device="cuda")
+    dz16 = torch.empty(B, 512, device="cuda", dtype=torch.bfloat16)
+    dzm = dz * (ref > 0)
+    ops.relu_mask_colsum(dz, z1.view(B, 512), db, True, out_bf16=dz16)
+    ok &= _report("top0:mask", dz, dzm, 1e-6)
+    ok &= _report("top0:db", db[None], dzm.sum(0)[None], 1e-4)
+    part = ops.conv_wgrad(h, dz16.view(B, 1, 1, 512), 5, 5, 1, 0, 0, splits=1)
+    dw = torch.empty(512, 1600, device="cuda")
+    ops.wgrad_finalize(part, w, dw, splits=1, Cout=512, Cin=64, R=5, S=5, K=1600)
+    ok &= _report("top0:dw", dw, dz16.float().t() @ flat, 1e-2)
+    cs = torch.zeros(64, device="cuda")
+    dh = ops.conv_gemm(dz16.view(B, 1, 1, 512), wd, 1, 4, 4, mask_src=h, colsum=cs)
+    dflat = dz16.float() @ wq                                         # [B, 1600] in c*25 + p order
+    dh_ref = dflat.view(B, 64, 5, 5).permute(0, 2, 3, 1) * (h.float() > 0)
+    ok &= _report("top0:dh", dh, dh_ref, 2e-2)
+    ok &= _report("top0:dbias_head", cs[None], dh.float().reshape(-1, 64).sum(0)[None], 2e-3)
+    return ok
+
+
+@case
 def halo_conv_cases():
     ok = True
     ok &= _conv_case("halo_20x28", 3, 20, 28, 64, 64, 3, 1, 1, shift=True, residual=True, relu=True)

@@ -649,10 +649,11 @@ __global__ void bias_act_kernel(float* __restrict__ c, const float* __restrict__
   }
 }
 
-// dyp = dy * (y > 0 if relu); db[o] = sum_b dyp[b,o]   (one block per 32 columns)
+// dyp = dy * (y > 0 if relu); db[o] = sum_b dyp[b,o]   (one block per 32 columns);
+// dyp16: optional bf16 copy of dyp (operand of the tensor-core weight / data gradient of top.0)
 __global__ void mask_colsum_kernel(const float* __restrict__ dy, const float* __restrict__ y,
                                    float* __restrict__ dyp, float* __restrict__ db, int B, int O,
-                                   int relu) {
+                                   int relu, __nv_bfloat16* __restrict__ dyp16) {
   pdl_launch_dependents();
   pdl_wait();
   const int o = blockIdx.x * 32 + (threadIdx.x & 31);
@@ -663,6 +664,7 @@ __global__ void mask_colsum_kernel(const float* __restrict__ dy, const float* __
       float v = dy[(long)b * O + o];
       if (relu && !(y[(long)b * O + o] > 0.f)) v = 0.f;
       dyp[(long)b * O + o] = v;
+      if (dyp16 != nullptr) dyp16[(long)b * O + o] = __float2bfloat16_rn(v);
       s += v;
     }
   }
@@ -1001,7 +1003,7 @@ extern "C" int vdqn_linear_bwd(const float* x, const float* w, const float* y, f
   if (B == 0) return VDQN_OK;
   // dy is overwritten in place with the masked gradient (the caller owns it as scratch)
   float* dyp = dy;
-  launch_kernel(mask_colsum_kernel, (O + 31) / 32, 1024, 0, stream, dy, y, dyp, db, B, O, relu);
+  launch_kernel(mask_colsum_kernel, (O + 31) / 32, 1024, 0, stream, dy, y, dyp, db, B, O, relu, nullptr);
   VDQN_CHECK_LAUNCH("mask_colsum");
   // dw[o,k] = sum_b dyp[b,o] * x[b,k]
   int rc = launch_sgemm(dyp, x, dw, nullptr, O, K, B, 1, O, K, 1, K, 0, stream);
@@ -1009,6 +1011,18 @@ extern "C" int vdqn_linear_bwd(const float* x, const float* w, const float* y, f
   // dx[b,k] = sum_o dyp[b,o] * w[o,k]
   if (dx != nullptr) rc = launch_sgemm(dyp, w, dx, nullptr, B, K, O, O, 1, K, 1, K, 0, stream);
   return rc;
+}
+
+extern "C" int vdqn_relu_mask_colsum(float* dy, const float* y, void* dy_bf16, float* db, int32_t B, int32_t O,
+                                     int32_t relu, void* stream_v) {
+  if (dy == nullptr || db == nullptr) return set_error(VDQN_ERR_ARG, "relu_mask_colsum: null pointer");
+  if (relu && y == nullptr) return set_error(VDQN_ERR_ARG, "relu_mask_colsum: relu needs y");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+  if (B == 0) return VDQN_OK;
+  launch_kernel(mask_colsum_kernel, (O + 31) / 32, 1024, 0, stream, dy, y, dy, db, B, O, relu,
+                static_cast<__nv_bfloat16*>(dy_bf16));
+  VDQN_CHECK_LAUNCH("relu_mask_colsum");
+  return VDQN_OK;
 }
 
 extern "C" int vdqn_head_flatten_fwd(const void* h, float* flat, int32_t B, int32_t P, int32_t C, void* stream_v) {

@@ -18,6 +18,12 @@ from typing import Dict, List, Optional
 
 import os as _os
 
+# VDQN_TOP0_TENSOR=1: top.0 (1600 -> 512) on the tensor-core conv kernels with bf16 operands.  Off by
+# default: it saves ~0.2 ms of MLP kernels per step but rounds the first Q-head layer's weights to
+# bf16, which pushes the worst-case Q error (1.03e-2 measured) past the 1e-2 parity bar of SURVEY 8d;
+# the Q-head stays fp32 end to end.
+TOP0_TENSOR = _os.environ.get("VDQN_TOP0_TENSOR", "0") == "1"
+
 import torch
 
 from . import ops
@@ -70,6 +76,10 @@ class NetPlan:
     num_classes: int
     num_frames: int
     convs: List[ConvSpec] = field(default_factory=list)
+    # top.0 (Linear 1600 -> 512 on the flattened head output) as a 5x5 valid convolution over the
+    # [5,5,64] head output: flatten order c*25 + p == OIHW [512][64][5][5].  Single-frame nets only
+    # (with F frames the flattened index is frame-major).  None: fp32 SIMT path.
+    top0: Optional[ConvSpec] = None
 
 
 def make_plan(action_dim: int, num_classes: int = 5, num_frames: int = 1) -> NetPlan:
@@ -96,7 +106,14 @@ def make_plan(action_dim: int, num_classes: int = 5, num_frames: int = 1) -> Net
                     gemm_cin=512)
     plan = NetPlan(stem, blocks, head, action_dim, num_classes, num_frames)
     plan.convs = [stem] + [c for b in blocks for c in (b.conv1, b.conv2, b.ds) if c is not None] + [head]
+    if num_frames == 1 and TOP0_TENSOR:
+        plan.top0 = ConvSpec("top0", "top.0.weight", None, "top.0.bias", 64, 512, 5, 1, 0, 0, 5, 1, gemm_cin=64)
     return plan
+
+
+def prep_convs(plan: NetPlan) -> List[ConvSpec]:
+    """every tensor that has bf16 GEMM operands"""
+    return plan.convs + ([plan.top0] if plan.top0 is not None else [])
 
 
 def wgrad_uses_halo(spec: ConvSpec) -> bool:
@@ -130,7 +147,7 @@ class PreparedWeights:
         self.w_fwd: Dict[str, torch.Tensor] = {}
         self.w_dgrad: Dict[str, torch.Tensor] = {}
         self.shift: Dict[str, torch.Tensor] = {}
-        for c in plan.convs:
+        for c in prep_convs(plan):
             self.w_fwd[c.name] = torch.empty(c.cout, c.k, c.k, c.gemm_cin, device=device, dtype=bf16)
             if c.kmap == 0:
                 self.w_dgrad[c.name] = torch.empty(c.cin, c.k, c.k, c.cout, device=device, dtype=bf16)
@@ -141,8 +158,9 @@ class PreparedWeights:
         lives on the device and is rebuilt only when a parameter's storage moved."""
         import ctypes as C
         from . import _lib as L
-        sig = tuple(P[c.wkey].data_ptr() for c in self.plan.convs) + \
-            tuple(P[c.bn + ".weight"].data_ptr() for c in self.plan.convs if c.bn)
+        convs = prep_convs(self.plan)
+        sig = tuple(P[c.wkey].data_ptr() for c in convs) + \
+            tuple(P[c.bn + ".weight"].data_ptr() for c in convs if c.bn)
         if getattr(self, "_table_sig", None) != sig:
             # the stem (space-to-depth packing) goes through the element-wise kernel, everything else
             # through the tiled (coalesced) one
@@ -157,15 +175,20 @@ class PreparedWeights:
                     d.mean, d.var = P[c.bn + ".running_mean"].data_ptr(), P[c.bn + ".running_var"].data_ptr()
                 if c.bias is not None:
                     d.bias = P[c.bias].data_ptr()
-                d.Cout, d.Cin, d.R, d.S = w.shape
+                if w.dim() == 4:
+                    d.Cout, d.Cin, d.R, d.S = w.shape
+                else:                                   # top.0: [512, 1600] read as OIHW [512][64][5][5]
+                    d.Cout, d.Cin, d.R, d.S = c.cout, c.cin, c.k, c.k
                 d.K, d.kmap, d.eps = c.K, c.kmap, BN_EPS
                 d.dgrad_parity = int(c.kmap == 0 and c.stride == 2 and c.k == 3)
 
             def upload(descs):
                 return torch.frombuffer(bytearray(bytes(descs)), dtype=torch.uint8).clone().to(dev)
 
-            elem = [c for c in self.plan.convs if c.kmap != 0]
-            tiled = [c for c in self.plan.convs if c.kmap == 0]
+            # the tiled kernel holds 32 x 32 x (<= 9 taps) in shared memory; the stem (packing) and
+            # top.0 (25 taps) go through the element-wise one
+            elem = [c for c in convs if c.kmap != 0 or c.k * c.k > 9]
+            tiled = [c for c in convs if c.kmap == 0 and c.k * c.k <= 9]
             d_elem = (L.WprepDesc * len(elem))()
             offs, total = [], 0
             for d, c in zip(d_elem, elem):
@@ -251,7 +274,8 @@ class Workspace:
             self.r_dil = {b.out_hw: z(n, b.in_hw, b.in_hw, b.cin) for b in plan.blocks if b.stride == 2}
             self.dy_p = e(n, 56, 56, 64)
             self.dy_s = e(n, 112, 112, 64)
-            max_part = max(wgrad_splits(c, n) * c.cout * c.K for c in plan.convs)
+            max_part = max(wgrad_splits(c, n) * c.cout * c.K for c in prep_convs(plan))
+            self.dz1_bf16 = e(B, 512) if plan.top0 is not None else None
             self.part = e(max_part, dt=f32)
 
     def bwd_view(self):
@@ -330,13 +354,27 @@ def forward_packed(plan: NetPlan, W: PreparedWeights, P: Dict[str, torch.Tensor]
         _conv(W, b.conv2, ws.a1[i], ws.out[i], residual=idn, relu=True, **dual)
         x = ws.out[i]
     _conv(W, plan.head, x, ws.h, relu=True, **dual)
-    ops.head_flatten_fwd(ws.h, ws.flat)
-    parts = [(P, slice(0, ws.flat.shape[0]))]
+    t0 = plan.top0
+    nrow = ws.flat.shape[0]
+    if t0 is None:
+        ops.head_flatten_fwd(ws.h, ws.flat)
+    parts = [(P, W, slice(0, nrow))]
     if W2 is not None:
         bs = split // plan.num_frames
-        parts = [(P, slice(0, bs)), (P2, slice(bs, ws.flat.shape[0]))]
-    for Pn, rows in parts:
-        ops.linear_fwd(ws.flat[rows], Pn["top.0.weight"], Pn["top.0.bias"], True, ws.z1[rows])
+        parts = [(P, W, slice(0, bs)), (P2, W2, slice(bs, nrow))]
+    if t0 is not None:
+        # top.0 on the tensor cores: a 5x5 valid convolution over the head output, fp32 result
+        z1 = ws.z1.view(nrow, 1, 1, 512)
+        if W2 is not None and split % 128 == 0:
+            ops.conv_gemm(ws.h, W.w_fwd[t0.name], 1, 0, 0, shift=W.shift[t0.name], relu=True, out_f32=True, out=z1,
+                          w2=W2.w_fwd[t0.name], shift2=W2.shift[t0.name], split_n=split)
+        else:
+            for _, Wn, rows in parts:
+                ops.conv_gemm(ws.h[rows], Wn.w_fwd[t0.name], 1, 0, 0, shift=Wn.shift[t0.name], relu=True,
+                              out_f32=True, out=z1[rows])
+    for Pn, _, rows in parts:
+        if t0 is None:
+            ops.linear_fwd(ws.flat[rows], Pn["top.0.weight"], Pn["top.0.bias"], True, ws.z1[rows])
         ops.linear_fwd(ws.z1[rows], Pn["top.2.weight"], Pn["top.2.bias"], True, ws.z2[rows])
         ops.linear_fwd(ws.z2[rows], Pn["top.4.weight"], Pn["top.4.bias"], False, ws.q[rows])
     return ws.q
@@ -366,10 +404,21 @@ def backward(plan: NetPlan, W: PreparedWeights, P: Dict[str, torch.Tensor], G: D
     # ---- MLP (fp32)
     ops.linear_bwd(ws.z2, P["top.4.weight"], None, dq, G["top.4.weight"], G["top.4.bias"], False, dx=ws.dz2)
     ops.linear_bwd(ws.z1, P["top.2.weight"], ws.z2, ws.dz2, G["top.2.weight"], G["top.2.bias"], True, dx=ws.dz1)
-    ops.linear_bwd(ws.flat, P["top.0.weight"], ws.z1, ws.dz1, G["top.0.weight"], G["top.0.bias"], True,
-                   dx=ws.dflat)
-    # ---- head conv
-    ops.head_flatten_bwd(ws.dflat, ws.h, ws.dh, dbias=G["features.8.bias"])
+    t0 = plan.top0
+    if t0 is None:
+        ops.linear_bwd(ws.flat, P["top.0.weight"], ws.z1, ws.dz1, G["top.0.weight"], G["top.0.bias"], True,
+                       dx=ws.dflat)
+        # ---- head conv
+        ops.head_flatten_bwd(ws.dflat, ws.h, ws.dh, dbias=G["features.8.bias"])
+    else:
+        # top.0 backward on the tensor cores: masked gradient (+ bias gradient) in fp32 and bf16, then
+        # the weight gradient as a 5x5 conv weight gradient over the head output and the data gradient
+        # as the matching full correlation, whose epilogue applies the head ReLU mask and accumulates
+        # the head bias gradient
+        ops.relu_mask_colsum(ws.dz1, ws.z1, G["top.0.bias"], True, out_bf16=ws.dz1_bf16)
+        dy0 = ws.dz1_bf16.view(ws.dz1_bf16.shape[0], 1, 1, 512)
+        _wgrad(plan, P, G, ws, t0, ws.h, dy0, None)
+        ops.conv_gemm(dy0, W.w_dgrad[t0.name], 1, 4, 4, mask_src=ws.h, colsum=G["features.8.bias"], out=ws.dh)
     last = plan.blocks[-1]
     x_head = ws.out[-1]
     _wgrad(plan, P, G, ws, plan.head, x_head, ws.dh, None)

@@ -249,6 +249,16 @@ def linear_bwd(x, w, y, dy, dw, db, relu, dx=None, need_dx=True):
     return dx
 
 
+def relu_mask_colsum(dy, y, db, relu=True, out_bf16=None):
+    """dy <- dy * (y > 0) in place (fp32 [B, O]); db[o] = sum_b dy[b, o]; optional bf16 copy."""
+    lib = L.load()
+    B, O = dy.shape
+    with _Prof("mlp", (B, O)):
+        L.check(lib.vdqn_relu_mask_colsum(dy.data_ptr(), L.ptr(y), L.ptr(out_bf16), db.data_ptr(), B, O,
+                                          int(relu), L.stream_ptr()), "relu_mask_colsum")
+    return dy
+
+
 def head_flatten_fwd(h, flat=None):
     lib = L.load()
     _cuda(h, bf16, "h")
