@@ -218,6 +218,13 @@ typedef struct vdqn_td_desc {
   int32_t B, C, A;
   float gamma; float inv_count;
   int32_t double_dqn, clip_rect, linear, use_valid;
+  /* TRAIN_ON_GROUND_TRUTH (process_batch(compare_ground_truth=True), train_q_network.py:170-178):
+   * ground_truth != 0 regresses q_s[b,c,act[b]] onto gt[b,c] (float64, gamma^steps_to_reward from
+   * dataloaders/q_learning_real.py:86-89) instead of the Bellman target; q_next_*, rew, term are not
+   * read.  value_learning != 0 masks the NaN entries: l = 0.5 (q_b*mask - gt0)^2, mask = !isnan(gt);
+   * otherwise l = 0.5 (q_b - gt)^2 and NaNs propagate as in the reference. */
+  const double* gt;
+  int32_t ground_truth, value_learning;
 } vdqn_td_desc;
 int vdqn_td_epilogue(const vdqn_td_desc* d, void* stream);
 

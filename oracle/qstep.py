@@ -50,6 +50,8 @@ class StepConfig:
     TARGET_UPDATE_INTERVAL: int = 8000
     double_dqn: bool = True          # train_q_network.py:142 (143-144 is the plain variant)
     action_dim: int = 3
+    TRAIN_ON_GROUND_TRUTH: bool = False   # process_batch(compare_ground_truth=True), :224
+    VALUE_LEARNING: bool = False          # NaN-masked regression (:172-176); the net then has 1 action (:38)
 
 
 # ----------------------------------------------------------------------------
@@ -227,6 +229,23 @@ def td_loss(q_s, q_next_online, q_next_target, act, rew, term, valid_mask,
     return losses.mean(), {"best": best, "y": y, "q_b": q_b}
 
 
+def td_loss_ground_truth(q_s, act, ground_truth, value_learning: bool):
+    """The ``compare_ground_truth`` branch (TRAIN_ON_GROUND_TRUTH, train_q_network.py:170-178):
+    regress Q_b onto the discounted ground truth gamma^steps_to_reward
+    (dataloaders/q_learning_real.py:86-89).  With VALUE_LEARNING the NaN entries (classes never
+    reached) are masked: 0.5 (Q_b*mask - gt0)^2; without it the NaNs propagate, as in the reference."""
+    idx = act.view(-1, 1).repeat(1, NUM_CLASSES)
+    q_b = q_s.gather(2, idx.unsqueeze(2)).squeeze(2)
+    if value_learning:
+        mask = (1 - torch.isnan(ground_truth).int())
+        gt = ground_truth.clone()
+        gt[torch.isnan(ground_truth)] = 0
+        losses = 0.5 * (q_b * mask - gt.float()) ** 2
+    else:
+        losses = 0.5 * (q_b - ground_truth.float()) ** 2
+    return losses.mean()
+
+
 def td_grad_closed_form(q_s, act, y, valid_mask, cfg: StepConfig):
     """dLoss/dQ(s): (Q_b - y) * mask / (5B) on the taken action, else 0."""
     B = q_s.shape[0]
@@ -279,6 +298,11 @@ class OracleTrainer:
         self._realias(sd)
         A = self.cfg.action_dim
         q_s = q_forward(sd, before, A)
+        if self.cfg.TRAIN_ON_GROUND_TRUTH:
+            loss = td_loss_ground_truth(q_s, act, _gt, self.cfg.VALUE_LEARNING)
+            aux = {"q_s": q_s.detach()}
+            grads = torch.autograd.grad(loss, [leaves[n] for n in self.names])
+            return loss.detach(), dict(zip(self.names, grads)), aux
         with torch.no_grad():
             q_nt = q_forward(self.target, after, A)
             q_no = q_forward(sd, after, A)

@@ -384,3 +384,55 @@ def test_adam_and_target_sync_vs_oracle():
     opt2 = FusedAdam([torch.nn.Parameter(p.detach().clone()) for p in params], lr=1e-4)
     opt2.load_state_dict(sdict)
     assert opt2.state_dict()["state"][2]["exp_avg_sq"].shape == (512, 1600)
+
+
+@pytest.mark.gpu
+def test_td_branches_match_reference_goldens_on_device():
+    """The fused TD kernel on every loss branch of the reference (tests/golden/td_branches.npz, made by
+    the reference's own process_batch closure): loss and dLoss/dQ(s) to fp32 round-off."""
+    from video_dqn_b200 import ops
+    dev = _dev()
+    z = np.load(os.path.join(GOLD, "td_branches.npz"))
+    names = sorted({k.split("/")[0] for k in z.files})
+    assert len(names) == 6
+    for nm in names:
+        c = {k.split("/")[1]: torch.from_numpy(z[k]) for k in z.files if k.startswith(nm + "/")}
+        gamma, rect, linear, masked, vl, gt_mode, A = c["cfg"].tolist()
+        d = {k: v.to(dev) for k, v in c.items()}
+        if gt_mode:
+            loss, dq, _, _ = ops.td_epilogue(d["q_s"], None, None, d["act"], None, None, gt=d["gt"],
+                                             value_learning=bool(vl))
+        else:
+            loss, dq, _, _ = ops.td_epilogue(d["q_s"], d["q_no"], d["q_nt"], d["act"], d["rew"], d["rew"], d["valid"],
+                                             gamma=gamma, clip_rect=bool(rect), linear=bool(linear),
+                                             use_valid=bool(masked))
+        assert abs(loss.item() - c["loss"].item()) <= 2e-7 * max(1.0, abs(c["loss"].item())), nm
+        assert (dq.cpu() - c["dq"]).abs().max().item() <= 1e-7, nm
+
+
+@pytest.mark.gpu
+def test_ground_truth_value_learning_step_matches_oracle():
+    """TRAIN_ON_GROUND_TRUTH + VALUE_LEARNING (train_q_network.py:38,172-176,224): one action, the loss
+    regresses Q onto gamma^steps with NaN entries masked.  Fused learner step vs the oracle trainer."""
+    from video_dqn_b200.learner import QLearner, StepConfig
+    dev = _dev()
+    B = 8
+    sd = qstep.init_state(seed=4, action_dim=1, randomize_bn=True)
+    before, after, act, rew, term, _, valid = qstep.synthetic_batch(B, seed=1)
+    g = torch.Generator().manual_seed(11)
+    gt = torch.pow(torch.full((B, 5), 0.99, dtype=torch.float64), torch.randint(0, 40, (B, 5), generator=g).double())
+    gt[torch.rand(B, 5, generator=g) < 0.3] = float("nan")
+    batch = (before, after, torch.zeros(B, dtype=torch.long), rew, term, gt, valid)
+    ocfg = qstep.StepConfig(action_dim=1, TRAIN_ON_GROUND_TRUTH=True, VALUE_LEARNING=True)
+    tr = qstep.OracleTrainer(sd, ocfg)
+    l_ref, g_ref, _ = tr.loss_and_grads(batch)
+    m, t = _build(sd, dev, action_dim=1), _build(sd, dev, action_dim=1)
+    lr = QLearner(m, t, StepConfig(TRAIN_ON_GROUND_TRUTH=True, VALUE_LEARNING=True), batch_size=B, use_graph=False)
+    loss = lr.step([x.to(dev) if torch.is_tensor(x) else x for x in batch])
+    torch.cuda.synchronize()
+    assert abs(loss.item() - l_ref.item()) <= LOSS_RTOL * abs(l_ref.item()) + 1e-4
+    num = den = 0.0
+    for nme in m._grad_names:
+        a, b = lr.G[nme].detach().cpu().flatten().double(), g_ref[nme].flatten().double()
+        num += float(((a - b) ** 2).sum()); den += float((b ** 2).sum())
+    assert (num / den) ** 0.5 <= 0.2

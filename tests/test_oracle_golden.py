@@ -100,3 +100,31 @@ def test_u8_normalisation_fma_is_exact():
         fma = (np.arange(256, dtype=np.float64) * ka + kb).astype(np.float32)
         got = torch.from_numpy(fma).to(torch.bfloat16)
         assert torch.equal(got, ref[c]), c
+
+
+def _td_cases():
+    z = np.load(os.path.join(GOLD, "td_branches.npz"))
+    names = sorted({k.split("/")[0] for k in z.files})
+    for nm in names:
+        c = {k.split("/")[1]: torch.from_numpy(z[k]) for k in z.files if k.startswith(nm + "/")}
+        gamma, rect, linear, masked, vl, gt_mode, A = c["cfg"].tolist()
+        yield nm, c, qstep.StepConfig(GAMMA=gamma, LOSS_CLIP="rect" if rect else "none", LINEAR=bool(linear),
+                                      REMOVE_BEFORE_REWARD=bool(masked), action_dim=int(A)), bool(gt_mode), bool(vl)
+
+
+def test_td_branches_match_reference_goldens():
+    """Every branch of process_batch's loss (train_q_network.py:139-180: Double DQN, LINEAR, clip on/off,
+    REMOVE_BEFORE_REWARD, and the compare_ground_truth branches with / without VALUE_LEARNING) against
+    vectors produced by the reference's own closure (oracle/make_td_goldens.py): bit-identical."""
+    n = 0
+    for nm, c, cfg, gt_mode, vl in _td_cases():
+        qs = c["q_s"].clone().requires_grad_(True)
+        if gt_mode:
+            loss = qstep.td_loss_ground_truth(qs, c["act"], c["gt"], value_learning=vl)
+        else:
+            loss, _ = qstep.td_loss(qs, c["q_no"], c["q_nt"], c["act"], c["rew"], c["rew"], c["valid"], cfg)
+        loss.backward()
+        assert torch.equal(loss.detach(), c["loss"]), nm
+        assert torch.equal(qs.grad, c["dq"]), nm
+        n += 1
+    assert n == 6

@@ -48,7 +48,8 @@ class TdDesc(C.Structure):
     _fields_ = [(n, c_void_p) for n in ("q_s", "q_next_online", "q_next_target", "act", "rew", "term",
                                         "valid", "dq", "loss_out", "best_out", "y_out")] + \
                [(n, c_int) for n in ("B", "C", "A")] + [("gamma", c_float), ("inv_count", c_float)] + \
-               [(n, c_int) for n in ("double_dqn", "clip_rect", "linear", "use_valid")]
+               [(n, c_int) for n in ("double_dqn", "clip_rect", "linear", "use_valid")] + \
+               [("gt", c_void_p), ("ground_truth", c_int), ("value_learning", c_int)]
 
 
 EXPORTS = {

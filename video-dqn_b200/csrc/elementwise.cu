@@ -576,8 +576,8 @@ sgemm_strided_kernel(const float* __restrict__ A, const float* __restrict__ Bm, 
                      long b_rs, long b_cs, int ldc, int relu, int k_len) {
   pdl_launch_dependents();
   pdl_wait();
-  __shared__ float As[16][64 + 4];
-  __shared__ float Bs[16][64 + 4];
+  __shared__ __align__(16) float As[16][64 + 4];
+  __shared__ __align__(16) float Bs[16][64 + 4];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
   float acc[4][4];
@@ -605,11 +605,10 @@ sgemm_strided_kernel(const float* __restrict__ A, const float* __restrict__ Bm, 
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
-      float av[4], bv[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) av[i] = As[k][ty * 4 + i];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) bv[j] = Bs[k][tx * 4 + j];
+      // one 16-byte shared load per operand (row pitch 68 floats keeps ty*4 / tx*4 16-byte aligned)
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -724,6 +723,22 @@ __global__ void td_epilogue_kernel(const vdqn_td_desc d) {
        i += (long)gridDim.x * blockDim.x) {
     const long b = i / d.C;
     const float* qs = d.q_s + i * d.A;
+    if (d.ground_truth) {
+      // regression onto the ground-truth value (train_q_network.py:170-178)
+      const double gd = d.gt[i];
+      const int act = (int)d.act[b];
+      float mask = 1.f, g0 = (float)gd;
+      if (d.value_learning && isnan(gd)) { mask = 0.f; g0 = 0.f; }
+      const float diff = d.value_learning ? qs[act] * mask - g0 : qs[act] - g0;
+      local += 0.5f * diff * diff;
+      if (d.dq != nullptr) {
+        float* dq = d.dq + i * d.A;
+        for (int a = 0; a < d.A; ++a) dq[a] = (a == act) ? diff * mask * d.inv_count : 0.f;
+      }
+      if (d.y_out != nullptr) d.y_out[i] = g0;
+      if (d.best_out != nullptr) d.best_out[i] = 0;
+      continue;
+    }
     const float* qt = d.q_next_target + i * d.A;
     const float* qsel = d.double_dqn ? d.q_next_online + i * d.A : qt;
     int best = 0;
@@ -958,11 +973,13 @@ static int launch_sgemm(const float* A, const float* B, float* C, const float* b
   DeviceInfo* dev = device_info();
   if (dev == nullptr) return VDQN_ERR_CUDA;
   dim3 grid((N + 63) / 64, (M + 63) / 64, 1);
-  // under-filled grids (the MLP has M = batch): split K across blockIdx.z
+  // under-filled grids (the MLP has M = batch): split K across blockIdx.z.  The kernel is single-
+  // buffered, so a block's k-loop runs at global-memory latency; about four resident blocks per SM
+  // hide it (one block per SM left the 1600-deep top.0 products at 40-65 us).
   const int tiles = grid.x * grid.y;
   int splitk = 1;
-  if (tiles * 2 <= dev->num_sms && ldc == N) {
-    splitk = (dev->num_sms + tiles - 1) / tiles;
+  if (tiles < 4 * dev->num_sms && ldc == N) {
+    splitk = (4 * dev->num_sms + tiles - 1) / tiles;
     if (splitk > 16) splitk = 16;
     while (splitk > 1 && K / splitk < 64) --splitk;
   }
@@ -1048,11 +1065,16 @@ extern "C" int vdqn_head_flatten_bwd(const float* dflat, const void* h, void* dh
 }
 
 extern "C" int vdqn_td_epilogue(const vdqn_td_desc* d, void* stream_v) {
-  if (d == nullptr || d->q_s == nullptr || d->q_next_target == nullptr || d->act == nullptr ||
-      d->rew == nullptr || d->term == nullptr)
+  if (d == nullptr || d->q_s == nullptr || d->act == nullptr)
     return set_error(VDQN_ERR_ARG, "td_epilogue: null pointer");
-  if (d->double_dqn && d->q_next_online == nullptr)
-    return set_error(VDQN_ERR_ARG, "td_epilogue: double DQN needs q_next_online");
+  if (d->ground_truth) {
+    if (d->gt == nullptr) return set_error(VDQN_ERR_ARG, "td_epilogue: ground-truth mode needs gt");
+  } else {
+    if (d->q_next_target == nullptr || d->rew == nullptr || d->term == nullptr)
+      return set_error(VDQN_ERR_ARG, "td_epilogue: null pointer");
+    if (d->double_dqn && d->q_next_online == nullptr)
+      return set_error(VDQN_ERR_ARG, "td_epilogue: double DQN needs q_next_online");
+  }
   if (d->use_valid && d->valid == nullptr) return set_error(VDQN_ERR_ARG, "td_epilogue: valid mask missing");
   if (d->A < 1 || d->C < 1 || d->B < 0) return set_error(VDQN_ERR_SHAPE, "td_epilogue: bad shape");
   GET_DEV();

@@ -37,12 +37,18 @@ class StepConfig:
     LEARNING_RATE: float = 1e-4
     TARGET_UPDATE_INTERVAL: int = 8000
     double_dqn: bool = True
+    # process_batch(compare_ground_truth=config.TRAIN_ON_GROUND_TRUTH) (train_q_network.py:224):
+    # regress Q(s, a) onto the loader's discounted ground truth instead of the Bellman target;
+    # VALUE_LEARNING masks its NaN entries (:172-176)
+    TRAIN_ON_GROUND_TRUTH: bool = False
+    VALUE_LEARNING: bool = False
 
     @classmethod
     def from_config(cls, config):
         """Build from the reference's flattened ExperimentConfig attribute bag."""
         kw = {f: getattr(config, f) for f in ("GAMMA", "LOSS_CLIP", "LINEAR", "REMOVE_BEFORE_REWARD",
-                                              "LEARNING_RATE", "TARGET_UPDATE_INTERVAL") if hasattr(config, f)}
+                                              "LEARNING_RATE", "TARGET_UPDATE_INTERVAL",
+                                              "TRAIN_ON_GROUND_TRUTH", "VALUE_LEARNING") if hasattr(config, f)}
         return cls(**kw)
 
 
@@ -83,17 +89,21 @@ class QLearner:
         self.scalars_dev = torch.zeros(2, device=dev, dtype=torch.float32)
         # ---- static inputs
         n = batch_size * F
+        self.gt_mode = bool(self.cfg.TRAIN_ON_GROUND_TRUTH)
+        nb = 1 if self.gt_mode else 2            # ground-truth regression never looks at s'
         # `before` and `after` are the two halves of one [2B, ...] buffer: the online network runs on
         # both in a single 2B forward (bit-identical to two B forwards: eval-mode BN has no batch
         # statistics)
         if frames_uint8:
-            shp = (2 * batch_size, F, 224, 224, 3) if F > 1 else (2 * batch_size, 224, 224, 3)
+            shp = (nb * batch_size, F, 224, 224, 3) if F > 1 else (nb * batch_size, 224, 224, 3)
             self.frames2 = torch.zeros(shp, device=dev, dtype=torch.uint8)
         else:
-            shp = (2 * batch_size, F, 3, 224, 224) if F > 1 else (2 * batch_size, 3, 224, 224)
+            shp = (nb * batch_size, F, 3, 224, 224) if F > 1 else (nb * batch_size, 3, 224, 224)
             self.frames2 = torch.zeros(shp, device=dev, dtype=torch.float32)
-        self.before, self.after = self.frames2[:batch_size], self.frames2[batch_size:]
+        self.before = self.frames2[:batch_size]
+        self.after = None if self.gt_mode else self.frames2[batch_size:]
         C = self.plan.num_classes
+        self.gt = torch.full((batch_size, C), float("nan"), device=dev, dtype=torch.float64)
         self.act = torch.zeros(batch_size, device=dev, dtype=torch.int64)
         self.rew = torch.zeros(batch_size, C, device=dev, dtype=torch.int64)
         self.term = torch.zeros(batch_size, C, device=dev, dtype=torch.int64)
@@ -102,8 +112,13 @@ class QLearner:
         # B*F % 64 == 0: online [s ; s'] and target [s'] share ONE 3B forward pass (every conv launch
         # splits its CTAs between the two networks); otherwise a 2B online pass + a B target pass
         self.one_pass = (n % 64 == 0) if one_pass is None else (bool(one_pass) and n % 64 == 0)
-        self.ws_train = E.Workspace(self.plan, (3 if self.one_pass else 2) * n, dev, train=True, n_bwd=n)
-        self.ws_eval = None if self.one_pass else E.Workspace(self.plan, n, dev, train=False)
+        if self.gt_mode:
+            self.one_pass = False
+            self.ws_train = E.Workspace(self.plan, n, dev, train=True, n_bwd=n)
+            self.ws_eval = None
+        else:
+            self.ws_train = E.Workspace(self.plan, (3 if self.one_pass else 2) * n, dev, train=True, n_bwd=n)
+            self.ws_eval = None if self.one_pass else E.Workspace(self.plan, n, dev, train=False)
         A = self.plan.action_dim
         self.dq = torch.empty(batch_size, C * A, device=dev, dtype=torch.float32)
         self.loss = torch.zeros(1, device=dev, dtype=torch.float32)
@@ -128,7 +143,12 @@ class QLearner:
         # target net on s' (nothing kept)
         B = self.B
         wt = self.ws_train
-        if self.one_pass:
+        if self.gt_mode:
+            E.forward(plan, st.W, st.P, wt, self._frames(self.frames2))
+            ops.td_epilogue(wt.q.view(B, C, A), None, None, self.act, None, None, gt=self.gt,
+                            value_learning=cfg.VALUE_LEARNING, inv_count=1.0 / (B * C),
+                            dq=self.dq.view(B, C, A), loss=self.loss)
+        elif self.one_pass:
             n = B * plan.num_frames
             ops.stem_pack(self._frames(self.frames2), wt.xp[:2 * n])
             wt.xp[2 * n:].copy_(wt.xp[n:2 * n])            # the target net sees s' too
@@ -138,12 +158,13 @@ class QLearner:
             E.forward(plan, st.W, st.P, wt, self._frames(self.frames2))
             E.forward(plan, tt.W, tt.P, self.ws_eval, self._frames(self.after))
             q_nt = self.ws_eval.q
-        ops.td_epilogue(wt.q[:B].view(B, C, A), wt.q[B:2 * B].view(B, C, A),
-                        q_nt.view(B, C, A), self.act, self.rew, self.term, self.valid,
-                        gamma=cfg.GAMMA, double_dqn=cfg.double_dqn, clip_rect=(cfg.LOSS_CLIP == "rect"),
-                        linear=cfg.LINEAR, use_valid=cfg.REMOVE_BEFORE_REWARD,
-                        inv_count=1.0 / (B * C), dq=self.dq.view(B, C, A), loss=self.loss,
-                        best=self.best, y=self.y)
+        if not self.gt_mode:
+            ops.td_epilogue(wt.q[:B].view(B, C, A), wt.q[B:2 * B].view(B, C, A),
+                            q_nt.view(B, C, A), self.act, self.rew, self.term, self.valid,
+                            gamma=cfg.GAMMA, double_dqn=cfg.double_dqn, clip_rect=(cfg.LOSS_CLIP == "rect"),
+                            linear=cfg.LINEAR, use_valid=cfg.REMOVE_BEFORE_REWARD,
+                            inv_count=1.0 / (B * C), dq=self.dq.view(B, C, A), loss=self.loss,
+                            best=self.best, y=self.y)
         sync = self.grad_sync
         E.backward(plan, st.W, st.P, self.G, self.ws_train, self.dq,
                    on_grads_ready=(sync.on_stage if sync is not None else None))
@@ -163,10 +184,14 @@ class QLearner:
     def load_batch(self, batch, non_blocking: bool = True):
         """Copy a reference-format batch (before, after, act, rew, term, gt, valid_mask)
         (dataloaders/q_learning_real.py:98) into the static device buffers."""
-        before, after, act, rew, term, _gt, valid = batch
+        before, after, act, rew, term, gt, valid = batch
         if before.shape[0] != self.B:
             raise ValueError("bad shape")
         self.before.copy_(before.view(self.before.shape), non_blocking=non_blocking)
+        if self.gt_mode:
+            self.gt.copy_(torch.as_tensor(gt, dtype=torch.float64).view(self.gt.shape), non_blocking=non_blocking)
+            self.act.copy_(act.view(-1), non_blocking=non_blocking)
+            return
         self.after.copy_(after.view(self.after.shape), non_blocking=non_blocking)
         self.act.copy_(act.view(-1), non_blocking=non_blocking)
         self.rew.copy_(rew, non_blocking=non_blocking)

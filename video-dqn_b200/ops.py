@@ -288,19 +288,29 @@ def head_flatten_bwd(dflat, h, dh=None, dbias=None):
 
 def td_epilogue(q_s, q_next_online, q_next_target, act, rew, term, valid=None, *, gamma=0.99,
                 double_dqn=True, clip_rect=True, linear=False, use_valid=False, inv_count=None,
-                dq=None, loss=None, best=None, y=None, want_aux=False):
-    """Fused Double-DQN TD loss + gradient.  Returns (loss[1] fp32, dq [B,C,A] fp32, best, y)."""
+                dq=None, loss=None, best=None, y=None, want_aux=False, gt=None, value_learning=False):
+    """Fused Double-DQN TD loss + gradient.  Returns (loss[1] fp32, dq [B,C,A] fp32, best, y).
+    `gt` (float64 [B,C]) switches to the ground-truth regression of
+    process_batch(compare_ground_truth=True) (train_q_network.py:170-178); q_next_*, rew, term may
+    then be None."""
     lib = L.load()
-    for t, n in ((q_s, "q_s"), (q_next_target, "q_next_target")):
-        _cuda(t, torch.float32, n)
-    _req(q_s.dim() == 3 and q_s.shape == q_next_target.shape, "bad shape")
+    _cuda(q_s, torch.float32, "q_s")
+    _req(q_s.dim() == 3, "bad shape")
     B, Cc, A = q_s.shape
-    for t, n in ((act, "act"), (rew, "rew"), (term, "term")):
-        _cuda(t, torch.int64, n)
-    _req(act.numel() == B and rew.numel() == B * Cc and term.numel() == B * Cc, "bad shape")
-    if q_next_online is not None:
-        _cuda(q_next_online, torch.float32, "q_next_online")
-        _req(q_next_online.shape == q_s.shape, "bad shape")
+    _cuda(act, torch.int64, "act")
+    _req(act.numel() == B, "bad shape")
+    if gt is None:
+        _cuda(q_next_target, torch.float32, "q_next_target")
+        _req(q_s.shape == q_next_target.shape, "bad shape")
+        for t, n in ((rew, "rew"), (term, "term")):
+            _cuda(t, torch.int64, n)
+        _req(rew.numel() == B * Cc and term.numel() == B * Cc, "bad shape")
+        if q_next_online is not None:
+            _cuda(q_next_online, torch.float32, "q_next_online")
+            _req(q_next_online.shape == q_s.shape, "bad shape")
+    else:
+        _cuda(gt, torch.float64, "ground_truth")
+        _req(gt.numel() == B * Cc, "bad shape")
     if use_valid:
         _cuda(valid, torch.int64, "valid_mask")
     dev = q_s.device
@@ -312,13 +322,14 @@ def td_epilogue(q_s, q_next_online, q_next_target, act, rew, term, valid=None, *
         best = torch.empty(B, Cc, device=dev, dtype=torch.int64) if best is None else best
         y = torch.empty(B, Cc, device=dev, dtype=torch.float32) if y is None else y
     d = L.TdDesc()
-    d.q_s, d.q_next_online, d.q_next_target = q_s.data_ptr(), L.ptr(q_next_online), q_next_target.data_ptr()
-    d.act, d.rew, d.term, d.valid = act.data_ptr(), rew.data_ptr(), term.data_ptr(), L.ptr(valid)
+    d.q_s, d.q_next_online, d.q_next_target = q_s.data_ptr(), L.ptr(q_next_online), L.ptr(q_next_target)
+    d.act, d.rew, d.term, d.valid = act.data_ptr(), L.ptr(rew), L.ptr(term), L.ptr(valid)
     d.dq, d.loss_out, d.best_out, d.y_out = dq.data_ptr(), loss.data_ptr(), L.ptr(best), L.ptr(y)
     d.B, d.C, d.A = B, Cc, A
     d.gamma = gamma
     d.inv_count = (1.0 / (B * Cc)) if inv_count is None else inv_count
     d.double_dqn, d.clip_rect, d.linear, d.use_valid = int(double_dqn), int(clip_rect), int(linear), int(use_valid)
+    d.gt, d.ground_truth, d.value_learning = L.ptr(gt), int(gt is not None), int(value_learning)
     with _Prof("td", (B, Cc, A)):
         L.check(lib.vdqn_td_epilogue(C.byref(d), L.stream_ptr()), "td_epilogue")
     return loss, dq, best, y

@@ -13,7 +13,10 @@ class BatchStager:
     def __init__(self, learner, depth: int = 2):
         self.lr = learner
         self.copy_stream = torch.cuda.Stream()
-        fields = ("before", "after", "act", "rew", "term", "valid")
+        # ground-truth regression (TRAIN_ON_GROUND_TRUTH) consumes only (before, act, gt)
+        fields = ("before", "act", "gt") if getattr(learner, "gt_mode", False) else \
+            ("before", "after", "act", "rew", "term", "valid")
+        self.fields = fields
         self.dev = [{f: torch.empty_like(getattr(learner, f)) for f in fields} for _ in range(depth)]
         self.pin = [{f: torch.empty(getattr(learner, f).shape, dtype=getattr(learner, f).dtype,
                                     pin_memory=True) for f in fields} for _ in range(depth)]
@@ -27,8 +30,9 @@ class BatchStager:
     def push(self, batch):
         """Host side: copy into pinned memory (if not already pinned) and enqueue the H2D."""
         i = self.head % self.depth
-        before, after, act, rew, term, _gt, valid = batch
-        src = dict(before=before, after=after, act=act.view(-1), rew=rew, term=term, valid=valid)
+        before, after, act, rew, term, gt, valid = batch
+        src = dict(before=before, after=after, act=act.view(-1), rew=rew, term=term, valid=valid, gt=gt)
+        src = {f: src[f] for f in self.fields}
         self.consumed[i].synchronize()                 # slot free (its D2D copy has run)
         with torch.cuda.stream(self.copy_stream):
             for f, t in src.items():
