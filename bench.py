@@ -130,7 +130,7 @@ def make_config(world, B, graph):
             "random_init_weights": True}
 
 
-def run_reference(a):
+def run_reference(a, out_stream=sys.stdout):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -149,11 +149,22 @@ def run_reference(a):
                        sample=sample, threads=threads),
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    }), file=out_stream, flush=True)
 
 
 # ----------------------------------------------------------------------------------------------
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Native libraries write there too (NCCL prints its
+    version banner on stdout when NCCL_DEBUG is set in the environment), so keep a private handle on
+    the real stdout for the JSON line and point file descriptor 1 at stderr for everything else."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 def main():
+    out_stream = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
@@ -167,7 +178,7 @@ def main():
     ap.add_argument("--no-inference", action="store_true")
     a = ap.parse_args()
     if a.impl == "reference":
-        return run_reference(a)
+        return run_reference(a, out_stream)
     a.warmup = max(a.warmup, 3)
 
     import torch
@@ -394,7 +405,7 @@ def main():
             "breakdown_eager_ms": breakdown if rank == 0 else None,
             "inference": inference,
         }
-        print(json.dumps(out))
+        print(json.dumps(out), file=out_stream, flush=True)
     if world > 1:
         # NCCL collectives captured in CUDA graphs keep the communicator busy at teardown
         # (destroy_process_group blocks); everything is reported, so leave without the destructor.
