@@ -436,3 +436,34 @@ def test_ground_truth_value_learning_step_matches_oracle():
         a, b = lr.G[nme].detach().cpu().flatten().double(), g_ref[nme].flatten().double()
         num += float(((a - b) ** 2).sum()); den += float((b ** 2).sum())
     assert (num / den) ** 0.5 <= 0.2
+
+
+@pytest.mark.gpu
+def test_real_data_batch_through_stager_and_learner():
+    """SURVEY 8f-3 end to end: data.feather + JPEGs -> pinned uint8 batch (realdata.QuadrupletLoader) ->
+    BatchStager (async H2D) -> fused step, against the oracle fed the reference loader's normalised
+    float frames for the same rows."""
+    from video_dqn_b200.learner import QLearner, StepConfig
+    from video_dqn_b200.realdata import QuadrupletLoader, QuadrupletTable
+    from video_dqn_b200.staging import BatchStager
+    dev = _dev()
+    root = os.path.join(GOLD, "realdata")
+    tab = QuadrupletTable(os.path.join(root, "data.feather"), inverse_actions=True)
+    ld = QuadrupletLoader(tab, batch_size=4, seed=0, prefetch=1, workers=2)
+    batch = next(ld)
+    sd = qstep.init_state(seed=4, randomize_bn=True)
+    ref_batch = (qstep.to_imgnet(batch[0]), qstep.to_imgnet(batch[1])) + tuple(t.clone() for t in batch[2:])
+    l_ref, g_ref, _ = qstep.OracleTrainer(sd).loss_and_grads(ref_batch)
+    m, t = _build(sd, dev), _build(sd, dev)
+    lr = QLearner(m, t, StepConfig(), batch_size=4, frames_uint8=True, use_graph=False)
+    st = BatchStager(lr)
+    st.push(batch)
+    st.pop_into_learner()
+    loss = lr.step()
+    torch.cuda.synchronize()
+    assert abs(loss.item() - l_ref.item()) <= LOSS_RTOL * abs(l_ref.item()) + 1e-4
+    num = den = 0.0
+    for nme in m._grad_names:
+        a, b = lr.G[nme].detach().cpu().flatten().double(), g_ref[nme].flatten().double()
+        num += float(((a - b) ** 2).sum()); den += float((b ** 2).sum())
+    assert (num / den) ** 0.5 <= 0.2
