@@ -467,3 +467,31 @@ def test_real_data_batch_through_stager_and_learner():
         a, b = lr.G[nme].detach().cpu().flatten().double(), g_ref[nme].flatten().double()
         num += float(((a - b) ** 2).sum()); den += float((b ** 2).sum())
     assert (num / den) ** 0.5 <= 0.2
+
+
+@pytest.mark.gpu
+def test_inverse_action_model_forward_matches_reference_golden():
+    """the inverse-dynamics network that labels the `inverse_actions` column
+    (archs/inverse_action2.py:45-100, dataset/process_episodes_real.py:171-179), forward only, on the
+    conv engine -- against tests/golden/inverse_b4.npz, which oracle/make_inverse_goldens.py produced
+    with the reference's own module (oracle == reference to 0 ulp there)."""
+    from oracle import inverse as oinv
+    from video_dqn_b200.inverse import InverseActionRunner
+    dev = _dev()
+    z = np.load(os.path.join(GOLD, "inverse_b4.npz"))
+    sd = oinv.init_state(seed=int(z["seed"]))
+    g = torch.Generator().manual_seed(int(z["data_seed"]))
+    k = torch.randn(4, 3, 224, 224, generator=g)
+    k1 = torch.randn(4, 3, 224, 224, generator=g)
+    run = InverseActionRunner(sd, 4, dev)
+    enc, y = run(k.to(dev), k1.to(dev))
+    torch.cuda.synchronize()
+    y_ref, enc_ref = torch.from_numpy(z["y"]), torch.from_numpy(z["encoding"])
+    scale = y_ref.abs().max().item()
+    assert (y.cpu() - y_ref).abs().max().item() <= 2e-2 * max(1.0, scale)
+    assert (enc.cpu() - enc_ref).abs().max().item() <= 2e-2
+    top2 = y_ref.topk(2, dim=1).values
+    clear = (top2[:, 0] - top2[:, 1]) > 4e-2 * max(1.0, scale)
+    assert (run.label(k.to(dev), k1.to(dev)).cpu()[clear] == y_ref.argmax(1)[clear]).all()
+    with pytest.raises(ValueError, match="bad shape"):
+        run(k[:2].to(dev), k1[:2].to(dev))

@@ -128,3 +128,19 @@ def test_td_branches_match_reference_goldens():
         assert torch.equal(qs.grad, c["dq"]), nm
         n += 1
     assert n == 6
+
+
+def test_inverse_model_oracle_reproduces_reference_golden():
+    """oracle/inverse.py against the outputs of the reference's own inverse_action2.model
+    (tests/golden/inverse_b4.npz, oracle/make_inverse_goldens.py)."""
+    from oracle import inverse as oinv
+    z = np.load(os.path.join(GOLD, "inverse_b4.npz"))
+    sd = oinv.init_state(seed=int(z["seed"]))
+    g = torch.Generator().manual_seed(int(z["data_seed"]))
+    k = torch.randn(4, 3, 224, 224, generator=g)
+    k1 = torch.randn(4, 3, 224, 224, generator=g)
+    with torch.no_grad():
+        enc, y = oinv.forward(sd, k, k1)
+    np.testing.assert_allclose(y.numpy(), z["y"], atol=1e-5)
+    np.testing.assert_allclose(enc.numpy(), z["encoding"], atol=1e-6)
+    assert torch.equal(oinv.label(sd, k, k1), torch.from_numpy(z["y"]).argmax(1))

@@ -142,12 +142,14 @@ def wgrad_splits(spec: ConvSpec, n_img: int, sms: int = 0) -> int:
 class PreparedWeights:
     """bf16 GEMM operands + fp32 shifts for every conv, regenerated from the fp32 masters."""
 
-    def __init__(self, plan: NetPlan, device):
+    def __init__(self, plan: NetPlan, device, trunk_only: bool = False):
+        """trunk_only: the ResNet trunk alone (the inverse-dynamics model reuses it under its own head)"""
         self.plan = plan
         self.w_fwd: Dict[str, torch.Tensor] = {}
         self.w_dgrad: Dict[str, torch.Tensor] = {}
         self.shift: Dict[str, torch.Tensor] = {}
-        for c in prep_convs(plan):
+        self.convs = [c for c in prep_convs(plan) if not (trunk_only and c.name in ("head", "top0"))]
+        for c in self.convs:
             self.w_fwd[c.name] = torch.empty(c.cout, c.k, c.k, c.gemm_cin, device=device, dtype=bf16)
             if c.kmap == 0:
                 self.w_dgrad[c.name] = torch.empty(c.cin, c.k, c.k, c.cout, device=device, dtype=bf16)
@@ -158,7 +160,7 @@ class PreparedWeights:
         lives on the device and is rebuilt only when a parameter's storage moved."""
         import ctypes as C
         from . import _lib as L
-        convs = prep_convs(self.plan)
+        convs = self.convs
         sig = tuple(P[c.wkey].data_ptr() for c in convs) + \
             tuple(P[c.bn + ".weight"].data_ptr() for c in convs if c.bn)
         if getattr(self, "_table_sig", None) != sig:
@@ -336,7 +338,7 @@ def forward(plan: NetPlan, W: PreparedWeights, P: Dict[str, torch.Tensor], ws: W
 
 def forward_packed(plan: NetPlan, W: PreparedWeights, P: Dict[str, torch.Tensor], ws: Workspace,
                    W2: Optional[PreparedWeights] = None, P2: Optional[Dict[str, torch.Tensor]] = None,
-                   split: int = 0) -> torch.Tensor:
+                   split: int = 0, trunk_only: bool = False) -> torch.Tensor:
     """Forward from the packed input ws.xp.  With (W2, P2, split) the frames [split, n) go through a
     SECOND network (the target net) inside the same launches: every conv kernel partitions its CTAs
     between the two image ranges, so online and target forwards share one pass (better SM filling
@@ -353,6 +355,8 @@ def forward_packed(plan: NetPlan, W: PreparedWeights, P: Dict[str, torch.Tensor]
             idn = ws.idn[i]
         _conv(W, b.conv2, ws.a1[i], ws.out[i], residual=idn, relu=True, **dual)
         x = ws.out[i]
+    if trunk_only:
+        return x                                      # [n, 7, 7, 512] bf16
     _conv(W, plan.head, x, ws.h, relu=True, **dual)
     t0 = plan.top0
     nrow = ws.flat.shape[0]
