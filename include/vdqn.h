@@ -89,6 +89,10 @@ typedef struct vdqn_conv_desc {
   const void* w2;
   const float* shift2;
   int32_t split_n;
+  /* Input aliasing (packed-stem halo kernel only): images n >= x_alias_from are read from image
+   * n - x_alias_shift of x.  The fused step runs online [s ; s'] and target [s'] as one 3B pass; the
+   * third range re-reads the packed s' frames instead of keeping a copy.  0 / 0: off. */
+  int32_t x_alias_from, x_alias_shift;
 } vdqn_conv_desc;
 int vdqn_conv_gemm(const vdqn_conv_desc* d, void* stream);
 
@@ -130,6 +134,17 @@ typedef struct vdqn_wgrad_fin_desc {
   float eps;
 } vdqn_wgrad_fin_desc;
 int vdqn_wgrad_finalize(const vdqn_wgrad_fin_desc* d, void* stream);
+
+/* Many reductions in one launch.  `items` is a DEVICE array of n entries; build each entry on the host
+ * with vdqn_wgrad_finalize_plan (returns the number of thread blocks the tensor needs, 0 if it has to
+ * go through vdqn_wgrad_finalize instead -- the packed stem), set first_block to the running sum of
+ * those counts, copy the array to the device once and reuse it (pointers are static across steps). */
+typedef struct vdqn_wgrad_fin_item {
+  vdqn_wgrad_fin_desc d;
+  int32_t cn, items, TX, TY, nchunks, first_block;
+} vdqn_wgrad_fin_item;
+int vdqn_wgrad_finalize_plan(const vdqn_wgrad_fin_desc* d, vdqn_wgrad_fin_item* out);
+int vdqn_wgrad_finalize_multi(const vdqn_wgrad_fin_item* items_dev, int32_t n, int32_t total_blocks, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * fp32 master weights -> bf16 GEMM operands with BN folded in.

@@ -23,7 +23,8 @@ class ConvDesc(C.Structure):
                                      "pad_lo", "pad_hi", "ldc", "ldr", "ldm", "out2_ld",
                                      "out_scatter", "flags", "tile_n", "max_ctas", "algo", "pad_hi_w",
                                      "scatter_off_h", "scatter_off_w")] + \
-               [("w2", c_void_p), ("shift2", c_void_p), ("split_n", c_int)]
+               [("w2", c_void_p), ("shift2", c_void_p), ("split_n", c_int), ("x_alias_from", c_int),
+                ("x_alias_shift", c_int)]
 
 
 class WgradDesc(C.Structure):
@@ -35,6 +36,10 @@ class WgradDesc(C.Structure):
 class WgradFinDesc(C.Structure):
     _fields_ = [(n, c_void_p) for n in ("part", "w", "gamma", "var", "mean", "dbeta", "dw", "dgamma")] + \
                [(n, c_int) for n in ("splits", "Cout", "Cin", "R", "S", "K", "kmap")] + [("eps", c_float)]
+
+
+class WgradFinItem(C.Structure):
+    _fields_ = [("d", WgradFinDesc)] + [(n, c_int) for n in ("cn", "items", "TX", "TY", "nchunks", "first_block")]
 
 
 class WprepDesc(C.Structure):
@@ -61,6 +66,8 @@ EXPORTS = {
     "vdqn_conv_gemm": (c_int, [C.POINTER(ConvDesc), c_void_p]),
     "vdqn_conv_wgrad": (c_int, [C.POINTER(WgradDesc), c_void_p]),
     "vdqn_wgrad_finalize": (c_int, [C.POINTER(WgradFinDesc), c_void_p]),
+    "vdqn_wgrad_finalize_plan": (c_int, [C.POINTER(WgradFinDesc), C.POINTER(WgradFinItem)]),
+    "vdqn_wgrad_finalize_multi": (c_int, [c_void_p, c_int, c_int, c_void_p]),
     "vdqn_weight_prep": (c_int, [C.POINTER(WprepDesc), c_void_p]),
     "vdqn_weight_prep_multi": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_void_p]),
     "vdqn_weight_prep_tiled": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p]),

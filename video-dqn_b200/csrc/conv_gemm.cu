@@ -22,6 +22,7 @@
 #include "epilogue.cuh"
 #include "ptx.cuh"
 #include "vdqn_internal.h"
+#include "role_profile.cuh"
 
 namespace vdqn {
 
@@ -151,7 +152,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     // ------------------------------------------------------------ TMA producer
     int stage = 0;
     uint32_t phase = 0;
+    PROF_BEGIN
     for (int t = tile0; t < num_tiles; t += tstep) {
+      PROF_TILE
       const int n_t = t % a.num_n_tiles, m_t = (t / a.num_n_tiles) * MT + rank;
       const int m0 = m_t * Cfg::BM;
       const int img = m0 / HoWo;
@@ -162,7 +165,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       // an integer division per k-block would sit on its critical path
       int c0 = 0, off_w = 0, off_h = 0, s_i = 0, jk = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(empty_bar(stage), phase ^ 1);
+        PROF_WAIT_A(mbar_wait(empty_bar(stage), phase ^ 1))
         const bool leader = elect_one();
         // PAIR: the leader CTA's barrier collects the bytes of both CTAs' loads
         if (leader && rank == 0) mbar_expect_tx(full_bar(stage), MT * Cfg::STAGE_BYTES);
@@ -194,6 +197,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
       }
     }
+    PROF_END(0)
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (PAIR: leader CTA only)
     constexpr uint32_t idesc = make_idesc_bf16(PAIR ? 256 : 128, BN, 0, 0);
@@ -201,14 +205,16 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
+    PROF_BEGIN
     for (int t = tile0; t < num_tiles; t += tstep, ++it) {
+      PROF_TILE
       const int acc = it % Cfg::NACC;
       const uint32_t acc_phase = (it / Cfg::NACC) & 1;
-      mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+      PROF_WAIT_A(mbar_wait(tempty_bar(acc), acc_phase ^ 1))
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BN;
       for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(full_bar(stage), phase);
+        PROF_WAIT_B(mbar_wait(full_bar(stage), phase))
         tc_fence_after();
         if (elect_one()) {
           const uint32_t sA = smem_base + stage * Cfg::STAGE_BYTES;
@@ -237,6 +243,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
       }
     }
+    PROF_END(4)
   } else {
     // ------------------------------------------------------------ epilogue (warps 2..9)
     const int ew = warp - 2;                   // 0..7
@@ -329,7 +336,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     };
     if (fast && has_in && tile0 < num_tiles) issue_inputs(tile0);
     int it = 0;
+    PROF_BEGIN
     for (int t = tile0; t < num_tiles; t += tstep, ++it) {
+      PROF_TILE
       int n_t, m_t;
       tile_mn(t, n_t, m_t);
       if (n_t != cs_nt) { flush_colsum(); cs_nt = n_t; }
@@ -339,11 +348,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const bool valid = m < a.M_total;
       if (fast) {
         const int row0 = m_t * Cfg::BM + quad * 32;            // this warp's 32 output rows
-        mbar_wait(tfull_bar(acc), acc_phase);
+        PROF_WAIT_A(mbar_wait(tfull_bar(acc), acc_phase))
         tc_fence_after();
         const uint32_t stg = stg_out_base + (uint32_t)((it % Cfg::OUT_BUFS) * NCH) * 2048u;
-        if (elect_one()) tma_store_wait_read<Cfg::OUT_BUFS - 1>();   // this out buffer's last store has been read
-        __syncwarp();
+        PROF_WAIT_B(if (elect_one()) tma_store_wait_read<Cfg::OUT_BUFS - 1>(); __syncwarp())   // this out buffer's last store has been read
 #pragma unroll 1
         for (int ci = 0; ci < NCH; ++ci) {
           const int chunk = half + 2 * ci;
@@ -351,8 +359,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           tmem_ld_32x32(tmem_base + acc * BN + chunk * 32 + ((uint32_t)(quad * 32) << 16), raw);
           tmem_ld_wait();
           if (ci == 0 && has_in) {
-            if (gather) { cp_async_wait_all(); __syncwarp(); }
-            else mbar_wait(ld_bar, ld_parity);
+            if (gather) { PROF_WAIT_B(cp_async_wait_all(); __syncwarp()) }
+            else { PROF_WAIT_B(mbar_wait(ld_bar, ld_parity)) }
           }
           const float cs = epilogue_half_staged<64, EPI>(epi, raw, valid, n_t * BN + chunk * 32, 0, lane, stg + ci * 2048,
                                                     stg_in + ci * 2048, stg_in + (NCH + ci) * 2048);
@@ -425,6 +433,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       __syncwarp();
       if (lane == 0) release_acc(acc);
     }
+    PROF_END(5 + ew)
     flush_colsum();
     };
     if constexpr (Cfg::FAST_EPI) epi_dispatch(fast ? epi_mode(epi) : EPI_HAS_ALL, epi_loop);
@@ -515,6 +524,8 @@ extern "C" int vdqn_conv_gemm(const vdqn_conv_desc* d, void* stream_v) {
   if (d->algo == 2 && !halo_conv_supported(d))
     return set_error(VDQN_ERR_SHAPE, "conv_gemm: halo algorithm requested for an unsupported shape");
   if (d->algo != 1 && d->tile_n == 0 && halo_conv_supported(d)) return halo_conv_launch(d, stream);
+  if (d->x_alias_from > 0)
+    return set_error(VDQN_ERR_ARG, "conv_gemm: input aliasing needs the packed-stem halo kernel");
 
   CUtensorMap tmA, tmB;
   int rc = make_im2col_map(&tmA, d->x, d->N, d->H, d->W, d->Cin, CK, 128, d->stride,
@@ -581,3 +592,5 @@ extern "C" int vdqn_conv_gemm(const vdqn_conv_desc* d, void* stream_v) {
     default: return launch_igemm<256, 64>(tmA, tmB, tmB2, epi_maps, a, sms, stream);
   }
 }
+
+VDQN_DEFINE_ROLE_PROFILE_READER(vdqn_debug_role_profile_igemm)

@@ -239,13 +239,9 @@ struct FinRowCfg {
   int cn, items, TX, TY;
 };
 
-__global__ void __launch_bounds__(256)
-wgrad_finalize_rows_kernel(const vdqn_wgrad_fin_desc d, const FinRowCfg c) {
-  pdl_launch_dependents();
-  pdl_wait();
-  __shared__ float red[4608 + 160];
-  __shared__ float wsum[8];
-  const int co = blockIdx.y, ci0 = blockIdx.x * c.cn;
+__device__ __forceinline__ void finalize_rows_body(const vdqn_wgrad_fin_desc& d, const FinRowCfg& c, int chunk,
+                                                   int co, float* red, float* wsum) {
+  const int ci0 = chunk * c.cn;
   const int RS = d.R * d.S;
   const int E = c.cn * RS;
   const int pitch = c.cn + 1;                    // per-tap pitch in shared memory (bank spread)
@@ -305,10 +301,41 @@ wgrad_finalize_rows_kernel(const vdqn_wgrad_fin_desc d, const FinRowCfg c) {
       float v = 0.f;
       for (int w = 0; w < 8; ++w) v += wsum[w];
       v *= rstd;
-      if (blockIdx.x == 0 && d.dbeta != nullptr) v -= rstd * d.mean[co] * d.dbeta[co];
+      if (chunk == 0 && d.dbeta != nullptr) v -= rstd * d.mean[co] * d.dbeta[co];
       atomicAdd(d.dgamma + co, v);
     }
   }
+}
+
+__global__ void __launch_bounds__(256, 5)
+wgrad_finalize_rows_kernel(const vdqn_wgrad_fin_desc d, const FinRowCfg c) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float red[4608 + 160];
+  __shared__ float wsum[8];
+  finalize_rows_body(d, c, blockIdx.x, blockIdx.y, red, wsum);
+}
+
+// Every split reduction of a backward pass (or of one data-parallel stage) in ONE launch: block ->
+// (tensor, output channel, input-channel chunk) through a table of per-tensor descriptors that lives
+// on the device.  Removes ~20 launch + tail gaps per step and lets the partials of all layers be
+// reduced at full HBM rate.
+__global__ void __launch_bounds__(256, 5)
+wgrad_finalize_multi_kernel(const vdqn_wgrad_fin_item* __restrict__ items, int n) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float red[4608 + 160];
+  __shared__ float wsum[8];
+  int lo = 0, hi = n - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (items[mid].first_block <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const vdqn_wgrad_fin_item it = items[lo];
+  const int b = (int)blockIdx.x - it.first_block;
+  FinRowCfg c;
+  c.cn = it.cn; c.items = it.items; c.TX = it.TX; c.TY = it.TY;
+  finalize_rows_body(it.d, c, b % it.nchunks, b / it.nchunks, red, wsum);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -883,30 +910,56 @@ extern "C" int vdqn_weight_prep_tiled(const vdqn_wprep_desc* descs_dev, const in
   return VDQN_OK;
 }
 
+// Row-form applicability + launch shape of one reduction (host helper of the two entry points
+// below; also exported so a caller can build the table of vdqn_wgrad_finalize_multi).
+extern "C" int vdqn_wgrad_finalize_plan(const vdqn_wgrad_fin_desc* d, vdqn_wgrad_fin_item* out) {
+  if (d == nullptr || out == nullptr) return 0;
+  DeviceInfo* dev = device_info();
+  const int num_sms = dev != nullptr ? dev->num_sms : 148;
+  const int RS = d->R * d->S;
+  if (!(d->kmap == 0 && d->K == RS * d->Cin && d->Cin % 16 == 0 && d->K <= 4608 &&
+        (reinterpret_cast<uintptr_t>(d->part) & 15) == 0))
+    return 0;
+  // input-channel chunks: enough blocks to cover the SMs while a chunk stays >= 16 channels
+  int nchunks = 1;
+  while (d->Cout * nchunks < 2 * num_sms && d->Cin / (2 * nchunks) >= 16 && d->Cin % (2 * nchunks) == 0)
+    nchunks *= 2;
+  out->d = *d;
+  out->cn = d->Cin / nchunks;
+  out->items = RS * (out->cn / 4);
+  out->TX = out->items < 256 ? out->items : 256;
+  out->TY = 256 / out->TX;
+  if (out->TY > d->splits) out->TY = d->splits;
+  out->nchunks = nchunks;
+  out->first_block = 0;
+  // shared memory: TY lanes x RS x (cn + 1) floats
+  if ((long)out->TY * RS * (out->cn + 1) > 4608 + 160) return 0;
+  return nchunks * d->Cout;
+}
+
+extern "C" int vdqn_wgrad_finalize_multi(const vdqn_wgrad_fin_item* items_dev, int32_t n, int32_t total_blocks,
+                                         void* stream_v) {
+  if (items_dev == nullptr || n < 1 || total_blocks < 1)
+    return set_error(VDQN_ERR_ARG, "wgrad_finalize_multi: empty table");
+  GET_DEV();
+  (void)dev;
+  launch_kernel(wgrad_finalize_multi_kernel, total_blocks, 256, 0, stream, items_dev, n);
+  VDQN_CHECK_LAUNCH("wgrad_finalize_multi");
+  return VDQN_OK;
+}
+
 extern "C" int vdqn_wgrad_finalize(const vdqn_wgrad_fin_desc* d, void* stream_v) {
   if (d == nullptr || d->part == nullptr || d->w == nullptr || d->dw == nullptr)
     return set_error(VDQN_ERR_ARG, "wgrad_finalize: null pointer");
   GET_DEV();
   (void)dev;
-  const int RS = d->R * d->S;
-  if (d->kmap == 0 && d->K == RS * d->Cin && d->Cin % 16 == 0 && d->K <= 4608 &&
-      (reinterpret_cast<uintptr_t>(d->part) & 15) == 0) {
-    // input-channel chunks: enough blocks to cover the SMs while a chunk stays >= 16 channels
-    int nchunks = 1;
-    while (d->Cout * nchunks < 2 * dev->num_sms && d->Cin / (2 * nchunks) >= 16 && d->Cin % (2 * nchunks) == 0)
-      nchunks *= 2;
+  vdqn_wgrad_fin_item item;
+  if (vdqn_wgrad_finalize_plan(d, &item) > 0) {
     FinRowCfg c;
-    c.cn = d->Cin / nchunks;
-    c.items = RS * (c.cn / 4);
-    c.TX = c.items < 256 ? c.items : 256;
-    c.TY = 256 / c.TX;
-    if (c.TY > d->splits) c.TY = d->splits;
-    // shared memory: TY lanes x RS x (cn + 1) floats
-    if ((long)c.TY * RS * (c.cn + 1) <= 4608 + 160) {
-      launch_kernel(wgrad_finalize_rows_kernel, dim3(nchunks, d->Cout), 256, 0, stream, *d, c);
-      VDQN_CHECK_LAUNCH("wgrad_finalize_rows");
-      return VDQN_OK;
-    }
+    c.cn = item.cn; c.items = item.items; c.TX = item.TX; c.TY = item.TY;
+    launch_kernel(wgrad_finalize_rows_kernel, dim3(item.nchunks, d->Cout), 256, 0, stream, *d, c);
+    VDQN_CHECK_LAUNCH("wgrad_finalize_rows");
+    return VDQN_OK;
   }
   launch_kernel(wgrad_finalize_kernel, dim3((d->K + 63) / 64, d->Cout), dim3(64, 4), 0, stream, *d);
   VDQN_CHECK_LAUNCH("wgrad_finalize");

@@ -15,30 +15,9 @@
 #include "epilogue.cuh"
 #include "ptx.cuh"
 #include "vdqn_internal.h"
+#include "role_profile.cuh"
 
 namespace vdqn {
-
-// Instrumented build (-DVDQN_ROLE_PROFILE, tools/role_profile.py): every role records the cycles it
-// spent blocked on its two kinds of waits and its total loop time, per CTA -- the role that never
-// waits is the bottleneck.  Compiles to nothing otherwise.
-#ifdef VDQN_ROLE_PROFILE
-__device__ unsigned long long g_role_prof[160 * 16 * 4];
-#define PROF_BEGIN long long prof_wa = 0, prof_wb = 0, prof_n = 0; const long long prof_t0 = clock64();
-#define PROF_WAIT_A(x) { const long long w0_ = clock64(); x; prof_wa += clock64() - w0_; }
-#define PROF_WAIT_B(x) { const long long w0_ = clock64(); x; prof_wb += clock64() - w0_; }
-#define PROF_TILE ++prof_n;
-#define PROF_END(role)                                                                   \
-  if (lane == 0) {                                                                       \
-    unsigned long long* p_ = g_role_prof + ((size_t)blockIdx.x * 16 + (role)) * 4;       \
-    p_[0] = prof_wa; p_[1] = prof_wb; p_[2] = clock64() - prof_t0; p_[3] = prof_n;       \
-  }
-#else
-#define PROF_BEGIN
-#define PROF_WAIT_A(x) x;
-#define PROF_WAIT_B(x) x;
-#define PROF_TILE
-#define PROF_END(role)
-#endif
 
 struct HaloArgs {
   int N, H, W, Cout;
@@ -50,6 +29,7 @@ struct HaloArgs {
   // CTAs [0, split_cta) work on the first range, the rest on the second (split_cta == 0: off)
   int split_tile, split_cta;
   const float* shift2;
+  int alias_from, alias_shift;     // images >= alias_from are read from image n - alias_shift (stem only)
   EpiArgs epi;
 };
 
@@ -247,7 +227,8 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         const int stage = k % Cfg::STAGES;
         PROF_WAIT_A(mbar_wait(empty_bar(stage), (((uint32_t)(k / Cfg::STAGES)) & 1u) ^ 1u))
         const uint32_t base = sA0 + stage * Cfg::STAGE_BYTES;
-        const __nv_bfloat16* img = a.x + (long)n * a.H * a.W * 16;
+        const int n_src = (a.alias_from > 0 && n >= a.alias_from) ? n - a.alias_shift : n;
+        const __nv_bfloat16* img = a.x + (long)n_src * a.H * a.W * 16;
 #pragma unroll
         for (int i = 0; i < PER_LANE; ++i) {
           if (hywx[i] == 0xffffffffu) continue;
@@ -518,6 +499,9 @@ static int launch_halo(const vdqn_conv_desc* d, cudaStream_t stream) {
   a.tiles_h = (d->H + Cfg::TH - 1) / Cfg::TH;
   a.num_tiles = d->N * a.tiles_w * a.tiles_h;
   a.epi = make_epi_args(d);
+  a.alias_from = d->x_alias_from; a.alias_shift = d->x_alias_shift;
+  if (a.alias_from > 0 && (CK != 16 || a.alias_shift <= 0 || a.alias_shift > a.alias_from))
+    return set_error(VDQN_ERR_ARG, "halo_conv: input aliasing is for the packed stem only (0 < shift <= first)");
   const int sms = d->max_ctas > 0 && d->max_ctas < dev->num_sms ? d->max_ctas : dev->num_sms;
   // schedule units: CTAs over tiles, or (PAIR) CTA pairs over pairs of tiles
   constexpr int MT = PAIR ? 2 : 1;
@@ -574,13 +558,4 @@ int halo_conv_launch(const vdqn_conv_desc* d, cudaStream_t stream) {
 
 }  // namespace vdqn
 
-// instrumented builds only (not part of include/vdqn.h): copies the per-CTA role counters
-extern "C" int vdqn_debug_role_profile(unsigned long long* out, int count) {
-#ifdef VDQN_ROLE_PROFILE
-  cudaError_t e = cudaMemcpyFromSymbol(out, vdqn::g_role_prof, sizeof(unsigned long long) * count);
-  return e == cudaSuccess ? 0 : -1;
-#else
-  (void)out; (void)count;
-  return -2;
-#endif
-}
+VDQN_DEFINE_ROLE_PROFILE_READER(vdqn_debug_role_profile)

@@ -244,7 +244,8 @@ class Workspace:
         z = lambda *s, dt=bf16: torch.zeros(*s, device=device, dtype=dt)  # noqa: E731
         self.xp = e(nf, 112, 112, 16)
         self.s = e(nf, 112, 112, 64)
-        self.idx = e(nf, 56, 56, 64, dt=torch.uint8) if train else None
+        # arg-max slots of the max-pool: only the frames that are back-propagated through need them
+        self.idx = e(self.n_bwd, 56, 56, 64, dt=torch.uint8) if train else None
         self.p = e(nf, 56, 56, 64)
         self.a1, self.idn, self.out = [], [], []
         for b in plan.blocks:
@@ -279,6 +280,13 @@ class Workspace:
             max_part = max(wgrad_splits(c, n) * c.cout * c.K for c in prep_convs(plan))
             self.dz1_bf16 = e(B, 512) if plan.top0 is not None else None
             self.part = e(max_part, dt=f32)
+            # deferred split reductions (set `defer_fin` to use): every weight gradient keeps its own
+            # partial buffer and ONE multi-tensor launch reduces them all at the end of the backward pass
+            # (or of each data-parallel stage)
+            self.defer_fin = False
+            self._part_of: Dict[str, torch.Tensor] = {}
+            self._pending: List[tuple] = []
+            self._fin_tables: Dict[tuple, tuple] = {}
 
     def bwd_view(self):
         """The workspace as the backward pass sees it: activations sliced to the first n_bwd frames."""
@@ -305,6 +313,8 @@ import os as _os
 
 # column-tile width for the Cout >= 256 layers (0 = kernel default 256); tuning knob
 TILE_N_WIDE = int(_os.environ.get("VDQN_TILE_N_WIDE", "0"))
+# fused step: one multi-tensor launch for all split reductions of the backward pass (0: one per layer)
+DEFER_FINALIZE = _os.environ.get("VDQN_DEFER_FINALIZE", "1") != "0"
 # column-tile width of the layer4 data gradients (196 tiles of 128x256 on 148 SMs = two uneven waves
 # at B = 256; 128 gives 392 smaller tiles)
 TILE_N_DGRAD4 = int(_os.environ.get("VDQN_TILE_N_DGRAD4", "0"))
@@ -338,14 +348,20 @@ def forward(plan: NetPlan, W: PreparedWeights, P: Dict[str, torch.Tensor], ws: W
 
 def forward_packed(plan: NetPlan, W: PreparedWeights, P: Dict[str, torch.Tensor], ws: Workspace,
                    W2: Optional[PreparedWeights] = None, P2: Optional[Dict[str, torch.Tensor]] = None,
-                   split: int = 0, trunk_only: bool = False) -> torch.Tensor:
+                   split: int = 0, trunk_only: bool = False, x_alias=None) -> torch.Tensor:
     """Forward from the packed input ws.xp.  With (W2, P2, split) the frames [split, n) go through a
     SECOND network (the target net) inside the same launches: every conv kernel partitions its CTAs
     between the two image ranges, so online and target forwards share one pass (better SM filling
     for the small late layers, a third fewer launches)."""
     dual = dict(W2=W2, split=split) if W2 is not None else {}
-    _conv(W, plan.stem, ws.xp, ws.s, relu=True, **dual)
-    ops.maxpool_fwd(ws.s, ws.p, ws.idx)
+    # x_alias = (first, shift): packed frames >= first are read from frame - shift (the target range of
+    # the 3B pass re-reads the online network's s' frames)
+    _conv(W, plan.stem, ws.xp, ws.s, relu=True, x_alias=x_alias, **dual)
+    nb = ws.n_bwd if ws.idx is not None else 0
+    if nb:
+        ops.maxpool_fwd(ws.s[:nb], ws.p[:nb], ws.idx)
+    if nb < ws.n:
+        ops.maxpool_fwd(ws.s[nb:], ws.p[nb:], None)
     x = ws.p
     for i, b in enumerate(plan.blocks):
         _conv(W, b.conv1, x, ws.a1[i], relu=True, **dual)
@@ -386,15 +402,38 @@ def forward_packed(plan: NetPlan, W: PreparedWeights, P: Dict[str, torch.Tensor]
 
 def _wgrad(plan, P, G, ws: Workspace, c: ConvSpec, x, dy, dbeta_key: Optional[str]):
     splits = wgrad_splits(c, ws.n)
-    part = ws.part[: splits * c.cout * c.K]
+    defer = ws.defer_fin and c.kmap == 0
+    if defer:
+        part = ws._part_of.get(c.name)
+        if part is None:
+            part = ws._part_of[c.name] = torch.empty(splits * c.cout * c.K, device=ws.part.device,
+                                                     dtype=torch.float32)
+    else:
+        part = ws.part[: splits * c.cout * c.K]
     ops.conv_wgrad(x, dy, c.k, c.k, c.stride, c.pad_lo, c.pad_hi, splits=splits, part=part,
                    algo=2 if wgrad_uses_halo(c) else 0)
     kw = {}
     if c.bn is not None:
         kw = dict(gamma=P[c.bn + ".weight"], var=P[c.bn + ".running_var"], mean=P[c.bn + ".running_mean"],
                   dbeta=G[c.bn + ".bias"], dgamma=G[c.bn + ".weight"])
-    ops.wgrad_finalize(part, P[c.wkey], G[c.wkey], splits=splits, Cout=c.cout, Cin=c.gemm_cin, R=c.k,
-                       S=c.k, K=c.K, kmap=c.kmap, eps=BN_EPS, **kw)
+    args = dict(splits=splits, Cout=c.cout, Cin=c.gemm_cin, R=c.k, S=c.k, K=c.K, kmap=c.kmap, eps=BN_EPS, **kw)
+    if defer:
+        ws._pending.append((c.name, part, P[c.wkey], G[c.wkey], args))
+    else:
+        ops.wgrad_finalize(part, P[c.wkey], G[c.wkey], **args)
+
+
+def _flush_finalize(ws: Workspace):
+    """reduce the split partials of every weight gradient enqueued since the last flush: one launch"""
+    if not ws._pending:
+        return
+    key = tuple((nm, w.data_ptr(), dw.data_ptr()) for nm, _, w, dw, _ in ws._pending)
+    tab = ws._fin_tables.get(key)
+    if tab is None:
+        descs = [ops.wgrad_finalize_desc(part, w, dw, **args) for _, part, w, dw, args in ws._pending]
+        tab = ws._fin_tables[key] = ops.wgrad_finalize_table(descs, ws.part.device)
+    ops.wgrad_finalize_multi(tab)
+    ws._pending.clear()
 
 
 def backward(plan: NetPlan, W: PreparedWeights, P: Dict[str, torch.Tensor], G: Dict[str, torch.Tensor],
@@ -403,8 +442,13 @@ def backward(plan: NetPlan, W: PreparedWeights, P: Dict[str, torch.Tensor], G: D
     (views of the flat gradient arena; BN-bias slots must be zero on entry: they are accumulated
     with atomics).  `on_grads_ready(stage)` is called after each stage's gradients are enqueued
     (used by the data-parallel wrapper to launch bucketed all-reduces)."""
-    notify = on_grads_ready or (lambda stage: None)
     ws = ws.bwd_view()
+    if on_grads_ready is None:
+        notify = lambda stage: None  # noqa: E731
+    else:
+        def notify(stage):
+            _flush_finalize(ws)          # the stage's gradients are complete only once its reductions ran
+            on_grads_ready(stage)
     # ---- MLP (fp32)
     ops.linear_bwd(ws.z2, P["top.4.weight"], None, dq, G["top.4.weight"], G["top.4.bias"], False, dx=ws.dz2)
     ops.linear_bwd(ws.z1, P["top.2.weight"], ws.z2, ws.dz2, G["top.2.weight"], G["top.2.bias"], True, dx=ws.dz1)
@@ -477,4 +521,5 @@ def backward(plan: NetPlan, W: PreparedWeights, P: Dict[str, torch.Tensor], G: D
     # ---- max-pool + stem
     ops.maxpool_bwd(ws.dy_p, ws.idx, ws.p, ws.dy_s, colsum=G[plan.stem.bn + ".bias"])
     _wgrad(plan, P, G, ws, plan.stem, ws.xp, ws.dy_s, None)
+    _flush_finalize(ws)
     notify("stem")

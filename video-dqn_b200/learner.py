@@ -119,6 +119,7 @@ class QLearner:
         else:
             self.ws_train = E.Workspace(self.plan, (3 if self.one_pass else 2) * n, dev, train=True, n_bwd=n)
             self.ws_eval = None if self.one_pass else E.Workspace(self.plan, n, dev, train=False)
+        self.ws_train.defer_fin = E.DEFER_FINALIZE
         A = self.plan.action_dim
         self.dq = torch.empty(batch_size, C * A, device=dev, dtype=torch.float32)
         self.loss = torch.zeros(1, device=dev, dtype=torch.float32)
@@ -151,8 +152,8 @@ class QLearner:
         elif self.one_pass:
             n = B * plan.num_frames
             ops.stem_pack(self._frames(self.frames2), wt.xp[:2 * n])
-            wt.xp[2 * n:].copy_(wt.xp[n:2 * n])            # the target net sees s' too
-            E.forward_packed(plan, st.W, st.P, wt, W2=tt.W, P2=tt.P, split=2 * n)
+            # the target net sees s' too: its range [2n, 3n) of the stem re-reads frames [n, 2n)
+            E.forward_packed(plan, st.W, st.P, wt, W2=tt.W, P2=tt.P, split=2 * n, x_alias=(2 * n, n))
             q_nt = wt.q[2 * B:3 * B]
         else:
             E.forward(plan, st.W, st.P, wt, self._frames(self.frames2))

@@ -68,9 +68,10 @@ def conv_out_hw(H, W, R, S, stride, pad_lo, pad_hi, dil=1):
 def conv_gemm(x, w, stride=1, pad_lo=0, pad_hi=None, *, shift=None, residual=None, mask_src=None,
               relu=False, out_f32=False, colsum=None, out=None, out2=None, out_scatter=1,
               tile_n=0, max_ctas=0, dil=1, algo=0, pad_hi_w=-1, scatter_off=(0, 0), scatter_inputs=False,
-              w2=None, shift2=None, split_n=0):
+              w2=None, shift2=None, split_n=0, x_alias=None):
     """x [N,H,W,Cin] bf16, w [Cout,R,S,Cin] bf16 -> out [N,Ho,Wo,Cout] (or zero-dilated
-    [N,2Ho,2Wo,Cout] when out_scatter == 2; `out` must then be pre-zeroed)."""
+    [N,2Ho,2Wo,Cout] when out_scatter == 2; `out` must then be pre-zeroed).
+    x_alias = (first, shift): images n >= first are read from image n - shift (packed stem only)."""
     lib = L.load()
     _cuda(x, bf16, "x"); _cuda(w, bf16, "w")
     _req(x.dim() == 4 and w.dim() == 4 and x.shape[3] == w.shape[3], "bad shape")
@@ -113,6 +114,8 @@ def conv_gemm(x, w, stride=1, pad_lo=0, pad_hi=None, *, shift=None, residual=Non
         _cuda(w2, bf16, "w2"); _req(w2.shape == w.shape and shift2 is not None, "bad shape")
         d.w2, d.shift2, d.split_n = w2.data_ptr(), shift2.data_ptr(), split_n
     d.tile_n, d.max_ctas, d.algo = tile_n, max_ctas, algo
+    if x_alias is not None:
+        d.x_alias_from, d.x_alias_shift = x_alias
     with _Prof("igemm", (N, H, W_, Cin, Cout, R, stride)):
         L.check(lib.vdqn_conv_gemm(C.byref(d), L.stream_ptr()), "conv_gemm")
     return out
@@ -142,15 +145,44 @@ def conv_wgrad(x, dy, R, S, stride=1, pad_lo=0, pad_hi=None, *, splits=1, part=N
     return part
 
 
-def wgrad_finalize(part, w, dw, *, splits, Cout, Cin, R, S, K, kmap=0, gamma=None, var=None,
-                   mean=None, dbeta=None, dgamma=None, eps=1e-5):
-    lib = L.load()
+def wgrad_finalize_desc(part, w, dw, *, splits, Cout, Cin, R, S, K, kmap=0, gamma=None, var=None,
+                        mean=None, dbeta=None, dgamma=None, eps=1e-5):
     d = L.WgradFinDesc()
     d.part, d.w, d.dw = part.data_ptr(), w.data_ptr(), dw.data_ptr()
     d.gamma, d.var, d.mean = L.ptr(gamma), L.ptr(var), L.ptr(mean)
     d.dbeta, d.dgamma = L.ptr(dbeta), L.ptr(dgamma)
     d.splits, d.Cout, d.Cin, d.R, d.S, d.K, d.kmap = splits, Cout, Cin, R, S, K, kmap
     d.eps = eps
+    return d
+
+
+def wgrad_finalize_table(descs, device):
+    """Device table for wgrad_finalize_multi from a list of WgradFinDesc (all must be row-form
+    capable).  Returns (table uint8 tensor, n, total_blocks)."""
+    lib = L.load()
+    items = (L.WgradFinItem * len(descs))()
+    total = 0
+    for it, d in zip(items, descs):
+        nb = lib.vdqn_wgrad_finalize_plan(C.byref(d), C.byref(it))
+        _req(nb > 0, "wgrad_finalize_multi: tensor not reducible by the row-form kernel")
+        it.first_block = total
+        total += nb
+    tab = torch.frombuffer(bytearray(bytes(items)), dtype=torch.uint8).clone().to(device)
+    return tab, len(descs), total
+
+
+def wgrad_finalize_multi(table):
+    lib = L.load()
+    tab, n, total = table
+    with _Prof("wgrad_finalize", (n, total)):
+        L.check(lib.vdqn_wgrad_finalize_multi(tab.data_ptr(), n, total, L.stream_ptr()), "wgrad_finalize_multi")
+
+
+def wgrad_finalize(part, w, dw, *, splits, Cout, Cin, R, S, K, kmap=0, gamma=None, var=None,
+                   mean=None, dbeta=None, dgamma=None, eps=1e-5):
+    lib = L.load()
+    d = wgrad_finalize_desc(part, w, dw, splits=splits, Cout=Cout, Cin=Cin, R=R, S=S, K=K, kmap=kmap,
+                            gamma=gamma, var=var, mean=mean, dbeta=dbeta, dgamma=dgamma, eps=eps)
     with _Prof("wgrad_finalize", (Cout, K, splits)):
         L.check(lib.vdqn_wgrad_finalize(C.byref(d), L.stream_ptr()), "wgrad_finalize")
     return dw
