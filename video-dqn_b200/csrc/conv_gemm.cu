@@ -269,11 +269,25 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     float csum[NCH];                     // per-lane column sums of this warp's chunks of the current column tile
 #pragma unroll
     for (int i = 0; i < NCH; ++i) csum[i] = 0.f;
+    // staged path: each thread keeps running sums of its own row (32 per chunk) and the warp
+    // transpose-reduce runs once per column tile instead of once per chunk per tile
+    constexpr bool ROWACC = Cfg::FAST_EPI && (EPI & EPI_HAS_COLSUM) != 0;
+    float row_acc[ROWACC ? NCH * 32 : 1];
+#pragma unroll
+    for (int i = 0; i < (ROWACC ? NCH * 32 : 1); ++i) row_acc[i] = 0.f;
     int cs_nt = -1;
     auto flush_colsum = [&]() {
       if (a.epi.colsum != nullptr && cs_nt >= 0) {
 #pragma unroll
         for (int i = 0; i < NCH; ++i) {
+          if constexpr (ROWACC) {
+            if (fast) {
+              float v[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) { v[j] = row_acc[i * 32 + j]; row_acc[i * 32 + j] = 0.f; }
+              csum[i] += warp_transpose_reduce(v, lane);
+            }
+          }
           atomicAdd(a.epi.colsum + cs_nt * BN + (half + 2 * i) * 32 + lane, csum[i]);
           csum[i] = 0.f;
         }
@@ -352,7 +366,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         tc_fence_after();
         const uint32_t stg = stg_out_base + (uint32_t)((it % Cfg::OUT_BUFS) * NCH) * 2048u;
         PROF_WAIT_B(if (elect_one()) tma_store_wait_read<Cfg::OUT_BUFS - 1>(); __syncwarp())   // this out buffer's last store has been read
-#pragma unroll 1
+#pragma unroll
         for (int ci = 0; ci < NCH; ++ci) {
           const int chunk = half + 2 * ci;
           uint32_t raw[32];
@@ -362,8 +376,9 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             if (gather) { PROF_WAIT_B(cp_async_wait_all(); __syncwarp()) }
             else { PROF_WAIT_B(mbar_wait(ld_bar, ld_parity)) }
           }
+          float* racc = ROWACC ? row_acc + ci * 32 : nullptr;      // ci is a compile-time constant here
           const float cs = epilogue_half_staged<64, EPI>(epi, raw, valid, n_t * BN + chunk * 32, 0, lane, stg + ci * 2048,
-                                                    stg_in + ci * 2048, stg_in + (NCH + ci) * 2048);
+                                                    stg_in + ci * 2048, stg_in + (NCH + ci) * 2048, racc);
 #pragma unroll
           for (int i = 0; i < NCH; ++i)
             if (i == ci) csum[i] += cs;

@@ -325,9 +325,18 @@ def _scatter_tile_n(ch: int) -> int:
     return 128 if ch >= 256 else 0
 
 
+# column-tile width of the stride-1 data gradients with >= 256 channels (layers 3-4): 128 selects the
+# staged epilogue (TMA-moved mask / residual / output tiles, specialised loops); with 256-wide tiles
+# the direct epilogue (per-lane global loads of the mask, a warp transpose per 32 columns for the column
+# sums) was the longest role -- 23.7 k cycles per tile against 18.4 k of MMA issue (role profile)
+TILE_N_DGRAD = int(_os.environ.get("VDQN_TILE_N_DGRAD", "128"))
+
+
 def _dgrad_tile_n(ch: int) -> int:
     if ch >= 512 and TILE_N_DGRAD4:
         return TILE_N_DGRAD4
+    if ch >= 256 and TILE_N_DGRAD:
+        return TILE_N_DGRAD
     return TILE_N_WIDE if ch >= 256 else 0
 
 
