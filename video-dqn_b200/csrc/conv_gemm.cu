@@ -39,6 +39,7 @@ struct IgemmArgs {
   // [0, split_cta) work on the first range, the rest on the second (split_cta == 0: off)
   int split_m_tile, split_cta;
   const float* shift2;
+  int stages;         // pipeline depth of this launch (IgemmCfg::stages_for)
 };
 
 // PAIR: the CTA is one half of a cta_group::2 pair -- the pair computes a 256 x BN tile, this CTA
@@ -60,17 +61,28 @@ struct IgemmCfg {
   // eight epilogue warps; a warp's staging tiles are [32 pixels][32 channels] (64-byte rows, 64B
   // swizzle), one set (residual, mask, OUT_BUFS x out) per 32-column chunk it owns (GROUPS of them)
   static constexpr int EPI_WARPS = 8;
-  static constexpr int EPI_WARP_BYTES = FAST_EPI ? (GROUPS * (2 + OUT_BUFS)) * 2048 : 0;
-  static constexpr int EPI_BYTES = EPI_WARPS * EPI_WARP_BYTES;
   static constexpr int THREADS = (2 + EPI_WARPS) * 32;
-  static constexpr int PIPE_BUDGET = 224 * 1024 - EPI_BYTES;
-  static constexpr int STAGES = PIPE_BUDGET / STAGE_BYTES > 8 ? 8 : PIPE_BUDGET / STAGE_BYTES;
+  // Shared memory is split AT LAUNCH between the pipeline and the epilogue staging: a launch only
+  // reserves the staging tiles it uses (out, + residual, + mask), the rest becomes pipeline stages.
+  // The BN = 128 layers are bound by bytes in flight (5 -> 3 stages costs 27 %): a plain forward conv
+  // gets 8 stages instead of the 5 a worst-case static split would leave.
+  static constexpr int SMEM_LAYOUT = 224 * 1024;
+#ifndef VDQN_MAX_STAGES
+#define VDQN_MAX_STAGES 8          // (experiments: -DVDQN_MAX_STAGES=n caps the pipeline depth)
+#endif
+  static constexpr int MAX_STAGES = VDQN_MAX_STAGES;
+  __host__ __device__ static constexpr int epi_warp_bytes(int n_in) { return FAST_EPI ? GROUPS * (n_in + OUT_BUFS) * 2048 : 0; }
+  __host__ __device__ static constexpr int stages_for(int n_in) {
+    return (SMEM_LAYOUT - EPI_WARPS * epi_warp_bytes(n_in)) / STAGE_BYTES > MAX_STAGES
+               ? MAX_STAGES
+               : (SMEM_LAYOUT - EPI_WARPS * epi_warp_bytes(n_in)) / STAGE_BYTES;
+  }
   // accumulator ring over all 512 TMEM columns (8 / 4 / 2 accumulators for BN = 64 / 128 / 256): the
   // MMA warp may run that many tiles ahead of the epilogue, which hides the mbarrier hand-off
   // latencies that otherwise bound launches with few k-blocks per tile (1x1, parity-class convs)
   static constexpr int NACC = 512 / BN;
   static constexpr int TMEM_COLS = 512;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align*/ + 512 /*barriers*/;
+  static constexpr int SMEM_BYTES = SMEM_LAYOUT + 1024 /*align*/ + 512 /*barriers*/;
   static constexpr uint64_t SWZ = (CK == 64) ? kSwz128 : kSwz32;
   static constexpr int ROW_BYTES = CK * 2;          // bytes per smem row (= swizzle span)
   static constexpr int SBO = 8 * ROW_BYTES;         // 8-row group pitch
@@ -84,14 +96,15 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   using Cfg = IgemmCfg<BN, CK, PAIR>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t epi_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
-  const uint32_t bar_base = epi_base + Cfg::EPI_BYTES;
+  const int nstages = a.stages;                      // pipeline depth of this launch (host: stages_for)
+  const uint32_t epi_base = smem_base + nstages * Cfg::STAGE_BYTES;
+  const uint32_t bar_base = smem_base + Cfg::SMEM_LAYOUT;
   // barriers: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then tmem ptr slot
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
-  auto tfull_bar = [&](int i) { return bar_base + 8u * (2 * Cfg::STAGES + i); };
-  auto tempty_bar = [&](int i) { return bar_base + 8u * (2 * Cfg::STAGES + Cfg::NACC + i); };
-  const uint32_t ld_bar0 = bar_base + 8u * (2 * Cfg::STAGES + 2 * Cfg::NACC);     // one per epilogue warp
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::MAX_STAGES + s); };
+  auto tfull_bar = [&](int i) { return bar_base + 8u * (2 * Cfg::MAX_STAGES + i); };
+  auto tempty_bar = [&](int i) { return bar_base + 8u * (2 * Cfg::MAX_STAGES + Cfg::NACC + i); };
+  const uint32_t ld_bar0 = bar_base + 8u * (2 * Cfg::MAX_STAGES + 2 * Cfg::NACC);     // one per epilogue warp
   const uint32_t tmem_slot = ld_bar0 + 8u * Cfg::EPI_WARPS;
   uint32_t* tmem_slot_ptr =
       reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
@@ -105,7 +118,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    for (int s = 0; s < Cfg::STAGES; ++s) {
+    for (int s = 0; s < Cfg::MAX_STAGES; ++s) {
       mbar_init(full_bar(s), 1);
       mbar_init(empty_bar(s), 1);
     }
@@ -194,7 +207,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           }
         }
         __syncwarp();
-        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        if (++stage == nstages) { stage = 0; phase ^= 1; }
       }
     }
     PROF_END(0)
@@ -240,7 +253,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           }
         }
         __syncwarp();
-        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        if (++stage == nstages) { stage = 0; phase ^= 1; }
       }
     }
     PROF_END(4)
@@ -252,8 +265,12 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const int row = quad * 32 + lane;
     constexpr int NCH = BN / 64;               // chunks per warp
     // per-warp staging: res[NCH] | mask[NCH] | out[OUT_BUFS][NCH], 2 KB tiles
-    const uint32_t stg_in = epi_base + ew * Cfg::EPI_WARP_BYTES;
-    const uint32_t stg_out_base = stg_in + 2 * NCH * 2048;
+    // per-warp staging of this launch: [residual x NCH] [mask x NCH] [out x OUT_BUFS x NCH], absent
+    // inputs take no room
+    const int n_in = (a.epi.residual != nullptr ? 1 : 0) + (a.epi.mask_src != nullptr ? 1 : 0);
+    const uint32_t stg_in = epi_base + ew * (uint32_t)Cfg::epi_warp_bytes(n_in);
+    const uint32_t stg_mask0 = stg_in + (a.epi.residual != nullptr ? NCH * 2048 : 0);
+    const uint32_t stg_out_base = stg_in + n_in * NCH * 2048;
     const uint32_t ld_bar = ld_bar0 + 8u * ew;
     EpiArgs epi = a.epi;
     if (second) epi.shift = a.shift2;
@@ -330,7 +347,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           for (int ci = 0; ci < NCH; ++ci) {
             const int col = nn_t * BN + (half + 2 * ci) * 32 + (lane & 3) * 8;
             if (has_res) cp_async_16(stg_in + ci * 2048 + dst, epi.residual + prc * epi.ldr + col, nb);
-            if (has_mask) cp_async_16(stg_in + (NCH + ci) * 2048 + dst, epi.mask_src + prc * epi.ldm + col, nb);
+            if (has_mask) cp_async_16(stg_mask0 + ci * 2048 + dst, epi.mask_src + prc * epi.ldm + col, nb);
           }
         }
         cp_async_commit();
@@ -343,7 +360,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         for (int ci = 0; ci < NCH; ++ci) {
           const int col = nn_t * BN + (half + 2 * ci) * 32;
           if (has_res) tma_load_2d(stg_in + ci * 2048, &tmRes, ld_bar, col, r0);
-          if (has_mask) tma_load_2d(stg_in + (NCH + ci) * 2048, &tmMask, ld_bar, col, r0);
+          if (has_mask) tma_load_2d(stg_mask0 + ci * 2048, &tmMask, ld_bar, col, r0);
         }
       }
       __syncwarp();
@@ -378,7 +395,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           }
           float* racc = ROWACC ? row_acc + ci * 32 : nullptr;      // ci is a compile-time constant here
           const float cs = epilogue_half_staged<64, EPI>(epi, raw, valid, n_t * BN + chunk * 32, 0, lane, stg + ci * 2048,
-                                                    stg_in + ci * 2048, stg_in + (NCH + ci) * 2048, racc);
+                                                    stg_in + ci * 2048, stg_mask0 + ci * 2048, racc);
 #pragma unroll
           for (int i = 0; i < NCH; ++i)
             if (i == ci) csum[i] += cs;
@@ -485,6 +502,9 @@ static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
                                            cudaGetErrorString(e));
     attr_set = true;
   }
+  a.stages = Cfg::stages_for(a.fast ? (a.epi.residual != nullptr ? 1 : 0) + (a.epi.mask_src != nullptr ? 1 : 0) : 0);
+  if (!a.fast) a.stages = Cfg::SMEM_LAYOUT / Cfg::STAGE_BYTES > Cfg::MAX_STAGES ? Cfg::MAX_STAGES
+                                                                                : Cfg::SMEM_LAYOUT / Cfg::STAGE_BYTES;
   // schedule units: CTAs over tiles, or (PAIR) CTA pairs over pairs of m-tiles
   constexpr int MT = PAIR ? 2 : 1;
   const int tiles = (a.num_m_tiles / MT) * a.num_n_tiles;
