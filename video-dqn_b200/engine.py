@@ -436,7 +436,7 @@ def _flush_finalize(ws: Workspace):
     """reduce the split partials of every weight gradient enqueued since the last flush: one launch"""
     if not ws._pending:
         return
-    key = tuple((nm, w.data_ptr(), dw.data_ptr()) for nm, _, w, dw, _ in ws._pending)
+    key = tuple((nm, w.data_ptr(), dw.data_ptr(), args["splits"]) for nm, _, w, dw, args in ws._pending)
     tab = ws._fin_tables.get(key)
     if tab is None:
         descs = [ops.wgrad_finalize_desc(part, w, dw, **args) for _, part, w, dw, args in ws._pending]
