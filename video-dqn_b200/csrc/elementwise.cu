@@ -433,7 +433,7 @@ __global__ void stem_pack_u8_kernel(const uint8_t* __restrict__ x, __nv_bfloat16
 // -inf afterwards: no branch sits between the loads, so nine are in flight per thread (the branchy
 // form had one, and ran at half the HBM rate).
 template <bool IDX>
-__global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+__global__ void __launch_bounds__(256, 6) maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
                                    uint8_t* __restrict__ idx, int N, int H, int W, int C) {
   pdl_launch_dependents();
   pdl_wait();
