@@ -18,7 +18,10 @@ import torch.distributed as dist
 
 
 class GradSync:
-    def __init__(self, learner, process_group=None, bucket_bytes: int = 8 << 20):
+    def __init__(self, learner, process_group=None, bucket_bytes: int = None):
+        if bucket_bytes is None:
+            import os
+            bucket_bytes = int(os.environ.get("VDQN_DDP_BUCKET_MB", "8")) << 20
         self.pg = process_group
         self.arena = learner.opt.grad_arena
         self.bucket_elems = bucket_bytes // 4
