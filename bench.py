@@ -335,11 +335,16 @@ def main():
             stager.push(host[(i + 2) % len(host)])
         barrier()
         t0 = time.perf_counter()
+        base = learner.steps_done
         for i in range(k):
             stager.pop_into_learner()
-            loss = learner.step()
+            learner.step()
             stager.push(host[(i + 5) % len(host)])           # next batch's H2D overlaps this step
-            _ = loss.item()                                   # D2H of the step result, every step (:229)
+            # D2H of the step result, every step (:229): each loss is copied to pinned memory by the
+            # step itself and read here one step behind, so the device is not idle while the host reads
+            if i > 0:
+                _ = learner.loss_value(base + i - 1)
+        _ = learner.loss_value(base + k - 1)
         barrier()
         dt = max_over_ranks(time.perf_counter() - t0) / k
         e2e = {"value": world * B * 2 / dt, "unit": "frames/s", "h2d_bytes_per_step": stager.h2d_bytes,

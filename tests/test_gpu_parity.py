@@ -495,3 +495,23 @@ def test_inverse_action_model_forward_matches_reference_golden():
     assert (run.label(k.to(dev), k1.to(dev)).cpu()[clear] == y_ref.argmax(1)[clear]).all()
     with pytest.raises(ValueError, match="bad shape"):
         run(k[:2].to(dev), k1[:2].to(dev))
+
+
+@pytest.mark.gpu
+def test_loss_ring_matches_loss_tensor():
+    """`QLearner.loss_value(k)` (pinned ring filled by the step, read behind the launch of the next
+    step) returns the same numbers as `loss.item()` right after each step."""
+    from video_dqn_b200.learner import QLearner, StepConfig
+    dev = _dev()
+    sd = qstep.init_state(seed=4, randomize_bn=True)
+    m, t = _build(sd, dev), _build(sd, dev)
+    lr = QLearner(m, t, StepConfig(), batch_size=8)
+    seen = []
+    for i in range(5):
+        batch = [x.to(dev) for x in qstep.synthetic_batch(8, seed=1 + i)]
+        seen.append(lr.step(batch).item())
+    for k in (1, 2, 3, 4):
+        assert lr.loss_value(k) == seen[k]
+    assert lr.loss_value() == seen[-1]
+    with pytest.raises(ValueError):
+        lr.loss_value(0)                                  # fell out of the four-slot ring

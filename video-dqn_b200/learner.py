@@ -125,6 +125,12 @@ class QLearner:
         self.loss = torch.zeros(1, device=dev, dtype=torch.float32)
         self.best = torch.empty(batch_size, C, device=dev, dtype=torch.int64)
         self.y = torch.empty(batch_size, C, device=dev, dtype=torch.float32)
+        # every step's loss also goes to a small pinned ring with an event per slot, so a training loop
+        # can read step k's loss after it has launched step k+1 (`loss_value(k)`): the device never
+        # waits for the host between steps, which `loss.item()` right after `step()` makes it do
+        self._loss_ring = torch.zeros(4, dtype=torch.float32, pin_memory=True)
+        self._loss_events = [torch.cuda.Event() for _ in range(4)]
+        self.steps_done = 0
         self.sample_number = 0
         self._graphs: Dict[bool, torch.cuda.CUDAGraph] = {}
         self._eager_steps = 0
@@ -221,11 +227,24 @@ class QLearner:
         else:
             self._enqueue(sync_target)
             self._eager_steps += 1
+        slot = self.steps_done % 4
+        self._loss_ring[slot:slot + 1].copy_(self.loss, non_blocking=True)
+        self._loss_events[slot].record()
+        self.steps_done += 1
         # the bf16 operands were just re-derived inside the step: mark the modules in sync
         self.model._eng.sig = None
         self.target_net._eng.sig = None
         self._mark_clean()
         return self.loss
+
+    def loss_value(self, step_index: int = -1) -> float:
+        """Loss of step `step_index` (0-based count of `step()` calls; default: the latest) as a host
+        float, from the pinned ring: waits for that step only.  At most the last four steps are kept."""
+        k = self.steps_done - 1 if step_index < 0 else step_index
+        if not (self.steps_done - 4 <= k < self.steps_done) or k < 0:
+            raise ValueError("loss_value: step not in the ring")
+        self._loss_events[k % 4].synchronize()
+        return float(self._loss_ring[k % 4])
 
     def _mark_clean(self):
         from .optim import arena_epoch
