@@ -214,6 +214,10 @@ int vdqn_relu_mask_colsum(float* dy, const float* y, void* dy_bf16, float* db, i
 /* head conv output bf16 [B][P][C] (NHWC) <-> fp32 [B][C*P] (torch Flatten order); the backward
  * also applies the head ReLU mask and accumulates the conv-bias gradient. */
 int vdqn_head_flatten_fwd(const void* h_nhwc, float* flat, int32_t B, int32_t P, int32_t C, void* stream);
+/* out[n][c] = mean over the P pixels of x[n][p][c] (NHWC bf16 -> fp32): the AdaptiveAvgPool2d(1) that
+ * ends the trunk of the `basic` architecture (archs/HabitatDQNMultiAction.py:33, extra_capacity=False). */
+int vdqn_avgpool_fwd(const void* x_nhwc, float* out, int32_t N, int32_t P, int32_t C, void* stream);
+
 int vdqn_head_flatten_bwd(const float* dflat, const void* h_nhwc, void* dh_nhwc, float* dbias,
                           int32_t B, int32_t P, int32_t C, void* stream);
 

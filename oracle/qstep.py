@@ -203,6 +203,33 @@ def q_forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, action_dim: int = 3
 # TD loss (train_q_network.py:126-181)
 # ----------------------------------------------------------------------------
 
+def init_state_basic(seed: int = 4, action_dim: int = 3, randomize_bn: bool = True, num_frames: int = 1
+                     ) -> Dict[str, torch.Tensor]:
+    """State dict of the `basic` architecture (extra_capacity=False,
+    archs/HabitatDQNMultiAction.py:32-34): the same trunk keys (resnet.* + features.* aliases), no
+    head conv, `top` = one Linear(512*F, A*5)."""
+    sd = {k: v for k, v in init_state(seed, action_dim, randomize_bn).items()
+          if not (k.startswith("features.8.") or k.startswith("top."))}
+    g = torch.Generator().manual_seed(seed + 77)
+    b = 1 / math.sqrt(512 * num_frames)
+    sd["top.weight"] = (torch.rand(action_dim * NUM_CLASSES, 512 * num_frames, generator=g) * 2 - 1) * b
+    sd["top.bias"] = (torch.rand(action_dim * NUM_CLASSES, generator=g) * 2 - 1) * b
+    return sd
+
+
+def q_forward_basic(sd: Dict[str, torch.Tensor], x: torch.Tensor, action_dim: int = 3) -> torch.Tensor:
+    """Q[B,5,A] of the `basic` architecture in eval mode: trunk -> AdaptiveAvgPool2d(1) -> cat over
+    frames -> Linear (archs/HabitatDQNMultiAction.py:33-34,44-54)."""
+    if x.dim() == 4:
+        x = x.unsqueeze(1)
+    nf = sd["top.weight"].shape[1] // 512
+    if x.shape[1] != nf:
+        raise Exception("bad shape")
+    feats = [trunk_forward(sd, x[:, i]).mean(dim=(2, 3)) for i in range(nf)]
+    q = F.linear(torch.cat(feats, 1), sd["top.weight"], sd["top.bias"])
+    return q.view(-1, NUM_CLASSES, action_dim)
+
+
 def td_targets(q_next_online, q_next_target, rew, term, cfg: StepConfig):
     sel = q_next_online if cfg.double_dqn else q_next_target
     best = sel.argmax(-1)                                           # [B,5], first max on ties

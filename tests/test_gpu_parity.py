@@ -515,3 +515,33 @@ def test_loss_ring_matches_loss_tensor():
     assert lr.loss_value() == seen[-1]
     with pytest.raises(ValueError):
         lr.loss_value(0)                                  # fell out of the four-slot ring
+
+
+@pytest.mark.gpu
+def test_basic_architecture_eval_forward():
+    """`HabitatDQNMultiAction(..., extra_capacity=False)` (archs/HabitatDQNMultiAction.py:32-34): the
+    drop-in module's eval-mode forward (trunk on the conv engine, global average pool, Linear) against
+    the reference module's outputs (tests/golden/basic_b4.npz), F = 1 and F = 4; train-mode BatchNorm
+    is refused loudly."""
+    from video_dqn_b200.qnet import HabitatDQNMultiAction
+    dev = _dev()
+    z = np.load(os.path.join(GOLD, "basic_b4.npz"))
+    for tag, F in (("f1", 1), ("f4", 4)):
+        sd = qstep.init_state_basic(seed=4, num_frames=F)
+        m = HabitatDQNMultiAction(3, 5, extra_capacity=False, panorama=(F == 4))
+        res = m.load_state_dict(sd, strict=False)
+        assert not res.unexpected_keys
+        m = m.to(dev).eval()
+        g = torch.Generator().manual_seed(int(z[f"{tag}/data_seed"]))
+        B = 4 if F == 1 else 2
+        x = torch.randn(B, F, 3, 224, 224, generator=g) if F > 1 else torch.randn(B, 3, 224, 224, generator=g)
+        q = m(x.to(dev))
+        torch.cuda.synchronize()
+        assert q.shape == (B, 5, 3)
+        q_ref = torch.from_numpy(z[f"{tag}/q"])
+        # Q is an unnormalised linear read-out of pooled features here (|Q| up to ~9 with the random
+        # BatchNorm statistics of the fixture): the 1e-2 bar is taken relative to the largest |Q|
+        assert (q.cpu() - q_ref).abs().max().item() <= Q_TOL * max(1.0, q_ref.abs().max().item())
+    m.train()
+    with pytest.raises(NotImplementedError):
+        m(x.to(dev))

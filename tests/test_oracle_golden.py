@@ -144,3 +144,17 @@ def test_inverse_model_oracle_reproduces_reference_golden():
     np.testing.assert_allclose(y.numpy(), z["y"], atol=1e-5)
     np.testing.assert_allclose(enc.numpy(), z["encoding"], atol=1e-6)
     assert torch.equal(oinv.label(sd, k, k1), torch.from_numpy(z["y"]).argmax(1))
+
+
+def test_basic_architecture_oracle_reproduces_reference_golden():
+    """extra_capacity=False (trunk + global average pool + one Linear), eval mode, F = 1 and F = 4:
+    oracle against the outputs of the reference module (oracle/make_basic_goldens.py)."""
+    z = np.load(os.path.join(GOLD, "basic_b4.npz"))
+    for tag, F in (("f1", 1), ("f4", 4)):
+        sd = qstep.init_state_basic(seed=4, num_frames=F)
+        g = torch.Generator().manual_seed(int(z[f"{tag}/data_seed"]))
+        B = 4 if F == 1 else 2
+        x = torch.randn(B, F, 3, 224, 224, generator=g) if F > 1 else torch.randn(B, 3, 224, 224, generator=g)
+        with torch.no_grad():
+            q = qstep.q_forward_basic(sd, x)
+        np.testing.assert_allclose(q.numpy(), z[f"{tag}/q"], atol=2e-6)

@@ -79,6 +79,7 @@ EXPORTS = {
     "vdqn_linear_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "vdqn_linear_bwd": (c_int, [c_void_p] * 7 + [c_int, c_int, c_int, c_int, c_void_p]),
     "vdqn_relu_mask_colsum": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "vdqn_avgpool_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "vdqn_head_flatten_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "vdqn_head_flatten_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "vdqn_td_epilogue": (c_int, [C.POINTER(TdDesc), c_void_p]),

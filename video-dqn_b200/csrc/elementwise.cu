@@ -704,6 +704,22 @@ __global__ void mask_colsum_kernel(const float* __restrict__ dy, const float* __
   }
 }
 
+// out[n][c] = mean_p x[n][p][c]  (AdaptiveAvgPool2d(1) of the `basic` architecture's trunk,
+// archs/HabitatDQNMultiAction.py:33): one thread per (n, c), fp32 accumulation in pixel order
+__global__ void avgpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, int N, int P, int C) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long total = (long)N * C;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long n = i / C;
+    const int c = (int)(i - n * C);
+    const __nv_bfloat16* px = x + n * P * C + c;
+    float s = 0.f;
+    for (int p = 0; p < P; ++p) s += __bfloat162float(px[(long)p * C]);
+    out[i] = s / (float)P;
+  }
+}
+
 __global__ void head_flatten_fwd_kernel(const __nv_bfloat16* __restrict__ h, float* __restrict__ flat,
                                         int B, int P, int C) {
   pdl_launch_dependents();
@@ -1102,6 +1118,17 @@ extern "C" int vdqn_head_flatten_fwd(const void* h, float* flat, int32_t B, int3
   if (total == 0) return VDQN_OK;
   launch_kernel(head_flatten_fwd_kernel, grid_for(total, 256, dev->num_sms), 256, 0, stream, static_cast<const __nv_bfloat16*>(h), flat, B, P, C);
   VDQN_CHECK_LAUNCH("head_flatten_fwd");
+  return VDQN_OK;
+}
+
+extern "C" int vdqn_avgpool_fwd(const void* x, float* out, int32_t N, int32_t P, int32_t C, void* stream_v) {
+  if (x == nullptr || out == nullptr) return set_error(VDQN_ERR_ARG, "avgpool_fwd: null pointer");
+  GET_DEV();
+  const long total = (long)N * C;
+  if (total == 0) return VDQN_OK;
+  launch_kernel(avgpool_fwd_kernel, grid_for(total, 256, dev->num_sms), 256, 0, stream,
+                static_cast<const __nv_bfloat16*>(x), out, N, P, C);
+  VDQN_CHECK_LAUNCH("avgpool_fwd");
   return VDQN_OK;
 }
 

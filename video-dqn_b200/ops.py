@@ -291,6 +291,19 @@ def relu_mask_colsum(dy, y, db, relu=True, out_bf16=None):
     return dy
 
 
+def avgpool_fwd(x, out=None):
+    """x [N,H,W,C] bf16 -> [N,C] fp32 mean over pixels."""
+    lib = L.load()
+    _cuda(x, bf16, "x")
+    N, Cc = x.shape[0], x.shape[-1]
+    P = x.numel() // max(N * Cc, 1)
+    if out is None:
+        out = torch.empty(N, Cc, device=x.device, dtype=torch.float32)
+    with _Prof("mlp", (N,)):
+        L.check(lib.vdqn_avgpool_fwd(x.data_ptr(), out.data_ptr(), N, P, Cc, L.stream_ptr()), "avgpool_fwd")
+    return out
+
+
 def head_flatten_fwd(h, flat=None):
     lib = L.load()
     _cuda(h, bf16, "h")

@@ -145,8 +145,7 @@ class HabitatDQNMultiAction(nn.Module):
             raise RuntimeError("video_dqn_b200.HabitatDQNMultiAction has no CPU path: move the module "
                                "and its input to a B200 (the CPU oracle lives in oracle/, tests only)")
         if not self.extra_capacity:
-            raise NotImplementedError("only the shipped `extra_capacity` architecture is implemented "
-                                      "on the CUDA path (configs/experiments/real_data/config.yml:5)")
+            return self._basic_forward(inp)
         if any(m.training for m in self.resnet.modules() if isinstance(m, nn.BatchNorm2d)):
             raise NotImplementedError("trunk BatchNorm in training mode is not implemented: call "
                                       "set_train() (or eval()) as the reference trainer does")
@@ -163,6 +162,47 @@ class HabitatDQNMultiAction(nn.Module):
             frames = inp.reshape(B * F, 3, 224, 224).float().contiguous()
         params = [self._state().P[n] for n in self._grad_names]
         q = _QNetFn.apply(frames, self, *params)
+        return q.view(-1, self.num_classes, self.action_dim)
+
+    def _basic_forward(self, inp):
+        """The `basic` architecture (extra_capacity=False, archs/HabitatDQNMultiAction.py:32-34): trunk +
+        global average pool + one Linear.  Forward only, eval mode (BatchNorm running statistics): what
+        the value-map / policy callers need for checkpoints of that architecture.  Its training keeps
+        the trunk BatchNorms in train mode (set_train() only freezes them for extra_capacity, :37-40),
+        which the CUDA path does not implement."""
+        if any(m.training for m in self.resnet.modules() if isinstance(m, nn.BatchNorm2d)):
+            raise NotImplementedError("the `basic` architecture is forward-only on the CUDA path: call "
+                                      "eval() first (its training runs the trunk BatchNorms in train mode)")
+        B, F = inp.shape[0], inp.shape[1]
+        if B == 0:
+            return inp.new_zeros((0, self.num_classes, self.action_dim), dtype=torch.float32)
+        if inp.dtype == torch.uint8:
+            frames = inp.reshape(B * F, *inp.shape[2:]).contiguous()
+        else:
+            if inp.shape[2] != 3 or inp.shape[3] != 224 or inp.shape[4] != 224:
+                raise Exception("bad shape")
+            frames = inp.reshape(B * F, 3, 224, 224).float().contiguous()
+        nt = self._named_tensors()
+        dev = nt["top.weight"].device
+        st = getattr(self, "_basic_eng", None)
+        if st is None or st["dev"] != dev:
+            plan = E.make_plan(self.action_dim, self.num_classes, self.num_frames)
+            st = self._basic_eng = {"dev": dev, "plan": plan, "W": E.PreparedWeights(plan, dev, trunk_only=True),
+                                    "sig": None, "ws": {}}
+        sig = tuple((t.data_ptr(), t._version) for t in nt.values())
+        if sig != st["sig"]:
+            st["P"] = {k: v.detach() for k, v in nt.items()}
+            st["W"].prepare(st["P"])
+            st["sig"] = sig
+        n = B * F
+        ws = st["ws"].get(n)
+        if ws is None:
+            ws = st["ws"][n] = E.Workspace(st["plan"], n, dev, train=False)
+        with torch.no_grad():
+            ops.stem_pack(frames, ws.xp)
+            feat = E.forward_packed(st["plan"], st["W"], st["P"], ws, trunk_only=True)      # [n,7,7,512]
+            pooled = ops.avgpool_fwd(feat)                                                     # [n,512] fp32
+            q = ops.linear_fwd(pooled.view(B, F * 512), st["P"]["top.weight"], st["P"]["top.bias"], False)
         return q.view(-1, self.num_classes, self.action_dim)
 
     # -- engine plumbing -------------------------------------------------------------------
