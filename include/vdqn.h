@@ -253,6 +253,27 @@ int vdqn_td_epilogue(const vdqn_td_desc* d, void* stream);
 int vdqn_q_max(const float* q, float* value, int64_t* arg, int64_t rows, int32_t A, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Training step of the inverse-dynamics model (train_inverse_model.py:85-110): the pieces the
+ * Q-learning path does not already have.
+ *
+ * Softmax cross-entropy with mean reduction, `nn.CrossEntropyLoss()(y, act)` (:100-102) and the
+ * accuracy count `y.argmax(1) == act` (:105-106), fused with the gradient:
+ *   loss_out[0] += inv_count * sum_b (logsumexp(y[b,:]) - y[b,act[b]])     (zero it before the call)
+ *   dlogits[b,c] = inv_count * (softmax(y[b,:])[c] - [c == act[b]])        (may be NULL: validation)
+ *   correct_out[0] += #{b : first arg-max of y[b,:] == act[b]}             (may be NULL)
+ * logits fp32 [B,C] row-major, labels int64 [B], 1 <= C <= 32. */
+int vdqn_cross_entropy(const float* logits, const int64_t* labels, float* dlogits, float* loss_out,
+                       int32_t* correct_out, int32_t B, int32_t C, float inv_count, void* stream);
+/* Element dropout of `nn.Dropout2d(0.5)` applied to the [B,128] fc1 output (:44,78; on a 2-D input it
+ * drops single elements).  keep[i] in {0,1}:
+ *   vdqn_dropout_mask : keep[i] = u(seed, counter, i) >= p, u uniform in [0,1) from a counter-based
+ *                       generator (splitmix64 of seed, counter, i) -- stateless, graph-replay safe
+ *   vdqn_dropout_apply: y[i] = keep[i] ? x[i] * scale : 0   (scale = 1/(1-p); y may alias x; the same
+ *                       call is the backward pass on the gradient) */
+int vdqn_dropout_mask(uint8_t* keep, int64_t n, float p, uint64_t seed, uint64_t counter, void* stream);
+int vdqn_dropout_apply(const float* x, const uint8_t* keep, float scale, float* y, int64_t n, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Fused multi-tensor Adam (+ optional hard target-network sync in the same pass).
  * Replaces optim.Adam.step (train_q_network.py:124,227; ~550 launches under torch 1.3.1)
  * and target_net.load_state_dict(model.state_dict()) (:215-216).

@@ -3,7 +3,8 @@ the network that labels the `inverse_actions` column of the quadruplet table
 (dataset/process_episodes_real.py:92-95,171-179).
 
 TEST INFRASTRUCTURE ONLY (see qstep.py).  Pinned against the reference class itself by
-oracle/make_inverse_goldens.py.  Eval mode, as the labelling script runs it (`model.eval()`, :95):
+oracle/make_inverse_goldens.py; the training step below (train_inverse_model.py:30-110,176) by
+oracle/make_inverse_train_goldens.py.  Eval mode, as the labelling script runs it (`model.eval()`, :95):
 the two Dropout2d layers are identities; the ResNet-18 trunk is frozen with eval-mode BN (:56-58,75).
 
 State-dict layout of the reference module: the trunk is `nn.Sequential(children()[:-2])`, so its keys
@@ -73,3 +74,72 @@ def forward(sd: Dict[str, torch.Tensor], k: torch.Tensor, k_plus_one: torch.Tens
 def label(sd, k, k_plus_one) -> torch.Tensor:
     """`model(be, ae)[1].argmax(dim=1)` (dataset/process_episodes_real.py:176-177)"""
     return forward(sd, k, k_plus_one)[1].argmax(dim=1)
+
+
+# ----------------------------------------------------------------------------
+# training step of the inverse model (train_inverse_model.py)
+# ----------------------------------------------------------------------------
+TRAINABLE = ("conv1.weight", "conv1.bias", "conv2.weight", "conv2.bias", "conv3.weight", "conv3.bias",
+             "fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias", "fc_accuracy.weight", "fc_accuracy.bias")
+DROPOUT_P = 0.5
+
+
+def train_forward(sd: Dict[str, torch.Tensor], k: torch.Tensor, k_plus_one: torch.Tensor,
+                  keep: torch.Tensor | None) -> torch.Tensor:
+    """The TRAINER's forward (train_inverse_model.py:55-82) -- not the arch file's: ReLU after fc2, only
+    `y = fc_accuracy(.)` is returned, and `dropout1` (nn.Dropout2d(0.5) on the 2-D fc1 output, i.e.
+    element dropout) is active in train mode.  `keep` [B,128] in {0,1} is the dropout draw (None: eval
+    mode, identity); the trunk is frozen and in eval mode either way (:39-42,58)."""
+    rs = trunk_keys_to_resnet(sd)
+    with torch.no_grad():
+        a = qstep.trunk_forward(rs, k)
+        b = qstep.trunk_forward(rs, k_plus_one)
+    x = torch.cat([a, b], dim=1)
+    x = F.relu(F.conv2d(x, sd["conv1.weight"], sd["conv1.bias"]))
+    x = F.relu(F.conv2d(x, sd["conv2.weight"], sd["conv2.bias"]))
+    x = F.relu(F.conv2d(x, sd["conv3.weight"], sd["conv3.bias"]))
+    x = x.view(x.size(0), -1)
+    x = F.relu(F.linear(x, sd["fc1.weight"], sd["fc1.bias"]))
+    if keep is not None:
+        x = x * keep.to(x.dtype) * (1.0 / (1.0 - DROPOUT_P))
+    x = F.relu(F.linear(x, sd["fc2.weight"], sd["fc2.bias"]))
+    return F.linear(x, sd["fc_accuracy.weight"], sd["fc_accuracy.bias"])
+
+
+class InverseOracleTrainer:
+    """`optimizer.zero_grad(); y = model(be, ae); loss = CrossEntropyLoss()(y, act); loss.backward();
+    optimizer.step()` (train_inverse_model.py:93-110) with `Adam(model.parameters(), lr, weight_decay=0)`
+    (:176; the frozen trunk has no gradients and is skipped)."""
+
+    def __init__(self, sd: Dict[str, torch.Tensor], lr: float = 1e-4):
+        self.sd = {k: v.clone() for k, v in sd.items()}
+        self.lr, self.t = lr, 0
+        self.exp_avg = {n: torch.zeros_like(self.sd[n]) for n in TRAINABLE}
+        self.exp_avg_sq = {n: torch.zeros_like(self.sd[n]) for n in TRAINABLE}
+
+    def loss_and_grads(self, k, k1, act, keep):
+        leaves = {n: self.sd[n].detach().clone().requires_grad_(True) for n in TRAINABLE}
+        sd = dict(self.sd)
+        sd.update(leaves)
+        y = train_forward(sd, k, k1, keep)
+        loss = F.cross_entropy(y, act)
+        grads = torch.autograd.grad(loss, [leaves[n] for n in TRAINABLE])
+        correct = int((y.argmax(dim=1) == act).sum())
+        return loss.detach(), dict(zip(TRAINABLE, grads)), y.detach(), correct
+
+    def adam(self, grads):
+        import math
+        self.t += 1
+        b1, b2, eps = 0.9, 0.999, 1e-8
+        bc1, bc2 = 1 - b1 ** self.t, 1 - b2 ** self.t
+        for n in TRAINABLE:
+            g, m, v = grads[n], self.exp_avg[n], self.exp_avg_sq[n]
+            m.mul_(b1).add_(g, alpha=1 - b1)
+            v.mul_(b2).addcmul_(g, g, value=1 - b2)
+            denom = (v.sqrt() / math.sqrt(bc2)).add_(eps)
+            self.sd[n].addcdiv_(m, denom, value=-self.lr / bc1)
+
+    def step(self, k, k1, act, keep):
+        loss, grads, y, correct = self.loss_and_grads(k, k1, act, keep)
+        self.adam(grads)
+        return loss, grads, y, correct

@@ -158,3 +158,36 @@ def test_basic_architecture_oracle_reproduces_reference_golden():
         with torch.no_grad():
             q = qstep.q_forward_basic(sd, x)
         np.testing.assert_allclose(q.numpy(), z[f"{tag}/q"], atol=2e-6)
+
+
+def inverse_train_batches(z):
+    """the seeded batches oracle/make_inverse_train_goldens.py stepped the reference on"""
+    g = torch.Generator().manual_seed(int(z["data_seed"]))
+    B = int(z["batch"])
+    for s in range(int(z["steps"])):
+        k = torch.randn(B, 3, 224, 224, generator=g)
+        k1 = torch.randn(B, 3, 224, 224, generator=g)
+        act = torch.randint(0, 3, (B,), generator=g)
+        yield s, k, k1, act, torch.from_numpy(z[f"keep{s}"])
+
+
+def test_inverse_model_training_oracle_reproduces_reference_golden():
+    """oracle/inverse.py's training step (trainer forward with ReLU after fc2 and element dropout,
+    cross-entropy, Adam) against three steps of the reference's own train_inverse_model.model +
+    nn.CrossEntropyLoss + torch.optim.Adam (tests/golden/inverse_train_b4.npz)."""
+    from oracle import inverse as oinv
+    torch.set_num_threads(os.cpu_count() or 1)
+    z = np.load(os.path.join(GOLD, "inverse_train_b4.npz"))
+    tr = oinv.InverseOracleTrainer(oinv.init_state(seed=int(z["seed"])), lr=float(z["lr"]))
+    for s, k, k1, act, keep in inverse_train_batches(z):
+        loss, grads, y, correct = tr.step(k, k1, act, keep)
+        assert abs(loss.item() - float(z[f"loss{s}"])) <= 2e-6
+        np.testing.assert_allclose(y.numpy(), z[f"y{s}"], atol=2e-6)
+        assert correct == int(z[f"correct{s}"])                   # integer: exact
+        for n in oinv.TRAINABLE:
+            ref_l2 = float(z[f"s{s}/grad/{n}/l2"])
+            assert abs(grads[n].double().norm().item() - ref_l2) <= 1e-4 * ref_l2 + 1e-12, n
+            np.testing.assert_allclose(_sample(grads[n]), z[f"s{s}/grad/{n}/sample"],
+                                       rtol=1e-3, atol=1e-5 * ref_l2 + 1e-12, err_msg=n)
+            np.testing.assert_allclose(_sample(tr.sd[n]), z[f"s{s}/param/{n}/sample"],
+                                       rtol=1e-5, atol=2e-6, err_msg=n)

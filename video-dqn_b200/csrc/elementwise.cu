@@ -837,6 +837,92 @@ __global__ void q_max_kernel(const float* __restrict__ q, float* __restrict__ va
 }
 
 // ------------------------------------------------------------------------------------------
+// inverse-dynamics training step (train_inverse_model.py:85-110): softmax cross-entropy (mean) with
+// its gradient and the accuracy count, one thread per sample; element dropout with a counter-based
+// generator.
+__global__ void cross_entropy_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels,
+                                     float* __restrict__ dlogits, float* __restrict__ loss_out,
+                                     int* __restrict__ correct_out, int B, int C, float inv_count) {
+  pdl_launch_dependents();
+  pdl_wait();
+  float local = 0.f;
+  int hits = 0;
+  for (long b = blockIdx.x * (long)blockDim.x + threadIdx.x; b < B; b += (long)gridDim.x * blockDim.x) {
+    const float* y = logits + b * C;
+    float v[32];
+    float mx = y[0];
+    int best = 0;
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+      if (c < C) {
+        v[c] = y[c];
+        if (v[c] > mx) { mx = v[c]; best = c; }      // strict > : first maximum wins (torch.argmax)
+      }
+    }
+    float se = 0.f;
+#pragma unroll
+    for (int c = 0; c < 32; ++c)
+      if (c < C) { v[c] = expf(v[c] - mx); se += v[c]; }
+    const int lab = (int)labels[b];
+    const float inv = 1.f / se;
+    local += logf(se) + mx - y[lab];
+    hits += (best == lab);
+    if (dlogits != nullptr) {
+#pragma unroll
+      for (int c = 0; c < 32; ++c)
+        if (c < C) dlogits[b * C + c] = (v[c] * inv - (c == lab ? 1.f : 0.f)) * inv_count;
+    }
+  }
+  __shared__ float red[32];
+  __shared__ int redh[32];
+  for (int off = 16; off; off >>= 1) {
+    local += __shfl_xor_sync(0xffffffffu, local, off);
+    hits += __shfl_xor_sync(0xffffffffu, hits, off);
+  }
+  if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = local; redh[threadIdx.x >> 5] = hits; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const bool in = threadIdx.x < (blockDim.x >> 5);
+    float t = in ? red[threadIdx.x] : 0.f;
+    int h = in ? redh[threadIdx.x] : 0;
+    for (int off = 16; off; off >>= 1) {
+      t += __shfl_xor_sync(0xffffffffu, t, off);
+      h += __shfl_xor_sync(0xffffffffu, h, off);
+    }
+    if (threadIdx.x == 0) {
+      if (loss_out != nullptr) atomicAdd(loss_out, t * inv_count);
+      if (correct_out != nullptr && h != 0) atomicAdd(correct_out, h);
+    }
+  }
+}
+
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
+__global__ void dropout_mask_kernel(uint8_t* __restrict__ keep, long n, float p, uint64_t seed, uint64_t counter) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const uint64_t key = splitmix64(seed ^ splitmix64(counter));
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const uint64_t r = splitmix64(key + (uint64_t)i);
+    const float u = (float)(r >> 40) * (1.0f / 16777216.0f);      // 24 random bits -> [0, 1)
+    keep[i] = u >= p ? 1 : 0;
+  }
+}
+
+__global__ void dropout_apply_kernel(const float* __restrict__ x, const uint8_t* __restrict__ keep, float scale,
+                                     float* __restrict__ y, long n) {
+  pdl_launch_dependents();
+  pdl_wait();
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+    y[i] = keep[i] ? x[i] * scale : 0.f;
+}
+
+// ------------------------------------------------------------------------------------------
 // fused Adam (+ target sync), flat fp32 arenas, 16-byte vectors
 __global__ void __launch_bounds__(256)
 adam_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m,
@@ -1183,6 +1269,41 @@ extern "C" int vdqn_q_max(const float* q, float* value, int64_t* arg, int64_t ro
   if (rows == 0) return VDQN_OK;
   launch_kernel(q_max_kernel, grid_for(rows, 256, dev->num_sms), 256, 0, stream, q, value, arg, rows, A);
   VDQN_CHECK_LAUNCH("q_max");
+  return VDQN_OK;
+}
+
+extern "C" int vdqn_cross_entropy(const float* logits, const int64_t* labels, float* dlogits, float* loss_out,
+                                  int32_t* correct_out, int32_t B, int32_t C, float inv_count, void* stream_v) {
+  if (C < 1 || C > 32 || B < 0) return set_error(VDQN_ERR_SHAPE, "cross_entropy: bad shape (1 <= C <= 32)");
+  if (B == 0) return VDQN_OK;                     // empty batch: nothing to add to loss / correct
+  if (logits == nullptr || labels == nullptr) return set_error(VDQN_ERR_ARG, "cross_entropy: null pointer");
+  GET_DEV();
+  launch_kernel(cross_entropy_kernel, grid_for(B, 128, dev->num_sms), 128, 0, stream, logits, labels, dlogits,
+                loss_out, correct_out, B, C, inv_count);
+  VDQN_CHECK_LAUNCH("cross_entropy");
+  return VDQN_OK;
+}
+
+extern "C" int vdqn_dropout_mask(uint8_t* keep, int64_t n, float p, uint64_t seed, uint64_t counter,
+                                 void* stream_v) {
+  if (keep == nullptr) return set_error(VDQN_ERR_ARG, "dropout_mask: null pointer");
+  if (!(p >= 0.f && p < 1.f) || n < 0) return set_error(VDQN_ERR_ARG, "dropout_mask: need 0 <= p < 1");
+  GET_DEV();
+  if (n == 0) return VDQN_OK;
+  launch_kernel(dropout_mask_kernel, grid_for(n, 256, dev->num_sms), 256, 0, stream, keep, (long)n, p,
+                (uint64_t)seed, (uint64_t)counter);
+  VDQN_CHECK_LAUNCH("dropout_mask");
+  return VDQN_OK;
+}
+
+extern "C" int vdqn_dropout_apply(const float* x, const uint8_t* keep, float scale, float* y, int64_t n,
+                                  void* stream_v) {
+  if (x == nullptr || keep == nullptr || y == nullptr) return set_error(VDQN_ERR_ARG, "dropout_apply: null pointer");
+  if (n < 0) return set_error(VDQN_ERR_SHAPE, "dropout_apply: bad shape");
+  GET_DEV();
+  if (n == 0) return VDQN_OK;
+  launch_kernel(dropout_apply_kernel, grid_for(n, 256, dev->num_sms), 256, 0, stream, x, keep, scale, y, (long)n);
+  VDQN_CHECK_LAUNCH("dropout_apply");
   return VDQN_OK;
 }
 

@@ -394,6 +394,50 @@ def q_max(q, value=None, arg=None, want_arg=False):
     return value, arg
 
 
+def cross_entropy(logits, labels, *, dlogits=None, loss=None, correct=None, inv_count=None, want_grad=True):
+    """`nn.CrossEntropyLoss()(logits, labels)` (mean) + gradient + number of correct arg-max predictions
+    (train_inverse_model.py:100-106).  `loss` (fp32[1]) and `correct` (int32[1]) are ACCUMULATED into:
+    zero them first.  Returns (loss, dlogits, correct)."""
+    lib = L.load()
+    _cuda(logits, torch.float32, "logits"); _cuda(labels, torch.int64, "labels")
+    _req(logits.dim() == 2 and labels.numel() == logits.shape[0], "bad shape")
+    B, Cc = logits.shape
+    dev = logits.device
+    if want_grad and dlogits is None:
+        dlogits = torch.empty_like(logits)
+    if loss is None:
+        loss = torch.zeros(1, device=dev, dtype=torch.float32)
+    if correct is None:
+        correct = torch.zeros(1, device=dev, dtype=torch.int32)
+    with _Prof("ce", (B, Cc)):
+        L.check(lib.vdqn_cross_entropy(logits.data_ptr(), labels.data_ptr(), L.ptr(dlogits) if want_grad else None,
+                                       loss.data_ptr(), correct.data_ptr(), B, Cc,
+                                       (1.0 / max(B, 1)) if inv_count is None else inv_count, L.stream_ptr()),
+                "cross_entropy")
+    return loss, dlogits, correct
+
+
+def dropout_mask(keep, p, seed, counter):
+    """keep (uint8, any shape) <- Bernoulli(1 - p) from the counter-based generator."""
+    lib = L.load()
+    _cuda(keep, torch.uint8, "keep")
+    L.check(lib.vdqn_dropout_mask(keep.data_ptr(), keep.numel(), float(p), int(seed) & (2 ** 64 - 1),
+                                  int(counter), L.stream_ptr()), "dropout_mask")
+    return keep
+
+
+def dropout_apply(x, keep, scale, y=None):
+    """y = keep ? x * scale : 0 (y may be x)."""
+    lib = L.load()
+    _cuda(x, torch.float32, "x"); _cuda(keep, torch.uint8, "keep")
+    _req(keep.numel() == x.numel(), "bad shape")
+    if y is None:
+        y = torch.empty_like(x)
+    L.check(lib.vdqn_dropout_apply(x.data_ptr(), keep.data_ptr(), float(scale), y.data_ptr(), x.numel(),
+                                   L.stream_ptr()), "dropout_apply")
+    return y
+
+
 def adam_fused(p, g, m, v, *, lr, step=None, betas=(0.9, 0.999), eps=1e-8, target=None, grad_scale=1.0,
                step_dev=None, scalars_dev=None):
     """Fused Adam over flat fp32 arenas.  Either `step` (host int) or `step_dev` + `scalars_dev`
