@@ -381,6 +381,54 @@ def main():
                                        "e2e_ms": host_ms, "views_per_sec_e2e": nb / host_ms * 1e3}
         model.set_train()
 
+    # ---------------- inverse-dynamics model (BASELINE configs[4]): training step on frame pairs at the
+    # reference's batch (train_inverse_model.py:21,93-110) and the labelling forward
+    # (dataset/process_episodes_real.py:171-179)
+    inverse = None
+    if rank == 0 and world == 1 and not a.no_inference:
+        from video_dqn_b200.inverse import InverseActionModule, InverseActionRunner, InverseModelTrainer
+        nb = 128
+        torch.manual_seed(7)
+        isd = InverseActionModule().state_dict()    # random init in the reference module's key layout
+        g = torch.Generator().manual_seed(11)
+        hk = torch.randn(nb, 3, 224, 224, generator=g).pin_memory()
+        hk1 = torch.randn(nb, 3, 224, 224, generator=g).pin_memory()
+        hact = torch.randint(0, 3, (nb,), generator=g).pin_memory()
+        dk, dk1, dact = hk.to(dev), hk1.to(dev), hact.to(dev)
+        tr = InverseModelTrainer(isd, nb, lr=1e-4, device=dev)
+        for _ in range(5):
+            tr.step(dk, dk1, dact)
+        torch.cuda.synchronize()
+        iters = 50
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            tr.step(dk, dk1, dact)
+        e1.record(); torch.cuda.synchronize()
+        train_ms = e0.elapsed_time(e1) / iters
+        t0 = time.perf_counter()
+        for _ in range(iters):
+            lt = tr.step(hk, hk1, hact)             # H2D of the fp32 pair batch (154 MB) + step
+        _ = lt.item()
+        train_e2e_ms = (time.perf_counter() - t0) / iters * 1e3
+        run = InverseActionRunner(isd, nb, dev)
+        for _ in range(3):
+            run.label(dk, dk1)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(iters):
+            run.label(dk, dk1)
+        e1.record(); torch.cuda.synchronize()
+        label_ms = e0.elapsed_time(e1) / iters
+        # per pair: two trunk forwards + head forward (7.31 GFLOP) + head backward (2 x 29.0 MMAC x 2)
+        flop_pair = 7.31e9 + 0.116e9
+        inverse = {"batch": nb, "train_step_ms": train_ms, "pairs_per_sec_device": nb / train_ms * 1e3,
+                   "train_step_e2e_ms": train_e2e_ms, "pairs_per_sec_e2e": nb / train_e2e_ms * 1e3,
+                   "train_tflops": flop_pair * nb / (train_ms * 1e-3) / 1e12,
+                   "label_ms": label_ms, "pairs_per_sec_label": nb / label_ms * 1e3,
+                   "frames": "fp32 NCHW pairs (the reference loader's output)", "loss": float(lt.item())}
+        del tr, run
+
     # ---------------- CPU baseline (rank 0, N = 1): bounded sample of the same workload
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
@@ -408,7 +456,7 @@ def main():
             "gpu_launches_per_step": per_step_launches,
             "e2e": e2e, "roofline": roof, "roofline_kernels": roof_other, "cpu_baseline": cpu,
             "breakdown_eager_ms": breakdown if rank == 0 else None,
-            "inference": inference,
+            "inference": inference, "inverse_model": inverse,
         }
         print(json.dumps(out), file=out_stream, flush=True)
     if world > 1:

@@ -104,3 +104,21 @@ def test_plan_matches_survey_flop_count():
     assert macs == 1821888256
     for c in plan.convs:
         assert 1 <= E.wgrad_splits(c, 256, sms=148) <= 4096
+
+
+def test_inverse_module_container_keeps_reference_layout():
+    """`InverseActionModule` (the parameter container behind the inverse-model runner / trainer) has the
+    key layout that oracle.inverse.init_state was loaded into the reference's own module with
+    (oracle/make_inverse_goldens.py, strict), trains exactly the reference's 12 head tensors and has no
+    CPU forward."""
+    sys.path.insert(0, ROOT)
+    from oracle import inverse as oinv
+    from video_dqn_b200.inverse import InverseActionModule
+    m = InverseActionModule()
+    ref = oinv.init_state(seed=7)
+    assert set(m.state_dict()) == set(ref)
+    assert all(m.state_dict()[k].shape == v.shape for k, v in ref.items())
+    assert tuple(n for n, p in m.named_parameters() if p.requires_grad) == oinv.TRAINABLE
+    assert not m.resnet18.training
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        m(torch.zeros(1, 3, 224, 224), torch.zeros(1, 3, 224, 224))

@@ -38,6 +38,34 @@ def _trunk_params(sd: Dict[str, torch.Tensor], device) -> Dict[str, torch.Tensor
     return P
 
 
+class InverseActionModule(torch.nn.Module):
+    """Parameter container with the reference module's layout and default initialisation
+    (`train_inverse_model.py:30-53`, `archs/inverse_action2.py:45-70`): `resnet18` = positional
+    `nn.Sequential(children()[:-2])`, frozen (`requires_grad=False`, eval), then `conv1/conv2/conv3`, `fc1`,
+    `fc2` (bottleneck 3), `fc_accuracy`.  Its `state_dict()` is what `InverseActionRunner` /
+    `InverseModelTrainer` take and what `model-N.pth` files hold; there is no CPU forward."""
+
+    def __init__(self, bottleneck_size: int = 3):
+        super().__init__()
+        from .qnet import _make_resnet18
+        nn = torch.nn
+        self.resnet18 = nn.Sequential(*list(_make_resnet18(True).children())[:-2])
+        self.resnet18.eval()
+        for p in self.resnet18.parameters():
+            p.requires_grad = False
+        self.conv1 = nn.Conv2d(1024, 256, kernel_size=1)
+        self.conv2 = nn.Conv2d(256, 256, kernel_size=3)
+        self.conv3 = nn.Conv2d(256, 64, kernel_size=3)
+        self.dropout1 = nn.Dropout2d(0.5)
+        self.fc1 = nn.Linear(64 * 3 * 3, 128)
+        self.fc2 = nn.Linear(128, bottleneck_size)
+        self.fc_accuracy = nn.Linear(bottleneck_size, 3)
+
+    def forward(self, k, k_plus_one):
+        raise RuntimeError("InverseActionModule is a parameter container (no CPU path): run it through "
+                           "InverseActionRunner / InverseModelTrainer on a B200")
+
+
 class InverseActionRunner:
     """`runner(k, k_plus_one)` -> (encoding [B,3], y [B,3]); `runner.label(k, k1)` -> actions [B].
     Frames: fp32 NCHW normalised (the reference's loader output) or uint8 HWC."""

@@ -260,3 +260,46 @@ class QLearner:
         tb, mb = dict(self.target_net.named_buffers()), dict(self.model.named_buffers())
         for k, v in tb.items():
             v.copy_(mb[k])
+
+    # ------------------------------------------------------------------ checkpoint / resume
+    def checkpoint(self) -> dict:
+        """The dictionary the reference saves every CHECKPOINT_INTERVAL steps (train_q_network.py:241-247):
+        `sample_number`, the model's 250-key `state_dict()` and the optimizer's `state_dict()` in
+        torch.optim.Adam's layout -- loadable by the reference's own resume code (:192-198) and by
+        `load_model_number` (:50-57)."""
+        torch.cuda.current_stream().synchronize()
+        return {"sample_number": self.sample_number,
+                "model_state_dict": {k: v.detach().cpu().clone() for k, v in self.model.state_dict().items()},
+                "optimizer_state_dict": _to_cpu(self.opt.state_dict())}
+
+    def save_checkpoint(self, path: str):
+        """`torch.save({...}, f'{config.folder}/models/sample{sample_number}.torch')` (:241-247)"""
+        torch.save(self.checkpoint(), path)
+
+    def resume(self, snapshot, resume_from: Optional[int] = None):
+        """The reference's resume sequence (train_q_network.py:190-208) on a `sample{n}.torch` snapshot
+        (path or loaded dict, written by the reference or by `save_checkpoint`): load the model and
+        optimizer state, `sample_number = resume_from + 1` (:190; default: the snapshot's own number),
+        then `target_net.load_state_dict(model.state_dict())` (:208)."""
+        if isinstance(snapshot, (str, bytes)) or hasattr(snapshot, "__fspath__"):
+            snapshot = torch.load(snapshot, map_location="cpu")
+        self.model.load_state_dict(snapshot["model_state_dict"])           # writes into the parameter arena
+        self.opt.load_state_dict(snapshot["optimizer_state_dict"])
+        self.step_dev.fill_(self.opt._step)
+        n = snapshot.get("sample_number", -1) if resume_from is None else resume_from
+        self.sample_number = int(n) + 1
+        bump_arena_epoch(self.opt.param_arena)
+        self.sync_target_now()
+        self.model.set_train()
+        self.target_net.eval()
+        self.model._state(); self.target_net._state()                      # bf16 operands of both networks
+
+
+def _to_cpu(obj):
+    if torch.is_tensor(obj):
+        return obj.detach().cpu().clone()
+    if isinstance(obj, dict):
+        return {k: _to_cpu(v) for k, v in obj.items()}
+    if isinstance(obj, (list, tuple)):
+        return type(obj)(_to_cpu(v) for v in obj)
+    return obj

@@ -141,8 +141,23 @@ class FusedAdam(torch.optim.Optimizer):
         return super().state_dict()
 
     def load_state_dict(self, state_dict):
+        """torch layout in (e.g. the `optimizer_state_dict` of a reference checkpoint,
+        train_q_network.py:198; `step` may be an int as torch 1.3.1 wrote it).  The arenas keep their
+        addresses -- gradient views and captured graphs of a learner stay valid: the loaded moments are
+        copied into them."""
         super().load_state_dict(state_dict)
-        # torch re-materialises the state tensors; fold them back into the arenas on next use
-        members, self._members = self._members, None
-        if members is not None:
-            self._build(members)
+        if self._members is None:
+            return                                # folded into the arenas when they are built
+        if not any("exp_avg" in self.state[p] for p in self._members):
+            self._step = 0                        # a snapshot taken before the first step
+        for i, p in enumerate(self._members):
+            st = self.state[p]
+            if "exp_avg" in st:
+                self._m.view(i).copy_(st["exp_avg"])
+                self._v.view(i).copy_(st["exp_avg_sq"])
+                self._step = int(st["step"]) if not torch.is_tensor(st["step"]) else int(st["step"].item())
+            else:
+                self._m.view(i).zero_()
+                self._v.view(i).zero_()
+            st["step"] = torch.tensor(float(self._step))
+            st["exp_avg"], st["exp_avg_sq"] = self._m.view(i), self._v.view(i)
