@@ -437,6 +437,12 @@ def main():
         cpu = {"value": 16 / dtc, "unit": "frames/s", "cores": threads, "kind": "port",
                "sample": "4 steps of 8 quadruplets (of the 256-quadruplet workload), fp32 oracle port",
                "ms_per_step_b8": dtc * 1e3}
+        # also the reference's real batch (16, train_q_network.py:98) on all cores, and the
+        # as-shipped thread setting (torch.set_num_threads(1), :85)
+        dt16 = cpu_reference_arm(steps=3, warmup=1, batch=16, threads=threads)
+        dt1 = cpu_reference_arm(steps=2, warmup=1, batch=8, threads=1)
+        cpu["batch16_all_cores"] = {"value": 32 / dt16, "unit": "frames/s", "ms_per_step": dt16 * 1e3}
+        cpu["as_shipped_1_thread"] = {"value": 16 / dt1, "unit": "frames/s", "cores": 1, "ms_per_step_b8": dt1 * 1e3}
 
     if rank == 0 and a.detail and conv_detail:
         for k, v in sorted(conv_detail.items(), key=lambda kv: -kv[1][0] * kv[1][1]):
