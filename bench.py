@@ -411,6 +411,20 @@ def main():
             lt = tr.step(hk, hk1, hact)             # H2D of the fp32 pair batch (154 MB) + step
         _ = lt.item()
         train_e2e_ms = (time.perf_counter() - t0) / iters * 1e3
+        loss_f32 = float(lt.item())
+        # the same from uint8 HWC frames (decoder output; normalisation fused into the first kernel): 39 MB H2D
+        del tr
+        tr = InverseModelTrainer(isd, nb, lr=1e-4, device=dev, frames_uint8=True)
+        hu = torch.empty(nb, 224, 224, 3, dtype=torch.uint8, pin_memory=True).random_(0, 256)
+        hu1 = torch.empty(nb, 224, 224, 3, dtype=torch.uint8, pin_memory=True).random_(0, 256)
+        for _ in range(5):
+            tr.step(hu, hu1, hact)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(iters):
+            lt = tr.step(hu, hu1, hact)
+        _ = lt.item()
+        train_e2e_u8_ms = (time.perf_counter() - t0) / iters * 1e3
         run = InverseActionRunner(isd, nb, dev)
         for _ in range(3):
             run.label(dk, dk1)
@@ -424,9 +438,11 @@ def main():
         flop_pair = 7.31e9 + 0.116e9
         inverse = {"batch": nb, "train_step_ms": train_ms, "pairs_per_sec_device": nb / train_ms * 1e3,
                    "train_step_e2e_ms": train_e2e_ms, "pairs_per_sec_e2e": nb / train_e2e_ms * 1e3,
+                   "train_step_e2e_uint8_ms": train_e2e_u8_ms, "pairs_per_sec_e2e_uint8": nb / train_e2e_u8_ms * 1e3,
                    "train_tflops": flop_pair * nb / (train_ms * 1e-3) / 1e12,
                    "label_ms": label_ms, "pairs_per_sec_label": nb / label_ms * 1e3,
-                   "frames": "fp32 NCHW pairs (the reference loader's output)", "loss": float(lt.item())}
+                   "frames": "fp32 NCHW pairs (the reference loader's output); *_uint8: uint8 HWC pairs",
+                   "loss": loss_f32}
         del tr, run
 
     # ---------------- CPU baseline (rank 0, N = 1): bounded sample of the same workload

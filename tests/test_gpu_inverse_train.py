@@ -161,3 +161,26 @@ def test_inverse_training_reduces_loss_at_reference_batch_size():
     assert all(torch.isfinite(v).all() for v in tr.p.values())
     assert not torch.equal(keeps[0], keeps[1]) and not torch.equal(keeps[-1], keeps[-2])
     assert tr.steps_done == 40 and tr.step_dev.item() == 40
+
+
+def test_inverse_trainer_uint8_frames_equal_normalised_fp32_frames():
+    """uint8 HWC frames (normalisation fused into the first kernel) give the same step as the loader's
+    normalised fp32 NCHW frames (util/torch.py:5-12,26-36)."""
+    from oracle import qstep
+    from video_dqn_b200.inverse import InverseModelTrainer
+    dev = torch.device("cuda:0")
+    B = 4
+    g = torch.Generator().manual_seed(2)
+    ku8 = torch.randint(0, 256, (B, 224, 224, 3), generator=g, dtype=torch.uint8)
+    k1u8 = torch.randint(0, 256, (B, 224, 224, 3), generator=g, dtype=torch.uint8)
+    act = torch.randint(0, 3, (B,), generator=g)
+    keep = (torch.rand(B, 128, generator=g) >= 0.5).to(torch.uint8)
+    sd = oinv.init_state(seed=7)
+    a = InverseModelTrainer(sd, B, device=dev, frames_uint8=True, use_graph=False)
+    b = InverseModelTrainer(sd, B, device=dev, use_graph=False)
+    la = a.step(ku8.to(dev), k1u8.to(dev), act.to(dev), keep=keep).item()
+    lb = b.step(qstep.to_imgnet(ku8).to(dev), qstep.to_imgnet(k1u8).to(dev), act.to(dev), keep=keep).item()
+    assert abs(la - lb) <= 2e-3 * max(1.0, abs(lb)), (la, lb)
+    assert (a.y - b.y).abs().max().item() <= 5e-3 * max(1.0, b.y.abs().max().item())
+    with pytest.raises(ValueError):
+        a.step(qstep.to_imgnet(ku8).to(dev), qstep.to_imgnet(k1u8).to(dev), act.to(dev))

@@ -161,7 +161,11 @@ class InverseModelTrainer:
     (`model-N.pth`, :131-132).  CUDA only, no fallback."""
 
     def __init__(self, state_dict: Dict[str, torch.Tensor], batch_size: int, lr: float = 1e-4,
-                 weight_decay: float = 0.0, seed: int = 0, device=None, use_graph: bool = True):
+                 weight_decay: float = 0.0, seed: int = 0, device=None, use_graph: bool = True,
+                 frames_uint8: bool = False):
+        """frames_uint8: frames arrive as uint8 HWC [B,224,224,3] (decoder output; the ImageNet
+        normalisation of the reference's loader is then fused into the first kernel, 4x less H2D)
+        instead of the loader's normalised fp32 NCHW [B,3,224,224]."""
         from .optim import FlatArena
         dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         if dev.type != "cuda":
@@ -209,8 +213,9 @@ class InverseModelTrainer:
         self.dflat = e(B, 576, dt=f32)
         self.dx3, self.dx2, self.dx1 = e(B, 3, 3, 64), e(B, 5, 5, 256), e(B, 7, 7, 256)
         # static inputs (graph replay reads these)
-        self.k = torch.zeros(B, 3, 224, 224, device=dev, dtype=f32)
-        self.k1 = torch.zeros(B, 3, 224, 224, device=dev, dtype=f32)
+        fshape, fdt = ((B, 224, 224, 3), torch.uint8) if frames_uint8 else ((B, 3, 224, 224), f32)
+        self.k = torch.zeros(fshape, device=dev, dtype=fdt)
+        self.k1 = torch.zeros(fshape, device=dev, dtype=fdt)
         self.act = torch.zeros(B, device=dev, dtype=torch.int64)
         self.loss = torch.zeros(1, device=dev, dtype=f32)
         self.correct = torch.zeros(1, device=dev, dtype=torch.int32)
@@ -316,10 +321,10 @@ class InverseModelTrainer:
 
     # ------------------------------------------------------------------ public API
     def _load(self, k, k_plus_one, act):
-        if k.shape[0] != self.B or k_plus_one.shape != k.shape or act.numel() != self.B:
+        if k.shape != self.k.shape or k_plus_one.shape != k.shape or act.numel() != self.B:
             raise ValueError("bad shape")
         if k.dtype != self.k.dtype:
-            raise ValueError("frames must be fp32 NCHW (the reference loader's output)")
+            raise ValueError(f"frames must be {self.k.dtype} (see frames_uint8)")
         self.k.copy_(k, non_blocking=True)
         self.k1.copy_(k_plus_one, non_blocking=True)
         self.act.copy_(act.view(-1), non_blocking=True)
