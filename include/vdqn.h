@@ -274,6 +274,39 @@ int vdqn_dropout_mask(uint8_t* keep, int64_t n, float p, uint64_t seed, uint64_t
 int vdqn_dropout_apply(const float* x, const uint8_t* keep, float scale, float* y, int64_t n, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Train-mode BatchNorm2d for the `basic` architecture (ARCHITECTURE != 'extra_capacity'): `set_train()`
+ * leaves its trunk BatchNorms in train mode (archs/HabitatDQNMultiAction.py:37-40), so `model(before)`
+ * and `model(after)` (train_q_network.py:131,142) normalise with BATCH statistics and update the running
+ * ones (torch.nn.BatchNorm2d: momentum 0.1, eps 1e-5, unbiased running variance).  Activations are
+ * NHWC bf16 viewed as [M = N*H*W, C], C % 8 == 0; statistics fp32, their sums fp64.
+ *
+ *   vdqn_bn_stats       sums[0:C] = sum_m x[m,c],  sums[C:2C] = sum_m x[m,c]^2   (the call zeroes sums)
+ *   vdqn_bn_finalize    mean = sums/M, var = sumsq/M - mean^2 (biased), rstd = 1/sqrt(var + eps);
+ *                       scale = gamma*rstd, shift = beta - mean*scale;
+ *                       if running_mean != NULL: running_mean = (1-mom)*running_mean + mom*mean,
+ *                       running_var = (1-mom)*running_var + mom*var*M/(M-1); if nbt != NULL: ++*nbt
+ *   vdqn_bn_apply       y = x*scale[c] + shift[c] (+ residual) (ReLU if relu), bf16
+ *   vdqn_bn_bwd_reduce  sums[0:C] = sum_m dy, sums[C:2C] = sum_m dy * xhat,  xhat = (x - mean)*rstd
+ *   vdqn_bn_bwd_apply   dgamma = sums[C:2C], dbeta = sums[0:C] (fp32, overwritten);
+ *                       dx = gamma*rstd * (dy - dbeta/M - xhat*dgamma/M), bf16
+ * dy is the gradient w.r.t. the BatchNorm OUTPUT (already masked by the following ReLU).
+ *   vdqn_avgpool_bwd    dfeat[n,p,c] = feat[n,p,c] > 0 ? dpooled[n,c] / P : 0  (AdaptiveAvgPool2d(1) after the
+ *                       last block's ReLU, archs/HabitatDQNMultiAction.py:33) */
+int vdqn_bn_stats(const void* x, double* sums, int64_t M, int32_t C, void* stream);
+int vdqn_bn_finalize(const double* sums, int64_t M, int32_t C, const float* gamma, const float* beta,
+                     float* running_mean, float* running_var, int64_t* num_batches_tracked, float momentum,
+                     float eps, float* mean, float* rstd, float* scale, float* shift, void* stream);
+int vdqn_bn_apply(const void* x, const float* scale, const float* shift, const void* residual, int32_t relu,
+                  void* y, int64_t M, int32_t C, void* stream);
+int vdqn_bn_bwd_reduce(const void* dy, const void* x, const float* mean, const float* rstd, double* sums,
+                       int64_t M, int32_t C, void* stream);
+int vdqn_bn_bwd_apply(const void* dy, const void* x, const float* mean, const float* rstd, const float* gamma,
+                      const double* sums, float* dgamma, float* dbeta, void* dx, int64_t M, int32_t C,
+                      void* stream);
+int vdqn_avgpool_bwd(const float* dpooled, const void* feat, void* dfeat, int32_t N, int32_t P, int32_t C,
+                     void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Fused multi-tensor Adam (+ optional hard target-network sync in the same pass).
  * Replaces optim.Adam.step (train_q_network.py:124,227; ~550 launches under torch 1.3.1)
  * and target_net.load_state_dict(model.state_dict()) (:215-216).

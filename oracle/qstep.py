@@ -396,3 +396,96 @@ def to_imgnet(im_u8_hwc: torch.Tensor) -> torch.Tensor:
     x = x.permute(0, 3, 1, 2)
     x = x - torch.tensor(IMAGENET_MEAN).view(1, 3, 1, 1)
     return x / torch.tensor(IMAGENET_STD).view(1, 3, 1, 1)
+
+
+# ----------------------------------------------------------------------------
+# `basic` architecture, training step
+# ----------------------------------------------------------------------------
+BN_MOMENTUM = 0.1
+
+
+def _bn_train(x, sd, p):
+    """BatchNorm2d in TRAIN mode: batch statistics, running statistics updated in place (momentum 0.1,
+    unbiased variance), num_batches_tracked incremented (torch.nn.BatchNorm2d.forward)."""
+    key = p + ".num_batches_tracked"
+    if key in sd:
+        sd[key] += 1
+    return F.batch_norm(x, sd[p + ".running_mean"], sd[p + ".running_var"], sd[p + ".weight"], sd[p + ".bias"],
+                        True, BN_MOMENTUM, BN_EPS)
+
+
+def trunk_forward_bn_train(sd: Dict[str, torch.Tensor], x: torch.Tensor) -> torch.Tensor:
+    """ResNet-18 children()[:-2] with TRAIN-mode BN (what `set_train()` leaves the `basic` architecture
+    in: archs/HabitatDQNMultiAction.py:37-40 only freezes the trunk for extra_capacity).  Mutates the
+    running statistics in `sd`."""
+    y = F.conv2d(x, sd["resnet.conv1.weight"], None, 2, 3)
+    y = F.relu(_bn_train(y, sd, "resnet.bn1"))
+    y = F.max_pool2d(y, 3, 2, 1)
+    for li, (_, _cin, _cout, stride, ds) in enumerate(_STAGES, start=1):
+        for b in range(2):
+            p = f"resnet.layer{li}.{b}."
+            s = stride if b == 0 else 1
+            o = F.conv2d(y, sd[p + "conv1.weight"], None, s, 1)
+            o = F.relu(_bn_train(o, sd, p + "bn1"))
+            o = F.conv2d(o, sd[p + "conv2.weight"], None, 1, 1)
+            o = _bn_train(o, sd, p + "bn2")
+            if ds and b == 0:
+                idn = F.conv2d(y, sd[p + "downsample.0.weight"], None, s, 0)
+                idn = _bn_train(idn, sd, p + "downsample.1")
+            else:
+                idn = y
+            y = F.relu(o + idn)
+    return y
+
+
+def q_forward_basic_train(sd, x, action_dim: int = 3):
+    """Q[B,5,A] of the single-frame `basic` architecture with train-mode BN (mutates running stats)."""
+    f = trunk_forward_bn_train(sd, x).mean(dim=(2, 3))
+    return F.linear(f, sd["top.weight"], sd["top.bias"]).view(-1, NUM_CLASSES, action_dim)
+
+
+def grad_param_names_basic() -> List[str]:
+    """The 62 tensors of the `basic` architecture that receive gradients, `model.parameters()` order."""
+    return trunk_param_names() + ["top.weight", "top.bias"]
+
+
+class BasicOracleTrainer:
+    """One iteration of the reference loop body (train_q_network.py:211-229) for ARCHITECTURE != 
+    'extra_capacity': `model(before)` and `model(after)` run the trunk BatchNorms in train mode (in
+    that order: both update the running statistics, :131,142), `target_net(after)` in eval mode
+    (:122,140), backward through `model(before)`, Adam."""
+
+    def __init__(self, sd: Dict[str, torch.Tensor], cfg: StepConfig | None = None):
+        self.cfg = cfg or StepConfig()
+        self.sd = {k: v.clone() for k, v in sd.items()}
+        self.target = {k: v.clone() for k, v in self.sd.items()}
+        self.names = grad_param_names_basic()
+        self.exp_avg = {n: torch.zeros_like(self.sd[n]) for n in self.names}
+        self.exp_avg_sq = {n: torch.zeros_like(self.sd[n]) for n in self.names}
+        self.t = 0
+        self.betas, self.eps = (0.9, 0.999), 1e-8
+
+    def sync_target(self):
+        self.target = {k: v.clone() for k, v in self.sd.items()}
+
+    def loss_and_grads(self, batch):
+        before, after, act, rew, term, _gt, valid_mask = batch
+        leaves = {n: self.sd[n].detach().clone().requires_grad_(True) for n in self.names}
+        sd = dict(self.sd)                      # buffers are shared: running stats update self.sd
+        sd.update(leaves)
+        A = self.cfg.action_dim
+        q_s = q_forward_basic_train(sd, before, A)
+        with torch.no_grad():
+            q_nt = q_forward_basic(self.target, after, A)
+            q_no = q_forward_basic_train(sd, after, A)
+        loss, aux = td_loss(q_s, q_no, q_nt, act, rew, term, valid_mask, self.cfg)
+        grads = torch.autograd.grad(loss, [leaves[n] for n in self.names])
+        aux.update(q_s=q_s.detach(), q_next_online=q_no, q_next_target=q_nt)
+        return loss.detach(), dict(zip(self.names, grads)), aux
+
+    adam = OracleTrainer.adam
+
+    def step(self, batch):
+        loss, grads, aux = self.loss_and_grads(batch)
+        self.adam(grads)
+        return loss, grads, aux

@@ -1,0 +1,197 @@
+"""training step of the `basic` architecture (trunk BatchNorms in TRAIN mode) on the CUDA
+path against the CPU oracle (oracle/qstep.py:BasicOracleTrainer, bit-identical to the reference's own
+module + process_batch + Adam: tests/golden/basic_train_b8.npz).  Needs a B200.
+
+Tolerances: the train-mode BatchNorm kernels alone vs torch fp32 on the same bf16 inputs: 1e-2 relative
+to the output scale (bf16 output rounding), statistics 1e-5; the full step: the Q-learning step's bars
+(Q 1e-2 relative to max(1,|Q|), loss 5e-3 relative... see each assert)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import qstep
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _cos(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return (a @ b / (a.norm() * b.norm() + 1e-30)).item()
+
+
+@pytest.mark.parametrize("shape", [(2, 7, 7, 512), (3, 28, 28, 128), (4, 56, 56, 64), (1, 5, 3, 256)])
+def test_train_mode_batchnorm_kernels_match_torch(shape):
+    from video_dqn_b200 import ops
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(sum(shape))
+    C = shape[-1]
+    x = (torch.randn(*shape, generator=g) * 1.7 + 0.4).to(torch.bfloat16)
+    res = torch.randn(*shape, generator=g).to(torch.bfloat16)
+    gamma, beta = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.1
+    rm, rv = torch.randn(C, generator=g) * 0.1, torch.rand(C, generator=g) + 0.5
+    nbt = torch.tensor(3, dtype=torch.int64)
+    # torch reference on the same bf16 values, NCHW fp32
+    xr = x.float().permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    rm_ref, rv_ref = rm.clone(), rv.clone()
+    y_ref = F.relu(F.batch_norm(xr, rm_ref, rv_ref, gr, br, True, 0.1, 1e-5) + res.float().permute(0, 3, 1, 2))
+    dy = (torch.randn(*shape, generator=g) * 0.01).to(torch.bfloat16)
+    st = ops.BnBatchStats(C, dev)
+    d = lambda t: t.to(dev)  # noqa: E731
+    rm_d, rv_d, nbt_d = d(rm), d(rv), d(nbt)
+    y = torch.empty(*shape, device=dev, dtype=torch.bfloat16)
+    ops.bn_train_fwd(d(x), st, d(gamma), d(beta), rm_d, rv_d, nbt_d, y, residual=d(res), relu=True)
+    torch.cuda.synchronize()
+    M = x.numel() // C
+    assert torch.allclose(st.mean.cpu(), x.float().reshape(M, C).mean(0), atol=1e-5, rtol=1e-5)
+    assert torch.allclose(rm_d.cpu(), rm_ref, atol=1e-6, rtol=1e-5) and torch.allclose(rv_d.cpu(), rv_ref, atol=1e-6, rtol=1e-5)
+    assert nbt_d.item() == 4
+    y_nhwc = y_ref.detach().permute(0, 2, 3, 1)
+    assert (y.float().cpu() - y_nhwc).abs().max().item() <= 1e-2 * max(1.0, y_nhwc.abs().max().item())
+    # backward: gradient w.r.t. the BatchNorm output = dy masked by the ReLU (as the conv epilogue hands it over)
+    mask = (y_nhwc > 0)
+    dym = (dy.float() * mask).to(torch.bfloat16)
+    y_ref.backward(dym.float().permute(0, 3, 1, 2))
+    dgamma, dbeta = torch.empty(C, device=dev), torch.empty(C, device=dev)
+    dx = torch.empty(*shape, device=dev, dtype=torch.bfloat16)
+    ops.bn_train_bwd(d(dym), d(x), st, d(gamma), dgamma, dbeta, dx)
+    torch.cuda.synchronize()
+    assert torch.allclose(dbeta.cpu(), br.grad, rtol=1e-4, atol=1e-6)
+    assert torch.allclose(dgamma.cpu(), gr.grad, rtol=1e-3, atol=1e-5)
+    dx_ref = xr.grad.permute(0, 2, 3, 1)
+    assert (dx.float().cpu() - dx_ref).abs().max().item() <= 1e-2 * dx_ref.abs().max().item() + 1e-7
+    # no running-statistics update when asked not to
+    ops.bn_train_fwd(d(x), st, d(gamma), d(beta), rm_d, rv_d, nbt_d, y, update_running=False)
+    torch.cuda.synchronize()
+    assert nbt_d.item() == 4 and torch.allclose(rm_d.cpu(), rm_ref, atol=1e-6, rtol=1e-5)
+    with pytest.raises(ValueError):
+        ops.bn_train_fwd(d(x)[..., :4].contiguous(), ops.BnBatchStats(4, dev), d(gamma)[:4], d(beta)[:4], rm_d[:4],
+                         rv_d[:4], None, y[..., :4].contiguous())
+
+
+def test_avgpool_bwd_kernel():
+    from video_dqn_b200 import ops
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(0)
+    feat = torch.randn(3, 7, 7, 512, generator=g).clamp_min(0).to(torch.bfloat16)
+    dp = torch.randn(3, 512, generator=g)
+    out = ops.avgpool_bwd(dp.to(dev), feat.to(dev)).float().cpu()
+    ref = ((feat.float() > 0) * (dp / 49).view(3, 1, 1, 512)).to(torch.bfloat16).float()
+    assert torch.equal(out, ref)
+
+
+def _build(sd, dev):
+    from video_dqn_b200.qnet import HabitatDQNMultiAction
+    m = HabitatDQNMultiAction(3, 5, extra_capacity=False, panorama=False)
+    res = m.load_state_dict(sd, strict=False)
+    assert not res.unexpected_keys and all(k.endswith("num_batches_tracked") for k in res.missing_keys)
+    return m.to(dev)
+
+
+def test_basic_architecture_training_step_matches_oracle():
+    """Bars (bf16 operands and bf16 raw conv outputs, normalised with the batch statistics of B = 8
+    frames -- 392 values per channel in layer 4 -- vs the fp32 oracle): Q max-abs <= 2e-2 * max(1, |Q|max)
+    (measured 1.6e-2 on |Q| <= 1.5), loss 3e-2 relative, gradients per-tensor cosine >= 0.82 and global
+    rel-L2 <= 0.35, running statistics 2e-2 of their largest entry, num_batches_tracked exact.
+    The gradient bars are calibrated on what PyTorch's OWN bf16 autocast gives for this very step against
+    its fp32 run (oracle/probe_basic_bf16.py: max |dQ| 1.2e-2, global rel-L2 0.296, worst cosine 0.881,
+    median 0.937; the CUDA path measures 1.6e-2 / 0.29 / 0.866): the batch-statistics BatchNorm backward
+    subtracts the per-channel mean of dy, so bf16 rounding of dy is amplified wherever that mean
+    dominates, and the loss compounds over the 20 BatchNorms down to the stem.  The kernels themselves
+    are pinned tightly (1e-2 of the output scale, statistics 1e-5) in
+    test_train_mode_batchnorm_kernels_match_torch."""
+    from video_dqn_b200.learner import StepConfig
+    from video_dqn_b200.learner_basic import BasicQLearner, grad_param_names_basic
+    dev = torch.device("cuda:0")
+    torch.set_num_threads(os.cpu_count() or 1)
+    z = np.load(os.path.join(GOLD, "basic_train_b8.npz"))
+    B = int(z["meta/B"])
+    sd = qstep.init_state_basic(seed=4, num_frames=1)
+    oracle = qstep.BasicOracleTrainer(sd)
+    names = grad_param_names_basic()
+    assert names == oracle.names
+    model, target = _build(sd, dev), _build(sd, dev)
+    lr = BasicQLearner(model, target, StepConfig(), batch_size=B)
+    mp = dict(model.named_parameters())
+    mb = dict(model.named_buffers())
+    bad, report = [], []
+
+    def check(ok, msg):
+        report.append(("ok   " if ok else "FAIL ") + msg)
+        if not ok:
+            bad.append(msg)
+
+    for it in range(int(z["meta/steps"])):
+        batch = qstep.synthetic_batch(B, seed=1 + it)
+        # the oracle starts every step from the GPU's current parameters and running statistics (Adam's
+        # sign-normalised update amplifies bf16 noise into the trajectory; see test_gpu_parity.py)
+        for n in names:
+            oracle.sd[n].copy_(mp[n].detach().cpu())
+        for k, v in mb.items():
+            if k.startswith("resnet.") and k in oracle.sd:
+                oracle.sd[k].copy_(v.detach().cpu())
+        loss_ref, grads_ref, aux = oracle.loss_and_grads(batch)
+        loss = lr.step(batch)
+        torch.cuda.synchronize()
+        scale = max(1.0, aux["q_s"].abs().max().item())
+        for tag, got, ref in (("q_s", lr.ws_s.q.view(B, 5, 3).cpu(), aux["q_s"]),
+                              ("q_next_online", lr.ws_next.q.view(B, 5, 3).cpu(), aux["q_next_online"]),
+                              ("q_next_target", lr.q_next_target.cpu(), aux["q_next_target"])):
+            e = (got - ref).abs().max().item()
+            check(e <= 2e-2 * scale, f"step {it} {tag}: max-abs {e:.4f} (scale {scale:.2f})")
+        e = abs(loss.item() - loss_ref.item()) / abs(loss_ref.item())
+        check(e <= 3e-2, f"step {it} loss {loss.item():.5f} vs oracle {loss_ref.item():.5f}: rel {e:.4f}")
+        if it == 0:
+            e = abs(loss.item() - float(z["step0/loss"])) / float(z["step0/loss"])
+            check(e <= 3e-2, f"step 0 loss vs the reference's own number: rel {e:.4f}")
+        num = den = 0.0
+        worst = (2.0, "")
+        for n in names:
+            g = lr.G[n].detach().cpu()
+            check(bool(torch.isfinite(g).all()), f"step {it} {n} finite") if not torch.isfinite(g).all() else None
+            c = _cos(g, grads_ref[n])
+            worst = min(worst, (c, n))
+            floor = 0.82
+            if c < floor:
+                check(False, f"step {it} {n}: cosine {c:.4f} < {floor}")
+            num += (g.double() - grads_ref[n].double()).pow(2).sum().item()
+            den += grads_ref[n].double().pow(2).sum().item()
+        rel = (num / den) ** 0.5
+        check(rel <= 0.35, f"step {it} gradient global rel-L2 {rel:.4f}, worst cosine {worst[0]:.4f} ({worst[1]})")
+        # running statistics after the step's TWO train-mode forwards (oracle.sd was updated in place)
+        wb = (0.0, "")
+        for k, v in mb.items():
+            if k.endswith("running_mean") or k.endswith("running_var"):
+                ref = oracle.sd[k]
+                wb = max(wb, ((v.cpu() - ref).abs().max().item() / max(1e-3, ref.abs().max().item()), k))
+        check(wb[0] <= 2e-2, f"step {it} running statistics worst rel deviation {wb[0]:.5f} ({wb[1]})")
+        check(int(mb["resnet.bn1.num_batches_tracked"]) == 2 * (it + 1), f"step {it} num_batches_tracked")
+    # the module's eval forward sees the trained parameters and statistics
+    model.eval()
+    x = qstep.synthetic_batch(B, seed=9)[0]
+    with torch.no_grad():
+        q = model(x.to(dev)).cpu()
+        for n in names:
+            oracle.sd[n].copy_(mp[n].detach().cpu())
+        for k, v in mb.items():
+            if k in oracle.sd:
+                oracle.sd[k].copy_(v.detach().cpu())
+        q_ref = qstep.q_forward_basic(oracle.sd, x)
+    e = (q - q_ref).abs().max().item()
+    check(e <= 1e-2 * max(1.0, q_ref.abs().max().item()), f"eval forward after training: max-abs {e:.4f}")
+    print("\n".join(report))
+    os.makedirs(os.path.join(os.path.dirname(GOLD), "..", "gpurun_out"), exist_ok=True)
+    with open(os.path.join(os.path.dirname(GOLD), "..", "gpurun_out", "basic_train_report.txt"), "w") as f:
+        f.write("\n".join(report) + "\n")
+    assert not bad, "\n".join(report)
+    with pytest.raises(ValueError):
+        QLearnerBasicMisuse = BasicQLearner(_build_extra(dev), _build_extra(dev))   # noqa: F841
+
+
+def _build_extra(dev):
+    from video_dqn_b200.qnet import HabitatDQNMultiAction
+    return HabitatDQNMultiAction(3, 5, extra_capacity=True, panorama=False).to(dev)

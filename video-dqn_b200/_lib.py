@@ -84,6 +84,13 @@ EXPORTS = {
     "vdqn_head_flatten_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "vdqn_td_epilogue": (c_int, [C.POINTER(TdDesc), c_void_p]),
     "vdqn_q_max": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
+    "vdqn_bn_stats": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p]),
+    "vdqn_bn_finalize": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float,
+                                 c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "vdqn_bn_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int64, c_int, c_void_p]),
+    "vdqn_bn_bwd_reduce": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
+    "vdqn_bn_bwd_apply": (c_int, [c_void_p] * 9 + [c_int64, c_int, c_void_p]),
+    "vdqn_avgpool_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "vdqn_cross_entropy": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float,
                                    c_void_p]),
     "vdqn_dropout_mask": (c_int, [c_void_p, c_int64, c_float, C.c_uint64, C.c_uint64, c_void_p]),

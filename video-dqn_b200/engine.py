@@ -142,9 +142,12 @@ def wgrad_splits(spec: ConvSpec, n_img: int, sms: int = 0) -> int:
 class PreparedWeights:
     """bf16 GEMM operands + fp32 shifts for every conv, regenerated from the fp32 masters."""
 
-    def __init__(self, plan: NetPlan, device, trunk_only: bool = False):
-        """trunk_only: the ResNet trunk alone (the inverse-dynamics model reuses it under its own head)"""
+    def __init__(self, plan: NetPlan, device, trunk_only: bool = False, fold_bn: bool = True):
+        """trunk_only: the ResNet trunk alone (the inverse-dynamics model reuses it under its own head).
+        fold_bn=False: plain bf16 casts of the weights (scale 1, shift 0) -- the train-mode BatchNorm path
+        of the `basic` architecture normalises with batch statistics in separate kernels."""
         self.plan = plan
+        self.fold_bn = fold_bn
         self.w_fwd: Dict[str, torch.Tensor] = {}
         self.w_dgrad: Dict[str, torch.Tensor] = {}
         self.shift: Dict[str, torch.Tensor] = {}
@@ -172,7 +175,7 @@ class PreparedWeights:
                 w = P[c.wkey]
                 d.w, d.w_fwd, d.shift = w.data_ptr(), self.w_fwd[c.name].data_ptr(), self.shift[c.name].data_ptr()
                 d.w_dgrad = L.ptr(self.w_dgrad.get(c.name))
-                if c.bn is not None:
+                if c.bn is not None and self.fold_bn:
                     d.gamma, d.beta = P[c.bn + ".weight"].data_ptr(), P[c.bn + ".bias"].data_ptr()
                     d.mean, d.var = P[c.bn + ".running_mean"].data_ptr(), P[c.bn + ".running_var"].data_ptr()
                 if c.bias is not None:

@@ -1,0 +1,260 @@
+"""Training step of the `basic` architecture (ARCHITECTURE != 'extra_capacity').
+
+`HabitatDQNMultiAction(..., extra_capacity=False)` is trunk + AdaptiveAvgPool2d(1) + one Linear
+(archs/HabitatDQNMultiAction.py:32-34).  `set_train()` only freezes the trunk for extra_capacity
+(:37-40), so here the 20 trunk BatchNorms run in TRAIN mode inside the loop body of
+train_q_network.py:211-229:
+
+    model(before)       batch statistics of `before`, running statistics updated, graph kept    (:131)
+    target_net(after)   eval mode (running statistics of the target copy)                        (:122,140)
+    model(after)        batch statistics of `after`, running statistics updated AGAIN            (:142)
+    TD loss, backward through model(before) with the batch-statistics BatchNorm backward, Adam
+
+Batch statistics depend on the conv OUTPUT, so BatchNorm cannot be folded into the conv weights as on
+the shipped (eval-mode) path: every conv runs on the tensor-core kernels with plain bf16 weights and
+writes its raw output; `bn_stats -> bn_finalize -> bn_apply` (csrc/batchnorm.cu, HBM-bound) normalise
+it (+ residual, + ReLU); the backward inserts `bn_bwd_reduce -> bn_bwd_apply` between the data
+gradient of the layer above and the weight / data gradient of the conv below.  Single frame (F = 1)
+only: with F frames the reference pushes each frame through the trunk separately (:49-51), i.e. F
+separate sets of batch statistics per forward.  One process (no SyncBN: the reference has no
+data-parallel mode).  Eager launches, no CUDA graph.  CUDA only, no fallback.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+
+from . import engine as E
+from . import ops
+from .learner import StepConfig
+from .optim import FusedAdam
+from .qnet import HabitatDQNMultiAction
+
+bf16 = torch.bfloat16
+
+
+def grad_param_names_basic() -> List[str]:
+    """The 62 tensors that receive gradients, `model.parameters()` order (resnet.fc.* never get one)."""
+    from .qnet import grad_param_names
+    return [n for n in grad_param_names() if n.startswith("resnet.")] + ["top.weight", "top.bias"]
+
+
+class BnTrainWorkspace:
+    """Raw conv outputs, normalised activations and per-BatchNorm batch statistics of one train-mode
+    forward over `n` frames; with `train` also the gradient buffers of its backward."""
+
+    def __init__(self, plan: E.NetPlan, n: int, device, train: bool):
+        self.n, self.train = n, train
+        e = lambda *s, dt=bf16: torch.empty(*s, device=device, dtype=dt)  # noqa: E731
+        z = lambda *s, dt=bf16: torch.zeros(*s, device=device, dtype=dt)  # noqa: E731
+        self.xp = e(n, 112, 112, 16)
+        self.s_raw, self.s = e(n, 112, 112, 64), e(n, 112, 112, 64)
+        self.idx = e(n, 56, 56, 64, dt=torch.uint8) if train else None
+        self.p = e(n, 56, 56, 64)
+        self.c1_raw, self.a1, self.c2_raw, self.ds_raw, self.idn, self.out = [], [], [], [], [], []
+        for b in plan.blocks:
+            shp = (n, b.out_hw, b.out_hw, b.cout)
+            self.c1_raw.append(e(*shp)); self.a1.append(e(*shp)); self.c2_raw.append(e(*shp)); self.out.append(e(*shp))
+            self.ds_raw.append(e(*shp) if b.ds is not None else None)
+            self.idn.append(e(*shp) if b.ds is not None else None)
+        self.stats: Dict[str, ops.BnBatchStats] = {c.bn: ops.BnBatchStats(c.cout, device) for c in plan.convs
+                                                   if c.bn is not None}
+        f32 = torch.float32
+        self.pooled = e(n, 512, dt=f32)
+        self.q = e(n, plan.num_classes * plan.action_dim, dt=f32)
+        if train:
+            self.dpooled = e(n, 512, dt=f32)
+            self.dy_out = {b.out_hw: (e(n, b.out_hw, b.out_hw, b.cout), e(n, b.out_hw, b.out_hw, b.cout))
+                           for b in plan.blocks}
+            self.dy_a1 = {b.out_hw: e(n, b.out_hw, b.out_hw, b.cout) for b in plan.blocks}
+            self.d_c2 = {b.out_hw: e(n, b.out_hw, b.out_hw, b.cout) for b in plan.blocks}
+            self.d_ds = {b.out_hw: e(n, b.out_hw, b.out_hw, b.cout) for b in plan.blocks if b.ds is not None}
+            self.r_dil = {b.out_hw: z(n, b.in_hw, b.in_hw, b.cin) for b in plan.blocks if b.stride == 2}
+            self.dy_p = e(n, 56, 56, 64)
+            self.dy_s = e(n, 112, 112, 64)
+            convs = [c for c in plan.convs if c.name != "head"]
+            self.part = e(max(E.wgrad_splits(c, n) * c.cout * c.K for c in convs), dt=f32)
+
+
+def _bn(ws: BnTrainWorkspace, P, c: E.ConvSpec, x_raw, y, *, residual=None, relu=False, update_running=True):
+    p = c.bn
+    return ops.bn_train_fwd(x_raw, ws.stats[p], P[p + ".weight"], P[p + ".bias"], P[p + ".running_mean"],
+                            P[p + ".running_var"], P.get(p + ".num_batches_tracked"), y, residual=residual,
+                            relu=relu, momentum=0.1, eps=E.BN_EPS, update_running=update_running)
+
+
+def forward_bn_train(plan: E.NetPlan, W: E.PreparedWeights, P: Dict[str, torch.Tensor], ws: BnTrainWorkspace,
+                     update_running: bool = True) -> torch.Tensor:
+    """Train-mode forward from the packed input ws.xp -> Q [n, classes*actions] fp32.  `W` must hold
+    UNFOLDED weights (PreparedWeights(fold_bn=False))."""
+    assert not W.fold_bn
+    # shift = 0 for unfolded weights; it is passed so the launches take the same (tested) epilogue variants
+    # as the folded path
+    conv = lambda c, x, out: ops.conv_gemm(x, W.w_fwd[c.name], c.stride, c.pad_lo, c.pad_hi,  # noqa: E731
+                                           shift=W.shift[c.name], out=out)
+    kw = dict(update_running=update_running)
+    conv(plan.stem, ws.xp, ws.s_raw)
+    _bn(ws, P, plan.stem, ws.s_raw, ws.s, relu=True, **kw)
+    ops.maxpool_fwd(ws.s, ws.p, ws.idx)
+    x = ws.p
+    for i, b in enumerate(plan.blocks):
+        conv(b.conv1, x, ws.c1_raw[i])
+        _bn(ws, P, b.conv1, ws.c1_raw[i], ws.a1[i], relu=True, **kw)
+        conv(b.conv2, ws.a1[i], ws.c2_raw[i])
+        idn = x
+        if b.ds is not None:
+            conv(b.ds, x, ws.ds_raw[i])
+            idn = _bn(ws, P, b.ds, ws.ds_raw[i], ws.idn[i], **kw)
+        # torchvision BasicBlock: bn2 before the downsample branch's BatchNorm (resnet.py:89-105) -- the
+        # order only matters for nothing observable (independent layers), kept for readability
+        _bn(ws, P, b.conv2, ws.c2_raw[i], ws.out[i], residual=idn, relu=True, **kw)
+        x = ws.out[i]
+    ops.avgpool_fwd(x, ws.pooled)
+    ops.linear_fwd(ws.pooled, P["top.weight"], P["top.bias"], False, ws.q)
+    return ws.q
+
+
+def _wgrad_raw(ws: BnTrainWorkspace, P, G, c: E.ConvSpec, x, dy):
+    splits = E.wgrad_splits(c, ws.n)
+    part = ws.part[: splits * c.cout * c.K]
+    ops.conv_wgrad(x, dy, c.k, c.k, c.stride, c.pad_lo, c.pad_hi, splits=splits, part=part,
+                   algo=2 if E.wgrad_uses_halo(c) else 0)
+    ops.wgrad_finalize(part, P[c.wkey], G[c.wkey], splits=splits, Cout=c.cout, Cin=c.gemm_cin, R=c.k, S=c.k,
+                       K=c.K, kmap=c.kmap)
+
+
+def _bn_bwd(ws: BnTrainWorkspace, P, G, c: E.ConvSpec, dy, x_raw, dx):
+    p = c.bn
+    return ops.bn_train_bwd(dy, x_raw, ws.stats[p], P[p + ".weight"], G[p + ".weight"], G[p + ".bias"], dx)
+
+
+def backward_bn_train(plan: E.NetPlan, W: E.PreparedWeights, P, G, ws: BnTrainWorkspace, dq: torch.Tensor):
+    """dq [n, classes*actions] fp32 (overwritten) -> every parameter gradient in G."""
+    ops.linear_bwd(ws.pooled, P["top.weight"], None, dq, G["top.weight"], G["top.bias"], False, dx=ws.dpooled)
+    last = plan.blocks[-1]
+    ci = 0
+    cur = ws.dy_out[last.out_hw][ci]
+    ops.avgpool_bwd(ws.dpooled, ws.out[-1], cur)           # d loss / d (block sum), masked by the block's ReLU
+    for i in range(len(plan.blocks) - 1, -1, -1):
+        b = plan.blocks[i]
+        x_in = ws.out[i - 1] if i > 0 else ws.p
+        prev = plan.blocks[i - 1] if i > 0 else None
+        # bn2 -> conv2
+        d_c2 = _bn_bwd(ws, P, G, b.conv2, cur, ws.c2_raw[i], ws.d_c2[b.out_hw])
+        _wgrad_raw(ws, P, G, b.conv2, ws.a1[i], d_c2)
+        dy_a1 = ws.dy_a1[b.out_hw]
+        ops.conv_gemm(d_c2, W.w_dgrad[b.conv2.name], 1, 1, 1, mask_src=ws.a1[i], out=dy_a1,
+                      tile_n=E._dgrad_tile_n(b.cout))
+        # bn1 (in place: dy_a1 becomes the gradient w.r.t. conv1's raw output)
+        d_c1 = _bn_bwd(ws, P, G, b.conv1, dy_a1, ws.c1_raw[i], dy_a1)
+        # identity / downsample branch
+        if b.ds is not None:
+            d_ds = _bn_bwd(ws, P, G, b.ds, cur, ws.ds_raw[i], ws.d_ds[b.out_hw])
+            _wgrad_raw(ws, P, G, b.ds, x_in, d_ds)
+            res = ws.r_dil[b.out_hw]
+            ops.conv_gemm(d_ds, W.w_dgrad[b.ds.name], 1, 0, 0, out=res, out_scatter=2,
+                          tile_n=E._scatter_tile_n(b.cin))
+        else:
+            res = cur
+        _wgrad_raw(ws, P, G, b.conv1, x_in, d_c1)
+        if prev is not None:
+            ni = (1 - ci) if prev.out_hw == b.out_hw else 0
+            dst, mask = ws.dy_out[prev.out_hw][ni], x_in
+        else:
+            ni, dst, mask = 0, ws.dy_p, None
+        if b.stride == 2:
+            for pa, pb, wf in E.parity_filters(W, b.conv1):
+                ops.conv_gemm(d_c1, wf, 1, 0, wf.shape[1] - 1, pad_hi_w=wf.shape[2] - 1, residual=res,
+                              mask_src=mask, out=dst, out_scatter=2, scatter_off=(pa, pb),
+                              scatter_inputs=True, tile_n=E._scatter_tile_n(b.cin))
+        else:
+            ops.conv_gemm(d_c1, W.w_dgrad[b.conv1.name], 1, 1, 1, residual=res, mask_src=mask, out=dst,
+                          tile_n=E._dgrad_tile_n(b.cin))
+        cur, ci = dst, ni
+    # max-pool (routes through the arg-max and applies the stem ReLU mask), stem BatchNorm, stem conv
+    ops.maxpool_bwd(ws.dy_p, ws.idx, ws.p, ws.dy_s, colsum=None)
+    _bn_bwd(ws, P, G, plan.stem, ws.dy_s, ws.s_raw, ws.dy_s)
+    _wgrad_raw(ws, P, G, plan.stem, ws.xp, ws.dy_s)
+
+
+class BasicQLearner:
+    """`learner.step(batch)` = one iteration of train_q_network.py:211-229 for the `basic` architecture
+    (see the module docstring); returns the loss as a 1-element device tensor.  `batch` is the loader's
+    7-tuple (dataloaders/q_learning_real.py:98).  The hard target sync of :215-216 happens at the top of
+    the step, as in the reference."""
+
+    def __init__(self, model: HabitatDQNMultiAction, target_net: HabitatDQNMultiAction,
+                 cfg: Optional[StepConfig] = None, batch_size: int = 16, *,
+                 optimizer: Optional[FusedAdam] = None):
+        if model.extra_capacity or target_net.extra_capacity:
+            raise ValueError("BasicQLearner is for extra_capacity=False; use QLearner for the shipped architecture")
+        if model.num_frames != 1:
+            raise NotImplementedError("train-mode BatchNorm path: single-frame networks only")
+        self.cfg = cfg or StepConfig()
+        if self.cfg.TRAIN_ON_GROUND_TRUTH:
+            raise NotImplementedError("ground-truth regression is implemented for the extra_capacity path only")
+        dev = next(model.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("BasicQLearner needs the model on a CUDA device (no CPU path)")
+        self.model, self.target_net, self.B, self.device = model, target_net, batch_size, dev
+        model.set_train()                                   # BatchNorms stay in train mode (:37-40)
+        target_net.eval()
+        self.plan = E.make_plan(model.action_dim, model.num_classes, 1)
+        self.names = grad_param_names_basic()
+        self.opt = optimizer or FusedAdam(model.parameters(), lr=self.cfg.LEARNING_RATE)
+        mp = dict(model.named_parameters())
+        self.opt.adopt([mp[n] for n in self.names])
+        self.G: Dict[str, torch.Tensor] = dict(zip(self.names, self.opt.grad_views()))
+        self.W = E.PreparedWeights(self.plan, dev, trunk_only=True, fold_bn=False)
+        self.ws_s = BnTrainWorkspace(self.plan, batch_size, dev, train=True)
+        self.ws_next = BnTrainWorkspace(self.plan, batch_size, dev, train=False)
+        C, A = self.plan.num_classes, self.plan.action_dim
+        self.dq = torch.empty(batch_size, C * A, device=dev, dtype=torch.float32)
+        self.loss = torch.zeros(1, device=dev, dtype=torch.float32)
+        self.best = torch.empty(batch_size, C, device=dev, dtype=torch.int64)
+        self.y = torch.empty(batch_size, C, device=dev, dtype=torch.float32)
+        self.sample_number = 0
+        self.q_next_target = None
+
+    def _tensors(self) -> Dict[str, torch.Tensor]:
+        d = {k: v.detach() for k, v in self.model.named_parameters()}
+        d.update(dict(self.model.named_buffers()))
+        return d
+
+    @torch.no_grad()
+    def step(self, batch) -> torch.Tensor:
+        before, after, act, rew, term, _gt, valid = [t.to(self.device, non_blocking=True) if torch.is_tensor(t) else t
+                                                     for t in batch]
+        B, cfg, plan = self.B, self.cfg, self.plan
+        if before.shape[0] != B or after.shape != before.shape:
+            raise ValueError("bad shape")
+        self.sample_number += 1
+        if self.sample_number % cfg.TARGET_UPDATE_INTERVAL == 0:
+            self.target_net.load_state_dict(self.model.state_dict())          # :215-216
+        P = self._tensors()
+        self.W.prepare(P)                                    # plain bf16 operands of the current weights
+        C, A = plan.num_classes, plan.action_dim
+        self.opt.grad_arena.zero_()
+        self.loss.zero_()
+        # model(before): activations kept
+        ops.stem_pack(before.contiguous(), self.ws_s.xp)
+        q_s = forward_bn_train(plan, self.W, P, self.ws_s)
+        # target_net(after): eval mode, the module's own forward-only path
+        q_nt = self.target_net(after).reshape(B, C, A).contiguous()
+        # model(after): train mode again (second running-statistics update of the step), nothing kept
+        ops.stem_pack(after.contiguous(), self.ws_next.xp)
+        q_no = forward_bn_train(plan, self.W, P, self.ws_next)
+        ops.td_epilogue(q_s.view(B, C, A), q_no.view(B, C, A), q_nt, act.view(-1), rew, term, valid,
+                        gamma=cfg.GAMMA, double_dqn=cfg.double_dqn, clip_rect=(cfg.LOSS_CLIP == "rect"),
+                        linear=cfg.LINEAR, use_valid=cfg.REMOVE_BEFORE_REWARD, inv_count=1.0 / (B * C),
+                        dq=self.dq.view(B, C, A), loss=self.loss, best=self.best, y=self.y)
+        self.q_next_target = q_nt
+        backward_bn_train(plan, self.W, P, self.G, self.ws_s, self.dq)
+        self.opt.step(grads_in_arena=True)
+        # parameters and running statistics changed behind torch's version counters: make the module's
+        # forward-only path re-derive its folded operands next time it is used
+        st = getattr(self.model, "_basic_eng", None)
+        if st is not None:
+            st["sig"] = None
+        return self.loss

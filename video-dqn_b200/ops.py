@@ -394,6 +394,86 @@ def q_max(q, value=None, arg=None, want_arg=False):
     return value, arg
 
 
+class BnBatchStats:
+    """Per-layer scratch of a train-mode BatchNorm: fp64 sums, fp32 mean / rstd / scale / shift."""
+
+    def __init__(self, C, device):
+        self.C = C
+        self.sums = torch.zeros(2 * C, device=device, dtype=torch.float64)
+        self.mean = torch.empty(C, device=device, dtype=torch.float32)
+        self.rstd = torch.empty(C, device=device, dtype=torch.float32)
+        self.scale = torch.empty(C, device=device, dtype=torch.float32)
+        self.shift = torch.empty(C, device=device, dtype=torch.float32)
+        self.bsums = torch.zeros(2 * C, device=device, dtype=torch.float64)     # backward: sum dy, sum dy*xhat
+
+
+def bn_train_fwd(x, st: "BnBatchStats", gamma, beta, running_mean, running_var, nbt, y, *, residual=None,
+                 relu=False, momentum=0.1, eps=1e-5, update_running=True):
+    """Train-mode BatchNorm2d (+ residual) (+ ReLU) on raw conv output x [.., C] bf16 -> y bf16; batch
+    statistics stay in `st` for the backward pass; running statistics / num_batches_tracked are updated
+    in place (torch.nn.BatchNorm2d.forward)."""
+    lib = L.load()
+    _cuda(x, bf16, "x"); _cuda(y, bf16, "y")
+    Cc = x.shape[-1]
+    M = x.numel() // Cc
+    _req(Cc == st.C and y.numel() == x.numel() and M >= 1, "bad shape")
+    for t, n in ((gamma, "gamma"), (beta, "beta"), (running_mean, "running_mean"), (running_var, "running_var")):
+        _cuda(t, torch.float32, n); _req(t.numel() == Cc, "bad shape")
+    if residual is not None:
+        _cuda(residual, bf16, "residual"); _req(residual.numel() == x.numel(), "bad shape")
+    if nbt is not None:
+        _cuda(nbt, torch.int64, "num_batches_tracked")
+    sp = L.stream_ptr()
+    with _Prof("bn", (M, Cc)):
+        L.check(lib.vdqn_bn_stats(x.data_ptr(), st.sums.data_ptr(), M, Cc, sp), "bn_stats")
+        L.check(lib.vdqn_bn_finalize(st.sums.data_ptr(), M, Cc, gamma.data_ptr(), beta.data_ptr(),
+                                     running_mean.data_ptr() if update_running else None,
+                                     running_var.data_ptr() if update_running else None,
+                                     L.ptr(nbt) if update_running else None, momentum, eps,
+                                     st.mean.data_ptr(), st.rstd.data_ptr(), st.scale.data_ptr(),
+                                     st.shift.data_ptr(), sp), "bn_finalize")
+        L.check(lib.vdqn_bn_apply(x.data_ptr(), st.scale.data_ptr(), st.shift.data_ptr(), L.ptr(residual),
+                                  int(relu), y.data_ptr(), M, Cc, sp), "bn_apply")
+    return y
+
+
+def bn_train_bwd(dy, x, st: "BnBatchStats", gamma, dgamma, dbeta, dx):
+    """dy = gradient w.r.t. the BatchNorm output (bf16, already masked by the following ReLU), x = the
+    raw conv output the forward normalised.  Writes dgamma / dbeta (fp32, overwritten) and dx (bf16, may
+    alias dy)."""
+    lib = L.load()
+    _cuda(dy, bf16, "dy"); _cuda(x, bf16, "x"); _cuda(dx, bf16, "dx")
+    Cc = x.shape[-1]
+    M = x.numel() // Cc
+    _req(Cc == st.C and dy.numel() == x.numel() and dx.numel() == x.numel() and M >= 1, "bad shape")
+    _cuda(dgamma, torch.float32, "dgamma"); _cuda(dbeta, torch.float32, "dbeta")
+    _req(dgamma.numel() == Cc and dbeta.numel() == Cc, "bad shape")
+    sp = L.stream_ptr()
+    with _Prof("bn", (M, Cc)):
+        L.check(lib.vdqn_bn_bwd_reduce(dy.data_ptr(), x.data_ptr(), st.mean.data_ptr(), st.rstd.data_ptr(),
+                                       st.bsums.data_ptr(), M, Cc, sp), "bn_bwd_reduce")
+        L.check(lib.vdqn_bn_bwd_apply(dy.data_ptr(), x.data_ptr(), st.mean.data_ptr(), st.rstd.data_ptr(),
+                                      gamma.data_ptr(), st.bsums.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(),
+                                      dx.data_ptr(), M, Cc, sp), "bn_bwd_apply")
+    return dx
+
+
+def avgpool_bwd(dpooled, feat, dfeat=None):
+    """dfeat[n,p,c] = feat > 0 ? dpooled[n,c] / P : 0 (bf16): gradient of mean-over-pixels through the last
+    block's ReLU."""
+    lib = L.load()
+    _cuda(dpooled, torch.float32, "dpooled"); _cuda(feat, bf16, "feat")
+    N, Cc = feat.shape[0], feat.shape[-1]
+    P = feat.numel() // max(N * Cc, 1)
+    _req(dpooled.numel() == N * Cc, "bad shape")
+    if dfeat is None:
+        dfeat = torch.empty_like(feat)
+    with _Prof("mlp", (N,)):
+        L.check(lib.vdqn_avgpool_bwd(dpooled.data_ptr(), feat.data_ptr(), dfeat.data_ptr(), N, P, Cc,
+                                     L.stream_ptr()), "avgpool_bwd")
+    return dfeat
+
+
 def cross_entropy(logits, labels, *, dlogits=None, loss=None, correct=None, inv_count=None, want_grad=True):
     """`nn.CrossEntropyLoss()(logits, labels)` (mean) + gradient + number of correct arg-max predictions
     (train_inverse_model.py:100-106).  `loss` (fp32[1]) and `correct` (int32[1]) are ACCUMULATED into:
