@@ -166,13 +166,14 @@ class HabitatDQNMultiAction(nn.Module):
 
     def _basic_forward(self, inp):
         """The `basic` architecture (extra_capacity=False, archs/HabitatDQNMultiAction.py:32-34): trunk +
-        global average pool + one Linear.  Forward only, eval mode (BatchNorm running statistics): what
-        the value-map / policy callers need for checkpoints of that architecture.  Its training keeps
-        the trunk BatchNorms in train mode (set_train() only freezes them for extra_capacity, :37-40),
-        which the CUDA path does not implement."""
+        global average pool + one Linear.  The module's own forward is the eval-mode one (BatchNorm
+        running statistics): what the value-map / policy callers need for checkpoints of that
+        architecture.  Its training keeps the trunk BatchNorms in train mode (set_train() only freezes
+        them for extra_capacity, :37-40); that step lives in learner_basic.BasicQLearner."""
         if any(m.training for m in self.resnet.modules() if isinstance(m, nn.BatchNorm2d)):
-            raise NotImplementedError("the `basic` architecture is forward-only on the CUDA path: call "
-                                      "eval() first (its training runs the trunk BatchNorms in train mode)")
+            raise NotImplementedError("the module forward of the `basic` architecture is the eval-mode one: "
+                                      "call eval() first, or train it through "
+                                      "video_dqn_b200.learner_basic.BasicQLearner (train-mode BatchNorm step)")
         B, F = inp.shape[0], inp.shape[1]
         if B == 0:
             return inp.new_zeros((0, self.num_classes, self.action_dim), dtype=torch.float32)
