@@ -191,3 +191,29 @@ def test_inverse_model_training_oracle_reproduces_reference_golden():
                                        rtol=1e-3, atol=1e-5 * ref_l2 + 1e-12, err_msg=n)
             np.testing.assert_allclose(_sample(tr.sd[n]), z[f"s{s}/param/{n}/sample"],
                                        rtol=1e-5, atol=2e-6, err_msg=n)
+
+
+def test_basic_architecture_training_oracle_reproduces_reference_golden():
+    """oracle/qstep.py:BasicOracleTrainer (train-mode BatchNorm: batch statistics, two running-statistics
+    updates per step) against two steps of the reference's own module built with extra_capacity=False, its
+    own process_batch and torch.optim.Adam (tests/golden/basic_train_b8.npz)."""
+    torch.set_num_threads(os.cpu_count() or 1)
+    g = np.load(os.path.join(GOLD, "basic_train_b8.npz"))
+    B = int(g["meta/B"])
+    tr = qstep.BasicOracleTrainer(qstep.init_state_basic(seed=4, num_frames=1))
+    for it in range(int(g["meta/steps"])):
+        loss, grads, aux = tr.step(qstep.synthetic_batch(B, seed=1 + it))
+        p = f"step{it}/"
+        assert abs(loss.item() - float(g[p + "loss"])) <= 2e-6 * abs(float(g[p + "loss"]))
+        np.testing.assert_allclose(aux["q_s"].numpy(), g[p + "q_s"], atol=5e-6)
+        np.testing.assert_allclose(aux["q_next_online"].numpy(), g[p + "q_next_online"], atol=5e-6)
+        assert (aux["best"].numpy() == g[p + "best"]).all()
+        for n in tr.names:
+            ref_l2 = float(g[p + f"grad/{n}/l2"])
+            assert abs(grads[n].double().norm().item() - ref_l2) <= 1e-4 * ref_l2 + 1e-12, n
+            np.testing.assert_allclose(_sample(tr.sd[n]), g[p + f"param/{n}/sample"], rtol=1e-5, atol=1e-7,
+                                       err_msg=n)
+        for k in tr.sd:
+            if k.startswith("resnet.") and (k.endswith("running_mean") or k.endswith("running_var")):
+                np.testing.assert_allclose(_sample(tr.sd[k]), g[p + f"buffer/{k}/sample"], rtol=1e-5, atol=1e-7,
+                                           err_msg=k)
