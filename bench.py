@@ -152,6 +152,98 @@ def run_reference(a, out_stream=sys.stdout):
     }), file=out_stream, flush=True)
 
 
+def _inverse_block(dev):
+    """Inverse-dynamics model (BASELINE configs[4]): training step on frame pairs at the reference's batch
+    (train_inverse_model.py:21,93-110) and the labelling forward (dataset/process_episodes_real.py:171-179)."""
+    import torch
+    from video_dqn_b200.inverse import InverseActionModule, InverseActionRunner, InverseModelTrainer
+    nb = 128
+    torch.manual_seed(7)
+    isd = InverseActionModule().state_dict()    # random init in the reference module's key layout
+    g = torch.Generator().manual_seed(11)
+    hk = torch.randn(nb, 3, 224, 224, generator=g).pin_memory()
+    hk1 = torch.randn(nb, 3, 224, 224, generator=g).pin_memory()
+    hact = torch.randint(0, 3, (nb,), generator=g).pin_memory()
+    dk, dk1, dact = hk.to(dev), hk1.to(dev), hact.to(dev)
+    tr = InverseModelTrainer(isd, nb, lr=1e-4, device=dev)
+    for _ in range(5):
+        tr.step(dk, dk1, dact)
+    torch.cuda.synchronize()
+    iters = 50
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        tr.step(dk, dk1, dact)
+    e1.record(); torch.cuda.synchronize()
+    train_ms = e0.elapsed_time(e1) / iters
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        lt = tr.step(hk, hk1, hact)             # H2D of the fp32 pair batch (154 MB) + step
+    _ = lt.item()
+    train_e2e_ms = (time.perf_counter() - t0) / iters * 1e3
+    loss_f32 = float(lt.item())
+    # the same from uint8 HWC frames (decoder output; normalisation fused into the first kernel): 39 MB H2D
+    del tr
+    tr = InverseModelTrainer(isd, nb, lr=1e-4, device=dev, frames_uint8=True)
+    hu = torch.empty(nb, 224, 224, 3, dtype=torch.uint8, pin_memory=True).random_(0, 256)
+    hu1 = torch.empty(nb, 224, 224, 3, dtype=torch.uint8, pin_memory=True).random_(0, 256)
+    for _ in range(5):
+        tr.step(hu, hu1, hact)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        lt = tr.step(hu, hu1, hact)
+    _ = lt.item()
+    train_e2e_u8_ms = (time.perf_counter() - t0) / iters * 1e3
+    run = InverseActionRunner(isd, nb, dev)
+    for _ in range(3):
+        run.label(dk, dk1)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(iters):
+        run.label(dk, dk1)
+    e1.record(); torch.cuda.synchronize()
+    label_ms = e0.elapsed_time(e1) / iters
+    # per pair: two trunk forwards + head forward (7.31 GFLOP, SURVEY 8d) + head backward (2 x 29.0 MMAC x 2)
+    flop_pair = 7.31e9 + 0.116e9
+    return {"batch": nb, "train_step_ms": train_ms, "pairs_per_sec_device": nb / train_ms * 1e3,
+               "train_step_e2e_ms": train_e2e_ms, "pairs_per_sec_e2e": nb / train_e2e_ms * 1e3,
+               "train_step_e2e_uint8_ms": train_e2e_u8_ms, "pairs_per_sec_e2e_uint8": nb / train_e2e_u8_ms * 1e3,
+               "train_tflops": flop_pair * nb / (train_ms * 1e-3) / 1e12,
+               "label_ms": label_ms, "pairs_per_sec_label": nb / label_ms * 1e3,
+               "frames": "fp32 NCHW pairs (the reference loader's output); *_uint8: uint8 HWC pairs",
+               "loss": loss_f32}
+
+
+def _basic_block(dev, B):
+    """Training step of the `basic` architecture (train-mode BatchNorm) at the bench batch:
+    eager launches, device-resident fp32 frames."""
+    import torch
+    from video_dqn_b200.learner import StepConfig
+    from video_dqn_b200.learner_basic import BasicQLearner
+    from video_dqn_b200.qnet import HabitatDQNMultiAction
+    torch.manual_seed(4)
+    nets = [HabitatDQNMultiAction(3, 5, extra_capacity=False, panorama=False).to(dev) for _ in range(2)]
+    nets[1].load_state_dict(nets[0].state_dict())
+    lr = BasicQLearner(nets[0], nets[1], StepConfig(), batch_size=B)
+    batches = [[t.to(dev) for t in synthetic_quads(B, seed=50 + i, pinned=False)] for i in range(2)]
+    for i in range(3):
+        lr.step(batches[i % 2])
+    torch.cuda.synchronize()
+    iters = 10
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(iters):
+        loss = lr.step(batches[i % 2])
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    out = {"batch": B, "ms_per_step": ms, "frames_per_sec": 2 * B / ms * 1e3, "loss": float(loss.item()),
+           "mode": "train-mode BatchNorm (batch statistics), eager launches, no CUDA graph"}
+    del lr, nets, batches
+    torch.cuda.empty_cache()
+    return out
+
+
 # ----------------------------------------------------------------------------------------------
 def _claim_stdout():
     """The contract is ONE JSON line on stdout.  Native libraries write there too (NCCL prints its
@@ -386,64 +478,16 @@ def main():
     # (dataset/process_episodes_real.py:171-179)
     inverse = None
     if rank == 0 and world == 1 and not a.no_inference:
-        from video_dqn_b200.inverse import InverseActionModule, InverseActionRunner, InverseModelTrainer
-        nb = 128
-        torch.manual_seed(7)
-        isd = InverseActionModule().state_dict()    # random init in the reference module's key layout
-        g = torch.Generator().manual_seed(11)
-        hk = torch.randn(nb, 3, 224, 224, generator=g).pin_memory()
-        hk1 = torch.randn(nb, 3, 224, 224, generator=g).pin_memory()
-        hact = torch.randint(0, 3, (nb,), generator=g).pin_memory()
-        dk, dk1, dact = hk.to(dev), hk1.to(dev), hact.to(dev)
-        tr = InverseModelTrainer(isd, nb, lr=1e-4, device=dev)
-        for _ in range(5):
-            tr.step(dk, dk1, dact)
-        torch.cuda.synchronize()
-        iters = 50
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(iters):
-            tr.step(dk, dk1, dact)
-        e1.record(); torch.cuda.synchronize()
-        train_ms = e0.elapsed_time(e1) / iters
-        t0 = time.perf_counter()
-        for _ in range(iters):
-            lt = tr.step(hk, hk1, hact)             # H2D of the fp32 pair batch (154 MB) + step
-        _ = lt.item()
-        train_e2e_ms = (time.perf_counter() - t0) / iters * 1e3
-        loss_f32 = float(lt.item())
-        # the same from uint8 HWC frames (decoder output; normalisation fused into the first kernel): 39 MB H2D
-        del tr
-        tr = InverseModelTrainer(isd, nb, lr=1e-4, device=dev, frames_uint8=True)
-        hu = torch.empty(nb, 224, 224, 3, dtype=torch.uint8, pin_memory=True).random_(0, 256)
-        hu1 = torch.empty(nb, 224, 224, 3, dtype=torch.uint8, pin_memory=True).random_(0, 256)
-        for _ in range(5):
-            tr.step(hu, hu1, hact)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(iters):
-            lt = tr.step(hu, hu1, hact)
-        _ = lt.item()
-        train_e2e_u8_ms = (time.perf_counter() - t0) / iters * 1e3
-        run = InverseActionRunner(isd, nb, dev)
-        for _ in range(3):
-            run.label(dk, dk1)
-        torch.cuda.synchronize()
-        e0.record()
-        for _ in range(iters):
-            run.label(dk, dk1)
-        e1.record(); torch.cuda.synchronize()
-        label_ms = e0.elapsed_time(e1) / iters
-        # per pair: two trunk forwards + head forward (7.31 GFLOP) + head backward (2 x 29.0 MMAC x 2)
-        flop_pair = 7.31e9 + 0.116e9
-        inverse = {"batch": nb, "train_step_ms": train_ms, "pairs_per_sec_device": nb / train_ms * 1e3,
-                   "train_step_e2e_ms": train_e2e_ms, "pairs_per_sec_e2e": nb / train_e2e_ms * 1e3,
-                   "train_step_e2e_uint8_ms": train_e2e_u8_ms, "pairs_per_sec_e2e_uint8": nb / train_e2e_u8_ms * 1e3,
-                   "train_tflops": flop_pair * nb / (train_ms * 1e-3) / 1e12,
-                   "label_ms": label_ms, "pairs_per_sec_label": nb / label_ms * 1e3,
-                   "frames": "fp32 NCHW pairs (the reference loader's output); *_uint8: uint8 HWC pairs",
-                   "loss": loss_f32}
-        del tr, run
+        try:
+            inverse = _inverse_block(dev)
+        except Exception as exc:                      # an auxiliary block must not take the headline line down
+            inverse = {"error": repr(exc)}
+    basic = None
+    if rank == 0 and world == 1 and not a.no_inference:
+        try:
+            basic = _basic_block(dev, B)
+        except Exception as exc:
+            basic = {"error": repr(exc)}
 
     # ---------------- CPU baseline (rank 0, N = 1): bounded sample of the same workload
     cpu = None
@@ -478,7 +522,7 @@ def main():
             "gpu_launches_per_step": per_step_launches,
             "e2e": e2e, "roofline": roof, "roofline_kernels": roof_other, "cpu_baseline": cpu,
             "breakdown_eager_ms": breakdown if rank == 0 else None,
-            "inference": inference, "inverse_model": inverse,
+            "inference": inference, "inverse_model": inverse, "basic_architecture": basic,
         }
         print(json.dumps(out), file=out_stream, flush=True)
     if world > 1:
