@@ -258,3 +258,25 @@ class BasicQLearner:
         if st is not None:
             st["sig"] = None
         return self.loss
+
+    # ------------------------------------------------------------------ snapshots (train_q_network.py:190-208,241-247)
+    def checkpoint(self) -> dict:
+        from .learner import _to_cpu
+        torch.cuda.current_stream().synchronize()
+        return {"sample_number": self.sample_number,
+                "model_state_dict": {k: v.detach().cpu().clone() for k, v in self.model.state_dict().items()},
+                "optimizer_state_dict": _to_cpu(self.opt.state_dict())}
+
+    def save_checkpoint(self, path: str):
+        torch.save(self.checkpoint(), path)
+
+    def resume(self, snapshot, resume_from: Optional[int] = None):
+        if isinstance(snapshot, (str, bytes)) or hasattr(snapshot, "__fspath__"):
+            snapshot = torch.load(snapshot, map_location="cpu")
+        self.model.load_state_dict(snapshot["model_state_dict"])           # parameters (arena views) and BN buffers
+        self.opt.load_state_dict(snapshot["optimizer_state_dict"])
+        n = snapshot.get("sample_number", -1) if resume_from is None else resume_from
+        self.sample_number = int(n) + 1                                      # :190
+        self.target_net.load_state_dict(self.model.state_dict())            # :208
+        self.model.set_train()
+        self.target_net.eval()

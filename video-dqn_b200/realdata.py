@@ -25,6 +25,7 @@ Host-side mirror of `dataloaders/q_learning_real.py:14-98` (QLearningRealDataset
 from __future__ import annotations
 
 import os
+import threading
 import re
 from concurrent.futures import ThreadPoolExecutor
 from typing import List, Optional, Tuple
@@ -103,18 +104,28 @@ class QuadrupletTable:
 
 
 _resize = None
+_resize_lock = threading.Lock()
+
+
+def _ensure_resize():
+    """Build the Resize/CenterCrop pipeline once.  Called from the constructing (main) thread before any
+    decode job is submitted: importing torchvision from several worker threads at once -- or from a
+    worker while the main thread imports torchvision.models -- races inside the import system."""
+    global _resize
+    with _resize_lock:
+        if _resize is None:
+            import torchvision.transforms as T
+            _resize = T.Compose([T.Resize(224), T.CenterCrop(224)])
+    return _resize
 
 
 def decode_frame(path: str, out: np.ndarray):
     """JPEG -> uint8 HWC [224,224,3], resized and cropped as util/torch.py:5-12 (stops before
     ToTensor/Normalize)."""
-    global _resize
     from PIL import Image
-    if _resize is None:
-        import torchvision.transforms as T
-        _resize = T.Compose([T.Resize(224), T.CenterCrop(224)])
+    resize = _resize if _resize is not None else _ensure_resize()
     with Image.open(path) as im:
-        out[...] = np.asarray(_resize(im))
+        out[...] = np.asarray(resize(im))
 
 
 class PinnedFrameRing:
@@ -137,6 +148,8 @@ class PinnedFrameRing:
                            gt=mk(batch_size, *gshape, dt=torch.float64),
                            valid=mk(batch_size, NUM_CLASSES, dt=torch.from_numpy(table.valid_mask[:1]).dtype))
                       for _ in range(depth)]
+        _ensure_resize()                                  # in this thread, before the workers exist
+        import PIL.Image  # noqa: F401
         self.pool = ThreadPoolExecutor(max_workers=workers)
 
     def fill(self, slot: int, rows) -> tuple:
