@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import argparse
 import hashlib
+import json
 import os
 import sys
 
@@ -100,6 +101,9 @@ def main():
                 out[f"{name}/term{i}"] = np.asarray(term)
                 out[f"{name}/gt{i}"] = np.asarray(gt, dtype=np.float64)
                 out[f"{name}/valid{i}"] = np.asarray(valid)
+        # `Reward Ratio` the trainer prints (train_q_network.py:110), from the reference's own class
+        with open("reward_percentage.json", "w") as f:
+            json.dump({"reward_percentage": float(ds.reward_percentage())}, f)
     finally:
         os.chdir(cwd)
         sys.path.remove(REF)

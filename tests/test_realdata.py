@@ -61,3 +61,12 @@ def test_missing_action_source_raises_like_the_reference():
     import pytest
     with pytest.raises(Exception, match="not implemented"):
         QuadrupletTable(os.path.join(ROOT, "data.feather"))
+
+
+def test_reward_ratio_matches_the_reference_dataset_class():
+    """`dataset.reward_percentage()` (dataloaders/q_learning_real.py:51-53), value written by the
+    reference's own class (oracle/make_loader_goldens.py)."""
+    import json
+    tab = QuadrupletTable(os.path.join(ROOT, "data.feather"), inverse_actions=True)
+    ref = json.load(open(os.path.join(ROOT, "reward_percentage.json")))["reward_percentage"]
+    assert tab.reward_percentage() == ref

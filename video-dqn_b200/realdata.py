@@ -81,12 +81,17 @@ class QuadrupletTable:
         else:
             raise Exception("not implemented")           # q_learning_real.py:96-97
         self.frames_per_state = 4 if previous_images else 1
+        self._sparse_reward = _multi_get(t, "sparse_reward") if "sparse_reward0" in t.columns else None
 
     def __len__(self):
         return len(self.before)
 
     def reward_percentage(self) -> float:
-        raise NotImplementedError("needs the sparse_reward columns; use the reference's table tools")
+        """fraction of rows with a sparse reward for any class (dataloaders/q_learning_real.py:51-53; printed
+        as 'Reward Ratio' by the trainer, train_q_network.py:110)"""
+        if self._sparse_reward is None:
+            raise KeyError("data.feather has no sparse_reward0..4 columns")
+        return float((self._sparse_reward.max(axis=1) > 0).sum() / self._sparse_reward.shape[0])
 
     def frame_paths(self, index: int) -> Tuple[List[str], List[str]]:
         """files of state s and s' of row `index` (1 or 4 each)"""

@@ -112,6 +112,10 @@ def run_train(config, resume_from: int = -1, *, max_steps: Optional[int] = None,
                             inverse_actions=config.USE_INVERSE_ACTIONS,
                             previous_images=config.PREVIOUS_IMAGES)
     log(f"Load data from {config.DATASET}")
+    try:
+        log(f"Reward Ratio: {table.reward_percentage()}")                                # :110
+    except KeyError:
+        pass
     loader = QuadrupletLoader(table, batch_size, seed=config.SEED, workers=workers)      # :98,113 (drop_last, shuffle)
     model = build_model(config)                                                          # :119-122
     target_net = build_model(config)
