@@ -390,14 +390,17 @@ def main():
             nb = 1 << 20
             q = [torch.randn(nb, 5, 3, device=dev) for _ in range(3)]
             act = torch.randint(0, 3, (nb,), device=dev); rw = (torch.rand(nb, 5, device=dev) < 0.1).long()
+            # outputs preallocated: the timed region holds the kernel launches only (tools/td_bandwidth.py)
+            dq_big, loss_big = torch.empty_like(q[0]), torch.zeros(1, device=dev)
             for _ in range(3):
-                ops.td_epilogue(q[0], q[1], q[2], act, rw, rw)
+                ops.td_epilogue(q[0], q[1], q[2], act, rw, rw, dq=dq_big, loss=loss_big)
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
             for _ in range(10):
-                ops.td_epilogue(q[0], q[1], q[2], act, rw, rw)
+                ops.td_epilogue(q[0], q[1], q[2], act, rw, rw, dq=dq_big, loss=loss_big)
             e.record(); torch.cuda.synchronize()
             t_ms = s.elapsed_time(e) / 10
+            del dq_big, loss_big
             byts = nb * (3 * 60 + 8 + 40 + 40 + 60)
             roof_other.append({"kernel": "td@B=2^20", "bound": "hbm", "achieved": byts / t_ms / 1e6,
                                "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": byts / t_ms / 1e6 / pk["hbm_gbs"],

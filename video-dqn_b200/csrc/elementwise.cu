@@ -7,6 +7,9 @@
 
 #include <cuda_bf16.h>
 
+#include <cstdint>
+#include <cstdlib>
+
 namespace vdqn {
 
 // ------------------------------------------------------------------------------------------
@@ -819,6 +822,98 @@ __global__ void td_epilogue_kernel(const vdqn_td_desc d) {
   }
 }
 
+// Same computation for 16-byte aligned Q tensors (Bellman branch only), with the three Q arrays and dQ moved
+// through shared memory: thread t of a block owns element base + t and its A actions, i.e. a warp touches
+// 32*A consecutive floats per array with a stride-A pattern -- as direct loads that is A wavefronts per
+// request over the same sectors (the kernel ran at 61 % of HBM copy bandwidth at B = 2^20: LSU-bound, not
+// DRAM-bound).  Here each 256-element chunk of every array is loaded and stored as full 16-byte vectors
+// (chunk offsets are multiples of 1024*A bytes) and the stride-A accesses hit shared memory, where an odd A
+// is conflict-free.  Element -> thread mapping and per-element arithmetic are those of td_epilogue_kernel, so
+// results (including the summation order of the loss) are bit-identical.
+constexpr int kTdChunk = 256;
+
+__device__ __forceinline__ void td_stage_in(float* __restrict__ dst, const float* __restrict__ src, int nf) {
+  const int nv = nf >> 2;
+  const float4* s4 = reinterpret_cast<const float4*>(src);
+  float4* d4 = reinterpret_cast<float4*>(dst);
+  for (int v = threadIdx.x; v < nv; v += kTdChunk) d4[v] = s4[v];
+  for (int v = (nv << 2) + threadIdx.x; v < nf; v += kTdChunk) dst[v] = src[v];
+}
+
+__global__ void __launch_bounds__(kTdChunk) td_epilogue_staged_kernel(const vdqn_td_desc d) {
+  pdl_launch_dependents();
+  pdl_wait();
+  extern __shared__ __align__(16) float td_sm[];
+  const int A = d.A;
+  float* sm_qs = td_sm;                       // later reused for dQ
+  float* sm_qt = td_sm + kTdChunk * A;
+  float* sm_qo = td_sm + 2 * kTdChunk * A;
+  const long total = (long)d.B * d.C;
+  float local = 0.f;
+  for (long base = (long)blockIdx.x * kTdChunk; base < total; base += (long)gridDim.x * kTdChunk) {
+    const int n = (int)min((long)kTdChunk, total - base);
+    const int nf = n * A;
+    // issue the scalar per-element loads first so they are in flight while the tiles are staged
+    const long i = base + threadIdx.x;
+    const bool live = threadIdx.x < n;
+    float term = 0.f, rew = 0.f, mask = 1.f;
+    int act = 0;
+    if (live) {
+      term = (float)d.term[i];
+      rew = (float)d.rew[i];
+      act = (int)d.act[i / d.C];
+      if (d.use_valid) mask = (float)d.valid[i];
+    }
+    td_stage_in(sm_qs, d.q_s + base * A, nf);
+    td_stage_in(sm_qt, d.q_next_target + base * A, nf);
+    if (d.double_dqn) td_stage_in(sm_qo, d.q_next_online + base * A, nf);
+    __syncthreads();
+    if (live) {
+      const float* qs = sm_qs + threadIdx.x * A;
+      const float* qt = sm_qt + threadIdx.x * A;
+      const float* qsel = d.double_dqn ? sm_qo + threadIdx.x * A : qt;
+      int best = 0;
+      float bv = qsel[0];
+      for (int a = 1; a < A; ++a) {
+        const float v = qsel[a];
+        if (v > bv) { bv = v; best = a; }            // strict > : first maximum wins (torch.argmax)
+      }
+      const float q_a = qt[best] * (1.f - term);
+      float y = d.linear ? rew + (q_a - 0.1f) : rew + d.gamma * q_a;
+      if (d.clip_rect) y = fminf(fmaxf(y, 0.f), 1.f);
+      const float diff = qs[act] - y;
+      float l = 0.5f * diff * diff;
+      if (d.use_valid) l *= mask;
+      local += l;
+      if (d.dq != nullptr) {
+        float* dq = sm_qs + threadIdx.x * A;         // own slots only: read above, overwritten here
+        for (int a = 0; a < A; ++a) dq[a] = (a == act) ? diff * mask * d.inv_count : 0.f;
+      }
+      if (d.best_out != nullptr) d.best_out[i] = best;
+      if (d.y_out != nullptr) d.y_out[i] = y;
+    }
+    __syncthreads();
+    if (d.dq != nullptr) {
+      float* g = d.dq + base * A;
+      const int nv = nf >> 2;
+      float4* g4 = reinterpret_cast<float4*>(g);
+      const float4* s4 = reinterpret_cast<const float4*>(sm_qs);
+      for (int v = threadIdx.x; v < nv; v += kTdChunk) g4[v] = s4[v];
+      for (int v = (nv << 2) + threadIdx.x; v < nf; v += kTdChunk) g[v] = sm_qs[v];
+    }
+    __syncthreads();                                  // the tiles are overwritten by the next chunk
+  }
+  __shared__ float red[32];
+  for (int off = 16; off; off >>= 1) local += __shfl_xor_sync(0xffffffffu, local, off);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    for (int off = 16; off; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if (threadIdx.x == 0 && d.loss_out != nullptr) atomicAdd(d.loss_out, v * d.inv_count);
+  }
+}
+
 // value[b,c] = max_a q[b,c,a] (+ first arg-max): the `model(images).max(2)` of the value-map / policy
 // callers (visualize_value.py:96-97, evaluation/evaluate.py:110-114)
 __global__ void q_max_kernel(const float* __restrict__ q, float* __restrict__ value, int64_t* __restrict__ arg,
@@ -1246,6 +1341,20 @@ extern "C" int vdqn_td_epilogue(const vdqn_td_desc* d, void* stream_v) {
   GET_DEV();
   const long total = (long)d->B * d->C;
   if (total == 0) return VDQN_OK;
+  // staged variant: Bellman branch, a few actions, every Q tensor and dQ 16-byte aligned (chunk offsets are
+  // multiples of 1024*A bytes, so base alignment is all that is needed); VDQN_TD_STAGED=0 forces the direct one
+  auto al16 = [](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  static const bool staged_ok = []() {
+    const char* e = getenv("VDQN_TD_STAGED");
+    return !(e != nullptr && e[0] == '0');
+  }();
+  if (staged_ok && !d->ground_truth && d->A <= 8 && al16(d->q_s) && al16(d->q_next_target) &&
+      al16(d->q_next_online) && al16(d->dq)) {
+    const size_t smem = sizeof(float) * 3 * kTdChunk * (size_t)d->A;
+    launch_kernel(td_epilogue_staged_kernel, grid_for(total, kTdChunk, dev->num_sms, 8), kTdChunk, smem, stream, *d);
+    VDQN_CHECK_LAUNCH("td_epilogue_staged");
+    return VDQN_OK;
+  }
   launch_kernel(td_epilogue_kernel, grid_for(total, 256, dev->num_sms, 8), 256, 0, stream, *d);
   VDQN_CHECK_LAUNCH("td_epilogue");
   return VDQN_OK;
