@@ -4,7 +4,6 @@ layout)}.  CPU part: file format and naming; the cross-loading test against the 
 runs only where /root/reference exists (this container).  GPU part: save -> resume -> identical next
 step."""
 import os
-import sys
 import types
 
 import pytest

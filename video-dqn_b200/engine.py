@@ -161,7 +161,6 @@ class PreparedWeights:
     def prepare(self, P: Dict[str, torch.Tensor]):
         """Re-derive every bf16 operand from the fp32 masters in ONE launch.  The descriptor table
         lives on the device and is rebuilt only when a parameter's storage moved."""
-        import ctypes as C
         from . import _lib as L
         convs = self.convs
         sig = tuple(P[c.wkey].data_ptr() for c in convs) + \
