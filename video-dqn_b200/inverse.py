@@ -16,6 +16,7 @@ fp32 accumulation; the labelling script only consumes the arg-max.  Inference on
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, Tuple
 
 import torch
@@ -363,3 +364,55 @@ class InverseModelTrainer:
         correct = torch.zeros(1, device=self.dev, dtype=torch.int32)
         ops.cross_entropy(self.y, self.act, loss=loss, correct=correct, want_grad=False)
         return loss, correct
+
+
+# ------------------------------------------------------------------------------------------------
+# pseudo-labelling of the quadruplet table (dataset/process_episodes_real.py:165-181)
+# ------------------------------------------------------------------------------------------------
+def label_frame_pairs(before_paths, after_paths, runner, *, workers: int = 4, root: str = None):
+    """The reference's labelling loop: `for be, ae in DataLoader(ImageStream(ims), batch_size=8):
+    acts = model(be.cuda(), ae.cuda())[1].argmax(dim=1, keepdim=True)` (:165-177).  `runner` is an
+    `InverseActionRunner` (anything with `.B`, `.dev` and `.label(k, k_plus_one)`); frames are decoded to
+    uint8 HWC in a thread pool (resize / centre-crop as `imageNetTransformPIL`, the normalisation is the
+    first kernel's job) and fed in batches of `runner.B`; the last batch is padded by repeating its final
+    pair and trimmed.  Returns int64 [N, 1] -- the shape the reference assigns to the `inverse_actions`
+    column."""
+    import numpy as np
+    from concurrent.futures import ThreadPoolExecutor
+    from . import realdata
+    n = len(before_paths)
+    if len(after_paths) != n:
+        raise ValueError("bad shape")
+    B = runner.B
+    realdata._ensure_resize()
+    resolve = (lambda p: p) if root is None else (lambda p: p if os.path.isabs(p) else os.path.join(root, p))
+    pin = torch.cuda.is_available()
+    bufs = [torch.empty(B, 224, 224, 3, dtype=torch.uint8, pin_memory=pin) for _ in range(2)]
+    out = []
+    with ThreadPoolExecutor(max_workers=max(1, workers)) as pool:
+        for lo in range(0, n, B):
+            rows = list(range(lo, min(lo + B, n)))
+            rows += [rows[-1]] * (B - len(rows))
+            jobs = []
+            for which, paths in ((0, before_paths), (1, after_paths)):
+                dst = bufs[which].numpy()
+                jobs += [pool.submit(realdata.decode_frame, resolve(paths[r]), dst[i]) for i, r in enumerate(rows)]
+            for j in jobs:
+                j.result()
+            acts = runner.label(bufs[0].to(runner.dev), bufs[1].to(runner.dev))
+            out.append(acts.detach().cpu().view(-1, 1)[: min(lo + B, n) - lo].to(torch.int64))
+    return torch.cat(out) if out else torch.zeros(0, 1, dtype=torch.int64)
+
+
+def label_table(feather_path: str, runner, *, workers: int = 4, out_path: str = None):
+    """Write the `inverse_actions` column of a quadruplet table the way the data-set builder does
+    (dataset/process_episodes_real.py:165-181): label every (before_image, after_image) row and save the
+    table.  Paths in the table are relative to its directory."""
+    import pandas as pd
+    t = pd.read_feather(feather_path)
+    acts = label_frame_pairs(list(t["before_image"]), list(t["after_image"]), runner, workers=workers,
+                             root=os.path.dirname(os.path.abspath(feather_path)))
+    t["inverse_actions"] = acts.numpy()
+    t.reset_index(drop=True, inplace=True)
+    t.to_feather(out_path or feather_path)
+    return acts
