@@ -13,4 +13,10 @@ OUTPUTS OF THE REFERENCE ITSELF run in the build container
 (``oracle/make_goldens.py`` imports ``/root/reference/archs/HabitatDQNMultiAction.py``
 and runs the reference's own ``run_train`` for three steps) and the resulting
 vectors are committed under ``tests/golden/``.
+
+Files: ``qstep.py`` (Q-learning step, both architectures), ``inverse.py`` (inverse-dynamics model: labelling
+forward and training step), ``td_adam_ref.c`` (plain-C restatement of the TD loss and Adam, built by
+``oracle/Makefile`` into ``oracle/_ref/libtdref.so``: a torch-free second oracle pinned to the same vectors),
+``make_*goldens.py`` (the generators, each executing the reference's own code), ``probe_basic_bf16.py``
+(what PyTorch's own bf16 autocast does to the train-mode-BatchNorm step: the yardstick for that path's bars).
 """

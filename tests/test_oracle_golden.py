@@ -217,3 +217,74 @@ def test_basic_architecture_training_oracle_reproduces_reference_golden():
             if k.startswith("resnet.") and (k.endswith("running_mean") or k.endswith("running_var")):
                 np.testing.assert_allclose(_sample(tr.sd[k]), g[p + f"buffer/{k}/sample"], rtol=1e-5, atol=1e-7,
                                            err_msg=k)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# plain-C restatement (oracle/td_adam_ref.c -> oracle/_ref/libtdref.so): a second, torch-free oracle for the
+# index / fp32 pieces, pinned to the same vectors from the reference's own process_batch closure
+# ---------------------------------------------------------------------------------------------------------
+def _tdref():
+    import ctypes as C
+    import subprocess
+    odir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle")
+    so = os.path.join(odir, "_ref", "libtdref.so")
+    if not os.path.exists(so):
+        subprocess.check_call(["make", "-C", odir])
+    lib = C.CDLL(so)
+    P = C.c_void_p
+    lib.td_ref.argtypes = [P] * 8 + [C.c_int] * 3 + [C.c_float] + [C.c_int] * 6 + [P] * 4
+    lib.td_ref.restype = C.c_int
+    lib.adam_ref.argtypes = [P, P, P, P, C.c_long, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int]
+    lib.adam_ref.restype = C.c_int
+    return lib
+
+
+def test_c_restatement_of_td_loss_matches_reference_goldens():
+    lib = _tdref()
+    z = np.load(os.path.join(GOLD, "td_branches.npz"))
+    names = sorted({k.split("/")[0] for k in z.keys()})
+    assert len(names) == 6
+    ptr = lambda a: a.ctypes.data  # noqa: E731
+    for name in names:
+        gamma, rect, linear, use_valid, value_learning, gt_mode, A = z[f"{name}/cfg"]
+        q_s, q_no, q_nt = (np.ascontiguousarray(z[f"{name}/{k}"], dtype=np.float32) for k in ("q_s", "q_no", "q_nt"))
+        act, rew, valid = (np.ascontiguousarray(z[f"{name}/{k}"], dtype=np.int64) for k in ("act", "rew", "valid"))
+        B, Cc = rew.shape
+        gt = np.ascontiguousarray(np.broadcast_to(z[f"{name}/gt"].reshape(B, -1), (B, Cc)), dtype=np.float64)
+        dq, y = np.empty_like(q_s), np.empty((B, Cc), np.float32)
+        best, loss = np.empty((B, Cc), np.int64), np.zeros(1, np.float32)
+        rc = lib.td_ref(ptr(q_s), ptr(q_no), ptr(q_nt), ptr(act), ptr(rew), ptr(rew), ptr(valid), ptr(gt), B, Cc,
+                        int(A), float(gamma), 1, int(rect), int(linear), int(use_valid), int(gt_mode),
+                        int(value_learning), ptr(dq), ptr(y), ptr(best), ptr(loss))
+        assert rc == 0
+        ref_loss = float(z[f"{name}/loss"])
+        if np.isnan(ref_loss):
+            assert np.isnan(loss[0]), name
+        else:
+            assert abs(loss[0] - ref_loss) <= 1e-6 * abs(ref_loss) + 1e-9, (name, loss[0], ref_loss)
+        np.testing.assert_allclose(dq, z[f"{name}/dq"], rtol=0, atol=1e-7, equal_nan=True, err_msg=name)
+        if not gt_mode:                                   # arg-max against the torch oracle: integers, exact
+            cfg = qstep.StepConfig(GAMMA=float(gamma), LOSS_CLIP="rect" if rect else "none", LINEAR=bool(linear),
+                                   action_dim=int(A))
+            b_ref, y_ref = qstep.td_targets(torch.from_numpy(q_no), torch.from_numpy(q_nt), torch.from_numpy(rew),
+                                            torch.from_numpy(rew), cfg)
+            assert (best == b_ref.numpy()).all(), name
+            np.testing.assert_array_equal(y, y_ref.numpy(), err_msg=name)      # same fp32 operations: bit-exact
+
+
+def test_c_restatement_of_adam_matches_torch():
+    lib = _tdref()
+    g = torch.Generator().manual_seed(0)
+    p0 = torch.randn(1000, generator=g)
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([ref], lr=1e-4)
+    p = p0.numpy().copy()
+    m, v = np.zeros_like(p), np.zeros_like(p)
+    for step in range(1, 5):
+        gr = (torch.randn(1000, generator=g) * 0.01)
+        ref.grad = gr.clone()
+        opt.step()
+        gnp = gr.numpy().copy()
+        assert lib.adam_ref(p.ctypes.data, gnp.ctypes.data, m.ctypes.data, v.ctypes.data, 1000, 1e-4, 0.9, 0.999,
+                            1e-8, step) == 0
+    np.testing.assert_allclose(p, ref.detach().numpy(), rtol=0, atol=2e-7)
