@@ -152,3 +152,40 @@ def test_learner_resume_reproduces_the_uninterrupted_run(tmp_path):
     to = dict(other.target_net.named_parameters())
     assert (ta["top.4.weight"] - to["top.4.weight"]).abs().max().item() <= 1e-7   # target <- model at resume (:208)
     assert other.opt.state_dict()["state"][0]["step"].item() == 4
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "archs")), reason="needs the reference checkout")
+def test_inverse_module_state_loads_strictly_into_both_reference_classes(tmp_path):
+    """`InverseActionModule().state_dict()` (what `InverseModelTrainer.state_dict()` returns and
+    `model-N.pth` / `inverse_model.torch` hold) loads with strict=True into the trainer's class
+    (train_inverse_model.model) and into the labeller's class (archs/inverse_action2.model), and theirs
+    load into it."""
+    import sys
+    from oracle.make_inverse_train_goldens import import_reference_trainer
+    from video_dqn_b200.inverse import InverseActionModule
+    mine = InverseActionModule()
+    sd = mine.state_dict()
+    _T, trainer_model = import_reference_trainer()
+    res = trainer_model.load_state_dict(sd, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    # the arch file defines the same absl flag as the trainer ('bottleneck_size'), so the two reference
+    # modules cannot be imported into one process: the labeller's class is checked in a child process
+    import subprocess
+    path = str(tmp_path / "inverse_model.torch")
+    torch.save(sd, path)
+    child = (
+        "import sys, torch, torchvision.models as tvm\n"
+        "orig = tvm.resnet18\n"
+        "tvm.resnet18 = lambda pretrained=False, **kw: orig(weights=None, **kw)\n"
+        f"sys.path.insert(0, {REF!r})\n"
+        "from archs import inverse_action2\n"
+        "m = inverse_action2.model()\n"
+        f"res = m.load_state_dict(torch.load({path!r}, map_location='cpu'), strict=True)\n"   # process_episodes_real.py:92-93
+        "assert not res.missing_keys and not res.unexpected_keys\n"
+        "print('arch-ok')\n")
+    out = subprocess.run([sys.executable, "-c", child], capture_output=True, text=True)
+    assert "arch-ok" in out.stdout, out.stderr[-2000:]
+    res = mine.load_state_dict(trainer_model.state_dict(), strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    assert [n for n, p in mine.named_parameters() if p.requires_grad] == \
+        [n for n, p in trainer_model.named_parameters() if p.requires_grad]
