@@ -7,6 +7,7 @@ import os
 import re
 import subprocess
 import sys
+import types
 
 import pytest
 import torch
@@ -122,3 +123,27 @@ def test_inverse_module_container_keeps_reference_layout():
     assert not m.resnet18.training
     with pytest.raises(RuntimeError, match="no CPU path"):
         m(torch.zeros(1, 3, 224, 224), torch.zeros(1, 3, 224, 224))
+
+
+def test_new_wrappers_refuse_cpu_tensors_before_launch(lib):
+    """No CPU fallback anywhere: the tensor-level wrappers of the inverse-model / train-mode-BatchNorm
+    kernels raise on host tensors before the library is called."""
+    from video_dqn_b200 import ops
+    x = torch.zeros(2, 4, 4, 64, dtype=torch.bfloat16)
+    c = torch.zeros(64)
+    with pytest.raises(ValueError, match="CUDA"):
+        ops.cross_entropy(torch.zeros(4, 3), torch.zeros(4, dtype=torch.int64))
+    with pytest.raises(ValueError, match="CUDA"):
+        ops.dropout_mask(torch.zeros(8, dtype=torch.uint8), 0.5, 0, 0)
+    with pytest.raises(ValueError, match="CUDA"):
+        ops.dropout_apply(torch.zeros(8), torch.zeros(8, dtype=torch.uint8), 2.0)
+    with pytest.raises(ValueError, match="CUDA"):
+        ops.avgpool_bwd(torch.zeros(2, 64), x)
+    st = types.SimpleNamespace(C=64)
+    with pytest.raises(ValueError, match="CUDA"):
+        ops.bn_train_fwd(x, st, c, c, c, c, None, x.clone())
+    with pytest.raises(ValueError, match="CUDA"):
+        ops.bn_train_bwd(x, x, st, c, c, c, x.clone())
+    from video_dqn_b200.inverse import InverseActionModule, InverseModelTrainer
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        InverseModelTrainer(InverseActionModule().state_dict(), 4, device="cpu")
