@@ -17,6 +17,7 @@ vectors are committed under ``tests/golden/``.
 Files: ``qstep.py`` (Q-learning step, both architectures), ``inverse.py`` (inverse-dynamics model: labelling
 forward and training step), ``td_adam_ref.c`` (plain-C restatement of the TD loss and Adam, built by
 ``oracle/Makefile`` into ``oracle/_ref/libtdref.so``: a torch-free second oracle pinned to the same vectors),
-``make_*goldens.py`` (the generators, each executing the reference's own code), ``probe_basic_bf16.py``
+``make_*goldens.py`` (the generators, each executing the reference's own code), ``crosscheck_run_train.py``
+(the reference's own ``run_train`` loop run live against the oracle), ``probe_basic_bf16.py``
 (what PyTorch's own bf16 autocast does to the train-mode-BatchNorm step: the yardstick for that path's bars).
 """

@@ -288,3 +288,14 @@ def test_c_restatement_of_adam_matches_torch():
         assert lib.adam_ref(p.ctypes.data, gnp.ctypes.data, m.ctypes.data, v.ctypes.data, 1000, 1e-4, 0.9, 0.999,
                             1e-8, step) == 0
     np.testing.assert_allclose(p, ref.detach().numpy(), rtol=0, atol=2e-7)
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(os.environ.get("VDQN_REFERENCE", "/root/reference"), "archs")),
+                    reason="needs the reference checkout (this container)")
+def test_oracle_reproduces_the_reference_run_train_end_to_end():
+    """the reference's own `train_q_network.run_train` (imported unmodified, three steps on a
+    table built from the committed mini data set, recording Adam + DataLoader) against the oracle started
+    from the recorded initial parameters and stepped on the recorded batches, target sync included."""
+    from oracle import crosscheck_run_train
+    worst = crosscheck_run_train.run(verbose=False)
+    assert worst < 1e-4
