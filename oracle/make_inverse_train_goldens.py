@@ -9,7 +9,8 @@ with `oracle.inverse.init_state(seed)`, put in train mode as `train()` does (:87
 times with the loop body of :93-110.  The dropout draw of each step is recorded with a forward hook
 on `dropout1` (keep = output != 0 wherever the input is > 0; where the input is 0 the draw cannot
 influence anything) and handed to the oracle, which must reproduce loss, logits, every gradient and
-the parameters after each Adam step.
+the parameters after each Adam step.  Finally the reference's own `train()` function (:85-140) is run on the same
+batches and dropout seed and must end on bit-identical parameters.
 
 usage:  python -m oracle.make_inverse_train_goldens [--out tests/golden]
 """
@@ -77,10 +78,12 @@ def main():
     out = {"seed": 7, "data_seed": 33, "steps": STEPS, "batch": B, "lr": T.FLAGS.lr}
     worst = 0.0
     m.train()                                                                                    # :87
+    batches = []
     for s in range(STEPS):
         k = torch.randn(B, 3, 224, 224, generator=g)
         k1 = torch.randn(B, 3, 224, 224, generator=g)
         act = torch.randint(0, 3, (B,), generator=g)
+        batches.append((k, k1, act, None, None, None))
         opt.zero_grad()                                                                          # :94
         y = m(k, k1)                                                                             # :97
         loss = torch.nn.CrossEntropyLoss()(y, act)                                               # :100-101
@@ -107,6 +110,25 @@ def main():
         out.update(summarize({f"s{s}/grad/{n}": grads_ref[n] for n in names}))
         out.update(summarize({f"s{s}/param/{n}": ref_p[n] for n in names}))
     print("oracle == reference over", STEPS, "steps; worst relative gradient deviation", worst)
+    # the loop body above is a transcription of train() (:93-110); run the reference's OWN train() on the same
+    # batches and dropout seed with a fresh copy of the module: it must end on the same parameters, bit for bit
+    import torchvision.models as tvm
+    orig = tvm.resnet18
+    tvm.resnet18 = lambda pretrained=False, **kw: orig(weights=None, **kw)
+    try:
+        m2 = T.model()
+    finally:
+        tvm.resnet18 = orig
+    m2.load_state_dict(sd, strict=False)
+    opt2 = torch.optim.Adam(m2.parameters(), lr=T.FLAGS.lr, weight_decay=T.FLAGS.weight_decay)
+    torch.manual_seed(5)
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        T.train(m2, torch.device("cpu"), batches, opt2, 1, None, None, 0)
+    p1, p2 = dict(m.named_parameters()), dict(m2.named_parameters())
+    assert all(torch.equal(p1[n], p2[n]) for n in names), "transcribed loop != the reference's train()"
+    print("the reference's own train() ends on identical parameters")
     path = os.path.join(a.out, "inverse_train_b4.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path) // 1024, "KiB")
