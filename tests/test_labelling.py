@@ -57,3 +57,39 @@ def test_label_table_writes_the_column(tmp_path):
     t1 = pd.read_feather(path)
     assert "inverse_actions" in t1.columns and np.array_equal(np.asarray(t1["inverse_actions"]).reshape(-1, 1), acts.numpy())
     assert list(t1["before_image"]) == list(t0["before_image"])
+
+
+import pytest  # noqa: E402
+
+REF = os.environ.get("VDQN_REFERENCE", "/root/reference")
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "dataloaders")), reason="needs the reference checkout")
+def test_pairs_match_the_reference_image_stream():
+    """The uint8 pairs `label_frame_pairs` feeds the labeller, normalised as the first kernel does, equal
+    what the reference's own `ImageStream` yields for the same rows (dataloaders/image_streams.py:15-27;
+    dataset/process_episodes_real.py:168-173)."""
+    import sys
+    from oracle import qstep
+    t = pd.read_feather(os.path.join(ROOT, "data.feather"))
+    before, after = list(t["before_image"]), list(t["after_image"])
+    sys.path.insert(0, REF)
+    cwd = os.getcwd()
+    try:
+        from dataloaders.image_streams import ImageStream
+        os.chdir(ROOT)                                   # the table's paths are relative to its directory
+        ims = np.stack((t["before_image"], t["after_image"]), axis=1)         # :168-169
+        ref = [ImageStream(ims)[i] for i in range(len(t))]
+    finally:
+        os.chdir(cwd)
+        sys.path.remove(REF)
+
+    class Capture(FakeLabeller):
+        def label(self, k, k1):
+            self.k, self.k1 = k.clone(), k1.clone()
+            return super().label(k, k1)
+    c = Capture(len(t))
+    label_frame_pairs(before, after, c, workers=2, root=ROOT)
+    for i, (be, ae) in enumerate(ref):
+        assert (qstep.to_imgnet(c.k[i:i + 1])[0] - be).abs().max().item() <= 1e-6
+        assert (qstep.to_imgnet(c.k1[i:i + 1])[0] - ae).abs().max().item() <= 1e-6

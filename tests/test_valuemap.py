@@ -67,3 +67,51 @@ def test_panorama_rotation(tmp_path):
             # heading slot s of the rotated panorama holds view (ori + s) % 4 (cat(images[ori:], images[:ori]))
             want = [level[(rr, cc, (ori + (k % 4)) % 4)] * (k + 1) for k in range(5)]
             np.testing.assert_allclose(maps[ori][rr, cc], want, atol=1e-4)
+
+
+import pytest  # noqa: E402
+
+REF = os.environ.get("VDQN_REFERENCE", "/root/reference")
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "dataloaders")), reason="needs the reference checkout")
+def test_views_match_the_reference_dataset_class(tmp_path):
+    """The frames `build_value_maps` hands to the runner, normalised as the first kernel does
+    (`to_imgnet`), equal what the reference's own `HabitatQVisualizationDatasetGibson` yields for the same
+    folder, cell, orientation and panorama switch (dataloaders/habitat_visualization_data_gibson.py:13-36)."""
+    import sys
+    from oracle import qstep
+    rng = np.random.default_rng(0)
+    cells = [(5, 9), (2, 3), (7, 7)]
+    for r, c in cells:
+        for i in range(4):
+            Image.fromarray(rng.integers(0, 256, (260, 340, 3), dtype=np.uint8)).save(
+                os.path.join(tmp_path, f"{r}-{c}-{i}.jpg"), quality=92)
+    sys.path.insert(0, REF)
+    try:
+        from dataloaders.habitat_visualization_data_gibson import HabitatQVisualizationDatasetGibson
+    finally:
+        sys.path.remove(REF)
+
+    class Capture:
+        def __init__(self, B):
+            self.B, self.seen = B, []
+
+        def __call__(self, frames):
+            self.seen.append(frames.clone())
+            return None, torch.zeros(self.B, 5), None
+
+    for panorama in (False, True):
+        cap = Capture(4)
+        build_value_maps(str(tmp_path), cap, panorama=panorama, resolution=16, workers=2)
+        assert len(cap.seen) == 4                                           # one (padded) batch per orientation
+        order = list_cells(str(tmp_path))
+        for ori in range(4):
+            ds = HabitatQVisualizationDatasetGibson(str(tmp_path), orientation=ori, panorama=panorama)
+            ref = {(r, c): im for r, c, im in (ds[k] for k in range(len(ds)))}
+            assert sorted(ref) == order
+            for b, cell in enumerate(order):
+                mine = cap.seen[ori][b]
+                mine = qstep.to_imgnet(mine if panorama else mine[None])    # [F,3,224,224]
+                want = ref[cell] if panorama else ref[cell][None]
+                assert (mine - want).abs().max().item() <= 1e-6, (panorama, ori, cell)
