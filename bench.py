@@ -113,11 +113,12 @@ def cpu_reference_arm(steps, warmup, batch, threads):
     data = [qstep.synthetic_batch(batch, seed=1 + i) for i in range(2)]
     for i in range(warmup):
         tr.step(data[i % 2])
-    t0 = time.perf_counter()
+    times = []
     for i in range(steps):
+        t0 = time.perf_counter()
         tr.step(data[i % 2])
-    dt = (time.perf_counter() - t0) / max(steps, 1)
-    return dt
+        times.append(time.perf_counter() - t0)
+    return statistics.median(times) if times else 0.0      # median of the timed steps
 
 
 def make_config(world, B, graph):
@@ -139,7 +140,8 @@ def run_reference(a, out_stream=sys.stdout):
     steps, warmup = max(1, min(a.steps, 12)), max(1, min(a.warmup, 3))
     dt = cpu_reference_arm(steps, warmup, B, threads)
     fps = 2 * B / dt
-    sample = f"{steps} steps of {B} quadruplets (of the {BATCH_PER_GPU}-quadruplet workload), fp32"
+    sample = (f"median of {steps} steps of {B} quadruplets after {warmup} warm-up steps (of the {BATCH_PER_GPU}-quadruplet "
+              "workload), fp32 oracle port on all host cores")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": a.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": dt * 1e3, "steps_per_sec": 1.0 / dt,
@@ -496,14 +498,15 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        dtc = cpu_reference_arm(steps=4, warmup=1, batch=8, threads=threads)
+        dtc = cpu_reference_arm(steps=5, warmup=3, batch=8, threads=threads)
         cpu = {"value": 16 / dtc, "unit": "frames/s", "cores": threads, "kind": "port",
-               "sample": "4 steps of 8 quadruplets (of the 256-quadruplet workload), fp32 oracle port",
+               "sample": "median of 5 steps of 8 quadruplets after 3 warm-up steps (of the 256-quadruplet "
+                         "workload), fp32 oracle port",
                "ms_per_step_b8": dtc * 1e3}
         # also the reference's real batch (16, train_q_network.py:98) on all cores, and the
         # as-shipped thread setting (torch.set_num_threads(1), :85)
-        dt16 = cpu_reference_arm(steps=3, warmup=1, batch=16, threads=threads)
-        dt1 = cpu_reference_arm(steps=2, warmup=1, batch=8, threads=1)
+        dt16 = cpu_reference_arm(steps=5, warmup=3, batch=16, threads=threads)
+        dt1 = cpu_reference_arm(steps=5, warmup=1, batch=8, threads=1)
         cpu["batch16_all_cores"] = {"value": 32 / dt16, "unit": "frames/s", "ms_per_step": dt16 * 1e3}
         cpu["as_shipped_1_thread"] = {"value": 16 / dt1, "unit": "frames/s", "cores": 1, "ms_per_step_b8": dt1 * 1e3}
 
