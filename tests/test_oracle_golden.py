@@ -299,3 +299,40 @@ def test_oracle_reproduces_the_reference_run_train_end_to_end():
     from oracle import crosscheck_run_train
     worst = crosscheck_run_train.run(verbose=False)
     assert worst < 1e-4
+
+
+def test_c_restatement_agrees_with_the_torch_oracle_on_random_cases():
+    """The two oracles against each other over random shapes and switches (including B = 0, B = 1, ties in
+    the arg-max, one action, all-terminal rows): arg-max and y bit-exact, dQ to 1e-7, loss to 1e-6."""
+    lib = _tdref()
+    g = torch.Generator().manual_seed(123)
+    ptr = lambda a: a.ctypes.data  # noqa: E731
+    for case in range(40):
+        B = [0, 1, 2, 7, 64][case % 5]
+        A = 1 if case % 7 == 0 else 3
+        cfg = qstep.StepConfig(GAMMA=0.99 if case % 3 else 0.9, LOSS_CLIP="rect" if case % 2 else "none",
+                               LINEAR=(case % 4 == 3), REMOVE_BEFORE_REWARD=(case % 5 == 4), action_dim=A)
+        q_s, q_no, q_nt = (torch.randn(B, 5, A, generator=g) for _ in range(3))
+        if B > 1:
+            q_no[0, :, :] = 0.25                          # ties: the first maximum must win
+        act = torch.randint(0, A, (B,), generator=g)
+        rew = (torch.rand(B, 5, generator=g) < 0.3).long()
+        term = rew.clone() if case % 2 else torch.ones_like(rew)
+        valid = (torch.rand(B, 5, generator=g) < 0.7).long()
+        dq = np.zeros((B, 5, A), np.float32)
+        y, best, loss = np.zeros((B, 5), np.float32), np.zeros((B, 5), np.int64), np.zeros(1, np.float32)
+        arrs = [np.ascontiguousarray(t.numpy()) for t in (q_s, q_no, q_nt, act, rew, term, valid)]
+        gt = np.zeros((max(B, 1), 5), np.float64)
+        rc = lib.td_ref(*[ptr(a) for a in arrs], ptr(gt), B, 5, A, float(cfg.GAMMA), 1,
+                        int(cfg.LOSS_CLIP == "rect"), int(cfg.LINEAR), int(cfg.REMOVE_BEFORE_REWARD), 0, 0,
+                        ptr(dq), ptr(y), ptr(best), ptr(loss))
+        assert rc == 0
+        if B == 0:
+            continue
+        qs = q_s.clone().requires_grad_(True)
+        l_ref, aux = qstep.td_loss(qs, q_no, q_nt, act, rew, term, valid, cfg)
+        l_ref.backward()
+        assert (best == aux["best"].numpy()).all(), case
+        np.testing.assert_array_equal(y, aux["y"].numpy(), err_msg=str(case))
+        np.testing.assert_allclose(dq, qs.grad.numpy(), rtol=0, atol=1e-7, err_msg=str(case))
+        assert abs(loss[0] - l_ref.item()) <= 1e-6 * max(1.0, abs(l_ref.item())), case
