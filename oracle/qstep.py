@@ -439,9 +439,17 @@ def trunk_forward_bn_train(sd: Dict[str, torch.Tensor], x: torch.Tensor) -> torc
 
 
 def q_forward_basic_train(sd, x, action_dim: int = 3):
-    """Q[B,5,A] of the single-frame `basic` architecture with train-mode BN (mutates running stats)."""
-    f = trunk_forward_bn_train(sd, x).mean(dim=(2, 3))
-    return F.linear(f, sd["top.weight"], sd["top.bias"]).view(-1, NUM_CLASSES, action_dim)
+    """Q[B,5,A] of the `basic` architecture with train-mode BN (mutates running stats).  With F frames
+    ([B,F,3,224,224], panorama / previous-images networks) every frame goes through the trunk separately, in
+    order (archs/HabitatDQNMultiAction.py:49-51): F sets of batch statistics and F running-statistics
+    updates per forward."""
+    if x.dim() == 4:
+        x = x.unsqueeze(1)
+    nf = sd["top.weight"].shape[1] // 512
+    if x.shape[1] != nf:
+        raise Exception("bad shape")
+    feats = [trunk_forward_bn_train(sd, x[:, i]).mean(dim=(2, 3)) for i in range(nf)]
+    return F.linear(torch.cat(feats, 1), sd["top.weight"], sd["top.bias"]).view(-1, NUM_CLASSES, action_dim)
 
 
 def grad_param_names_basic() -> List[str]:

@@ -193,16 +193,19 @@ def test_inverse_model_training_oracle_reproduces_reference_golden():
                                        rtol=1e-5, atol=2e-6, err_msg=n)
 
 
-def test_basic_architecture_training_oracle_reproduces_reference_golden():
+@pytest.mark.parametrize("fixture", ["basic_train_b8.npz", "basic_train_f4_b4.npz"])
+def test_basic_architecture_training_oracle_reproduces_reference_golden(fixture):
     """oracle/qstep.py:BasicOracleTrainer (train-mode BatchNorm: batch statistics, two running-statistics
-    updates per step) against two steps of the reference's own module built with extra_capacity=False, its
-    own process_batch and torch.optim.Adam (tests/golden/basic_train_b8.npz)."""
+    updates per frame and step) against two steps of the reference's own module built with
+    extra_capacity=False, its own process_batch and torch.optim.Adam: single frame at B = 8 and the
+    four-frame panorama layout at B = 4 (every frame through the trunk separately)."""
+    from oracle.make_basic_train_goldens import frames_batch
     torch.set_num_threads(os.cpu_count() or 1)
-    g = np.load(os.path.join(GOLD, "basic_train_b8.npz"))
-    B = int(g["meta/B"])
-    tr = qstep.BasicOracleTrainer(qstep.init_state_basic(seed=4, num_frames=1))
+    g = np.load(os.path.join(GOLD, fixture))
+    B, nf = int(g["meta/B"]), int(g["meta/frames"])
+    tr = qstep.BasicOracleTrainer(qstep.init_state_basic(seed=4, num_frames=nf))
     for it in range(int(g["meta/steps"])):
-        loss, grads, aux = tr.step(qstep.synthetic_batch(B, seed=1 + it))
+        loss, grads, aux = tr.step(frames_batch(B, nf, 1 + it))
         p = f"step{it}/"
         assert abs(loss.item() - float(g[p + "loss"])) <= 2e-6 * abs(float(g[p + "loss"]))
         np.testing.assert_allclose(aux["q_s"].numpy(), g[p + "q_s"], atol=5e-6)
