@@ -21,7 +21,10 @@ class FakeLearner:
         self.steps_done += 1
         self._losses.append(float(batch))
         self.calls.append(batch)
-        return torch.tensor([float(batch)])
+        if not hasattr(self, "_buf"):
+            self._buf = torch.zeros(1)
+        self._buf.fill_(float(batch))            # ONE loss buffer, overwritten every step (as the learners do)
+        return self._buf
 
     def _loss_value(self, k):
         assert k <= self.steps_done - 1 and k >= self.steps_done - 4      # still inside the four-slot ring

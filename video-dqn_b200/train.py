@@ -67,7 +67,9 @@ class TrainLoop:
             # index of this step in the learner's pinned loss ring (its own count of step() calls)
             k = getattr(self.learner, "steps_done", done + 1) - 1
             self._pending.append((self.sample_number, k, loss))
-            self._drain(keep=1)                   # read step k's loss only after step k+1 is in flight
+            # with a pinned loss ring, read step k's loss only after step k+1 is in flight; a learner
+            # without one returns its single loss buffer, which the next step overwrites: read it now
+            self._drain(keep=1 if hasattr(self.learner, "loss_value") else 0)
             done += 1
             if self.sample_number % cfg.CHECKPOINT_INTERVAL == 0:                        # :241-247
                 self._drain(keep=0)
