@@ -29,8 +29,8 @@ def pytest_collection_modifyitems(config, items):
 @pytest.fixture(scope="session", autouse=True)
 def _built_library():
     """The C-ABI library is a build artefact (git-ignored): build it once per session if absent."""
-    so = os.path.join(ROOT, "video-dqn_b200", "libvdqn.so")
+    so = os.path.join(ROOT, "video_dqn_b200", "libvdqn.so")
     if not os.path.exists(so):
         import subprocess
-        subprocess.check_call([sys.executable, os.path.join(ROOT, "video-dqn_b200", "build.py")])
+        subprocess.check_call([sys.executable, os.path.join(ROOT, "video_dqn_b200", "build.py")])
     yield

@@ -19,9 +19,9 @@ HDR = os.path.join(ROOT, "include", "vdqn.h")
 @pytest.fixture(scope="module")
 def lib():
     sys.path.insert(0, ROOT)
-    so = os.path.join(ROOT, "video-dqn_b200", "libvdqn.so")
+    so = os.path.join(ROOT, "video_dqn_b200", "libvdqn.so")
     if not os.path.exists(so):
-        subprocess.check_call([sys.executable, os.path.join(ROOT, "video-dqn_b200", "build.py")])
+        subprocess.check_call([sys.executable, os.path.join(ROOT, "video_dqn_b200", "build.py")])
     from video_dqn_b200 import _lib
     return _lib
 

@@ -1,6 +1,6 @@
 """Which warp role bounds the halo convolution kernels?  Needs the instrumented library:
 
-    VDQN_NVCC_FLAGS=-DVDQN_ROLE_PROFILE python video-dqn_b200/build.py --force
+    VDQN_NVCC_FLAGS=-DVDQN_ROLE_PROFILE python video_dqn_b200/build.py --force
     python tools/role_profile.py
 
 Every role (producer warps 0-3, MMA issuer, epilogue warps 0-3) reports cycles blocked in its waits

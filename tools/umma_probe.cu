@@ -3,7 +3,7 @@
 // that is not a multiple of 1024 bytes?  If yes, a 3x3 convolution can read its nine shifted
 // windows out of ONE shared-memory copy of the input tile instead of nine im2col copies from L2.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O2 -std=c++17 -o umma_probe umma_probe.cu
-#include "../video-dqn_b200/csrc/ptx.cuh"
+#include "../video_dqn_b200/csrc/ptx.cuh"
 
 #include <cuda_bf16.h>
 #include <math.h>

@@ -115,7 +115,7 @@ def load():
     if _lib is not None:
         return _lib
     if not os.path.exists(LIB_PATH):
-        raise VdqnError(f"{LIB_PATH} not found: build it with `python video-dqn_b200/build.py` "
+        raise VdqnError(f"{LIB_PATH} not found: build it with `python video_dqn_b200/build.py` "
                         "(there is no CPU fallback)")
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in EXPORTS.items():

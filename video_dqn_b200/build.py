@@ -1,6 +1,6 @@
 """Build libvdqn.so (the C-ABI CUDA library) in-tree for sm_100a.
 
-    python video-dqn_b200/build.py [--force]
+    python video_dqn_b200/build.py [--force]
 
 nvcc cross-compiles without a GPU.  The .so is git-ignored but travels to the GPU box with
 the gpurun snapshot.  cudart is linked statically and the driver is reached through
