@@ -45,14 +45,46 @@ def peaks():
 
 
 class ClockSampler:
+    """SM clock + throttle reasons DURING the timed region.  A timed region of K graph replays lasts a
+    fraction of a second, too short for `nvidia-smi -lms`, so a thread polls NVML (nvidia-ml-py) every
+    5 ms with host time stamps; `stop(t0, t1)` keeps the samples taken between the two.  Falls back to
+    the nvidia-smi loop of /opt/skills/guides/B200_PROFILING.md when NVML cannot be opened."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.p = index, None
+        self.index, self.p, self.thread, self.samples, self._stop = index, None, None, [], False
+
+    def _nvml_loop(self, nv, h):
+        R = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+             "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+        while not self._stop:
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                bits = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                self.samples.append((time.perf_counter(), float(mhz), [k for k, b in R.items() if bits & b]))
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def start(self):
+        try:
+            import threading
+            import pynvml as nv
+            nv.nvmlInit()
+            # NVML enumerates physical devices: map through CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            idx = self.index
+            if vis and all(v.strip().isdigit() for v in vis.split(",")):
+                idx = int(vis.split(",")[self.index])
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.smax = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                        "--format=csv,noheader,nounits", "-lms", "100"],
@@ -60,7 +92,17 @@ class ClockSampler:
         except Exception:
             self.p = None
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        if self.thread is not None:
+            self._stop = True
+            self.thread.join(timeout=2)
+            inside = [x for x in self.samples if t0 is None or t0 <= x[0] <= t1]
+            use = inside if inside else self.samples
+            sm = [x[1] for x in use]
+            reasons = sorted({r for x in use for r in x[2]})
+            return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.smax, "reasons": reasons,
+                    "samples": len(inside), "samples_total": len(self.samples), "source": "nvml thread, 5 ms period, "
+                    "samples between the first launch and the final synchronize of the timed region"}
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
         self.p.terminate()
@@ -85,7 +127,7 @@ class ClockSampler:
         load = [c for c in sm if c > 0.5 * max(sm)] if sm else []
         return {"sm_mhz": statistics.median(load) if load else None,
                 "sm_max_mhz": max(smax) if smax else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
 def synthetic_quads(B, seed, pinned=True):
@@ -131,17 +173,80 @@ def make_config(world, B, graph):
             "random_init_weights": True}
 
 
+def find_reference():
+    """Directory holding the UNMODIFIED reference sources of the path (archs/HabitatDQNMultiAction.py and
+    train_q_network.py): `baseline/_ref` (git-ignored copy made by __graft_entry__.build(); travels to the
+    GPU box with the snapshot) or the container's /root/reference.  None: only the oracle port is left."""
+    for d in (os.path.join(ROOT, "baseline", "_ref"), "/root/reference"):
+        if os.path.exists(os.path.join(d, "archs", "HabitatDQNMultiAction.py")) and \
+                os.path.exists(os.path.join(d, "train_q_network.py")):
+            return d
+    return None
+
+
+def cpu_reference_real(ref_dir, steps, warmup, batch, threads):
+    """The reference ITSELF on the host cores: its own `HabitatDQNMultiAction` (imported unmodified; only
+    the ImageNet download is patched out), its own `process_batch` (lifted out of `run_train` with ast, it is
+    a closure) and `torch.optim.Adam`, driven by the loop body of train_q_network.py:221-229."""
+    import types
+    import torch
+    os.environ["VDQN_REFERENCE"] = ref_dir
+    from oracle import make_goldens, qstep
+    make_goldens.REF = ref_dir
+    torch.set_num_threads(threads)
+    RefNet, restore = make_goldens.import_reference_model()
+    cfg = qstep.StepConfig()
+    refcfg = types.SimpleNamespace(device="cpu", LINEAR=cfg.LINEAR, GAMMA=cfg.GAMMA, LOSS_CLIP=cfg.LOSS_CLIP,
+                                   VALUE_LEARNING=False, REMOVE_BEFORE_REWARD=cfg.REMOVE_BEFORE_REWARD)
+    model = RefNet(3, 5, extra_capacity=True, panorama=False)
+    target = RefNet(3, 5, extra_capacity=True, panorama=False)
+    restore()
+    model.load_state_dict(qstep.init_state(seed=4), strict=True)
+    target.load_state_dict(model.state_dict())
+    target.eval()
+    opt = torch.optim.Adam(model.parameters(), lr=cfg.LEARNING_RATE)
+    process_batch = make_goldens.lift_process_batch(model, target, refcfg)
+    data = [qstep.synthetic_batch(batch, seed=1 + i) for i in range(2)]
+
+    def one(b):
+        model.set_train()
+        opt.zero_grad()
+        loss = process_batch(b)
+        loss.backward()
+        opt.step()
+        return loss.item()
+    for i in range(warmup):
+        one(data[i % 2])
+    times = []
+    for i in range(steps):
+        t0 = time.perf_counter()
+        one(data[i % 2])
+        times.append(time.perf_counter() - t0)
+    return statistics.median(times) if times else 0.0
+
+
 def run_reference(a, out_stream=sys.stdout):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
     B = 8
-    steps, warmup = max(1, min(a.steps, 12)), max(1, min(a.warmup, 3))
-    dt = cpu_reference_arm(steps, warmup, B, threads)
+    steps, warmup = max(1, a.steps), max(0, a.warmup)       # as given; a B = 8 step is ~0.1 s on 16 cores
+    ref_dir = find_reference()
+    kind, dt = "port", None
+    if ref_dir is not None:
+        try:
+            dt = cpu_reference_real(ref_dir, steps, warmup, B, threads)
+            kind = "reference"
+        except Exception as exc:                            # noqa: BLE001  (report the port instead)
+            print(f"reference arm: could not run the reference from {ref_dir}: {exc!r}", file=sys.stderr)
+    if dt is None:
+        dt = cpu_reference_arm(steps, warmup, B, threads)
     fps = 2 * B / dt
+    what = ("the reference's own HabitatDQNMultiAction + process_batch + torch.optim.Adam"
+            if kind == "reference" else "fp32 oracle port")
     sample = (f"median of {steps} steps of {B} quadruplets after {warmup} warm-up steps (of the {BATCH_PER_GPU}-quadruplet "
-              "workload), fp32 oracle port on all host cores")
+              f"workload), {what}, fp32, all host cores")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": a.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": dt * 1e3, "steps_per_sec": 1.0 / dt,
@@ -149,7 +254,7 @@ def run_reference(a, out_stream=sys.stdout):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": dict(make_config(a.gpus, BATCH_PER_GPU, False), cuda_graph=None, parallelism="cpu",
                        sample=sample, threads=threads),
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }), file=out_stream, flush=True)
 
@@ -246,6 +351,57 @@ def _basic_block(dev, B):
     return out
 
 
+def dp_check(dev, rank, world, make_sync):
+    """On-hardware data-parallel correctness (the reference has no DP, train_q_network.py:275):
+    every rank takes ONE small step on its own 8 quadruplets with the gradient exchange of the timed run,
+    then (a) the parameters of all ranks must be bit-identical and (b) the exchanged (averaged) gradient is
+    compared with the gradient a single process computes on the concatenated global batch (the loss is a
+    mean over B*5 entries, so the global-batch gradient is the average of the per-rank ones)."""
+    import torch
+    import torch.distributed as dist
+    from video_dqn_b200.learner import QLearner, StepConfig
+    from video_dqn_b200.qnet import HabitatDQNMultiAction
+    Bs = 8
+
+    def nets():
+        torch.manual_seed(4)
+        m = HabitatDQNMultiAction(3, 5, extra_capacity=True, panorama=False).to(dev)
+        t = HabitatDQNMultiAction(3, 5, extra_capacity=True, panorama=False).to(dev)
+        t.load_state_dict(m.state_dict())
+        return m, t
+    m, t = nets()
+    lr = QLearner(m, t, StepConfig(), batch_size=Bs, frames_uint8=True, use_graph=False, world_size=world)
+    lr.grad_sync = make_sync(lr)
+    lr.step([x.to(dev) for x in synthetic_quads(Bs, seed=500 + rank, pinned=False)])
+    torch.cuda.synchronize()
+    p = lr.opt.param_arena
+    ref = p.clone()
+    dist.broadcast(ref, 0)
+    diff = (p - ref).abs().max().reshape(1)
+    dist.all_reduce(diff, op=dist.ReduceOp.MAX)
+    g_avg = (lr.opt.grad_arena / world).clone()
+    loss_mean = lr.loss.clone()
+    dist.all_reduce(loss_mean, op=dist.ReduceOp.SUM)
+    out = {"batch_per_rank": Bs, "max_param_diff_across_ranks": float(diff.item())}
+    if hasattr(lr.grad_sync, "close"):
+        lr.grad_sync.close()
+    del lr, m, t
+    if rank == 0:
+        m, t = nets()
+        big = QLearner(m, t, StepConfig(), batch_size=world * Bs, frames_uint8=True, use_graph=False)
+        parts = [synthetic_quads(Bs, seed=500 + r, pinned=False) for r in range(world)]
+        big.step([torch.cat([pt[i] for pt in parts]).to(dev) for i in range(7)])
+        torch.cuda.synchronize()
+        g = big.opt.grad_arena
+        out["avg_grad_rel_l2_vs_global_batch"] = float(((g_avg - g).norm() / g.norm()).item())
+        out["loss_mean_over_ranks"] = float(loss_mean.item() / world)
+        out["loss_global_batch"] = float(big.loss.item())
+        del big, m, t
+    torch.cuda.empty_cache()
+    dist.barrier()
+    return out
+
+
 # ----------------------------------------------------------------------------------------------
 def _claim_stdout():
     """The contract is ONE JSON line on stdout.  Native libraries write there too (NCCL prints its
@@ -301,7 +457,9 @@ def main():
     target.eval()
     learner = QLearner(model, target, StepConfig(), batch_size=B, frames_uint8=True,
                        use_graph=not a.no_graph, world_size=world)
+    dpc = None
     if world > 1:
+        dpc = dp_check(dev, rank, world, GradSync)
         learner.grad_sync = GradSync(learner)
     host = [synthetic_quads(B, seed=1 + rank + 97 * i) for i in range(3)]
     pool = [[t.to(dev) for t in b] for b in host]          # device-resident batches (> L2 together)
@@ -320,7 +478,7 @@ def main():
 
     # ---------------- device-resident timing ("value")
     sampler = ClockSampler(local)
-    sampler.start()                            # nvidia-smi needs ~0.5 s to start streaming samples
+    sampler.start()
     learner.model._state(); learner.target_net._state()
     torch.cuda.synchronize()
     lc0 = lib.vdqn_launch_count()
@@ -333,14 +491,16 @@ def main():
     torch.cuda.synchronize()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_region0 = time.perf_counter()
     e0.record()
     for i in range(a.steps):
         learner.load_batch(pool[i % len(pool)])
         learner.step()
     e1.record()
     barrier()
+    t_region1 = time.perf_counter()
     ms = max_over_ranks(e0.elapsed_time(e1)) / a.steps
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_region0, t_region1)
     loss_dev = float(learner.loss.item())
 
     # ---------------- per-kernel roofline (eager instrumented steps, CUDA events on the launch stream)
@@ -351,15 +511,25 @@ def main():
         learner.use_graph = False
         learner.grad_sync = None           # rank-local pass: no collectives (other ranks are not in it)
         ops.PROFILE = []
-        nprof = 3
+        nprof = 10
+        marks = []
         for i in range(nprof):
             learner.load_batch(pool[i % len(pool)])
             learner.step()
+            marks.append(len(ops.PROFILE))
         torch.cuda.synchronize()
-        agg = {}
-        for kind, tag, s, e in ops.PROFILE:
-            t, n = agg.get(kind, (0.0, 0))
-            agg[kind] = (t + s.elapsed_time(e), n + 1)
+        # per kernel family: the MEDIAN over the instrumented steps of that step's summed launch time
+        # (x nprof, so the per-step / per-launch arithmetic below is unchanged)
+        per_step, lo = [], 0
+        for hi in marks:
+            d = {}
+            for kind, tag, s, e in ops.PROFILE[lo:hi]:
+                t, n = d.get(kind, (0.0, 0))
+                d[kind] = (t + s.elapsed_time(e), n + 1)
+            per_step.append(d)
+            lo = hi
+        agg = {k: (statistics.median(d[k][0] for d in per_step if k in d) * nprof,
+                   sum(d[k][1] for d in per_step if k in d)) for k in per_step[0]}
         learner.use_graph, learner.grad_sync = learner_use_graph, saved_sync
         step_ms_eager = sum(t for t, _ in agg.values()) / nprof
         breakdown = {k: {"ms_per_step": round(t / nprof, 4), "launches_per_step": n / nprof}
@@ -416,6 +586,9 @@ def main():
             tr = json.load(open(ncu))
             if roof["kernel"] in tr:
                 roof["traffic"] = tr[roof["kernel"]]
+                roof["traffic_source"] = ("profiles/ncu_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum per "
+                                          "launch from the committed ncu launch list of this command (not measured in "
+                                          "this run: ncu cannot run inside a timed bench)")
             for r in roof_other:
                 if r.get("kernel") in tr:
                     r["traffic"] = tr[r["kernel"]]
@@ -526,7 +699,7 @@ def main():
             "loss": loss_dev,
             "clocks": clocks, "gpu_launches": (per_step_launches or 0) * a.steps,
             "gpu_launches_per_step": per_step_launches,
-            "e2e": e2e, "roofline": roof, "roofline_kernels": roof_other, "cpu_baseline": cpu,
+            "dp_check": dpc, "e2e": e2e, "roofline": roof, "roofline_kernels": roof_other, "cpu_baseline": cpu,
             "breakdown_eager_ms": breakdown if rank == 0 else None,
             "inference": inference, "inverse_model": inverse, "basic_architecture": basic,
         }

@@ -244,6 +244,10 @@ typedef struct vdqn_td_desc {
    * otherwise l = 0.5 (q_b - gt)^2 and NaNs propagate as in the reference. */
   const double* gt;
   int32_t ground_truth, value_learning;
+  /* CONFIDENCE_REWARD (train_q_network.py:101, dataloaders/q_learning_real.py:76-77): the loader then
+   * yields the detector scores (floating point) as reward and terminal, which process_batch casts with
+   * `.float()` (:158-160).  labels_f32 != 0: rew / term / valid point to float32 arrays (the cast done). */
+  int32_t labels_f32;
 } vdqn_td_desc;
 int vdqn_td_epilogue(const vdqn_td_desc* d, void* stream);
 

@@ -29,6 +29,9 @@ CASES = [
     ("masked", 3, {"REMOVE_BEFORE_REWARD": True}, False),
     ("gt_value_learning", 1, {"VALUE_LEARNING": True}, True),
     ("gt_plain", 3, {"VALUE_LEARNING": False}, True),
+    # CONFIDENCE_REWARD (train_q_network.py:101): reward = terminal = the float64 detector scores
+    # (dataloaders/q_learning_real.py:76-77); process_batch takes their .float() (:158-160)
+    ("confidence_reward", 3, {"REMOVE_BEFORE_REWARD": True, "_float_labels": True}, False),
 ]
 
 
@@ -42,6 +45,9 @@ def build_case(name, A, over, gt_mode, seed):
         q_no[0, 0, 1] = q_no[0, 0, 0] = q_no[0, 0].max() + 1.0      # an exact tie: first index must win
     act = torch.randint(0, A, (B,), generator=g)
     rew = (torch.rand(B, C, generator=g) < 0.3).long()
+    over = dict(over)
+    if over.pop("_float_labels", False):
+        rew = torch.rand(B, C, generator=g, dtype=torch.float64)
     valid = (torch.rand(B, C, generator=g) < 0.7).long()
     if gt_mode:
         steps = torch.randint(0, 30, (B, C), generator=g).double()

@@ -16,11 +16,14 @@
  */
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 
-int td_ref(const float* q_s, const float* q_no, const float* q_nt, const int64_t* act, const int64_t* rew,
-           const int64_t* term, const int64_t* valid, const double* gt, int B, int C, int A, float gamma,
-           int double_dqn, int clip_rect, int linear, int use_valid, int ground_truth, int value_learning,
-           float* dq, float* y_out, int64_t* best_out, float* loss_out) {
+/* labels (rew / term / valid_mask) as fp32: what `.float()` makes of the loader's int64 detections or, with
+ * CONFIDENCE_REWARD, of its float64 detector scores (train_q_network.py:158-160, 166-167) */
+int td_ref_f32(const float* q_s, const float* q_no, const float* q_nt, const int64_t* act, const float* rew,
+               const float* term, const float* valid, const double* gt, int B, int C, int A, float gamma,
+               int double_dqn, int clip_rect, int linear, int use_valid, int ground_truth, int value_learning,
+               float* dq, float* y_out, int64_t* best_out, float* loss_out) {
   if (B < 0 || C < 1 || A < 1) return -2;
   const long total = (long)B * C;
   const float inv = total > 0 ? 1.0f / (float)total : 0.f;
@@ -48,14 +51,14 @@ int td_ref(const float* q_s, const float* q_no, const float* q_nt, const int64_t
       for (int a = 1; a < A; ++a)
         if (sel[a] > bv) { bv = sel[a]; best = a; }               /* argmax(-1): first maximum (:147) */
       float q_a = q_nt[i * A + best];                             /* :153-154 */
-      q_a = q_a * (1.f - (float)term[i]);                         /* :158 */
-      y = linear ? (float)rew[i] + (q_a - 0.1f) : (float)rew[i] + gamma * q_a;   /* :159-162 */
+      q_a = q_a * (1.f - term[i]);                                /* :158 */
+      y = linear ? rew[i] + (q_a - 0.1f) : rew[i] + gamma * q_a;  /* :159-162 */
       if (clip_rect) y = fminf(fmaxf(y, 0.f), 1.f);               /* :163-164 */
       diff = q_b - y;
     }
     float l = 0.5f * (diff * diff);                               /* :165 */
     if (use_valid && !ground_truth) {                             /* :166-167 */
-      mask = (float)valid[i];
+      mask = valid[i];
       l = l * mask;
     }
     sum += (double)l;
@@ -66,6 +69,26 @@ int td_ref(const float* q_s, const float* q_no, const float* q_nt, const int64_t
   }
   if (loss_out != 0) *loss_out = (float)(sum * (double)inv);      /* .mean() (:180) */
   return 0;
+}
+
+/* the loader's usual int64 labels (dataloaders/q_learning_real.py:78-84) */
+int td_ref(const float* q_s, const float* q_no, const float* q_nt, const int64_t* act, const int64_t* rew,
+           const int64_t* term, const int64_t* valid, const double* gt, int B, int C, int A, float gamma,
+           int double_dqn, int clip_rect, int linear, int use_valid, int ground_truth, int value_learning,
+           float* dq, float* y_out, int64_t* best_out, float* loss_out) {
+  if (B < 0 || C < 1 || A < 1) return -2;
+  const long total = (long)B * C;
+  float* f = (float*)malloc(sizeof(float) * 3 * (size_t)(total > 0 ? total : 1));
+  if (f == 0) return -3;
+  for (long i = 0; i < total; ++i) {
+    f[i] = rew != 0 ? (float)rew[i] : 0.f;
+    f[total + i] = term != 0 ? (float)term[i] : 0.f;
+    f[2 * total + i] = valid != 0 ? (float)valid[i] : 1.f;
+  }
+  const int rc = td_ref_f32(q_s, q_no, q_nt, act, f, f + total, f + 2 * total, gt, B, C, A, gamma, double_dqn,
+                            clip_rect, linear, use_valid, ground_truth, value_learning, dq, y_out, best_out, loss_out);
+  free(f);
+  return rc;
 }
 
 int adam_ref(float* p, const float* g, float* m, float* v, long n, double lr, double b1, double b2, double eps,

@@ -394,11 +394,15 @@ def test_td_branches_match_reference_goldens_on_device():
     dev = _dev()
     z = np.load(os.path.join(GOLD, "td_branches.npz"))
     names = sorted({k.split("/")[0] for k in z.files})
-    assert len(names) == 6
+    assert len(names) == 7
     for nm in names:
         c = {k.split("/")[1]: torch.from_numpy(z[k]) for k in z.files if k.startswith(nm + "/")}
         gamma, rect, linear, masked, vl, gt_mode, A = c["cfg"].tolist()
         d = {k: v.to(dev) for k, v in c.items()}
+        if c["rew"].is_floating_point():       # CONFIDENCE_REWARD: float64 scores, `.float()` (train_q_network.py:158-160)
+            with pytest.raises(ValueError):
+                ops.td_epilogue(d["q_s"], d["q_no"], d["q_nt"], d["act"], d["rew"], d["rew"])      # float64: refused
+            d["rew"], d["valid"] = d["rew"].float(), d["valid"].float()
         if gt_mode:
             loss, dq, _, _ = ops.td_epilogue(d["q_s"], None, None, d["act"], None, None, gt=d["gt"],
                                              value_learning=bool(vl))

@@ -1,0 +1,250 @@
+"""Parity of the fused step at every BASELINE configuration the bench runs, and the tight gradient bar.
+
+* B = 256 / B = 64 (the one-pass 3B schedule `bench.py` times, BASELINE configs[1]) against the fp32
+  oracle: loss, arg-max where the margin is clear, all 68 gradients;
+* F = 4 (PANORAMA / PREVIOUS_IMAGES, train_q_network.py:36-47) through `QLearner`, two-pass and one-pass;
+* the tight bar: against `oracle/qstep_bf16.py`, the same reference graph with the kernels' rounding
+  points (bf16 operands / stored activations / stored gradients, fp32 accumulation), what is left is
+  accumulation order, so a wrong scale factor in ONE layer (a mis-folded BatchNorm, a wrong d gamma)
+  cannot hide in bf16 noise: per-tensor norm ratio, per-tensor cosine and rel-L2;
+* SURVEY 8d's "bf16-autocast GPU run of the reference Python": qstep under torch.autocast on the GPU as
+  a third opinion.  Two different bf16 schedules differ from each other by about as much as each
+  differs from fp32 (independent rounding), so the bar SURVEY guessed (rel-L2 <= 3e-2) is not one any
+  bf16 implementation can meet against another; what is asserted is that this path is no further
+  from the fp32 oracle than PyTorch's own bf16 is, and the three distances are written to
+  gpurun_out/grad_bars.json.
+
+Needs a B200: `pytest -m gpu`.
+"""
+import json
+import os
+
+import pytest
+import torch
+
+from oracle import qstep, qstep_bf16
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+Q_TOL, LOSS_RTOL, MARGIN = 1e-2, 5e-3, 2e-2
+# against the rounding-point oracle (measured on B200, gpurun_out/grad_bars.json: see DESIGN.md 2)
+EMUL_GLOBAL_REL, EMUL_TENSOR_REL, EMUL_NORM, EMUL_COS = 3e-2, 6e-2, 2e-2, 0.998
+
+
+def _dev():
+    return torch.device("cuda:0")
+
+
+def _build(sd, device, action_dim=3, panorama=False):
+    from video_dqn_b200.qnet import HabitatDQNMultiAction
+    m = HabitatDQNMultiAction(action_dim, 5, extra_capacity=True, panorama=panorama)
+    m.load_state_dict(sd, strict=True)
+    return m.to(device)
+
+
+def _note(key, value):
+    """measured numbers go to gpurun_out/grad_bars.json (scratch; copied into profiles/ by hand)"""
+    try:
+        d = os.path.join(ROOT, "gpurun_out")
+        os.makedirs(d, exist_ok=True)
+        p = os.path.join(d, "grad_bars.json")
+        cur = json.load(open(p)) if os.path.exists(p) else {}
+        cur[key] = value
+        json.dump(cur, open(p, "w"), indent=1, sort_keys=True)
+    except Exception:
+        pass
+
+
+def _fp32_bars(got, ref, names):
+    rows, rel = qstep_bf16.grad_report(got, ref, names)
+    for n, (c, _nr, _r) in rows.items():
+        assert torch.isfinite(got[n]).all(), n
+        floor = 0.90 if n in ("resnet.conv1.weight", "resnet.bn1.weight", "resnet.bn1.bias") else 0.95
+        assert c >= floor, f"{n}: cosine {c:.4f} < {floor}"
+    assert rel <= 0.2, f"global gradient rel-L2 {rel:.3f} vs the fp32 oracle"
+    return rows, rel
+
+
+def _emul_bars(got, ref, names, tag):
+    rows, rel = qstep_bf16.grad_report(got, ref, names)
+    worst_c = min(rows.items(), key=lambda kv: kv[1][0])
+    worst_n = max(rows.items(), key=lambda kv: abs(kv[1][1]))
+    worst_r = max(rows.items(), key=lambda kv: kv[1][2])
+    _note(tag, {"global_rel_l2": rel, "worst_cosine": [worst_c[0], worst_c[1][0]],
+                "worst_norm_ratio_minus_1": [worst_n[0], worst_n[1][1]],
+                "worst_rel_l2": [worst_r[0], worst_r[1][2]]})
+    print(f"{tag}: vs rounding-point oracle: global rel-L2 {rel:.4f}, worst cosine {worst_c[1][0]:.5f} "
+          f"({worst_c[0]}), worst |norm ratio - 1| {abs(worst_n[1][1]):.4f} ({worst_n[0]}), worst rel-L2 "
+          f"{worst_r[1][2]:.4f} ({worst_r[0]})")
+    assert rel <= EMUL_GLOBAL_REL, f"global rel-L2 {rel:.4f} vs the rounding-point oracle"
+    for n, (c, nr, r) in rows.items():
+        assert c >= EMUL_COS, f"{n}: cosine {c:.5f}"
+        assert abs(nr) <= EMUL_NORM, f"{n}: gradient norm off by {nr:+.4f}"
+        assert r <= EMUL_TENSOR_REL, f"{n}: rel-L2 {r:.4f}"
+    return rows, rel
+
+
+def _argmax_clear(best_gpu, aux):
+    top2 = aux["q_next_online"].topk(2, dim=-1).values
+    clear = (top2[..., 0] - top2[..., 1]) > MARGIN
+    assert clear.float().mean().item() > 0.3
+    assert (best_gpu.cpu()[clear] == aux["best"][clear]).all()
+
+
+@pytest.mark.parametrize("B,graph", [(8, False), (64, True), (256, True)])
+def test_fused_step_against_both_oracles(B, graph):
+    """The fused step (B = 64 / 256: the one-pass 3B schedule, graph-captured as bench.py runs it)
+    against the fp32 oracle (SURVEY 8d bars) and the rounding-point oracle (tight bars)."""
+    from video_dqn_b200.learner import QLearner, StepConfig
+    dev = _dev()
+    sd = qstep.init_state(seed=4, randomize_bn=True)
+    sd_t = qstep.init_state(seed=5, randomize_bn=True)           # online and target networks DIFFER
+    batch = qstep.synthetic_batch(B, seed=3)
+    names = qstep.grad_param_names()
+    ref32 = qstep.OracleTrainer(sd)
+    ref32.target = {k: v.clone() for k, v in sd_t.items()}
+    ref32._realias(ref32.target)
+    refbf = qstep_bf16.EmulatedTrainer(sd)
+    refbf.target = {k: v.clone() for k, v in sd_t.items()}
+    refbf._realias(refbf.target)
+    l32, g32, a32 = ref32.loss_and_grads(batch)
+    lbf, gbf, abf = refbf.loss_and_grads(batch)
+    lr = QLearner(_build(sd, dev), _build(sd_t, dev), StepConfig(), batch_size=B, use_graph=graph)
+    assert lr.one_pass == (B % 64 == 0)
+    dbatch = [t.to(dev) for t in batch]
+    for _ in range(2 if graph else 1):               # graph: eager step, then capture + replay
+        # every step starts from the oracle's weights: undo the previous Adam update
+        lr.model.load_state_dict(sd)
+        lr.opt._m.flat.zero_(); lr.opt._v.flat.zero_()
+        lr.model._state()
+        loss = lr.step(dbatch)
+    torch.cuda.synchronize()
+    lv = loss.item()
+    q_s = lr.ws_train.q[:B].view(B, 5, 3).cpu()
+    assert abs(lv - l32.item()) <= LOSS_RTOL * abs(l32.item()), (lv, l32.item())
+    assert (q_s - a32["q_s"]).abs().max().item() <= Q_TOL
+    _argmax_clear(lr.best, a32)
+    got = {n: g.detach().cpu() for n, g in lr.G.items()}
+    _, rel32 = _fp32_bars(got, g32, names)
+    # tight bars
+    dq_max = (q_s - abf["q_s"]).abs().max().item()
+    _note(f"fused_B{B}_summary", {"loss": lv, "loss_fp32_oracle": l32.item(), "loss_rounding_oracle": lbf.item(),
+                                  "q_maxabs_vs_rounding_oracle": dq_max, "grad_rel_l2_vs_fp32": rel32})
+    _emul_bars(got, gbf, names, f"fused_B{B}")
+    assert abs(lv - lbf.item()) <= 1e-3 * abs(lbf.item()), (lv, lbf.item())
+    assert dq_max <= 2e-3, dq_max
+
+
+@pytest.mark.parametrize("B", [2, 16])
+def test_fused_step_four_frames(B):
+    """F = 4 through QLearner (B = 16: 64 frames per forward -> the one-pass schedule)."""
+    from video_dqn_b200.learner import QLearner, StepConfig
+    dev = _dev()
+    sd = qstep.init_state(seed=4, randomize_bn=True, num_frames=4)
+    g = torch.Generator().manual_seed(13)
+    base = qstep.synthetic_batch(B, seed=4)
+    before = torch.randn(B, 4, 3, 224, 224, generator=g)
+    after = torch.randn(B, 4, 3, 224, 224, generator=g)
+    batch = (before, after) + tuple(base[2:])
+    names = qstep.grad_param_names()
+    l32, g32, a32 = qstep.OracleTrainer(sd).loss_and_grads(batch)
+    lbf, gbf, abf = qstep_bf16.EmulatedTrainer(sd).loss_and_grads(batch)
+    lr = QLearner(_build(sd, dev, panorama=True), _build(sd, dev, panorama=True), StepConfig(), batch_size=B,
+                  use_graph=False)
+    assert lr.plan.num_frames == 4 and lr.one_pass == (B == 16)
+    loss = lr.step([t.to(dev) for t in batch])
+    torch.cuda.synchronize()
+    lv = loss.item()
+    assert abs(lv - l32.item()) <= LOSS_RTOL * abs(l32.item()), (lv, l32.item())
+    q_s = lr.ws_train.q[:B].view(B, 5, 3).cpu()
+    assert (q_s - a32["q_s"]).abs().max().item() <= Q_TOL
+    got = {n: g_.detach().cpu() for n, g_ in lr.G.items()}
+    _fp32_bars(got, g32, names)
+    _emul_bars(got, gbf, names, f"fused_F4_B{B}")
+
+
+def test_three_way_bf16_comparison():
+    """SURVEY 8d's second gradient bar, as measured: this path, PyTorch's bf16 autocast of the oracle on
+    the same GPU, and the fp32 oracle.  Asserted: this path is not further from fp32 than autocast is
+    (x1.25 + 1e-2 slack).  Written to gpurun_out/grad_bars.json: all three pairwise distances."""
+    from video_dqn_b200.learner import QLearner, StepConfig
+    dev = _dev()
+    B = 8
+    sd = qstep.init_state(seed=4, randomize_bn=True)
+    batch = qstep.synthetic_batch(B, seed=1)
+    names = qstep.grad_param_names()
+    l32, g32, _ = qstep.OracleTrainer(sd).loss_and_grads(batch)
+    # the oracle itself on the GPU under autocast (cuDNN / cuBLAS bf16): test infrastructure, not product
+    sd_gpu = {k: v.to(dev) for k, v in sd.items()}
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        lac, gac, _ = qstep.OracleTrainer(sd_gpu).loss_and_grads([t.to(dev) for t in batch])
+    gac = {n: v.float().cpu() for n, v in gac.items()}
+    lr = QLearner(_build(sd, dev), _build(sd, dev), StepConfig(), batch_size=B, use_graph=False)
+    loss = lr.step([t.to(dev) for t in batch])
+    torch.cuda.synchronize()
+    got = {n: g.detach().cpu() for n, g in lr.G.items()}
+    _, ours_fp32 = qstep_bf16.grad_report(got, g32, names)
+    _, auto_fp32 = qstep_bf16.grad_report(gac, g32, names)
+    _, ours_auto = qstep_bf16.grad_report(got, gac, names)
+    _note("three_way_B8", {"ours_vs_fp32": ours_fp32, "autocast_vs_fp32": auto_fp32, "ours_vs_autocast": ours_auto,
+                           "loss_ours": loss.item(), "loss_fp32": l32.item(), "loss_autocast": float(lac)})
+    print(f"gradient rel-L2: ours vs fp32 {ours_fp32:.4f}, autocast vs fp32 {auto_fp32:.4f}, ours vs autocast "
+          f"{ours_auto:.4f}")
+    assert ours_fp32 <= 1.25 * auto_fp32 + 1e-2
+    assert ours_auto <= 0.2
+
+
+@pytest.mark.parametrize("B,use_valid,double_dqn", [(1 << 20, False, True), (300001, True, True), (70001, False, False)])
+def test_streaming_td_epilogue_is_bit_identical_to_the_per_thread_kernel(B, use_valid, double_dqn):
+    """Large batches take the bulk-copy TD kernel (td_bulk.cu) on the full 1024-element chunks + the
+    per-thread kernel on the tail.  Against the same batch pushed through the per-thread kernels in slices
+    of 8192 samples (below the streaming threshold): y, arg-max and dQ bit-identical, loss to fp32 summation
+    order; and against the oracle's formula on the CPU."""
+    from video_dqn_b200 import ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(B)
+    q = [torch.randn(B, 5, 3, generator=g).to(dev) for _ in range(3)]
+    act = torch.randint(0, 3, (B,), generator=g).to(dev)
+    rew = (torch.rand(B, 5, generator=g) < 0.1).long().to(dev)
+    valid = (torch.rand(B, 5, generator=g) < 0.7).long().to(dev)
+    kw = dict(use_valid=use_valid, double_dqn=double_dqn, inv_count=1.0 / (B * 5))
+    loss, dq, best, y = ops.td_epilogue(q[0], q[1], q[2], act, rew, rew, valid, want_aux=True, **kw)
+    S = 8192
+    loss2 = torch.zeros(1, device=dev)
+    dq2, best2, y2 = torch.empty_like(dq), torch.empty_like(best), torch.empty_like(y)
+    for lo in range(0, B, S):
+        hi = min(B, lo + S)
+        ops.td_epilogue(q[0][lo:hi], q[1][lo:hi], q[2][lo:hi], act[lo:hi], rew[lo:hi], rew[lo:hi], valid[lo:hi],
+                        dq=dq2[lo:hi], loss=loss2, best=best2[lo:hi], y=y2[lo:hi], **kw)
+    torch.cuda.synchronize()
+    assert torch.equal(dq, dq2) and torch.equal(best, best2) and torch.equal(y, y2)
+    assert abs(loss.item() - loss2.item()) <= 2e-6 * abs(loss2.item())
+    cfg = qstep.StepConfig(double_dqn=double_dqn, REMOVE_BEFORE_REWARD=use_valid)
+    l_ref, aux = qstep.td_loss(q[0].cpu(), q[1].cpu(), q[2].cpu(), act.cpu(), rew.cpu(), rew.cpu(), valid.cpu(), cfg)
+    assert torch.equal(y.cpu(), aux["y"]) and torch.equal(best.cpu(), aux["best"])
+    assert abs(loss.item() - l_ref.item()) <= 1e-5 * abs(l_ref.item())
+
+
+def test_confidence_reward_step():
+    """CONFIDENCE_REWARD (train_q_network.py:101): float64 detector scores as reward and terminal
+    (dataloaders/q_learning_real.py:76-77), used as `.float()` by process_batch (:158-160).  A learner built
+    for it keeps fp32 label buffers; one built without refuses such a batch instead of truncating it to 0."""
+    from video_dqn_b200.learner import QLearner, StepConfig
+    dev = _dev()
+    B = 8
+    sd = qstep.init_state(seed=4, randomize_bn=True)
+    before, after, act, _rew, _term, gt, valid = qstep.synthetic_batch(B, seed=2)
+    g = torch.Generator().manual_seed(5)
+    score = torch.rand(B, 5, generator=g, dtype=torch.float64)
+    batch = (before, after, act, score, score.clone(), gt, valid)
+    l_ref, g_ref, aux = qstep.OracleTrainer(sd).loss_and_grads(batch)
+    lr = QLearner(_build(sd, dev), _build(sd, dev), StepConfig(CONFIDENCE_REWARD=True), batch_size=B, use_graph=False)
+    loss = lr.step([t.to(dev) for t in batch])
+    torch.cuda.synchronize()
+    assert abs(loss.item() - l_ref.item()) <= LOSS_RTOL * abs(l_ref.item()), (loss.item(), l_ref.item())
+    assert (lr.y.cpu() - aux["y"]).abs().max().item() <= Q_TOL
+    _fp32_bars({n: g_.detach().cpu() for n, g_ in lr.G.items()}, g_ref, qstep.grad_param_names())
+    plain = QLearner(_build(sd, dev), _build(sd, dev), StepConfig(), batch_size=B, use_graph=False)
+    with pytest.raises(ValueError, match="CONFIDENCE_REWARD"):
+        plain.step([t.to(dev) for t in batch])

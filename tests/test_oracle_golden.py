@@ -127,7 +127,7 @@ def test_td_branches_match_reference_goldens():
         assert torch.equal(loss.detach(), c["loss"]), nm
         assert torch.equal(qs.grad, c["dq"]), nm
         n += 1
-    assert n == 6
+    assert n == 7
 
 
 def test_inverse_model_oracle_reproduces_reference_golden():
@@ -237,6 +237,8 @@ def _tdref():
     P = C.c_void_p
     lib.td_ref.argtypes = [P] * 8 + [C.c_int] * 3 + [C.c_float] + [C.c_int] * 6 + [P] * 4
     lib.td_ref.restype = C.c_int
+    lib.td_ref_f32.argtypes = lib.td_ref.argtypes
+    lib.td_ref_f32.restype = C.c_int
     lib.adam_ref.argtypes = [P, P, P, P, C.c_long, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int]
     lib.adam_ref.restype = C.c_int
     return lib
@@ -246,19 +248,24 @@ def test_c_restatement_of_td_loss_matches_reference_goldens():
     lib = _tdref()
     z = np.load(os.path.join(GOLD, "td_branches.npz"))
     names = sorted({k.split("/")[0] for k in z.keys()})
-    assert len(names) == 6
+    assert len(names) == 7
     ptr = lambda a: a.ctypes.data  # noqa: E731
     for name in names:
         gamma, rect, linear, use_valid, value_learning, gt_mode, A = z[f"{name}/cfg"]
         q_s, q_no, q_nt = (np.ascontiguousarray(z[f"{name}/{k}"], dtype=np.float32) for k in ("q_s", "q_no", "q_nt"))
-        act, rew, valid = (np.ascontiguousarray(z[f"{name}/{k}"], dtype=np.int64) for k in ("act", "rew", "valid"))
+        # CONFIDENCE_REWARD case: float64 scores in the fixture, `.float()` = fp32 labels for td_ref_f32
+        flt = z[f"{name}/rew"].dtype.kind == "f"
+        ldt = np.float32 if flt else np.int64
+        act = np.ascontiguousarray(z[f"{name}/act"], dtype=np.int64)
+        rew, valid = (np.ascontiguousarray(z[f"{name}/{k}"], dtype=ldt) for k in ("rew", "valid"))
         B, Cc = rew.shape
         gt = np.ascontiguousarray(np.broadcast_to(z[f"{name}/gt"].reshape(B, -1), (B, Cc)), dtype=np.float64)
         dq, y = np.empty_like(q_s), np.empty((B, Cc), np.float32)
         best, loss = np.empty((B, Cc), np.int64), np.zeros(1, np.float32)
-        rc = lib.td_ref(ptr(q_s), ptr(q_no), ptr(q_nt), ptr(act), ptr(rew), ptr(rew), ptr(valid), ptr(gt), B, Cc,
-                        int(A), float(gamma), 1, int(rect), int(linear), int(use_valid), int(gt_mode),
-                        int(value_learning), ptr(dq), ptr(y), ptr(best), ptr(loss))
+        fn = lib.td_ref_f32 if flt else lib.td_ref
+        rc = fn(ptr(q_s), ptr(q_no), ptr(q_nt), ptr(act), ptr(rew), ptr(rew), ptr(valid), ptr(gt), B, Cc,
+                int(A), float(gamma), 1, int(rect), int(linear), int(use_valid), int(gt_mode),
+                int(value_learning), ptr(dq), ptr(y), ptr(best), ptr(loss))
         assert rc == 0
         ref_loss = float(z[f"{name}/loss"])
         if np.isnan(ref_loss):
@@ -269,8 +276,8 @@ def test_c_restatement_of_td_loss_matches_reference_goldens():
         if not gt_mode:                                   # arg-max against the torch oracle: integers, exact
             cfg = qstep.StepConfig(GAMMA=float(gamma), LOSS_CLIP="rect" if rect else "none", LINEAR=bool(linear),
                                    action_dim=int(A))
-            b_ref, y_ref = qstep.td_targets(torch.from_numpy(q_no), torch.from_numpy(q_nt), torch.from_numpy(rew),
-                                            torch.from_numpy(rew), cfg)
+            rew_t = torch.from_numpy(z[f"{name}/rew"])
+            b_ref, y_ref = qstep.td_targets(torch.from_numpy(q_no), torch.from_numpy(q_nt), rew_t, rew_t, cfg)
             assert (best == b_ref.numpy()).all(), name
             np.testing.assert_array_equal(y, y_ref.numpy(), err_msg=name)      # same fp32 operations: bit-exact
 
@@ -339,3 +346,29 @@ def test_c_restatement_agrees_with_the_torch_oracle_on_random_cases():
         np.testing.assert_array_equal(y, aux["y"].numpy(), err_msg=str(case))
         np.testing.assert_allclose(dq, qs.grad.numpy(), rtol=0, atol=1e-7, err_msg=str(case))
         assert abs(loss[0] - l_ref.item()) <= 1e-6 * max(1.0, abs(l_ref.item())), case
+
+
+def test_rounding_point_oracle_is_the_same_graph():
+    """oracle/qstep_bf16.py (the tight-bar oracle of tests/test_gpu_parity_full.py) is qstep's graph with
+    rounding inserted: with the rounding functions switched off it reproduces qstep (BatchNorm folding is
+    exact up to fp32 round-off), with them on it sits at bf16 distance from it."""
+    from oracle import qstep_bf16 as qb
+    sd = qstep.init_state(seed=4, randomize_bn=True)
+    batch = qstep.synthetic_batch(2, seed=1)
+    l0, g0, a0 = qstep.OracleTrainer(sd).loss_and_grads(batch)
+    l1, g1, a1 = qb.EmulatedTrainer(sd).loss_and_grads(batch)
+    assert abs(l1.item() - l0.item()) <= 1e-2 * abs(l0.item())
+    assert (a1["q_s"] - a0["q_s"]).abs().max().item() <= 1e-2
+    _, rel = qb.grad_report(g1, g0)
+    assert 1e-2 < rel < 0.2                                  # it does round, and only that
+    saved = (qb._RoundBoth.apply, qb._RoundValue.apply, qb._RoundGrad.apply)
+    try:
+        for c in (qb._RoundBoth, qb._RoundValue, qb._RoundGrad):
+            c.apply = staticmethod(lambda x: x)
+        l2, g2, a2 = qb.EmulatedTrainer(sd).loss_and_grads(batch)
+    finally:
+        qb._RoundBoth.apply, qb._RoundValue.apply, qb._RoundGrad.apply = saved
+    assert abs(l2.item() - l0.item()) <= 1e-5 * abs(l0.item())
+    rows, rel2 = qb.grad_report(g2, g0)
+    assert rel2 <= 1e-4, rel2
+    assert max(abs(v[1]) for v in rows.values()) <= 1e-4

@@ -54,7 +54,7 @@ class TdDesc(C.Structure):
                                         "valid", "dq", "loss_out", "best_out", "y_out")] + \
                [(n, c_int) for n in ("B", "C", "A")] + [("gamma", c_float), ("inv_count", c_float)] + \
                [(n, c_int) for n in ("double_dqn", "clip_rect", "linear", "use_valid")] + \
-               [("gt", c_void_p), ("ground_truth", c_int), ("value_learning", c_int)]
+               [("gt", c_void_p), ("ground_truth", c_int), ("value_learning", c_int), ("labels_f32", c_int)]
 
 
 EXPORTS = {

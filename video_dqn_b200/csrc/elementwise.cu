@@ -759,13 +759,20 @@ __global__ void head_flatten_bwd_kernel(const float* __restrict__ dflat, const _
 }
 
 // ------------------------------------------------------------------------------------------
-// fused TD epilogue: one thread per (sample, class)
-__global__ void td_epilogue_kernel(const vdqn_td_desc d) {
+// rew / term / valid_mask as the loader types them: int64 (thresholded detections,
+// dataloaders/q_learning_real.py:78-84) or, with CONFIDENCE_REWARD, the detector scores themselves, which
+// the reference casts with `.float()` (train_q_network.py:158-160): labels_f32 = the already cast fp32
+__device__ __forceinline__ float td_label(const void* p, long i, int f32) {
+  return f32 ? static_cast<const float*>(p)[i] : (float)static_cast<const int64_t*>(p)[i];
+}
+
+// fused TD epilogue: one thread per (sample, class); elements [i_begin, B*C)
+__global__ void td_epilogue_kernel(const vdqn_td_desc d, const long i_begin) {
   pdl_launch_dependents();
   pdl_wait();
   const long total = (long)d.B * d.C;
   float local = 0.f;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total;
+  for (long i = i_begin + blockIdx.x * (long)blockDim.x + threadIdx.x; i < total;
        i += (long)gridDim.x * blockDim.x) {
     const long b = i / d.C;
     const float* qs = d.q_s + i * d.A;
@@ -793,16 +800,16 @@ __global__ void td_epilogue_kernel(const vdqn_td_desc d) {
       const float v = qsel[a];
       if (v > bv) { bv = v; best = a; }            // strict > : first maximum wins (torch.argmax)
     }
-    const float term = (float)d.term[i];
+    const float term = td_label(d.term, i, d.labels_f32);
     const float q_a = qt[best] * (1.f - term);
-    const float rew = (float)d.rew[i];
+    const float rew = td_label(d.rew, i, d.labels_f32);
     float y = d.linear ? rew + (q_a - 0.1f) : rew + d.gamma * q_a;
     if (d.clip_rect) y = fminf(fmaxf(y, 0.f), 1.f);
     const int act = (int)d.act[b];
     const float diff = qs[act] - y;
     float l = 0.5f * diff * diff;
     float mask = 1.f;
-    if (d.use_valid) { mask = (float)d.valid[i]; l *= mask; }
+    if (d.use_valid) { mask = td_label(d.valid, i, d.labels_f32); l *= mask; }
     local += l;
     if (d.dq != nullptr) {
       float* dq = d.dq + i * d.A;
@@ -831,6 +838,7 @@ __global__ void td_epilogue_kernel(const vdqn_td_desc d) {
 // is conflict-free.  Element -> thread mapping and per-element arithmetic are those of td_epilogue_kernel, so
 // results (including the summation order of the loss) are bit-identical.
 constexpr int kTdChunk = 256;
+constexpr long kTdBulkMinElems = 64 * 1024;     // below this the launch, not HBM, is what the kernel costs
 
 __device__ __forceinline__ void td_stage_in(float* __restrict__ dst, const float* __restrict__ src, int nf) {
   const int nv = nf >> 2;
@@ -859,10 +867,10 @@ __global__ void __launch_bounds__(kTdChunk) td_epilogue_staged_kernel(const vdqn
     float term = 0.f, rew = 0.f, mask = 1.f;
     int act = 0;
     if (live) {
-      term = (float)d.term[i];
-      rew = (float)d.rew[i];
+      term = td_label(d.term, i, d.labels_f32);
+      rew = td_label(d.rew, i, d.labels_f32);
       act = (int)d.act[i / d.C];
-      if (d.use_valid) mask = (float)d.valid[i];
+      if (d.use_valid) mask = td_label(d.valid, i, d.labels_f32);
     }
     td_stage_in(sm_qs, d.q_s + base * A, nf);
     td_stage_in(sm_qt, d.q_next_target + base * A, nf);
@@ -1348,6 +1356,23 @@ extern "C" int vdqn_td_epilogue(const vdqn_td_desc* d, void* stream_v) {
     const char* e = getenv("VDQN_TD_STAGED");
     return !(e != nullptr && e[0] == '0');
   }();
+  // large batches: the streaming form (td_bulk.cu) on the full 1024-element chunks, the per-thread kernel
+  // on the tail; VDQN_TD_BULK=0 switches it off
+  static const bool bulk_ok = []() {
+    const char* e = getenv("VDQN_TD_BULK");
+    return !(e != nullptr && e[0] == '0');
+  }();
+  if (bulk_ok && total >= kTdBulkMinElems && td_bulk_supported(d)) {
+    const long n_chunks = total / 1024;
+    const int rc = td_bulk_launch(d, n_chunks, stream);
+    if (rc != VDQN_OK) return rc;
+    const long done = n_chunks * 1024;
+    if (done < total) {
+      launch_kernel(td_epilogue_kernel, grid_for(total - done, 256, dev->num_sms, 8), 256, 0, stream, *d, done);
+      VDQN_CHECK_LAUNCH("td_epilogue (tail)");
+    }
+    return VDQN_OK;
+  }
   if (staged_ok && !d->ground_truth && d->A <= 8 && al16(d->q_s) && al16(d->q_next_target) &&
       al16(d->q_next_online) && al16(d->dq)) {
     const size_t smem = sizeof(float) * 3 * kTdChunk * (size_t)d->A;
@@ -1355,7 +1380,7 @@ extern "C" int vdqn_td_epilogue(const vdqn_td_desc* d, void* stream_v) {
     VDQN_CHECK_LAUNCH("td_epilogue_staged");
     return VDQN_OK;
   }
-  launch_kernel(td_epilogue_kernel, grid_for(total, 256, dev->num_sms, 8), 256, 0, stream, *d);
+  launch_kernel(td_epilogue_kernel, grid_for(total, 256, dev->num_sms, 8), 256, 0, stream, *d, 0L);
   VDQN_CHECK_LAUNCH("td_epilogue");
   return VDQN_OK;
 }

@@ -46,6 +46,10 @@ int halo_wgrad_launch(const vdqn_wgrad_desc* d, cudaStream_t stream);
 bool halo_wgrad_stem_supported(const vdqn_wgrad_desc* d);
 int halo_wgrad_stem_launch(const vdqn_wgrad_desc* d, cudaStream_t stream);
 
+// td_bulk.cu: streaming TD epilogue over the first n_chunks * 1024 elements (Bellman branch)
+bool td_bulk_supported(const vdqn_td_desc* d);
+int td_bulk_launch(const vdqn_td_desc* d, long n_chunks, cudaStream_t stream);
+
 inline int ceil_div(long a, long b) { return (int)((a + b - 1) / b); }
 
 // every kernel launch of the library is counted (bench.py reports it as `gpu_launches`)

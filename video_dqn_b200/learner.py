@@ -42,13 +42,18 @@ class StepConfig:
     # VALUE_LEARNING masks its NaN entries (:172-176)
     TRAIN_ON_GROUND_TRUTH: bool = False
     VALUE_LEARNING: bool = False
+    # the data set then yields the detector SCORES (floating point) as reward and terminal
+    # (train_q_network.py:101, dataloaders/q_learning_real.py:76-77) and process_batch uses their
+    # `.float()` (:158-160): the step's label buffers are fp32 instead of int64
+    CONFIDENCE_REWARD: bool = False
 
     @classmethod
     def from_config(cls, config):
         """Build from the reference's flattened ExperimentConfig attribute bag."""
         kw = {f: getattr(config, f) for f in ("GAMMA", "LOSS_CLIP", "LINEAR", "REMOVE_BEFORE_REWARD",
                                               "LEARNING_RATE", "TARGET_UPDATE_INTERVAL",
-                                              "TRAIN_ON_GROUND_TRUTH", "VALUE_LEARNING") if hasattr(config, f)}
+                                              "TRAIN_ON_GROUND_TRUTH", "VALUE_LEARNING", "CONFIDENCE_REWARD")
+              if hasattr(config, f)}
         return cls(**kw)
 
 
@@ -105,9 +110,10 @@ class QLearner:
         C = self.plan.num_classes
         self.gt = torch.full((batch_size, C), float("nan"), device=dev, dtype=torch.float64)
         self.act = torch.zeros(batch_size, device=dev, dtype=torch.int64)
-        self.rew = torch.zeros(batch_size, C, device=dev, dtype=torch.int64)
-        self.term = torch.zeros(batch_size, C, device=dev, dtype=torch.int64)
-        self.valid = torch.ones(batch_size, C, device=dev, dtype=torch.int64)
+        ldt = torch.float32 if self.cfg.CONFIDENCE_REWARD else torch.int64
+        self.rew = torch.zeros(batch_size, C, device=dev, dtype=ldt)
+        self.term = torch.zeros(batch_size, C, device=dev, dtype=ldt)
+        self.valid = torch.ones(batch_size, C, device=dev, dtype=ldt)
         # ---- workspaces and step outputs
         # B*F % 64 == 0: online [s ; s'] and target [s'] share ONE 3B forward pass (every conv launch
         # splits its CTAs between the two networks); otherwise a 2B online pass + a B target pass
@@ -199,6 +205,7 @@ class QLearner:
             self.gt.copy_(torch.as_tensor(gt, dtype=torch.float64).view(self.gt.shape), non_blocking=non_blocking)
             self.act.copy_(act.view(-1), non_blocking=non_blocking)
             return
+        check_label_dtypes(self, rew, term)
         self.after.copy_(after.view(self.after.shape), non_blocking=non_blocking)
         self.act.copy_(act.view(-1), non_blocking=non_blocking)
         self.rew.copy_(rew, non_blocking=non_blocking)
@@ -293,6 +300,14 @@ class QLearner:
         self.model.set_train()
         self.target_net.eval()
         self.model._state(); self.target_net._state()                      # bf16 operands of both networks
+
+
+def check_label_dtypes(learner, rew, term):
+    """A floating-point reward / terminal (CONFIDENCE_REWARD data) copied into the int64 label buffers of a
+    learner built without that switch would silently become 0: refuse."""
+    if (rew.is_floating_point() or term.is_floating_point()) and not learner.rew.is_floating_point():
+        raise ValueError("floating-point rewards / terminals (CONFIDENCE_REWARD data set) need a learner built "
+                         "with StepConfig(CONFIDENCE_REWARD=True): its label buffers are int64")
 
 
 def _to_cpu(obj):

@@ -347,8 +347,11 @@ def td_epilogue(q_s, q_next_online, q_next_target, act, rew, term, valid=None, *
     if gt is None:
         _cuda(q_next_target, torch.float32, "q_next_target")
         _req(q_s.shape == q_next_target.shape, "bad shape")
+        # int64 labels (thresholded detections) or, with CONFIDENCE_REWARD, the detector scores the
+        # reference casts with `.float()` (train_q_network.py:158-160): fp32, all label arrays alike
+        ldt = torch.float32 if rew.dtype == torch.float32 else torch.int64
         for t, n in ((rew, "rew"), (term, "term")):
-            _cuda(t, torch.int64, n)
+            _cuda(t, ldt, n)
         _req(rew.numel() == B * Cc and term.numel() == B * Cc, "bad shape")
         if q_next_online is not None:
             _cuda(q_next_online, torch.float32, "q_next_online")
@@ -356,8 +359,10 @@ def td_epilogue(q_s, q_next_online, q_next_target, act, rew, term, valid=None, *
     else:
         _cuda(gt, torch.float64, "ground_truth")
         _req(gt.numel() == B * Cc, "bad shape")
+    labels_f32 = gt is None and rew.dtype == torch.float32
     if use_valid:
-        _cuda(valid, torch.int64, "valid_mask")
+        _cuda(valid, torch.float32 if labels_f32 else torch.int64, "valid_mask")
+        _req(valid.numel() == B * Cc, "bad shape")
     dev = q_s.device
     if dq is None:
         dq = torch.empty_like(q_s)
@@ -375,6 +380,7 @@ def td_epilogue(q_s, q_next_online, q_next_target, act, rew, term, valid=None, *
     d.inv_count = (1.0 / (B * Cc)) if inv_count is None else inv_count
     d.double_dqn, d.clip_rect, d.linear, d.use_valid = int(double_dqn), int(clip_rect), int(linear), int(use_valid)
     d.gt, d.ground_truth, d.value_learning = L.ptr(gt), int(gt is not None), int(value_learning)
+    d.labels_f32 = int(labels_f32)
     with _Prof("td", (B, Cc, A)):
         L.check(lib.vdqn_td_epilogue(C.byref(d), L.stream_ptr()), "td_epilogue")
     return loss, dq, best, y

@@ -24,21 +24,30 @@ from .optim import arena_epoch
 
 
 def _make_resnet18(pretrained: bool):
-    """torchvision ResNet-18 container.  The reference asks for ImageNet weights
-    (archs/HabitatDQNMultiAction.py:11); they are used when torchvision can find them in the local
-    hub cache, otherwise the trunk keeps torchvision's random init (no network here)."""
+    """torchvision ResNet-18 container.  The reference always starts from ImageNet weights
+    (`models.resnet18(pretrained=True)`, archs/HabitatDQNMultiAction.py:11).  They are taken from the local
+    torch hub cache (either file name torchvision has used); if they are not there -- no network on the build /
+    GPU boxes -- the trunk keeps torchvision's RANDOM init and that is said loudly: a from-scratch run would
+    otherwise train a random trunk with identity BatchNorm statistics without a word in the log.  Loading a
+    checkpoint afterwards (what every test and the bench do) overwrites it.  Set VDQN_REQUIRE_PRETRAINED=1 to
+    make the missing file an error."""
+    import os
+    import warnings
     import torchvision.models as tvm
     if pretrained:
-        try:
-            import os
-            from torch.hub import get_dir
-            f = os.path.join(get_dir(), "checkpoints", "resnet18-f37072fd.pth")
+        from torch.hub import get_dir
+        for name in ("resnet18-f37072fd.pth", "resnet18-5c106cde.pth"):
+            f = os.path.join(get_dir(), "checkpoints", name)
             if os.path.exists(f):
                 m = tvm.resnet18(weights=None)
                 m.load_state_dict(torch.load(f, map_location="cpu"))
                 return m
-        except Exception:
-            pass
+        msg = ("ImageNet weights for resnet18 not found in the torch hub cache "
+               f"({os.path.join(get_dir(), 'checkpoints')}): the trunk is RANDOMLY initialised, unlike the "
+               "reference's models.resnet18(pretrained=True); load a checkpoint or place resnet18-f37072fd.pth there")
+        if os.environ.get("VDQN_REQUIRE_PRETRAINED", "0") == "1":
+            raise FileNotFoundError(msg)
+        warnings.warn(msg, RuntimeWarning, stacklevel=3)
     return tvm.resnet18(weights=None)
 
 

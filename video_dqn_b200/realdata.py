@@ -186,6 +186,9 @@ class QuadrupletLoader:
 
     def __init__(self, table: QuadrupletTable, batch_size: int, *, seed: int = 0, prefetch: int = 2,
                  workers: int = 8, pin: Optional[bool] = None):
+        if len(table) < batch_size:
+            raise ValueError(f"QuadrupletLoader: the table has {len(table)} rows, fewer than one batch of {batch_size} "
+                             "(incomplete batches are dropped, train_q_network.py:113)")
         self.t, self.B = table, batch_size
         # a handed-out batch stays valid until TWO further batches have been requested (its pinned
         # memory may still be the source of an asynchronous H2D copy when the next one is asked for)

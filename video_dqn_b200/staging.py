@@ -33,6 +33,9 @@ class BatchStager:
         before, after, act, rew, term, gt, valid = batch
         src = dict(before=before, after=after, act=act.view(-1), rew=rew, term=term, valid=valid, gt=gt)
         src = {f: src[f] for f in self.fields}
+        if "rew" in src:
+            from .learner import check_label_dtypes
+            check_label_dtypes(self.lr, src["rew"], src["term"])
         self.consumed[i].synchronize()                 # slot free (its D2D copy has run)
         with torch.cuda.stream(self.copy_stream):
             for f, t in src.items():

@@ -60,6 +60,10 @@ class TrainLoop:
         self.sample_number = resume_from + 1                                             # :189
         if resume_from > -1:
             self.learner.resume(self.snapshot_path(resume_from), resume_from)            # :191-198, 208
+        elif hasattr(self.learner, "sample_number"):
+            # a fresh run() numbers its steps from 1 again: the learner's own counter (snapshot contents,
+            # target-sync phase) must restart with it, or file names and contents diverge on a second run()
+            self.learner.sample_number = self.sample_number
         done = 0
         while self.sample_number < cfg.NUM_STEPS and (max_steps is None or done < max_steps):
             self.sample_number += 1                                                      # :213
@@ -107,6 +111,9 @@ def run_train(config, resume_from: int = -1, *, max_steps: Optional[int] = None,
     from .optim import FusedAdam
     from .realdata import QuadrupletLoader, QuadrupletTable
     from .staging import BatchStager
+    if getattr(config, "BOOTSTRAP", False):
+        raise NotImplementedError("BOOTSTRAP (train_q_network.py:200-206: start from a hard-coded path to another "
+                                  "run's snapshot) is not carried over; load that snapshot with QLearner.resume")
     torch.manual_seed(config.SEED)                                                       # :86
     table = QuadrupletTable(config.DATASET, one_action=True,                             # :99-106
                             confidence_reward=getattr(config, "CONFIDENCE_REWARD", False),
