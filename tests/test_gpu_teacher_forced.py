@@ -1,0 +1,271 @@
+"""The TIGHT parity bar: every layer of one fused step checked on its own, teacher-forced.
+
+End to end, a bf16 pipeline can only be compared with an oracle at bf16-noise level (gradient rel-L2
+~0.07): rounding makes the network chaotic at the ulp scale -- a 1e-7 difference in accumulation order
+flips the bf16 rounding of a few activations, each flip is a full-ulp error that flips more roundings in the
+next layer, and after ~6 layers two pipelines with IDENTICAL rounding points are as far apart as either is
+from fp32 (measured: oracle/qstep_bf16.py vs this path 0.069, fp32 oracle vs this path 0.071;
+profiles/grad_bars_r02.json).  A wrong scale factor of 10 % in one layer hides under that.
+
+So this test removes the propagation: after one eager step it takes the activations and gradients the
+CUDA path itself stored (Workspace buffers, gradient arena) and recomputes EACH kernel's output on the CPU
+from that kernel's own inputs -- reference convolution in fp32 over the same bf16 values, eval-mode
+BatchNorm folded as archs/HabitatDQNMultiAction.py:37-40 + torchvision BasicBlock define it, backward by
+torch autograd through exactly that expression.  What is left per layer is fp32 accumulation order plus at
+most one bf16 rounding flip of the output, so the bars are:
+  stored bf16 tensors (activations, data gradients): every element within 1 bf16 ulp (2 where two rounded
+      terms are added), at most 2 % of elements different at all;
+  fp32 results (weight / gamma / beta gradients, MLP): rel-L2 <= 2e-3, |norm ratio - 1| <= 1e-3.
+A 1 % scale error anywhere fails.  Needs a B200: `pytest -m gpu`.
+"""
+import json
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import qstep
+from oracle.qstep import BN_EPS
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REPORT = {}
+
+
+def _bf(x):
+    return x.to(torch.bfloat16).float()
+
+
+def _nchw(t):
+    return t.detach().float().cpu().permute(0, 3, 1, 2).contiguous()
+
+
+def _check_bf16(name, got, ref, ulps=1, frac=0.02, mag=None):
+    """stored bf16 tensor vs the rounded CPU recomputation.  `mag`: magnitude that sets the ulp where the
+    stored value is a sum of separately rounded terms (the error is an ulp of the TERMS, which under
+    cancellation is much more than an ulp of the sum)"""
+    got, ref = got.float(), ref.float()
+    scale = ref.abs().max().item() + 1e-30
+    diff = (got - ref).abs()
+    m = torch.maximum(ref.abs(), got.abs()) if mag is None else torch.maximum(mag, torch.maximum(ref.abs(), got.abs()))
+    tol = ulps * 2.0 ** -7 * m + 1e-5 * scale
+    bad = (diff > tol)
+    neq = (diff > 0).float().mean().item()
+    REPORT[name] = {"frac_different": neq, "max_diff_over_max": diff.max().item() / scale}
+    assert not bad.any(), f"{name}: {int(bad.sum())} elements off by more than {ulps} ulp (max diff {diff.max().item():.3e}, scale {scale:.3e})"
+    assert neq <= frac, f"{name}: {neq:.4f} of the elements differ"
+
+
+def _check_f32(name, got, ref, rel=2e-3, norm=1e-3):
+    got, ref = got.detach().double().cpu().flatten(), ref.detach().double().flatten()
+    nr = ref.norm().item() + 1e-300
+    r = (got - ref).norm().item() / nr
+    n = got.norm().item() / nr - 1.0
+    REPORT[name] = {"rel_l2": r, "norm_ratio_minus_1": n}
+    assert r <= rel, f"{name}: rel-L2 {r:.3e}"
+    assert abs(n) <= norm, f"{name}: gradient norm off by {n:+.3e}"
+
+
+class _Layer:
+    """conv + eval-mode BatchNorm as one differentiable expression of the fp32 masters (w, gamma, beta),
+    evaluated the way the kernels do: bf16(w * gamma * rstd) operands, fp32 shift."""
+
+    def __init__(self, sd, wkey, bn, stride, pad, bias=None):
+        self.w = sd[wkey].clone().requires_grad_(True)
+        self.stride, self.pad, self.bn = stride, pad, bn
+        if bn is not None:
+            self.gamma = sd[bn + ".weight"].clone().requires_grad_(True)
+            self.beta = sd[bn + ".bias"].clone().requires_grad_(True)
+            self.rstd = torch.rsqrt(sd[bn + ".running_var"] + BN_EPS)
+            self.mean = sd[bn + ".running_mean"]
+        else:
+            self.bias = sd[bias].clone().requires_grad_(True)
+
+    def folded(self):
+        from oracle.qstep_bf16 import _RoundValue
+        if self.bn is None:
+            return _RoundValue.apply(self.w), self.bias
+        scale = self.gamma * self.rstd
+        return _RoundValue.apply(self.w * scale.view(-1, 1, 1, 1)), self.beta - self.mean * scale
+
+    def __call__(self, x):
+        wf, shift = self.folded()
+        return F.conv2d(x, wf, None, self.stride, self.pad) + shift.view(1, -1, 1, 1)
+
+    def grads(self, x, dy):
+        """(dL/dx, {param grads}) for L = sum(y * dy), x and dy the CUDA path's own bf16 tensors"""
+        x = x.clone().requires_grad_(True)
+        y = self(x)
+        leaves = [x, self.w] + ([self.gamma, self.beta] if self.bn is not None else [self.bias])
+        g = torch.autograd.grad((y * dy).sum(), leaves)
+        return g[0], g[1:]
+
+
+def test_every_layer_of_one_step_teacher_forced():
+    from video_dqn_b200.learner import QLearner, StepConfig
+    from video_dqn_b200.qnet import HabitatDQNMultiAction
+    dev = torch.device("cuda:0")
+    B = 8
+    sd = qstep.init_state(seed=4, randomize_bn=True)
+    batch = qstep.synthetic_batch(B, seed=6)
+
+    def mk():
+        m = HabitatDQNMultiAction(3, 5, extra_capacity=True, panorama=False)
+        m.load_state_dict(sd)
+        return m.to(dev)
+    lr = QLearner(mk(), mk(), StepConfig(), batch_size=B, use_graph=False)
+    lr.step([t.to(dev) for t in batch])
+    torch.cuda.synchronize()
+    ws = lr.ws_train
+    bw = ws.bwd_view()
+    G = {n: g.detach().cpu() for n, g in lr.G.items()}
+    plan = lr.plan
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+
+    # ------------------------------------------------------------------ forward, all 2B frames
+    frames = torch.cat([batch[0], batch[1]])
+    x = _bf(frames)
+    stem = _Layer(sd, "resnet.conv1.weight", "resnet.bn1", 2, 3)
+    with torch.no_grad():
+        s_ref = _bf(F.relu(stem(x)))
+        if getattr(ws, "s", None) is not None:
+            s_gpu = _nchw(ws.s)
+            _check_bf16("fwd/stem", s_gpu, s_ref)
+            assert torch.equal(F.max_pool2d(s_gpu, 3, 2, 1), _nchw(ws.p)), "max-pool"
+        else:
+            _check_bf16("fwd/stem+pool", _nchw(ws.p), F.max_pool2d(s_ref, 3, 2, 1))
+        cur = _nchw(ws.p)
+        layers = []
+        for i, b in enumerate(plan.blocks):
+            c1 = _Layer(sd, b.conv1.wkey, b.conv1.bn, b.stride, 1)
+            c2 = _Layer(sd, b.conv2.wkey, b.conv2.bn, 1, 1)
+            ds = _Layer(sd, b.ds.wkey, b.ds.bn, b.stride, 0) if b.ds is not None else None
+            layers.append((c1, c2, ds))
+            a1_gpu = _nchw(ws.a1[i])
+            _check_bf16(f"fwd/{b.conv1.name}", a1_gpu, _bf(F.relu(c1(cur))))
+            if ds is not None and ws.idn[i] is not None:
+                idn = _nchw(ws.idn[i])
+                _check_bf16(f"fwd/{b.ds.name}", idn, _bf(ds(cur)))
+                out_ref, ulps = _bf(F.relu(c2(a1_gpu) + idn)), 1
+            elif ds is not None:            # downsample accumulated inside conv2's kernel: never rounded on its own
+                out_ref, ulps = _bf(F.relu(c2(a1_gpu) + ds(cur))), 1
+            else:
+                out_ref, ulps = _bf(F.relu(c2(a1_gpu) + cur)), 1
+            out_gpu = _nchw(ws.out[i])
+            _check_bf16(f"fwd/{b.conv2.name}", out_gpu, out_ref, ulps)
+            cur = out_gpu
+        head = _Layer(sd, "features.8.weight", None, 1, 0, bias="features.8.bias")
+        h_gpu = _nchw(ws.h)
+        _check_bf16("fwd/head", h_gpu, _bf(F.relu(head(cur))))
+        flat = h_gpu.flatten(1)
+        z1 = F.relu(F.linear(flat, sd["top.0.weight"], sd["top.0.bias"]))
+        z2 = F.relu(F.linear(z1, sd["top.2.weight"], sd["top.2.bias"]))
+        q = F.linear(z2, sd["top.4.weight"], sd["top.4.bias"])
+        _check_f32("fwd/mlp_q", ws.q[:2 * B], q, rel=2e-4, norm=1e-4)
+
+    # ------------------------------------------------------------------ TD loss on the path's own Q
+    q_gpu = ws.q.detach().cpu()
+    qs = q_gpu[:B].view(B, 5, 3).clone().requires_grad_(True)
+    q_no = q_gpu[B:2 * B].view(B, 5, 3)
+    q_nt = (lr.ws_eval.q if lr.ws_eval is not None else ws.q[2 * B:3 * B]).detach().cpu().view(B, 5, 3)
+    loss, _aux = qstep.td_loss(qs, q_no, q_nt, batch[2], batch[3], batch[4], batch[6], qstep.StepConfig())
+    loss.backward()
+    assert abs(lr.loss.item() - loss.item()) <= 1e-6 * abs(loss.item())
+    dq = qs.grad.view(B, 15)
+    _check_f32("bwd/dq", lr.dq.view(B, 15), dq, rel=1e-6, norm=1e-6)
+
+    # ------------------------------------------------------------------ MLP backward (fp32)
+    hb = h_gpu[:B]
+    flat = hb.flatten(1).clone().requires_grad_(True)
+    P = {k: sd[k].clone().requires_grad_(True) for k in ("top.0.weight", "top.0.bias", "top.2.weight", "top.2.bias",
+                                                         "top.4.weight", "top.4.bias")}
+    z1 = F.relu(F.linear(flat, P["top.0.weight"], P["top.0.bias"]))
+    z2 = F.relu(F.linear(z1, P["top.2.weight"], P["top.2.bias"]))
+    qq = F.linear(z2, P["top.4.weight"], P["top.4.bias"])
+    gr = torch.autograd.grad((qq * dq).sum(), [flat] + list(P.values()))
+    for k, g_ref in zip(P, gr[1:]):
+        _check_f32(f"bwd/{k}", G[k], g_ref, rel=1e-3, norm=5e-4)
+    dh_ref = _bf(gr[0].view(B, 64, 5, 5) * (hb > 0))
+    dh_gpu = _nchw(bw.dh)
+    _check_bf16("bwd/dh", dh_gpu, dh_ref)
+
+    # ------------------------------------------------------------------ head conv backward
+    blocks = plan.blocks
+    outs = [_nchw(ws.out[i])[:B] for i in range(len(blocks))]
+    a1s = [_nchw(ws.a1[i])[:B] for i in range(len(blocks))]
+    p_in = _nchw(ws.p)[:B]
+    dx, (dw8, db8) = head.grads(outs[-1], dh_gpu)
+    _check_f32("bwd/features.8.weight", G["features.8.weight"], dw8)
+    _check_f32("bwd/features.8.bias", G["features.8.bias"], db8)
+
+    def block_grad_out(i):
+        """the gradient w.r.t. block i's output as the path stored it (engine.backward's rotating buffers)"""
+        hw = blocks[i].out_hw
+        first_of_res = (i % 2 == 0)
+        return _nchw(bw.dy_out[hw][1 if first_of_res else 0])
+    cur_gpu = block_grad_out(len(blocks) - 1)
+    _check_bf16("bwd/dgrad_head", cur_gpu, _bf(dx * (outs[-1] > 0)))
+
+    # ------------------------------------------------------------------ residual blocks, last to first
+    for i in range(len(blocks) - 1, -1, -1):
+        b = blocks[i]
+        c1, c2, ds = layers[i]
+        x_in = outs[i - 1] if i > 0 else p_in
+        cur_gpu = block_grad_out(i)
+        # conv2 + bn2 from (a1, cur)
+        dx2, (dw, dgam, dbet) = c2.grads(a1s[i], cur_gpu)
+        _check_f32(f"bwd/{b.conv2.wkey}", G[b.conv2.wkey], dw)
+        _check_f32(f"bwd/{b.conv2.bn}.weight", G[b.conv2.bn + ".weight"], dgam)
+        _check_f32(f"bwd/{b.conv2.bn}.bias", G[b.conv2.bn + ".bias"], dbet)
+        dy_a1_ref = _bf(dx2 * (a1s[i] > 0))
+        if i % 2 == 0:                       # the buffer of this resolution still holds this block's dy_a1
+            dy_a1 = _nchw(bw.dy_a1[b.out_hw])
+            _check_bf16(f"bwd/dgrad_{b.conv2.name}", dy_a1, dy_a1_ref)
+            loose = 1.0
+        else:                                # overwritten by the block below: use the recomputed one
+            dy_a1, loose = dy_a1_ref, 3.0
+        dx1, (dw, dgam, dbet) = c1.grads(x_in, dy_a1)
+        _check_f32(f"bwd/{b.conv1.wkey}", G[b.conv1.wkey], dw, rel=2e-3 * loose, norm=1e-3 * loose)
+        _check_f32(f"bwd/{b.conv1.bn}.weight", G[b.conv1.bn + ".weight"], dgam, rel=2e-3 * loose, norm=1e-3 * loose)
+        _check_f32(f"bwd/{b.conv1.bn}.bias", G[b.conv1.bn + ".bias"], dbet, rel=2e-3 * loose, norm=1e-3 * loose)
+        if ds is not None:
+            dxd, (dw, dgam, dbet) = ds.grads(x_in, cur_gpu)
+            _check_f32(f"bwd/{b.ds.wkey}", G[b.ds.wkey], dw)
+            _check_f32(f"bwd/{b.ds.bn}.weight", G[b.ds.bn + ".weight"], dgam)
+            _check_f32(f"bwd/{b.ds.bn}.bias", G[b.ds.bn + ".bias"], dbet)
+            dx_in, mag = dx1 + dxd, dx1.abs() + dxd.abs()
+        else:
+            dx_in, mag = dx1 + cur_gpu, dx1.abs() + cur_gpu.abs()
+        if i % 2 == 0:                       # dy_a1 was the path's own: its block-input gradient is checkable
+            if i > 0:
+                _check_bf16(f"bwd/dgrad_{b.conv1.name}", block_grad_out(i - 1), _bf(dx_in * (x_in > 0)), ulps=2, mag=mag,
+                            frac=0.10 if ds is not None else 0.02)    # the downsample term is rounded on its own
+            else:
+                _check_bf16("bwd/dgrad_l1.0.c1", _nchw(bw.dy_p), _bf(dx_in), ulps=2, mag=mag)
+
+    # ------------------------------------------------------------------ max-pool + stem
+    if getattr(bw, "dy_s", None) is not None and getattr(ws, "s", None) is not None:
+        s_b = _nchw(ws.s)[:B].clone().requires_grad_(True)
+        pooled = F.max_pool2d(s_b, 3, 2, 1)
+        (g_s,) = torch.autograd.grad((pooled * _nchw(bw.dy_p)).sum(), [s_b])
+        dy_s_ref = _bf(g_s * (s_b.detach() > 0))
+        dy_s = _nchw(bw.dy_s)
+        _check_bf16("bwd/maxpool", dy_s, dy_s_ref, ulps=1, frac=0.002)
+    else:                                     # pooling gradient formed inside the stem weight-gradient kernel
+        s_b = _bf(F.relu(stem(x[:B]))).detach().requires_grad_(True)
+        pooled = F.max_pool2d(s_b, 3, 2, 1)
+        (g_s,) = torch.autograd.grad((pooled * _nchw(bw.dy_p)).sum(), [s_b])
+        dy_s = _bf(g_s * (s_b.detach() > 0))
+    _dx, (dw, dgam, dbet) = stem.grads(x[:B], dy_s)
+    _check_f32("bwd/resnet.conv1.weight", G["resnet.conv1.weight"], dw)
+    _check_f32("bwd/resnet.bn1.weight", G["resnet.bn1.weight"], dgam)
+    _check_f32("bwd/resnet.bn1.bias", G["resnet.bn1.bias"], dbet)
+    try:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        json.dump(REPORT, open(os.path.join(ROOT, "gpurun_out", "teacher_forced.json"), "w"), indent=1, sort_keys=True)
+    except Exception:
+        pass
+    worst = max((v["rel_l2"], k) for k, v in REPORT.items() if "rel_l2" in v)
+    print("teacher-forced: worst fp32 rel-L2", worst, "; worst fraction of differing bf16 elements",
+          max((v["frac_different"], k) for k, v in REPORT.items() if "frac_different" in v))

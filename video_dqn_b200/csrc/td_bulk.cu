@@ -22,8 +22,9 @@
 namespace vdqn {
 
 constexpr int kTdBulkChunk = 1024;      // elements (b, c) per chunk
-constexpr int kTdBulkThreads = 256;
+constexpr int kTdBulkThreads = 1024;    // one element per thread and chunk: 32 warps hide the shared-memory / act latencies
 constexpr int kTdBulkStages = 3;
+constexpr int kTdBulkMaxSmem = 224 * 1024;   // dynamic part; the kernel also has ~1.3 KB of static shared memory
 
 __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
@@ -50,12 +51,16 @@ __host__ __device__ inline TdBulkLayout td_bulk_layout(const vdqn_td_desc& d) {
   return L;
 }
 
+// A_T: the number of actions as a compile-time constant (0: read d.A).  With a run-time A the arg-max / dQ
+// loops stay loops and the first version of this kernel issued ~150 instructions per element from 8 warps:
+// ncu showed 28 % issue utilisation, DRAM 42 % busy -- bound by its own instruction latencies, not by HBM.
+template <int A_T>
 __global__ void __launch_bounds__(kTdBulkThreads, 1) td_epilogue_bulk_kernel(const vdqn_td_desc d, const long n_chunks) {
   extern __shared__ __align__(128) uint8_t td_smem[];
   __shared__ __align__(8) uint64_t full_bar[kTdBulkStages];
   __shared__ float red[kTdBulkThreads / 32];
   const TdBulkLayout L = td_bulk_layout(d);
-  const int A = d.A;
+  const int A = A_T > 0 ? A_T : d.A;
   const uint32_t smem0 = smem_u32(td_smem);
   const uint32_t out0 = smem0 + kTdBulkStages * L.stage_bytes;           // two dQ tiles
   pdl_launch_dependents();
@@ -115,6 +120,7 @@ __global__ void __launch_bounds__(kTdBulkThreads, 1) td_epilogue_bulk_kernel(con
       const float* qsel = sm_qo + e * A;
       int best = 0;
       float bv = qsel[0];
+#pragma unroll
       for (int a = 1; a < A; ++a) {
         const float v = qsel[a];
         if (v > bv) { bv = v; best = a; }            // strict > : first maximum wins (torch.argmax)
@@ -147,6 +153,7 @@ __global__ void __launch_bounds__(kTdBulkThreads, 1) td_epilogue_bulk_kernel(con
 #pragma unroll
       for (int k = 0; k < kTdBulkChunk / kTdBulkThreads; ++k) {
         float* o = so + (k * kTdBulkThreads + threadIdx.x) * A;
+#pragma unroll
         for (int a = 0; a < A; ++a) o[a] = (a == act[k]) ? g[k] : 0.f;
       }
       fence_proxy_async();
@@ -173,7 +180,7 @@ bool td_bulk_supported(const vdqn_td_desc* d) {
   if (d->ground_truth || d->A < 1 || d->A > 8) return false;
   auto al16 = [](const void* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   const TdBulkLayout L = td_bulk_layout(*d);
-  if ((size_t)kTdBulkStages * L.stage_bytes + 2 * (size_t)L.q_bytes > 227u * 1024u) return false;
+  if ((size_t)kTdBulkStages * L.stage_bytes + 2 * (size_t)L.q_bytes > (size_t)kTdBulkMaxSmem) return false;
   return al16(d->q_s) && al16(d->q_next_target) && al16(d->q_next_online) && al16(d->dq) && al16(d->rew) &&
          al16(d->term) && al16(d->valid);
 }
@@ -185,12 +192,19 @@ int td_bulk_launch(const vdqn_td_desc* d, long n_chunks, cudaStream_t stream) {
   const size_t smem = (size_t)kTdBulkStages * L.stage_bytes + 2 * (size_t)L.q_bytes;
   static size_t attr_smem = 0;
   if (smem > attr_smem) {
-    cudaError_t e = cudaFuncSetAttribute(td_epilogue_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return set_error(VDQN_ERR_CUDA, "cudaFuncSetAttribute(td_bulk): %s", cudaGetErrorString(e));
-    attr_smem = smem;
+    cudaError_t e = cudaSuccess;
+    for (auto fn : {td_epilogue_bulk_kernel<0>, td_epilogue_bulk_kernel<1>, td_epilogue_bulk_kernel<3>})
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kTdBulkMaxSmem);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return set_error(VDQN_ERR_CUDA, "cudaFuncSetAttribute(td_bulk): %s", cudaGetErrorString(e));
+    }
+    attr_smem = kTdBulkMaxSmem;
   }
   const int grid = (int)(n_chunks < dev->num_sms ? n_chunks : dev->num_sms);
-  launch_kernel(td_epilogue_bulk_kernel, grid, kTdBulkThreads, smem, stream, *d, n_chunks);
+  // the shipped configuration has 3 actions (configs/experiments/real_data/config.yml:5), VALUE_LEARNING 1
+  auto kfn = d->A == 3 ? td_epilogue_bulk_kernel<3> : d->A == 1 ? td_epilogue_bulk_kernel<1> : td_epilogue_bulk_kernel<0>;
+  launch_kernel(kfn, grid, kTdBulkThreads, smem, stream, *d, n_chunks);
   VDQN_CHECK_LAUNCH("td_epilogue_bulk");
   return VDQN_OK;
 }
