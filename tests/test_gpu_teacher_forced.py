@@ -14,9 +14,10 @@ BatchNorm folded as archs/HabitatDQNMultiAction.py:37-40 + torchvision BasicBloc
 torch autograd through exactly that expression.  What is left per layer is fp32 accumulation order plus at
 most one bf16 rounding flip of the output, so the bars are:
   stored bf16 tensors (activations, data gradients): every element within 1 bf16 ulp (2 where two rounded
-      terms are added), at most 2 % of elements different at all;
-  fp32 results (weight / gamma / beta gradients, MLP): rel-L2 <= 2e-3, |norm ratio - 1| <= 1e-3.
-A 1 % scale error anywhere fails.  Needs a B200: `pytest -m gpu`.
+      terms are added), at most 0.5 % of elements different at all (measured: < 0.1 %);
+  fp32 results (weight / gamma / beta gradients, MLP): rel-L2 <= 5e-4, |norm ratio - 1| <= 1e-4
+      (measured: 1.1e-4 / 1.1e-5 at worst; profiles/teacher_forced_r02.json).
+A 0.1 % scale error anywhere fails.  Needs a B200: `pytest -m gpu`.
 """
 import json
 import os
@@ -41,7 +42,7 @@ def _nchw(t):
     return t.detach().float().cpu().permute(0, 3, 1, 2).contiguous()
 
 
-def _check_bf16(name, got, ref, ulps=1, frac=0.02, mag=None):
+def _check_bf16(name, got, ref, ulps=1, frac=0.005, mag=None):
     """stored bf16 tensor vs the rounded CPU recomputation.  `mag`: magnitude that sets the ulp where the
     stored value is a sum of separately rounded terms (the error is an ulp of the TERMS, which under
     cancellation is much more than an ulp of the sum)"""
@@ -57,7 +58,7 @@ def _check_bf16(name, got, ref, ulps=1, frac=0.02, mag=None):
     assert neq <= frac, f"{name}: {neq:.4f} of the elements differ"
 
 
-def _check_f32(name, got, ref, rel=2e-3, norm=1e-3):
+def _check_f32(name, got, ref, rel=5e-4, norm=1e-4):
     got, ref = got.detach().double().cpu().flatten(), ref.detach().double().flatten()
     nr = ref.norm().item() + 1e-300
     r = (got - ref).norm().item() / nr
@@ -226,9 +227,9 @@ def test_every_layer_of_one_step_teacher_forced():
         else:                                # overwritten by the block below: use the recomputed one
             dy_a1, loose = dy_a1_ref, 3.0
         dx1, (dw, dgam, dbet) = c1.grads(x_in, dy_a1)
-        _check_f32(f"bwd/{b.conv1.wkey}", G[b.conv1.wkey], dw, rel=2e-3 * loose, norm=1e-3 * loose)
-        _check_f32(f"bwd/{b.conv1.bn}.weight", G[b.conv1.bn + ".weight"], dgam, rel=2e-3 * loose, norm=1e-3 * loose)
-        _check_f32(f"bwd/{b.conv1.bn}.bias", G[b.conv1.bn + ".bias"], dbet, rel=2e-3 * loose, norm=1e-3 * loose)
+        _check_f32(f"bwd/{b.conv1.wkey}", G[b.conv1.wkey], dw, rel=5e-4 * loose, norm=1e-4 * loose)
+        _check_f32(f"bwd/{b.conv1.bn}.weight", G[b.conv1.bn + ".weight"], dgam, rel=5e-4 * loose, norm=1e-4 * loose)
+        _check_f32(f"bwd/{b.conv1.bn}.bias", G[b.conv1.bn + ".bias"], dbet, rel=5e-4 * loose, norm=1e-4 * loose)
         if ds is not None:
             dxd, (dw, dgam, dbet) = ds.grads(x_in, cur_gpu)
             _check_f32(f"bwd/{b.ds.wkey}", G[b.ds.wkey], dw)
@@ -240,7 +241,7 @@ def test_every_layer_of_one_step_teacher_forced():
         if i % 2 == 0:                       # dy_a1 was the path's own: its block-input gradient is checkable
             if i > 0:
                 _check_bf16(f"bwd/dgrad_{b.conv1.name}", block_grad_out(i - 1), _bf(dx_in * (x_in > 0)), ulps=2, mag=mag,
-                            frac=0.10 if ds is not None else 0.02)    # the downsample term is rounded on its own
+                            frac=0.10 if ds is not None else 0.005)    # the downsample term is rounded on its own
             else:
                 _check_bf16("bwd/dgrad_l1.0.c1", _nchw(bw.dy_p), _bf(dx_in), ulps=2, mag=mag)
 
@@ -248,10 +249,13 @@ def test_every_layer_of_one_step_teacher_forced():
     if getattr(bw, "dy_s", None) is not None and getattr(ws, "s", None) is not None:
         s_b = _nchw(ws.s)[:B].clone().requires_grad_(True)
         pooled = F.max_pool2d(s_b, 3, 2, 1)
-        (g_s,) = torch.autograd.grad((pooled * _nchw(bw.dy_p)).sum(), [s_b])
+        (g_s,) = torch.autograd.grad((pooled * _nchw(bw.dy_p)).sum(), [s_b], retain_graph=True)
+        (g_abs,) = torch.autograd.grad((pooled * _nchw(bw.dy_p).abs()).sum(), [s_b])
         dy_s_ref = _bf(g_s * (s_b.detach() > 0))
         dy_s = _nchw(bw.dy_s)
-        _check_bf16("bwd/maxpool", dy_s, dy_s_ref, ulps=1, frac=0.002)
+        # an input pixel that is the arg-max of up to four windows receives the sum of their gradients; the
+        # kernel adds them pairwise in bf16 (packed __hadd2), the reference in fp32: 2 ulp of the terms
+        _check_bf16("bwd/maxpool", dy_s, dy_s_ref, ulps=2, frac=0.01, mag=g_abs)
     else:                                     # pooling gradient formed inside the stem weight-gradient kernel
         s_b = _bf(F.relu(stem(x[:B]))).detach().requires_grad_(True)
         pooled = F.max_pool2d(s_b, 3, 2, 1)
