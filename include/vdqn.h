@@ -222,6 +222,46 @@ int vdqn_head_flatten_bwd(const float* dflat, const void* h_nhwc, void* dh_nhwc,
                           int32_t B, int32_t P, int32_t C, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Q-head MLP on the tensor cores at fp32-grade accuracy (the fast path of the fused step; replaces the
+ * cuBLAS sgemm calls PyTorch dispatches for top.0 / top.2 / top.4 and their backward,
+ * archs/HabitatDQNMultiAction.py:31,53).  Every fp32 operand is held as TWO bf16 matrices hi = bf16(x),
+ * lo = bf16(x - hi); a GEMM accumulates up to three operand pairs ("segments": hi*hi, lo*hi, hi*lo) into
+ * one fp32 tile:
+ *     D[m,n] = sum_s sum_k A_s[m,k] * B_s[n,k]
+ * Operands are row-major bf16 matrices with 16-byte aligned rows, read either K-major (matrix [M or N][K])
+ * or, with a_mn / b_mn != 0, MN-major (matrix [K][M or N]) -- the same buffers serve x W^T, dy W and dy^T x.
+ * Epilogue, in this order: + bias[n]; ReLU; zero where mask_f32 / mask_bf16 [m][n] <= 0 (ReLU mask of a stored
+ * activation); then any of: fp32 store (optionally un-permuting columns: n = f*c*p + pp*c + cc goes to
+ * f*c*p + cc*p + pp, for d top.0.weight), hi/lo bf16 store (columns up to ld_hl, zeros beyond N), bf16
+ * store, per-column sums accumulated with atomics into colsum[n % colsum_mod] (bias gradients).
+ * split_m > 0 (multiple of 128): rows >= split_m use the second operand set b2 / bias2 (target network). */
+typedef struct vdqn_mlp_operand {
+  const void* ptr;          /* bf16 */
+  int32_t rows, cols, ld;   /* the matrix as stored; ld in elements, multiple of 8 */
+} vdqn_mlp_operand;
+typedef struct vdqn_mlp_gemm_desc {
+  vdqn_mlp_operand a[3], b[3], b2[3];
+  int32_t K[3];
+  int32_t nseg, M, N, BN /* 64, 128 or 256 */, a_mn, b_mn, split_m;
+  const float* bias; const float* bias2;
+  int32_t relu;
+  const float* mask_f32; const void* mask_bf16; int32_t ldmask;
+  float* out_f32; int32_t ld_f32, perm_c, perm_p;
+  void* out_hi; void* out_lo; int32_t ld_hl;
+  void* out_bf16; int32_t ld_bf16;
+  float* colsum; int32_t colsum_mod;
+} vdqn_mlp_gemm_desc;
+int vdqn_mlp_gemm(const vdqn_mlp_gemm_desc* d, void* stream);
+/* up to 4 independent GEMMs in ONE launch (each is latency-bound: the three weight gradients and the head
+ * conv's dy of the backward pass share a launch); only descs[0] may use split_m */
+int vdqn_mlp_gemm_grouped(const vdqn_mlp_gemm_desc* descs, int32_t n, void* stream);
+/* x fp32 [rows][cols] -> hi / lo bf16 [rows][ld_out] (columns >= cols zero); perm_c != 0 re-orders the
+ * columns of every (perm_c x perm_p) block from c*perm_p + p to p*perm_c + c (top.0.weight -> the NHWC order
+ * of the head-conv output); colsum (optional) accumulates the per-column sums of x. */
+int vdqn_split_bf16(const float* x, void* hi, void* lo, int32_t rows, int32_t cols, int32_t ld_out,
+                    int32_t perm_c, int32_t perm_p, float* colsum, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Fused TD epilogue: replaces the ~24 ATen launches of process_batch
  * (train_q_network.py:134-180): repeat/gather/argmax/gather/detach/mul/add/clamp/sub/pow/mean
  * and their backward.  q_* are fp32 [B][C][A]; act int64 [B]; rew/term/valid int64 [B][C].

@@ -57,6 +57,19 @@ class TdDesc(C.Structure):
                [("gt", c_void_p), ("ground_truth", c_int), ("value_learning", c_int), ("labels_f32", c_int)]
 
 
+class MlpOperand(C.Structure):
+    _fields_ = [("ptr", c_void_p), ("rows", c_int), ("cols", c_int), ("ld", c_int)]
+
+
+class MlpGemmDesc(C.Structure):
+    _fields_ = [("a", MlpOperand * 3), ("b", MlpOperand * 3), ("b2", MlpOperand * 3), ("K", c_int * 3)] + \
+               [(n, c_int) for n in ("nseg", "M", "N", "BN", "a_mn", "b_mn", "split_m")] + \
+               [("bias", c_void_p), ("bias2", c_void_p), ("relu", c_int), ("mask_f32", c_void_p),
+                ("mask_bf16", c_void_p), ("ldmask", c_int), ("out_f32", c_void_p), ("ld_f32", c_int),
+                ("perm_c", c_int), ("perm_p", c_int), ("out_hi", c_void_p), ("out_lo", c_void_p), ("ld_hl", c_int),
+                ("out_bf16", c_void_p), ("ld_bf16", c_int), ("colsum", c_void_p), ("colsum_mod", c_int)]
+
+
 EXPORTS = {
     "vdqn_last_error": (C.c_char_p, []),
     "vdqn_abi_version": (c_int, []),
@@ -82,6 +95,9 @@ EXPORTS = {
     "vdqn_avgpool_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "vdqn_head_flatten_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "vdqn_head_flatten_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "vdqn_mlp_gemm": (c_int, [C.POINTER(MlpGemmDesc), c_void_p]),
+    "vdqn_mlp_gemm_grouped": (c_int, [C.POINTER(MlpGemmDesc), c_int, c_void_p]),
+    "vdqn_split_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "vdqn_td_epilogue": (c_int, [C.POINTER(TdDesc), c_void_p]),
     "vdqn_q_max": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "vdqn_bn_stats": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p]),

@@ -18,12 +18,6 @@ from typing import Dict, List, Optional
 
 import os as _os
 
-# VDQN_TOP0_TENSOR=1: top.0 (1600 -> 512) on the tensor-core conv kernels with bf16 operands.  Off by
-# default: it saves ~0.2 ms of MLP kernels per step but rounds the first Q-head layer's weights to
-# bf16, which pushes the worst-case Q error (1.03e-2 measured) past the 1e-2 parity bar of SURVEY 8d;
-# the Q-head stays fp32 end to end.
-TOP0_TENSOR = _os.environ.get("VDQN_TOP0_TENSOR", "0") == "1"
-
 import torch
 
 from . import ops
@@ -76,10 +70,6 @@ class NetPlan:
     num_classes: int
     num_frames: int
     convs: List[ConvSpec] = field(default_factory=list)
-    # top.0 (Linear 1600 -> 512 on the flattened head output) as a 5x5 valid convolution over the
-    # [5,5,64] head output: flatten order c*25 + p == OIHW [512][64][5][5].  Single-frame nets only
-    # (with F frames the flattened index is frame-major).  None: fp32 SIMT path.
-    top0: Optional[ConvSpec] = None
 
 
 def make_plan(action_dim: int, num_classes: int = 5, num_frames: int = 1) -> NetPlan:
@@ -106,14 +96,12 @@ def make_plan(action_dim: int, num_classes: int = 5, num_frames: int = 1) -> Net
                     gemm_cin=512)
     plan = NetPlan(stem, blocks, head, action_dim, num_classes, num_frames)
     plan.convs = [stem] + [c for b in blocks for c in (b.conv1, b.conv2, b.ds) if c is not None] + [head]
-    if num_frames == 1 and TOP0_TENSOR:
-        plan.top0 = ConvSpec("top0", "top.0.weight", None, "top.0.bias", 64, 512, 5, 1, 0, 0, 5, 1, gemm_cin=64)
     return plan
 
 
 def prep_convs(plan: NetPlan) -> List[ConvSpec]:
     """every tensor that has bf16 GEMM operands"""
-    return plan.convs + ([plan.top0] if plan.top0 is not None else [])
+    return plan.convs
 
 
 def wgrad_uses_halo(spec: ConvSpec) -> bool:
@@ -151,7 +139,14 @@ class PreparedWeights:
         self.w_fwd: Dict[str, torch.Tensor] = {}
         self.w_dgrad: Dict[str, torch.Tensor] = {}
         self.shift: Dict[str, torch.Tensor] = {}
-        self.convs = [c for c in prep_convs(plan) if not (trunk_only and c.name in ("head", "top0"))]
+        self.convs = [c for c in prep_convs(plan) if not (trunk_only and c.name == "head")]
+        # Q-head MLP operands (mlp_gemm.cu): every fp32 weight as hi + lo bf16; top.0's columns in the NHWC
+        # order of the head-conv output (p*64 + c per frame instead of the reference's Flatten order c*25 + p)
+        self.mlp: Dict[str, tuple] = {}
+        if not trunk_only:
+            nq = plan.num_classes * plan.action_dim
+            for key, (o, k) in (("top.0", (512, 1600 * plan.num_frames)), ("top.2", (256, 512)), ("top.4", (nq, 256))):
+                self.mlp[key] = (torch.empty(o, k, device=device, dtype=bf16), torch.empty(o, k, device=device, dtype=bf16))
         for c in self.convs:
             self.w_fwd[c.name] = torch.empty(c.cout, c.k, c.k, c.gemm_cin, device=device, dtype=bf16)
             if c.kmap == 0:
@@ -216,6 +211,8 @@ class PreparedWeights:
             t, o, n, tot = self._tiled
             L.check(lib.vdqn_weight_prep_tiled(t.data_ptr(), o.data_ptr(), n, tot, L.stream_ptr()),
                     "weight_prep_tiled")
+        for key, (hi, lo) in self.mlp.items():
+            ops.split_bf16(P[key + ".weight"], hi, lo, perm=(64, 25) if key == "top.0" else None)
 
 
 # output-parity classes of a 3x3 stride-2 data gradient: (a, b, taps_h, taps_w, offset in taps)
@@ -258,17 +255,18 @@ class Workspace:
         F = plan.num_frames
         Bf, B = nf // F, n // F
         f32 = torch.float32
-        self.flat = e(Bf, 1600 * F, dt=f32)
-        self.z1 = e(Bf, 512, dt=f32)
-        self.z2 = e(Bf, 256, dt=f32)
-        self.q = e(Bf, plan.num_classes * plan.action_dim, dt=f32)
+        # Q-head MLP activations as hi + lo bf16 pairs (the operands of the next GEMM; hi > 0 is the ReLU mask)
+        nq = plan.num_classes * plan.action_dim
+        self.z1 = (e(Bf, 512), e(Bf, 512))
+        self.z2 = (e(Bf, 256), e(Bf, 256))
+        self.q = e(Bf, nq, dt=f32)
         self._fwd_names = ("xp", "s", "idx", "p", "h")
-        self._mlp_names = ("flat", "z1", "z2", "q")
+        self._mlp_names = ("q",)
         self._F = F
         if train:
-            self.dz2 = e(B, 256, dt=f32)
-            self.dz1 = e(B, 512, dt=f32)
-            self.dflat = e(B, 1600 * F, dt=f32)
+            self.dq_hl = (z(B, (nq + 7) // 8 * 8), z(B, (nq + 7) // 8 * 8))
+            self.dz2 = (e(B, 256), e(B, 256))
+            self.dz1 = (e(B, 512), e(B, 512))
             self.dh = e(n, 5, 5, 64)
             # gradient wrt block outputs / conv1 outputs: two rotating buffers per resolution
             self.dy_out = {b.out_hw: (e(n, b.out_hw, b.out_hw, b.cout), e(n, b.out_hw, b.out_hw, b.cout))
@@ -280,7 +278,6 @@ class Workspace:
             self.dy_p = e(n, 56, 56, 64)
             self.dy_s = e(n, 112, 112, 64)
             max_part = max(wgrad_splits(c, n) * c.cout * c.K for c in prep_convs(plan))
-            self.dz1_bf16 = e(B, 512) if plan.top0 is not None else None
             self.part = e(max_part, dt=f32)
             # deferred split reductions (set `defer_fin` to use): every weight gradient keeps its own
             # partial buffer and ONE multi-tensor launch reduces them all at the end of the backward pass
@@ -303,6 +300,8 @@ class Workspace:
                 setattr(v, nm, None if t is None else t[:nb])
             for nm in self._mlp_names:
                 setattr(v, nm, getattr(self, nm)[:Bb])
+            v.z1 = tuple(t[:Bb] for t in self.z1)
+            v.z2 = tuple(t[:Bb] for t in self.z2)
             v.a1 = [t[:nb] for t in self.a1]
             v.out = [t[:nb] for t in self.out]
             v.idn = [None if t is None else t[:nb] for t in self.idn]
@@ -385,30 +384,77 @@ def forward_packed(plan: NetPlan, W: PreparedWeights, P: Dict[str, torch.Tensor]
     if trunk_only:
         return x                                      # [n, 7, 7, 512] bf16
     _conv(W, plan.head, x, ws.h, relu=True, **dual)
-    t0 = plan.top0
-    nrow = ws.flat.shape[0]
-    if t0 is None:
-        ops.head_flatten_fwd(ws.h, ws.flat)
-    parts = [(P, W, slice(0, nrow))]
-    if W2 is not None:
-        bs = split // plan.num_frames
-        parts = [(P, W, slice(0, bs)), (P2, W2, slice(bs, nrow))]
-    if t0 is not None:
-        # top.0 on the tensor cores: a 5x5 valid convolution over the head output, fp32 result
-        z1 = ws.z1.view(nrow, 1, 1, 512)
-        if W2 is not None and split % 128 == 0:
-            ops.conv_gemm(ws.h, W.w_fwd[t0.name], 1, 0, 0, shift=W.shift[t0.name], relu=True, out_f32=True, out=z1,
-                          w2=W2.w_fwd[t0.name], shift2=W2.shift[t0.name], split_n=split)
-        else:
-            for _, Wn, rows in parts:
-                ops.conv_gemm(ws.h[rows], Wn.w_fwd[t0.name], 1, 0, 0, shift=Wn.shift[t0.name], relu=True,
-                              out_f32=True, out=z1[rows])
-    for Pn, _, rows in parts:
-        if t0 is None:
-            ops.linear_fwd(ws.flat[rows], Pn["top.0.weight"], Pn["top.0.bias"], True, ws.z1[rows])
-        ops.linear_fwd(ws.z1[rows], Pn["top.2.weight"], Pn["top.2.bias"], True, ws.z2[rows])
-        ops.linear_fwd(ws.z2[rows], Pn["top.4.weight"], Pn["top.4.bias"], False, ws.q[rows])
+    mlp_forward(plan, W, P, ws, W2, P2, split)
     return ws.q
+
+
+def mlp_forward(plan: NetPlan, W: PreparedWeights, P, ws: Workspace, W2=None, P2=None, split: int = 0):
+    """top.0 / top.2 / top.4 (archs/HabitatDQNMultiAction.py:31,53) as three tensor-core GEMMs over split-bf16
+    operands (csrc/mlp_gemm.cu): the head-conv output [frames, 5, 5, 64] is read in place as [B, 1600 F]
+    (top.0's columns were permuted to that order when its operands were prepared), z1 / z2 only exist as the
+    hi + lo operand pairs of the next GEMM, Q is fp32.  With a second network, rows >= split // F use its
+    weights inside the same launches when that row is a multiple of 128, otherwise in a second set of launches."""
+    F = plan.num_frames
+    rows = ws.h.shape[0] // F
+    hA = ws.h.view(rows, 1600 * F)
+    nq = plan.num_classes * plan.action_dim
+    bs = split // F if W2 is not None else 0
+
+    def run(r0, r1, Wn, Pn, Wd=None, Pd=None, split_m=0):
+        m = r1 - r0
+        h, z1, z2, q = hA[r0:r1], tuple(t[r0:r1] for t in ws.z1), tuple(t[r0:r1] for t in ws.z2), ws.q[r0:r1]
+        w0, w2, w4 = Wn.mlp["top.0"], Wn.mlp["top.2"], Wn.mlp["top.4"]
+        d0, d2, d4 = (Wd.mlp[k] for k in ("top.0", "top.2", "top.4")) if Wd is not None else (None, None, None)
+        kw = lambda k: dict(split_m=split_m, bias2=Pd[k + ".bias"]) if Wd is not None else {}  # noqa: E731
+        ops.mlp_gemm([(h, w0[0], 1600 * F), (h, w0[1], 1600 * F)], m, 512, bias=Pn["top.0.bias"], relu=True,
+                     segments2=[(h, d0[0], 0), (h, d0[1], 0)] if Wd is not None else None,
+                     out_hi=z1[0], out_lo=z1[1], **kw("top.0"))
+        ops.mlp_gemm([(z1[0], w2[0], 512), (z1[1], w2[0], 512), (z1[0], w2[1], 512)], m, 256, bias=Pn["top.2.bias"],
+                     relu=True, out_hi=z2[0], out_lo=z2[1],
+                     segments2=[(None, d2[0], 0), (None, d2[0], 0), (None, d2[1], 0)] if Wd is not None else None,
+                     **kw("top.2"))
+        ops.mlp_gemm([(z2[0], w4[0], 256), (z2[1], w4[0], 256), (z2[0], w4[1], 256)], m, nq, bias=Pn["top.4.bias"],
+                     out_f32=q,
+                     segments2=[(None, d4[0], 0), (None, d4[0], 0), (None, d4[1], 0)] if Wd is not None else None,
+                     **kw("top.4"))
+    if W2 is None:
+        run(0, rows, W, P)
+    elif bs % 128 == 0:
+        run(0, rows, W, P, W2, P2, split_m=bs)
+    else:
+        run(0, bs, W, P)
+        run(bs, rows, W2, P2)
+
+
+def mlp_backward(plan: NetPlan, W: PreparedWeights, P, G, ws: Workspace, dq: torch.Tensor):
+    """Backward of the Q-head MLP on the same kernel: per layer the data gradient dy W (W read MN-major, ReLU
+    mask and bias-gradient column sums in the epilogue, result kept as a hi + lo pair) and the weight gradient
+    dy^T x (both operands MN-major, fp32 result straight into the gradient arena; d top.0.weight is un-permuted
+    on the way out).  The last data gradient is the head conv's dy: bf16 NHWC, masked by the head ReLU, with the
+    head bias gradient as its column sums.  `ws` is the backward view (first n_bwd frames)."""
+    F = plan.num_frames
+    B = ws.h.shape[0] // F
+    hA = ws.h.view(B, 1600 * F)
+    nq = plan.num_classes * plan.action_dim
+    w0, w2, w4 = W.mlp["top.0"], W.mlp["top.2"], W.mlp["top.4"]
+    dqh, dql = ws.dq_hl
+    z1, z2, dz1, dz2 = ws.z1, ws.z2, ws.dz1, ws.dz2
+    ops.split_bf16(dq.view(B, nq), dqh, dql, colsum=G["top.4.bias"])
+    # data-gradient chain: dq -> dz2 -> dz1 (each needs the previous one)
+    ops.mlp_gemm([(dqh, w4[0], nq), (dql, w4[0], nq), (dqh, w4[1], nq)], B, 256, b_mn=True, mask_bf16=z2[0],
+                 out_hi=dz2[0], out_lo=dz2[1], colsum=G["top.2.bias"])
+    ops.mlp_gemm([(dz2[0], w2[0], 256), (dz2[1], w2[0], 256), (dz2[0], w2[1], 256)], B, 512, b_mn=True,
+                 mask_bf16=z1[0], out_hi=dz1[0], out_lo=dz1[1], colsum=G["top.0.bias"])
+    # the three weight gradients and the head conv's dy are independent of each other: one launch
+    ops.mlp_gemm_grouped([
+        ops.mlp_problem([(dz1[0], hA, B), (dz1[1], hA, B)], 512, 1600 * F, a_mn=True, b_mn=True,
+                        out_f32=G["top.0.weight"], perm=(64, 25)),
+        ops.mlp_problem([(dz1[0], w0[0], 512), (dz1[1], w0[0], 512), (dz1[0], w0[1], 512)], B, 1600 * F, b_mn=True,
+                        mask_bf16=hA, out_bf16=ws.dh.view(B, 1600 * F), colsum=G["features.8.bias"], colsum_mod=64),
+        ops.mlp_problem([(dz2[0], z1[0], B), (dz2[1], z1[0], B), (dz2[0], z1[1], B)], 256, 512, a_mn=True, b_mn=True,
+                        out_f32=G["top.2.weight"]),
+        ops.mlp_problem([(dqh, z2[0], B), (dql, z2[0], B), (dqh, z2[1], B)], nq, 256, a_mn=True, b_mn=True,
+                        out_f32=G["top.4.weight"])])
 
 
 def _wgrad(plan, P, G, ws: Workspace, c: ConvSpec, x, dy, dbeta_key: Optional[str]):
@@ -460,24 +506,8 @@ def backward(plan: NetPlan, W: PreparedWeights, P: Dict[str, torch.Tensor], G: D
         def notify(stage):
             _flush_finalize(ws)          # the stage's gradients are complete only once its reductions ran
             on_grads_ready(stage)
-    # ---- MLP (fp32)
-    ops.linear_bwd(ws.z2, P["top.4.weight"], None, dq, G["top.4.weight"], G["top.4.bias"], False, dx=ws.dz2)
-    ops.linear_bwd(ws.z1, P["top.2.weight"], ws.z2, ws.dz2, G["top.2.weight"], G["top.2.bias"], True, dx=ws.dz1)
-    t0 = plan.top0
-    if t0 is None:
-        ops.linear_bwd(ws.flat, P["top.0.weight"], ws.z1, ws.dz1, G["top.0.weight"], G["top.0.bias"], True,
-                       dx=ws.dflat)
-        # ---- head conv
-        ops.head_flatten_bwd(ws.dflat, ws.h, ws.dh, dbias=G["features.8.bias"])
-    else:
-        # top.0 backward on the tensor cores: masked gradient (+ bias gradient) in fp32 and bf16, then
-        # the weight gradient as a 5x5 conv weight gradient over the head output and the data gradient
-        # as the matching full correlation, whose epilogue applies the head ReLU mask and accumulates
-        # the head bias gradient
-        ops.relu_mask_colsum(ws.dz1, ws.z1, G["top.0.bias"], True, out_bf16=ws.dz1_bf16)
-        dy0 = ws.dz1_bf16.view(ws.dz1_bf16.shape[0], 1, 1, 512)
-        _wgrad(plan, P, G, ws, t0, ws.h, dy0, None)
-        ops.conv_gemm(dy0, W.w_dgrad[t0.name], 1, 4, 4, mask_src=ws.h, colsum=G["features.8.bias"], out=ws.dh)
+    # ---- Q-head MLP + the head conv's dy (ws.dh)
+    mlp_backward(plan, W, P, G, ws, dq)
     last = plan.blocks[-1]
     x_head = ws.out[-1]
     _wgrad(plan, P, G, ws, plan.head, x_head, ws.dh, None)

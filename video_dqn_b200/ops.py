@@ -281,6 +281,74 @@ def linear_bwd(x, w, y, dy, dw, db, relu, dx=None, need_dx=True):
     return dx
 
 
+def split_bf16(x, hi, lo, *, perm=None, colsum=None):
+    """x fp32 [rows, cols] -> hi = bf16(x), lo = bf16(x - hi), both [rows, ld] with ld >= cols (zero padded);
+    perm = (c, p): every block of c*p columns is re-ordered from c-major to p-major (top.0.weight)."""
+    lib = L.load()
+    _cuda(x, torch.float32, "x"); _cuda(hi, bf16, "hi"); _cuda(lo, bf16, "lo")
+    _req(x.dim() == 2 and hi.shape == lo.shape and hi.shape[0] == x.shape[0] and hi.shape[1] >= x.shape[1], "bad shape")
+    pc, pp = perm if perm is not None else (0, 0)
+    with _Prof("mlp", (x.shape[0], x.shape[1])):
+        L.check(lib.vdqn_split_bf16(x.data_ptr(), hi.data_ptr(), lo.data_ptr(), x.shape[0], x.shape[1], hi.shape[1],
+                                    pc, pp, L.ptr(colsum), L.stream_ptr()), "split_bf16")
+
+
+def mlp_problem(segments, M, N, *, a_mn=False, b_mn=False, segments2=None, split_m=0, bias=None, bias2=None,
+                relu=False, mask_f32=None, mask_bf16=None, out_f32=None, perm=None, out_hi=None, out_lo=None,
+                out_bf16=None, colsum=None, colsum_mod=0, BN=64):
+    """One GEMM of the Q-head MLP as a descriptor: D[M, N] = sum over `segments` [(A, B, K), ...] of
+    A[m, :K] . B[n, :K] (bf16 operands, fp32 accumulation; include/vdqn.h).  A / B are 2-D bf16 tensors:
+    [M or N, >= K] K-major, or with a_mn / b_mn [>= K, M or N] MN-major.  `segments2` (+ bias2, split_m): the
+    B operands of rows >= split_m.  Returns (descriptor, tensors it points into)."""
+    d = L.MlpGemmDesc()
+    _req(1 <= len(segments) <= 3, "mlp_gemm: 1..3 segments")
+    keep = []
+
+    def fill(op, t, name):
+        _req(t.is_cuda and t.dtype == bf16 and t.dim() == 2 and t.stride(1) == 1, f"{name}: 2-D bf16, unit column stride")
+        op.ptr, op.rows, op.cols, op.ld = t.data_ptr(), t.shape[0], t.shape[1], t.stride(0)
+        keep.append(t)
+    for i, (A, B, K) in enumerate(segments):
+        fill(d.a[i], A, "A"); fill(d.b[i], B, "B")
+        d.K[i] = K
+        if segments2 is not None:
+            fill(d.b2[i], segments2[i][1], "B2")
+    d.nseg, d.M, d.N, d.BN = len(segments), M, N, BN
+    d.a_mn, d.b_mn, d.split_m = int(a_mn), int(b_mn), int(split_m if segments2 is not None else 0)
+    d.bias, d.bias2, d.relu = L.ptr(bias), L.ptr(bias2), int(relu)
+    if mask_f32 is not None:
+        d.mask_f32, d.ldmask = mask_f32.data_ptr(), mask_f32.stride(0)
+    if mask_bf16 is not None:
+        d.mask_bf16, d.ldmask = mask_bf16.data_ptr(), mask_bf16.stride(0)
+    if out_f32 is not None:
+        _req(out_f32.dtype == torch.float32 and out_f32.stride(-1) == 1, "out_f32")
+        d.out_f32, d.ld_f32 = out_f32.data_ptr(), out_f32.stride(0)
+        if perm is not None:
+            d.perm_c, d.perm_p = perm
+    if out_hi is not None:
+        _req(out_hi.shape == out_lo.shape and out_hi.dtype == bf16, "out_hi / out_lo")
+        d.out_hi, d.out_lo, d.ld_hl = out_hi.data_ptr(), out_lo.data_ptr(), out_hi.stride(0)
+    if out_bf16 is not None:
+        _req(out_bf16.dtype == bf16, "out_bf16")
+        d.out_bf16, d.ld_bf16 = out_bf16.data_ptr(), out_bf16.stride(0)
+    if colsum is not None:
+        _cuda(colsum, torch.float32, "colsum")
+        d.colsum, d.colsum_mod = colsum.data_ptr(), colsum_mod
+    return d, keep
+
+
+def mlp_gemm_grouped(problems):
+    """Up to four independent `mlp_problem`s in one launch."""
+    lib = L.load()
+    arr = (L.MlpGemmDesc * len(problems))(*[p[0] for p in problems])
+    with _Prof("mlp", tuple((p[0].M, p[0].N) for p in problems)):
+        L.check(lib.vdqn_mlp_gemm_grouped(arr, len(problems), L.stream_ptr()), "mlp_gemm")
+
+
+def mlp_gemm(segments, M, N, **kw):
+    mlp_gemm_grouped([mlp_problem(segments, M, N, **kw)])
+
+
 def relu_mask_colsum(dy, y, db, relu=True, out_bf16=None):
     """dy <- dy * (y > 0) in place (fp32 [B, O]); db[o] = sum_b dy[b, o]; optional bf16 copy."""
     lib = L.load()
