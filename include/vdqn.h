@@ -93,6 +93,14 @@ typedef struct vdqn_conv_desc {
    * n - x_alias_shift of x.  The fused step runs online [s ; s'] and target [s'] as one 3B pass; the
    * third range re-reads the packed s' frames instead of keeping a copy.  0 / 0: off. */
   int32_t x_alias_from, x_alias_shift;
+  /* Packed stem fused with torchvision's resnet.maxpool (max_pool2d(3, 2, 1)): when pool_out != NULL the
+   * conv + shift + ReLU result is NOT stored (`out` is ignored); pool_out receives the pooled tensor
+   * bf16 [N][H/2][W/2][Cout] and, for images n < pool_idx_images, pool_idx (uint8, same shape, may be NULL)
+   * the arg-max slot r*3+s of every window (first maximum in scan order, as torch picks it) that
+   * vdqn_maxpool_bwd consumes.  Needs H %% 14 == 0, W %% 8 == 0, flags = VDQN_EPI_RELU, no residual / mask. */
+  void* pool_out;
+  uint8_t* pool_idx;
+  int32_t pool_idx_images;
 } vdqn_conv_desc;
 int vdqn_conv_gemm(const vdqn_conv_desc* d, void* stream);
 

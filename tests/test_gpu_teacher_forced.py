@@ -256,6 +256,20 @@ def test_every_layer_of_one_step_teacher_forced():
         # an input pixel that is the arg-max of up to four windows receives the sum of their gradients; the
         # kernel adds them pairwise in bf16 (packed __hadd2), the reference in fp32: 2 ulp of the terms
         _check_bf16("bwd/maxpool", dy_s, dy_s_ref, ulps=2, frac=0.01, mag=g_abs)
+    elif getattr(bw, "dy_s", None) is not None:
+        # stem + pool fused in the forward pass: the stem output never reached HBM, so the arg-max routing is
+        # recomputed from the CPU's stem output.  That one differs from the kernel's by a few bf16 rounding
+        # flips, each of which can move a window's arg-max: the routing check is looser (1 % of the pixels),
+        # the stem weight gradient below is then formed from the kernel's OWN dy_s and stays tight
+        s_b = _bf(F.relu(stem(x[:B]))).detach().requires_grad_(True)
+        pooled = F.max_pool2d(s_b, 3, 2, 1)
+        (g_s,) = torch.autograd.grad((pooled * _nchw(bw.dy_p)).sum(), [s_b], retain_graph=True)
+        (g_abs,) = torch.autograd.grad((pooled * _nchw(bw.dy_p).abs()).sum(), [s_b])
+        dy_s = _nchw(bw.dy_s)
+        ref = _bf(g_s * (s_b.detach() > 0))
+        differ = ((dy_s - ref).abs() > 2 * 2.0 ** -7 * g_abs + 1e-5 * ref.abs().max()).float().mean().item()
+        REPORT["bwd/maxpool (routing from the CPU stem output)"] = {"frac_different": differ}
+        assert differ <= 0.01, differ
     else:                                     # pooling gradient formed inside the stem weight-gradient kernel
         s_b = _bf(F.relu(stem(x[:B]))).detach().requires_grad_(True)
         pooled = F.max_pool2d(s_b, 3, 2, 1)

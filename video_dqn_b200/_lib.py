@@ -24,7 +24,7 @@ class ConvDesc(C.Structure):
                                      "out_scatter", "flags", "tile_n", "max_ctas", "algo", "pad_hi_w",
                                      "scatter_off_h", "scatter_off_w")] + \
                [("w2", c_void_p), ("shift2", c_void_p), ("split_n", c_int), ("x_alias_from", c_int),
-                ("x_alias_shift", c_int)]
+                ("x_alias_shift", c_int), ("pool_out", c_void_p), ("pool_idx", c_void_p), ("pool_idx_images", c_int)]
 
 
 class WgradDesc(C.Structure):

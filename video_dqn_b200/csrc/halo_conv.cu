@@ -31,6 +31,11 @@ struct HaloArgs {
   const float* shift2;
   int alias_from, alias_shift;     // images >= alias_from are read from image n - alias_shift (stem only)
   EpiArgs epi;
+  // POOL variant (packed stem fused with max_pool2d(3, 2, 1), torchvision resnet.maxpool): pooled output
+  // [N][H/2][W/2][64] bf16, arg-max slots (uint8, window scan order r*3+s) for images < idx_images
+  __nv_bfloat16* pool_out;
+  uint8_t* pool_idx;
+  int idx_images;
 };
 
 // PAIR (CK = 64 only): the CTA is one half of a cta_group::2 pair.  The pair works on two tiles at a
@@ -38,9 +43,19 @@ struct HaloArgs {
 // the filter rows -- these kernels are bound by the shared-memory reads of the MMA operands
 // (role profile: ~1900 cycles per tile against 1152 of tensor-pipe time), and the filter is a third
 // of them.
-template <int CK, bool PAIR = false>
+// POOL (CK = 16 only): the stem's ReLU output never goes to HBM.  Tiles overlap by two rows -- a tile covers
+// stem rows 14*th - 1 .. 14*th + 14, i.e. the rows of 7 pooled rows (row 15 of the tile is computed and not
+// used: 14 % more MMA work) -- and a CTA walks the 14 tiles of a strip (image, th) from left to right, keeping
+// the last column of a tile for the next one, so every 3x3/2 window is complete inside the CTA.  The eight
+// epilogue warps put the tile (bf16, after shift + ReLU) into one of three shared buffers [16][9][64] (column 0
+// = the column carried over), meet at a named barrier, and 224 threads form the 7 x 4 pooled pixels (and the
+// arg-max slots the backward pass needs) from it.  HBM: 1176 MB written + 1234 MB re-read by the pooling
+// kernels per 768 frames become 308 MB written.
+template <int CK, bool PAIR = false, bool POOL = false>
 struct HaloCfg {
   static constexpr int TH = 16, TW = 8, BN = 64;
+  static constexpr int POOL_ROWS = 14;                  // stem rows a pooled tile advances by
+  static constexpr int POOL_BUF_BYTES = 16 * 9 * 128;   // [16 rows][1 carried + 8 columns][64 ch] bf16
   static constexpr int ROW_BYTES = CK * 2;
   static constexpr uint64_t SWZ = (CK == 64) ? kSwz128 : kSwz32;
   static constexpr int R = (CK == 64) ? 3 : 4, S = R;   // filter size is fixed per variant
@@ -63,12 +78,14 @@ struct HaloCfg {
   static constexpr int EPI_WARPS = 8;
   static constexpr int OUT_BUFS = (CK == 64 && !PAIR) ? 1 : 2;
   static constexpr int EPI_WARP_BYTES = (OUT_BUFS + 4) * 2048;
-  static constexpr int EPI_BYTES = EPI_WARPS * EPI_WARP_BYTES;
+  static constexpr int EPI_BYTES = POOL ? 3 * POOL_BUF_BYTES : EPI_WARPS * EPI_WARP_BYTES;
   // 12 warps = 384 threads: the register file then allows 168 registers per thread (416 threads were
   // compiled against the 512-thread limit of 128 and spilled)
   static constexpr int PROD_WARPS = 3;
   static constexpr int MMA_WARP = PROD_WARPS;
-  static constexpr int THREADS = (PROD_WARPS + 1 + EPI_WARPS) * 32;
+  // POOL: four more warps do the pooling, so a tile's pooling overlaps the next tile's TMEM drain
+  static constexpr int POOL_WARPS = POOL ? 4 : 0;
+  static constexpr int THREADS = (PROD_WARPS + 1 + EPI_WARPS + POOL_WARPS) * 32;
   static constexpr int SMEM_BYTES = W_BYTES + STAGES * STAGE_BYTES + EPI_BYTES + 1024 + 512;
   // accumulator ring: with 64-column accumulators TMEM holds 4 of them, so the MMA warp can run up to
   // 4 tiles ahead of the epilogue and the mbarrier hand-off latencies (MMA -> epilogue -> MMA) overlap
@@ -85,13 +102,14 @@ __device__ __forceinline__ void tma_load_tiled_4d(uint32_t dst, const void* tmap
       : "memory");
 }
 
-template <int CK, bool PAIR>
-__global__ void __launch_bounds__(HaloCfg<CK, PAIR>::THREADS, 1)
+template <int CK, bool PAIR, bool POOL = false>
+__global__ void __launch_bounds__(HaloCfg<CK, PAIR, POOL>::THREADS, 1)
 halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                  const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
                  const __grid_constant__ CUtensorMap tmMask, const HaloArgs a) {
-  using Cfg = HaloCfg<CK, PAIR>;
+  using Cfg = HaloCfg<CK, PAIR, POOL>;
   static_assert(!PAIR || CK == 64, "CTA pairs: 64-channel variant only");
+  static_assert(!POOL || (CK == 16 && !PAIR), "fused pooling: packed stem only");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sW = smem_base;
@@ -124,7 +142,16 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       mbar_init(tempty_bar(i), (PAIR ? 2 : 1) * Cfg::EPI_WARPS);
     }
     mbar_init(w_bar, 1);
-    for (int i = 0; i < 2 * Cfg::EPI_WARPS; ++i) mbar_init(ld_bar0 + 8u * i, 1);
+    if constexpr (POOL) {
+      // ld_bar0 + 8*i: i = 0..2 "buffer i holds a drained tile" (one arrive per drain warp),
+      //                i = 3..5 "buffer i-3 has been pooled" (one arrive per pooling warp)
+      for (int i = 0; i < 3; ++i) {
+        mbar_init(ld_bar0 + 8u * i, Cfg::EPI_WARPS);
+        mbar_init(ld_bar0 + 8u * (3 + i), Cfg::POOL_WARPS);
+      }
+    } else {
+      for (int i = 0; i < 2 * Cfg::EPI_WARPS; ++i) mbar_init(ld_bar0 + 8u * i, 1);
+    }
     fence_mbar_init();
   }
   // warps 0-2: producers (the cp.async variant uses all three, the TMA variant only warp 0),
@@ -177,6 +204,39 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     if (c.tw >= a.tiles_w) { c.tw -= a.tiles_w; ++c.th; }
     if (c.th >= a.tiles_h) { c.th -= a.tiles_h; ++c.n; }
   };
+  // POOL: the CTA's k-th tile.  Tiles are numbered strip-major (t = strip * tiles_w + tw, strip = n * tiles_h
+  // + th) exactly as above, but a CTA takes WHOLE strips: its strips are strip0 + i * sstep, and its k-th
+  // tile is column k % tiles_w of its (k / tiles_w)-th strip.
+  const int strip0 = (second ? a.split_tile / a.tiles_w : 0) + (cta - (second ? split_cta : 0));
+  const int sstep = tstep;                       // CTAs of this range
+  const int strip_end = tile_end / a.tiles_w;
+  const int my_strips = strip0 < strip_end ? (strip_end - strip0 + sstep - 1) / sstep : 0;
+  const int my_tiles = POOL ? my_strips * a.tiles_w : 0;
+  auto pool_tile = [&](int k, int& n, int& th, int& tw) {
+    const int si = k / a.tiles_w;
+    tw = k - si * a.tiles_w;
+    const int strip = strip0 + si * sstep;
+    n = strip / a.tiles_h;
+    th = strip - n * a.tiles_h;
+  };
+  // the same walk without divisions (two per tile sat on the critical path of every role: ~350 cycles of a
+  // ~1100-cycle tile): `step` tiles further along this CTA's tile sequence
+  struct PoolIt { int n, th, tw, dn, dth; };
+  auto pool_it = [&](int k) {
+    PoolIt c;
+    pool_tile(k, c.n, c.th, c.tw);
+    c.dn = sstep / a.tiles_h;
+    c.dth = sstep - c.dn * a.tiles_h;
+    return c;
+  };
+  auto pool_next_strip = [&](PoolIt& c) {
+    c.n += c.dn; c.th += c.dth;
+    if (c.th >= a.tiles_h) { c.th -= a.tiles_h; ++c.n; }
+  };
+  auto pool_advance = [&](PoolIt& c, int step) {       // step < tiles_w
+    c.tw += step;
+    if (c.tw >= a.tiles_w) { c.tw -= a.tiles_w; pool_next_strip(c); }
+  };
 
   if (warp < Cfg::PROD_WARPS) {
     // the filter: one [64 x CK] tile per tap, resident for the whole kernel
@@ -221,8 +281,15 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       PROF_BEGIN
       constexpr int NP = Cfg::PROD_WARPS;
       TileIt ti = tile_it(tile0 + warp * tstep, NP * tstep);
-      for (int t = tile0 + warp * tstep; t < tile_end; t += NP * tstep, k += NP, advance(ti)) {
-        const int n = ti.n, h0 = ti.th * Cfg::TH, w0 = ti.tw * Cfg::TW;
+      PoolIt pit = pool_it(POOL ? warp : 0);
+      for (int t = tile0 + warp * tstep; POOL ? k < my_tiles : t < tile_end; t += NP * tstep, k += NP, advance(ti)) {
+        int n = ti.n, h0 = ti.th * Cfg::TH, w0 = ti.tw * Cfg::TW;
+        if constexpr (POOL) {
+          n = pit.n;
+          h0 = pit.th * Cfg::POOL_ROWS - 1;
+          w0 = pit.tw * Cfg::TW;
+          pool_advance(pit, NP);
+        }
         PROF_TILE
         const int stage = k % Cfg::STAGES;
         PROF_WAIT_A(mbar_wait(empty_bar(stage), (((uint32_t)(k / Cfg::STAGES)) & 1u) ^ 1u))
@@ -289,7 +356,7 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     uint32_t phase = 0;
     int it = 0;
     PROF_BEGIN
-    for (int t = tile0; t < tile_end; t += tstep, ++it) {
+    for (int t = tile0; POOL ? it < my_tiles : t < tile_end; t += tstep, ++it) {
       const int acc = it % Cfg::NACC;
       const uint32_t acc_phase = (it / Cfg::NACC) & 1;
       PROF_TILE
@@ -328,6 +395,129 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
     }
     PROF_END(4)
+  } else if (POOL && warp >= Cfg::MMA_WARP + 1 + Cfg::EPI_WARPS) {
+    // ---------------------------------------------------------------- pooling warps (POOL variant)
+    if constexpr (POOL) {
+      const int ptid = (warp - (Cfg::MMA_WARP + 1 + Cfg::EPI_WARPS)) * 32 + lane;      // 0..127
+      const int Hp = a.H / 2, Wp = a.W / 2;
+      PROF_BEGIN
+      PoolIt pit = pool_it(0);
+      int buf = 0;
+      uint32_t ready_phase = 0;
+      for (int k = 0; k < my_tiles; ++k, buf = (buf == 2 ? 0 : buf + 1)) {
+        PROF_TILE
+        const int n = pit.n, th = pit.th, tw = pit.tw;
+        pool_advance(pit, 1);
+        const uint32_t sbuf = epi_base + (uint32_t)buf * Cfg::POOL_BUF_BYTES;
+        const uint8_t* sbuf_p = smem_raw + (sbuf - smem_u32(smem_raw));
+        const bool want_idx = a.pool_idx != nullptr && n < a.idx_images;
+        PROF_WAIT_A(mbar_wait(ld_bar0 + 8u * buf, ready_phase))
+        if (buf == 2) ready_phase ^= 1u;
+        if (a.epi.flags & 8) {             // debug: no pooling work (bottleneck probing)
+          __syncwarp();
+          if (lane == 0) mbar_arrive(ld_bar0 + 8u * (3 + buf));
+          continue;
+        }
+        // Separable 3x3 maximum: thread (row group rg, pooled column pc, channel group pk) reduces the three
+        // columns of each of its (up to) five tile rows once, then combines rows {0,1,2} and {2,3,4} into its two
+        // pooled rows -- 15 loads and ~half the compares of nine taps per output, and all 28 x 8 outputs of the
+        // tile in ONE pass of the four warps.  Slots keep torch's choice: first maximum in (row, column) order.
+        const int rg = ptid >> 5, pc = (ptid >> 3) & 3, pk = ptid & 7;
+        const int nrow = rg < 3 ? 5 : 3;
+        // all fifteen loads first (plain loads: the compiler keeps them in flight together)
+        uint4 ld[5][3];
+#pragma unroll
+        for (int r = 0; r < 5; ++r) {
+#pragma unroll
+          for (int sx = 0; sx < 3; ++sx) {
+            const int gg = 4 * rg + (r < nrow ? r : 0), cc = 2 * pc + sx;
+            ld[r][sx] = *reinterpret_cast<const uint4*>(sbuf_p + (gg * 9 + cc) * 128 + ((pk ^ ((cc + 7) & 7)) << 4));
+          }
+        }
+        uint32_t best[2][4], slot[2][4];
+        if (!want_idx) {
+          // values only (two thirds of the frames of a step: s' is never back-propagated through).  Every value
+          // is >= +0 or the -inf of the padding, so bf16 order is the order of the bit patterns as signed
+          // 16-bit integers and a three-way integer maximum does two columns / rows per instruction.
+          uint32_t hv[5][4];
+#pragma unroll
+          for (int r = 0; r < 5; ++r) {
+            const uint32_t v0[4] = {ld[r][0].x, ld[r][0].y, ld[r][0].z, ld[r][0].w};
+            const uint32_t v1[4] = {ld[r][1].x, ld[r][1].y, ld[r][1].z, ld[r][1].w};
+            const uint32_t v2[4] = {ld[r][2].x, ld[r][2].y, ld[r][2].z, ld[r][2].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) hv[r][e] = __vimax3_s16x2(v0[e], v1[e], v2[e]);
+          }
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            best[0][e] = __vimax3_s16x2(hv[0][e], hv[1][e], hv[2][e]);
+            best[1][e] = __vimax3_s16x2(hv[2][e], hv[3][e], hv[4][e]);
+            slot[0][e] = slot[1][e] = 0u;
+          }
+        } else {
+        uint32_t hv[5][4], hs[5][4];
+#pragma unroll
+        for (int r = 0; r < 5; ++r) {
+          if (r < nrow) {
+            const uint4 c3[3] = {ld[r][0], ld[r][1], ld[r][2]};
+            const uint32_t v0[4] = {c3[0].x, c3[0].y, c3[0].z, c3[0].w};
+            const uint32_t v1[4] = {c3[1].x, c3[1].y, c3[1].z, c3[1].w};
+            const uint32_t v2[4] = {c3[2].x, c3[2].y, c3[2].z, c3[2].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const __nv_bfloat162 a0 = *reinterpret_cast<const __nv_bfloat162*>(&v0[e]);
+              const __nv_bfloat162 a1 = *reinterpret_cast<const __nv_bfloat162*>(&v1[e]);
+              const __nv_bfloat162 a2 = *reinterpret_cast<const __nv_bfloat162*>(&v2[e]);
+              const __nv_bfloat162 m01 = __hmax2(a0, a1);
+              const __nv_bfloat162 m012 = __hmax2(m01, a2);
+              hv[r][e] = *reinterpret_cast<const uint32_t*>(&m012);
+              const uint32_t g1 = __hgt2_mask(a1, a0);                 // column 1 beats column 0
+              const uint32_t g2 = __hgt2_mask(a2, m01);                // column 2 beats both
+              hs[r][e] = (g2 & 0x00020002u) | (~g2 & g1 & 0x00010001u);
+            }
+          }
+        }
+#pragma unroll
+        for (int o = 0; o < 2; ++o) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const __nv_bfloat162 b0 = *reinterpret_cast<const __nv_bfloat162*>(&hv[2 * o][e]);
+            if (2 * o + 2 < nrow) {
+              const __nv_bfloat162 b1 = *reinterpret_cast<const __nv_bfloat162*>(&hv[2 * o + 1][e]);
+              const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&hv[2 * o + 2][e]);
+              const __nv_bfloat162 m01 = __hmax2(b0, b1);
+              const __nv_bfloat162 m012 = __hmax2(m01, b2);
+              best[o][e] = *reinterpret_cast<const uint32_t*>(&m012);
+              const uint32_t g1 = __hgt2_mask(b1, b0);
+              const uint32_t g2 = __hgt2_mask(b2, m01);
+              const uint32_t s01 = (g1 & (hs[2 * o + 1][e] + 0x00030003u)) | (~g1 & hs[2 * o][e]);
+              slot[o][e] = (g2 & (hs[2 * o + 2][e] + 0x00060006u)) | (~g2 & s01);
+            } else {
+              best[o][e] = 0u; slot[o][e] = 0u;
+            }
+          }
+        }
+        }
+        __syncwarp();                                   // every lane's reads of the buffer are complete
+        if (lane == 0) mbar_arrive(ld_bar0 + 8u * (3 + buf));
+        PROF_WAIT_B(;)
+#pragma unroll
+        for (int o = 0; o < 2; ++o) {
+          const int pr = 2 * rg + o;
+          if (pr < 7 && !(a.epi.flags & 64)) {       // flag 64: debug, no global stores
+            const long off = ((((long)n * Hp + th * (Cfg::POOL_ROWS / 2) + pr) * Wp + tw * (Cfg::TW / 2) + pc) * 64 + pk * 8);
+            *reinterpret_cast<uint4*>(a.pool_out + off) = make_uint4(best[o][0], best[o][1], best[o][2], best[o][3]);
+            if (want_idx) {
+              uint2 ip;
+              ip.x = __byte_perm(slot[o][0], slot[o][1], 0x6420);
+              ip.y = __byte_perm(slot[o][2], slot[o][3], 0x6420);
+              *reinterpret_cast<uint2*>(a.pool_idx + off) = ip;
+            }
+          }
+        }
+      }
+      PROF_END(13 + (warp & 1))
+    }
   } else {
     const int ew = warp - (Cfg::MMA_WARP + 1);   // 0..7
     const int quad = warp & 3;                // TMEM lane quadrant this warp may touch
@@ -440,10 +630,89 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         atomicAdd(a.epi.colsum + c0 + lane, csum);
       }
     };
+    if constexpr (POOL) {
+      // ---------------------------------------------------------------- stem drain (the pooling warps take it from here)
+      float shift_r[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) shift_r[i] = epi.shift != nullptr ? __ldg(epi.shift + c0 + i) : 0.f;
+      PROF_BEGIN
+      PoolIt pit = pool_it(0);
+      // buf = k % 3: this tile's buffer; nbuf = (k + 1) % 3 = (k - 2) % 3: the next tile's, which is also the one
+      // tile k-2 was pooled from
+      int buf = 0, nbuf = 1;
+      uint32_t done_phase = 0;
+      if (j == 7) {            // column -1 of the CTA's first tile (a strip start): padding
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4)
+          sts128(epi_base + (uint32_t)(g * 9 * 128) + ((uint32_t)((half * 4 + q4) ^ 7) << 4),
+                 make_uint4(0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u));
+      }
+      for (int k = 0; k < my_tiles; ++k, buf = nbuf, nbuf = (nbuf == 2 ? 0 : nbuf + 1)) {
+        PROF_TILE
+        const int th = pit.th;
+        const bool last_of_strip = pit.tw == a.tiles_w - 1;
+        pool_advance(pit, 1);
+        const int acc = k % Cfg::NACC;
+        const uint32_t acc_phase = (k / Cfg::NACC) & 1;
+        PROF_WAIT_A(mbar_wait(tfull_bar(acc), acc_phase))
+        tc_fence_after();
+        uint32_t raw[32];
+        tmem_ld_32x32(tmem_base + acc * Cfg::BN + c0 + ((uint32_t)(quad * 32) << 16), raw);
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) release_acc(acc);
+        // this thread's pixel: tile row g = stem row 14*th - 1 + g (rows outside the image are padding: -inf)
+        const int hs = th * Cfg::POOL_ROWS - 1 + g;
+        const bool rvalid = (unsigned)hs < (unsigned)a.H;
+        uint4 pkd[4];
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&pkd[q4]);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float x0 = fmaxf(__uint_as_float(raw[8 * q4 + 2 * e]) + shift_r[8 * q4 + 2 * e], 0.f);
+            const float x1 = fmaxf(__uint_as_float(raw[8 * q4 + 2 * e + 1]) + shift_r[8 * q4 + 2 * e + 1], 0.f);
+            h2[e] = __floats2bfloat162_rn(x0, x1);
+          }
+          if (!rvalid) pkd[q4] = make_uint4(0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u);
+        }
+        // tile k writes buffer k % 3 (last read by the pooling of tile k-3) and column 0 of buffer (k+1) % 3
+        // (last read by the pooling of tile k-2): wait for tile k-2 to have been pooled
+        if (k >= 2) {
+          PROF_WAIT_B(mbar_wait(ld_bar0 + 8u * (3 + nbuf), done_phase))
+          if (nbuf == 2) done_phase ^= 1u;
+        }
+        if (epi.flags & 32) {              // debug: drain without the shared-memory stores (bottleneck probing)
+          __syncwarp();
+          if (lane == 0) mbar_arrive(ld_bar0 + 8u * buf);
+          continue;
+        }
+        // buffer [g][c][8 chunks of 16 B], chunk position XOR-ed with (c - 1) & 7 so that the eight pixels of a
+        // tile row (128 B apart) do not share banks
+        const uint32_t sbuf = epi_base + (uint32_t)buf * Cfg::POOL_BUF_BYTES;
+        const uint32_t prow = sbuf + (uint32_t)((g * 9 + j + 1) * 128);
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) sts128(prow + ((uint32_t)((half * 4 + q4) ^ j) << 4), pkd[q4]);
+        if (j == 7) {        // the tile's last column is column 0 of the next tile's buffer
+          const uint32_t nrow = epi_base + (uint32_t)nbuf * Cfg::POOL_BUF_BYTES + (uint32_t)(g * 9 * 128);
+          if (last_of_strip) {     // the next tile starts a strip: its column -1 is padding
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) pkd[q4] = make_uint4(0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u, 0xFF80FF80u);
+          }
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) sts128(nrow + ((uint32_t)((half * 4 + q4) ^ 7) << 4), pkd[q4]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(ld_bar0 + 8u * buf);
+      }
+      PROF_END(5 + ew)
+    } else {
     epi_dispatch(a.fast ? epi_mode(epi) : EPI_HAS_ALL, epi_loop);
     if (a.fast) {
       if (elect_one()) tma_store_wait<0>();
       __syncwarp();
+    }
     }
   }
 
@@ -534,6 +803,64 @@ static int make_tiled_map_4d(CUtensorMap* map, const void* base, int N, int H, i
   return make_tiled_map_nhwc(map, base, N, H, W, C, box_c, box_w, box_h, swizzle_bytes);
 }
 
+// packed stem + max-pool in one kernel (HaloCfg POOL): d->pool_out receives max_pool2d(relu(conv + shift), 3, 2, 1)
+static int launch_halo_pool(const vdqn_conv_desc* d, cudaStream_t stream) {
+  using Cfg = HaloCfg<16, false, true>;
+  DeviceInfo* dev = device_info();
+  if (dev == nullptr) return VDQN_ERR_CUDA;
+  if (d->H % Cfg::POOL_ROWS != 0 || d->W % Cfg::TW != 0 || (d->H & 1) || (d->W & 1) || !(d->flags & VDQN_EPI_RELU) ||
+      d->residual != nullptr || d->mask_src != nullptr || d->colsum != nullptr)
+    return set_error(VDQN_ERR_SHAPE, "halo_conv: fused pooling needs H %% 14 == 0, W %% 8 == 0 and a plain ReLU epilogue");
+  static bool attr_set = false;
+  auto kfn = halo_conv_kernel<16, false, true>;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return set_error(VDQN_ERR_CUDA, "cudaFuncSetAttribute(halo_conv pool): %s", cudaGetErrorString(e));
+    }
+    attr_set = true;
+  }
+  CUtensorMap tmX, tmW;
+  int rc = make_tiled_map_4d(&tmX, d->x, d->N, d->H, d->W, d->Cin, 16, Cfg::TW + d->S - 1, Cfg::TH + d->R - 1, 32);
+  if (rc != VDQN_OK) return rc;
+  rc = make_tiled_map_2d(&tmW, d->w, (uint64_t)d->R * d->S * d->Cin, d->Cout, 16, Cfg::W_ROWS, 32);
+  if (rc != VDQN_OK) return rc;
+  HaloArgs a{};
+  a.fast = 0;
+  a.x = static_cast<const __nv_bfloat16*>(d->x);
+  a.N = d->N; a.H = d->H; a.W = d->W; a.Cout = d->Cout;
+  a.R = d->R; a.S = d->S; a.pad_lo = d->pad_lo;
+  a.tiles_w = d->W / Cfg::TW;
+  a.tiles_h = d->H / Cfg::POOL_ROWS;                  // strips per image
+  a.num_tiles = d->N * a.tiles_w * a.tiles_h;
+  a.epi = make_epi_args(d);
+  a.alias_from = d->x_alias_from; a.alias_shift = d->x_alias_shift;
+  if (a.alias_from > 0 && (a.alias_shift <= 0 || a.alias_shift > a.alias_from))
+    return set_error(VDQN_ERR_ARG, "halo_conv: input aliasing needs 0 < shift <= first");
+  a.pool_out = static_cast<__nv_bfloat16*>(d->pool_out);
+  a.pool_idx = d->pool_idx;
+  a.idx_images = d->pool_idx_images;
+  const int sms = d->max_ctas > 0 && d->max_ctas < dev->num_sms ? d->max_ctas : dev->num_sms;
+  const int strips = d->N * a.tiles_h;
+  const int grid = strips < sms ? strips : sms;
+  CUtensorMap tmW2 = tmW;
+  a.split_tile = 0; a.split_cta = 0; a.shift2 = d->shift2;
+  if (d->split_n > 0) {
+    if (d->w2 == nullptr || d->split_n >= d->N || grid < 2) return set_error(VDQN_ERR_SHAPE, "halo_conv: bad dual-network launch");
+    rc = make_tiled_map_2d(&tmW2, d->w2, (uint64_t)d->R * d->S * d->Cin, d->Cout, 16, Cfg::W_ROWS, 32);
+    if (rc != VDQN_OK) return rc;
+    a.split_tile = d->split_n * a.tiles_w * a.tiles_h;
+    int g0 = (int)((long)grid * d->split_n / d->N);
+    if (g0 < 1) g0 = 1;
+    if (g0 > grid - 1) g0 = grid - 1;
+    a.split_cta = g0;
+  }
+  launch_kernel(kfn, grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream, tmX, tmW, tmW2, tmX, tmX, tmX, a);
+  VDQN_CHECK_LAUNCH("halo_conv (stem + pool) launch");
+  return VDQN_OK;
+}
+
 // Shapes this kernel takes: stride-1 "same" convolutions with Cout = 64 whose whole filter fits in
 // shared memory: 3x3 over 64 channels (layer1 fwd/dgrad) and the packed 4x4 x 16-channel stem.
 bool halo_conv_supported(const vdqn_conv_desc* d) {
@@ -546,6 +873,10 @@ bool halo_conv_supported(const vdqn_conv_desc* d) {
 }
 
 int halo_conv_launch(const vdqn_conv_desc* d, cudaStream_t stream) {
+  if (d->pool_out != nullptr) {
+    if (d->Cin != 16) return set_error(VDQN_ERR_SHAPE, "halo_conv: fused pooling is for the packed stem");
+    return launch_halo_pool(d, stream);
+  }
   if (d->Cin != 64) return launch_halo<16, false>(d, stream);
   // CTA pairs need an even number of tiles (in both image ranges of a dual-network launch)
   const int per_img = ((d->W + 7) / 8) * ((d->H + 15) / 16);

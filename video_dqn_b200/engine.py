@@ -231,7 +231,8 @@ class Workspace:
     """All activation / gradient buffers for one forward (and optionally its backward) at a
     fixed number of frames `n` (= B * num_frames)."""
 
-    def __init__(self, plan: NetPlan, n: int, device, train: bool, n_bwd: Optional[int] = None):
+    def __init__(self, plan: NetPlan, n: int, device, train: bool, n_bwd: Optional[int] = None,
+                 keep_stem: bool = False):
         """`n` frames go through the forward; the backward (if `train`) covers the first `n_bwd`
         (default all) -- the fused step runs the online net on [s ; s'] in one 2B forward and
         back-propagates through the s half only."""
@@ -242,7 +243,9 @@ class Workspace:
         e = lambda *s, dt=bf16: torch.empty(*s, device=device, dtype=dt)  # noqa: E731
         z = lambda *s, dt=bf16: torch.zeros(*s, device=device, dtype=dt)  # noqa: E731
         self.xp = e(nf, 112, 112, 16)
-        self.s = e(nf, 112, 112, 64)
+        # the stem's ReLU output only exists in HBM when asked for (train-mode BatchNorm of the `basic`
+        # architecture normalises it before pooling); otherwise the stem kernel pools in its epilogue
+        self.s = e(nf, 112, 112, 64) if keep_stem else None
         # arg-max slots of the max-pool: only the frames that are back-propagated through need them
         self.idx = e(self.n_bwd, 56, 56, 64, dt=torch.uint8) if train else None
         self.p = e(nf, 56, 56, 64)
@@ -260,7 +263,7 @@ class Workspace:
         self.z1 = (e(Bf, 512), e(Bf, 512))
         self.z2 = (e(Bf, 256), e(Bf, 256))
         self.q = e(Bf, nq, dt=f32)
-        self._fwd_names = ("xp", "s", "idx", "p", "h")
+        self._fwd_names = ("xp", "s", "idx", "p", "h")        # `s` may be None
         self._mlp_names = ("q",)
         self._F = F
         if train:
@@ -312,6 +315,9 @@ class Workspace:
 
 import os as _os
 
+# stem + max-pool fused into one kernel (0: the stem writes its full-resolution output and a pooling kernel
+# re-reads it -- the A/B switch for measurements)
+FUSE_POOL = _os.environ.get("VDQN_FUSE_POOL", "1") != "0"
 # column-tile width for the Cout >= 256 layers (0 = kernel default 256); tuning knob
 TILE_N_WIDE = int(_os.environ.get("VDQN_TILE_N_WIDE", "0"))
 # fused step: one multi-tensor launch for all split reductions of the backward pass (0: one per layer)
@@ -366,12 +372,20 @@ def forward_packed(plan: NetPlan, W: PreparedWeights, P: Dict[str, torch.Tensor]
     dual = dict(W2=W2, split=split) if W2 is not None else {}
     # x_alias = (first, shift): packed frames >= first are read from frame - shift (the target range of
     # the 3B pass re-reads the online network's s' frames)
-    _conv(W, plan.stem, ws.xp, ws.s, relu=True, x_alias=x_alias, **dual)
     nb = ws.n_bwd if ws.idx is not None else 0
-    if nb:
-        ops.maxpool_fwd(ws.s[:nb], ws.p[:nb], ws.idx)
-    if nb < ws.n:
-        ops.maxpool_fwd(ws.s[nb:], ws.p[nb:], None)
+    if ws.s is None and FUSE_POOL:
+        # stem conv + bn1 + ReLU + max-pool in ONE kernel: only the pooled tensor (and, for the frames that are
+        # back-propagated through, the arg-max slots) reaches HBM
+        _conv(W, plan.stem, ws.xp, None, relu=True, x_alias=x_alias, pool_out=ws.p, pool_idx=ws.idx,
+              pool_idx_images=nb, **dual)
+    else:
+        if ws.s is None:
+            ws.s = torch.empty(ws.n, 112, 112, 64, device=ws.xp.device, dtype=bf16)
+        _conv(W, plan.stem, ws.xp, ws.s, relu=True, x_alias=x_alias, **dual)
+        if nb:
+            ops.maxpool_fwd(ws.s[:nb], ws.p[:nb], ws.idx)
+        if nb < ws.n:
+            ops.maxpool_fwd(ws.s[nb:], ws.p[nb:], None)
     x = ws.p
     for i, b in enumerate(plan.blocks):
         _conv(W, b.conv1, x, ws.a1[i], relu=True, **dual)

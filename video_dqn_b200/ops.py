@@ -68,7 +68,8 @@ def conv_out_hw(H, W, R, S, stride, pad_lo, pad_hi, dil=1):
 def conv_gemm(x, w, stride=1, pad_lo=0, pad_hi=None, *, shift=None, residual=None, mask_src=None,
               relu=False, out_f32=False, colsum=None, out=None, out2=None, out_scatter=1,
               tile_n=0, max_ctas=0, dil=1, algo=0, pad_hi_w=-1, scatter_off=(0, 0), scatter_inputs=False,
-              w2=None, shift2=None, split_n=0, x_alias=None):
+              w2=None, shift2=None, split_n=0, x_alias=None, pool_out=None, pool_idx=None, pool_idx_images=0,
+              debug_flags=0):
     """x [N,H,W,Cin] bf16, w [Cout,R,S,Cin] bf16 -> out [N,Ho,Wo,Cout] (or zero-dilated
     [N,2Ho,2Wo,Cout] when out_scatter == 2; `out` must then be pre-zeroed).
     x_alias = (first, shift): images n >= first are read from image n - shift (packed stem only)."""
@@ -81,6 +82,14 @@ def conv_gemm(x, w, stride=1, pad_lo=0, pad_hi=None, *, shift=None, residual=Non
     Ho = conv_out_hw(H, W_, R, S, stride, pad_lo, pad_hi, dil)[0]
     Wo = conv_out_hw(H, W_, R, S, stride, pad_lo, pad_hi if pad_hi_w < 0 else pad_hi_w, dil)[1]
     odt = torch.float32 if out_f32 else bf16
+    if pool_out is not None:
+        # packed stem + max_pool2d(3, 2, 1) in one kernel: only the pooled tensor (and arg-max slots) is stored
+        _cuda(pool_out, bf16, "pool_out")
+        _req(pool_out.numel() == N * (Ho // 2) * (Wo // 2) * Cout, "bad shape")
+        if pool_idx is not None:
+            _cuda(pool_idx, torch.uint8, "pool_idx")
+            _req(pool_idx.numel() >= pool_idx_images * (Ho // 2) * (Wo // 2) * Cout, "bad shape")
+        out = pool_out                      # placeholder: `out` is not written
     if out is None:
         if out_scatter == 2:
             out = torch.zeros(N, 2 * Ho, 2 * Wo, Cout, device=x.device, dtype=odt)
@@ -108,7 +117,7 @@ def conv_gemm(x, w, stride=1, pad_lo=0, pad_hi=None, *, shift=None, residual=Non
     d.ldc = d.ldr = d.ldm = d.out2_ld = Cout
     d.out_scatter = out_scatter
     d.flags = (L.EPI_RELU if relu else 0) | (L.EPI_OUT_F32 if out_f32 else 0) | \
-        (L.EPI_SCATTER_INPUTS if scatter_inputs else 0)
+        (L.EPI_SCATTER_INPUTS if scatter_inputs else 0) | int(debug_flags)
     d.pad_hi_w, d.scatter_off_h, d.scatter_off_w = pad_hi_w, scatter_off[0], scatter_off[1]
     if split_n:
         _cuda(w2, bf16, "w2"); _req(w2.shape == w.shape and shift2 is not None, "bad shape")
@@ -116,6 +125,8 @@ def conv_gemm(x, w, stride=1, pad_lo=0, pad_hi=None, *, shift=None, residual=Non
     d.tile_n, d.max_ctas, d.algo = tile_n, max_ctas, algo
     if x_alias is not None:
         d.x_alias_from, d.x_alias_shift = x_alias
+    if pool_out is not None:
+        d.pool_out, d.pool_idx, d.pool_idx_images = pool_out.data_ptr(), L.ptr(pool_idx), int(pool_idx_images)
     with _Prof("igemm", (N, H, W_, Cin, Cout, R, stride)):
         L.check(lib.vdqn_conv_gemm(C.byref(d), L.stream_ptr()), "conv_gemm")
     return out
