@@ -351,7 +351,27 @@ def _basic_block(dev, B):
     return out
 
 
-def dp_check(dev, rank, world, make_sync):
+def make_dp_learner(dev, world, B, use_graph, kind):
+    """One learner of the data-parallel job: `kind` = "nvl" (the gradient arena in NVLink symmetric memory, the
+    exchange is this library's kernel) or "nccl" (bucketed NCCL all-reduce from inside the backward pass)."""
+    import torch
+    from video_dqn_b200.ddp import GradSync, NvlGradSync
+    from video_dqn_b200.learner import QLearner, StepConfig
+    from video_dqn_b200.qnet import HabitatDQNMultiAction
+    torch.manual_seed(4)                      # SEED of configs/experiments/real_data/config.yml:11
+    model = HabitatDQNMultiAction(3, 5, extra_capacity=True, panorama=False).to(dev)
+    target = HabitatDQNMultiAction(3, 5, extra_capacity=True, panorama=False).to(dev)
+    target.load_state_dict(model.state_dict())
+    target.eval()
+    alloc = NvlGradSync.allocator() if (world > 1 and kind == "nvl") else None
+    learner = QLearner(model, target, StepConfig(), batch_size=B, frames_uint8=True, use_graph=use_graph,
+                       world_size=world, grad_alloc=alloc)
+    if world > 1:
+        learner.grad_sync = NvlGradSync(learner, alloc) if alloc is not None else GradSync(learner)
+    return model, target, learner
+
+
+def dp_check(dev, rank, world, kind):
     """On-hardware data-parallel correctness (the reference has no DP, train_q_network.py:275):
     every rank takes ONE small step on its own 8 quadruplets with the gradient exchange of the timed run,
     then (a) the parameters of all ranks must be bit-identical and (b) the exchanged (averaged) gradient is
@@ -359,19 +379,8 @@ def dp_check(dev, rank, world, make_sync):
     mean over B*5 entries, so the global-batch gradient is the average of the per-rank ones)."""
     import torch
     import torch.distributed as dist
-    from video_dqn_b200.learner import QLearner, StepConfig
-    from video_dqn_b200.qnet import HabitatDQNMultiAction
     Bs = 8
-
-    def nets():
-        torch.manual_seed(4)
-        m = HabitatDQNMultiAction(3, 5, extra_capacity=True, panorama=False).to(dev)
-        t = HabitatDQNMultiAction(3, 5, extra_capacity=True, panorama=False).to(dev)
-        t.load_state_dict(m.state_dict())
-        return m, t
-    m, t = nets()
-    lr = QLearner(m, t, StepConfig(), batch_size=Bs, frames_uint8=True, use_graph=False, world_size=world)
-    lr.grad_sync = make_sync(lr)
+    m, t, lr = make_dp_learner(dev, world, Bs, False, kind)
     lr.step([x.to(dev) for x in synthetic_quads(Bs, seed=500 + rank, pinned=False)])
     torch.cuda.synchronize()
     p = lr.opt.param_arena
@@ -382,13 +391,14 @@ def dp_check(dev, rank, world, make_sync):
     g_avg = (lr.opt.grad_arena / world).clone()
     loss_mean = lr.loss.clone()
     dist.all_reduce(loss_mean, op=dist.ReduceOp.SUM)
-    out = {"batch_per_rank": Bs, "max_param_diff_across_ranks": float(diff.item())}
+    out = {"batch_per_rank": Bs, "max_param_diff_across_ranks": float(diff.item()),
+           "exchange": type(lr.grad_sync).__name__, "multicast": getattr(lr.grad_sync, "multicast", None),
+           "exchange_us": getattr(lr.grad_sync, "tuning", None)}
     if hasattr(lr.grad_sync, "close"):
         lr.grad_sync.close()
     del lr, m, t
     if rank == 0:
-        m, t = nets()
-        big = QLearner(m, t, StepConfig(), batch_size=world * Bs, frames_uint8=True, use_graph=False)
+        m, t, big = make_dp_learner(dev, 1, world * Bs, False, kind)
         parts = [synthetic_quads(Bs, seed=500 + r, pinned=False) for r in range(world)]
         big.step([torch.cat([pt[i] for pt in parts]).to(dev) for i in range(7)])
         torch.cuda.synchronize()
@@ -450,17 +460,19 @@ def main():
     _lib.check(lib.vdqn_init(local), "init")
     B = a.batch
 
-    torch.manual_seed(4)                      # SEED of configs/experiments/real_data/config.yml:11
-    model = HabitatDQNMultiAction(3, 5, extra_capacity=True, panorama=False).to(dev)
-    target = HabitatDQNMultiAction(3, 5, extra_capacity=True, panorama=False).to(dev)
-    target.load_state_dict(model.state_dict())
-    target.eval()
-    learner = QLearner(model, target, StepConfig(), batch_size=B, frames_uint8=True,
-                       use_graph=not a.no_graph, world_size=world)
+    # gradient exchange: VDQN_DDP=nvl (default: this library's NVLink kernel) | nccl
+    dp_kind = os.environ.get("VDQN_DDP", "nvl") if world > 1 else None
     dpc = None
     if world > 1:
-        dpc = dp_check(dev, rank, world, GradSync)
-        learner.grad_sync = GradSync(learner)
+        try:
+            dpc = dp_check(dev, rank, world, dp_kind)
+        except Exception as exc:                      # symmetric memory unavailable on this fabric: NCCL buckets
+            if dp_kind != "nvl":
+                raise
+            print(f"bench: NVLink exchange unavailable ({exc!r}); falling back to NCCL", file=sys.stderr)
+            dp_kind = "nccl"
+            dpc = dp_check(dev, rank, world, dp_kind)
+    model, target, learner = make_dp_learner(dev, world, B, not a.no_graph, dp_kind)
     host = [synthetic_quads(B, seed=1 + rank + 97 * i) for i in range(3)]
     pool = [[t.to(dev) for t in b] for b in host]          # device-resident batches (> L2 together)
 
@@ -699,17 +711,21 @@ def main():
             "loss": loss_dev,
             "clocks": clocks, "gpu_launches": (per_step_launches or 0) * a.steps,
             "gpu_launches_per_step": per_step_launches,
-            "dp_check": dpc, "e2e": e2e, "roofline": roof, "roofline_kernels": roof_other, "cpu_baseline": cpu,
+            "dp_check": dpc, "grad_exchange": dp_kind, "e2e": e2e, "roofline": roof, "roofline_kernels": roof_other, "cpu_baseline": cpu,
             "breakdown_eager_ms": breakdown if rank == 0 else None,
             "inference": inference, "inverse_model": inverse, "basic_architecture": basic,
         }
         print(json.dumps(out), file=out_stream, flush=True)
     if world > 1:
-        # NCCL collectives captured in CUDA graphs keep the communicator busy at teardown
-        # (destroy_process_group blocks); everything is reported, so leave without the destructor.
         barrier()
         sys.stdout.flush(); sys.stderr.flush()
-        os._exit(0)
+        if dp_kind == "nvl":
+            del learner
+            dist.destroy_process_group()          # nothing of NCCL's is captured in the step graph: a clean teardown
+        else:
+            # NCCL collectives captured in CUDA graphs keep the communicator busy at teardown
+            # (destroy_process_group blocks); everything is reported, so leave without the destructor.
+            os._exit(0)
 
 
 if __name__ == "__main__":

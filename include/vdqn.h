@@ -270,6 +270,32 @@ int vdqn_split_bf16(const float* x, void* hi, void* lo, int32_t rows, int32_t co
                     int32_t perm_c, int32_t perm_p, float* colsum, void* stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Data-parallel gradient exchange as one kernel over NVLink / NVSwitch peer memory (the reference is
+ * single-GPU, train_q_network.py:275).  The flat fp32 gradient arena of every rank lives in
+ * symmetric memory: peer_bufs[r] / peer_flags[r] are THIS process' device pointers to rank r's arena and to
+ * rank r's flag block (uint32[8 * world], zero-initialised once); multicast_ptr is the NVSwitch multicast
+ * address of the arena or NULL (then plain peer loads / stores are used).  After the call, enqueued on every
+ * rank's stream, every arena holds the element-wise SUM over ranks, bit-identical on all ranks (each element is
+ * summed by one rank and copied).  epoch / counter: two zero-initialised uint32 in LOCAL device memory that the
+ * kernel maintains (CUDA-graph replay safe).  n (elements) must be a multiple of 4 * world. */
+typedef struct vdqn_nvl_desc {
+  void* const* peer_bufs;
+  void* const* peer_flags;
+  void* multicast_ptr;
+  uint32_t* epoch;
+  uint32_t* counter;
+  int64_t n;                /* elements exchanged, starting at element `first` of the arena (multiple of 4) */
+  int32_t rank, world, max_ctas;
+  int64_t first;
+  /* Several exchanges may be in flight (an early one next to the backward pass, the rest after it): each uses
+   * its own channel 0..3 = its own flag slots [channel * 2 world, ...) of the flag block (uint32[8 * world])
+   * and its own epoch / counter pair.  threads: 128 / 256 / 512 per CTA (0 = 512): 128-thread CTAs fit on an
+   * SM beside a persistent conv CTA. */
+  int32_t channel, threads;
+} vdqn_nvl_desc;
+int vdqn_nvl_allreduce(const vdqn_nvl_desc* d, void* stream);
+
+/* ---------------------------------------------------------------------------------------
  * Fused TD epilogue: replaces the ~24 ATen launches of process_batch
  * (train_q_network.py:134-180): repeat/gather/argmax/gather/detach/mul/add/clamp/sub/pow/mean
  * and their backward.  q_* are fp32 [B][C][A]; act int64 [B]; rew/term/valid int64 [B][C].

@@ -70,6 +70,12 @@ class MlpGemmDesc(C.Structure):
                 ("out_bf16", c_void_p), ("ld_bf16", c_int), ("colsum", c_void_p), ("colsum_mod", c_int)]
 
 
+class NvlDesc(C.Structure):
+    _fields_ = [("peer_bufs", C.POINTER(c_void_p)), ("peer_flags", C.POINTER(c_void_p)), ("multicast_ptr", c_void_p),
+                ("epoch", c_void_p), ("counter", c_void_p), ("n", c_int64), ("rank", c_int), ("world", c_int),
+                ("max_ctas", c_int), ("first", c_int64), ("channel", c_int), ("threads", c_int)]
+
+
 EXPORTS = {
     "vdqn_last_error": (C.c_char_p, []),
     "vdqn_abi_version": (c_int, []),
@@ -98,6 +104,7 @@ EXPORTS = {
     "vdqn_mlp_gemm": (c_int, [C.POINTER(MlpGemmDesc), c_void_p]),
     "vdqn_mlp_gemm_grouped": (c_int, [C.POINTER(MlpGemmDesc), c_int, c_void_p]),
     "vdqn_split_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "vdqn_nvl_allreduce": (c_int, [C.POINTER(NvlDesc), c_void_p]),
     "vdqn_td_epilogue": (c_int, [C.POINTER(TdDesc), c_void_p]),
     "vdqn_q_max": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "vdqn_bn_stats": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p]),

@@ -17,7 +17,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libvdqn.so")
-SOURCES = ["common.cu", "conv_gemm.cu", "halo_conv.cu", "wgrad_gemm.cu", "halo_wgrad.cu", "halo_wgrad_stem.cu", "elementwise.cu", "td_bulk.cu", "mlp_gemm.cu", "batchnorm.cu"]
+SOURCES = ["common.cu", "conv_gemm.cu", "halo_conv.cu", "wgrad_gemm.cu", "halo_wgrad.cu", "halo_wgrad_stem.cu", "elementwise.cu", "td_bulk.cu", "mlp_gemm.cu", "nvl_allreduce.cu", "batchnorm.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "--use_fast_math=false"]

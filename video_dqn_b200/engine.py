@@ -517,7 +517,11 @@ def backward(plan: NetPlan, W: PreparedWeights, P: Dict[str, torch.Tensor], G: D
     if on_grads_ready is None:
         notify = lambda stage: None  # noqa: E731
     else:
+        wants = getattr(getattr(on_grads_ready, "__self__", None), "wants", None)
+
         def notify(stage):
+            if wants is not None and not wants(stage) and stage != "stem":
+                return                   # this exchange does not act on the stage: no reduction needed yet
             _flush_finalize(ws)          # the stage's gradients are complete only once its reductions ran
             on_grads_ready(stage)
     # ---- Q-head MLP + the head conv's dy (ws.dh)

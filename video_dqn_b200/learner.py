@@ -61,7 +61,8 @@ class QLearner:
     def __init__(self, model: HabitatDQNMultiAction, target_net: HabitatDQNMultiAction,
                  cfg: Optional[StepConfig] = None, batch_size: int = 16, *,
                  optimizer: Optional[FusedAdam] = None, frames_uint8: bool = False,
-                 use_graph: bool = True, grad_sync=None, world_size: int = 1, one_pass: Optional[bool] = None):
+                 use_graph: bool = True, grad_sync=None, world_size: int = 1, one_pass: Optional[bool] = None,
+                 grad_alloc=None):
         self.cfg = cfg or StepConfig()
         self.model, self.target_net = model, target_net
         self.B = batch_size
@@ -78,7 +79,7 @@ class QLearner:
         F = self.plan.num_frames
         names = model._grad_names
         # ---- parameters / gradients / Adam state / target copy in flat arenas
-        self.opt = optimizer or FusedAdam(model.parameters(), lr=self.cfg.LEARNING_RATE)
+        self.opt = optimizer or FusedAdam(model.parameters(), lr=self.cfg.LEARNING_RATE, grad_alloc=grad_alloc)
         mp = dict(model.named_parameters())
         self.opt.adopt([mp[n] for n in names])
         self.G: Dict[str, torch.Tensor] = dict(zip(names, self.opt.grad_views()))

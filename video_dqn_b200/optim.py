@@ -35,13 +35,19 @@ def bump_arena_epoch(t: torch.Tensor):
 class FlatArena:
     """Contiguous fp32 buffer with one 16-byte aligned slot per tensor."""
 
-    def __init__(self, shapes: List[torch.Size], device):
+    def __init__(self, shapes: List[torch.Size], device, alloc=None):
+        """`alloc(total, device) -> zeroed fp32 tensor of at least `total` elements`: where the buffer comes from
+        (the data-parallel learner puts the gradient arena into NVLink symmetric memory)."""
         self.offsets, total = [], 0
         for s in shapes:
             self.offsets.append(total)
             total += (s.numel() + 3) // 4 * 4
         self.shapes = shapes
-        self.flat = torch.zeros(total, device=device, dtype=torch.float32)
+        if alloc is None:
+            self.flat = torch.zeros(total, device=device, dtype=torch.float32)
+        else:
+            self.storage = alloc(total, device)          # may be longer (padded for the exchange kernel)
+            self.flat = self.storage[:total]
 
     def view(self, i: int) -> torch.Tensor:
         s = self.shapes[i]
@@ -52,8 +58,9 @@ class FlatArena:
 
 
 class FusedAdam(torch.optim.Optimizer):
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, grad_alloc=None):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
+        self._grad_alloc = grad_alloc
         self._members: Optional[List[torch.nn.Parameter]] = None
         self._p = self._g = self._m = self._v = None
         self._step = 0
@@ -62,7 +69,7 @@ class FusedAdam(torch.optim.Optimizer):
     def _build(self, members: List[torch.nn.Parameter]):
         dev = members[0].device
         shapes = [p.shape for p in members]
-        self._p, self._g = FlatArena(shapes, dev), FlatArena(shapes, dev)
+        self._p, self._g = FlatArena(shapes, dev), FlatArena(shapes, dev, alloc=self._grad_alloc)
         self._m, self._v = FlatArena(shapes, dev), FlatArena(shapes, dev)
         for i, p in enumerate(members):
             if p.dtype != torch.float32 or not p.is_cuda:
