@@ -101,6 +101,18 @@ typedef struct vdqn_conv_desc {
   void* pool_out;
   uint8_t* pool_idx;
   int32_t pool_idx_images;
+  /* Second operand accumulated into the same output tile (im2col kernel, 64-channel blocks): after the
+   * R*S*Cin reduction over x, Cin2 more channels are reduced over x2 (bf16 [N][H2][W2][Cin2], read through a
+   * 1x1 window at stride2: pixel (p*stride2, q*stride2) feeds output pixel (p, q)); each row of `w` (and w2)
+   * is [R*S*Cin | Cin2] long.  Forward: the 1x1/2 downsample branch of a residual block inside its conv2
+   * (torchvision BasicBlock.forward: out = bn2(conv2(..)) + downsample(x)); backward: the downsample's data
+   * gradient inside conv1's.  NULL: off. */
+  const void* x2;
+  int32_t Cin2, H2, W2, stride2;
+  /* out_scatter == 3: stride-2 data gradient as ONE dense GEMM.  The Cout = 4 Cq columns are ordered
+   * (a, b, c): row (n, p, q), column (a, b, c) is dX[n][2p + a][2q + b][c] of `out` [N][2Ho][2Wo][Cq] (the
+   * filter holds the taps every output-parity class uses, zeros elsewhere); residual / mask_src / colsum are
+   * indexed like the output (VDQN_EPI_SCATTER_INPUTS), colsum has Cq entries.  Needs tile_n = 128. */
 } vdqn_conv_desc;
 int vdqn_conv_gemm(const vdqn_conv_desc* d, void* stream);
 
@@ -176,6 +188,15 @@ typedef struct vdqn_wprep_desc {
    * classes (h%2, w%2) back to back -- class (a,b) is [Cin][na][nb][Cout] with na = 1 + a,
    * nb = 1 + b taps (rows r = 1 | {2, 0}, same for columns), class offsets 0, 1, 3, 5 taps x Cin*Cout. */
   int32_t dgrad_parity;
+  /* Concatenated layouts (0 = the plain ones above).  ldw_fwd / fwd_col0: row pitch and first column of
+   * this tensor inside a wider forward matrix (the 1x1 downsample appended to conv2's rows); gamma_b ..
+   * var_b: a second BatchNorm whose shift beta_b - mean_b * gamma_b / sqrt(var_b + eps) is ADDED to this
+   * tensor's (conv2 carries the downsample's).  ldw_dgrad / dgrad_col0: the same for the data-gradient
+   * matrix.  dgrad_parity == 2: the data-gradient filter of a 3x3 stride-2 conv as one [4 Cin][2][2][Cout]
+   * matrix (row (a*2 + b)*Cin + ci, column (u*2 + v)*Cout + co; taps a class does not use stay zero: the
+   * buffer must be zero-initialised once). */
+  int32_t ldw_fwd, fwd_col0, ldw_dgrad, dgrad_col0;
+  const float* gamma_b; const float* beta_b; const float* mean_b; const float* var_b;
 } vdqn_wprep_desc;
 int vdqn_weight_prep(const vdqn_wprep_desc* d, void* stream);
 /* Same for `n` tensors in one launch: `descs_dev` / `offsets_dev` are DEVICE arrays (offsets[t] = sum of

@@ -241,7 +241,7 @@ def test_every_layer_of_one_step_teacher_forced():
         if i % 2 == 0:                       # dy_a1 was the path's own: its block-input gradient is checkable
             if i > 0:
                 _check_bf16(f"bwd/dgrad_{b.conv1.name}", block_grad_out(i - 1), _bf(dx_in * (x_in > 0)), ulps=2, mag=mag,
-                            frac=0.10 if ds is not None else 0.005)    # the downsample term is rounded on its own
+                            frac=0.005)
             else:
                 _check_bf16("bwd/dgrad_l1.0.c1", _nchw(bw.dy_p), _bf(dx_in), ulps=2, mag=mag)
 

@@ -24,7 +24,8 @@ class ConvDesc(C.Structure):
                                      "out_scatter", "flags", "tile_n", "max_ctas", "algo", "pad_hi_w",
                                      "scatter_off_h", "scatter_off_w")] + \
                [("w2", c_void_p), ("shift2", c_void_p), ("split_n", c_int), ("x_alias_from", c_int),
-                ("x_alias_shift", c_int), ("pool_out", c_void_p), ("pool_idx", c_void_p), ("pool_idx_images", c_int)]
+                ("x_alias_shift", c_int), ("pool_out", c_void_p), ("pool_idx", c_void_p), ("pool_idx_images", c_int),
+                ("x2", c_void_p), ("Cin2", c_int), ("H2", c_int), ("W2", c_int), ("stride2", c_int)]
 
 
 class WgradDesc(C.Structure):
@@ -46,7 +47,9 @@ class WprepDesc(C.Structure):
     _fields_ = [(n, c_void_p) for n in ("w", "gamma", "beta", "mean", "var", "bias", "w_fwd",
                                         "w_dgrad", "shift")] + \
                [(n, c_int) for n in ("Cout", "Cin", "R", "S", "K", "kmap")] + [("eps", c_float),
-                                                                                ("dgrad_parity", c_int)]
+                                                                                ("dgrad_parity", c_int)] + \
+               [(n, c_int) for n in ("ldw_fwd", "fwd_col0", "ldw_dgrad", "dgrad_col0")] + \
+               [(n, c_void_p) for n in ("gamma_b", "beta_b", "mean_b", "var_b")]
 
 
 class TdDesc(C.Structure):

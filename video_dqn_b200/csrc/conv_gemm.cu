@@ -40,6 +40,15 @@ struct IgemmArgs {
   int split_m_tile, split_cta;
   const float* shift2;
   int stages;         // pipeline depth of this launch (IgemmCfg::stages_for)
+  // Second K segment: after the R*S*Cin/CK k-blocks of the main operand, seg2_kb more whose A tiles come
+  // from ANOTHER tensor (tmA2: a 1x1 window at stride2 over the same output grid) and whose B columns simply
+  // continue in the weight matrix.  Forward: the 1x1/2 downsample of a residual block accumulated into its
+  // conv2 (archs/HabitatDQNMultiAction.py -> torchvision BasicBlock: out = bn2(conv2(..)) + downsample(x));
+  // backward: the downsample's data gradient accumulated into conv1's.
+  int seg2_kb, stride2;
+  // out_scatter == 3: the GEMM's Cout = 4 Cq columns are the 2x2 output-parity classes (a, b, c) of a stride-2
+  // data gradient: row (n, p, q), column (a, b, c) is pixel (2p + a, 2q + b), channel c of dX [N][2Ho][2Wo][Cq]
+  int Cq;
 };
 
 // PAIR: the CTA is one half of a cta_group::2 pair -- the pair computes a 256 x BN tile, this CTA
@@ -92,7 +101,7 @@ template <int BN, int CK, bool PAIR>
 __global__ void __launch_bounds__(320, 1)
 igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmB2, const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
-             const __grid_constant__ CUtensorMap tmMask, const IgemmArgs a) {
+             const __grid_constant__ CUtensorMap tmMask, const __grid_constant__ CUtensorMap tmA2, const IgemmArgs a) {
   using Cfg = IgemmCfg<BN, CK, PAIR>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -159,6 +168,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const int cblks = a.Cin / CK;
   const int num_sub = a.R * a.S * cblks;
   const int num_kb = num_sub / Cfg::KSUB;
+  const int total_kb = num_kb + a.seg2_kb;          // seg2_kb > 0 only on the 64-channel-block path (KSUB == 1)
   const int HoWo = a.Ho * a.Wo;
 
   if (warp == 0) {
@@ -209,6 +219,30 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         __syncwarp();
         if (++stage == nstages) { stage = 0; phase ^= 1; }
       }
+      if constexpr (CK == 64) {
+        // second segment: 1x1 window over the other tensor, B columns continue at jk
+        const int cw2 = q0 * a.stride2, ch2 = p0 * a.stride2;
+        for (int kb = 0; kb < a.seg2_kb; ++kb) {
+          PROF_WAIT_A(mbar_wait(empty_bar(stage), phase ^ 1))
+          const bool leader = elect_one();
+          if (leader && rank == 0) mbar_expect_tx(full_bar(stage), MT * Cfg::STAGE_BYTES);
+          const uint32_t fbar = PAIR ? mapa_u32(full_bar(stage), 0) : full_bar(stage);
+          const uint32_t sA = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint32_t sB = sA + Cfg::KSUB * Cfg::A_SUB_BYTES;
+          if (leader) {
+            if (PAIR) {
+              tma_load_im2col_4d_pair(sA, &tmA2, fbar, kb * CK, cw2, ch2, img, 0, 0);
+              tma_load_2d_pair(sB, tmBp, fbar, jk, n_t * BN + rank * Cfg::B_ROWS);
+            } else {
+              tma_load_im2col_4d(sA, &tmA2, fbar, kb * CK, cw2, ch2, img, 0, 0);
+              tma_load_2d(sB, tmBp, fbar, jk, n_t * BN);
+            }
+          }
+          jk += CK;
+          __syncwarp();
+          if (++stage == nstages) { stage = 0; phase ^= 1; }
+        }
+      }
     }
     PROF_END(0)
   } else if (warp == 1) {
@@ -226,7 +260,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       PROF_WAIT_A(mbar_wait(tempty_bar(acc), acc_phase ^ 1))
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * BN;
-      for (int kb = 0; kb < num_kb; ++kb) {
+      for (int kb = 0; kb < total_kb; ++kb) {
         PROF_WAIT_B(mbar_wait(full_bar(stage), phase))
         tc_fence_after();
         if (elect_one()) {
@@ -246,10 +280,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           }
           if (PAIR) {
             umma_commit_pair(empty_bar(stage));
-            if (kb == num_kb - 1) umma_commit_pair(tfull_bar(acc));
+            if (kb == total_kb - 1) umma_commit_pair(tfull_bar(acc));
           } else {
             umma_commit(empty_bar(stage));
-            if (kb == num_kb - 1) umma_commit(tfull_bar(acc));
+            if (kb == total_kb - 1) umma_commit(tfull_bar(acc));
           }
         }
         __syncwarp();
@@ -305,7 +339,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               csum[i] += warp_transpose_reduce(v, lane);
             }
           }
-          atomicAdd(a.epi.colsum + cs_nt * BN + (half + 2 * i) * 32 + lane, csum[i]);
+          const int cidx = cs_nt * BN + (half + 2 * i) * 32 + lane;
+          atomicAdd(a.epi.colsum + (a.out_scatter == 3 ? cidx % a.Cq : cidx), csum[i]);
           csum[i] = 0.f;
         }
       }
@@ -318,13 +353,22 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     // scatter launches (zero-dilated destination: parity-class data gradients): the same staged
     // tiles, but rows live at per-pixel addresses a tensor map cannot describe, so the LSU moves
     // them -- four lanes per 64-byte row (whole sectors), cp.async for the inputs
-    const bool gather = a.out_scatter == 2;
-    auto scatter_pix = [&](int mm) -> long {
+    const bool gather = a.out_scatter >= 2;
+    const bool blocks2 = a.out_scatter == 3;
+    // out_scatter 2: pixel (2p + off_h, 2q + off_w) of the zero-dilated destination, row pitch ld.
+    // out_scatter 3: the column tile starting at col0 lies in image row 2p + col0 / (2 Cq), starting at pixel 2q:
+    //   element offset = pixel * Cq + col % (2 Cq)  (the two pixels 2q, 2q+1 are adjacent in memory)
+    auto scatter_pix = [&](int mm, int nn_t) -> long {
       if (mm >= a.M_total) return -1;
       const int img = mm / HoWo;
       const int rem = mm - img * HoWo;
       const int p = rem / a.Wo, q = rem - p * a.Wo;
+      if (blocks2) return ((long)img * (2 * a.Ho) + 2 * p + (nn_t * BN) / (2 * a.Cq)) * (2 * a.Wo) + 2 * q;
       return ((long)img * (2 * a.Ho) + 2 * p + a.off_h) * (2 * a.Wo) + 2 * q + a.off_w;
+    };
+    // element offset of column `col` of a row whose scatter_pix is `pix` in a tensor of row pitch `ld`
+    auto scatter_off = [&](long pix, int col, int ld) -> long {
+      return blocks2 ? pix * a.Cq + (col % (2 * a.Cq)) : pix * ld + col;
     };
     auto tile_mn = [&](int tt, int& nn_t, int& mm_t) {
       nn_t = tt % a.num_n_tiles;
@@ -335,7 +379,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       int nn_t, mm_t;
       tile_mn(tt, nn_t, mm_t);
       if (gather) {
-        const long pix = scatter_pix(mm_t * Cfg::BM + row);
+        const long pix = scatter_pix(mm_t * Cfg::BM + row, nn_t);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int r = 8 * i + (lane >> 2);
@@ -346,8 +390,8 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
           for (int ci = 0; ci < NCH; ++ci) {
             const int col = nn_t * BN + (half + 2 * ci) * 32 + (lane & 3) * 8;
-            if (has_res) cp_async_16(stg_in + ci * 2048 + dst, epi.residual + prc * epi.ldr + col, nb);
-            if (has_mask) cp_async_16(stg_mask0 + ci * 2048 + dst, epi.mask_src + prc * epi.ldm + col, nb);
+            if (has_res) cp_async_16(stg_in + ci * 2048 + dst, epi.residual + scatter_off(prc, col, epi.ldr), nb);
+            if (has_mask) cp_async_16(stg_mask0 + ci * 2048 + dst, epi.mask_src + scatter_off(prc, col, epi.ldm), nb);
           }
         }
         cp_async_commit();
@@ -409,7 +453,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         }
         if (gather) {
           __syncwarp();                       // the staged tiles are complete
-          const long pix = scatter_pix(m);
+          const long pix = scatter_pix(m, n_t);
           __nv_bfloat16* obase = static_cast<__nv_bfloat16*>(epi.out);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -420,7 +464,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             for (int ci = 0; ci < NCH; ++ci) {
               const uint4 v4 = lds128(stg + ci * 2048 + src);
               if (pr >= 0)
-                *reinterpret_cast<uint4*>(obase + pr * epi.ldc + n_t * BN + (half + 2 * ci) * 32 + (lane & 3) * 8) = v4;
+                *reinterpret_cast<uint4*>(obase + scatter_off(pr, n_t * BN + (half + 2 * ci) * 32 + (lane & 3) * 8, epi.ldc)) = v4;
             }
           }
           __syncwarp();
@@ -492,6 +536,7 @@ teardown:
 template <int BN, int CK, bool PAIR = false>
 static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmB2,
                         const CUtensorMap* epi_maps, IgemmArgs& a, int num_sms, cudaStream_t stream) {
+  const CUtensorMap& tmA2 = epi_maps[3];
   using Cfg = IgemmCfg<BN, CK, PAIR>;
   static bool attr_set = false;
   auto kfn = igemm_kernel<BN, CK, PAIR>;
@@ -521,9 +566,9 @@ static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
   }
   if (PAIR)
     launch_kernel_cluster(kfn, grid * 2, Cfg::THREADS, Cfg::SMEM_BYTES, stream, 2, tmA, tmB, tmB2, epi_maps[0], epi_maps[1],
-                          epi_maps[2], a);
+                          epi_maps[2], tmA2, a);
   else
-    launch_kernel(kfn, grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream, tmA, tmB, tmB2, epi_maps[0], epi_maps[1], epi_maps[2], a);
+    launch_kernel(kfn, grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream, tmA, tmB, tmB2, epi_maps[0], epi_maps[1], epi_maps[2], tmA2, a);
   VDQN_CHECK_LAUNCH("igemm launch");
   return VDQN_OK;
 }
@@ -558,7 +603,7 @@ extern "C" int vdqn_conv_gemm(const vdqn_conv_desc* d, void* stream_v) {
   if (dev == nullptr) return VDQN_ERR_CUDA;
   if (d->algo == 2 && !halo_conv_supported(d))
     return set_error(VDQN_ERR_SHAPE, "conv_gemm: halo algorithm requested for an unsupported shape");
-  if (d->algo != 1 && d->tile_n == 0 && halo_conv_supported(d)) return halo_conv_launch(d, stream);
+  if (d->algo != 1 && d->tile_n == 0 && d->x2 == nullptr && halo_conv_supported(d)) return halo_conv_launch(d, stream);
   if (d->x_alias_from > 0)
     return set_error(VDQN_ERR_ARG, "conv_gemm: input aliasing needs the packed-stem halo kernel");
 
@@ -577,8 +622,17 @@ extern "C" int vdqn_conv_gemm(const vdqn_conv_desc* d, void* stream_v) {
   if (d->algo == 3 && !pair)
     return set_error(VDQN_ERR_SHAPE, "conv_gemm: CTA-pair kernel requested for an unsupported shape");
   const int b_rows = pair ? BN / 2 : BN;
-  rc = make_tiled_map_2d(&tmB, d->w, (uint64_t)d->R * d->S * d->Cin, d->Cout, CK, b_rows,
-                         CK == 64 ? 128 : 32);
+  // second K segment (x2: a 1x1 / stride2 window over another tensor, same output grid): the weight rows are
+  // [R*S*Cin | Cin2] long
+  const bool seg2 = d->x2 != nullptr;
+  if (seg2) {
+    if (CK != 64 || d->Cin2 % 64 != 0 || d->stride2 < 1 || (reinterpret_cast<uintptr_t>(d->x2) & 15))
+      return set_error(VDQN_ERR_SHAPE, "conv_gemm: the second operand needs 64-channel blocks");
+    if ((d->H2 - 1) / d->stride2 + 1 != Ho || (d->W2 - 1) / d->stride2 + 1 != Wo)
+      return set_error(VDQN_ERR_SHAPE, "conv_gemm: the second operand does not cover the same output grid");
+  }
+  const uint64_t k_total = (uint64_t)d->R * d->S * d->Cin + (seg2 ? d->Cin2 : 0);
+  rc = make_tiled_map_2d(&tmB, d->w, k_total, d->Cout, CK, b_rows, CK == 64 ? 128 : 32);
   if (rc != VDQN_OK) return rc;
 
   IgemmArgs a{};
@@ -589,15 +643,26 @@ extern "C" int vdqn_conv_gemm(const vdqn_conv_desc* d, void* stream_v) {
   a.num_m_tiles = (a.M_total + 127) / 128;
   a.num_n_tiles = d->Cout / BN;
   a.epi = make_epi_args(d);
-  a.out_scatter = d->out_scatter == 2 ? 2 : 1;
+  a.out_scatter = (d->out_scatter == 2 || d->out_scatter == 3) ? d->out_scatter : 1;
   a.off_h = d->scatter_off_h; a.off_w = d->scatter_off_w;
-  a.scatter_inputs = (d->out_scatter == 2 && (d->flags & VDQN_EPI_SCATTER_INPUTS)) ? 1 : 0;
+  a.scatter_inputs = (d->out_scatter >= 2 && (d->flags & VDQN_EPI_SCATTER_INPUTS)) ? 1 : 0;
+  a.seg2_kb = seg2 ? d->Cin2 / 64 : 0;
+  a.stride2 = seg2 ? d->stride2 : 1;
+  a.Cq = d->Cout / 4;
+  if (d->out_scatter == 3 && (BN > 2 * a.Cq || (2 * a.Cq) % BN != 0 || d->Cout % 4 != 0))
+    return set_error(VDQN_ERR_SHAPE, "conv_gemm: 2x2-block scatter needs column tiles inside one image row (tile %d, Cout %d)", BN, d->Cout);
 
   // staged epilogue: 2-D maps over the [M][ld] output / residual / mask matrices, boxes of
   // 32 channels x 32 pixels (64-byte rows)
-  CUtensorMap epi_maps[3] = {tmB, tmB, tmB};
+  CUtensorMap epi_maps[4] = {tmB, tmB, tmB, tmA};
   a.fast = (BN <= 128 && fast_epilogue_ok(d)) ? 1 : 0;
-  if (a.fast && d->out_scatter != 2) {     // scatter launches move the staged tiles with the LSU
+  if (d->out_scatter == 3 && !a.fast)
+    return set_error(VDQN_ERR_SHAPE, "conv_gemm: 2x2-block scatter needs the staged epilogue (bf16 output, tile <= 128)");
+  if (seg2) {
+    rc = make_im2col_map(&epi_maps[3], d->x2, d->N, d->H2, d->W2, d->Cin2, 64, 128, d->stride2, 0, 0, 0, 0, 128);
+    if (rc != VDQN_OK) return rc;
+  }
+  if (a.fast && d->out_scatter < 2) {      // scatter launches move the staged tiles with the LSU
     rc = make_tiled_map_2d(&epi_maps[0], d->out, d->Cout, a.M_total, 32, 32, 64, d->ldc);
     if (rc == VDQN_OK && d->residual)
       rc = make_tiled_map_2d(&epi_maps[1], d->residual, d->Cout, a.M_total, 32, 32, 64, d->ldr);
@@ -611,7 +676,7 @@ extern "C" int vdqn_conv_gemm(const vdqn_conv_desc* d, void* stream_v) {
     const long split_m = (long)d->split_n * Ho * Wo;
     if (d->w2 == nullptr || d->split_n >= d->N || split_m % 128 != 0)
       return set_error(VDQN_ERR_SHAPE, "conv_gemm: dual-network launch needs w2 and split_n*Ho*Wo %% 128 == 0");
-    rc = make_tiled_map_2d(&tmB2, d->w2, (uint64_t)d->R * d->S * d->Cin, d->Cout, CK, b_rows, CK == 64 ? 128 : 32);
+    rc = make_tiled_map_2d(&tmB2, d->w2, k_total, d->Cout, CK, b_rows, CK == 64 ? 128 : 32);
     if (rc != VDQN_OK) return rc;
     a.split_m_tile = (int)(split_m / 128);
   }

@@ -118,7 +118,7 @@ __device__ __forceinline__ void weight_prep_tile(const vdqn_wprep_desc& d, int c
   for (int e = tid; e < 16 * run; e += 256) {                  // forward: [co][tap][ci], ci fastest
     const int cil = (e & 15) * 2, rest = e >> 4;
     const int c = rest / RS, tap = rest - c * RS;
-    const long o = (long)(co0 + c) * d.K + (long)tap * d.Cin + ci0 + cil;
+    const long o = (long)(co0 + c) * (d.ldw_fwd > 0 ? d.ldw_fwd : d.K) + d.fwd_col0 + (long)tap * d.Cin + ci0 + cil;
     wf[o >> 1] = __floats2bfloat162_rn(sw[c][cil * RS + tap], sw[c][(cil + 1) * RS + tap]);
   }
   if (d.w_dgrad != nullptr) {
@@ -129,14 +129,21 @@ __device__ __forceinline__ void weight_prep_tile(const vdqn_wprep_desc& d, int c
       const int r = tap / d.S, sx = tap - r * d.S;
       const int ci = ci0 + cil, co = co0 + c;
       long di;
-      if (d.dgrad_parity) {
+      if (d.dgrad_parity == 2) {
+        // one dense matrix for all four output-parity classes: row (a, b, ci), column (u, v, co)
+        const int pa = (r == 1) ? 0 : 1, u = (r == 0) ? 1 : 0;
+        const int pb = (sx == 1) ? 0 : 1, v = (sx == 0) ? 1 : 0;
+        const long ld = d.ldw_dgrad > 0 ? d.ldw_dgrad : 4 * d.Cout;
+        di = ((long)(pa * 2 + pb) * d.Cin + ci) * ld + (long)(u * 2 + v) * d.Cout + co;
+      } else if (d.dgrad_parity) {
         const int pa = (r == 1) ? 0 : 1, u = (r == 0) ? 1 : 0;
         const int pb = (sx == 1) ? 0 : 1, v = (sx == 0) ? 1 : 0;
         const int nb = 1 + pb, nt = (1 + pa) * nb;
         const int cls_off = (pa == 0) ? (pb == 0 ? 0 : 1) : (pb == 0 ? 3 : 5);
         di = (long)cls_off * d.Cin * d.Cout + (long)ci * (nt * d.Cout) + (long)(u * nb + v) * d.Cout + co;
       } else {
-        di = (long)ci * (RS * d.Cout) + (long)((d.R - 1 - r) * d.S + (d.S - 1 - sx)) * d.Cout + co;
+        di = (long)ci * (d.ldw_dgrad > 0 ? d.ldw_dgrad : RS * d.Cout) + d.dgrad_col0 +
+             (long)((d.R - 1 - r) * d.S + (d.S - 1 - sx)) * d.Cout + co;
       }
       wd[di >> 1] = __floats2bfloat162_rn(sw[c][cil * RS + tap], sw[c + 1][cil * RS + tap]);
     }
@@ -167,6 +174,8 @@ weight_prep_tiled_kernel(const vdqn_wprep_desc* __restrict__ descs, const int* _
       float sh = 0.f;
       if (d.gamma != nullptr) sh = d.beta[co] - d.mean[co] * scale;
       if (d.bias != nullptr) sh += d.bias[co];
+      if (d.gamma_b != nullptr)      // the shift of a second BatchNorm whose conv is accumulated into this one
+        sh += d.beta_b[co] - d.mean_b[co] * (d.gamma_b[co] * (1.0f / sqrtf(d.var_b[co] + d.eps)));
       d.shift[co] = sh;
     }
   }

@@ -287,7 +287,7 @@ __device__ __forceinline__ float epilogue_half_staged(const EpiArgs& a, const ui
 // indexed by the scattered pixel as well (or absent)
 inline bool fast_epilogue_ok(const vdqn_conv_desc* d) {
   const bool has_in = d->residual != nullptr || d->mask_src != nullptr;
-  if (d->out_scatter == 2 && has_in && !(d->flags & VDQN_EPI_SCATTER_INPUTS)) return false;
+  if (d->out_scatter >= 2 && has_in && !(d->flags & VDQN_EPI_SCATTER_INPUTS)) return false;
   return !(d->flags & VDQN_EPI_OUT_F32) && d->out2 == nullptr &&
          d->ldc % 8 == 0 && (d->residual == nullptr || d->ldr % 8 == 0) &&
          (d->mask_src == nullptr || d->ldm % 8 == 0);

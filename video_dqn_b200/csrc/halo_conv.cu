@@ -864,7 +864,7 @@ static int launch_halo_pool(const vdqn_conv_desc* d, cudaStream_t stream) {
 // Shapes this kernel takes: stride-1 "same" convolutions with Cout = 64 whose whole filter fits in
 // shared memory: 3x3 over 64 channels (layer1 fwd/dgrad) and the packed 4x4 x 16-channel stem.
 bool halo_conv_supported(const vdqn_conv_desc* d) {
-  if (d->stride != 1 || d->dil != 1 || d->Cout != 64 || d->out_scatter == 2 || d->out2 != nullptr)
+  if (d->stride != 1 || d->dil != 1 || d->Cout != 64 || d->out_scatter >= 2 || d->out2 != nullptr)
     return false;
   if (d->pad_hi_w >= 0 && d->pad_hi_w != d->pad_hi) return false;
   if (d->Cin == 64 && d->R == 3 && d->S == 3 && d->pad_lo == 1 && d->pad_hi == 1) return true;

@@ -147,9 +147,27 @@ class PreparedWeights:
             nq = plan.num_classes * plan.action_dim
             for key, (o, k) in (("top.0", (512, 1600 * plan.num_frames)), ("top.2", (256, 512)), ("top.4", (nq, 256))):
                 self.mlp[key] = (torch.empty(o, k, device=device, dtype=bf16), torch.empty(o, k, device=device, dtype=bf16))
+        # Strided residual blocks with folded BatchNorm: the 1x1/2 downsample is not a launch of its own.
+        # Forward: its weights are appended to conv2's rows ([Cout][9 Cout | Cin]) and conv2's kernel reduces
+        # over a1 AND the block input (second K segment); its shift is added to conv2's.  Backward: conv1's
+        # strided data gradient is ONE dense GEMM over a [4 Cin][2x2 taps x Cout | Cout] matrix -- the four
+        # output-parity classes as column groups, zeros where a class does not use a tap -- and the last Cout
+        # columns are the downsample's data gradient (class (0, 0) only), reduced over the block's output gradient.
+        self.fuse_ds = bool(fold_bn) and FUSE_DS
+        fused_c2 = {b.conv2.name: b for b in plan.blocks if b.ds is not None} if self.fuse_ds else {}
+        fused_c1 = {b.conv1.name: b for b in plan.blocks if b.ds is not None} if self.fuse_ds else {}
+        fused_ds = {b.ds.name: b for b in plan.blocks if b.ds is not None} if self.fuse_ds else {}
+        self._fused = (fused_c2, fused_c1, fused_ds)
         for c in self.convs:
-            self.w_fwd[c.name] = torch.empty(c.cout, c.k, c.k, c.gemm_cin, device=device, dtype=bf16)
-            if c.kmap == 0:
+            if c.name in fused_ds:
+                pass                                                       # lives inside conv2 / conv1 buffers
+            elif c.name in fused_c2:
+                self.w_fwd[c.name] = torch.empty(c.cout, c.K + fused_c2[c.name].cin, device=device, dtype=bf16)
+            else:
+                self.w_fwd[c.name] = torch.empty(c.cout, c.k, c.k, c.gemm_cin, device=device, dtype=bf16)
+            if c.kmap == 0 and c.name in fused_c1:
+                self.w_dgrad[c.name] = torch.zeros(4 * c.cin, 5 * c.cout, device=device, dtype=bf16)
+            elif c.kmap == 0 and c.name not in fused_ds:
                 self.w_dgrad[c.name] = torch.empty(c.cin, c.k, c.k, c.cout, device=device, dtype=bf16)
             self.shift[c.name] = torch.empty(c.cout, device=device, dtype=torch.float32)
 
@@ -165,10 +183,26 @@ class PreparedWeights:
             # through the tiled (coalesced) one
             dev = self.shift["stem"].device
 
+            fused_c2, fused_c1, fused_ds = self._fused
+
             def fill(d, c):
                 w = P[c.wkey]
-                d.w, d.w_fwd, d.shift = w.data_ptr(), self.w_fwd[c.name].data_ptr(), self.shift[c.name].data_ptr()
-                d.w_dgrad = L.ptr(self.w_dgrad.get(c.name))
+                d.w, d.shift = w.data_ptr(), self.shift[c.name].data_ptr()
+                if c.name in fused_ds:
+                    b = fused_ds[c.name]          # columns [9 Cout, 9 Cout + Cin) of conv2's rows; last Cout columns of conv1's
+                    d.w_fwd, d.ldw_fwd, d.fwd_col0 = self.w_fwd[b.conv2.name].data_ptr(), b.conv2.K + b.cin, b.conv2.K
+                    d.w_dgrad, d.ldw_dgrad, d.dgrad_col0 = self.w_dgrad[b.conv1.name].data_ptr(), 5 * b.cout, 4 * b.cout
+                else:
+                    d.w_fwd = self.w_fwd[c.name].data_ptr()
+                    d.w_dgrad = L.ptr(self.w_dgrad.get(c.name))
+                if c.name in fused_c2:
+                    b = fused_c2[c.name]
+                    d.ldw_fwd = c.K + b.cin
+                    bn2 = b.ds.bn
+                    d.gamma_b, d.beta_b = P[bn2 + ".weight"].data_ptr(), P[bn2 + ".bias"].data_ptr()
+                    d.mean_b, d.var_b = P[bn2 + ".running_mean"].data_ptr(), P[bn2 + ".running_var"].data_ptr()
+                if c.name in fused_c1:
+                    d.ldw_dgrad = 5 * c.cout
                 if c.bn is not None and self.fold_bn:
                     d.gamma, d.beta = P[c.bn + ".weight"].data_ptr(), P[c.bn + ".bias"].data_ptr()
                     d.mean, d.var = P[c.bn + ".running_mean"].data_ptr(), P[c.bn + ".running_var"].data_ptr()
@@ -179,7 +213,7 @@ class PreparedWeights:
                 else:                                   # top.0: [512, 1600] read as OIHW [512][64][5][5]
                     d.Cout, d.Cin, d.R, d.S = c.cout, c.cin, c.k, c.k
                 d.K, d.kmap, d.eps = c.K, c.kmap, BN_EPS
-                d.dgrad_parity = int(c.kmap == 0 and c.stride == 2 and c.k == 3)
+                d.dgrad_parity = (2 if c.name in fused_c1 else 1) if (c.kmap == 0 and c.stride == 2 and c.k == 3) else 0
 
             def upload(descs):
                 return torch.frombuffer(bytearray(bytes(descs)), dtype=torch.uint8).clone().to(dev)
@@ -252,7 +286,7 @@ class Workspace:
         self.a1, self.idn, self.out = [], [], []
         for b in plan.blocks:
             self.a1.append(e(nf, b.out_hw, b.out_hw, b.cout))
-            self.idn.append(e(nf, b.out_hw, b.out_hw, b.cout) if b.ds is not None else None)
+            self.idn.append(None)          # identity tensor of a strided block: only the unfused path makes one
             self.out.append(e(nf, b.out_hw, b.out_hw, b.cout))
         self.h = e(nf, 5, 5, 64)
         F = plan.num_frames
@@ -277,7 +311,7 @@ class Workspace:
             self.dy_a1 = {b.out_hw: e(n, b.out_hw, b.out_hw, b.cout) for b in plan.blocks}
             # zero-dilated buffer the 1x1/2 downsample data gradient scatters into (odd positions stay
             # zero forever); it is the residual of the strided conv1 data gradient
-            self.r_dil = {b.out_hw: z(n, b.in_hw, b.in_hw, b.cin) for b in plan.blocks if b.stride == 2}
+            self.r_dil = {}                # (unfused path only, made on first use)
             self.dy_p = e(n, 56, 56, 64)
             self.dy_s = e(n, 112, 112, 64)
             max_part = max(wgrad_splits(c, n) * c.cout * c.K for c in prep_convs(plan))
@@ -315,6 +349,9 @@ class Workspace:
 
 import os as _os
 
+# 1x1/2 downsample of a strided block inside conv2 (forward) / conv1's merged data gradient (backward); 0: its
+# own launches and four parity-class launches for the strided data gradient (the A/B switch for measurements)
+FUSE_DS = _os.environ.get("VDQN_FUSE_DS", "1") != "0"
 # stem + max-pool fused into one kernel (0: the stem writes its full-resolution output and a pooling kernel
 # re-reads it -- the A/B switch for measurements)
 FUSE_POOL = _os.environ.get("VDQN_FUSE_POOL", "1") != "0"
@@ -351,8 +388,10 @@ def _conv(W: PreparedWeights, c: ConvSpec, x, out, W2: Optional[PreparedWeights]
     tn = TILE_N_WIDE if c.cout >= 256 else 0
     if W2 is not None:
         kw.update(w2=W2.w_fwd[c.name], shift2=W2.shift[c.name], split_n=split)
-    return ops.conv_gemm(x, W.w_fwd[c.name], c.stride, c.pad_lo, c.pad_hi, shift=W.shift[c.name],
-                         out=out, tile_n=tn, **kw)
+    w = W.w_fwd[c.name]
+    if w.dim() == 2:
+        kw["ksize"] = (c.k, c.k)
+    return ops.conv_gemm(x, w, c.stride, c.pad_lo, c.pad_hi, shift=W.shift[c.name], out=out, tile_n=tn, **kw)
 
 
 def forward(plan: NetPlan, W: PreparedWeights, P: Dict[str, torch.Tensor], ws: Workspace,
@@ -389,11 +428,17 @@ def forward_packed(plan: NetPlan, W: PreparedWeights, P: Dict[str, torch.Tensor]
     x = ws.p
     for i, b in enumerate(plan.blocks):
         _conv(W, b.conv1, x, ws.a1[i], relu=True, **dual)
-        idn = x
-        if b.ds is not None:
-            _conv(W, b.ds, x, ws.idn[i], **dual)
-            idn = ws.idn[i]
-        _conv(W, b.conv2, ws.a1[i], ws.out[i], residual=idn, relu=True, **dual)
+        if b.ds is not None and W.fuse_ds:
+            # downsample accumulated inside conv2's kernel: no identity tensor, no residual read
+            _conv(W, b.conv2, ws.a1[i], ws.out[i], x2=x, stride2=b.stride, relu=True, **dual)
+        else:
+            idn = x
+            if b.ds is not None:
+                if ws.idn[i] is None:
+                    ws.idn[i] = torch.empty_like(ws.out[i])
+                _conv(W, b.ds, x, ws.idn[i], **dual)
+                idn = ws.idn[i]
+            _conv(W, b.conv2, ws.a1[i], ws.out[i], residual=idn, relu=True, **dual)
         x = ws.out[i]
     if trunk_only:
         return x                                      # [n, 7, 7, 512] bf16
@@ -552,8 +597,13 @@ def backward(plan: NetPlan, W: PreparedWeights, P: Dict[str, torch.Tensor], G: D
         # identity / downsample branch
         if b.ds is not None:
             _wgrad(plan, P, G, ws, b.ds, x_in, cur, None)
-            res = ws.r_dil[b.out_hw]
-            ops.conv_gemm(cur, W.w_dgrad[b.ds.name], 1, 0, 0, out=res, out_scatter=2, tile_n=_scatter_tile_n(b.cin))
+            if W.fuse_ds:
+                res = None               # the downsample's data gradient is a K segment of conv1's (below)
+            else:
+                if b.out_hw not in ws.r_dil:
+                    ws.r_dil[b.out_hw] = torch.zeros(ws.n, b.in_hw, b.in_hw, b.cin, device=cur.device, dtype=bf16)
+                res = ws.r_dil[b.out_hw]
+                ops.conv_gemm(cur, W.w_dgrad[b.ds.name], 1, 0, 0, out=res, out_scatter=2, tile_n=_scatter_tile_n(b.cin))
         else:
             res = cur
         # conv1: weight gradient, then the gradient wrt the block input (+ identity branch),
@@ -565,7 +615,15 @@ def backward(plan: NetPlan, W: PreparedWeights, P: Dict[str, torch.Tensor], G: D
             colsum, mask = G[prev.conv2.bn + ".bias"], x_in
         else:
             ni, dst, colsum, mask = 0, ws.dy_p, None, None
-        if b.stride == 2:
+        if b.stride == 2 and W.fuse_ds:
+            # strided data gradient + downsample data gradient as ONE dense GEMM: 2x2 window over dy_a1 with the
+            # four output-parity classes as column groups (taps a class does not use are zero columns: 16/9 of
+            # the minimal MMA work, but one launch with 5 Cout of K per tile instead of four latency-bound ones
+            # with Cout .. 4 Cout), plus the K segment over `cur` for the downsample; every row writes its 2x2
+            # pixel block of dX
+            ops.conv_gemm(dy_a1, W.w_dgrad[b.conv1.name], 1, 0, 1, ksize=(2, 2), x2=cur, stride2=1, mask_src=mask,
+                          colsum=colsum, out=dst, out_scatter=3, scatter_inputs=True, tile_n=128)
+        elif b.stride == 2:
             # strided data gradient, one small stride-1 conv per output-parity class (h%2, w%2): exactly
             # the 9 taps of work, each class scattering into its own pixels of dX
             for pa, pb, wf in parity_filters(W, b.conv1):

@@ -69,15 +69,23 @@ def conv_gemm(x, w, stride=1, pad_lo=0, pad_hi=None, *, shift=None, residual=Non
               relu=False, out_f32=False, colsum=None, out=None, out2=None, out_scatter=1,
               tile_n=0, max_ctas=0, dil=1, algo=0, pad_hi_w=-1, scatter_off=(0, 0), scatter_inputs=False,
               w2=None, shift2=None, split_n=0, x_alias=None, pool_out=None, pool_idx=None, pool_idx_images=0,
-              debug_flags=0):
+              debug_flags=0, x2=None, stride2=1, ksize=None):
     """x [N,H,W,Cin] bf16, w [Cout,R,S,Cin] bf16 -> out [N,Ho,Wo,Cout] (or zero-dilated
     [N,2Ho,2Wo,Cout] when out_scatter == 2; `out` must then be pre-zeroed).
     x_alias = (first, shift): images n >= first are read from image n - shift (packed stem only)."""
     lib = L.load()
     _cuda(x, bf16, "x"); _cuda(w, bf16, "w")
-    _req(x.dim() == 4 and w.dim() == 4 and x.shape[3] == w.shape[3], "bad shape")
     N, H, W_, Cin = x.shape
-    Cout, R, S, _ = w.shape
+    if ksize is not None:
+        # `w` as a matrix [Cout, R*S*Cin (+ Cin2)]: the rows may carry the columns of a second operand x2 (a
+        # 1x1 / stride2 window over another tensor, accumulated into the same output tile)
+        R, S = ksize
+        Cout = w.shape[0]
+        _req(x.dim() == 4 and w.dim() == 2 and w.shape[1] == R * S * Cin + (x2.shape[3] if x2 is not None else 0),
+             "bad shape")
+    else:
+        _req(x.dim() == 4 and w.dim() == 4 and x.shape[3] == w.shape[3] and x2 is None, "bad shape")
+        Cout, R, S, _ = w.shape
     pad_hi = pad_lo if pad_hi is None else pad_hi
     Ho = conv_out_hw(H, W_, R, S, stride, pad_lo, pad_hi, dil)[0]
     Wo = conv_out_hw(H, W_, R, S, stride, pad_lo, pad_hi if pad_hi_w < 0 else pad_hi_w, dil)[1]
@@ -103,13 +111,14 @@ def conv_gemm(x, w, stride=1, pad_lo=0, pad_hi=None, *, shift=None, residual=Non
     d.colsum = L.ptr(colsum)
     if shift is not None:
         _cuda(shift, torch.float32, "shift"); _req(shift.numel() == Cout, "bad shape")
-    n_in = N * Ho * Wo * Cout * (4 if scatter_inputs else 1)
+    n_in = N * Ho * Wo * Cout * (4 if (scatter_inputs and out_scatter == 2) else 1)
     if residual is not None:
         _cuda(residual, bf16, "residual"); _req(residual.numel() == n_in, "bad shape")
     if mask_src is not None:
         _cuda(mask_src, bf16, "mask_src"); _req(mask_src.numel() == n_in, "bad shape")
     if colsum is not None:
-        _cuda(colsum, torch.float32, "colsum"); _req(colsum.numel() == Cout, "bad shape")
+        _cuda(colsum, torch.float32, "colsum")
+        _req(colsum.numel() == (Cout // 4 if out_scatter == 3 else Cout), "bad shape")
     if out2 is not None:
         _cuda(out2, bf16, "out2"); _req(out2.numel() == N * 4 * Ho * Wo * Cout, "bad shape")
     d.N, d.H, d.W, d.Cin, d.Cout, d.R, d.S = N, H, W_, Cin, Cout, R, S
@@ -127,6 +136,9 @@ def conv_gemm(x, w, stride=1, pad_lo=0, pad_hi=None, *, shift=None, residual=Non
         d.x_alias_from, d.x_alias_shift = x_alias
     if pool_out is not None:
         d.pool_out, d.pool_idx, d.pool_idx_images = pool_out.data_ptr(), L.ptr(pool_idx), int(pool_idx_images)
+    if x2 is not None:
+        _cuda(x2, bf16, "x2"); _req(x2.dim() == 4 and x2.shape[0] == N, "bad shape")
+        d.x2, d.H2, d.W2, d.Cin2, d.stride2 = x2.data_ptr(), x2.shape[1], x2.shape[2], x2.shape[3], stride2
     with _Prof("igemm", (N, H, W_, Cin, Cout, R, stride)):
         L.check(lib.vdqn_conv_gemm(C.byref(d), L.stream_ptr()), "conv_gemm")
     return out
