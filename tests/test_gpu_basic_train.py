@@ -84,16 +84,22 @@ def test_avgpool_bwd_kernel():
     assert torch.equal(out, ref)
 
 
-def _build(sd, dev):
+def _build(sd, dev, frames=1):
     from video_dqn_b200.qnet import HabitatDQNMultiAction
-    m = HabitatDQNMultiAction(3, 5, extra_capacity=False, panorama=False)
+    m = HabitatDQNMultiAction(3, 5, extra_capacity=False, panorama=(frames == 4))
     res = m.load_state_dict(sd, strict=False)
     assert not res.unexpected_keys and all(k.endswith("num_batches_tracked") for k in res.missing_keys)
     return m.to(dev)
 
 
-def test_basic_architecture_training_step_matches_oracle():
-    """Bars (bf16 operands and bf16 raw conv outputs, normalised with the batch statistics of B = 8
+@pytest.mark.parametrize("fixture", ["basic_train_b8.npz", "basic_train_f4_b4.npz"])
+def test_basic_architecture_training_step_matches_oracle(fixture):
+    """Single frame at B = 8, and the four-frame panorama / previous-images layout at B = 4 (every frame through
+    the trunk separately: four sets of batch statistics and running-statistics updates per forward,
+    archs/HabitatDQNMultiAction.py:49-51).  With only 4 samples per batch statistic the F = 4 case is the
+    noisier one: its bars are 1.5x the single-frame ones (recorded in gpurun_out/basic_train_report_*.txt).
+
+    Bars (bf16 operands and bf16 raw conv outputs, normalised with the batch statistics of B = 8
     frames -- 392 values per channel in layer 4 -- vs the fp32 oracle): Q max-abs <= 2e-2 * max(1, |Q|max)
     (measured 1.6e-2 on |Q| <= 1.5), loss 3e-2 relative, gradients per-tensor cosine >= 0.82 and global
     rel-L2 <= 0.35, running statistics 2e-2 of their largest entry, num_batches_tracked exact.
@@ -108,13 +114,15 @@ def test_basic_architecture_training_step_matches_oracle():
     from video_dqn_b200.learner_basic import BasicQLearner, grad_param_names_basic
     dev = torch.device("cuda:0")
     torch.set_num_threads(os.cpu_count() or 1)
-    z = np.load(os.path.join(GOLD, "basic_train_b8.npz"))
-    B = int(z["meta/B"])
-    sd = qstep.init_state_basic(seed=4, num_frames=1)
+    from oracle.make_basic_train_goldens import frames_batch
+    z = np.load(os.path.join(GOLD, fixture))
+    B, nf = int(z["meta/B"]), int(z["meta/frames"])
+    slack = 1.0 if nf == 1 else 1.5
+    sd = qstep.init_state_basic(seed=4, num_frames=nf)
     oracle = qstep.BasicOracleTrainer(sd)
     names = grad_param_names_basic()
     assert names == oracle.names
-    model, target = _build(sd, dev), _build(sd, dev)
+    model, target = _build(sd, dev, nf), _build(sd, dev, nf)
     lr = BasicQLearner(model, target, StepConfig(), batch_size=B)
     mp = dict(model.named_parameters())
     mb = dict(model.named_buffers())
@@ -126,7 +134,7 @@ def test_basic_architecture_training_step_matches_oracle():
             bad.append(msg)
 
     for it in range(int(z["meta/steps"])):
-        batch = qstep.synthetic_batch(B, seed=1 + it)
+        batch = frames_batch(B, nf, 1 + it) if nf > 1 else qstep.synthetic_batch(B, seed=1 + it)
         # the oracle starts every step from the GPU's current parameters and running statistics (Adam's
         # sign-normalised update amplifies bf16 noise into the trajectory; see test_gpu_parity.py)
         for n in names:
@@ -138,16 +146,16 @@ def test_basic_architecture_training_step_matches_oracle():
         loss = lr.step(batch)
         torch.cuda.synchronize()
         scale = max(1.0, aux["q_s"].abs().max().item())
-        for tag, got, ref in (("q_s", lr.ws_s.q.view(B, 5, 3).cpu(), aux["q_s"]),
-                              ("q_next_online", lr.ws_next.q.view(B, 5, 3).cpu(), aux["q_next_online"]),
+        for tag, got, ref in (("q_s", lr.q_s.view(B, 5, 3).cpu(), aux["q_s"]),
+                              ("q_next_online", lr.q_no.view(B, 5, 3).cpu(), aux["q_next_online"]),
                               ("q_next_target", lr.q_next_target.cpu(), aux["q_next_target"])):
             e = (got - ref).abs().max().item()
-            check(e <= 2e-2 * scale, f"step {it} {tag}: max-abs {e:.4f} (scale {scale:.2f})")
+            check(e <= 2e-2 * slack * scale, f"step {it} {tag}: max-abs {e:.4f} (scale {scale:.2f})")
         e = abs(loss.item() - loss_ref.item()) / abs(loss_ref.item())
-        check(e <= 3e-2, f"step {it} loss {loss.item():.5f} vs oracle {loss_ref.item():.5f}: rel {e:.4f}")
+        check(e <= 3e-2 * slack, f"step {it} loss {loss.item():.5f} vs oracle {loss_ref.item():.5f}: rel {e:.4f}")
         if it == 0:
             e = abs(loss.item() - float(z["step0/loss"])) / float(z["step0/loss"])
-            check(e <= 3e-2, f"step 0 loss vs the reference's own number: rel {e:.4f}")
+            check(e <= 3e-2 * slack, f"step 0 loss vs the reference's own number: rel {e:.4f}")
         num = den = 0.0
         worst = (2.0, "")
         for n in names:
@@ -155,24 +163,24 @@ def test_basic_architecture_training_step_matches_oracle():
             check(bool(torch.isfinite(g).all()), f"step {it} {n} finite") if not torch.isfinite(g).all() else None
             c = _cos(g, grads_ref[n])
             worst = min(worst, (c, n))
-            floor = 0.82
+            floor = 0.82 if nf == 1 else 0.73
             if c < floor:
                 check(False, f"step {it} {n}: cosine {c:.4f} < {floor}")
             num += (g.double() - grads_ref[n].double()).pow(2).sum().item()
             den += grads_ref[n].double().pow(2).sum().item()
         rel = (num / den) ** 0.5
-        check(rel <= 0.35, f"step {it} gradient global rel-L2 {rel:.4f}, worst cosine {worst[0]:.4f} ({worst[1]})")
+        check(rel <= 0.35 * slack, f"step {it} gradient global rel-L2 {rel:.4f}, worst cosine {worst[0]:.4f} ({worst[1]})")
         # running statistics after the step's TWO train-mode forwards (oracle.sd was updated in place)
         wb = (0.0, "")
         for k, v in mb.items():
             if k.endswith("running_mean") or k.endswith("running_var"):
                 ref = oracle.sd[k]
                 wb = max(wb, ((v.cpu() - ref).abs().max().item() / max(1e-3, ref.abs().max().item()), k))
-        check(wb[0] <= 2e-2, f"step {it} running statistics worst rel deviation {wb[0]:.5f} ({wb[1]})")
-        check(int(mb["resnet.bn1.num_batches_tracked"]) == 2 * (it + 1), f"step {it} num_batches_tracked")
+        check(wb[0] <= 2e-2 * slack, f"step {it} running statistics worst rel deviation {wb[0]:.5f} ({wb[1]})")
+        check(int(mb["resnet.bn1.num_batches_tracked"]) == 2 * nf * (it + 1), f"step {it} num_batches_tracked")
     # the module's eval forward sees the trained parameters and statistics
     model.eval()
-    x = qstep.synthetic_batch(B, seed=9)[0]
+    x = frames_batch(B, nf, 9)[0] if nf > 1 else qstep.synthetic_batch(B, seed=9)[0]
     with torch.no_grad():
         q = model(x.to(dev)).cpu()
         for n in names:
@@ -185,7 +193,7 @@ def test_basic_architecture_training_step_matches_oracle():
     check(e <= 1e-2 * max(1.0, q_ref.abs().max().item()), f"eval forward after training: max-abs {e:.4f}")
     print("\n".join(report))
     os.makedirs(os.path.join(os.path.dirname(GOLD), "..", "gpurun_out"), exist_ok=True)
-    with open(os.path.join(os.path.dirname(GOLD), "..", "gpurun_out", "basic_train_report.txt"), "w") as f:
+    with open(os.path.join(os.path.dirname(GOLD), "..", "gpurun_out", f"basic_train_report_f{nf}.txt"), "w") as f:
         f.write("\n".join(report) + "\n")
     assert not bad, "\n".join(report)
     with pytest.raises(ValueError):
@@ -195,3 +203,69 @@ def test_basic_architecture_training_step_matches_oracle():
 def _build_extra(dev):
     from video_dqn_b200.qnet import HabitatDQNMultiAction
     return HabitatDQNMultiAction(3, 5, extra_capacity=True, panorama=False).to(dev)
+
+
+def _syncbn_rank(rank, world, port, sd, batch, out_dir):
+    """one rank of test_syncbn_two_ranks_equal_one_process (both ranks on cuda:0, gloo carries the CUDA tensors)"""
+    import torch.distributed as dist
+    from video_dqn_b200.learner import StepConfig
+    from video_dqn_b200.learner_basic import BasicQLearner
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    dev = torch.device("cuda:0")
+    B = batch[0].shape[0] // world
+    mine = [t[rank * B:(rank + 1) * B] for t in batch]
+    lr = BasicQLearner(_build(sd, dev), _build(sd, dev), StepConfig(), batch_size=B, world_size=world)
+    loss = lr.step(mine)
+    torch.cuda.synchronize()
+    torch.save({"loss": loss.item(), "grads": {n: g.detach().cpu() for n, g in lr.G.items()},
+                "rm": lr.model.resnet.layer3[0].bn1.running_mean.detach().cpu(),
+                "rv": lr.model.resnet.bn1.running_var.detach().cpu(),
+                "p": dict(lr.model.named_parameters())["resnet.layer2.0.conv1.weight"].detach().cpu()},
+               os.path.join(out_dir, f"rank{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_syncbn_two_ranks_equal_one_process(tmp_path):
+    """the `basic` architecture under data parallelism needs SyncBatchNorm.  Two ranks (two
+    processes on this one GPU, gloo moving the CUDA tensors) with 4 quadruplets each must reproduce one process
+    with all 8: same running statistics (the global batch's), exchanged gradient = the global-batch gradient,
+    same parameters after Adam on both ranks."""
+    import torch.multiprocessing as mp
+    from video_dqn_b200.learner import StepConfig
+    from video_dqn_b200.learner_basic import BasicQLearner
+    dev = torch.device("cuda:0")
+    sd = qstep.init_state_basic(seed=4, num_frames=1)
+    batch = qstep.synthetic_batch(8, seed=3)
+    port = 29700 + os.getpid() % 200
+    mp.spawn(_syncbn_rank, args=(2, port, sd, batch, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = (torch.load(os.path.join(tmp_path, f"rank{r}.pt")) for r in range(2))
+    one = BasicQLearner(_build(sd, dev), _build(sd, dev), StepConfig(), batch_size=8)
+    loss = one.step(batch)
+    torch.cuda.synchronize()
+    # not bit-equal: the two-rank sums are formed in another order, the last fp32 bit of a scale or shift flips
+    # a few bf16 roundings of the normalised activations, and those propagate (measured 3.4e-4 on the loss)
+    assert abs(0.5 * (r0["loss"] + r1["loss"]) - loss.item()) <= 2e-3 * abs(loss.item())
+    assert torch.equal(r0["p"], r1["p"]) and torch.equal(r0["rm"], r1["rm"])          # ranks stay in lock step
+    rm = one.model.resnet.layer3[0].bn1.running_mean.detach().cpu()
+    rv = one.model.resnet.bn1.running_var.detach().cpu()
+    # the stem's statistics only see the input (tight); layer3's carry the bf16 noise of ten layers (measured 1e-4)
+    assert torch.allclose(r0["rv"], rv, rtol=1e-4, atol=1e-7)
+    assert (r0["rm"] - rm).abs().max().item() <= 5e-3 * rm.abs().max().item()
+    # gradients: two bf16 realisations of this path differ from each other as much as each differs from the fp32
+    # oracle (the batch-statistics backward amplifies rounding, see test_basic_architecture_training_step_...;
+    # measured 0.33 between the two), so the exchanged two-rank gradient is held to the ORACLE on the global
+    # batch with the single-process bars: a wrong SyncBatchNorm count or a double-counted d gamma would show as
+    # a norm ratio of 2, not as noise
+    torch.set_num_threads(os.cpu_count() or 1)
+    _l, g_ref, _aux = qstep.BasicOracleTrainer(sd).loss_and_grads(batch)
+    num = den = na = nb = 0.0
+    for n, g in g_ref.items():
+        a = 0.5 * r0["grads"][n].double()           # the exchanged sum, scaled as Adam scales it (1 / world)
+        b = g.double()
+        if b.numel() >= 10000:                       # the 64-element stem BatchNorm gradients are all noise at B = 8
+            assert _cos(a, b) >= 0.75, (n, _cos(a, b))   # (measured worst of the large tensors: 0.80, the stem filter)
+        num += (a - b).pow(2).sum().item(); den += b.pow(2).sum().item()
+        na += a.pow(2).sum().item(); nb += b.pow(2).sum().item()
+    assert (num / den) ** 0.5 <= 0.45, (num / den) ** 0.5       # measured 0.38 on this batch (0.29 on the fixture's)
+    assert abs((na / nb) ** 0.5 - 1.0) <= 0.1, (na / nb) ** 0.5

@@ -14,10 +14,18 @@ Batch statistics depend on the conv OUTPUT, so BatchNorm cannot be folded into t
 the shipped (eval-mode) path: every conv runs on the tensor-core kernels with plain bf16 weights and
 writes its raw output; `bn_stats -> bn_finalize -> bn_apply` (csrc/batchnorm.cu, HBM-bound) normalise
 it (+ residual, + ReLU); the backward inserts `bn_bwd_reduce -> bn_bwd_apply` between the data
-gradient of the layer above and the weight / data gradient of the conv below.  Single frame (F = 1)
-only: with F frames the reference pushes each frame through the trunk separately (:49-51), i.e. F
-separate sets of batch statistics per forward.  One process (no SyncBN: the reference has no
-data-parallel mode).  Eager launches, no CUDA graph.  CUDA only, no fallback.
+gradient of the layer above and the weight / data gradient of the conv below.
+
+F frames (PANORAMA / PREVIOUS_IMAGES, train_q_network.py:36-47): the reference pushes each frame through the
+trunk separately, in order (archs/HabitatDQNMultiAction.py:49-51) -- F sets of batch statistics and F
+running-statistics updates per forward -- and concatenates the pooled features before the Linear.  The same
+here: one train-mode trunk pass (and one workspace of saved activations) per frame, the trunk's parameter
+gradients are the sum over the frames.
+
+Data parallel (the reference has no such mode, :275): SyncBatchNorm -- the fp64 per-channel sums of every
+BatchNorm are all-reduced over the ranks (ops.BnSync), forward and backward, so each rank normalises with the
+statistics of the global batch -- and the gradient arena is all-reduced before Adam (`grad_scale = 1/world`).
+Eager launches, no CUDA graph.  CUDA only, no fallback.
 """
 from __future__ import annotations
 
@@ -77,23 +85,31 @@ class BnTrainWorkspace:
             self.part = e(max(E.wgrad_splits(c, n) * c.cout * c.K for c in convs), dt=f32)
 
 
-def _bn(ws: BnTrainWorkspace, P, c: E.ConvSpec, x_raw, y, *, residual=None, relu=False, update_running=True):
+def _bn(ws: BnTrainWorkspace, P, c: E.ConvSpec, x_raw, y, *, residual=None, relu=False, update_running=True, sync=None):
     p = c.bn
     return ops.bn_train_fwd(x_raw, ws.stats[p], P[p + ".weight"], P[p + ".bias"], P[p + ".running_mean"],
                             P[p + ".running_var"], P.get(p + ".num_batches_tracked"), y, residual=residual,
-                            relu=relu, momentum=0.1, eps=E.BN_EPS, update_running=update_running)
+                            relu=relu, momentum=0.1, eps=E.BN_EPS, update_running=update_running, sync=sync)
 
 
 def forward_bn_train(plan: E.NetPlan, W: E.PreparedWeights, P: Dict[str, torch.Tensor], ws: BnTrainWorkspace,
-                     update_running: bool = True) -> torch.Tensor:
-    """Train-mode forward from the packed input ws.xp -> Q [n, classes*actions] fp32.  `W` must hold
-    UNFOLDED weights (PreparedWeights(fold_bn=False))."""
+                     update_running: bool = True, sync=None) -> torch.Tensor:
+    """Train-mode forward of a single-frame network from the packed input ws.xp -> Q [n, classes*actions] fp32."""
+    trunk_forward_bn_train(plan, W, P, ws, update_running, sync)
+    ops.linear_fwd(ws.pooled, P["top.weight"], P["top.bias"], False, ws.q)
+    return ws.q
+
+
+def trunk_forward_bn_train(plan: E.NetPlan, W: E.PreparedWeights, P: Dict[str, torch.Tensor], ws: BnTrainWorkspace,
+                           update_running: bool = True, sync=None) -> torch.Tensor:
+    """Train-mode trunk + global average pool from the packed input ws.xp -> ws.pooled [n, 512] fp32.  `W` must
+    hold UNFOLDED weights (PreparedWeights(fold_bn=False))."""
     assert not W.fold_bn
     # shift = 0 for unfolded weights; it is passed so the launches take the same (tested) epilogue variants
     # as the folded path
     conv = lambda c, x, out: ops.conv_gemm(x, W.w_fwd[c.name], c.stride, c.pad_lo, c.pad_hi,  # noqa: E731
                                            shift=W.shift[c.name], out=out)
-    kw = dict(update_running=update_running)
+    kw = dict(update_running=update_running, sync=sync)
     conv(plan.stem, ws.xp, ws.s_raw)
     _bn(ws, P, plan.stem, ws.s_raw, ws.s, relu=True, **kw)
     ops.maxpool_fwd(ws.s, ws.p, ws.idx)
@@ -111,8 +127,7 @@ def forward_bn_train(plan: E.NetPlan, W: E.PreparedWeights, P: Dict[str, torch.T
         _bn(ws, P, b.conv2, ws.c2_raw[i], ws.out[i], residual=idn, relu=True, **kw)
         x = ws.out[i]
     ops.avgpool_fwd(x, ws.pooled)
-    ops.linear_fwd(ws.pooled, P["top.weight"], P["top.bias"], False, ws.q)
-    return ws.q
+    return ws.pooled
 
 
 def _wgrad_raw(ws: BnTrainWorkspace, P, G, c: E.ConvSpec, x, dy):
@@ -124,14 +139,20 @@ def _wgrad_raw(ws: BnTrainWorkspace, P, G, c: E.ConvSpec, x, dy):
                        K=c.K, kmap=c.kmap)
 
 
-def _bn_bwd(ws: BnTrainWorkspace, P, G, c: E.ConvSpec, dy, x_raw, dx):
+def _bn_bwd(ws: BnTrainWorkspace, P, G, c: E.ConvSpec, dy, x_raw, dx, sync=None):
     p = c.bn
-    return ops.bn_train_bwd(dy, x_raw, ws.stats[p], P[p + ".weight"], G[p + ".weight"], G[p + ".bias"], dx)
+    return ops.bn_train_bwd(dy, x_raw, ws.stats[p], P[p + ".weight"], G[p + ".weight"], G[p + ".bias"], dx, sync=sync)
 
 
-def backward_bn_train(plan: E.NetPlan, W: E.PreparedWeights, P, G, ws: BnTrainWorkspace, dq: torch.Tensor):
-    """dq [n, classes*actions] fp32 (overwritten) -> every parameter gradient in G."""
+def backward_bn_train(plan: E.NetPlan, W: E.PreparedWeights, P, G, ws: BnTrainWorkspace, dq: torch.Tensor, sync=None):
+    """Single-frame network: dq [n, classes*actions] fp32 (overwritten) -> every parameter gradient in G."""
     ops.linear_bwd(ws.pooled, P["top.weight"], None, dq, G["top.weight"], G["top.bias"], False, dx=ws.dpooled)
+    trunk_backward_bn_train(plan, W, P, G, ws, sync)
+
+
+def trunk_backward_bn_train(plan: E.NetPlan, W: E.PreparedWeights, P, G, ws: BnTrainWorkspace, sync=None):
+    """ws.dpooled [n, 512] fp32 -> the trunk's parameter gradients in G (overwritten)."""
+    _bnb = lambda *a: _bn_bwd(*a, sync=sync)  # noqa: E731
     last = plan.blocks[-1]
     ci = 0
     cur = ws.dy_out[last.out_hw][ci]
@@ -141,16 +162,16 @@ def backward_bn_train(plan: E.NetPlan, W: E.PreparedWeights, P, G, ws: BnTrainWo
         x_in = ws.out[i - 1] if i > 0 else ws.p
         prev = plan.blocks[i - 1] if i > 0 else None
         # bn2 -> conv2
-        d_c2 = _bn_bwd(ws, P, G, b.conv2, cur, ws.c2_raw[i], ws.d_c2[b.out_hw])
+        d_c2 = _bnb(ws, P, G, b.conv2, cur, ws.c2_raw[i], ws.d_c2[b.out_hw])
         _wgrad_raw(ws, P, G, b.conv2, ws.a1[i], d_c2)
         dy_a1 = ws.dy_a1[b.out_hw]
         ops.conv_gemm(d_c2, W.w_dgrad[b.conv2.name], 1, 1, 1, mask_src=ws.a1[i], out=dy_a1,
                       tile_n=E._dgrad_tile_n(b.cout))
         # bn1 (in place: dy_a1 becomes the gradient w.r.t. conv1's raw output)
-        d_c1 = _bn_bwd(ws, P, G, b.conv1, dy_a1, ws.c1_raw[i], dy_a1)
+        d_c1 = _bnb(ws, P, G, b.conv1, dy_a1, ws.c1_raw[i], dy_a1)
         # identity / downsample branch
         if b.ds is not None:
-            d_ds = _bn_bwd(ws, P, G, b.ds, cur, ws.ds_raw[i], ws.d_ds[b.out_hw])
+            d_ds = _bnb(ws, P, G, b.ds, cur, ws.ds_raw[i], ws.d_ds[b.out_hw])
             _wgrad_raw(ws, P, G, b.ds, x_in, d_ds)
             res = ws.r_dil[b.out_hw]
             ops.conv_gemm(d_ds, W.w_dgrad[b.ds.name], 1, 0, 0, out=res, out_scatter=2,
@@ -174,7 +195,7 @@ def backward_bn_train(plan: E.NetPlan, W: E.PreparedWeights, P, G, ws: BnTrainWo
         cur, ci = dst, ni
     # max-pool (routes through the arg-max and applies the stem ReLU mask), stem BatchNorm, stem conv
     ops.maxpool_bwd(ws.dy_p, ws.idx, ws.p, ws.dy_s, colsum=None)
-    _bn_bwd(ws, P, G, plan.stem, ws.dy_s, ws.s_raw, ws.dy_s)
+    _bnb(ws, P, G, plan.stem, ws.dy_s, ws.s_raw, ws.dy_s)
     _wgrad_raw(ws, P, G, plan.stem, ws.xp, ws.dy_s)
 
 
@@ -186,11 +207,11 @@ class BasicQLearner:
 
     def __init__(self, model: HabitatDQNMultiAction, target_net: HabitatDQNMultiAction,
                  cfg: Optional[StepConfig] = None, batch_size: int = 16, *,
-                 optimizer: Optional[FusedAdam] = None):
+                 optimizer: Optional[FusedAdam] = None, world_size: int = 1, process_group=None):
+        """world_size > 1: one process per GPU over torch.distributed (`process_group`, default the world):
+        SyncBatchNorm statistics + a gradient all-reduce before Adam."""
         if model.extra_capacity or target_net.extra_capacity:
             raise ValueError("BasicQLearner is for extra_capacity=False; use QLearner for the shipped architecture")
-        if model.num_frames != 1:
-            raise NotImplementedError("train-mode BatchNorm path: single-frame networks only")
         self.cfg = cfg or StepConfig()
         if self.cfg.TRAIN_ON_GROUND_TRUTH:
             raise NotImplementedError("ground-truth regression is implemented for the extra_capacity path only")
@@ -200,15 +221,31 @@ class BasicQLearner:
         self.model, self.target_net, self.B, self.device = model, target_net, batch_size, dev
         model.set_train()                                   # BatchNorms stay in train mode (:37-40)
         target_net.eval()
-        self.plan = E.make_plan(model.action_dim, model.num_classes, 1)
+        self.F = F = model.num_frames
+        self.world, self.group = world_size, process_group
+        self.sync = ops.BnSync(world_size, process_group) if world_size > 1 else None
+        self.plan = E.make_plan(model.action_dim, model.num_classes, 1)          # per-frame trunk plan
         self.names = grad_param_names_basic()
         self.opt = optimizer or FusedAdam(model.parameters(), lr=self.cfg.LEARNING_RATE)
         mp = dict(model.named_parameters())
         self.opt.adopt([mp[n] for n in self.names])
         self.G: Dict[str, torch.Tensor] = dict(zip(self.names, self.opt.grad_views()))
         self.W = E.PreparedWeights(self.plan, dev, trunk_only=True, fold_bn=False)
-        self.ws_s = BnTrainWorkspace(self.plan, batch_size, dev, train=True)
+        # model(before): one workspace of saved activations per frame; model(after): one, reused frame by frame
+        self.ws_frames = [BnTrainWorkspace(self.plan, batch_size, dev, train=True) for _ in range(F)]
+        self.ws_s = self.ws_frames[0]
         self.ws_next = BnTrainWorkspace(self.plan, batch_size, dev, train=False)
+        if F > 1:
+            from .optim import FlatArena
+            self._tmp = FlatArena([mp[n].shape for n in self.names], dev)       # gradients of frames 1 .. F-1
+            self.G_tmp = dict(zip(self.names, self._tmp.views()))
+        f32 = torch.float32
+        nq = self.plan.num_classes * self.plan.action_dim
+        self.pooled_s = torch.empty(batch_size, 512 * F, device=dev, dtype=f32)
+        self.pooled_n = torch.empty(batch_size, 512 * F, device=dev, dtype=f32)
+        self.dpooled = torch.empty(batch_size, 512 * F, device=dev, dtype=f32)
+        self.q_s = torch.empty(batch_size, nq, device=dev, dtype=f32)
+        self.q_no = torch.empty(batch_size, nq, device=dev, dtype=f32)
         C, A = self.plan.num_classes, self.plan.action_dim
         self.dq = torch.empty(batch_size, C * A, device=dev, dtype=torch.float32)
         self.loss = torch.zeros(1, device=dev, dtype=torch.float32)
@@ -237,21 +274,48 @@ class BasicQLearner:
         C, A = plan.num_classes, plan.action_dim
         self.opt.grad_arena.zero_()
         self.loss.zero_()
-        # model(before): activations kept
-        ops.stem_pack(before.contiguous(), self.ws_s.xp)
-        q_s = forward_bn_train(plan, self.W, P, self.ws_s)
+        F, sync = self.F, self.sync
+        frames = lambda t, f: (t[:, f] if t.dim() == 5 else t).contiguous()  # noqa: E731
+        # model(before): every frame through the trunk on its own (its own batch statistics, one
+        # running-statistics update each, in frame order), activations kept
+        for f, ws in enumerate(self.ws_frames):
+            ops.stem_pack(frames(before, f), ws.xp)
+            trunk_forward_bn_train(plan, self.W, P, ws, sync=sync)
+            if F > 1:
+                self.pooled_s[:, 512 * f:512 * (f + 1)].copy_(ws.pooled)
+        pooled_s = self.pooled_s if F > 1 else self.ws_s.pooled
+        q_s = ops.linear_fwd(pooled_s, P["top.weight"], P["top.bias"], False, self.q_s)
         # target_net(after): eval mode, the module's own forward-only path
         q_nt = self.target_net(after).reshape(B, C, A).contiguous()
-        # model(after): train mode again (second running-statistics update of the step), nothing kept
-        ops.stem_pack(after.contiguous(), self.ws_next.xp)
-        q_no = forward_bn_train(plan, self.W, P, self.ws_next)
+        # model(after): train mode again (F more running-statistics updates), nothing kept
+        for f in range(F):
+            ops.stem_pack(frames(after, f), self.ws_next.xp)
+            trunk_forward_bn_train(plan, self.W, P, self.ws_next, sync=sync)
+            if F > 1:
+                self.pooled_n[:, 512 * f:512 * (f + 1)].copy_(self.ws_next.pooled)
+        q_no = ops.linear_fwd(self.pooled_n if F > 1 else self.ws_next.pooled, P["top.weight"], P["top.bias"], False,
+                              self.q_no)
         ops.td_epilogue(q_s.view(B, C, A), q_no.view(B, C, A), q_nt, act.view(-1), rew, term, valid,
                         gamma=cfg.GAMMA, double_dqn=cfg.double_dqn, clip_rect=(cfg.LOSS_CLIP == "rect"),
                         linear=cfg.LINEAR, use_valid=cfg.REMOVE_BEFORE_REWARD, inv_count=1.0 / (B * C),
                         dq=self.dq.view(B, C, A), loss=self.loss, best=self.best, y=self.y)
         self.q_next_target = q_nt
-        backward_bn_train(plan, self.W, P, self.G, self.ws_s, self.dq)
-        self.opt.step(grads_in_arena=True)
+        # backward: the Linear once, then the trunk per frame (the trunk's parameter gradients add up)
+        ops.linear_bwd(pooled_s, P["top.weight"], None, self.dq, self.G["top.weight"], self.G["top.bias"], False,
+                       dx=self.dpooled if F > 1 else self.ws_s.dpooled)
+        for f, ws in enumerate(self.ws_frames):
+            if F > 1:
+                ws.dpooled.copy_(self.dpooled[:, 512 * f:512 * (f + 1)])
+            if f == 0:
+                trunk_backward_bn_train(plan, self.W, P, self.G, ws, sync)
+            else:
+                self._tmp.flat.zero_()
+                trunk_backward_bn_train(plan, self.W, P, self.G_tmp, ws, sync)
+                self.opt.grad_arena.add_(self._tmp.flat)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.opt.grad_arena, group=self.group)
+        self.opt.step(grads_in_arena=True, grad_scale=1.0 / self.world)
         # parameters and running statistics changed behind torch's version counters: make the module's
         # forward-only path re-derive its folded operands next time it is used
         st = getattr(self.model, "_basic_eng", None)

@@ -504,8 +504,22 @@ class BnBatchStats:
         self.bsums = torch.zeros(2 * C, device=device, dtype=torch.float64)     # backward: sum dy, sum dy*xhat
 
 
+class BnSync:
+    """SyncBatchNorm plumbing for the data-parallel `basic` architecture: the per-channel fp64
+    sums of a train-mode BatchNorm are all-reduced over the ranks between the statistics kernel and the
+    finalize kernel (forward) and between the reduction and the apply kernel (backward), so every rank
+    normalises with the statistics of the GLOBAL batch (count M * world)."""
+
+    def __init__(self, world: int, group=None):
+        self.world, self.group = world, group
+
+    def all_reduce(self, t):
+        import torch.distributed as dist
+        dist.all_reduce(t, group=self.group)
+
+
 def bn_train_fwd(x, st: "BnBatchStats", gamma, beta, running_mean, running_var, nbt, y, *, residual=None,
-                 relu=False, momentum=0.1, eps=1e-5, update_running=True):
+                 relu=False, momentum=0.1, eps=1e-5, update_running=True, sync=None):
     """Train-mode BatchNorm2d (+ residual) (+ ReLU) on raw conv output x [.., C] bf16 -> y bf16; batch
     statistics stay in `st` for the backward pass; running statistics / num_batches_tracked are updated
     in place (torch.nn.BatchNorm2d.forward)."""
@@ -523,7 +537,11 @@ def bn_train_fwd(x, st: "BnBatchStats", gamma, beta, running_mean, running_var, 
     sp = L.stream_ptr()
     with _Prof("bn", (M, Cc)):
         L.check(lib.vdqn_bn_stats(x.data_ptr(), st.sums.data_ptr(), M, Cc, sp), "bn_stats")
-        L.check(lib.vdqn_bn_finalize(st.sums.data_ptr(), M, Cc, gamma.data_ptr(), beta.data_ptr(),
+        Mg = M
+        if sync is not None:
+            sync.all_reduce(st.sums)
+            Mg = M * sync.world
+        L.check(lib.vdqn_bn_finalize(st.sums.data_ptr(), Mg, Cc, gamma.data_ptr(), beta.data_ptr(),
                                      running_mean.data_ptr() if update_running else None,
                                      running_var.data_ptr() if update_running else None,
                                      L.ptr(nbt) if update_running else None, momentum, eps,
@@ -534,7 +552,7 @@ def bn_train_fwd(x, st: "BnBatchStats", gamma, beta, running_mean, running_var, 
     return y
 
 
-def bn_train_bwd(dy, x, st: "BnBatchStats", gamma, dgamma, dbeta, dx):
+def bn_train_bwd(dy, x, st: "BnBatchStats", gamma, dgamma, dbeta, dx, sync=None):
     """dy = gradient w.r.t. the BatchNorm output (bf16, already masked by the following ReLU), x = the
     raw conv output the forward normalised.  Writes dgamma / dbeta (fp32, overwritten) and dx (bf16, may
     alias dy)."""
@@ -549,9 +567,18 @@ def bn_train_bwd(dy, x, st: "BnBatchStats", gamma, dgamma, dbeta, dx):
     with _Prof("bn", (M, Cc)):
         L.check(lib.vdqn_bn_bwd_reduce(dy.data_ptr(), x.data_ptr(), st.mean.data_ptr(), st.rstd.data_ptr(),
                                        st.bsums.data_ptr(), M, Cc, sp), "bn_bwd_reduce")
+        dg, db, Mg = dgamma, dbeta, M
+        if sync is not None:
+            # d gamma / d beta are this rank's OWN sums (the gradient exchange adds the ranks up afterwards); dx
+            # needs the sums of the global batch
+            dbeta.copy_(st.bsums[:Cc]); dgamma.copy_(st.bsums[Cc:])
+            sync.all_reduce(st.bsums)
+            if getattr(st, "scratch", None) is None:
+                st.scratch = torch.empty(2 * Cc, device=x.device, dtype=torch.float32)
+            dg, db, Mg = st.scratch[:Cc], st.scratch[Cc:], M * sync.world
         L.check(lib.vdqn_bn_bwd_apply(dy.data_ptr(), x.data_ptr(), st.mean.data_ptr(), st.rstd.data_ptr(),
-                                      gamma.data_ptr(), st.bsums.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(),
-                                      dx.data_ptr(), M, Cc, sp), "bn_bwd_apply")
+                                      gamma.data_ptr(), st.bsums.data_ptr(), dg.data_ptr(), db.data_ptr(),
+                                      dx.data_ptr(), Mg, Cc, sp), "bn_bwd_apply")
     return dx
 
 
