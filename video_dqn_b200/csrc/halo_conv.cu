@@ -66,7 +66,13 @@ struct HaloCfg {
   static constexpr int W_ROWS = PAIR ? BN / 2 : BN;               // filter rows staged by this CTA
   static constexpr int W_TILE_BYTES = W_ROWS * ROW_BYTES;          // one tap: W_ROWS x CK
   static constexpr int W_BYTES = MAX_TAPS * W_TILE_BYTES;          // 72 KB / 32 KB, resident
-  static constexpr int STAGES = (CK == 64) ? 3 : 12;
+#ifndef VDQN_POOL_STAGES
+#define VDQN_POOL_STAGES 15      // (sweep on B200: 12/4 480 us, 15/5 453 us, 18/6 453 us for 768 frames)
+#endif
+#ifndef VDQN_POOL_DEPTH
+#define VDQN_POOL_DEPTH 5
+#endif
+  static constexpr int STAGES = (CK == 64) ? 3 : (POOL ? VDQN_POOL_STAGES : 12);
   // EIGHT epilogue warps, two per TMEM lane quadrant, each owning 32 of the 64 output columns with
   // private staging tiles [32 pixels][32 ch] (64-byte rows, 64B swizzle): OUT_BUFS x out,
   // 2 x (residual, mask).  The out tile is double-buffered wherever shared memory allows (not next to
@@ -263,7 +269,7 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       // padding) into the 32B-swizzled layout the MMA descriptors expect, DEPTH tiles in flight each.
       // each warp waits for the tile it issued DEPTH-1 iterations ago: with too few tiles in flight the
       // loop period is the memory latency (measured: 84 us floor at DEPTH 2); 3 warps x 4 tiles in flight of the 16 stages
-      constexpr int DEPTH = 4;
+      constexpr int DEPTH = POOL ? VDQN_POOL_DEPTH : 4;
       constexpr int CHUNKS = Cfg::HALO_H * Cfg::HALO_W * 2;
       constexpr int PER_LANE = (CHUNKS + 31) / 32;
       // the chunk -> (window pixel, smem offset) map is the same for every tile: keep it in registers
