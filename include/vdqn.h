@@ -45,6 +45,10 @@ int vdqn_init(int device);
 int vdqn_num_sms(void);
 /* Number of kernels this library has launched (or captured into a graph) so far in this process. */
 long long vdqn_launch_count(void);
+/* Zero `bytes` bytes of device memory on `stream` (cudaMemsetAsync: a memset node when captured in a CUDA
+ * graph, no kernel).  The fused step clears its gradient arena and loss accumulator with it, so every KERNEL of
+ * a step is one of this library's. */
+int vdqn_zero(void* ptr, int64_t bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * Implicit-GEMM convolution, forward and data-gradient (tcgen05 + TMA im2col).

@@ -85,6 +85,7 @@ EXPORTS = {
     "vdqn_init": (c_int, [c_int]),
     "vdqn_num_sms": (c_int, []),
     "vdqn_launch_count": (C.c_longlong, []),
+    "vdqn_zero": (c_int, [c_void_p, c_int64, c_void_p]),
     "vdqn_conv_gemm": (c_int, [C.POINTER(ConvDesc), c_void_p]),
     "vdqn_conv_wgrad": (c_int, [C.POINTER(WgradDesc), c_void_p]),
     "vdqn_wgrad_finalize": (c_int, [C.POINTER(WgradFinDesc), c_void_p]),

@@ -172,3 +172,11 @@ extern "C" int vdqn_num_sms(void) {
   return d ? d->num_sms : -1;
 }
 extern "C" long long vdqn_launch_count(void) { return vdqn::g_launches.load(); }
+
+extern "C" int vdqn_zero(void* ptr, int64_t bytes, void* stream_v) {
+  if (ptr == nullptr || bytes < 0) return vdqn::set_error(VDQN_ERR_ARG, "zero: bad argument");
+  if (bytes == 0) return VDQN_OK;
+  cudaError_t e = cudaMemsetAsync(ptr, 0, (size_t)bytes, static_cast<cudaStream_t>(stream_v));
+  if (e != cudaSuccess) return vdqn::set_error(VDQN_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
+  return VDQN_OK;
+}

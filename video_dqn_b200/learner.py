@@ -151,8 +151,8 @@ class QLearner:
         cfg, plan = self.cfg, self.plan
         st, tt = self.model._eng, self.target_net._eng
         C, A = plan.num_classes, plan.action_dim
-        self.opt.grad_arena.zero_()
-        self.loss.zero_()
+        ops.zero_(self.opt.grad_arena)
+        ops.zero_(self.loss)
         # online net on [s ; s'] in one 2B forward (activations of the s half feed the backward),
         # target net on s' (nothing kept)
         B = self.B

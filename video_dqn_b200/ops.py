@@ -60,6 +60,13 @@ def num_sms() -> int:
     return _NUM_SMS
 
 
+def zero_(t):
+    """t <- 0 through cudaMemsetAsync on the current stream (no kernel launch)."""
+    _req(t.is_cuda and t.is_contiguous(), "zero_: contiguous CUDA tensor")
+    L.check(L.load().vdqn_zero(t.data_ptr(), t.numel() * t.element_size(), L.stream_ptr()), "zero")
+    return t
+
+
 def conv_out_hw(H, W, R, S, stride, pad_lo, pad_hi, dil=1):
     return ((H + pad_lo + pad_hi - (R - 1) * dil - 1) // stride + 1,
             (W + pad_lo + pad_hi - (S - 1) * dil - 1) // stride + 1)
