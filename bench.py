@@ -488,6 +488,28 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return t.item()
 
+    # ---------------- N > 1: every rank's step time WITHOUT the exchange (its own GPU at its own clocks).  A
+    # data-parallel step ends when the slowest rank is done: t(rank 0) / max_r t(r) bounds the weak-scaling
+    # efficiency whatever the exchange costs (B200s under a power cap differ by a few percent).
+    local_ms = None
+    if world > 1:
+        sync, learner.grad_sync = learner.grad_sync, None
+        for i in range(4):
+            learner.load_batch(pool[i % len(pool)]); learner.step()
+        torch.cuda.synchronize(); dist.barrier()
+        l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0.record()
+        for i in range(20):
+            learner.load_batch(pool[i % len(pool)]); learner.step()
+        l1.record(); torch.cuda.synchronize()
+        mine = torch.tensor([l0.elapsed_time(l1) / 20], device=dev, dtype=torch.float64)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        local_ms = [round(float(t.item()), 4) for t in allr]
+        learner.grad_sync = sync
+        learner._graphs.clear()               # the captured step had no exchange in it: capture again
+        learner._eager_steps = 0
+
     # ---------------- device-resident timing ("value")
     sampler = ClockSampler(local)
     sampler.start()
@@ -711,7 +733,10 @@ def main():
             "loss": loss_dev,
             "clocks": clocks, "gpu_launches": (per_step_launches or 0) * a.steps,
             "gpu_launches_per_step": per_step_launches,
-            "dp_check": dpc, "grad_exchange": dp_kind, "e2e": e2e, "roofline": roof, "roofline_kernels": roof_other, "cpu_baseline": cpu,
+            "dp_check": dpc, "grad_exchange": dp_kind,
+            "per_rank_ms_without_exchange": local_ms,
+            "slowest_rank_bound_on_efficiency": (min(local_ms) / max(local_ms)) if local_ms else None,
+            "e2e": e2e, "roofline": roof, "roofline_kernels": roof_other, "cpu_baseline": cpu,
             "breakdown_eager_ms": breakdown if rank == 0 else None,
             "inference": inference, "inverse_model": inverse, "basic_architecture": basic,
         }
