@@ -12,6 +12,8 @@
 // so shifted starts and a non-1024B pitch read exactly what TMA wrote (verified on hardware by
 // tools/umma_probe.cu).  The whole filter (<= 72 KB) stays resident in shared memory for the
 // lifetime of the persistent CTA.  L2->SM traffic per layer1 conv drops 1.39 GB -> ~0.15 GB.
+#include <cstdlib>
+
 #include "epilogue.cuh"
 #include "ptx.cuh"
 #include "vdqn_internal.h"
@@ -24,6 +26,7 @@ struct HaloArgs {
   int R, S, pad_lo;
   int tiles_w, tiles_h, num_tiles;
   int fast;            // staged TMA epilogue (bf16 compact output)
+  int stages;          // 64-channel variants: halo-window stages of this launch (HaloCfg::stages_for)
   const __nv_bfloat16* x;   // input tensor (the 16-channel variant gathers it with cp.async)
   // dual-network launch: tiles [split_tile, num_tiles) (images >= split_n) use the second filter;
   // CTAs [0, split_cta) work on the first range, the rest on the second (split_cta == 0: off)
@@ -85,6 +88,19 @@ struct HaloCfg {
   static constexpr int OUT_BUFS = (CK == 64 && !PAIR) ? 1 : 2;
   static constexpr int EPI_WARP_BYTES = (OUT_BUFS + 4) * 2048;
   static constexpr int EPI_BYTES = POOL ? 3 * POOL_BUF_BYTES : EPI_WARPS * EPI_WARP_BYTES;
+  // 64-channel variants: shared memory is split AT LAUNCH between halo-window stages and epilogue staging (as
+  // in the im2col kernel): a launch reserves the out tiles and two prefetch sets of only the inputs it has, the
+  // rest becomes stages.  Role profile with the fixed 3 stages: the MMA warp waited 350 of 1750 cycles per tile
+  // for windows while the producer waited 1200 for a free stage.  Pair: 6 / 5 / 4 stages for 0 / 1 / 2 inputs.
+  static constexpr int MAX_STAGES = (CK == 64) ? 6 : STAGES;
+  static constexpr int SMEM_LAYOUT = (CK == 64) ? 225 * 1024 : W_BYTES + STAGES * STAGE_BYTES + EPI_BYTES;
+  __host__ __device__ static constexpr int epi_warp_bytes(int n_in) { return (OUT_BUFS + 2 * n_in) * 2048; }
+  __host__ __device__ static constexpr int stages_for(int n_in) {
+    return CK != 64 ? STAGES
+           : (SMEM_LAYOUT - W_BYTES - EPI_WARPS * epi_warp_bytes(n_in)) / STAGE_BYTES > MAX_STAGES
+               ? MAX_STAGES
+               : (SMEM_LAYOUT - W_BYTES - EPI_WARPS * epi_warp_bytes(n_in)) / STAGE_BYTES;
+  }
   // 12 warps = 384 threads: the register file then allows 168 registers per thread (416 threads were
   // compiled against the 512-thread limit of 128 and spilled)
   static constexpr int PROD_WARPS = 3;
@@ -92,7 +108,7 @@ struct HaloCfg {
   // POOL: four more warps do the pooling, so a tile's pooling overlaps the next tile's TMEM drain
   static constexpr int POOL_WARPS = POOL ? 4 : 0;
   static constexpr int THREADS = (PROD_WARPS + 1 + EPI_WARPS + POOL_WARPS) * 32;
-  static constexpr int SMEM_BYTES = W_BYTES + STAGES * STAGE_BYTES + EPI_BYTES + 1024 + 512;
+  static constexpr int SMEM_BYTES = SMEM_LAYOUT + 1024 + 512;
   // accumulator ring: with 64-column accumulators TMEM holds 4 of them, so the MMA warp can run up to
   // 4 tiles ahead of the epilogue and the mbarrier hand-off latencies (MMA -> epilogue -> MMA) overlap
   static constexpr int NACC = 4;
@@ -120,13 +136,14 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sW = smem_base;
   const uint32_t sA0 = smem_base + Cfg::W_BYTES;
-  const uint32_t epi_base = sA0 + Cfg::STAGES * Cfg::STAGE_BYTES;
-  const uint32_t bar_base = epi_base + Cfg::EPI_BYTES;
+  const int nstages = CK == 64 ? a.stages : Cfg::STAGES;      // halo-window stages of this launch
+  const uint32_t epi_base = sA0 + nstages * Cfg::STAGE_BYTES;
+  const uint32_t bar_base = smem_base + Cfg::SMEM_LAYOUT;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::STAGES + s); };
-  auto tfull_bar = [&](int i) { return bar_base + 8u * (2 * Cfg::STAGES + i); };
-  auto tempty_bar = [&](int i) { return bar_base + 8u * (2 * Cfg::STAGES + Cfg::NACC + i); };
-  const uint32_t w_bar = bar_base + 8u * (2 * Cfg::STAGES + 2 * Cfg::NACC);
+  auto empty_bar = [&](int s) { return bar_base + 8u * (Cfg::MAX_STAGES + s); };
+  auto tfull_bar = [&](int i) { return bar_base + 8u * (2 * Cfg::MAX_STAGES + i); };
+  auto tempty_bar = [&](int i) { return bar_base + 8u * (2 * Cfg::MAX_STAGES + Cfg::NACC + i); };
+  const uint32_t w_bar = bar_base + 8u * (2 * Cfg::MAX_STAGES + 2 * Cfg::NACC);
   const uint32_t ld_bar0 = w_bar + 8u;                                  // one barrier per epilogue warp
   const uint32_t tmem_slot = w_bar + 8u * (1 + 2 * Cfg::EPI_WARPS);
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
@@ -139,7 +156,7 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmW);
-    for (int s = 0; s < Cfg::STAGES; ++s) {
+    for (int s = 0; s < Cfg::MAX_STAGES; ++s) {
       mbar_init(full_bar(s), CK == 16 ? 32 : 1);     // cp.async variant: every producer lane arrives
       mbar_init(empty_bar(s), 1);
     }
@@ -350,7 +367,7 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           }
         }
         __syncwarp();
-        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+        if (++stage == nstages) { stage = 0; phase ^= 1; }
       }
       PROF_END(0)
     }
@@ -398,7 +415,7 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         }
       }
       __syncwarp();
-      if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+      if (++stage == nstages) { stage = 0; phase ^= 1; }
     }
     PROF_END(4)
   } else if (POOL && warp >= Cfg::MMA_WARP + 1 + Cfg::EPI_WARPS) {
@@ -530,8 +547,13 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     const int half = ew >> 2;                 // its 32 output columns: [half*32, half*32 + 32)
     const int row = quad * 32 + lane;
     const int g = row >> 3, j = row & 7;
-    const uint32_t stg_out0 = epi_base + ew * Cfg::EPI_WARP_BYTES;
-    const uint32_t stg_in0 = stg_out0 + Cfg::OUT_BUFS * 2048;   // input set s: residual at +s*4096, mask at +s*4096 + 2048
+    // per-warp staging of this launch: OUT_BUFS out tiles, then two prefetch sets of [residual][mask] with absent
+    // inputs taking no room (64-channel variants; the stem keeps the fixed layout)
+    const int n_in = CK == 64 ? (a.fast ? (a.epi.residual != nullptr ? 1 : 0) + (a.epi.mask_src != nullptr ? 1 : 0) : 0) : 2;
+    const uint32_t set_bytes = (uint32_t)n_in * 2048u;
+    const uint32_t mask_off = (CK != 64 || a.epi.residual != nullptr) ? 2048u : 0u;
+    const uint32_t stg_out0 = epi_base + ew * (uint32_t)Cfg::epi_warp_bytes(n_in);
+    const uint32_t stg_in0 = stg_out0 + Cfg::OUT_BUFS * 2048;   // input set s at + s * set_bytes: residual, then mask
     const uint32_t ld_bar = ld_bar0 + 16u * ew;        // two barriers, one per input set
     const int c0 = half * 32;
     EpiArgs epi = a.epi;
@@ -568,10 +590,10 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       // enough -- the role profile showed 600-800 cycles per tile waiting for these loads).
       auto issue_inputs = [&](const TileIt& c, int set) {
         if (elect_one()) {
-          const uint32_t bar = ld_bar + 8u * set, dst = stg_in0 + (uint32_t)set * 4096u;
+          const uint32_t bar = ld_bar + 8u * set, dst = stg_in0 + (uint32_t)set * set_bytes;
           mbar_expect_tx(bar, (has_res ? 2048u : 0u) + (has_mask ? 2048u : 0u));
           if (has_res) tma_load_4d(dst, &tmRes, bar, c0, c.tw * Cfg::TW, c.th * Cfg::TH + 4 * quad, c.n);
-          if (has_mask) tma_load_4d(dst + 2048, &tmMask, bar, c0, c.tw * Cfg::TW, c.th * Cfg::TH + 4 * quad, c.n);
+          if (has_mask) tma_load_4d(dst + mask_off, &tmMask, bar, c0, c.tw * Cfg::TW, c.th * Cfg::TH + 4 * quad, c.n);
         }
         __syncwarp();
       };
@@ -597,7 +619,7 @@ halo_conv_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         if (a.fast) {
           const uint32_t stg_out = stg_out0 + (uint32_t)(it % Cfg::OUT_BUFS) * 2048u;
           const int set = it & 1;
-          const uint32_t stg_res = stg_in0 + (uint32_t)set * 4096u, stg_mask = stg_res + 2048u;
+          const uint32_t stg_res = stg_in0 + (uint32_t)set * set_bytes, stg_mask = stg_res + mask_off;
           PROF_WAIT_B(if (elect_one()) tma_store_wait_read<Cfg::OUT_BUFS - 1>(); __syncwarp())   // this out tile's last store has been read
           tmem_ld_wait();
           if (has_in) PROF_WAIT_B(mbar_wait(ld_bar + 8u * set, (uint32_t)(it >> 1) & 1u))
@@ -767,6 +789,11 @@ static int launch_halo(const vdqn_conv_desc* d, cudaStream_t stream) {
   }
   HaloArgs a{};
   a.fast = fast ? 1 : 0;
+  a.stages = Cfg::stages_for(fast ? (d->residual != nullptr ? 1 : 0) + (d->mask_src != nullptr ? 1 : 0) : 0);
+  {
+    static const int cap = [] { const char* e = getenv("VDQN_HALO_STAGES"); return e != nullptr ? atoi(e) : 0; }();
+    if (CK == 64 && cap >= 2 && cap < a.stages) a.stages = cap;      // (experiments)
+  }
   a.x = static_cast<const __nv_bfloat16*>(d->x);
   a.N = d->N; a.H = d->H; a.W = d->W; a.Cout = d->Cout;
   a.R = d->R; a.S = d->S; a.pad_lo = d->pad_lo;
