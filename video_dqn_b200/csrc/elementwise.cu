@@ -262,7 +262,36 @@ __device__ __forceinline__ void finalize_rows_body(const vdqn_wgrad_fin_desc& d,
   const int lane = tid / c.TX, tx = tid - lane * c.TX;
   const long plane = (long)d.Cout * d.K;
   const int cn4 = c.cn >> 2;
-  if (lane < c.TY) {
+  if (lane < c.TY && d.splits <= 2 * c.TY) {
+    // few splits (layers 3-4: 2 .. 8): one or two loads per item and lane would leave a thread with two loads in
+    // flight; take four items at a time so that up to eight are
+    for (int item0 = tx; item0 < c.items; item0 += 4 * c.TX) {
+      float4 v[4][2];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int item = item0 + u * c.TX;
+        v[u][0] = v[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (item < c.items) {
+          const int tap = item / cn4, c4 = item - tap * cn4;
+          const float* p = d.part + (long)co * d.K + (long)tap * d.Cin + ci0 + 4 * c4;
+          v[u][0] = *reinterpret_cast<const float4*>(p + (long)lane * plane);
+          if (lane + c.TY < d.splits) v[u][1] = *reinterpret_cast<const float4*>(p + (long)(lane + c.TY) * plane);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int item = item0 + u * c.TX;
+        if (item < c.items) {
+          const int tap = item / cn4, c4 = item - tap * cn4;
+          float* r = red + lane * lane_pitch + tap * pitch + 4 * c4;
+          r[0] = v[u][0].x + v[u][1].x;
+          r[1] = v[u][0].y + v[u][1].y;
+          r[2] = v[u][0].z + v[u][1].z;
+          r[3] = v[u][0].w + v[u][1].w;
+        }
+      }
+    }
+  } else if (lane < c.TY) {
     for (int item = tx; item < c.items; item += c.TX) {
       const int tap = item / cn4, c4 = item - tap * cn4;
       const float* p = d.part + (long)co * d.K + (long)tap * d.Cin + ci0 + 4 * c4;
@@ -338,10 +367,24 @@ wgrad_finalize_multi_kernel(const vdqn_wgrad_fin_item* __restrict__ items, int n
   pdl_wait();
   __shared__ float red[4608 + 160];
   __shared__ float wsum[8];
-  int lo = 0, hi = n - 1;
-  while (lo < hi) {
-    const int mid = (lo + hi + 1) >> 1;
-    if (items[mid].first_block <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+  // which tensor: the last table entry whose first block is <= this block.  Up to 32 entries: one parallel load
+  // and a ballot (a binary search is five dependent L2 round trips in front of every block's work)
+  __shared__ int s_item;
+  int lo = 0;
+  if (n <= 32) {
+    if (threadIdx.x < 32) {
+      const int fb = (int)threadIdx.x < n ? items[threadIdx.x].first_block : 0x7fffffff;
+      const unsigned m = __ballot_sync(0xffffffffu, fb <= (int)blockIdx.x);
+      if (threadIdx.x == 0) s_item = 31 - __clz(m);
+    }
+    __syncthreads();
+    lo = s_item;
+  } else {
+    int hi = n - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (items[mid].first_block <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+    }
   }
   const vdqn_wgrad_fin_item it = items[lo];
   const int b = (int)blockIdx.x - it.first_block;

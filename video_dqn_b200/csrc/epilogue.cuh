@@ -235,24 +235,13 @@ __device__ __forceinline__ float epilogue_half_staged(const EpiArgs& a, const ui
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
   }
-  if ((EPI & EPI_HAS_MASK) && a.mask_src != nullptr) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const uint4 r4 = lds128(stg_mask + row_off + ((((uint32_t)(half * 4 + j)) ^ sw) << 4));
-      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r4);
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 f = __bfloat1622float2(h[e]);
-        if (!(f.x > 0.f)) v[8 * j + 2 * e] = 0.f;
-        if (!(f.y > 0.f)) v[8 * j + 2 * e + 1] = 0.f;
-      }
-    }
-  }
   // rows outside the image / matrix are never stored (TMA clips, the LSU copies check bounds): they
-  // only have to be zero for the column sums
-  if ((EPI & EPI_HAS_COLSUM) && !valid) {
+  // only have to be zero for the column sums.  Few tiles have such rows: warp-uniform branch.
+  if ((EPI & EPI_HAS_COLSUM) && __any_sync(0xffffffffu, !valid)) {
+    if (!valid) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = 0.f;
+      for (int j = 0; j < 32; ++j) v[j] = 0.f;
+    }
   }
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -260,6 +249,15 @@ __device__ __forceinline__ float epilogue_half_staged(const EpiArgs& a, const ui
     __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
 #pragma unroll
     for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[8 * j + 2 * e], v[8 * j + 2 * e + 1]);
+    // the ReLU mask is applied to the PACKED values: one packed compare (0xFFFF per half where the stored
+    // activation is > 0) and one AND per channel pair instead of two unpacks, two compares and two selects
+    if ((EPI & EPI_HAS_MASK) && a.mask_src != nullptr) {
+      const uint4 r4 = lds128(stg_mask + row_off + ((((uint32_t)(half * 4 + j)) ^ sw) << 4));
+      const __nv_bfloat162* mh = reinterpret_cast<const __nv_bfloat162*>(&r4);
+      const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
+      pk.x &= __hgt2_mask(mh[0], zero2); pk.y &= __hgt2_mask(mh[1], zero2);
+      pk.z &= __hgt2_mask(mh[2], zero2); pk.w &= __hgt2_mask(mh[3], zero2);
+    }
     sts128(stg_out + row_off + ((((uint32_t)(half * 4 + j)) ^ sw) << 4), pk);
     if ((EPI & EPI_HAS_COLSUM) && a.colsum != nullptr) {
       // column sums use the values as stored (rounded), so d beta matches what the weight gradient consumes
