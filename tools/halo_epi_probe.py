@@ -32,7 +32,12 @@ def timed(fn, reps=20):
 w1 = rn(64, 3, 3, 64, scale=1 / 24)
 sh = torch.randn(64, device="cuda", generator=g)
 cs = torch.zeros(64, device="cuda")
+ONLY = sys.argv[1] if len(sys.argv) > 1 else None      # e.g. `dgrad_res_mask`: that variant alone, flags 0 (ncu captures)
 for N, variants in ((768, ("fwd", "fwd_res")), (256, ("dgrad_mask", "dgrad_res_mask", "plain"))):
+    if ONLY is not None:
+        variants = tuple(v for v in variants if v == ONLY)
+        if not variants:
+            continue
     # three rotating input sets: the working set stays larger than L2
     xs = [rn(N, 56, 56, 64) for _ in range(3)]
     rs = [rn(N, 56, 56, 64) for _ in range(3)]
@@ -43,7 +48,7 @@ for N, variants in ((768, ("fwd", "fwd_res")), (256, ("dgrad_mask", "dgrad_res_m
               "dgrad_mask": dict(mask_src=True, colsum=cs), "dgrad_res_mask": dict(residual=True, mask_src=True, colsum=cs),
               "plain": {}}[v]
         line = []
-        for flags in (0, 8, 32, 40):
+        for flags in ((0,) if ONLY is not None else (0, 8, 32, 40)):
             i = [0]
 
             def fn():

@@ -323,6 +323,15 @@ class Workspace:
             self._part_of: Dict[str, torch.Tensor] = {}
             self._pending: List[tuple] = []
             self._fin_tables: Dict[tuple, tuple] = {}
+            self._side = None
+
+    def side_stream(self):
+        """the stream the weight-gradient kernels run on (engine.SideStream), or None when that is switched off"""
+        if not WGRAD_SIDE:
+            return None
+        if getattr(self, "_side", None) is None:
+            self._side = SideStream(self.part.device)
+        return self._side
 
     def bwd_view(self):
         """The workspace as the backward pass sees it: activations sliced to the first n_bwd frames."""
@@ -516,6 +525,53 @@ def mlp_backward(plan: NetPlan, W: PreparedWeights, P, G, ws: Workspace, dq: tor
                         out_f32=G["top.4.weight"])])
 
 
+# Weight-gradient kernels on a second stream.  A conv's weight gradient and its data gradient both read the same
+# dy and nothing else of the backward pass depends on the weight gradient, so the two chains -- data gradients
+# on the main stream, weight gradients on the side stream -- only meet at the split reduction.  Every kernel is
+# persistent with one CTA per SM, so two of them never share an SM; what the second stream buys is that the CTAs
+# of the next runnable kernel take over each SM the moment a CTA of the running one exits, instead of all SMs
+# waiting for the slowest CTA at every kernel boundary (data gradients of layers 3-4 at B = 256 are 5.3 and
+# 2.65 rounds of tiles per CTA pair: 12 % of their time is such a tail) and then for the next launch.
+WGRAD_SIDE = _os.environ.get("VDQN_WGRAD_SIDE", "1") != "0"
+
+
+class SideStream:
+    """Runs closures on a second stream after everything enqueued on the current one, and keeps, per buffer, the
+    event of the last side kernel that reads it so that the main stream can wait before overwriting it."""
+
+    def __init__(self, device, priority: int = 0):
+        self.stream = torch.cuda.Stream(device=device, priority=priority)
+        self._readers: Dict[int, torch.cuda.Event] = {}
+        self._last = None
+
+    def run(self, fn, reads=()):
+        if not WGRAD_SIDE or ops.PROFILE is not None:       # (per-kernel timing wants the kernels one after another)
+            fn()
+            return
+        main = torch.cuda.current_stream()
+        ready = torch.cuda.Event()
+        ready.record(main)
+        self.stream.wait_event(ready)
+        with torch.cuda.stream(self.stream):
+            fn()
+            done = torch.cuda.Event()
+            done.record(self.stream)
+        for t in reads:
+            self._readers[t.data_ptr()] = done
+        self._last = done
+
+    def before_write(self, t):
+        ev = self._readers.pop(t.data_ptr(), None)
+        if ev is not None:
+            torch.cuda.current_stream().wait_event(ev)
+
+    def join(self):
+        if self._last is not None:
+            torch.cuda.current_stream().wait_event(self._last)
+            self._last = None
+        self._readers.clear()
+
+
 def _wgrad(plan, P, G, ws: Workspace, c: ConvSpec, x, dy, dbeta_key: Optional[str]):
     splits = wgrad_splits(c, ws.n)
     defer = ws.defer_fin and c.kmap == 0
@@ -526,21 +582,33 @@ def _wgrad(plan, P, G, ws: Workspace, c: ConvSpec, x, dy, dbeta_key: Optional[st
                                                      dtype=torch.float32)
     else:
         part = ws.part[: splits * c.cout * c.K]
-    ops.conv_wgrad(x, dy, c.k, c.k, c.stride, c.pad_lo, c.pad_hi, splits=splits, part=part,
-                   algo=2 if wgrad_uses_halo(c) else 0)
     kw = {}
     if c.bn is not None:
         kw = dict(gamma=P[c.bn + ".weight"], var=P[c.bn + ".running_var"], mean=P[c.bn + ".running_mean"],
                   dbeta=G[c.bn + ".bias"], dgamma=G[c.bn + ".weight"])
     args = dict(splits=splits, Cout=c.cout, Cin=c.gemm_cin, R=c.k, S=c.k, K=c.K, kmap=c.kmap, eps=BN_EPS, **kw)
+
+    def launch():
+        ops.conv_wgrad(x, dy, c.k, c.k, c.stride, c.pad_lo, c.pad_hi, splits=splits, part=part,
+                       algo=2 if wgrad_uses_halo(c) else 0)
+        if not defer:
+            # (the shared partial buffer and the reduction stay in the order of the stream the kernels run on)
+            ops.wgrad_finalize(part, P[c.wkey], G[c.wkey], **args)
+
+    side = ws.side_stream()
+    if side is not None:
+        side.run(launch, reads=(dy,))
+    else:
+        launch()
     if defer:
         ws._pending.append((c.name, part, P[c.wkey], G[c.wkey], args))
-    else:
-        ops.wgrad_finalize(part, P[c.wkey], G[c.wkey], **args)
 
 
 def _flush_finalize(ws: Workspace):
     """reduce the split partials of every weight gradient enqueued since the last flush: one launch"""
+    side = ws.side_stream()
+    if side is not None:
+        side.join()                      # every weight gradient enqueued so far (and its readers) is accounted for
     if not ws._pending:
         return
     key = tuple((nm, w.data_ptr(), dw.data_ptr(), args["splits"]) for nm, _, w, dw, args in ws._pending)
@@ -569,6 +637,13 @@ def backward(plan: NetPlan, W: PreparedWeights, P: Dict[str, torch.Tensor], G: D
                 return                   # this exchange does not act on the stage: no reduction needed yet
             _flush_finalize(ws)          # the stage's gradients are complete only once its reductions ran
             on_grads_ready(stage)
+    side = ws.side_stream()
+
+    def guard(t):
+        """the main stream is about to overwrite `t`: wait for the weight-gradient kernels still reading it"""
+        if side is not None:
+            side.before_write(t)
+        return t
     # ---- Q-head MLP + the head conv's dy (ws.dh)
     mlp_backward(plan, W, P, G, ws, dq)
     last = plan.blocks[-1]
@@ -577,7 +652,7 @@ def backward(plan: NetPlan, W: PreparedWeights, P: Dict[str, torch.Tensor], G: D
     ci = 0
     cur = ws.dy_out[last.out_hw][ci]
     ops.conv_gemm(ws.dh, W.w_dgrad["head"], 1, 2, 2, mask_src=x_head, colsum=G[last.conv2.bn + ".bias"],
-                  out=cur)
+                  out=guard(cur))
     notify("head")
     # ---- residual blocks, last to first.  `cur` = d loss / d (block output), already masked by
     # the block's final ReLU; its column sums are already accumulated in G[bn2.bias].
@@ -590,7 +665,7 @@ def backward(plan: NetPlan, W: PreparedWeights, P: Dict[str, torch.Tensor], G: D
             G[b.ds.bn + ".bias"].copy_(G[b.conv2.bn + ".bias"])
         # conv2: weight gradient, then data gradient masked by relu(bn1(conv1))
         _wgrad(plan, P, G, ws, b.conv2, ws.a1[i], cur, None)
-        dy_a1 = ws.dy_a1[b.out_hw]
+        dy_a1 = guard(ws.dy_a1[b.out_hw])
         ops.conv_gemm(cur, W.w_dgrad[b.conv2.name], 1, 1, 1, mask_src=ws.a1[i],
                       colsum=G[b.conv1.bn + ".bias"], out=dy_a1,
                       tile_n=_dgrad_tile_n(b.cout))
@@ -615,6 +690,7 @@ def backward(plan: NetPlan, W: PreparedWeights, P: Dict[str, torch.Tensor], G: D
             colsum, mask = G[prev.conv2.bn + ".bias"], x_in
         else:
             ni, dst, colsum, mask = 0, ws.dy_p, None, None
+        guard(dst)
         if b.stride == 2 and W.fuse_ds:
             # strided data gradient + downsample data gradient as ONE dense GEMM: 2x2 window over dy_a1 with the
             # four output-parity classes as column groups (taps a class does not use are zero columns: 16/9 of
@@ -636,7 +712,7 @@ def backward(plan: NetPlan, W: PreparedWeights, P: Dict[str, torch.Tensor], G: D
         notify(b.conv1.name)
         cur, ci = dst, ni
     # ---- max-pool + stem
-    ops.maxpool_bwd(ws.dy_p, ws.idx, ws.p, ws.dy_s, colsum=G[plan.stem.bn + ".bias"])
+    ops.maxpool_bwd(ws.dy_p, ws.idx, ws.p, guard(ws.dy_s), colsum=G[plan.stem.bn + ".bias"])
     _wgrad(plan, P, G, ws, plan.stem, ws.xp, ws.dy_s, None)
     _flush_finalize(ws)
     notify("stem")
