@@ -19,6 +19,8 @@
 //               store, optional stride-2 scatter (zero-dilated gradient for strided dgrad).
 #include <stdlib.h>
 
+#include <cstdlib>
+
 #include "epilogue.cuh"
 #include "ptx.cuh"
 #include "vdqn_internal.h"
@@ -35,6 +37,7 @@ struct IgemmArgs {
   int off_h, off_w;
   int scatter_inputs; // residual / mask indexed by the scattered pixel
   int fast;           // staged TMA epilogue (BN <= 128, bf16 compact output)
+  int direct_pre;     // BN = 256: direct epilogue with residual / mask rows loaded one chunk ahead (bf16 compact output)
   // dual-network launch: m-tiles [split_m_tile, num_m_tiles) use the second weight set; CTAs
   // [0, split_cta) work on the first range, the rest on the second (split_cta == 0: off)
   int split_m_tile, split_cta;
@@ -410,6 +413,15 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       __syncwarp();
     };
     if (fast && has_in && tile0 < num_tiles) issue_inputs(tile0);
+    EpiRegs pre;
+    if constexpr (!Cfg::FAST_EPI) {
+      if (a.direct_pre && tile0 < num_tiles) {
+        int n0, m0;
+        tile_mn(tile0, n0, m0);
+        const long mrow = (long)m0 * Cfg::BM + row;
+        epilogue_load_regs<EPI>(epi, mrow < a.M_total, mrow, n0 * BN + half * 32, pre);
+      }
+    }
     int it = 0;
     PROF_BEGIN
     for (int t = tile0; t < num_tiles; t += tstep, ++it) {
@@ -481,6 +493,38 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         __syncwarp();
         continue;
       }
+      if constexpr (!Cfg::FAST_EPI) {
+        if (a.direct_pre) {
+          // inputs of chunk ci were loaded while chunk ci - 1 (or the previous tile's last chunk) was processed
+          mbar_wait(tfull_bar(acc), acc_phase);
+          tc_fence_after();
+#pragma unroll
+          for (int ci = 0; ci < NCH; ++ci) {
+            const int chunk = half + 2 * ci;
+            uint32_t raw[32];
+            tmem_ld_32x32(tmem_base + acc * BN + chunk * 32 + ((uint32_t)(quad * 32) << 16), raw);
+            EpiRegs nxt;
+            if (ci + 1 < NCH) {
+              epilogue_load_regs<EPI>(epi, valid, (long)m, n_t * BN + (chunk + 2) * 32, nxt);
+            } else if (t + tstep < num_tiles) {
+              int n2, m2;
+              tile_mn(t + tstep, n2, m2);
+              const long mrow = (long)m2 * Cfg::BM + row;
+              epilogue_load_regs<EPI>(epi, mrow < a.M_total, mrow, n2 * BN + half * 32, nxt);
+            }
+            tmem_ld_wait();
+            const float cs = epilogue_chunk_regs<EPI>(epi, raw, valid, (long)m, n_t * BN + chunk * 32, lane, pre);
+            pre = nxt;
+#pragma unroll
+            for (int i = 0; i < NCH; ++i)
+              if (i == ci) csum[i] += cs;
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) release_acc(acc);
+          continue;
+        }
+      }
       long opix = m;
       long opix2 = 0;
       if (a.out_scatter == 2 || a.epi.out2 != nullptr) {
@@ -513,7 +557,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     flush_colsum();
     };
     if constexpr (Cfg::FAST_EPI) epi_dispatch(fast ? epi_mode(epi) : EPI_HAS_ALL, epi_loop);
-    else epi_loop(EpiMode<EPI_HAS_ALL>{});
+    else epi_dispatch(a.direct_pre ? epi_mode(epi) : EPI_HAS_ALL, epi_loop);
     if (fast) {
       if (elect_one()) tma_store_wait<0>();
       __syncwarp();
@@ -656,6 +700,10 @@ extern "C" int vdqn_conv_gemm(const vdqn_conv_desc* d, void* stream_v) {
   // 32 channels x 32 pixels (64-byte rows)
   CUtensorMap epi_maps[4] = {tmB, tmB, tmB, tmA};
   a.fast = (BN <= 128 && fast_epilogue_ok(d)) ? 1 : 0;
+  {
+    static const bool pre_on = [] { const char* e = getenv("VDQN_DIRECT_PRE"); return e == nullptr || atoi(e) != 0; }();
+    a.direct_pre = (pre_on && BN == 256 && d->out_scatter <= 1 && !(d->flags & VDQN_EPI_SCATTER_INPUTS) && fast_epilogue_ok(d)) ? 1 : 0;
+  }
   if (d->out_scatter == 3 && !a.fast)
     return set_error(VDQN_ERR_SHAPE, "conv_gemm: 2x2-block scatter needs the staged epilogue (bf16 output, tile <= 128)");
   if (seg2) {

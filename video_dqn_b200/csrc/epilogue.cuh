@@ -280,6 +280,93 @@ __device__ __forceinline__ float epilogue_half_staged(const EpiArgs& a, const ui
   return 0.f;
 }
 
+// Direct epilogue with its inputs already in registers (BN = 256 tiles, whose shared memory all goes to the
+// pipeline): the caller loads a chunk's residual / mask rows (64 bytes per lane each) one chunk AHEAD, so the
+// global-load latency that the plain direct epilogue exposes per chunk (role profile: 23.7 k cycles per
+// 128 x 256 tile against 18.4 k of MMA issue) overlaps the previous chunk's math.  bf16 compact output only.
+struct EpiRegs {
+  uint4 res[4], mask[4];
+};
+
+template <int EPI>
+__device__ __forceinline__ void epilogue_load_regs(const EpiArgs& a, bool valid, long m, int c0, EpiRegs& r) {
+  if ((EPI & EPI_HAS_RES) && a.residual != nullptr) {
+    const uint4* rp = reinterpret_cast<const uint4*>(a.residual + m * a.ldr + c0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) r.res[j] = valid ? __ldg(rp + j) : make_uint4(0u, 0u, 0u, 0u);
+  }
+  if ((EPI & EPI_HAS_MASK) && a.mask_src != nullptr) {
+    const uint4* mp = reinterpret_cast<const uint4*>(a.mask_src + m * a.ldm + c0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) r.mask[j] = valid ? __ldg(mp + j) : make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
+template <int EPI>
+__device__ __forceinline__ float epilogue_chunk_regs(const EpiArgs& a, const uint32_t (&raw)[32], bool valid,
+                                                     long opix, int c0, int lane, const EpiRegs& r) {
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+  if ((EPI & EPI_HAS_SHIFT_RELU) && a.shift != nullptr) {
+    const float4* sp = reinterpret_cast<const float4*>(a.shift + c0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 s4 = __ldg(sp + j);
+      v[4 * j + 0] += s4.x; v[4 * j + 1] += s4.y; v[4 * j + 2] += s4.z; v[4 * j + 3] += s4.w;
+    }
+  }
+  if ((EPI & EPI_HAS_RES) && a.residual != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&r.res[j]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __bfloat1622float2(h[e]);
+        v[8 * j + 2 * e] += f.x;
+        v[8 * j + 2 * e + 1] += f.y;
+      }
+    }
+  }
+  if ((EPI & EPI_HAS_SHIFT_RELU) && (a.flags & VDQN_EPI_RELU)) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+  }
+  uint4 pk[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk[j]);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(v[8 * j + 2 * e], v[8 * j + 2 * e + 1]);
+    if ((EPI & EPI_HAS_MASK) && a.mask_src != nullptr) {
+      const __nv_bfloat162* mh = reinterpret_cast<const __nv_bfloat162*>(&r.mask[j]);
+      const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
+      pk[j].x &= __hgt2_mask(mh[0], zero2); pk[j].y &= __hgt2_mask(mh[1], zero2);
+      pk[j].z &= __hgt2_mask(mh[2], zero2); pk[j].w &= __hgt2_mask(mh[3], zero2);
+    }
+  }
+  if (valid) {
+    uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(a.out) + opix * a.ldc + c0);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) op[j] = pk[j];
+  }
+  if ((EPI & EPI_HAS_COLSUM) && a.colsum != nullptr) {
+    // the values as stored (rounded); rows outside the matrix contribute nothing
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pk[j]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __bfloat1622float2(h[e]);
+        v[8 * j + 2 * e] = valid ? f.x : 0.f;
+        v[8 * j + 2 * e + 1] = valid ? f.y : 0.f;
+      }
+    }
+    return warp_transpose_reduce(v, lane);
+  }
+  return 0.f;
+}
+
 // bf16 output: the staged epilogue applies -- to a compact destination through TMA, to a
 // zero-dilated (scatter) destination through per-row LSU copies, provided residual / mask are
 // indexed by the scattered pixel as well (or absent)
