@@ -6,6 +6,7 @@
 #include "vdqn_internal.h"
 
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include <cstdint>
 #include <cstdlib>
@@ -554,96 +555,122 @@ __global__ void __launch_bounds__(256, 6) maxpool_fwd_kernel(const __nv_bfloat16
 // dy, pooled y); a window's gradient goes to the pixel whose slot matches.  The stem ReLU mask is
 // taken from the POOLED output y (the arg-max element is > 0 exactly when the window maximum is), so
 // the 4x larger pre-pool activation is not re-read.  Accumulates per-channel sums (d beta of bn1).
+// A block walks pooled rows (n, i); its threads are the (j, channel group) items of a row, so no thread
+// divides per item (ncu of the flat-index version: 590 instructions per item, issue slots 69 % busy at 46 %
+// of DRAM bandwidth -- three 32-bit and one 64-bit runtime division and the emulated byte compare
+// __vcmpeq4 were two thirds of them).
 __global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const uint8_t* __restrict__ idx,
                                    const __nv_bfloat16* __restrict__ y, __nv_bfloat16* __restrict__ dx,
                                    float* __restrict__ colsum, int N, int H, int W, int C) {
   pdl_launch_dependents();
   pdl_wait();
   const int Ho = H / 2, Wo = W / 2, CG = C / 8;      // H, W even: 3x3/2/1 pooling halves them
-  const long total = (long)N * Ho * Wo * CG;
+  const int rows = N * Ho, items = Wo * CG;
   float acc[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-  const int cg = threadIdx.x % CG;                  // blockDim.x and the grid stride are multiples of CG
-  const int per_img = Ho * Wo * CG;
   const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
-  for (long t0 = blockIdx.x * (long)blockDim.x + threadIdx.x; t0 < total; t0 += (long)gridDim.x * blockDim.x) {
-    const int n = (int)(t0 / per_img);
-    int t = (int)(t0 - (long)n * per_img) / CG;
-    const int j = t % Wo;
-    const int i = t / Wo;
-    // masked window gradients gw[a][b] for windows (i+a, j+b) and their arg-max slots.  All twelve
-    // loads are issued first, from clamped addresses (no branch in between); windows outside the
-    // image are neutralised afterwards.
-    uint32_t gw[2][2][4];
-    uint2 sl[2][2];
-    uint4 gr[2][2], yr[2][2];
+  // this thread's items of a row: it0, it0 + blockDim.x, ...  (blockDim.x is a multiple of CG: the channel
+  // group is the same for all of them)
+  const int j0 = (int)threadIdx.x / CG, cg = (int)threadIdx.x - j0 * CG, dj = (int)blockDim.x / CG;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int n = row / Ho, i = row - n * Ho;
+    const int i1 = min(i + 1, Ho - 1);
+    const long in0 = ((long)n * Ho + i) * Wo * C, in1 = ((long)n * Ho + i1) * Wo * C;   // pooled rows i, i+1
+    const long out0 = ((long)n * H + 2 * i) * W * C;                                    // input row 2i
+    const bool row1_in = i + 1 < Ho;
+    for (int j = j0; j < Wo; j += dj) {
+      // masked window gradients gw[a][b] for windows (i+a, j+b) and their arg-max slots.  All twelve
+      // loads are issued first, from clamped addresses (no branch in between); windows outside the
+      // image are neutralised afterwards.
+      uint32_t gw[2][2][4];
+      uint2 sl[2][2];
+      uint4 gr[2][2], yr[2][2];
+      const int jj1 = min(j + 1, Wo - 1);
 #pragma unroll
-    for (int a = 0; a < 2; ++a)
+      for (int a = 0; a < 2; ++a)
 #pragma unroll
-      for (int b = 0; b < 2; ++b) {
-        const int ii = min(i + a, Ho - 1), jj = min(j + b, Wo - 1);
-        const long o = (((long)n * Ho + ii) * Wo + jj) * C + cg * 8;
-        sl[a][b] = __ldg(reinterpret_cast<const uint2*>(idx + o));
-        gr[a][b] = __ldg(reinterpret_cast<const uint4*>(dy + o));
-        yr[a][b] = __ldg(reinterpret_cast<const uint4*>(y + o));
-      }
-#pragma unroll
-    for (int a = 0; a < 2; ++a)
-#pragma unroll
-      for (int b = 0; b < 2; ++b) {
-        const bool in = (i + a < Ho) && (j + b < Wo);
-        const uint32_t gv[4] = {gr[a][b].x, gr[a][b].y, gr[a][b].z, gr[a][b].w};
-        const uint32_t yv[4] = {yr[a][b].x, yr[a][b].y, yr[a][b].z, yr[a][b].w};
-        if (!in) sl[a][b] = make_uint2(0xffffffffu, 0xffffffffu);      // slot 255 never matches
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-          gw[a][b][e] = in ? (gv[e] & __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&yv[e]), zero2)) : 0u;
-      }
-    // out[ph][pw] for input pixel (2i+ph, 2j+pw): window (i+a, j+b) reaches it through slot
-    // r*3+s with r = ph - 2a + 1, s = pw - 2b + 1 (valid when 0 <= r,s <= 2)
-#pragma unroll
-    for (int ph = 0; ph < 2; ++ph)
-#pragma unroll
-      for (int pw = 0; pw < 2; ++pw) {
-        uint32_t o2[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-        for (int a = 0; a < 2; ++a)
-#pragma unroll
-          for (int b = 0; b < 2; ++b) {
-            const int r = ph - 2 * a + 1, sx = pw - 2 * b + 1;
-            if (r < 0 || r > 2 || sx < 0 || sx > 2) continue;
-            const uint32_t want4 = (uint32_t)(r * 3 + sx) * 0x01010101u;
-            const uint32_t m_lo = __vcmpeq4(sl[a][b].x, want4), m_hi = __vcmpeq4(sl[a][b].y, want4);
-            const uint32_t m[4] = {__byte_perm(m_lo, 0, 0x1100), __byte_perm(m_lo, 0, 0x3322),
-                                   __byte_perm(m_hi, 0, 0x1100), __byte_perm(m_hi, 0, 0x3322)};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const uint32_t v = gw[a][b][e] & m[e];
-              const __nv_bfloat162 sum = __hadd2(*reinterpret_cast<const __nv_bfloat162*>(&o2[e]),
-                                                 *reinterpret_cast<const __nv_bfloat162*>(&v));
-              o2[e] = *reinterpret_cast<const uint32_t*>(&sum);
-            }
-          }
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&o2[e]));
-          acc[2 * e] += f.x;
-          acc[2 * e + 1] += f.y;
+        for (int b = 0; b < 2; ++b) {
+          const long o = (a ? in1 : in0) + (long)((b ? jj1 : j) * C + cg * 8);
+          sl[a][b] = __ldg(reinterpret_cast<const uint2*>(idx + o));
+          gr[a][b] = __ldg(reinterpret_cast<const uint4*>(dy + o));
+          yr[a][b] = __ldg(reinterpret_cast<const uint4*>(y + o));
         }
-        const long op = (((long)n * H + 2 * i + ph) * W + 2 * j + pw) * C + cg * 8;
-        *reinterpret_cast<uint4*>(dx + op) = make_uint4(o2[0], o2[1], o2[2], o2[3]);
-      }
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          const bool in = (a == 0 || row1_in) && (b == 0 || j + 1 < Wo);
+          const uint32_t gv[4] = {gr[a][b].x, gr[a][b].y, gr[a][b].z, gr[a][b].w};
+          const uint32_t yv[4] = {yr[a][b].x, yr[a][b].y, yr[a][b].z, yr[a][b].w};
+          if (!in) sl[a][b] = make_uint2(0xffffffffu, 0xffffffffu);      // slot 255 never matches
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            gw[a][b][e] = in ? (gv[e] & __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&yv[e]), zero2)) : 0u;
+        }
+      // slots as 16-bit lanes next to the bf16 pairs they steer: 0x3C00 | slot, i.e. the fp16 numbers
+      // 1 + slot / 1024, so that ONE packed fp16 compare per channel pair yields the 0xFFFF / 0 lane mask
+      uint32_t s16[2][2][4];
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          s16[a][b][0] = __byte_perm(sl[a][b].x, 0x3C3C3C3Cu, 0x4140);
+          s16[a][b][1] = __byte_perm(sl[a][b].x, 0x3C3C3C3Cu, 0x4342);
+          s16[a][b][2] = __byte_perm(sl[a][b].y, 0x3C3C3C3Cu, 0x4140);
+          s16[a][b][3] = __byte_perm(sl[a][b].y, 0x3C3C3C3Cu, 0x4342);
+        }
+      // out[ph][pw] for input pixel (2i+ph, 2j+pw): window (i+a, j+b) reaches it through slot
+      // r*3+s with r = ph - 2a + 1, s = pw - 2b + 1 (valid when 0 <= r,s <= 2)
+#pragma unroll
+      for (int ph = 0; ph < 2; ++ph)
+#pragma unroll
+        for (int pw = 0; pw < 2; ++pw) {
+          uint32_t o2[4] = {0u, 0u, 0u, 0u};
+          bool first = true;
+#pragma unroll
+          for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+              const int r = ph - 2 * a + 1, sx = pw - 2 * b + 1;
+              if (r < 0 || r > 2 || sx < 0 || sx > 2) continue;
+              const uint32_t want2 = 0x3C003C00u | ((uint32_t)(r * 3 + sx) * 0x00010001u);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const uint32_t v = gw[a][b][e] & __heq2_mask(*reinterpret_cast<const __half2*>(&s16[a][b][e]),
+                                                             *reinterpret_cast<const __half2*>(&want2));
+                if (first) {
+                  o2[e] = v;
+                } else {
+                  const __nv_bfloat162 sum = __hadd2(*reinterpret_cast<const __nv_bfloat162*>(&o2[e]),
+                                                     *reinterpret_cast<const __nv_bfloat162*>(&v));
+                  o2[e] = *reinterpret_cast<const uint32_t*>(&sum);
+                }
+              }
+              first = false;
+            }
+          // column sums of the values as stored (a pixel that is the arg-max of several windows holds their
+          // bf16 sum)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&o2[e]));
+            acc[2 * e] += f.x;
+            acc[2 * e + 1] += f.y;
+          }
+          const long op = out0 + (long)((ph * W + 2 * j + pw) * C + cg * 8);
+          *reinterpret_cast<uint4*>(dx + op) = make_uint4(o2[0], o2[1], o2[2], o2[3]);
+        }
+    }
   }
   if (colsum != nullptr) {
     extern __shared__ float sm[];      // [blockDim.x][8]
 #pragma unroll
     for (int e = 0; e < 8; ++e) sm[threadIdx.x * 8 + e] = acc[e];
     __syncthreads();
-    if (threadIdx.x < C) {
+    if ((int)threadIdx.x < C) {
       const int g0 = threadIdx.x / 8, e = threadIdx.x % 8;
       float s = 0.f;
-      for (int t = g0; t < blockDim.x; t += CG) s += sm[t * 8 + e];
+      for (int t = g0; t < (int)blockDim.x; t += CG) s += sm[t * 8 + e];
       atomicAdd(colsum + threadIdx.x, s);
     }
   }
@@ -1269,9 +1296,18 @@ extern "C" int vdqn_maxpool_bwd(const void* dy, const uint8_t* idx, const void* 
   if (C % 8 || 256 % (C / 8) || C > 256) return set_error(VDQN_ERR_SHAPE, "maxpool_bwd: unsupported C=%d", C);
   if ((H | W) & 1) return set_error(VDQN_ERR_SHAPE, "maxpool_bwd: H and W must be even");
   GET_DEV();
-  const long total = (long)N * (H / 2) * (W / 2) * (C / 8);
-  if (total == 0) return VDQN_OK;
-  launch_kernel(maxpool_bwd_kernel, grid_for(total, 256, dev->num_sms, 8), 256, 256 * 8 * sizeof(float), stream, static_cast<const __nv_bfloat16*>(dy), idx, static_cast<const __nv_bfloat16*>(y),
+  const long rows = (long)N * (H / 2);
+  if (rows == 0 || W == 0) return VDQN_OK;
+  if (rows > 0x7fffffffL) return set_error(VDQN_ERR_SHAPE, "maxpool_bwd: too many rows");
+  // a block per pooled row at a time; its threads are the row's (column, channel group) items, split evenly
+  // over the passes a block of <= 256 threads needs (W/2 = 56, C = 64: 448 items = 2 passes of 224 threads)
+  const int items = (W / 2) * (C / 8);
+  const int passes = (items + 255) / 256;
+  int threads = ((items + passes - 1) / passes + 31) / 32 * 32;
+  if (threads < C) threads = (C + 31) / 32 * 32;         // the block reduction of the column sums needs C threads
+  const long want = (long)dev->num_sms * 8;
+  const int grid = (int)(rows < want ? rows : want);
+  launch_kernel(maxpool_bwd_kernel, grid, threads, threads * 8 * sizeof(float), stream, static_cast<const __nv_bfloat16*>(dy), idx, static_cast<const __nv_bfloat16*>(y),
       static_cast<__nv_bfloat16*>(dx), colsum, N, H, W, C);
   VDQN_CHECK_LAUNCH("maxpool_bwd");
   return VDQN_OK;
