@@ -257,3 +257,44 @@ def test_confidence_reward_step():
     plain = QLearner(_build(sd, dev), _build(sd, dev), StepConfig(), batch_size=B, use_graph=False)
     with pytest.raises(ValueError, match="CONFIDENCE_REWARD"):
         plain.step([t.to(dev) for t in batch])
+
+
+@pytest.mark.parametrize("B,graph", [(8, False), (64, True)])
+def test_weight_gradients_on_the_second_stream_change_nothing(B, graph):
+    """engine.SideStream: the weight-gradient kernels run on a second stream, the data gradients on the main
+    one, with per-buffer events where the main stream overwrites a dy buffer a weight gradient still reads.
+    The gradients must be those of the single-stream order (weight gradients: bit-identical -- fixed split
+    reduction order; BatchNorm biases: fp32 atomics, 1e-5), also over repeated graph replays, where a missing
+    event would show up as a race."""
+    from video_dqn_b200 import engine as E
+    from video_dqn_b200.learner import QLearner, StepConfig
+    dev = _dev()
+    sd = qstep.init_state(seed=4, randomize_bn=True)
+    sd_t = qstep.init_state(seed=5, randomize_bn=True)
+    batch = [t.to(dev) for t in qstep.synthetic_batch(B, seed=3)]
+
+    def grads(side, repeats):
+        old = E.WGRAD_SIDE
+        E.WGRAD_SIDE = side
+        try:
+            lr = QLearner(_build(sd, dev), _build(sd_t, dev), StepConfig(), batch_size=B, use_graph=graph)
+            out = []
+            for _ in range(repeats):
+                lr.model.load_state_dict(sd)
+                lr.opt._m.flat.zero_(); lr.opt._v.flat.zero_()
+                lr.model._state()
+                lr.step(batch)
+                torch.cuda.synchronize()
+                out.append({n: g.detach().clone() for n, g in lr.G.items()})
+            return out
+        finally:
+            E.WGRAD_SIDE = old
+
+    ref = grads(False, 2)[-1]
+    for got in grads(True, 5 if graph else 2)[1:]:
+        for n, g in got.items():
+            r = ref[n]
+            if g.dim() == 4:                 # conv weights: deterministic split reduction
+                assert torch.equal(g, r), n
+            else:                            # BatchNorm / bias sums: fp32 atomics
+                assert (g - r).abs().max().item() <= 1e-5 * r.abs().max().item() + 1e-9, n
