@@ -252,10 +252,11 @@ struct FinRowCfg {
   int cn, items, TX, TY;
 };
 
-__device__ __forceinline__ void finalize_rows_body(const vdqn_wgrad_fin_desc& d, const FinRowCfg& c, int chunk,
-                                                   int co, float* red, float* wsum) {
+template <int RS_T>
+__device__ __forceinline__ void finalize_rows_body_t(const vdqn_wgrad_fin_desc& d, const FinRowCfg& c, int chunk,
+                                                     int co, float* red, float* wsum) {
   const int ci0 = chunk * c.cn;
-  const int RS = d.R * d.S;
+  const int RS = RS_T ? RS_T : d.R * d.S;            // compile-time for 3x3 / 1x1: the divisions below become multiplies
   const int E = c.cn * RS;
   const int pitch = c.cn + 1;                    // per-tap pitch in shared memory (bank spread)
   const int lane_pitch = RS * pitch;
@@ -327,13 +328,24 @@ __device__ __forceinline__ void finalize_rows_body(const vdqn_wgrad_fin_desc& d,
   }
   const long o0 = ((long)co * d.Cin + ci0) * RS;
   float dot = 0.f;
-  for (int j = tid; j < E; j += 256) {
-    const int cil = j / RS, tap = j - cil * RS;
-    const float* r = red + tap * pitch + cil;
-    float g = r[0];
-    for (int l = 1; l < c.TY; ++l) g += r[l * lane_pitch];
-    dot += __ldg(d.w + o0 + j) * g;
-    d.dw[o0 + j] = scale * g;
+  // four elements per thread and pass, their W loads issued together (one at a time, each pass waited a full
+  // memory latency: a quarter of the kernel's stall samples)
+  for (int j0 = tid; j0 < E; j0 += 1024) {
+    float wv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) wv[u] = (j0 + u * 256 < E) ? __ldg(d.w + o0 + j0 + u * 256) : 0.f;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int j = j0 + u * 256;
+      if (j < E) {
+        const int cil = j / RS, tap = j - cil * RS;
+        const float* r = red + tap * pitch + cil;
+        float g = r[0];
+        for (int l = 1; l < c.TY; ++l) g += r[l * lane_pitch];
+        dot += wv[u] * g;
+        d.dw[o0 + j] = scale * g;
+      }
+    }
   }
   if (d.dgamma != nullptr) {
     for (int off = 16; off; off >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, off);
@@ -347,6 +359,14 @@ __device__ __forceinline__ void finalize_rows_body(const vdqn_wgrad_fin_desc& d,
       atomicAdd(d.dgamma + co, v);
     }
   }
+}
+
+__device__ __forceinline__ void finalize_rows_body(const vdqn_wgrad_fin_desc& d, const FinRowCfg& c, int chunk,
+                                                   int co, float* red, float* wsum) {
+  const int RS = d.R * d.S;
+  if (RS == 9) finalize_rows_body_t<9>(d, c, chunk, co, red, wsum);
+  else if (RS == 1) finalize_rows_body_t<1>(d, c, chunk, co, red, wsum);
+  else finalize_rows_body_t<0>(d, c, chunk, co, red, wsum);
 }
 
 __global__ void __launch_bounds__(256, 5)
