@@ -102,17 +102,20 @@ __device__ __forceinline__ void weight_prep_tile(const vdqn_wprep_desc& d, int c
   const int tid = threadIdx.x;
   const float* wbase = d.w + ((long)co0 * d.Cin + ci0) * RS;
   const long co_pitch = (long)d.Cin * RS;
-  for (int e0 = 0; e0 < 32 * run; e0 += 1024) {               // 32*run is a multiple of 1024
-    float v[4];
-    int col[4], j[4];
+  // eight independent loads in flight per thread (a block is 9 passes of four otherwise, each a full memory
+  // latency: the kernel ran at a third of the HBM rate)
+  for (int e0 = 0; e0 < 32 * run; e0 += 2048) {               // 32*run is a multiple of 1024
+    float v[8];
+    int col[8], j[8];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < 8; ++u) {
       const int e = e0 + u * 256 + tid;
       col[u] = e / run; j[u] = e - col[u] * run;                // j = cil*RS + tap, contiguous in OIHW
-      v[u] = __ldg(wbase + col[u] * co_pitch + j[u]);
+      v[u] = e < 32 * run ? __ldg(wbase + col[u] * co_pitch + j[u]) : 0.f;
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) sw[col[u]][j[u]] = v[u] * sscale[col[u]];
+    for (int u = 0; u < 8; ++u)
+      if (e0 + u * 256 + tid < 32 * run) sw[col[u]][j[u]] = v[u] * sscale[col[u]];
   }
   __syncthreads();
   __nv_bfloat162* wf = reinterpret_cast<__nv_bfloat162*>(d.w_fwd);
@@ -157,10 +160,23 @@ weight_prep_tiled_kernel(const vdqn_wprep_desc* __restrict__ descs, const int* _
   pdl_wait();
   __shared__ float sw[32][32 * 9 + 1];
   __shared__ float sscale[32];
-  int lo = 0, hi = n - 1;
-  while (lo < hi) {
-    const int mid = (lo + hi + 1) >> 1;
-    if (tile_offsets[mid] <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+  // which tensor: up to 32 table entries are searched with one parallel load and a ballot
+  __shared__ int s_item;
+  int lo = 0;
+  if (n <= 32) {
+    if (threadIdx.x < 32) {
+      const int fb = (int)threadIdx.x < n ? tile_offsets[threadIdx.x] : 0x7fffffff;
+      const unsigned m = __ballot_sync(0xffffffffu, fb <= (int)blockIdx.x);
+      if (threadIdx.x == 0) s_item = 31 - __clz(m);
+    }
+    __syncthreads();
+    lo = s_item;
+  } else {
+    int hi = n - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (tile_offsets[mid] <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+    }
   }
   const vdqn_wprep_desc d = descs[lo];
   const int b = blockIdx.x - tile_offsets[lo];
