@@ -37,6 +37,7 @@ struct IgemmArgs {
   int off_h, off_w;
   int scatter_inputs; // residual / mask indexed by the scattered pixel
   int fast;           // staged TMA epilogue (BN <= 128, bf16 compact output)
+  int alias_out;      // BN = 128 staged epilogue: the out tile is written in place of the mask (else residual) tile
   int direct_pre;     // BN = 256: direct epilogue with residual / mask rows loaded one chunk ahead (bf16 compact output)
   // dual-network launch: m-tiles [split_m_tile, num_m_tiles) use the second weight set; CTAs
   // [0, split_cta) work on the first range, the rest on the second (split_cta == 0: off)
@@ -305,9 +306,14 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     // per-warp staging of this launch: [residual x NCH] [mask x NCH] [out x OUT_BUFS x NCH], absent
     // inputs take no room
     const int n_in = (a.epi.residual != nullptr ? 1 : 0) + (a.epi.mask_src != nullptr ? 1 : 0);
-    const uint32_t stg_in = epi_base + ew * (uint32_t)Cfg::epi_warp_bytes(n_in);
+    // alias_out: no out tiles of their own -- a lane overwrites the mask (else residual) row it has just consumed
+    // with its output row, and the next tile's inputs are only requested once the TMA store has read the tile.
+    // The shared memory saved becomes pipeline stages (mask only: 6 -> 8, residual + mask: 5 -> 6), which is
+    // what the 128-wide launches are short of; their long k-loops hide the later prefetch.
+    const bool alias = Cfg::FAST_EPI && a.alias_out != 0;
+    const uint32_t stg_in = epi_base + ew * (uint32_t)(alias ? n_in * NCH * 2048 : Cfg::epi_warp_bytes(n_in));
     const uint32_t stg_mask0 = stg_in + (a.epi.residual != nullptr ? NCH * 2048 : 0);
-    const uint32_t stg_out_base = stg_in + n_in * NCH * 2048;
+    const uint32_t stg_out_base = alias ? (a.epi.mask_src != nullptr ? stg_mask0 : stg_in) : stg_in + n_in * NCH * 2048;
     const uint32_t ld_bar = ld_bar0 + 8u * ew;
     EpiArgs epi = a.epi;
     if (second) epi.shift = a.shift2;
@@ -437,8 +443,10 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const int row0 = m_t * Cfg::BM + quad * 32;            // this warp's 32 output rows
         PROF_WAIT_A(mbar_wait(tfull_bar(acc), acc_phase))
         tc_fence_after();
-        const uint32_t stg = stg_out_base + (uint32_t)((it % Cfg::OUT_BUFS) * NCH) * 2048u;
-        PROF_WAIT_B(if (elect_one()) tma_store_wait_read<Cfg::OUT_BUFS - 1>(); __syncwarp())   // this out buffer's last store has been read
+        const uint32_t stg = alias ? stg_out_base : stg_out_base + (uint32_t)((it % Cfg::OUT_BUFS) * NCH) * 2048u;
+        if (!alias) {
+          PROF_WAIT_B(if (elect_one()) tma_store_wait_read<Cfg::OUT_BUFS - 1>(); __syncwarp())   // this out buffer's last store has been read
+        }
 #pragma unroll
         for (int ci = 0; ci < NCH; ++ci) {
           const int chunk = half + 2 * ci;
@@ -461,7 +469,7 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (lane == 0) release_acc(acc);
         if (has_in) {
           ld_parity ^= 1;
-          if (t + tstep < num_tiles) issue_inputs(t + tstep);
+          if (!alias && t + tstep < num_tiles) issue_inputs(t + tstep);
         }
         if (gather) {
           __syncwarp();                       // the staged tiles are complete
@@ -491,6 +499,11 @@ igemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           tma_store_commit();
         }
         __syncwarp();
+        if (alias) {
+          // the tile the store reads is the next tile's input buffer
+          PROF_WAIT_B(if (elect_one()) tma_store_wait_read<0>(); __syncwarp())
+          if (t + tstep < num_tiles) issue_inputs(t + tstep);
+        }
         continue;
       }
       if constexpr (!Cfg::FAST_EPI) {
@@ -592,6 +605,11 @@ static int launch_igemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
     attr_set = true;
   }
   a.stages = Cfg::stages_for(a.fast ? (a.epi.residual != nullptr ? 1 : 0) + (a.epi.mask_src != nullptr ? 1 : 0) : 0);
+  if (a.alias_out) {
+    const int n_in = (a.epi.residual != nullptr ? 1 : 0) + (a.epi.mask_src != nullptr ? 1 : 0);
+    const int st = (Cfg::SMEM_LAYOUT - Cfg::EPI_WARPS * n_in * Cfg::GROUPS * 2048) / Cfg::STAGE_BYTES;
+    a.stages = st > Cfg::MAX_STAGES ? Cfg::MAX_STAGES : st;
+  }
   if (!a.fast) a.stages = Cfg::SMEM_LAYOUT / Cfg::STAGE_BYTES > Cfg::MAX_STAGES ? Cfg::MAX_STAGES
                                                                                 : Cfg::SMEM_LAYOUT / Cfg::STAGE_BYTES;
   // schedule units: CTAs over tiles, or (PAIR) CTA pairs over pairs of m-tiles
@@ -703,6 +721,12 @@ extern "C" int vdqn_conv_gemm(const vdqn_conv_desc* d, void* stream_v) {
   {
     static const bool pre_on = [] { const char* e = getenv("VDQN_DIRECT_PRE"); return e == nullptr || atoi(e) != 0; }();
     a.direct_pre = (pre_on && BN == 256 && d->out_scatter <= 1 && !(d->flags & VDQN_EPI_SCATTER_INPUTS) && fast_epilogue_ok(d)) ? 1 : 0;
+  }
+  {
+    // 128-wide tiles with inputs and a k-loop long enough to hide the later prefetch (>= 9 k-blocks of 64)
+    static const bool alias_on = [] { const char* e = getenv("VDQN_ALIAS_OUT"); return e == nullptr || atoi(e) != 0; }();
+    a.alias_out = (alias_on && BN == 128 && CK == 64 && a.fast && d->out_scatter < 2 &&
+                   (d->residual != nullptr || d->mask_src != nullptr) && k_total >= 9 * 64) ? 1 : 0;
   }
   if (d->out_scatter == 3 && !a.fast)
     return set_error(VDQN_ERR_SHAPE, "conv_gemm: 2x2-block scatter needs the staged epilogue (bf16 output, tile <= 128)");
