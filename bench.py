@@ -324,29 +324,35 @@ def _inverse_block(dev):
 
 def _basic_block(dev, B):
     """Training step of the `basic` architecture (train-mode BatchNorm) at the bench batch:
-    eager launches, device-resident fp32 frames."""
+    CUDA-graph replay (and eager launches next to it), device-resident fp32 frames."""
     import torch
     from video_dqn_b200.learner import StepConfig
     from video_dqn_b200.learner_basic import BasicQLearner
     from video_dqn_b200.qnet import HabitatDQNMultiAction
-    torch.manual_seed(4)
-    nets = [HabitatDQNMultiAction(3, 5, extra_capacity=False, panorama=False).to(dev) for _ in range(2)]
-    nets[1].load_state_dict(nets[0].state_dict())
-    lr = BasicQLearner(nets[0], nets[1], StepConfig(), batch_size=B)
     batches = [[t.to(dev) for t in synthetic_quads(B, seed=50 + i, pinned=False)] for i in range(2)]
-    for i in range(3):
-        lr.step(batches[i % 2])
-    torch.cuda.synchronize()
-    iters = 10
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(iters):
-        loss = lr.step(batches[i % 2])
-    e1.record(); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / iters
-    out = {"batch": B, "ms_per_step": ms, "frames_per_sec": 2 * B / ms * 1e3, "loss": float(loss.item()),
-           "mode": "train-mode BatchNorm (batch statistics), eager launches, no CUDA graph"}
-    del lr, nets, batches
+    res = {}
+    for mode, graph in (("eager", False), ("graph", True)):
+        torch.manual_seed(4)
+        nets = [HabitatDQNMultiAction(3, 5, extra_capacity=False, panorama=False).to(dev) for _ in range(2)]
+        nets[1].load_state_dict(nets[0].state_dict())
+        lr = BasicQLearner(nets[0], nets[1], StepConfig(), batch_size=B, use_graph=graph)
+        for i in range(3):
+            lr.step(batches[i % 2])
+        torch.cuda.synchronize()
+        iters = 10
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(iters):
+            loss = lr.step(batches[i % 2])
+        e1.record(); torch.cuda.synchronize()
+        res[mode] = (e0.elapsed_time(e1) / iters, float(loss.item()))
+        del lr, nets
+        torch.cuda.empty_cache()
+    ms = res["graph"][0]
+    out = {"batch": B, "ms_per_step": ms, "frames_per_sec": 2 * B / ms * 1e3, "loss": res["graph"][1],
+           "ms_per_step_eager": res["eager"][0],
+           "mode": "train-mode BatchNorm (batch statistics), CUDA-graph replay (ms_per_step_eager: eager launches)"}
+    del batches
     torch.cuda.empty_cache()
     return out
 

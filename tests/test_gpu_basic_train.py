@@ -269,3 +269,44 @@ def test_syncbn_two_ranks_equal_one_process(tmp_path):
         na += a.pow(2).sum().item(); nb += b.pow(2).sum().item()
     assert (num / den) ** 0.5 <= 0.45, (num / den) ** 0.5       # measured 0.38 on this batch (0.29 on the fixture's)
     assert abs((na / nb) ** 0.5 - 1.0) <= 0.1, (na / nb) ** 0.5
+
+
+@pytest.mark.parametrize("nf,B", [(1, 8), (4, 4)])
+def test_basic_step_captured_in_a_graph_equals_the_eager_step(nf, B):
+    """BasicQLearner(use_graph=True): one eager step, then capture + replay.  Four steps on four different
+    batches, with a hard target sync in between (TARGET_UPDATE_INTERVAL = 3: the target module's folded
+    operands are re-derived outside the graph), against the eager learner from the same state: losses, Adam's
+    step count, num_batches_tracked, running statistics and parameters.  fp64 / fp32 atomics make the two runs
+    differ in the last bits, which bf16 rounding can amplify to ~1e-3 after four steps."""
+    from video_dqn_b200.learner import StepConfig
+    from video_dqn_b200.learner_basic import BasicQLearner
+    from oracle.make_basic_train_goldens import frames_batch
+    dev = torch.device("cuda:0")
+    sd = qstep.init_state_basic(seed=4, num_frames=nf)
+    cfg = StepConfig()
+    cfg.TARGET_UPDATE_INTERVAL = 3
+    batches = [frames_batch(B, nf, seed=20 + i) for i in range(4)]
+    runs = []
+    for graph in (False, True):
+        model, target = _build(sd, dev, nf), _build(sd, dev, nf)
+        lr = BasicQLearner(model, target, cfg, batch_size=B, use_graph=graph)
+        losses = []
+        for b in batches:
+            losses.append(lr.step(b).item())
+        torch.cuda.synchronize()
+        assert (lr._graph is not None) == graph
+        runs.append((losses, lr.opt._step, int(lr.step_dev.item()),
+                     {k: v.detach().float().cpu() for k, v in model.state_dict().items()},
+                     {k: v.detach().float().cpu() for k, v in target.state_dict().items()}))
+    (l0, s0, d0, m0, t0), (l1, s1, d1, m1, t1) = runs
+    assert s0 == s1 == d0 == d1 == 4
+    for a, b in zip(l0, l1):
+        assert abs(a - b) <= 2e-3 * abs(a) + 1e-7, (l0, l1)
+    for k in m0:
+        if k.endswith("num_batches_tracked"):
+            assert torch.equal(m0[k], m1[k]), k
+        else:
+            assert (m0[k] - m1[k]).abs().max().item() <= 2e-3 * m0[k].abs().max().item() + 1e-6, k
+    for k in t0:                      # the target network was synchronised at step 3 in both runs
+        if not k.endswith("num_batches_tracked"):
+            assert (t0[k] - t1[k]).abs().max().item() <= 2e-3 * t0[k].abs().max().item() + 1e-6, k

@@ -207,9 +207,14 @@ class BasicQLearner:
 
     def __init__(self, model: HabitatDQNMultiAction, target_net: HabitatDQNMultiAction,
                  cfg: Optional[StepConfig] = None, batch_size: int = 16, *,
-                 optimizer: Optional[FusedAdam] = None, world_size: int = 1, process_group=None):
+                 optimizer: Optional[FusedAdam] = None, world_size: int = 1, process_group=None,
+                 use_graph: bool = False):
         """world_size > 1: one process per GPU over torch.distributed (`process_group`, default the world):
-        SyncBatchNorm statistics + a gradient all-reduce before Adam."""
+        SyncBatchNorm statistics + a gradient all-reduce before Adam.
+        use_graph: after one eager step the ~330 launches of a step are captured in a CUDA graph and replayed
+        (single process only; batches are copied into static device buffers first)."""
+        if use_graph and world_size > 1:
+            raise ValueError("BasicQLearner: use_graph is for a single process (the SyncBatchNorm exchanges are not captured)")
         if model.extra_capacity or target_net.extra_capacity:
             raise ValueError("BasicQLearner is for extra_capacity=False; use QLearner for the shipped architecture")
         self.cfg = cfg or StepConfig()
@@ -253,6 +258,14 @@ class BasicQLearner:
         self.y = torch.empty(batch_size, C, device=dev, dtype=torch.float32)
         self.sample_number = 0
         self.q_next_target = None
+        self.use_graph = use_graph
+        self._graph = None
+        self._eager_steps = 0
+        self._in = None                          # static input buffers (graph mode)
+        # Adam's step count lives on the device so that a captured step replays (as in learner.QLearner)
+        self.step_dev = torch.zeros(1, device=dev, dtype=torch.int32)
+        self.step_dev.fill_(self.opt._step)
+        self.scalars_dev = torch.zeros(2, device=dev, dtype=torch.float32)
 
     def _tensors(self) -> Dict[str, torch.Tensor]:
         d = {k: v.detach() for k, v in self.model.named_parameters()}
@@ -261,14 +274,51 @@ class BasicQLearner:
 
     @torch.no_grad()
     def step(self, batch) -> torch.Tensor:
-        before, after, act, rew, term, _gt, valid = [t.to(self.device, non_blocking=True) if torch.is_tensor(t) else t
-                                                     for t in batch]
-        B, cfg, plan = self.B, self.cfg, self.plan
-        if before.shape[0] != B or after.shape != before.shape:
+        batch = [t.to(self.device, non_blocking=True) if torch.is_tensor(t) else t for t in batch]
+        before, after = batch[0], batch[1]
+        if before.shape[0] != self.B or after.shape != before.shape:
             raise ValueError("bad shape")
         self.sample_number += 1
-        if self.sample_number % cfg.TARGET_UPDATE_INTERVAL == 0:
+        if self.sample_number % self.cfg.TARGET_UPDATE_INTERVAL == 0:
             self.target_net.load_state_dict(self.model.state_dict())          # :215-216
+        if not self.use_graph:
+            self._enqueue(batch)
+        else:
+            if self._in is None:
+                self._in = [t.clone() if torch.is_tensor(t) else t for t in batch]
+            else:
+                for dst, src in zip(self._in, batch):
+                    if torch.is_tensor(dst):
+                        if dst.shape != src.shape or dst.dtype != src.dtype:
+                            raise ValueError("BasicQLearner(use_graph=True): batches must keep their shape and dtype")
+                        dst.copy_(src, non_blocking=True)
+            # host-side state the captured work relies on: the target module's folded operands follow its
+            # parameters (a hard sync above changes them) -- re-derived here, outside the graph
+            self.target_net._basic_state()
+            if self._eager_steps < 1:
+                self._enqueue(self._in)
+                self._eager_steps += 1
+            else:
+                if self._graph is None:
+                    g = torch.cuda.CUDAGraph()
+                    torch.cuda.synchronize()
+                    with torch.cuda.graph(g):
+                        self._enqueue(self._in)
+                    self._graph = g
+                    self.opt._step -= 1           # capture does not execute: undo the host bookkeeping
+                self._graph.replay()
+                self.opt.note_graph_replay()
+        # parameters and running statistics changed behind torch's version counters: make the module's
+        # forward-only path re-derive its folded operands next time it is used
+        st = getattr(self.model, "_basic_eng", None)
+        if st is not None:
+            st["sig"] = None
+        return self.loss
+
+    def _enqueue(self, batch):
+        """every launch of one step (the body that is captured)"""
+        before, after, act, rew, term, _gt, valid = batch
+        B, cfg, plan = self.B, self.cfg, self.plan
         P = self._tensors()
         self.W.prepare(P)                                    # plain bf16 operands of the current weights
         C, A = plan.num_classes, plan.action_dim
@@ -315,13 +365,8 @@ class BasicQLearner:
         if self.world > 1:
             import torch.distributed as dist
             dist.all_reduce(self.opt.grad_arena, group=self.group)
-        self.opt.step(grads_in_arena=True, grad_scale=1.0 / self.world)
-        # parameters and running statistics changed behind torch's version counters: make the module's
-        # forward-only path re-derive its folded operands next time it is used
-        st = getattr(self.model, "_basic_eng", None)
-        if st is not None:
-            st["sig"] = None
-        return self.loss
+        self.opt.step(grads_in_arena=True, grad_scale=1.0 / self.world, step_dev=self.step_dev,
+                      scalars_dev=self.scalars_dev)
 
     # ------------------------------------------------------------------ snapshots (train_q_network.py:190-208,241-247)
     def checkpoint(self) -> dict:
@@ -344,3 +389,4 @@ class BasicQLearner:
         self.target_net.load_state_dict(self.model.state_dict())            # :208
         self.model.set_train()
         self.target_net.eval()
+        self.step_dev.fill_(self.opt._step)

@@ -192,6 +192,22 @@ class HabitatDQNMultiAction(nn.Module):
             if inp.shape[2] != 3 or inp.shape[3] != 224 or inp.shape[4] != 224:
                 raise Exception("bad shape")
             frames = inp.reshape(B * F, 3, 224, 224).float().contiguous()
+        st = self._basic_state()
+        dev = st["dev"]
+        n = B * F
+        ws = st["ws"].get(n)
+        if ws is None:
+            ws = st["ws"][n] = E.Workspace(st["plan"], n, dev, train=False)
+        with torch.no_grad():
+            ops.stem_pack(frames, ws.xp)
+            feat = E.forward_packed(st["plan"], st["W"], st["P"], ws, trunk_only=True)      # [n,7,7,512]
+            pooled = ops.avgpool_fwd(feat)                                                     # [n,512] fp32
+            q = ops.linear_fwd(pooled.view(B, F * 512), st["P"]["top.weight"], st["P"]["top.bias"], False)
+        return q.view(-1, self.num_classes, self.action_dim)
+
+    def _basic_state(self):
+        """folded bf16 operands of the `basic` architecture's forward-only path, re-derived when a parameter or
+        buffer changed (torch version counters)"""
         nt = self._named_tensors()
         dev = nt["top.weight"].device
         st = getattr(self, "_basic_eng", None)
@@ -204,16 +220,7 @@ class HabitatDQNMultiAction(nn.Module):
             st["P"] = {k: v.detach() for k, v in nt.items()}
             st["W"].prepare(st["P"])
             st["sig"] = sig
-        n = B * F
-        ws = st["ws"].get(n)
-        if ws is None:
-            ws = st["ws"][n] = E.Workspace(st["plan"], n, dev, train=False)
-        with torch.no_grad():
-            ops.stem_pack(frames, ws.xp)
-            feat = E.forward_packed(st["plan"], st["W"], st["P"], ws, trunk_only=True)      # [n,7,7,512]
-            pooled = ops.avgpool_fwd(feat)                                                     # [n,512] fp32
-            q = ops.linear_fwd(pooled.view(B, F * 512), st["P"]["top.weight"], st["P"]["top.bias"], False)
-        return q.view(-1, self.num_classes, self.action_dim)
+        return st
 
     # -- engine plumbing -------------------------------------------------------------------
     def _named_tensors(self) -> Dict[str, torch.Tensor]:
