@@ -754,8 +754,11 @@ def main():
             del learner
             dist.destroy_process_group()          # nothing of NCCL's is captured in the step graph: a clean teardown
         else:
-            # NCCL collectives captured in CUDA graphs keep the communicator busy at teardown
-            # (destroy_process_group blocks); everything is reported, so leave without the destructor.
+            # NCCL fallback only (VDQN_DDP=nccl, or no symmetric memory): NCCL collectives captured in CUDA graphs
+            # keep the communicator busy at teardown -- destroy_process_group() blocks even after the graphs are
+            # released, the learner deleted and the device synchronised (measured again in round 2: a 300 s
+            # hang at N = 2).  Everything is reported and flushed, so this path leaves without the destructor;
+            # the default NVLink-kernel path above tears down normally.
             os._exit(0)
 
 
