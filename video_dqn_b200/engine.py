@@ -513,16 +513,24 @@ def mlp_backward(plan: NetPlan, W: PreparedWeights, P, G, ws: Workspace, dq: tor
                  out_hi=dz2[0], out_lo=dz2[1], colsum=G["top.2.bias"])
     ops.mlp_gemm([(dz2[0], w2[0], 256), (dz2[1], w2[0], 256), (dz2[0], w2[1], 256)], B, 512, b_mn=True,
                  mask_bf16=z1[0], out_hi=dz1[0], out_lo=dz1[1], colsum=G["top.0.bias"])
-    # the three weight gradients and the head conv's dy are independent of each other: one launch
-    ops.mlp_gemm_grouped([
+    # the three weight gradients and the head conv's dy are independent of each other.  Only the head's dy is on
+    # the path to everything else: the weight gradients go to the second stream (one grouped launch), or, without
+    # it, into the same launch as the data gradient
+    p_dh = ops.mlp_problem([(dz1[0], w0[0], 512), (dz1[1], w0[0], 512), (dz1[0], w0[1], 512)], B, 1600 * F, b_mn=True,
+                           mask_bf16=hA, out_bf16=ws.dh.view(B, 1600 * F), colsum=G["features.8.bias"], colsum_mod=64)
+    p_dw = [
         ops.mlp_problem([(dz1[0], hA, B), (dz1[1], hA, B)], 512, 1600 * F, a_mn=True, b_mn=True,
                         out_f32=G["top.0.weight"], perm=(64, 25)),
-        ops.mlp_problem([(dz1[0], w0[0], 512), (dz1[1], w0[0], 512), (dz1[0], w0[1], 512)], B, 1600 * F, b_mn=True,
-                        mask_bf16=hA, out_bf16=ws.dh.view(B, 1600 * F), colsum=G["features.8.bias"], colsum_mod=64),
         ops.mlp_problem([(dz2[0], z1[0], B), (dz2[1], z1[0], B), (dz2[0], z1[1], B)], 256, 512, a_mn=True, b_mn=True,
                         out_f32=G["top.2.weight"]),
         ops.mlp_problem([(dqh, z2[0], B), (dql, z2[0], B), (dqh, z2[1], B)], nq, 256, a_mn=True, b_mn=True,
-                        out_f32=G["top.4.weight"])])
+                        out_f32=G["top.4.weight"])]
+    side = ws.side_stream() if hasattr(ws, "side_stream") and getattr(ws, "part", None) is not None else None
+    if side is not None and WGRAD_SIDE and ops.PROFILE is None:
+        side.run(lambda: ops.mlp_gemm_grouped(p_dw))
+        ops.mlp_gemm_grouped([p_dh])
+    else:
+        ops.mlp_gemm_grouped([p_dw[0], p_dh, p_dw[1], p_dw[2]])
 
 
 # Weight-gradient kernels on a second stream.  A conv's weight gradient and its data gradient both read the same
